@@ -1,0 +1,234 @@
+"""Drop-ins for the compression functions/methods of the reference's ``model/cogreasoner_chat.py``.
+
+Same names, argument meaning, return types and error behaviour as the reference:
+
+    select_additional_frames(cls_feature, long_memory, cluster_assignments, additional_frame_num)   :50-64
+    Videollama3MetaForCausalLM.select_events_based_on_summary(self, mm_features, total_image_num, timestamps)  :278-333
+    Videollama3MetaForCausalLM.compress_unimportant_events(self, mm_features, patch_num, minor_frame_indices)  :434-447
+    Videollama3MetaForCausalLM._get_compression_mask(self, pixel_values, batched_num_patches, grid_sizes,
+                                                     merge_sizes, modals, threshold=0.1, min_tokens=1,
+                                                     minor_frame_indices=None)                       :383-432
+    Videollama3MetaForCausalLM._compress_visual_tokens(self, compression_mask, mm_features, input_ids,
+                                                     attention_mask=None, position_ids=None, labels=None) :449-476
+
+``VisualStreamCompressionMixin`` carries the four methods; ``install(chat_module)`` rebinds them (and the
+two module-level functions) on an imported reference module, which is all a maintainer has to do
+(INTEGRATION.md).  The frozen LLM forwards inside ``select_events_based_on_summary`` (:302-323) are
+called exactly like the reference calls them -- the pretrained model is untouched.
+Inference only: the CUDA ops have no backward (``forward_train`` keeps the reference path).
+"""
+from __future__ import annotations
+
+import math
+from typing import List, Optional
+
+import torch
+
+from . import ops
+from .kmeans_with_time import kmeans_with_time_min_max
+
+__all__ = ["select_additional_frames", "create_visual_summary_prompt", "VisualStreamCompressionMixin", "install"]
+
+
+def _frames_bf16(x: torch.Tensor) -> torch.Tensor:
+    if not x.is_cuda:
+        raise RuntimeError("cogstream_b200: CPU tensor given; there is no CPU fallback")
+    if x.dtype != torch.bfloat16:
+        y = x.to(torch.bfloat16)
+        if not torch.equal(y.to(x.dtype), x):
+            raise NotImplementedError("cogstream_b200: features must be bf16 (or exactly bf16-representable)")
+        x = y
+    return x.contiguous()
+
+
+def select_additional_frames(cls_feature, long_memory, cluster_assignments, additional_frame_num):
+    """Per event the ``additional_frame_num`` member frames nearest (L2) to the event centroid, nearest first;
+    events with no more members than that keep all of them (ascending).  cogreasoner_chat.py:50-64.
+
+    One streaming pass over the features computes every frame's distance to its own centroid
+    (``csb_dist_to_assigned``), a warp per event then selects.  Ties pick the lowest frame index
+    (``torch.topk``'s tie order is implementation-defined).
+    """
+    x = _frames_bf16(cls_feature)
+    T = x.shape[0]
+    k = long_memory.shape[0]
+    cent = long_memory.reshape(k, -1).to(torch.float32).contiguous()
+    assign = cluster_assignments.to(torch.int64).contiguous()
+    dist = ops.dist_to_assigned(x.view(T, -1), cent, assign)
+    reps, counts, _ = ops.select_representatives(dist, assign, k, int(additional_frame_num))
+    counts_h = counts.tolist()
+    return [reps[i, : counts_h[i]] for i in range(k)]
+
+
+def create_visual_summary_prompt(P, timestamps, image_token="<image>"):
+    """Prompt of the per-event summary forward (text layout of cogreasoner_chat.py:93-119; it has to match
+    token for token, since the frozen LLM's pooled hidden state is the event embedding)."""
+    n = len(timestamps)
+    per_frame = image_token * (P // n)
+    frames = []
+    for t in range(n):
+        v = timestamps[t].item() if isinstance(timestamps[t], torch.Tensor) else float(timestamps[t])
+        frames.append(f"Time {v:.1f}s:{per_frame}" + ("," if t < n - 1 else ""))
+    instruction = (
+        "Concisely list the key points of the event shown in the timestamped images, adhering strictly and honestly to "
+        "the visual content. For each key point, identify relevant objects or actions, note any visible text, and specify "
+        "the approximate timestamp(s). Provide an overview focusing on these key timestamped points."
+    )
+    return (
+        "<|im_start|>system\n"
+        "You are a helpful assistant specializing in summarizing events from timestamped visual data.<|im_end|>\n"
+        "<|im_start|>user\n" + "".join(frames) + "\n" + instruction + "<|im_end|>\n" + "<|im_start|>assistant"
+    )
+
+
+class VisualStreamCompressionMixin:
+    """The four compression methods of ``Videollama3MetaForCausalLM`` on the B200 kernels."""
+
+    # hard-coded in the reference; exposed here with the reference values as defaults
+    csb_frames_per_event = 15  # :280
+    csb_min_events = 9  # :281
+    csb_n_representatives = 2  # :284
+    csb_relevance_threshold = 0.45  # :329
+
+    # ------------------------------------------------------------------------------------------
+    def select_events_based_on_summary(self, mm_features, total_image_num, timestamps):
+        feats = _frames_bf16(mm_features)
+        T = int(total_image_num)
+        P = feats.shape[0] // T
+        D = feats.shape[1]
+        features = feats.view(T, P, D)  # :279
+        k = math.ceil(T / self.csb_frames_per_event)  # :280
+        if k <= self.csb_min_events:  # :281-282
+            return []
+        dev = feats.device
+        ts = timestamps if isinstance(timestamps, torch.Tensor) else torch.tensor(timestamps)
+        ts = ts.to(dev)
+        _, _, assign, info = kmeans_with_time_min_max(features, ts, k, return_info=True)  # :283
+        order, ev_off = ops.event_order(assign, k)
+        dist = ops.dist_to_assigned_gram(info.gram, assign, ev_off, order, k)  # :284 (distances from the Gram matrix)
+        _, _, rep_flags = ops.select_representatives(dist, assign, k, self.csb_n_representatives)
+
+        # chronological per-event gather (:286-296): one row-gather into a packed buffer, events are views
+        packed = torch.empty_like(features)
+        ops.gather_rows(features.view(T, P * D), order, packed.view(T, P * D), n=T)
+        off_h = ev_off.tolist()
+        ts_sorted = ts[order.long()].tolist()
+        events_repr = []
+        for i in range(k):  # :294-316, the frozen LLM is called exactly like the reference does
+            lo, hi = off_h[i], off_h[i + 1]
+            ev = packed[lo:hi].reshape(-1, D)
+            prompt = create_visual_summary_prompt(ev.shape[0], ts_sorted[lo:hi])
+            inputs = self.tokenizer(prompt, return_tensors="pt")
+            input_ids = inputs["input_ids"].to(dev)
+            attention_mask = inputs["attention_mask"].to(dev)
+            inputs_embeds = self.get_model().embed_tokens(input_ids).clone()
+            image_selected = input_ids == self.config.image_token_index
+            inputs_embeds[image_selected] = inputs_embeds[image_selected] * 0.0 + ev.to(inputs_embeds.dtype)
+            out = self.get_model()(position_ids=None, attention_mask=attention_mask.view(1, -1),
+                                   inputs_embeds=inputs_embeds.reshape(1, -1, inputs_embeds.shape[-1]))
+            events_repr.append(torch.mean(out.last_hidden_state, dim=1))  # :317
+        events_repr = torch.cat(events_repr, dim=0)  # :318
+        inputs = self.tokenizer(self.current_question, padding=True, truncation=True, return_tensors="pt", max_length=128)
+        model_device = next(self.get_model().parameters()).device
+        inputs = {kk: v.to(model_device) for kk, v in inputs.items()}
+        question = torch.mean(self.get_model()(**inputs).last_hidden_state, dim=1)  # :319-323
+
+        ev_c = events_repr.to(dev).contiguous()
+        q_c = question[0].to(device=dev, dtype=ev_c.dtype).contiguous()
+        if ev_c.dtype not in (torch.bfloat16, torch.float32):
+            ev_c, q_c = ev_c.float(), q_c.float()
+        _, low = ops.cosine_flags(q_c, ev_c, self.csb_relevance_threshold)  # :325-330
+        assert low.shape[0] == k  # :327
+        _, minor_list, n_minor = ops.minor_frames(assign, low, rep_flags)  # :331-332
+        return minor_list[: int(n_minor.item())].tolist()  # :333
+
+    # ------------------------------------------------------------------------------------------
+    def compress_unimportant_events(self, mm_features, patch_num, minor_frame_indices):
+        total_patches, embedding_dim = mm_features.shape
+        if total_patches % patch_num != 0:  # :440-441
+            raise ValueError(f"total patches ({total_patches}) not divisible by patches per frame ({patch_num})")
+        out = _frames_bf16(mm_features).clone()  # :443
+        if len(minor_frame_indices):
+            frames = torch.tensor(list(minor_frame_indices), dtype=torch.int32, device=out.device)
+            ops.pool_frames_inplace(out, int(patch_num), frames)  # :444-446
+        return out if out.dtype == mm_features.dtype else out.to(mm_features.dtype)
+
+    # ------------------------------------------------------------------------------------------
+    def _get_compression_mask(self, pixel_values, batched_num_patches, grid_sizes, merge_sizes, modals,
+                              threshold: float = 0.1, min_tokens: int = 1, minor_frame_indices: Optional[List[int]] = None):
+        if not pixel_values.is_cuda:
+            raise RuntimeError("cogstream_b200: CPU tensor given; there is no CPU fallback")
+        dev = pixel_values.device
+        pix = pixel_values if pixel_values.dtype in (torch.bfloat16, torch.float32) else pixel_values.float()
+        pix = pix.contiguous()
+        grids = grid_sizes.tolist()  # the reference syncs here too (:394)
+        merges = merge_sizes.tolist()
+        n_patches = [int(v) for v in batched_num_patches.tolist()]
+        total_frames = sum(int(g[0]) for g in grids)
+        minor_flags = None
+        if minor_frame_indices is not None:
+            minor_flags = torch.zeros(max(total_frames, 1), dtype=torch.uint8, device=dev)
+            if len(minor_frame_indices):
+                idx = torch.tensor([i for i in minor_frame_indices if 0 <= i < total_frames], dtype=torch.int64, device=dev)
+                minor_flags[idx] = 1
+        C = pix.shape[1]
+        masks, row0, frame0 = [], 0, 0
+        for (t, h, w), m, npat, modal in zip(grids, merges, n_patches, modals):
+            rows = t * h * w
+            if modal == "image" or (modal == "video" and t == 1):  # :401-403
+                masks.append(torch.ones((npat,), dtype=torch.bool, device=dev))
+            elif modal == "video":  # :405-425
+                if minor_frame_indices is None:
+                    raise TypeError("argument of type 'NoneType' is not iterable")  # what :419 raises in the reference
+                P = (h // m) * (w // m)
+                W = (rows * C) // (t * P)
+                item = pix[row0: row0 + rows]
+                mk = ops.pixel_mask(item, t, P, W, threshold=threshold, min_tokens=min_tokens, minor_flags=minor_flags,
+                                    frame0=frame0)
+                masks.append(mk.view(torch.bool))
+            else:  # :427-430 pseudo image
+                masks.append(torch.ones((0,), dtype=torch.bool, device=dev))
+            row0 += rows
+            frame0 += t
+        return torch.cat(masks)  # :432
+
+    # ------------------------------------------------------------------------------------------
+    def _compress_visual_tokens(self, compression_mask, mm_features, input_ids, attention_mask=None, position_ids=None,
+                                labels=None):
+        feats = _frames_bf16(mm_features)
+        mask_u8 = compression_mask.contiguous().view(torch.uint8) if compression_mask.dtype == torch.bool else \
+            compression_mask.to(torch.uint8).contiguous()
+        N = feats.shape[0]
+        out, _, n_kept = ops.compact_tokens(feats, N, 1, mask_u8)  # :458
+        ids = input_ids.contiguous()
+        o_ids, o_am, o_lb, o_ps, n_out = ops.filter_ids(ids, self.config.image_token_index, mask_u8, attention_mask, labels,
+                                                        position_ids)  # :459-474
+        nk, no = int(n_kept.item()), int(n_out.item())
+        mm = out[:nk]
+        if mm.dtype != mm_features.dtype:
+            mm = mm.to(mm_features.dtype)
+
+        def _cut(t, like):
+            if t is None:
+                return None
+            t = t[:no]
+            return t if like is None or t.dtype == like.dtype else t.to(like.dtype)
+
+        return mm, o_ids[:no], _cut(o_am, attention_mask), _cut(o_ps, position_ids), _cut(o_lb, labels)
+
+
+_METHODS = ("select_events_based_on_summary", "compress_unimportant_events", "_get_compression_mask",
+            "_compress_visual_tokens")
+
+
+def install(chat_module, *, model_class_name: str = "Videollama3MetaForCausalLM"):
+    """Rebind the hot path of an imported reference ``model.cogreasoner_chat`` module onto the B200 kernels."""
+    chat_module.kmeans_with_time_min_max = kmeans_with_time_min_max  # imported at cogreasoner_chat.py:32
+    chat_module.select_additional_frames = select_additional_frames
+    chat_module.create_visual_summary_prompt = create_visual_summary_prompt
+    cls = getattr(chat_module, model_class_name)
+    for name in _METHODS:
+        setattr(cls, name, getattr(VisualStreamCompressionMixin, name))
+    for name in ("csb_frames_per_event", "csb_min_events", "csb_n_representatives", "csb_relevance_threshold"):
+        setattr(cls, name, getattr(VisualStreamCompressionMixin, name))
+    return cls

@@ -1,0 +1,432 @@
+// Gram matrix G = X X^T of the flattened bf16 frame vectors X [T, K], fp64 output.
+//
+//  impl 0: tcgen05 / TMA / TMEM kernel (sm_100a).  X is both operands (K-major, 128-byte swizzle),
+//          so products are exact bf16 x bf16 and no limb splitting is needed.  Output tiles are
+//          128 x 128; only the upper triangle is computed.  A CTA owns up to four tiles (512 TMEM
+//          columns) and one K range; the ranges are summed afterwards in fp64 in a fixed order.
+//  impl 1: CUDA-core kernel with the same tiling / partial layout (validation oracle on device).
+//
+// Partial layout: partial[kr][tile][128][128] fp32, tile = upper-triangular (bi <= bj) row-major id.
+#include <cuda.h>
+
+#include "csb_common.cuh"
+
+namespace csb {
+
+constexpr int kTile = 128;       // output tile edge
+constexpr int kChunk = 64;       // K elements per pipeline stage (128 bytes = one swizzle atom)
+constexpr int kMaxSlots = 5;     // distinct 128-row blocks resident per stage
+constexpr int kMaxMma = 4;       // output tiles (TMEM 128-column groups) per CTA
+constexpr int kStages = 2;
+constexpr int kBlockBytes = kTile * kChunk * 2;  // 16 KB
+
+struct GramUnit {
+  int n_slots;
+  int n_tiles;
+  int slot_block[kMaxSlots];  // row block loaded into each smem slot
+  int a_slot[kMaxMma];        // per tile: smem slot of the A (row) block
+  int b_slot[kMaxMma];        // per tile: smem slot of the B (column) block
+  int tile_id[kMaxMma];       // upper-triangular tile id (for the partial buffer)
+};
+
+struct GramPlan {
+  int nb;        // 128-row blocks
+  int n_tiles;   // nb*(nb+1)/2
+  int n_units;
+  int n_kr;      // K ranges
+  int n_chunks;  // ceil(K / 64)
+};
+
+static inline int tri_id(int bi, int bj, int nb) { return bi * nb - bi * (bi - 1) / 2 + (bj - bi); }
+
+// Pack the upper-triangular tiles into units of <= 4 tiles touching <= 5 distinct row blocks.
+static void plan_units(int nb, GramUnit* units, int* n_units) {
+  int n = 0;
+  GramUnit cur;
+  memset(&cur, 0, sizeof(cur));
+  auto flush = [&]() {
+    if (cur.n_tiles) {
+      if (units) units[n] = cur;
+      ++n;
+      memset(&cur, 0, sizeof(cur));
+    }
+  };
+  auto slot_of = [&](int blk, bool add) -> int {
+    for (int s = 0; s < cur.n_slots; ++s)
+      if (cur.slot_block[s] == blk) return s;
+    if (!add || cur.n_slots == kMaxSlots) return -1;
+    cur.slot_block[cur.n_slots] = blk;
+    return cur.n_slots++;
+  };
+  for (int bi = 0; bi < nb; ++bi) {
+    for (int bj = bi; bj < nb; ++bj) {
+      int need = (slot_of(bi, false) < 0) + ((bj != bi) && slot_of(bj, false) < 0);
+      if (cur.n_tiles == kMaxMma || cur.n_slots + need > kMaxSlots) flush();
+      const int sa = slot_of(bi, true), sb = slot_of(bj, true);
+      cur.a_slot[cur.n_tiles] = sa;
+      cur.b_slot[cur.n_tiles] = sb;
+      cur.tile_id[cur.n_tiles] = tri_id(bi, bj, nb);
+      ++cur.n_tiles;
+    }
+  }
+  flush();
+  *n_units = n;
+}
+
+static GramPlan make_plan(int64_t T, int64_t K) {
+  GramPlan p;
+  p.nb = (int)((T + kTile - 1) / kTile);
+  p.n_tiles = p.nb * (p.nb + 1) / 2;
+  plan_units(p.nb, nullptr, &p.n_units);
+  p.n_chunks = (int)((K + kChunk - 1) / kChunk);
+  int kr = kNumSMs / p.n_units;
+  if (kr < 1) kr = 1;
+  if (kr > p.n_chunks) kr = p.n_chunks;
+  p.n_kr = kr;
+  return p;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// impl 1: CUDA cores.  CTA = one 128x128 tile x one K range; 256 threads, 8x8 register tile.
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) gram_simt_kernel(const __nv_bfloat16* __restrict__ X, int T, int64_t K, int nb,
+                                                        int n_tiles, int n_kr, int n_chunks, float* __restrict__ partial) {
+  __shared__ float sA[32][kTile + 4];
+  __shared__ float sB[32][kTile + 4];
+  // decode tile id -> (bi, bj)
+  int tid = blockIdx.x, bi = 0;
+  while (tid >= nb - bi) { tid -= nb - bi; ++bi; }
+  const int bj = bi + tid;
+  const int kr = blockIdx.y;
+  const int c0 = (int)((int64_t)kr * n_chunks / n_kr), c1 = (int)((int64_t)(kr + 1) * n_chunks / n_kr);
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  float acc[8][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+  for (int64_t k0 = (int64_t)c0 * kChunk; k0 < (int64_t)c1 * kChunk && k0 < K; k0 += 32) {
+    for (int e = threadIdx.x; e < kTile * 32; e += 256) {
+      const int r = e >> 5, kk = e & 31;
+      const int64_t kcol = k0 + kk;
+      const int ra = bi * kTile + r, rb = bj * kTile + r;
+      sA[kk][r] = (ra < T && kcol < K) ? __bfloat162float(X[(int64_t)ra * K + kcol]) : 0.f;
+      sB[kk][r] = (rb < T && kcol < K) ? __bfloat162float(X[(int64_t)rb * K + kcol]) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll 4
+    for (int kk = 0; kk < 32; ++kk) {
+      float a[8], b[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) a[i] = sA[kk][ty * 8 + i];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) b[j] = sB[kk][tx * 8 + j];
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+  float* out = partial + ((int64_t)kr * n_tiles + blockIdx.x) * (kTile * kTile);
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) out[(ty * 8 + i) * kTile + tx * 8 + j] = acc[i][j];
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Sum the K ranges in fp64 (fixed order) and write both triangles of G.
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) gram_reduce_kernel(const float* __restrict__ partial, int T, int nb, int n_tiles,
+                                                          int n_kr, double* __restrict__ G) {
+  int tid = blockIdx.x, bi = 0;
+  while (tid >= nb - bi) { tid -= nb - bi; ++bi; }
+  const int bj = bi + tid;
+  const float* base = partial + (int64_t)blockIdx.x * (kTile * kTile);
+  const int64_t kr_stride = (int64_t)n_tiles * kTile * kTile;
+  for (int e = threadIdx.x + blockIdx.y * 256; e < kTile * kTile; e += 256 * gridDim.y) {
+    const int r = e >> 7, c = e & 127;
+    const int gi = bi * kTile + r, gj = bj * kTile + c;
+    if (gi >= T || gj >= T) continue;
+    double s = 0.0;
+    for (int kr = 0; kr < n_kr; ++kr) s += (double)base[(int64_t)kr * kr_stride + e];
+    G[(int64_t)gi * T + gj] = s;
+    if (bi != bj) G[(int64_t)gj * T + gi] = s;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// impl 0: tcgen05 + TMA.
+// ---------------------------------------------------------------------------------------------------
+namespace ptx {
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t}" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish() { asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+}  // namespace ptx
+
+// K-major, 128-byte-swizzled shared-memory operand descriptor (cute::UMMA::SmemDescriptor layout):
+// start>>4 [0,14) | LBO=1 [16,30) | SBO=1024>>4 [32,46) | version=1 [46,48) | layout SWIZZLE_128B=2 [61,64)
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
+  return (uint64_t)((smem_addr >> 4) & 0x3FFFu) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+// kind::f16 instruction descriptor: D=f32 [4,6)=1, A=bf16 [7,10)=1, B=bf16 [10,13)=1, K-major both,
+// N>>3 at [17,23), M>>4 at [24,29)
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+struct __align__(8) GramSmemCtl {
+  uint64_t full[kStages];
+  uint64_t empty[kStages];
+  uint64_t accum_done;
+  uint32_t tmem_base;
+};
+
+__global__ void __launch_bounds__(128, 1) gram_tc_kernel(const __grid_constant__ CUtensorMap xmap,
+                                                         const GramUnit* __restrict__ units, int n_tiles, int n_kr,
+                                                         int n_chunks, float* __restrict__ partial) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // stage buffers first (1024-byte aligned for SWIZZLE_128B), control block after
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  GramSmemCtl* ctl = reinterpret_cast<GramSmemCtl*>(smem + (size_t)kStages * kMaxSlots * kBlockBytes);
+  __shared__ GramUnit unit;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int kr = blockIdx.y;
+  const int c0 = (int)((int64_t)kr * n_chunks / n_kr), c1 = (int)((int64_t)(kr + 1) * n_chunks / n_kr);
+  const int nchunk = c1 - c0;
+
+  if (threadIdx.x == 0) unit = units[blockIdx.x];
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      ptx::mbar_init(&ctl->full[s], 1);
+      ptx::mbar_init(&ctl->empty[s], 1);
+    }
+    ptx::mbar_init(&ctl->accum_done, 1);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 2) {
+    ptx::tmem_alloc(&ctl->tmem_base, 512);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = ctl->tmem_base;
+  const int n_slots = unit.n_slots, n_ut = unit.n_tiles;
+
+  if (warp == 0 && lane == 0) {
+    // ===== TMA producer =====
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&xmap) : "memory");
+    for (int c = 0; c < nchunk; ++c) {
+      const int s = c % kStages;
+      const uint32_t ph = (uint32_t)(c / kStages) & 1u;
+      ptx::mbar_wait(&ctl->empty[s], ph ^ 1u);
+      ptx::mbar_expect_tx(&ctl->full[s], (uint32_t)(n_slots * kBlockBytes));
+      uint8_t* stage = smem + (size_t)s * kMaxSlots * kBlockBytes;
+      for (int q = 0; q < n_slots; ++q)
+        ptx::tma_load_2d(stage + (size_t)q * kBlockBytes, &xmap, &ctl->full[s], (c0 + c) * kChunk, unit.slot_block[q] * kTile);
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ===== MMA issuer =====
+    constexpr uint32_t idesc = make_idesc(128, 128);
+    for (int c = 0; c < nchunk; ++c) {
+      const int s = c % kStages;
+      const uint32_t ph = (uint32_t)(c / kStages) & 1u;
+      ptx::mbar_wait(&ctl->full[s], ph);
+      ptx::tc_fence_after();
+      const uint32_t stage = ptx::smem_u32(smem + (size_t)s * kMaxSlots * kBlockBytes);
+      for (int t = 0; t < n_ut; ++t) {
+        const uint32_t a_addr = stage + (uint32_t)unit.a_slot[t] * kBlockBytes;
+        const uint32_t b_addr = stage + (uint32_t)unit.b_slot[t] * kBlockBytes;
+#pragma unroll
+        for (int ks = 0; ks < kChunk / 16; ++ks) {
+          ptx::umma_bf16(tmem_base + (uint32_t)t * 128u, make_smem_desc(a_addr + ks * 32), make_smem_desc(b_addr + ks * 32),
+                         idesc, (c > 0 || ks > 0) ? 1u : 0u);
+        }
+      }
+      ptx::umma_commit(&ctl->empty[s]);  // frees the stage once these MMAs have read it
+    }
+    ptx::umma_commit(&ctl->accum_done);
+  }
+  __syncwarp();
+
+  // ===== epilogue: TMEM -> registers -> fp32 partial tiles (all 4 warps; warp w owns lanes 32w..32w+31) =====
+  ptx::mbar_wait(&ctl->accum_done, 0);
+  ptx::tc_fence_after();
+  for (int t = 0; t < n_ut; ++t) {
+    float* out = partial + ((int64_t)kr * n_tiles + unit.tile_id[t]) * (kTile * kTile) + (int64_t)(warp * 32 + lane) * kTile;
+#pragma unroll 1
+    for (int cb = 0; cb < 4; ++cb) {
+      uint32_t r[32];
+      ptx::tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(t * 128 + cb * 32), r);
+      ptx::tmem_ld_wait();
+      float4* o4 = reinterpret_cast<float4*>(out + cb * 32);
+#pragma unroll
+      for (int v = 0; v < 8; ++v)
+        o4[v] = make_float4(__uint_as_float(r[4 * v]), __uint_as_float(r[4 * v + 1]), __uint_as_float(r[4 * v + 2]),
+                            __uint_as_float(r[4 * v + 3]));
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 2) ptx::tmem_dealloc(tmem_base, 512);
+}
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode_fn() {
+  static PFN_encodeTiled fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_encodeTiled>(p);
+  }
+  return fn;
+}
+
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+constexpr size_t kGramSmemBytes = (size_t)kStages * kMaxSlots * kBlockBytes + sizeof(GramSmemCtl) + 1024;
+
+}  // namespace csb
+
+using namespace csb;
+
+extern "C" {
+
+size_t csb_gram_workspace_bytes(int64_t T, int64_t K) {
+  if (T <= 0 || K <= 0) return 0;
+  GramPlan p = make_plan(T, K);
+  // the CUDA-core path may use more K ranges than the tensor path; size for the larger
+  int kr_simt = (2 * kNumSMs + p.n_tiles - 1) / p.n_tiles;
+  if (kr_simt > p.n_chunks) kr_simt = p.n_chunks;
+  const int kr = kr_simt > p.n_kr ? kr_simt : p.n_kr;
+  return align_up((size_t)kr * p.n_tiles * kTile * kTile * sizeof(float), 256) + align_up(sizeof(GramUnit) * p.n_units, 256);
+}
+
+int csb_gram(const void* x, int64_t T, int64_t K, double* G, void* workspace, size_t workspace_bytes, int impl,
+             csb_stream_t stream) {
+  CSB_DEVICE_OR_RETURN();
+  CSB_REQUIRE(x && G && workspace && T > 0 && K > 0, "gram: null argument or empty shape");
+  CSB_REQUIRE(K % 8 == 0 && (reinterpret_cast<uintptr_t>(x) & 15u) == 0, "gram: K %% 8 != 0 or x not 16-byte aligned");
+  CSB_REQUIRE(T < (1 << 24), "gram: T too large");
+  if (workspace_bytes < csb_gram_workspace_bytes(T, K)) {
+    set_error("gram: workspace %zu < %zu", workspace_bytes, csb_gram_workspace_bytes(T, K));
+    return CSB_ERR_WORKSPACE;
+  }
+  GramPlan p = make_plan(T, K);
+  cudaStream_t s = as_stream(stream);
+  float* partial = reinterpret_cast<float*>(workspace);
+  int n_kr;
+  if (impl == 1) {
+    n_kr = (2 * kNumSMs + p.n_tiles - 1) / p.n_tiles;
+    if (n_kr > p.n_chunks) n_kr = p.n_chunks;
+    dim3 grid((unsigned)p.n_tiles, (unsigned)n_kr);
+    gram_simt_kernel<<<grid, 256, 0, s>>>((const __nv_bfloat16*)x, (int)T, K, p.nb, p.n_tiles, n_kr, p.n_chunks, partial);
+    int st = check_launch("gram_simt");
+    if (st) return st;
+  } else if (impl == 0) {
+    n_kr = p.n_kr;
+    int kr_simt = (2 * kNumSMs + p.n_tiles - 1) / p.n_tiles;
+    if (kr_simt > p.n_chunks) kr_simt = p.n_chunks;
+    const int kr_max = kr_simt > p.n_kr ? kr_simt : p.n_kr;
+    GramUnit* d_units = reinterpret_cast<GramUnit*>(reinterpret_cast<char*>(workspace) +
+                                                    align_up((size_t)kr_max * p.n_tiles * kTile * kTile * sizeof(float), 256));
+    // unit table: tiny, rebuilt per call from the shape (pageable host copy is stream ordered and synchronous w.r.t. the host buffer)
+    static thread_local GramUnit h_units_small[64];
+    GramUnit* h_units = h_units_small;
+    GramUnit* heap = nullptr;
+    if (p.n_units > 64) { heap = (GramUnit*)malloc(sizeof(GramUnit) * p.n_units); h_units = heap; }
+    int n_units = 0;
+    plan_units(p.nb, h_units, &n_units);
+    cudaError_t e = cudaMemcpyAsync(d_units, h_units, sizeof(GramUnit) * n_units, cudaMemcpyHostToDevice, s);
+    if (heap) { cudaStreamSynchronize(s); free(heap); }
+    if (e != cudaSuccess) { set_error("gram: unit table copy: %s", cudaGetErrorString(e)); return CSB_ERR_CUDA; }
+
+    PFN_encodeTiled enc = get_encode_fn();
+    if (!enc) { set_error("gram: cuTensorMapEncodeTiled unavailable"); return CSB_ERR_CUDA; }
+    CUtensorMap map;
+    cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)T};
+    cuuint64_t strides[1] = {(cuuint64_t)K * 2};
+    cuuint32_t box[2] = {(cuuint32_t)kChunk, (cuuint32_t)kTile};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(&map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(x), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("gram: cuTensorMapEncodeTiled failed (%d)", (int)r); return CSB_ERR_CUDA; }
+    e = cudaFuncSetAttribute(gram_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGramSmemBytes);
+    if (e != cudaSuccess) { set_error("gram: smem attr: %s", cudaGetErrorString(e)); return CSB_ERR_CUDA; }
+    dim3 grid((unsigned)p.n_units, (unsigned)n_kr);
+    gram_tc_kernel<<<grid, 128, kGramSmemBytes, s>>>(map, d_units, p.n_tiles, n_kr, p.n_chunks, partial);
+    int st = check_launch("gram_tc");
+    if (st) return st;
+  } else {
+    set_error("gram: unknown impl %d", impl);
+    return CSB_ERR_ARG;
+  }
+  dim3 rgrid((unsigned)p.n_tiles, 8);
+  gram_reduce_kernel<<<rgrid, 256, 0, s>>>(partial, (int)T, p.nb, p.n_tiles, n_kr, G);
+  return check_launch("gram_reduce");
+}
+
+}  // extern "C"

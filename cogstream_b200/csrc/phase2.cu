@@ -1,0 +1,578 @@
+// Selection / masking / compaction kernels (reference: model/cogreasoner_chat.py:50-64, :285-296,
+// :325-333, :383-432, :449-476).  Integer and byte work is exact; bf16 arithmetic reproduces ATen's
+// op-by-op rounding (fp32 math, one round-to-nearest-even per reference op).
+#include "csb_common.cuh"
+
+namespace csb {
+
+// ---- block-wide exclusive scan of per-thread counts (blockDim <= 1024) -----------------------------
+__device__ __forceinline__ int block_exclusive_scan(int v, int* warp_tot /* smem[32] */, int* total) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = (blockDim.x + 31) >> 5;
+  int inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    int n = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += n;
+  }
+  __syncthreads();
+  if (lane == 31) warp_tot[warp] = inc;
+  __syncthreads();
+  if (warp == 0) {
+    int w = lane < nwarp ? warp_tot[lane] : 0;
+    int winc = w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      int n = __shfl_up_sync(0xffffffffu, winc, o);
+      if (lane >= o) winc += n;
+    }
+    warp_tot[lane] = winc - w;  // exclusive warp offsets
+    if (lane == 31) *total = winc;
+  }
+  __syncthreads();
+  return warp_tot[warp] + inc - v;
+}
+
+// ------------------------------------------------------------------------------------------------
+// distance to own centroid from the Gram matrix, a warp per frame, two passes:
+//   rowsum_i = sum_{m in M} G_im                     (M = members of assign[i])
+//   dist_i^2 = G_ii - (2/n) rowsum_i + (1/n^2) sum_{m in M} rowsum_m
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) gram_rowsum_kernel(const double* __restrict__ G, int T, const int64_t* __restrict__ assign,
+                                                          const int32_t* __restrict__ offs, const int32_t* __restrict__ memb,
+                                                          double* __restrict__ rowsum) {
+  const int lane = threadIdx.x & 31;
+  const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (i >= T) return;
+  const int j = (int)assign[i];
+  const int beg = offs[j], end = offs[j + 1];
+  const double* gi = G + (int64_t)i * T;
+  double s = 0.0;
+  for (int m = beg + lane; m < end; m += 32) s += gi[memb[m]];
+  s = warp_sum(s);
+  if (lane == 0) rowsum[i] = s;
+}
+
+__global__ void __launch_bounds__(256) dist_gram_kernel(const double* __restrict__ G, int T, const int64_t* __restrict__ assign,
+                                                        const int32_t* __restrict__ offs, const int32_t* __restrict__ memb,
+                                                        const double* __restrict__ rowsum, float* __restrict__ dist) {
+  const int lane = threadIdx.x & 31;
+  const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (i >= T) return;
+  const int j = (int)assign[i];
+  const int beg = offs[j], end = offs[j + 1];
+  double q = 0.0;
+  for (int m = beg + lane; m < end; m += 32) q += rowsum[memb[m]];
+  q = warp_sum(q);
+  if (lane == 0) {
+    const double nn = (double)(end - beg);
+    const double d2 = G[(int64_t)i * T + i] - 2.0 * (rowsum[i] / nn) + q / (nn * nn);
+    dist[i] = (float)sqrt(d2 > 0.0 ? d2 : 0.0);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// representatives: a warp per event; n_rep rounds of "smallest (dist, index) greater than the last".
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) clear_flags_kernel(uint8_t* f, int64_t n) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) f[i] = 0;
+}
+
+__global__ void __launch_bounds__(256) select_reps_kernel(const float* __restrict__ dist, const int64_t* __restrict__ assign,
+                                                          int T, int k, int n_rep, int64_t* __restrict__ reps,
+                                                          int32_t* __restrict__ rep_counts, uint8_t* __restrict__ rep_flags) {
+  const int lane = threadIdx.x & 31;
+  const int j = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (j >= k) return;
+  int cnt = 0;
+  for (int i0 = 0; i0 < T; i0 += 32) {
+    const int i = i0 + lane;
+    cnt += __popc(__ballot_sync(0xffffffffu, i < T && (int)assign[i] == j));
+  }
+  int64_t* out = reps + (int64_t)j * n_rep;
+  if (cnt <= n_rep) {
+    // all members, ascending (torch.nonzero order), cogreasoner_chat.py:58-59
+    int pos = 0;
+    for (int i0 = 0; i0 < T; i0 += 32) {
+      const int i = i0 + lane;
+      const bool hit = i < T && (int)assign[i] == j;
+      const unsigned bal = __ballot_sync(0xffffffffu, hit);
+      if (hit) {
+        out[pos + __popc(bal & ((1u << lane) - 1u))] = i;
+        rep_flags[i] = 1;
+      }
+      pos += __popc(bal);
+    }
+    for (int r = cnt + lane; r < n_rep; r += 32) out[r] = -1;
+    if (lane == 0) rep_counts[j] = cnt;
+    return;
+  }
+  float last_d = -1.f;
+  int last_i = -1;
+  for (int r = 0; r < n_rep; ++r) {
+    float bd = __int_as_float(0x7f800000);
+    int bi = 0x7fffffff;
+    for (int i = lane; i < T; i += 32) {
+      if ((int)assign[i] != j) continue;
+      const float d = dist[i];
+      const bool after = d > last_d || (d == last_d && i > last_i);
+      if (after && (d < bd || (d == bd && i < bi))) { bd = d; bi = i; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float od = __shfl_xor_sync(0xffffffffu, bd, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (od < bd || (od == bd && oi < bi)) { bd = od; bi = oi; }
+    }
+    if (lane == 0) {
+      out[r] = bi == 0x7fffffff ? -1 : bi;
+      if (bi != 0x7fffffff) rep_flags[bi] = 1;
+    }
+    last_d = bd;
+    last_i = bi;
+  }
+  if (lane == 0) rep_counts[j] = n_rep;
+}
+
+// ------------------------------------------------------------------------------------------------
+// chronological per-event order: a warp per event sweeps the assignments (stable, ascending).
+// Single CTA (offsets need a scan over k counts).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) event_order_kernel(const int64_t* __restrict__ assign, int T, int k,
+                                                           int32_t* __restrict__ order, int32_t* __restrict__ offsets) {
+  extern __shared__ int s_cnt[];  // k + 1
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  for (int j = warp; j < k; j += nwarp) {
+    int cnt = 0;
+    for (int i0 = 0; i0 < T; i0 += 32) {
+      const int i = i0 + lane;
+      cnt += __popc(__ballot_sync(0xffffffffu, i < T && (int)assign[i] == j));
+    }
+    if (lane == 0) s_cnt[j] = cnt;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int run = 0;
+    for (int j = 0; j < k; ++j) {
+      const int c = s_cnt[j];
+      s_cnt[j] = run;
+      offsets[j] = run;
+      run += c;
+    }
+    s_cnt[k] = run;
+    offsets[k] = run;
+  }
+  __syncthreads();
+  for (int j = warp; j < k; j += nwarp) {
+    int pos = s_cnt[j];
+    for (int i0 = 0; i0 < T; i0 += 32) {
+      const int i = i0 + lane;
+      const bool hit = i < T && (int)assign[i] == j;
+      const unsigned bal = __ballot_sync(0xffffffffu, hit);
+      if (hit) order[pos + __popc(bal & ((1u << lane) - 1u))] = i;
+      pos += __popc(bal);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// (c) cosine flags: one CTA per event.  bf16: every ATen op of F.cosine_similarity rounds to bf16:
+//   n = bf16(sqrt(sum x^2)); xn = bf16(x / max(n, bf16(1e-8))); cos = bf16(sum bf16(qn * en)).
+// ------------------------------------------------------------------------------------------------
+template <bool BF16>
+__device__ __forceinline__ float ld_elem(const void* p, int i) {
+  if (BF16) return bf16_bits_to_float(reinterpret_cast<const uint16_t*>(p)[i]);
+  return reinterpret_cast<const float*>(p)[i];
+}
+template <bool BF16>
+__device__ __forceinline__ float rnd(float v) { return BF16 ? round_bf16(v) : v; }
+
+template <bool BF16>
+__global__ void __launch_bounds__(256) cosine_flags_kernel(const void* __restrict__ q, const void* __restrict__ ev, int Dl,
+                                                           float threshold, void* __restrict__ cos_out,
+                                                           uint8_t* __restrict__ low) {
+  __shared__ float red[32];
+  const int j = blockIdx.x;
+  const void* e = BF16 ? (const void*)(reinterpret_cast<const uint16_t*>(ev) + (int64_t)j * Dl)
+                       : (const void*)(reinterpret_cast<const float*>(ev) + (int64_t)j * Dl);
+  float sq = 0.f, se = 0.f;
+  for (int i = threadIdx.x; i < Dl; i += blockDim.x) {
+    const float a = ld_elem<BF16>(q, i), b = ld_elem<BF16>(e, i);
+    sq = fmaf(a, a, sq);
+    se = fmaf(b, b, se);
+  }
+  sq = block_sum<float>(sq, red);
+  se = block_sum<float>(se, red);
+  const float eps = rnd<BF16>(1e-8f);
+  const float qn = fmaxf(rnd<BF16>(__fsqrt_rn(sq)), eps);
+  const float en = fmaxf(rnd<BF16>(__fsqrt_rn(se)), eps);
+  float dot = 0.f;
+  for (int i = threadIdx.x; i < Dl; i += blockDim.x) {
+    const float a = rnd<BF16>(__fdiv_rn(ld_elem<BF16>(q, i), qn));
+    const float b = rnd<BF16>(__fdiv_rn(ld_elem<BF16>(e, i), en));
+    dot += rnd<BF16>(__fmul_rn(a, b));
+  }
+  dot = block_sum<float>(dot, red);
+  if (threadIdx.x == 0) {
+    const float c = rnd<BF16>(dot);
+    if (BF16) reinterpret_cast<uint16_t*>(cos_out)[j] = (uint16_t)float_to_bf16_bits(c);
+    else reinterpret_cast<float*>(cos_out)[j] = c;
+    low[j] = c < threshold ? 1 : 0;  // strict, threshold already rounded to the dtype (:329-330)
+  }
+}
+
+// minor frames: flags + ascending list (single CTA scan)
+__global__ void __launch_bounds__(1024) minor_frames_kernel(const int64_t* __restrict__ assign, const uint8_t* __restrict__ low,
+                                                            const uint8_t* __restrict__ rep, int T,
+                                                            uint8_t* __restrict__ flags, int32_t* __restrict__ list,
+                                                            int64_t* __restrict__ n_minor) {
+  __shared__ int wt[32];
+  __shared__ int total;
+  const int per = (T + blockDim.x - 1) / blockDim.x;
+  const int beg = threadIdx.x * per, end = min(T, beg + per);
+  int cnt = 0;
+  for (int i = beg; i < end; ++i) {
+    const uint8_t f = (low[assign[i]] && !rep[i]) ? 1 : 0;
+    flags[i] = f;
+    cnt += f;
+  }
+  int pos = block_exclusive_scan(cnt, wt, &total);
+  for (int i = beg; i < end; ++i)
+    if (flags[i]) list[pos++] = i;
+  if (threadIdx.x == 0) *n_minor = total;
+}
+
+// ------------------------------------------------------------------------------------------------
+// (d) pixel-difference mask.  A warp owns one (frame, token): W contiguous elements of the current and
+// the previous frame, 128-bit loads; the previous frame's copy is an L2 hit (frames are swept in order).
+// ------------------------------------------------------------------------------------------------
+template <bool BF16>
+__global__ void __launch_bounds__(256) pixel_diff_kernel(const void* __restrict__ pix, int t, int P, int W, float thr_cmp,
+                                                         float first_val, uint8_t* __restrict__ mask) {
+  const int lane = threadIdx.x & 31;
+  const int64_t tok = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (tok >= (int64_t)t * P) return;
+  if (tok < P) {  // first frame: torch.full_like(threshold + 1) > threshold  (:411-412)
+    if (lane == 0) mask[tok] = first_val > thr_cmp ? 1 : 0;
+    return;
+  }
+  float s = 0.f;
+  if (BF16) {
+    const uint16_t* cur = reinterpret_cast<const uint16_t*>(pix) + tok * W;
+    const uint16_t* prv = cur - (int64_t)P * W;
+    if ((W & 7) == 0) {
+      const uint4* c4 = reinterpret_cast<const uint4*>(cur);
+      const uint4* p4 = reinterpret_cast<const uint4*>(prv);
+      const int Wv = W >> 3;
+      for (int v = lane; v < Wv; v += 32) {
+        float a[8], b[8];
+        unpack8(ldg_stream(c4 + v), a);
+        unpack8(__ldg(p4 + v), b);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) s += fabsf(round_bf16(__fsub_rn(a[e], b[e])));
+      }
+    } else {
+      for (int v = lane; v < W; v += 32) s += fabsf(round_bf16(__fsub_rn(bf16_bits_to_float(cur[v]), bf16_bits_to_float(prv[v]))));
+    }
+  } else {
+    const float* cur = reinterpret_cast<const float*>(pix) + tok * W;
+    const float* prv = cur - (int64_t)P * W;
+    for (int v = lane; v < W; v += 32) s += fabsf(__fsub_rn(cur[v], prv[v]));
+  }
+  s = warp_sum(s);
+  if (lane == 0) {
+    // mean = sum / W (ATen CPU mean for reduced types: fp32 sum, div, one cast), then * 255, each op rounded
+    float m = rnd<BF16>(__fdiv_rn(s, (float)W));
+    m = rnd<BF16>(__fmul_rn(m, 255.f));
+    mask[tok] = m > thr_cmp ? 1 : 0;
+  }
+}
+
+// per-frame rules: min_tokens padding (:413-414) then the minor-frame override (:416-422). A warp per frame.
+__global__ void __launch_bounds__(256) mask_finalize_kernel(uint8_t* __restrict__ mask, int t, int P, int min_tokens,
+                                                            const uint8_t* __restrict__ minor_flags, int64_t frame0) {
+  const int lane = threadIdx.x & 31;
+  const int f = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (f >= t) return;
+  uint8_t* m = mask + (int64_t)f * P;
+  if (minor_flags && minor_flags[frame0 + f]) {
+    for (int p = lane; p < P; p += 32) m[p] = (p == 0) ? 1 : 0;
+    return;
+  }
+  int cnt = 0;
+  for (int p = lane; p < P; p += 32) cnt += m[p];
+  cnt = warp_sum(cnt);
+  if (cnt < min_tokens)
+    for (int p = lane; p < min_tokens && p < P; p += 32) m[p] = 1;
+}
+
+// ------------------------------------------------------------------------------------------------
+// compaction: scan (single CTA), gather kept rows, emit pooled rows for pooled frames.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) mask_scan_kernel(const uint8_t* __restrict__ mask, int64_t n, int32_t* __restrict__ pos,
+                                                         int32_t* __restrict__ kept_index, int64_t* __restrict__ n_kept) {
+  __shared__ int wt[32];
+  __shared__ int total;
+  const int64_t per = (n + blockDim.x - 1) / blockDim.x;
+  const int64_t beg = threadIdx.x * per, end = min(n, beg + per);
+  int cnt = 0;
+  for (int64_t i = beg; i < end; ++i) cnt += mask[i] ? 1 : 0;
+  int p = block_exclusive_scan(cnt, wt, &total);
+  for (int64_t i = beg; i < end; ++i) {
+    pos[i] = p;
+    if (mask[i]) kept_index[p++] = (int32_t)i;
+  }
+  if (threadIdx.x == 0) *n_kept = total;
+}
+
+__global__ void __launch_bounds__(256) pool_emit_kernel(const uint4* __restrict__ x, int P, int Dv,
+                                                        const uint8_t* __restrict__ pool_flags,
+                                                        const uint8_t* __restrict__ mask, const int32_t* __restrict__ pos,
+                                                        uint4* __restrict__ out) {
+  const int64_t t = blockIdx.x;
+  if (!pool_flags[t] || !mask[t * P]) return;
+  const uint4* xf = x + t * (int64_t)P * Dv;
+  uint4* dst = out + (int64_t)pos[t * P] * Dv;
+  for (int c = threadIdx.x; c < Dv; c += blockDim.x) {
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    int p = 0;
+    for (; p + 4 <= P; p += 4) {
+      uint4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) v[u] = ldg_stream(xf + (int64_t)(p + u) * Dv + c);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        float f[8];
+        unpack8(v[u], f);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[e] += f[e];
+      }
+    }
+    for (; p < P; ++p) {
+      float f[8];
+      unpack8(ldg_stream(xf + (int64_t)p * Dv + c), f);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[e] += f[e];
+    }
+    float m[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) m[e] = __fdiv_rn(acc[e], (float)P);
+    uint4 o;
+    o.x = float_to_bf16_bits(m[0]) | (float_to_bf16_bits(m[1]) << 16);
+    o.y = float_to_bf16_bits(m[2]) | (float_to_bf16_bits(m[3]) << 16);
+    o.z = float_to_bf16_bits(m[4]) | (float_to_bf16_bits(m[5]) << 16);
+    o.w = float_to_bf16_bits(m[6]) | (float_to_bf16_bits(m[7]) << 16);
+    dst[c] = o;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// input-id filtering (:459-474), single CTA.  keep[i] = !is_image[i] || mask[rank_of_image(i)].
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) filter_ids_kernel(const int64_t* __restrict__ ids, int64_t n, int64_t image_tok,
+                                                          const uint8_t* __restrict__ mask, int64_t n_mask,
+                                                          const int64_t* __restrict__ attn, const int64_t* __restrict__ labels,
+                                                          const int64_t* __restrict__ posids, int64_t* __restrict__ o_ids,
+                                                          int64_t* __restrict__ o_attn, int64_t* __restrict__ o_labels,
+                                                          int64_t* __restrict__ o_pos, int64_t* __restrict__ n_out,
+                                                          int32_t* __restrict__ seg_start /* ws [n] */) {
+  __shared__ int wt[32];
+  __shared__ int total;
+  const int64_t per = (n + blockDim.x - 1) / blockDim.x;
+  const int64_t beg = threadIdx.x * per, end = min(n, beg + per);
+  // pass 1: rank among image tokens
+  int cnt = 0;
+  for (int64_t i = beg; i < end; ++i) cnt += ids[i] == image_tok;
+  int irank = block_exclusive_scan(cnt, wt, &total);
+  // pass 2: kept count
+  int kept = 0, r = irank;
+  for (int64_t i = beg; i < end; ++i) {
+    bool keep = true;
+    if (ids[i] == image_tok) { keep = r < n_mask ? mask[r] != 0 : false; ++r; }
+    kept += keep;
+  }
+  int opos = block_exclusive_scan(kept, wt, &total);
+  const int out_total = total;
+  r = irank;
+  for (int64_t i = beg; i < end; ++i) {
+    bool keep = true;
+    if (ids[i] == image_tok) { keep = r < n_mask ? mask[r] != 0 : false; ++r; }
+    if (keep) {
+      o_ids[opos] = ids[i];
+      if (attn) o_attn[opos] = attn[i];
+      if (labels) o_labels[opos] = labels[i];
+      if (posids) seg_start[opos] = (opos == 0 || posids[i] == 0) ? opos : -1;
+      ++opos;
+    }
+  }
+  if (threadIdx.x == 0) *n_out = out_total;
+  if (!posids) return;
+  // position ids restart at every kept element whose old position id was 0 (:472-474): running max of starts
+  __syncthreads();
+  const int64_t oper = ((int64_t)out_total + blockDim.x - 1) / blockDim.x;
+  const int64_t ob = threadIdx.x * oper, oe = min((int64_t)out_total, ob + oper);
+  int last = -1;
+  for (int64_t i = ob; i < oe; ++i) last = max(last, seg_start[i]);
+  // inclusive max-scan across threads
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = (blockDim.x + 31) >> 5;
+  int inc = last;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    int v = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc = max(inc, v);
+  }
+  if (lane == 31) wt[warp] = inc;
+  __syncthreads();
+  if (warp == 0) {
+    int w = lane < nwarp ? wt[lane] : -1;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      int v = __shfl_up_sync(0xffffffffu, w, o);
+      if (lane >= o) w = max(w, v);
+    }
+    wt[lane] = w;
+  }
+  __syncthreads();
+  int carry = warp > 0 ? wt[warp - 1] : -1;
+  int prev = __shfl_up_sync(0xffffffffu, inc, 1);
+  if (lane > 0) carry = max(carry, prev);
+  for (int64_t i = ob; i < oe; ++i) {
+    carry = max(carry, seg_start[i]);
+    o_pos[i] = i - carry;
+  }
+}
+
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+}  // namespace csb
+
+using namespace csb;
+
+extern "C" {
+
+int csb_dist_to_assigned_gram(const double* G, int64_t T, int64_t k, const int64_t* assignments, const int32_t* offs,
+                              const int32_t* memb, float* dist, double* rowsum_ws, csb_stream_t stream) {
+  CSB_DEVICE_OR_RETURN();
+  CSB_REQUIRE(G && assignments && offs && memb && dist && rowsum_ws && T > 0 && k > 0, "dist_to_assigned_gram: null argument");
+  cudaStream_t s = as_stream(stream);
+  gram_rowsum_kernel<<<(unsigned)((T + 7) / 8), 256, 0, s>>>(G, (int)T, assignments, offs, memb, rowsum_ws);
+  dist_gram_kernel<<<(unsigned)((T + 7) / 8), 256, 0, s>>>(G, (int)T, assignments, offs, memb, rowsum_ws, dist);
+  return check_launch("dist_to_assigned_gram");
+}
+
+int csb_select_representatives(const float* dist, const int64_t* assignments, int64_t T, int64_t k, int64_t n_rep, int64_t* reps,
+                               int32_t* rep_counts, uint8_t* rep_flags, csb_stream_t stream) {
+  CSB_DEVICE_OR_RETURN();
+  CSB_REQUIRE(dist && assignments && reps && rep_counts && rep_flags && T > 0 && k > 0 && n_rep > 0, "select_representatives: null argument");
+  cudaStream_t s = as_stream(stream);
+  clear_flags_kernel<<<(unsigned)((T + 255) / 256), 256, 0, s>>>(rep_flags, T);
+  select_reps_kernel<<<(unsigned)((k + 7) / 8), 256, 0, s>>>(dist, assignments, (int)T, (int)k, (int)n_rep, reps, rep_counts, rep_flags);
+  return check_launch("select_representatives");
+}
+
+int csb_event_order(const int64_t* assignments, int64_t T, int64_t k, int32_t* order, int32_t* event_offsets, csb_stream_t stream) {
+  CSB_DEVICE_OR_RETURN();
+  CSB_REQUIRE(assignments && order && event_offsets && T > 0 && k > 0, "event_order: null argument");
+  CSB_REQUIRE(k <= 10000, "event_order: k too large");
+  event_order_kernel<<<1, 1024, sizeof(int) * (k + 1), as_stream(stream)>>>(assignments, (int)T, (int)k, order, event_offsets);
+  return check_launch("event_order");
+}
+
+int csb_cosine_flags(const void* question, const void* events, int64_t k, int64_t Dl, int32_t dtype, double threshold,
+                     void* cos_out, uint8_t* low_flags, csb_stream_t stream) {
+  CSB_DEVICE_OR_RETURN();
+  CSB_REQUIRE(question && events && cos_out && low_flags && k > 0 && Dl > 0, "cosine_flags: null argument");
+  cudaStream_t s = as_stream(stream);
+  if (dtype == CSB_BF16) {
+    // `tensor_bf16 < python_float` compares against the scalar rounded to bf16
+    const float thr = __bfloat162float(__float2bfloat16_rn((float)threshold));
+    cosine_flags_kernel<true><<<(unsigned)k, 256, 0, s>>>(question, events, (int)Dl, thr, cos_out, low_flags);
+  } else if (dtype == CSB_F32) {
+    cosine_flags_kernel<false><<<(unsigned)k, 256, 0, s>>>(question, events, (int)Dl, (float)threshold, cos_out, low_flags);
+  } else {
+    set_error("cosine_flags: dtype must be bf16 or f32");
+    return CSB_ERR_UNSUPPORTED;
+  }
+  return check_launch("cosine_flags");
+}
+
+int csb_minor_frames(const int64_t* assignments, const uint8_t* low_flags, const uint8_t* rep_flags, int64_t T,
+                     uint8_t* minor_flags, int32_t* minor_list, int64_t* n_minor, csb_stream_t stream) {
+  CSB_DEVICE_OR_RETURN();
+  CSB_REQUIRE(assignments && low_flags && rep_flags && minor_flags && minor_list && n_minor && T > 0, "minor_frames: null argument");
+  minor_frames_kernel<<<1, 1024, 0, as_stream(stream)>>>(assignments, low_flags, rep_flags, (int)T, minor_flags, minor_list, n_minor);
+  return check_launch("minor_frames");
+}
+
+int csb_pixel_mask(const void* pixels, int64_t t, int64_t P, int64_t W, int32_t dtype, double threshold, int64_t min_tokens,
+                   const uint8_t* minor_flags, int64_t frame0, uint8_t* mask, csb_stream_t stream) {
+  CSB_DEVICE_OR_RETURN();
+  CSB_REQUIRE(pixels && mask && t > 0 && P > 0 && W > 0, "pixel_mask: null argument or empty shape");
+  CSB_REQUIRE(W < (1ll << 30) && P < (1ll << 30) && t < (1ll << 30), "pixel_mask: shape too large");
+  cudaStream_t s = as_stream(stream);
+  const int64_t ntok = t * P;
+  const unsigned blocks = (unsigned)((ntok + 7) / 8);
+  if (dtype == CSB_BF16) {
+    CSB_REQUIRE((W % 8 != 0) || (reinterpret_cast<uintptr_t>(pixels) & 15u) == 0, "pixel_mask: pixels not 16-byte aligned");
+    const float thr = __bfloat162float(__float2bfloat16_rn((float)threshold));
+    const float first = __bfloat162float(__float2bfloat16_rn((float)(threshold + 1.0)));
+    pixel_diff_kernel<true><<<blocks, 256, 0, s>>>(pixels, (int)t, (int)P, (int)W, thr, first, mask);
+  } else if (dtype == CSB_F32) {
+    pixel_diff_kernel<false><<<blocks, 256, 0, s>>>(pixels, (int)t, (int)P, (int)W, (float)threshold, (float)(threshold + 1.0), mask);
+  } else {
+    set_error("pixel_mask: dtype must be bf16 or f32");
+    return CSB_ERR_UNSUPPORTED;
+  }
+  int st = check_launch("pixel_diff");
+  if (st) return st;
+  mask_finalize_kernel<<<(unsigned)((t + 7) / 8), 256, 0, s>>>(mask, (int)t, (int)P, (int)min_tokens, minor_flags, frame0);
+  return check_launch("mask_finalize");
+}
+
+size_t csb_compact_workspace_bytes(int64_t n_tokens, int64_t n_ids) {
+  const int64_t n = n_tokens > n_ids ? n_tokens : n_ids;
+  return align_up(sizeof(int32_t) * (size_t)(n > 0 ? n : 1), 256);
+}
+
+int csb_compact_tokens(const void* x, int64_t T, int64_t P, int64_t D, const uint8_t* mask, const uint8_t* pool_flags, void* out,
+                       int32_t* kept_index, int64_t* n_kept, void* workspace, size_t workspace_bytes, csb_stream_t stream) {
+  CSB_DEVICE_OR_RETURN();
+  CSB_REQUIRE(x && mask && out && kept_index && n_kept && workspace && T > 0 && P > 0 && D > 0, "compact_tokens: null argument");
+  CSB_REQUIRE(D % 8 == 0, "compact_tokens: D %% 8 != 0");
+  const int64_t n = T * P;
+  CSB_REQUIRE(n < (1ll << 31), "compact_tokens: too many tokens");
+  if (workspace_bytes < csb_compact_workspace_bytes(n, 0)) { set_error("compact_tokens: workspace too small"); return CSB_ERR_WORKSPACE; }
+  cudaStream_t s = as_stream(stream);
+  int32_t* pos = reinterpret_cast<int32_t*>(workspace);
+  mask_scan_kernel<<<1, 1024, 0, s>>>(mask, n, pos, kept_index, n_kept);
+  int st = check_launch("mask_scan");
+  if (st) return st;
+  st = csb_gather_rows(x, D * 2, kept_index, 0, n_kept, n, out, stream);
+  if (st) return st;
+  if (pool_flags) {
+    const int Dv = (int)(D / 8);
+    const int threads = Dv >= 256 ? 256 : ((Dv + 31) / 32) * 32;
+    pool_emit_kernel<<<(unsigned)T, threads, 0, s>>>((const uint4*)x, (int)P, Dv, pool_flags, mask, pos, (uint4*)out);
+    st = check_launch("pool_emit");
+  }
+  return st;
+}
+
+int csb_filter_ids(const int64_t* input_ids, int64_t n_ids, int64_t image_token_index, const uint8_t* mask, int64_t n_mask,
+                   const int64_t* attention_mask, const int64_t* labels, const int64_t* position_ids, int64_t* out_ids,
+                   int64_t* out_attention_mask, int64_t* out_labels, int64_t* out_position_ids, int64_t* n_out, void* workspace,
+                   size_t workspace_bytes, csb_stream_t stream) {
+  CSB_DEVICE_OR_RETURN();
+  CSB_REQUIRE(input_ids && mask && out_ids && n_out && n_ids > 0, "filter_ids: null argument");
+  CSB_REQUIRE(!attention_mask || out_attention_mask, "filter_ids: attention_mask given without output");
+  CSB_REQUIRE(!labels || out_labels, "filter_ids: labels given without output");
+  CSB_REQUIRE(!position_ids || (out_position_ids && workspace), "filter_ids: position_ids given without output/workspace");
+  CSB_REQUIRE(n_ids < (1ll << 31), "filter_ids: too many ids");
+  if (position_ids && workspace_bytes < csb_compact_workspace_bytes(0, n_ids)) { set_error("filter_ids: workspace too small"); return CSB_ERR_WORKSPACE; }
+  filter_ids_kernel<<<1, 1024, 0, as_stream(stream)>>>(input_ids, n_ids, image_token_index, mask, n_mask, attention_mask, labels,
+                                                       position_ids, out_ids, out_attention_mask, out_labels, out_position_ids,
+                                                       n_out, reinterpret_cast<int32_t*>(workspace));
+  return check_launch("filter_ids");
+}
+
+}  // extern "C"

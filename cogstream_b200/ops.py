@@ -1,0 +1,344 @@
+"""Thin tensor-level wrappers over the C ABI (``include/cogstream_b200.h``).
+
+PyTorch is plumbing here: it owns device memory and the current CUDA stream; every op passes
+``data_ptr()``, sizes and the raw ``cudaStream_t`` to the shared library.  CUDA tensors only --
+a CPU tensor, a missing library or a non-sm_100 device raises (no fallback of any kind).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import CSB_BF16, CSB_F32, CSB_F64, KMeansParams, STATUS_WORDS, check
+
+_TS_DTYPE = {torch.float32: CSB_F32, torch.float64: CSB_F64}
+_EL_DTYPE = {torch.float32: CSB_F32, torch.bfloat16: CSB_BF16}
+
+
+def _stream(t: torch.Tensor) -> int:
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+def _need(t: torch.Tensor, name: str, dtype=None, dims: Optional[int] = None) -> torch.Tensor:
+    if not isinstance(t, torch.Tensor):
+        raise TypeError(f"{name}: expected a torch.Tensor, got {type(t).__name__}")
+    if not t.is_cuda:
+        raise RuntimeError(f"{name}: CPU tensor given; cogstream_b200 runs on sm_100a CUDA devices only (no CPU fallback)")
+    if dtype is not None and t.dtype != dtype:
+        raise TypeError(f"{name}: expected dtype {dtype}, got {t.dtype}")
+    if dims is not None and t.dim() != dims:
+        raise ValueError(f"{name}: expected {dims} dims, got shape {tuple(t.shape)}")
+    if not t.is_contiguous():
+        raise ValueError(f"{name}: tensor must be contiguous")
+    return t
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+class _on_device:
+    """Make the tensor's device current for the duration of a call (cheap when it already is)."""
+
+    def __init__(self, t: torch.Tensor):
+        self.idx = t.device.index if t.device.index is not None else torch.cuda.current_device()
+        self.prev = None
+
+    def __enter__(self):
+        cur = torch.cuda.current_device()
+        if cur != self.idx:
+            self.prev = cur
+            torch.cuda.set_device(self.idx)
+
+    def __exit__(self, *exc):
+        if self.prev is not None:
+            torch.cuda.set_device(self.prev)
+
+
+def check_device() -> None:
+    check(_lib.load().csb_check_device(), "check_device")
+
+
+# --------------------------------------------------------------------------------------------- (a)
+def pool_norm(x: torch.Tensor, *, want_bf16=True, want_f32=False, want_sqnorm=True):
+    """x [T,P,D] bf16 -> (pooled_bf16 [T,D] | None, pooled_f32 [T,D] | None, sqnorm [T] fp32 | None)."""
+    _need(x, "x", torch.bfloat16, 3)
+    T, P, D = x.shape
+    pb = torch.empty(T, D, dtype=torch.bfloat16, device=x.device) if want_bf16 else None
+    pf = torch.empty(T, D, dtype=torch.float32, device=x.device) if want_f32 else None
+    sq = torch.empty(T, dtype=torch.float32, device=x.device) if want_sqnorm else None
+    with _on_device(x):
+        check(_lib.load().csb_pool_norm(x.data_ptr(), T, P, D, _ptr(pb), _ptr(pf), _ptr(sq), _stream(x)), "pool_norm")
+    return pb, pf, sq
+
+
+# --------------------------------------------------------------------------------------------- (b)
+def gram_workspace_bytes(T: int, K: int) -> int:
+    return int(_lib.load().csb_gram_workspace_bytes(T, K))
+
+
+def gram(x: torch.Tensor, *, impl: int = 0, out: Optional[torch.Tensor] = None,
+         workspace: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """x [T,K] bf16 -> G [T,T] fp64 (G = x x^T, fp32 tensor-core partials summed in fp64)."""
+    _need(x, "x", torch.bfloat16, 2)
+    T, K = x.shape
+    G = out if out is not None else torch.empty(T, T, dtype=torch.float64, device=x.device)
+    _need(G, "out", torch.float64, 2)
+    need = gram_workspace_bytes(T, K)
+    ws = workspace if workspace is not None and workspace.numel() * workspace.element_size() >= need else \
+        torch.empty(need, dtype=torch.uint8, device=x.device)
+    with _on_device(x):
+        check(_lib.load().csb_gram(x.data_ptr(), T, K, G.data_ptr(), ws.data_ptr(), ws.numel() * ws.element_size(), impl,
+                                   _stream(x)), "gram")
+    return G
+
+
+def kmeans_workspace_bytes(T: int, k: int) -> int:
+    return int(_lib.load().csb_kmeans_workspace_bytes(T, k))
+
+
+class KMeansBuffers:
+    """Caller-owned outputs + workspace of one csb_kmeans_solve call."""
+
+    def __init__(self, T: int, k: int, ts_dtype: torch.dtype, device):
+        self.T, self.k = T, k
+        self.assignments = torch.empty(T, dtype=torch.int64, device=device)
+        self.centroid_times = torch.empty(k, dtype=ts_dtype, device=device)
+        self.member_offsets = torch.empty(k + 1, dtype=torch.int32, device=device)
+        self.members = torch.empty(T + k, dtype=torch.int32, device=device)
+        self.init_indices = torch.empty(k, dtype=torch.int64, device=device)
+        self.status = torch.zeros(STATUS_WORDS, dtype=torch.int32, device=device)
+        self.workspace = torch.empty(kmeans_workspace_bytes(T, k), dtype=torch.uint8, device=device)
+
+
+def kmeans_solve(G: torch.Tensor, timestamps: torch.Tensor, buf: KMeansBuffers, *, n_init_given: int,
+                 exp_noise: Optional[torch.Tensor], reseed_pool: Optional[torch.Tensor], alpha: float = 2.0,
+                 max_iteration: int = 30, tol: float = 1e-4) -> None:
+    """k-means++ + Lloyd on the Gram matrix.  ``buf.init_indices[:n_init_given]`` must be filled."""
+    _need(G, "G", torch.float64, 2)
+    _need(timestamps, "timestamps", None, 1)
+    if timestamps.dtype not in _TS_DTYPE:
+        raise TypeError(f"timestamps must be float32 or float64, got {timestamps.dtype}")
+    T, k = buf.T, buf.k
+    if G.shape != (T, T) or timestamps.shape[0] != T:
+        raise ValueError("kmeans_solve: shape mismatch")
+    if exp_noise is not None:
+        _need(exp_noise, "exp_noise", torch.float32, 2)
+        if exp_noise.shape != (k - 1, T):
+            raise ValueError(f"exp_noise must be [k-1, T] = [{k - 1}, {T}], got {tuple(exp_noise.shape)}")
+    n_pool = 0
+    if reseed_pool is not None:
+        _need(reseed_pool, "reseed_pool", torch.int64, 1)
+        n_pool = reseed_pool.numel()
+    p = KMeansParams(T, k, _TS_DTYPE[timestamps.dtype], int(max_iteration), float(alpha), float(tol), int(n_init_given), n_pool)
+    with _on_device(G):
+        check(_lib.load().csb_kmeans_solve(
+            G.data_ptr(), timestamps.data_ptr(), C.byref(p), buf.init_indices.data_ptr(), _ptr(exp_noise), _ptr(reseed_pool),
+            buf.assignments.data_ptr(), buf.centroid_times.data_ptr(), buf.member_offsets.data_ptr(), buf.members.data_ptr(),
+            buf.status.data_ptr(), buf.workspace.data_ptr(), buf.workspace.numel(), _stream(G)), "kmeans_solve")
+
+
+def decode_status(status_host: torch.Tensor) -> dict:
+    """Decode a host copy of the int32[8] status block."""
+    s = status_host.cpu()
+    f = s.view(torch.float32)
+    return dict(iterations=int(s[_lib.ST_ITER]), converged=bool(s[_lib.ST_CONV]), n_reseed_used=int(s[_lib.ST_RESEED]),
+                degenerate_rounds=int(s[_lib.ST_DEGEN]), reseed_overflow=bool(s[_lib.ST_OVERFLOW]),
+                n_noise_used=int(s[_lib.ST_NOISE]), min_margin=float(f[_lib.ST_MARGIN]), last_shift=float(f[_lib.ST_SHIFT]))
+
+
+def centroid_update(x: torch.Tensor, member_offsets: torch.Tensor, members: torch.Tensor, k: int,
+                    out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """x [T,K] bf16 + centre CSR -> centroids [k,K] fp32."""
+    _need(x, "x", torch.bfloat16, 2)
+    _need(member_offsets, "member_offsets", torch.int32, 1)
+    _need(members, "members", torch.int32, 1)
+    T, K = x.shape
+    Cn = out if out is not None else torch.empty(k, K, dtype=torch.float32, device=x.device)
+    with _on_device(x):
+        check(_lib.load().csb_centroid_update(x.data_ptr(), T, K, member_offsets.data_ptr(), members.data_ptr(), k,
+                                              Cn.data_ptr(), _stream(x)), "centroid_update")
+    return Cn
+
+
+def dist_to_assigned(x: torch.Tensor, centroids: torch.Tensor, assignments: torch.Tensor) -> torch.Tensor:
+    _need(x, "x", torch.bfloat16, 2)
+    _need(centroids, "centroids", torch.float32, 2)
+    _need(assignments, "assignments", torch.int64, 1)
+    T, K = x.shape
+    dist = torch.empty(T, dtype=torch.float32, device=x.device)
+    with _on_device(x):
+        check(_lib.load().csb_dist_to_assigned(x.data_ptr(), T, K, centroids.data_ptr(), centroids.shape[0],
+                                               assignments.data_ptr(), dist.data_ptr(), _stream(x)), "dist_to_assigned")
+    return dist
+
+
+def dist_to_assigned_gram(G: torch.Tensor, assignments: torch.Tensor, event_offsets: torch.Tensor, order: torch.Tensor,
+                          k: int) -> torch.Tensor:
+    _need(G, "G", torch.float64, 2)
+    T = G.shape[0]
+    dist = torch.empty(T, dtype=torch.float32, device=G.device)
+    ws = torch.empty(T, dtype=torch.float64, device=G.device)
+    with _on_device(G):
+        check(_lib.load().csb_dist_to_assigned_gram(G.data_ptr(), T, k, assignments.data_ptr(), event_offsets.data_ptr(),
+                                                    order.data_ptr(), dist.data_ptr(), ws.data_ptr(), _stream(G)),
+              "dist_to_assigned_gram")
+    return dist
+
+
+def select_representatives(dist: torch.Tensor, assignments: torch.Tensor, k: int, n_rep: int):
+    """-> (reps [k,n_rep] int64 (-1 padded), rep_counts [k] int32, rep_flags [T] uint8)."""
+    _need(dist, "dist", torch.float32, 1)
+    _need(assignments, "assignments", torch.int64, 1)
+    T = dist.shape[0]
+    reps = torch.empty(k, n_rep, dtype=torch.int64, device=dist.device)
+    counts = torch.empty(k, dtype=torch.int32, device=dist.device)
+    flags = torch.empty(T, dtype=torch.uint8, device=dist.device)
+    with _on_device(dist):
+        check(_lib.load().csb_select_representatives(dist.data_ptr(), assignments.data_ptr(), T, k, n_rep, reps.data_ptr(),
+                                                     counts.data_ptr(), flags.data_ptr(), _stream(dist)),
+              "select_representatives")
+    return reps, counts, flags
+
+
+def event_order(assignments: torch.Tensor, k: int):
+    """-> (order [T] int32: frames sorted by (event, frame), event_offsets [k+1] int32)."""
+    _need(assignments, "assignments", torch.int64, 1)
+    T = assignments.shape[0]
+    order = torch.empty(T, dtype=torch.int32, device=assignments.device)
+    offs = torch.empty(k + 1, dtype=torch.int32, device=assignments.device)
+    with _on_device(assignments):
+        check(_lib.load().csb_event_order(assignments.data_ptr(), T, k, order.data_ptr(), offs.data_ptr(),
+                                          _stream(assignments)), "event_order")
+    return order, offs
+
+
+def gather_rows(src: torch.Tensor, index: torch.Tensor, out: torch.Tensor, *, n: Optional[int] = None,
+                n_dev: Optional[torch.Tensor] = None, n_max: Optional[int] = None) -> torch.Tensor:
+    """out[r] = src[index[r]] for r < n (host int) or r < n_dev[0] (device int64)."""
+    _need(src, "src", None, 2)
+    _need(index, "index", torch.int32, 1)
+    _need(out, "out", src.dtype, 2)
+    row_bytes = src.shape[1] * src.element_size()
+    if n_max is None:
+        n_max = n if n is not None else index.shape[0]
+    with _on_device(src):
+        check(_lib.load().csb_gather_rows(src.data_ptr(), row_bytes, index.data_ptr(), 0 if n is None else n, _ptr(n_dev),
+                                          n_max, out.data_ptr(), _stream(src)), "gather_rows")
+    return out
+
+
+# --------------------------------------------------------------------------------------------- (c)
+def cosine_flags(question: torch.Tensor, events: torch.Tensor, threshold: float = 0.45):
+    """question [Dl] / events [k,Dl] (bf16 or fp32) -> (cos [k] same dtype, low_flags [k] uint8)."""
+    _need(events, "events", None, 2)
+    _need(question, "question", events.dtype, 1)
+    if events.dtype not in _EL_DTYPE:
+        raise TypeError(f"cosine_flags: dtype must be bfloat16 or float32, got {events.dtype}")
+    k, Dl = events.shape
+    cos = torch.empty(k, dtype=events.dtype, device=events.device)
+    low = torch.empty(k, dtype=torch.uint8, device=events.device)
+    with _on_device(events):
+        check(_lib.load().csb_cosine_flags(question.data_ptr(), events.data_ptr(), k, Dl, _EL_DTYPE[events.dtype],
+                                           float(threshold), cos.data_ptr(), low.data_ptr(), _stream(events)), "cosine_flags")
+    return cos, low
+
+
+def minor_frames(assignments: torch.Tensor, low_flags: torch.Tensor, rep_flags: torch.Tensor):
+    """-> (minor_flags [T] uint8, minor_list [T] int32 (first n_minor valid, ascending), n_minor [1] int64)."""
+    T = assignments.shape[0]
+    dev = assignments.device
+    flags = torch.empty(T, dtype=torch.uint8, device=dev)
+    lst = torch.empty(T, dtype=torch.int32, device=dev)
+    n = torch.empty(1, dtype=torch.int64, device=dev)
+    with _on_device(assignments):
+        check(_lib.load().csb_minor_frames(assignments.data_ptr(), low_flags.data_ptr(), rep_flags.data_ptr(), T,
+                                           flags.data_ptr(), lst.data_ptr(), n.data_ptr(), _stream(assignments)), "minor_frames")
+    return flags, lst, n
+
+
+# --------------------------------------------------------------------------------------------- (d)
+def pixel_mask(pixels: torch.Tensor, t: int, P: int, W: int, *, threshold: float = 0.1, min_tokens: int = 1,
+               minor_flags: Optional[torch.Tensor] = None, frame0: int = 0, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """One video item: pixels (t*P*W elements, bf16 or fp32) -> mask [t*P] uint8."""
+    _need(pixels, "pixels")
+    if pixels.dtype not in _EL_DTYPE:
+        raise TypeError(f"pixel_mask: dtype must be bfloat16 or float32, got {pixels.dtype}")
+    if pixels.numel() != t * P * W:
+        raise ValueError("pixel_mask: pixel count does not match t*P*W")
+    mask = out if out is not None else torch.empty(t * P, dtype=torch.uint8, device=pixels.device)
+    with _on_device(pixels):
+        check(_lib.load().csb_pixel_mask(pixels.data_ptr(), t, P, W, _EL_DTYPE[pixels.dtype], float(threshold), int(min_tokens),
+                                         _ptr(minor_flags), int(frame0), mask.data_ptr(), _stream(pixels)), "pixel_mask")
+    return mask
+
+
+def pool_frames_inplace(x: torch.Tensor, P: int, frames: torch.Tensor, *, n: Optional[int] = None,
+                        n_dev: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """x [T*P, D] bf16 (a private clone): token 0 of every listed frame <- mean of the frame's tokens."""
+    _need(x, "x", torch.bfloat16, 2)
+    _need(frames, "frames", torch.int32, 1)
+    TP, D = x.shape
+    T = TP // P
+    with _on_device(x):
+        check(_lib.load().csb_pool_frames_inplace(x.data_ptr(), T, P, D, frames.data_ptr(),
+                                                  frames.shape[0] if n is None else n, _ptr(n_dev), _stream(x)),
+              "pool_frames_inplace")
+    return x
+
+
+def compact_workspace_bytes(n_tokens: int, n_ids: int) -> int:
+    return int(_lib.load().csb_compact_workspace_bytes(n_tokens, n_ids))
+
+
+def compact_tokens(x: torch.Tensor, T: int, P: int, mask: torch.Tensor, pool_flags: Optional[torch.Tensor] = None, *,
+                   out: Optional[torch.Tensor] = None, workspace: Optional[torch.Tensor] = None):
+    """x [T*P, D] bf16, mask [T*P] uint8 -> (out [T*P, D] (first n_kept rows valid), kept_index [T*P] int32, n_kept [1] int64)."""
+    _need(x, "x", torch.bfloat16, 2)
+    _need(mask, "mask", torch.uint8, 1)
+    D = x.shape[1]
+    n = T * P
+    dev = x.device
+    o = out if out is not None else torch.empty(n, D, dtype=torch.bfloat16, device=dev)
+    kept = torch.empty(n, dtype=torch.int32, device=dev)
+    n_kept = torch.empty(1, dtype=torch.int64, device=dev)
+    need = compact_workspace_bytes(n, 0)
+    ws = workspace if workspace is not None and workspace.numel() >= need else torch.empty(need, dtype=torch.uint8, device=dev)
+    with _on_device(x):
+        check(_lib.load().csb_compact_tokens(x.data_ptr(), T, P, D, mask.data_ptr(), _ptr(pool_flags), o.data_ptr(),
+                                             kept.data_ptr(), n_kept.data_ptr(), ws.data_ptr(), ws.numel(), _stream(x)),
+              "compact_tokens")
+    return o, kept, n_kept
+
+
+def filter_ids(input_ids: torch.Tensor, image_token_index: int, mask: torch.Tensor,
+               attention_mask: Optional[torch.Tensor] = None, labels: Optional[torch.Tensor] = None,
+               position_ids: Optional[torch.Tensor] = None):
+    """-> (out_ids, out_attention_mask, out_labels, out_position_ids, n_out [1] int64); outputs sized like the inputs."""
+    _need(input_ids, "input_ids", torch.int64, 1)
+    _need(mask, "mask", torch.uint8, 1)
+    n = input_ids.shape[0]
+    dev = input_ids.device
+
+    def _opt(t, name):
+        if t is None:
+            return None, None
+        if t.dtype != torch.int64:
+            t = t.to(torch.int64)
+        _need(t, name, torch.int64, 1)
+        return t, torch.empty_like(t)
+
+    am, o_am = _opt(attention_mask, "attention_mask")
+    lb, o_lb = _opt(labels, "labels")
+    ps, o_ps = _opt(position_ids, "position_ids")
+    o_ids = torch.empty_like(input_ids)
+    n_out = torch.empty(1, dtype=torch.int64, device=dev)
+    ws = torch.empty(compact_workspace_bytes(0, n), dtype=torch.uint8, device=dev)
+    with _on_device(input_ids):
+        check(_lib.load().csb_filter_ids(input_ids.data_ptr(), n, int(image_token_index), mask.data_ptr(), mask.shape[0],
+                                         _ptr(am), _ptr(lb), _ptr(ps), o_ids.data_ptr(), _ptr(o_am), _ptr(o_lb), _ptr(o_ps),
+                                         n_out.data_ptr(), ws.data_ptr(), ws.numel(), _stream(input_ids)), "filter_ids")
+    return o_ids, o_am, o_lb, o_ps, n_out

@@ -1,0 +1,222 @@
+"""Fused Visual Stream Compression pipeline: the same path as the drop-in methods, but enqueued
+back-to-back on one CUDA stream with pre-allocated buffers and no host round trip inside a phase.
+
+    phase 1  (before the frozen LLM)  cogreasoner_chat.py:279-301
+        Gram (tcgen05) -> k-means++ + Lloyd (one cooperative kernel) -> fp32 centroids ->
+        chronological event order -> representatives -> packed per-event token gather
+    -- frozen LLM forwards (:302-323), untouched: event / question embeddings come back --
+    phase 2                          cogreasoner_chat.py:325-333, :551-564
+        cosine flags -> minor frames -> pixel-difference mask (+ min_tokens, minor override) ->
+        scan + compaction (minor frames emitted as their pooled token) -> input-id filtering
+
+Independent streams shard across ranks (``shard_streams``); the only collective is one all-gather of
+the per-stream stats rows (``gather_stats``), as in SURVEY.md section 8(e).
+"""
+from __future__ import annotations
+
+import math
+import random
+from dataclasses import dataclass
+from typing import Dict, List, Optional, Sequence
+
+import torch
+
+from . import ops
+
+STATS_FIELDS = ("T", "k", "iterations", "n_reseed", "n_minor", "n_kept", "n_ids_out", "converged")
+
+
+@dataclass
+class StreamConfig:
+    """Hot-path constants, reference values as defaults."""
+
+    frames_per_event: int = 15  # cogreasoner_chat.py:280
+    min_events: int = 9  # :281
+    n_representatives: int = 2  # :284
+    relevance_threshold: float = 0.45  # :329
+    pixel_threshold: float = 0.1  # :390
+    min_tokens: int = 1  # :391
+    alpha: float = 2.0  # kmeans_with_time.py:4
+    max_iteration: int = 30
+    tol: float = 1e-4
+    cluster_num: Optional[int] = None  # override k = ceil(T / frames_per_event) and its gate
+    gram_impl: int = 0
+    reseed_pool: int = 64
+    compute_centroids: bool = True
+    gather_events: bool = True
+
+    def clusters_for(self, T: int) -> int:
+        if self.cluster_num is not None:
+            return self.cluster_num
+        return math.ceil(T / self.frames_per_event)
+
+    def gate_open(self, T: int) -> bool:
+        k = self.clusters_for(T)
+        if T <= k:
+            return False
+        return self.cluster_num is not None or k > self.min_events
+
+
+class StreamCompressor:
+    """Buffers + launch sequence for streams of one shape (T frames, P tokens, D channels, W pixel width)."""
+
+    def __init__(self, T: int, P: int, D: int, W: int, n_ids: int, *, device, cfg: Optional[StreamConfig] = None,
+                 ts_dtype=torch.float64, embed_dim: int = 3584, embed_dtype=torch.bfloat16, image_token_index: int = 151665):
+        self.cfg = cfg or StreamConfig()
+        self.T, self.P, self.D, self.W, self.n_ids = T, P, D, W, n_ids
+        self.K = P * D
+        self.k = self.cfg.clusters_for(T)
+        self.device = torch.device(device)
+        self.image_token_index = image_token_index
+        self.gate = self.cfg.gate_open(T)
+        dev = self.device
+        ops.check_device()
+        k = self.k
+        if self.gate:
+            self.G = torch.empty(T, T, dtype=torch.float64, device=dev)
+            self.gram_ws = torch.empty(ops.gram_workspace_bytes(T, self.K), dtype=torch.uint8, device=dev)
+            self.km = ops.KMeansBuffers(T, k, ts_dtype, dev)
+            self.noise = torch.empty(max(k - 1, 1), T, dtype=torch.float32, device=dev)
+            self.pool = torch.zeros(self.cfg.reseed_pool, dtype=torch.int64, device=dev)
+            self.centroids = torch.empty(k, self.K, dtype=torch.float32, device=dev) if self.cfg.compute_centroids else None
+            self.packed = torch.empty(T, self.K, dtype=torch.bfloat16, device=dev) if self.cfg.gather_events else None
+        self.minor_flags = torch.zeros(T, dtype=torch.uint8, device=dev)
+        self.n_minor = torch.zeros(1, dtype=torch.int64, device=dev)
+        self.mask = torch.empty(T * P, dtype=torch.uint8, device=dev)
+        self.out = torch.empty(T * P, D, dtype=torch.bfloat16, device=dev)
+        self.compact_ws = torch.empty(ops.compact_workspace_bytes(T * P, n_ids), dtype=torch.uint8, device=dev)
+        self.order = self.ev_off = self.dist = self.reps = self.rep_counts = self.rep_flags = None
+        self.cos = self.low = self.minor_list = None
+        self.kept_index = self.n_kept = None
+        self.out_ids = self.out_attention = self.n_ids_out = None
+
+    # ------------------------------------------------------------------------------------------
+    def phase1(self, features: torch.Tensor, timestamps: torch.Tensor, *, init_indices: Optional[torch.Tensor] = None,
+               first_index: Optional[int] = None, exp_noise: Optional[torch.Tensor] = None,
+               reseed_pool: Optional[torch.Tensor] = None) -> None:
+        """features [T*P, D] bf16, timestamps [T] on the device.  Enqueues everything; returns at once."""
+        if not self.gate:
+            return
+        T, k = self.T, self.k
+        x2 = features.view(T, self.K)
+        ops.gram(x2, impl=self.cfg.gram_impl, out=self.G, workspace=self.gram_ws)
+        if init_indices is not None:
+            self.km.init_indices.copy_(init_indices, non_blocking=True)
+            n_given, noise = k, None
+        else:
+            first = random.randint(0, T - 1) if first_index is None else first_index  # kmeans_with_time.py:41
+            self.km.init_indices[:1].fill_(first)
+            n_given = 1
+            if exp_noise is not None:
+                noise = exp_noise
+            else:
+                noise = self.noise[: k - 1]
+                if k > 1:
+                    noise.exponential_(1)  # one batched draw (the drop-in function draws per round like ATen does)
+        pool = reseed_pool
+        if pool is None:
+            pool = self.pool
+            pool.random_(0, T)
+        ops.kmeans_solve(self.G, timestamps, self.km, n_init_given=n_given, exp_noise=noise if k > 1 else None,
+                         reseed_pool=pool, alpha=self.cfg.alpha, max_iteration=self.cfg.max_iteration, tol=self.cfg.tol)
+        if self.centroids is not None:
+            ops.centroid_update(x2, self.km.member_offsets, self.km.members, k, out=self.centroids)
+        assign = self.km.assignments
+        self.order, self.ev_off = ops.event_order(assign, k)
+        self.dist = ops.dist_to_assigned_gram(self.G, assign, self.ev_off, self.order, k)
+        self.reps, self.rep_counts, self.rep_flags = ops.select_representatives(self.dist, assign, k, self.cfg.n_representatives)
+        if self.packed is not None:
+            ops.gather_rows(x2, self.order, self.packed, n=T)
+
+    # ------------------------------------------------------------------------------------------
+    def phase2(self, features: torch.Tensor, events_repr: Optional[torch.Tensor], question: Optional[torch.Tensor],
+               pixel_values: torch.Tensor, input_ids: torch.Tensor, attention_mask: Optional[torch.Tensor] = None) -> None:
+        """events_repr [k, Dl], question [1, Dl] (frozen-LLM outputs); pixel_values [T*P*m*m, C]; ids [n_ids]."""
+        T, P = self.T, self.P
+        minor_flags = None
+        if self.gate:
+            self.cos, self.low = ops.cosine_flags(question.view(-1), events_repr, self.cfg.relevance_threshold)
+            self.minor_flags, self.minor_list, self.n_minor = ops.minor_frames(self.km.assignments, self.low, self.rep_flags)
+            minor_flags = self.minor_flags
+        else:
+            self.minor_flags.zero_()
+            self.n_minor.zero_()
+            minor_flags = self.minor_flags
+        ops.pixel_mask(pixel_values, T, P, self.W, threshold=self.cfg.pixel_threshold, min_tokens=self.cfg.min_tokens,
+                       minor_flags=minor_flags, frame0=0, out=self.mask)
+        _, self.kept_index, self.n_kept = ops.compact_tokens(features, T, P, self.mask, minor_flags, out=self.out,
+                                                             workspace=self.compact_ws)
+        self.out_ids, self.out_attention, _, _, self.n_ids_out = ops.filter_ids(input_ids, self.image_token_index, self.mask,
+                                                                                attention_mask)
+
+    # ------------------------------------------------------------------------------------------
+    def stats_row(self) -> torch.Tensor:
+        """[len(STATS_FIELDS)] int64 on the device (no sync): the per-stream row that ranks all-gather."""
+        dev = self.device
+        row = torch.zeros(len(STATS_FIELDS), dtype=torch.int64, device=dev)
+        row[0] = self.T
+        row[1] = self.k if self.gate else 0
+        if self.gate:
+            st = self.km.status
+            row[2] = st[0]
+            row[3] = st[2]
+            row[7] = st[1]
+        row[4:5] = self.n_minor
+        row[5:6] = self.n_kept
+        row[6:7] = self.n_ids_out
+        return row
+
+    def results(self) -> Dict[str, object]:
+        """Host view of the outputs (synchronises)."""
+        nk = int(self.n_kept.item())
+        no = int(self.n_ids_out.item())
+        res = dict(n_kept=nk, mask=self.mask.view(torch.bool), features=self.out[:nk], kept_index=self.kept_index[:nk],
+                   input_ids=self.out_ids[:no],
+                   attention_mask=None if self.out_attention is None else self.out_attention[:no])
+        if self.gate:
+            nm = int(self.n_minor.item())
+            cnt = self.rep_counts.tolist()
+            res.update(
+                status=ops.decode_status(self.km.status), assignments=self.km.assignments, init_indices=self.km.init_indices,
+                centroid_times=self.km.centroid_times,
+                centroids=None if self.centroids is None else self.centroids.view(self.k, self.P, self.D),
+                representatives=[self.reps[i, : cnt[i]] for i in range(self.k)], minor=self.minor_list[:nm].tolist(),
+                cos=self.cos, low_flags=self.low, event_order=self.order, event_offsets=self.ev_off, packed_events=self.packed,
+            )
+        else:
+            res.update(minor=[])
+        return res
+
+
+# ---------------------------------------------------------------------------------------------------
+# multi-GPU: independent streams, one stats all-gather
+# ---------------------------------------------------------------------------------------------------
+def shard_streams(n_streams: int, rank: int, world_size: int) -> List[int]:
+    """Stream s runs on rank s mod W (DistributedSampler-style round robin, answer_generate.py:186)."""
+    return list(range(rank, n_streams, world_size))
+
+
+def gather_stats(local_rows: torch.Tensor, world_size: Optional[int] = None) -> torch.Tensor:
+    """All-gather the [n_local, len(STATS_FIELDS)] int64 stats rows -> [world, n_local, F].
+
+    The only collective on the path (NCCL over NVLink on GPUs, gloo in the CPU tests).  Every rank must
+    pass the same number of rows (pad with zero rows when the stream count does not divide).
+    """
+    import torch.distributed as dist
+
+    if not (dist.is_available() and dist.is_initialized()):
+        return local_rows.unsqueeze(0)
+    ws = world_size or dist.get_world_size()
+    rows = local_rows.contiguous()
+    out = torch.empty((ws * rows.shape[0],) + tuple(rows.shape[1:]), dtype=rows.dtype, device=rows.device)
+    dist.all_gather_into_tensor(out, rows)  # rank-major concatenation along dim 0
+    return out.view((ws,) + tuple(rows.shape))
+
+
+def pad_rows(rows: Sequence[torch.Tensor], n: int, device) -> torch.Tensor:
+    """Stack per-stream rows and pad with zero rows to ``n`` (ranks with fewer streams)."""
+    F = len(STATS_FIELDS)
+    out = torch.zeros(n, F, dtype=torch.int64, device=device)
+    for i, r in enumerate(rows):
+        out[i] = r
+    return out

@@ -1,0 +1,211 @@
+/*
+ * cogstream_b200 -- C ABI of the B200-native Visual Stream Compression hot path.
+ *
+ * The reference (LiamZhao326/CogStream) is pure Python + torch and has NO FFI of its own;
+ * this header is the boundary a maintainer binds (ctypes) to replace the
+ * torch op sequences of
+ *     model/kmeans_with_time.py:4-137        (temporal-semantic k-means)
+ *     model/cogreasoner_chat.py:50-64        (select_additional_frames)
+ *     model/cogreasoner_chat.py:278-333      (select_events_based_on_summary, non-LLM parts)
+ *     model/cogreasoner_chat.py:383-432      (_get_compression_mask)
+ *     model/cogreasoner_chat.py:434-447      (compress_unimportant_events)
+ *     model/cogreasoner_chat.py:449-476      (_compress_visual_tokens)
+ * Each entry point cites the reference lines it replaces.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is DEVICE memory owned by the caller unless
+ *     it says "host"; nothing is allocated, freed or retained by the library;
+ *   - all work is enqueued on the given CUDA stream (a cudaStream_t passed as void*); no entry
+ *     point synchronises with the host;
+ *   - return 0 on success, a negative csb_status otherwise; csb_last_error() gives the text of
+ *     the last failure on the calling thread;
+ *   - sm_100a only: every launcher fails with CSB_ERR_ARCH on another device; there is no CPU
+ *     fallback;
+ *   - "bf16" buffers are raw 16-bit bfloat16; rows are contiguous and 16-byte aligned
+ *     (D % 8 == 0), which the reference already needs for its .view() calls
+ *     (kmeans_with_time.py:35, cogreasoner_chat.py:279).
+ */
+#ifndef COGSTREAM_B200_H_
+#define COGSTREAM_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CSB_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define CSB_API __attribute__((visibility("default")))
+#else
+#define CSB_API
+#endif
+
+typedef enum csb_status {
+  CSB_OK = 0,
+  CSB_ERR_ARG = -1,       /* bad shape / null pointer / misalignment */
+  CSB_ERR_ARCH = -2,      /* device is not sm_100 */
+  CSB_ERR_CUDA = -3,      /* launch or runtime failure (text in csb_last_error) */
+  CSB_ERR_WORKSPACE = -4, /* workspace too small */
+  CSB_ERR_UNSUPPORTED = -5
+} csb_status;
+
+typedef enum csb_dtype { CSB_F32 = 0, CSB_F64 = 1, CSB_BF16 = 2 } csb_dtype;
+
+typedef void* csb_stream_t; /* cudaStream_t */
+
+CSB_API int csb_abi_version(void);
+CSB_API const char* csb_last_error(void);
+/* 0 if the current device can run the kernels (compute capability 10.x), else CSB_ERR_ARCH. */
+CSB_API int csb_check_device(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * (a) frame-token pooling + squared L2 norm.                     cogreasoner_chat.py:444-446 (pool),
+ *     x [T,P,D] bf16 -> pooled_bf16 [T,D] (fp32 accumulate, one RN)  kmeans_with_time.py:73 (the ||x||^2
+ *                       pooled_f32  [T,D], sqnorm [T] fp32           term of cdist); any output may be NULL.
+ * ------------------------------------------------------------------------------------------- */
+CSB_API int csb_pool_norm(const void* x_bf16, int64_t T, int64_t P, int64_t D, void* pooled_bf16, float* pooled_f32,
+                  float* sqnorm, csb_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * (b) k-means.
+ * csb_gram: G[i][j] = <x_i, x_j> over the flattened [P*D] frame vectors, fp64 [T,T] (both
+ *     triangles).  bf16 products are exact in fp32; the tcgen05 kernel accumulates fp32 per
+ *     K-split in TMEM and the splits are summed in fp64 in a fixed order (deterministic).
+ *     Every feature distance the reference takes from torch.cdist (kmeans_with_time.py:48, :73;
+ *     cogreasoner_chat.py:61) is ||x_i||^2 + ||c||^2 - 2<x_i,c> with c a frame or a mean of
+ *     frames, i.e. a function of G.
+ *     impl: 0 = tcgen05/TMA kernel (default), 1 = CUDA-core reference kernel (validation only).
+ * ------------------------------------------------------------------------------------------- */
+CSB_API size_t csb_gram_workspace_bytes(int64_t T, int64_t K);
+CSB_API int csb_gram(const void* x_bf16, int64_t T, int64_t K, double* G, void* workspace, size_t workspace_bytes,
+             int impl, csb_stream_t stream);
+
+typedef struct csb_kmeans_params {
+  int64_t T;              /* frames */
+  int64_t k;              /* clusters, T > k >= 1 (T <= k is the caller's early return, :30-32) */
+  int32_t ts_dtype;       /* CSB_F32 or CSB_F64: dtype of timestamps / centroid_times */
+  int32_t max_iteration;  /* :4  default 30 */
+  double alpha;           /* :4  default 2 */
+  double tol;             /* :4  default 1e-4 */
+  int64_t n_init_given;   /* how many entries of init_indices are prescribed (>=1: the first centre is
+                             always drawn by the host, :41); the remaining k - n are sampled k-means++ */
+  int64_t n_reseed_pool;  /* entries available in reseed_pool (host random.randint(0, T-1) draws) */
+} csb_kmeans_params;
+
+/* Device-side result block, written by csb_kmeans_solve (read it after a stream sync). */
+typedef struct csb_kmeans_status {
+  int32_t iterations;        /* Lloyd iterations executed */
+  int32_t converged;         /* 1 if centre shift <= tol (:130) */
+  int32_t n_reseed_used;     /* entries of reseed_pool consumed: degenerate init rounds (:57) first, then
+                                empty-cluster re-seeds (:118), in the order the reference calls random.randint */
+  int32_t degenerate_rounds; /* init rounds that hit probs_sum == 0 (:55) */
+  int32_t reseed_overflow;   /* 1 if reseed_pool ran out (result invalid; re-run with a larger pool) */
+  int32_t n_noise_used;      /* rows of exp_noise consumed (= multinomial calls the reference would make) */
+  float min_margin;          /* smallest (2nd best - best) final distance over all rows/iterations */
+  float last_shift;          /* centre shift of the last iteration */
+} csb_kmeans_status;
+
+CSB_API size_t csb_kmeans_workspace_bytes(int64_t T, int64_t k);
+/*
+ * k-means++ init (kmeans_with_time.py:41-62) + Lloyd loop (:71-131) in ONE cooperative launch,
+ * no host round trips.  Sampling round m computes probs exactly as :46-59 and picks
+ * argmax(probs / exp_noise[m-1]) -- what torch.multinomial(probs, 1) evaluates internally with
+ * q ~ Exp(1) (the host draws exp_noise from the torch generator the reference would have used).
+ * Noise rows are consumed one per sampling round; a round with probs_sum == 0 (:55-57) takes the next
+ * reseed_pool entry instead, so both host RNG streams are consumed exactly like the reference does.
+ *   G             [T,T] fp64 (csb_gram)
+ *   timestamps    [T]   ts_dtype
+ *   init_indices  [k]   int64; first n_init_given entries are inputs, the rest are outputs
+ *   exp_noise     [k-1,T] fp32 or NULL when n_init_given == k
+ *   reseed_pool   [n_reseed_pool] int64 frame indices for empty clusters, consumed in order
+ *   assignments   [T]   int64  out (:104, lowest index wins ties)
+ *   centroid_times[k]   ts_dtype out (:115/:120)
+ *   member_offsets[k+1] int32 out, members [T+k] int32 out: CSR of the frames that DEFINE each returned
+ *                  centre (its assigned frames ascending; a re-seeded empty cluster lists its seed frame)
+ *   status        device csb_kmeans_status
+ */
+CSB_API int csb_kmeans_solve(const double* G, const void* timestamps, const csb_kmeans_params* params /* host */,
+                     int64_t* init_indices, const float* exp_noise, const int64_t* reseed_pool,
+                     int64_t* assignments, void* centroid_times, int32_t* member_offsets, int32_t* members,
+                     csb_kmeans_status* status, void* workspace, size_t workspace_bytes, csb_stream_t stream);
+
+/* Centroid features from the defining members: C[j] = (sum of member rows, ascending, fp32) / n_j.
+ * kmeans_with_time.py:110-120, one pass over the member rows; atomic-free and deterministic. */
+CSB_API int csb_centroid_update(const void* x_bf16, int64_t T, int64_t K, const int32_t* member_offsets,
+                        const int32_t* members, int64_t k, float* centroids /* [k,K] */, csb_stream_t stream);
+
+/* dist[i] = || x_i - C[assign[i]] ||_2 (fp32), one pass over x.  cogreasoner_chat.py:57-61. */
+CSB_API int csb_dist_to_assigned(const void* x_bf16, int64_t T, int64_t K, const float* centroids, int64_t k,
+                         const int64_t* assignments, float* dist, csb_stream_t stream);
+/* Same distances from the Gram matrix and the event CSR of csb_event_order (no pass over x).
+ *   rowsum_ws [T] fp64 scratch. */
+CSB_API int csb_dist_to_assigned_gram(const double* G, int64_t T, int64_t k, const int64_t* assignments,
+                              const int32_t* event_offsets, const int32_t* order, float* dist,
+                              double* rowsum_ws, csb_stream_t stream);
+/* Per event the n_rep members with the smallest dist (ascending dist, lowest index on ties); events with
+ * <= n_rep members list all members ascending.  cogreasoner_chat.py:55-63.
+ *   reps [k,n_rep] int64 (-1 padded), rep_counts [k] int32, rep_flags [T] uint8 (1 = representative). */
+CSB_API int csb_select_representatives(const float* dist, const int64_t* assignments, int64_t T, int64_t k, int64_t n_rep,
+                               int64_t* reps, int32_t* rep_counts, uint8_t* rep_flags, csb_stream_t stream);
+
+/* Chronological per-event order (cogreasoner_chat.py:291-296): order[] lists frame indices sorted by
+ * (event, frame); event_offsets [k+1].  Then csb_gather_rows(order) packs the event tokens. */
+CSB_API int csb_event_order(const int64_t* assignments, int64_t T, int64_t k, int32_t* order, int32_t* event_offsets,
+                    csb_stream_t stream);
+/* dst row r = src row index[r] for r < n (n read from n_dev when non-NULL, else n_host). */
+CSB_API int csb_gather_rows(const void* src, int64_t row_bytes, const int32_t* index, int64_t n_host,
+                    const int64_t* n_dev, int64_t n_max, void* dst, csb_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * (c) question relevance.  cogreasoner_chat.py:325-330: cosine_similarity(q, events) evaluated with
+ *     the dtype's op-by-op rounding (norm, clamp(1e-8), divide, multiply, sum), cos < threshold with the
+ *     threshold rounded to the dtype.  dtype CSB_BF16 or CSB_F32.
+ *       cos_out [k] (dtype), low_flags [k] uint8
+ * ------------------------------------------------------------------------------------------- */
+CSB_API int csb_cosine_flags(const void* question, const void* events, int64_t k, int64_t Dl, int32_t dtype,
+                     double threshold, void* cos_out, uint8_t* low_flags, csb_stream_t stream);
+/* minor[i] = low_flags[assign[i]] && !rep_flags[i]   (cogreasoner_chat.py:331-332)
+ *   minor_flags [T] uint8, minor_list [T] int32 ascending, n_minor device int64 */
+CSB_API int csb_minor_frames(const int64_t* assignments, const uint8_t* low_flags, const uint8_t* rep_flags, int64_t T,
+                     uint8_t* minor_flags, int32_t* minor_list, int64_t* n_minor, csb_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * (d) token mask, pooling of minor frames, chronological compaction.
+ * csb_pixel_mask: one video item [t, P, W] (W = merge^2 * C) -> mask [t*P] uint8.
+ *     cogreasoner_chat.py:407-422: keep iff mean|x_f - x_{f-1}| * 255 > threshold in the pixel dtype
+ *     (bf16: subtract, mean (fp32 accumulate, one RN), *255 and the threshold each round to bf16);
+ *     first frame compares threshold+1; frames with < min_tokens kept keep their first min_tokens;
+ *     frames flagged in minor_flags[frame0 + f] keep only token 0.  dtype CSB_BF16 or CSB_F32.
+ * ------------------------------------------------------------------------------------------- */
+CSB_API int csb_pixel_mask(const void* pixels, int64_t t, int64_t P, int64_t W, int32_t dtype, double threshold,
+                   int64_t min_tokens, const uint8_t* minor_flags, int64_t frame0, uint8_t* mask,
+                   csb_stream_t stream);
+
+/* In-place token-0 pooling of the listed frames (cogreasoner_chat.py:444-446) on a caller-made clone. */
+CSB_API int csb_pool_frames_inplace(void* x_bf16, int64_t T, int64_t P, int64_t D, const int32_t* frame_list,
+                            int64_t n_host, const int64_t* n_dev, csb_stream_t stream);
+
+CSB_API size_t csb_compact_workspace_bytes(int64_t n_tokens, int64_t n_ids);
+/* cogreasoner_chat.py:458 + :444-446 fused: out = x[mask] in chronological order, where token 0 of a
+ * frame flagged in pool_flags is emitted as that frame's pooled mean (so no 249 MB clone is made).
+ *   kept_index [n_tokens] int32 (token index of every kept row), n_kept device int64. */
+CSB_API int csb_compact_tokens(const void* x_bf16, int64_t T, int64_t P, int64_t D, const uint8_t* mask,
+                       const uint8_t* pool_flags, void* out_bf16, int32_t* kept_index, int64_t* n_kept,
+                       void* workspace, size_t workspace_bytes, csb_stream_t stream);
+/* cogreasoner_chat.py:459-474: keep every text id and the <image> ids whose mask bit is set (the j-th image
+ * id pairs with mask[j]); optional attention_mask / labels / position_ids (int64) are filtered alike and
+ * position_ids are rebuilt as 0..len-1 per sequence (a sequence starts where the filtered id is 0).
+ *   n_out device int64.  Any optional in/out pair may be NULL. */
+CSB_API int csb_filter_ids(const int64_t* input_ids, int64_t n_ids, int64_t image_token_index, const uint8_t* mask,
+                   int64_t n_mask, const int64_t* attention_mask, const int64_t* labels,
+                   const int64_t* position_ids, int64_t* out_ids, int64_t* out_attention_mask,
+                   int64_t* out_labels, int64_t* out_position_ids, int64_t* n_out, void* workspace,
+                   size_t workspace_bytes, csb_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* COGSTREAM_B200_H_ */

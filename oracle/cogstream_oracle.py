@@ -94,8 +94,9 @@ def kmeans_with_time_min_max(
 
     Injection (keyword only, not in the reference):
       init_indices    k frame indices used as initial centres instead of k-means++ sampling.
-      exp_noise       [k-1, T] fp32 Exp(1) draws; round m picks argmax(probs / exp_noise[m-1]),
-                      which is what ``torch.multinomial(probs, 1)`` computes internally.
+      exp_noise       [k-1, T] fp32 Exp(1) draws; the n-th SAMPLING round picks
+                      argmax(probs / exp_noise[n]), which is what ``torch.multinomial(probs, 1)``
+                      computes internally (degenerate rounds, :55-57, consume no row).
       reseed_indices  frame indices consumed (in order) by empty-cluster re-seeding (:118).
     """
     info = info if info is not None else KMeansInfo()
@@ -113,6 +114,7 @@ def kmeans_with_time_min_max(
         assert len(centers_indices) == cluster_num
     else:
         centers_indices = [random.randint(0, T - 1)]  # :41
+        n_sampled = 0  # multinomial calls so far == rows of exp_noise consumed
         while len(centers_indices) < cluster_num:  # :44
             dist_to_chosen = torch.cdist(X, X[centers_indices], p=2)  # :46-48
             nearest = dist_to_chosen.min(dim=1).values  # :50
@@ -124,9 +126,10 @@ def kmeans_with_time_min_max(
             else:
                 probs = probs / probs_sum  # :59
                 if exp_noise is not None:
-                    nxt = int(torch.argmax(probs / exp_noise[len(centers_indices) - 1]).item())
+                    nxt = int(torch.argmax(probs / exp_noise[n_sampled]).item())
                 else:
                     nxt = int(torch.multinomial(probs, 1).item())  # :60
+                n_sampled += 1
             centers_indices.append(nxt)  # :62
     info.init_indices = list(centers_indices)
 

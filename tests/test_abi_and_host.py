@@ -1,0 +1,104 @@
+"""CPU: the C-ABI library exports exactly what include/cogstream_b200.h declares; host-side logic."""
+import os
+import re
+import subprocess
+
+import pytest
+import torch
+
+from conftest import ROOT
+from cogstream_b200 import StreamConfig, _lib, ops, pad_rows, shard_streams, synthetic
+from cogstream_b200.compression import VisualStreamCompressionMixin, create_visual_summary_prompt
+from cogstream_b200.kmeans_with_time import kmeans_with_time_min_max
+
+
+def _declared():
+    text = open(os.path.join(ROOT, "include", "cogstream_b200.h")).read()
+    return sorted(set(re.findall(r"CSB_API\s+[\w\s\*]+?\b(csb_\w+)\s*\(", text)))
+
+
+def test_header_symbols_exported(built_lib):
+    declared = _declared()
+    assert len(declared) >= 20
+    out = subprocess.run(["nm", "-D", "--defined-only", _lib.LIB_PATH], capture_output=True, text=True, check=True).stdout
+    exported = sorted(set(re.findall(r"\sT\s+(csb_\w+)", out)))
+    assert exported == declared
+    assert sorted(_lib.PROTOTYPES) == declared  # the ctypes table mirrors the header one to one
+    for name in declared:
+        assert hasattr(built_lib, name)
+
+
+def test_abi_version_and_sizes(built_lib):
+    assert built_lib.csb_abi_version() == 1
+    # pure host arithmetic (no GPU): workspace sizes are positive and monotone
+    a = built_lib.csb_gram_workspace_bytes(600, 207360)
+    b = built_lib.csb_gram_workspace_bytes(64, 4608)
+    assert a > 0 and b > 0
+    assert built_lib.csb_kmeans_workspace_bytes(600, 40) > 2 * 600 * 40 * 8
+    assert built_lib.csb_compact_workspace_bytes(108000, 108037) >= 4 * 108037
+    assert built_lib.csb_gram_workspace_bytes(0, 0) == 0
+
+
+def test_sass_is_blackwell_native(built_lib):
+    """The Gram kernel must be tcgen05 + TMA + TMEM (UTCHMMA / UTMALDG / LDTM in SASS), not mma.sync."""
+    cuobjdump = "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    sass = subprocess.run([cuobjdump, "-sass", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    assert "UTCHMMA" in sass and "UTMALDG" in sass and "LDTM" in sass
+    assert "HMMA." not in sass.replace("UTCHMMA", "")
+    assert "sm_100a" in sass or "EF_CUDA_SM100" in sass
+
+
+def test_no_cpu_fallback():
+    x = torch.zeros(4, 2, 8, dtype=torch.bfloat16)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        kmeans_with_time_min_max(x, torch.arange(4.0), 2)
+    with pytest.raises(RuntimeError, match="CPU"):
+        ops.gram(x.view(4, 16))
+    with pytest.raises(RuntimeError, match="CPU"):
+        ops.pixel_mask(torch.zeros(8, 4, dtype=torch.bfloat16), 2, 2, 8)
+
+    class S(VisualStreamCompressionMixin):
+        pass
+
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        S().compress_unimportant_events(torch.zeros(8, 8, dtype=torch.bfloat16), 2, [1])
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "cogstream_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle", src, flags=re.M), f
+                assert "/root/reference" not in src, f
+
+
+def test_gate_and_cluster_count():
+    cfg = StreamConfig()
+    assert cfg.clusters_for(600) == 40 and cfg.gate_open(600)
+    assert cfg.clusters_for(135) == 9 and not cfg.gate_open(135)  # k <= 9 -> no compression (cogreasoner_chat.py:281)
+    assert cfg.clusters_for(136) == 10 and cfg.gate_open(136)
+    assert StreamConfig(cluster_num=8).gate_open(64) and not StreamConfig(cluster_num=8).gate_open(8)
+
+
+def test_shard_and_pad():
+    assert shard_streams(10, 1, 4) == [1, 5, 9]
+    assert sorted(sum((shard_streams(256, r, 8) for r in range(8)), [])) == list(range(256))
+    rows = pad_rows([torch.arange(8), torch.arange(8) + 1], 3, "cpu")
+    assert rows.shape == (3, 8) and rows[2].sum() == 0 and rows[1, 0] == 1
+
+
+def test_prompt_layout():
+    p = create_visual_summary_prompt(6, [0.0, 12.34, 99.0])
+    assert p.count("<image>") == 6 and "Time 12.3s:<image><image>," in p and p.endswith("<|im_start|>assistant")
+
+
+def test_synthetic_is_deterministic():
+    a = synthetic.make_stream(40, 3, 16, seed=5, C=4)
+    b = synthetic.make_stream(40, 3, 16, seed=5, C=4)
+    assert torch.equal(a.features, b.features) and torch.equal(a.pixel_values, b.pixel_values)
+    assert a.features.dtype == torch.bfloat16 and a.timestamps.dtype == torch.float64
+    assert a.pixel_values.shape == (40 * 3 * 4, 4) and a.input_ids.eq(synthetic.IMAGE_TOKEN_INDEX).sum() == 120
