@@ -1,0 +1,416 @@
+#!/usr/bin/env python
+"""Benchmark of the Visual Stream Compression hot path (BASELINE.json metric: frames/sec compressed).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" = one pass of the whole path (phase 1 + phase 2, the frozen-LLM forwards in between excluded, their
+outputs being synthetic inputs) over one stream per rank of BASELINE config 2:
+    T=600 frames (1 fps x 10 min), P=180 merged tokens/frame, D=1152 bf16 features, k=ceil(T/15)=40 events,
+    pixel_values [T*720, 588] bf16, event/question embeddings [40,3584]/[1,3584] bf16, float64 timestamps.
+Streams are independent, so N ranks run N streams with no data-path collective (weak scaling); the one
+collective is the all-gather of the per-stream stats rows after the timed region's last step.
+
+Prints ONE JSON line (rank 0).  `value` = device-resident throughput; `e2e` = through the public pipeline API
+with pinned HOST inputs, H2D copies of every input and a D2H read of the result inside the timed region.
+`--impl reference` times the CPU restatement of the reference (oracle/, kind "port": the reference is Python
+and /root/reference is not on the GPU box) on the host cores, rank 0 only.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import random
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC = "frames/sec compressed"
+UNIT = "frames/s"
+WORKLOAD = dict(T=600, P=180, D=1152, merge=2, C=588, Dl=3584, fps=1.0)
+
+
+def _peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(path):
+        p = json.load(open(path))
+        return dict(hbm_gbs=float(p["hbm_gbs"]), bf16_tflops=float(p["bf16_tflops"]),
+                    bf16_tflops_sustained=float(p.get("bf16_tflops_sustained", p["bf16_tflops"])), source="measured")
+    return dict(hbm_gbs=6650.0, bf16_tflops=1590.0, bf16_tflops_sustained=1400.0, source="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md clocks line)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, power = [], [], set(), []
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); power.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["no samples"])
+        return dict(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm),
+                    power_w_max=max(power) if power else None)
+
+
+# ----------------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port of the reference, all host threads
+# ----------------------------------------------------------------------------------------------------------
+def _cpu_path_once(st, ev, q, k, seed):
+    from cogstream_b200 import synthetic
+    from oracle import cogstream_oracle as orc
+
+    random.seed(seed)
+    torch.manual_seed(seed)
+    t0 = time.perf_counter()
+    p1 = orc.phase1(st.features, st.T, st.timestamps, cluster_num=k)  # k-means++ sampled like the reference does
+    p2 = orc.phase2(st.features, p1, ev, q, st.pixel_values, st.grid_sizes, st.merge_sizes, st.modals, st.input_ids,
+                    synthetic.IMAGE_TOKEN_INDEX, st.attention_mask)
+    dt = time.perf_counter() - t0
+    return dt, p1, p2
+
+
+def _make_cpu_sample(P_sample, seed=0):
+    from cogstream_b200 import synthetic
+
+    w = WORKLOAD
+    st = synthetic.make_stream(w["T"], P_sample, w["D"], seed, fps=w["fps"], merge=w["merge"], C=w["C"])
+    k = math.ceil(w["T"] / 15)
+    ev, q = synthetic.make_embeddings(k, w["Dl"], seed)
+    return st, ev, q, k
+
+
+def cpu_baseline(budget_s: float, n_runs: int = 1):
+    """Time the oracle on a bounded sample of config 2: same T, k, D; P reduced until one run fits the budget
+    (the CPU cost is ~linear in P; the value reported is the one measured on the sample)."""
+    torch.set_num_threads(os.cpu_count() or 1)
+    w = WORKLOAD
+    st, ev, q, k = _make_cpu_sample(6)
+    t_small, _, _ = _cpu_path_once(st, ev, q, k, 0)
+    t_small2, _, _ = _cpu_path_once(st, ev, q, k, 0)
+    per_p = min(t_small, t_small2) / 6.0
+    P_s = int(max(6, min(w["P"], budget_s / max(per_p, 1e-6) / max(n_runs, 1))))
+    if P_s >= w["P"] * 0.9:
+        P_s = w["P"]
+    st, ev, q, k = _make_cpu_sample(P_s)
+    times = []
+    for r in range(n_runs):
+        dt, p1, p2 = _cpu_path_once(st, ev, q, k, r)
+        times.append(dt)
+    t = statistics.median(times)
+    sample = (f"1 stream of config 2 with T={w['T']} k={k} D={w['D']} and P={P_s} of {w['P']} tokens/frame "
+              f"(CPU cost ~linear in P), k-means++ sampled, {n_runs} run(s), median")
+    return dict(value=w["T"] / t, unit=UNIT, cores=torch.get_num_threads(), kind="port", sample=sample,
+                seconds_per_run=t, value_full_P_estimate=w["T"] / (t * w["P"] / P_s)), times
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    total_budget = 150.0
+    per_step = total_budget / max(args.steps + args.warmup, 1)
+    torch.set_num_threads(os.cpu_count() or 1)
+    w = WORKLOAD
+    st, ev, q, k = _make_cpu_sample(6)
+    _cpu_path_once(st, ev, q, k, 0)
+    t_small, _, _ = _cpu_path_once(st, ev, q, k, 0)
+    P_s = int(max(4, min(w["P"], per_step / max(t_small / 6.0, 1e-6))))
+    if P_s >= w["P"] * 0.9:
+        P_s = w["P"]
+    st, ev, q, k = _make_cpu_sample(P_s)
+    for i in range(args.warmup):
+        _cpu_path_once(st, ev, q, k, 100 + i)
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        _cpu_path_once(st, ev, q, k, i)
+    dt = (time.perf_counter() - t0) / max(args.steps, 1)
+    value = w["T"] / dt
+    sample = (f"each step = 1 stream of config 2 with T={w['T']} k={k} D={w['D']} and P={P_s} of {w['P']} tokens/frame "
+              f"(bounded so K+W steps end within minutes; CPU cost ~linear in P)")
+    line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=args.gpus, steps=args.steps, warmup=args.warmup, ms_per_step=dt * 1e3,
+                higher_is_better=True, scaling="weak", vs_baseline=None, dtype="bf16", data="synthetic", impl="reference",
+                config=_config_dict(P_s),
+                cpu_baseline=dict(value=value, unit=UNIT, cores=torch.get_num_threads(), kind="port", sample=sample,
+                                  value_full_P_estimate=w["T"] / (dt * w["P"] / P_s)),
+                e2e=dict(value=value, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
+    print(json.dumps(line), flush=True)
+
+
+def _config_dict(P=None):
+    w = WORKLOAD
+    return dict(workload="BASELINE config 2: single stream per GPU, 1 fps x 10 min", T=w["T"], P=P or w["P"], D=w["D"],
+                k=math.ceil(w["T"] / 15), pixel_row=f"[T*{(P or w['P']) * w['merge'] ** 2}, {w['C']}] bf16", embed_dim=w["Dl"],
+                timestamps="float64", init="k-means++ sampled on device (Exp(1) noise drawn in the timed region)",
+                l2="inputs (757 MB/stream) exceed the 126 MB L2; no explicit flush", parallelism="independent streams, 1 per rank per step")
+
+
+# ----------------------------------------------------------------------------------------------------------
+# GPU arm
+# ----------------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch.distributed as dist
+
+    from cogstream_b200 import STATS_FIELDS, StreamCompressor, _lib, gather_stats, synthetic
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; cogstream_b200 has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.load()
+    w = WORKLOAD
+    T, P, D = w["T"], w["P"], w["D"]
+    k = math.ceil(T / 15)
+
+    # ---- synthetic stream of this rank (seed = rank), pinned on the host, resident copy on the device ----
+    st = synthetic.make_stream(T, P, D, seed=rank, fps=w["fps"], merge=w["merge"], C=w["C"])
+    ev, q = synthetic.make_embeddings(k, w["Dl"], seed=rank)
+    host = st.pin()
+    ev_h, q_h = ev.pin_memory(), q.pin_memory()
+    d = st.to(dev)
+    ev_d, q_d = ev.to(dev), q.to(dev)
+    W = st.pixel_values.numel() // (T * P)
+    sc = StreamCompressor(T, P, D, W, st.input_ids.numel(), device=dev)
+    torch.manual_seed(1234 + rank)
+    random.seed(1234 + rank)
+
+    def step_resident():
+        sc.phase1(d.features, d.timestamps)
+        sc.phase2(d.features, ev_d, q_d, d.pixel_values, d.input_ids, d.attention_mask)
+
+    # e2e staging buffers (device side of the H2D copies) + pinned result buffers
+    e_feat = torch.empty_like(d.features); e_pix = torch.empty_like(d.pixel_values); e_ts = torch.empty_like(d.timestamps)
+    e_ids = torch.empty_like(d.input_ids); e_am = torch.empty_like(d.attention_mask)
+    e_ev = torch.empty_like(ev_d); e_q = torch.empty_like(q_d)
+    r_stats = torch.empty(len(STATS_FIELDS), dtype=torch.int64).pin_memory()
+    r_mask = torch.empty(T * P, dtype=torch.uint8).pin_memory()
+    h2d = sum(t.numel() * t.element_size() for t in (host.features, host.pixel_values, host.timestamps, host.input_ids,
+                                                     host.attention_mask, ev_h, q_h))
+    d2h = r_stats.numel() * 8 + r_mask.numel()
+
+    def step_e2e():
+        e_feat.copy_(host.features, non_blocking=True)
+        e_ts.copy_(host.timestamps, non_blocking=True)
+        sc.phase1(e_feat, e_ts)
+        e_pix.copy_(host.pixel_values, non_blocking=True)
+        e_ids.copy_(host.input_ids, non_blocking=True)
+        e_am.copy_(host.attention_mask, non_blocking=True)
+        e_ev.copy_(ev_h, non_blocking=True)
+        e_q.copy_(q_h, non_blocking=True)
+        sc.phase2(e_feat, e_ev, e_q, e_pix, e_ids, e_am)
+        r_stats.copy_(sc.stats_row(), non_blocking=True)
+        r_mask.copy_(sc.mask, non_blocking=True)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        l0 = lib.csb_kernel_launches()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        launches = lib.csb_kernel_launches() - l0
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, launches
+
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    ms_total, launches = timed(step_resident, args.steps, max(args.warmup, 3))
+    clocks = sampler.stop() if sampler else None
+    iters_row = sc.stats_row().cpu()
+    ms_e2e, _ = timed(step_e2e, args.steps, max(args.warmup, 3))
+
+    # the one collective: all-gather of the per-stream stats rows
+    rows = gather_stats(sc.stats_row().unsqueeze(0))
+    torch.cuda.synchronize()
+
+    ms_step = ms_total / args.steps
+    value = world * T / (ms_step * 1e-3)
+    e2e_value = world * T / (ms_e2e / args.steps * 1e-3)
+
+    # ---- per-stage device times (CUDA events between the ops of extra, untimed steps) + roofline ----
+    stages = None
+    roofline = None
+    cpu = None
+    if rank == 0:
+        stages = _stage_times(sc, d, ev_d, q_d, reps=max(3, min(args.steps, 10)))
+        roofline = _roofline(stages, sc, d)
+        if world == 1 and not args.no_cpu_baseline:
+            cpu, _ = cpu_baseline(budget_s=20.0)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank != 0:
+        return
+    line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3),
+                ms_per_step=ms_step, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="bf16", data="synthetic",
+                config=_config_dict(), clocks=clocks,
+                e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
+                         ms_per_step=ms_e2e / args.steps),
+                gpu_launches=int(launches), roofline=roofline, stages_ms=stages,
+                stream_stats=dict(zip(STATS_FIELDS, [int(v) for v in iters_row.tolist()])),
+                all_gathered_stats_shape=list(rows.shape))
+    if cpu is not None:
+        line["cpu_baseline"] = cpu
+    print(json.dumps(line), flush=True)
+
+
+def _stage_times(sc, d, ev_d, q_d, reps=5):
+    """Average device time of every launcher of the path, CUDA events on the launching stream."""
+    from cogstream_b200 import ops
+
+    T, P, k = sc.T, sc.P, sc.k
+    x2 = d.features.view(T, sc.K)
+    acc = {}
+
+    def rec(name, fn):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out = fn()
+        e1.record()
+        acc.setdefault(name, []).append((e0, e1))
+        return out
+
+    for _ in range(reps + 1):
+        rec("gram", lambda: ops.gram(x2, out=sc.G, workspace=sc.gram_ws))
+        sc.km.init_indices[:1].fill_(random.randint(0, T - 1))
+        noise = sc.noise[: k - 1]
+        rec("rng_noise", lambda: noise.exponential_(1))
+        sc.pool.random_(0, T)
+        rec("kmeans_solve", lambda: ops.kmeans_solve(sc.G, d.timestamps, sc.km, n_init_given=1, exp_noise=noise, reseed_pool=sc.pool,
+                                                     alpha=sc.cfg.alpha, max_iteration=sc.cfg.max_iteration, tol=sc.cfg.tol))
+        rec("centroid_update", lambda: ops.centroid_update(x2, sc.km.member_offsets, sc.km.members, k, out=sc.centroids))
+        order, off = rec("event_order", lambda: ops.event_order(sc.km.assignments, k))
+        dist = rec("dist_gram", lambda: ops.dist_to_assigned_gram(sc.G, sc.km.assignments, off, order, k))
+        _, _, rflags = rec("select_reps", lambda: ops.select_representatives(dist, sc.km.assignments, k, 2))
+        rec("event_gather", lambda: ops.gather_rows(x2, order, sc.packed, n=T))
+        _, low = rec("cosine_flags", lambda: ops.cosine_flags(q_d.view(-1), ev_d, 0.45))
+        mflags, _, _ = rec("minor_frames", lambda: ops.minor_frames(sc.km.assignments, low, rflags))
+        rec("pixel_mask", lambda: ops.pixel_mask(d.pixel_values, T, P, sc.W, minor_flags=mflags, out=sc.mask))
+        rec("compact_tokens", lambda: ops.compact_tokens(d.features, T, P, sc.mask, mflags, out=sc.out, workspace=sc.compact_ws))
+        rec("filter_ids", lambda: ops.filter_ids(d.input_ids, sc.image_token_index, sc.mask, d.attention_mask))
+    torch.cuda.synchronize()
+    return {n: round(statistics.mean(a.elapsed_time(b) for a, b in ev[1:]), 5) for n, ev in acc.items()}
+
+
+def _roofline(stages, sc, d):
+    """Roofline of the dominant kernel (by measured time); algorithmic bytes / flops as defined in DESIGN.md."""
+    pk = _peaks()
+    T, P, D, k, K = sc.T, sc.P, sc.D, sc.k, sc.K
+    n_kept = int(sc.n_kept.item())
+    n_minor = int(sc.n_minor.item())
+    BX = 2 * T * K
+    alg_bytes = {
+        "gram": BX,
+        "centroid_update": BX + 4 * k * K,
+        "event_gather": 2 * BX,
+        "pixel_mask": 2 * T * P * sc.W,
+        "compact_tokens": 2 * 2 * n_kept * D + 2 * n_minor * P * D,
+    }
+    hbm = {n: dict(ms=stages[n], gbs=alg_bytes[n] / (stages[n] * 1e-3) / 1e9, frac=alg_bytes[n] / (stages[n] * 1e-3) / 1e9 / pk["hbm_gbs"])
+           for n in alg_bytes if stages.get(n)}
+    dom = max(stages, key=lambda n: stages[n])
+    gram_flops = T * (T + 1) * K  # 2 * (T(T+1)/2 unique entries) * K
+    gram_tf = gram_flops / (stages["gram"] * 1e-3) / 1e12
+    if dom == "gram":
+        roof = dict(bound="tensor", kernel="gram_tc_kernel", achieved=gram_tf, peak=pk["bf16_tflops"], unit="TFLOP/s",
+                    frac=gram_tf / pk["bf16_tflops"], traffic=None,
+                    hbm_view=dict(achieved=hbm["gram"]["gbs"], peak=pk["hbm_gbs"], unit="GB/s", frac=hbm["gram"]["frac"]))
+    elif dom in hbm:
+        roof = dict(bound="hbm", kernel=dom, achieved=hbm[dom]["gbs"], peak=pk["hbm_gbs"], unit="GB/s", frac=hbm[dom]["frac"], traffic=None)
+    else:
+        roof = dict(bound="latency", kernel=dom, achieved=None, peak=None, unit=None, frac=None, traffic=None,
+                    note="dominant stage is the L2-resident single-launch k-means solver (latency-bound by design)")
+    roof["peaks"] = pk["source"]
+    roof["per_kernel_hbm"] = {n: dict(ms=v["ms"], gbs=round(v["gbs"], 1), frac=round(v["frac"], 3)) for n, v in hbm.items()}
+    roof["gram_tensor"] = dict(ms=stages["gram"], tflops=round(gram_tf, 1), frac_of_burst=round(gram_tf / pk["bf16_tflops"], 3),
+                               algorithmic_flops=gram_flops)
+    whole = sum(alg_bytes.values())
+    total_ms = sum(stages.values())
+    roof["whole_path"] = dict(algorithmic_bytes=whole, sum_stage_ms=round(total_ms, 4),
+                              gbs=round(whole / (total_ms * 1e-3) / 1e9, 1), frac=round(whole / (total_ms * 1e-3) / 1e9 / pk["hbm_gbs"], 3))
+    return roof
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -41,6 +41,7 @@ PROTOTYPES = {
     "csb_abi_version": (C.c_int, []),
     "csb_last_error": (C.c_char_p, []),
     "csb_check_device": (C.c_int, []),
+    "csb_kernel_launches": (C.c_uint64, []),
     "csb_pool_norm": (C.c_int, [_p, _i64, _i64, _i64, _p, _p, _p, _p]),
     "csb_gram_workspace_bytes": (_sz, [_i64, _i64]),
     "csb_gram": (C.c_int, [_p, _i64, _i64, _p, _p, _sz, C.c_int, _p]),

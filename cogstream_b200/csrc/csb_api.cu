@@ -7,6 +7,9 @@
 namespace csb {
 
 static thread_local char g_err[512] = "";
+static unsigned long long g_launches = 0;  // kernels launched by this library in this process (bench bookkeeping)
+
+void count_launch(int n) { __atomic_fetch_add(&g_launches, (unsigned long long)n, __ATOMIC_RELAXED); }
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -16,6 +19,7 @@ void set_error(const char* fmt, ...) {
 }
 
 int check_launch(const char* what) {
+  count_launch(1);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
     set_error("%s: %s", what, cudaGetErrorString(e));
@@ -54,5 +58,6 @@ extern "C" {
 int csb_abi_version(void) { return CSB_ABI_VERSION; }
 const char* csb_last_error(void) { return csb::g_err; }
 int csb_check_device(void) { return csb::device_ok(); }
+uint64_t csb_kernel_launches(void) { return (uint64_t)__atomic_load_n(&csb::g_launches, __ATOMIC_RELAXED); }
 
 }  // extern "C"

@@ -12,7 +12,8 @@ namespace csb {
 
 // ---- error plumbing (no exceptions cross the C ABI) --------------------------------------------
 void set_error(const char* fmt, ...);
-int check_launch(const char* what);  // cudaGetLastError -> CSB_OK / CSB_ERR_CUDA
+int check_launch(const char* what);  // counts one launch; cudaGetLastError -> CSB_OK / CSB_ERR_CUDA
+void count_launch(int n);            // launches that do not go through check_launch
 int device_ok();                     // cached compute-capability check
 
 #define CSB_REQUIRE(cond, ...)        \

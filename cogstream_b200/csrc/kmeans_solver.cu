@@ -488,6 +488,7 @@ int csb_kmeans_solve(const double* G, const void* timestamps, const csb_kmeans_p
   void* args[] = {&a};
   e = cudaLaunchCooperativeKernel((const void*)kern, dim3((unsigned)nb), dim3(256), args, smem, s);
   if (e != cudaSuccess) { set_error("kmeans_solve: launch: %s", cudaGetErrorString(e)); return CSB_ERR_CUDA; }
+  count_launch(1);
   return CSB_OK;
 }
 

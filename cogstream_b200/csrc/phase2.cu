@@ -456,6 +456,7 @@ int csb_dist_to_assigned_gram(const double* G, int64_t T, int64_t k, const int64
   CSB_REQUIRE(G && assignments && offs && memb && dist && rowsum_ws && T > 0 && k > 0, "dist_to_assigned_gram: null argument");
   cudaStream_t s = as_stream(stream);
   gram_rowsum_kernel<<<(unsigned)((T + 7) / 8), 256, 0, s>>>(G, (int)T, assignments, offs, memb, rowsum_ws);
+  count_launch(1);
   dist_gram_kernel<<<(unsigned)((T + 7) / 8), 256, 0, s>>>(G, (int)T, assignments, offs, memb, rowsum_ws, dist);
   return check_launch("dist_to_assigned_gram");
 }
@@ -466,6 +467,7 @@ int csb_select_representatives(const float* dist, const int64_t* assignments, in
   CSB_REQUIRE(dist && assignments && reps && rep_counts && rep_flags && T > 0 && k > 0 && n_rep > 0, "select_representatives: null argument");
   cudaStream_t s = as_stream(stream);
   clear_flags_kernel<<<(unsigned)((T + 255) / 256), 256, 0, s>>>(rep_flags, T);
+  count_launch(1);
   select_reps_kernel<<<(unsigned)((k + 7) / 8), 256, 0, s>>>(dist, assignments, (int)T, (int)k, (int)n_rep, reps, rep_counts, rep_flags);
   return check_launch("select_representatives");
 }

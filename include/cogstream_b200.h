@@ -60,6 +60,8 @@ CSB_API int csb_abi_version(void);
 CSB_API const char* csb_last_error(void);
 /* 0 if the current device can run the kernels (compute capability 10.x), else CSB_ERR_ARCH. */
 CSB_API int csb_check_device(void);
+/* Kernels this library has launched in this process so far (bench.py reports the count per timed region). */
+CSB_API uint64_t csb_kernel_launches(void);
 
 /* ---------------------------------------------------------------------------------------------
  * (a) frame-token pooling + squared L2 norm.                     cogreasoner_chat.py:444-446 (pool),

@@ -86,6 +86,7 @@ def kmeans_with_time_min_max(
     exp_noise: Optional[torch.Tensor] = None,
     reseed_indices: Optional[Sequence[int]] = None,
     info: Optional[KMeansInfo] = None,
+    exact: bool = False,
 ):
     """Temporal-semantic k-means, model/kmeans_with_time.py:4-137.
 
@@ -98,6 +99,10 @@ def kmeans_with_time_min_max(
                       argmax(probs / exp_noise[n]), which is what ``torch.multinomial(probs, 1)``
                       computes internally (degenerate rounds, :55-57, consume no row).
       reseed_indices  frame indices consumed (in order) by empty-cluster re-seeding (:118).
+      exact           evaluate the SAME algorithm with feature distances and centroid means in float64
+                      (distances then rounded to the fp32 ``cdist`` output the reference works with): a
+                      machine-independent cross-check that the fp32 sgemm rounding noise of the reference
+                      (~1e-6 on the normalised distances) does not decide any assignment of a test case.
     """
     info = info if info is not None else KMeansInfo()
     features = features.to(dtype=torch.float32)  # :22
@@ -107,6 +112,11 @@ def kmeans_with_time_min_max(
     if T <= cluster_num:  # :30-32
         return features, timestamp[:cluster_num], None
     X = features.view(T, P * D)  # :35
+    if exact:
+        X = X.double()
+
+    def _cdist(a, b):
+        return torch.cdist(a, b, p=2).to(torch.float32) if exact else torch.cdist(a, b, p=2)
 
     # ---- k-means++ init on feature distance only (:41-62) -------------------------------
     if init_indices is not None:
@@ -116,7 +126,7 @@ def kmeans_with_time_min_max(
         centers_indices = [random.randint(0, T - 1)]  # :41
         n_sampled = 0  # multinomial calls so far == rows of exp_noise consumed
         while len(centers_indices) < cluster_num:  # :44
-            dist_to_chosen = torch.cdist(X, X[centers_indices], p=2)  # :46-48
+            dist_to_chosen = _cdist(X, X[centers_indices])  # :46-48
             nearest = dist_to_chosen.min(dim=1).values  # :50
             probs = nearest ** 2  # :53
             probs_sum = probs.sum()  # :54
@@ -139,7 +149,7 @@ def kmeans_with_time_min_max(
 
     assignments = None
     for iteration in range(max_iteration):  # :71
-        d_feat = torch.cdist(X, centers_features, p=2)  # :73   fp32 [T,k]
+        d_feat = _cdist(X, centers_features)  # :73   fp32 [T,k]
         d_time = torch.abs(timestamp.unsqueeze(1) - centers_times.unsqueeze(0))  # :76
         norm_feat = _row_minmax_normalise(d_feat)  # :86-91
         norm_time = _row_minmax_normalise(d_time)  # :94-99
@@ -175,7 +185,7 @@ def kmeans_with_time_min_max(
         if shift <= tol:  # :130
             info.converged = True
             break
-    return centers_features.view(cluster_num, P, D), centers_times, assignments  # :134-137
+    return centers_features.to(torch.float32).view(cluster_num, P, D), centers_times, assignments  # :134-137
 
 
 def select_additional_frames(

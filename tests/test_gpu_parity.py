@@ -1,0 +1,371 @@
+"""GPU (-m gpu): the CUDA path, called through the C ABI, against the reference's golden outputs and the CPU
+oracle on the same seeded inputs.  Integer / index / mask results must be bit-exact; pooled and centroid
+features within 1e-3 relative (north star), the tolerance being norm-wise plus at most one bf16 ulp per element.
+"""
+import math
+import random
+
+import pytest
+import torch
+
+from conftest import golden_names, load_golden
+from cogstream_b200 import StreamCompressor, StreamConfig, kmeans_with_time_min_max, ops, select_additional_frames, synthetic
+from cogstream_b200.compression import VisualStreamCompressionMixin
+from oracle import cogstream_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+REL_TOL = 1e-3  # north star: pooled / centroid features within 1e-3 relative (fp32 accumulate)
+
+
+@pytest.fixture(scope="module")
+def dev(built_lib):
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    assert built_lib.csb_check_device() == 0, "device is not sm_100"
+    return torch.device("cuda:0")
+
+
+def assert_times_equal(ct, want):
+    """Centroid times: bit-exact whenever the member sums are exact in the timestamp dtype (integer or dyadic
+    timestamps, i.e. every fps the processor emits at 1 / 2 / 4 fps); otherwise torch's own vectorised summation
+    order is CPU-ISA dependent, so the reference itself is only defined to the last ulp."""
+    ct, want = ct.cpu(), want.cpu()
+    assert ct.dtype == want.dtype and ct.shape == want.shape
+    if torch.equal(ct, want):
+        return
+    eps = torch.finfo(want.dtype).eps
+    assert bool(((ct - want).abs() <= 4 * eps * want.abs().clamp_min(1.0)).all())
+
+
+def rel_err(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+def assert_bf16_close(a, b):
+    """norm-wise 1e-3 and elementwise within one bf16 ulp (fp32-accumulation-order differences only)."""
+    assert a.shape == b.shape
+    if a.numel() == 0:
+        return
+    assert rel_err(a, b) < REL_TOL
+    af, bf = a.float().cpu(), b.float().cpu()
+    ulp = bf.abs().clamp_min(1e-30).log2().floor().exp2() * 2.0 ** -7
+    assert bool(((af - bf).abs() <= ulp * 1.001).all())
+
+
+class _Stub(VisualStreamCompressionMixin):
+    class config:
+        image_token_index = synthetic.IMAGE_TOKEN_INDEX
+        use_token_compression = True
+
+
+# ----------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("T,K", [(64, 512), (150, 768), (600, 4096), (129, 200 * 8), (300, 64)])
+@pytest.mark.parametrize("impl", [1, 0])
+def test_gram_matches_fp64(dev, T, K, impl):
+    g = torch.Generator().manual_seed(T * 7 + K)
+    x = torch.randn(T, K, generator=g).to(torch.bfloat16).to(dev)
+    G = ops.gram(x, impl=impl)
+    ref = x.double() @ x.double().T
+    scale = ref.diagonal().abs().max()
+    assert float((G - ref).abs().max() / scale) < 2e-6
+    assert torch.equal(G, G.T)
+
+
+def test_gram_tensor_core_equals_cuda_core_on_structured_data(dev):
+    st = synthetic.make_stream(600, 8, 1152, seed=11, C=4)
+    x = st.features.view(600, -1).to(dev)
+    G0, G1 = ops.gram(x, impl=0), ops.gram(x, impl=1)
+    ref = x.double() @ x.double().T
+    scale = float(ref.diagonal().max())
+    e0, e1 = float((G0 - ref).abs().max()) / scale, float((G1 - ref).abs().max()) / scale
+    print(f"gram rel err: tcgen05 {e0:.3e}  cuda-core {e1:.3e}")
+    assert e0 < 2e-6 and e1 < 2e-6
+    G0b = ops.gram(x, impl=0)
+    assert torch.equal(G0, G0b), "Gram kernel is not deterministic"
+
+
+# ----------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("impl", [1, 0])
+@pytest.mark.parametrize("name", golden_names())
+def test_kmeans_golden_injected_init(dev, name, impl):
+    g = load_golden(name)
+    s = g["spec"]
+    f3 = g["features"].view(s["T"], s["P"], s["D"]).to(dev)
+    cent, ct, assign, info = kmeans_with_time_min_max(f3, g["timestamps"].to(dev), s["k"], init_indices=g["init"],
+                                                      reseed_indices=[], gram_impl=impl, return_info=True)
+    assert assign.dtype == torch.int64 and cent.dtype == torch.float32 and ct.dtype == g["centroid_times"].dtype
+    assert cent.shape == g["centroids"].shape
+    assert torch.equal(assign.cpu(), g["assignments"]), f"assignments differ (reference min margin {g['min_margin']:.2e})"
+    assert info.iterations == g["iterations"] and info.converged == g["converged"]
+    if "fracfps" in name:
+        assert_times_equal(ct, g["centroid_times"])
+    else:
+        assert torch.equal(ct.cpu(), g["centroid_times"])
+    assert rel_err(cent, g["centroids"]) < REL_TOL
+    assert float((cent.cpu() - g["centroids"]).abs().max()) < 1e-3 * float(g["centroids"].abs().max())
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_kmeans_golden_sampled_init_with_injected_noise(dev, name):
+    g = load_golden(name)
+    s = g["spec"]
+    nz = g["noise"]
+    f3 = g["features"].view(s["T"], s["P"], s["D"]).to(dev)
+    _, _, assign, info = kmeans_with_time_min_max(f3, g["timestamps"].to(dev), s["k"], first_index=nz["first"],
+                                                  exp_noise=nz["exp_noise"], reseed_indices=[], return_info=True)
+    assert info.init_indices.tolist() == nz["init"], "k-means++ picked different centres than the reference"
+    assert info.n_noise_used == s["k"] - 1 and info.degenerate_rounds == 0
+    assert torch.equal(assign.cpu(), nz["assignments"])
+    assert info.iterations == nz["iterations"]
+
+
+def test_kmeans_edge_cases(dev, edge_cases):
+    e = edge_cases["early_return"]  # T <= k: (features_fp32 [T,...], timestamp[:k], None)
+    out = kmeans_with_time_min_max(e["features"].to(dev), e["timestamps"].to(dev), e["k"])
+    assert out[2] is None and torch.equal(out[0].cpu(), e["out_features"]) and torch.equal(out[1].cpu(), e["out_times"])
+
+    e = edge_cases["empty_cluster"]  # duplicate centre -> empty cluster -> re-seed from the injected pool
+    f3 = e["features"].view(e["T"], e["P"], e["D"]).to(dev)
+    cent, ct, assign, info = kmeans_with_time_min_max(f3, e["timestamps"].to(dev), e["k"], init_indices=e["init"],
+                                                      reseed_indices=e["reseed"], return_info=True)
+    assert info.n_reseed_used == len(e["used"]) >= 1
+    assert torch.equal(assign.cpu(), e["assignments"]) and torch.equal(ct.cpu(), e["centroid_times"])
+    assert info.iterations == e["iterations"] and rel_err(cent, e["centroids"]) < REL_TOL
+
+    e = edge_cases["duplicates"]  # static video: exact ties -> lowest index
+    f3 = e["features"].view(e["T"], e["P"], e["D"]).to(dev)
+    cent, ct, assign, info = kmeans_with_time_min_max(f3, e["timestamps"].to(dev), e["k"], init_indices=e["init"],
+                                                      reseed_indices=[1, 2, 3, 4], return_info=True)
+    assert torch.equal(assign.cpu(), e["assignments"]) and info.n_reseed_used == len(e["used"])
+    assert info.iterations == e["iterations"] and rel_err(cent, e["centroids"]) < REL_TOL
+
+
+def test_kmeans_python_rng_stream_is_rewound(dev):
+    """The speculative reseed pool must leave `random` exactly where the reference would (one randint for :41)."""
+    st = synthetic.make_stream(90, 2, 64, seed=8, C=4)
+    f3 = st.features.view(90, 2, 64).to(dev)
+    random.seed(123)
+    expect_first = random.randint(0, 89)
+    expect_next = random.random()
+    random.seed(123)
+    torch.manual_seed(5)
+    _, _, _, info = kmeans_with_time_min_max(f3, st.timestamps.to(dev), 6, return_info=True)
+    assert int(info.init_indices[0]) == expect_first
+    if info.n_reseed_used == 0:
+        assert random.random() == expect_next
+
+
+def test_kmeans_torch_rng_stream_matches_reference_on_device(dev):
+    """Unseeded-injection mode: the oracle (= the reference's torch calls) run ON THE GPU with the same seeds must
+    pick the same centres, i.e. our pre-drawn Exp(1) rows are the draws torch.multinomial makes on this device."""
+    T, P, D, k = 120, 2, 64, 9
+    st = synthetic.make_stream(T, P, D, seed=9, C=4)
+    f3 = st.features.view(T, P, D).to(dev)
+    ts = st.timestamps.to(dev)
+    random.seed(77); torch.manual_seed(77)
+    info_o = orc.KMeansInfo()
+    _, _, assign_o = orc.kmeans_with_time_min_max(f3, ts, k, info=info_o)
+    tail_o = torch.rand(4, device=dev)
+    random.seed(77); torch.manual_seed(77)
+    _, _, assign, info = kmeans_with_time_min_max(f3, ts, k, return_info=True)
+    tail = torch.rand(4, device=dev)
+    assert info.init_indices.tolist() == info_o.init_indices
+    assert torch.equal(assign, assign_o)
+    assert torch.equal(tail, tail_o), "CUDA generator not left in the state the reference would leave it in"
+
+
+# ----------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", golden_names())
+def test_selection_mask_compaction_golden(dev, name):
+    g = load_golden(name)
+    s = g["spec"]
+    T, P, D, k = s["T"], s["P"], s["D"], s["k"]
+    feats = g["features"].to(dev)
+    f3 = feats.view(T, P, D)
+    assign = g["assignments"].to(dev)
+    # representatives, drop-in signature (streams x against the given centroids)
+    reps = select_additional_frames(f3, g["centroids"].to(dev), assign, 2)
+    assert len(reps) == k and all(torch.equal(a.cpu(), b) for a, b in zip(reps, g["representatives"]))
+    # Gram-based distances give the same representatives
+    order, off = ops.event_order(assign, k)
+    dist = ops.dist_to_assigned_gram(ops.gram(f3.view(T, -1)), assign, off, order, k)
+    r2, c2, flags = ops.select_representatives(dist, assign, k, 2)
+    assert all(torch.equal(r2[i, : int(c2[i])].cpu(), g["representatives"][i]) for i in range(k))
+    # cosine flags
+    cos, low = ops.cosine_flags(g["question"][0].to(dev), g["events_repr"].to(dev), 0.45)
+    assert torch.equal(cos.cpu(), g["cos"])
+    assert torch.equal(torch.nonzero(low.cpu())[:, 0], g["low_events"])
+    mflags, mlist, nm = ops.minor_frames(assign, low, flags)
+    minor = mlist[: int(nm)].tolist()
+    assert minor == g["minor"]
+    stub = _Stub()
+    pooled = stub.compress_unimportant_events(feats, P, minor)
+    assert torch.equal(feats.cpu(), g["features"]), "input must not be modified"
+    if minor:
+        assert_bf16_close(pooled.view(T, P, D)[minor, 0, :], g["pooled_minor_tokens"])
+    keep_rows = torch.ones(T * P, dtype=torch.bool)
+    keep_rows[[m * P for m in minor]] = False
+    assert torch.equal(pooled.cpu()[keep_rows], g["features"][keep_rows])
+    npat = g["grid_sizes"].prod(dim=1).div(g["merge_sizes"] ** 2).long()
+    mask = stub._get_compression_mask(g["pixel_values"].to(dev), npat.to(dev), g["grid_sizes"].to(dev), g["merge_sizes"].to(dev),
+                                      ["video"], minor_frame_indices=minor)
+    assert mask.dtype == torch.bool and torch.equal(mask.cpu(), g["mask"])
+    pos = torch.arange(g["input_ids"].numel(), device=dev)
+    labels = torch.where(g["input_ids"] == synthetic.IMAGE_TOKEN_INDEX, torch.full_like(g["input_ids"], -100), g["input_ids"]).to(dev)
+    f2, ids2, am2, pos2, lab2 = stub._compress_visual_tokens(mask, pooled, g["input_ids"].to(dev), g["attention_mask"].to(dev),
+                                                             pos, labels)
+    assert torch.equal(ids2.cpu(), g["out_input_ids"]) and torch.equal(am2.cpu(), g["out_attention_mask"])
+    assert torch.equal(pos2.cpu(), g["out_position_ids"]) and torch.equal(lab2.cpu(), g["out_labels"])
+    assert_bf16_close(f2, g["out_features"])
+
+
+def test_mask_edge_cases(dev, edge_cases):
+    e = edge_cases["mask_mixed"]
+    stub = _Stub()
+    npat = e["grid_sizes"].prod(dim=1).div(e["merge_sizes"] ** 2).long()
+    mk = stub._get_compression_mask(e["pixel_values"].to(dev), npat, e["grid_sizes"], e["merge_sizes"], e["modals"],
+                                    minor_frame_indices=e["minor"])
+    assert torch.equal(mk.cpu(), e["mask"])
+    with pytest.raises(TypeError):
+        stub._get_compression_mask(e["pixel_values"].to(dev), npat, e["grid_sizes"], e["merge_sizes"], e["modals"])
+    # fp32 pixels take the fp32 arithmetic path
+    pix32 = e["pixel_values"].float()
+    want = orc.get_compression_mask(pix32, npat, e["grid_sizes"], e["merge_sizes"], e["modals"], minor_frame_indices=e["minor"])
+    got = stub._get_compression_mask(pix32.to(dev), npat, e["grid_sizes"], e["merge_sizes"], e["modals"], minor_frame_indices=e["minor"])
+    assert torch.equal(got.cpu(), want)
+
+
+def test_pool_norm(dev):
+    st = synthetic.make_stream(50, 7, 1152, seed=4, C=4)
+    x = st.features.view(50, 7, 1152).to(dev)
+    pb, pf, sq = ops.pool_norm(x, want_f32=True)
+    ref = st.features.view(50, 7, 1152)
+    assert_bf16_close(pb, ref.mean(dim=1))
+    assert rel_err(pf, ref.float().mean(dim=1)) < 1e-6
+    assert rel_err(sq, ref.double().pow(2).sum(dim=(1, 2))) < 1e-6
+    G = ops.gram(x.view(50, -1))
+    assert rel_err(G.diagonal(), ref.double().pow(2).sum(dim=(1, 2))) < 1e-6
+
+
+# ----------------------------------------------------------------------------------------------------
+CASES = [  # T, P, D, k, seed, iid  -- sizes the oracle finishes in seconds
+    (300, 16, 1152, None, 21, False),
+    (240, 9, 3584, None, 22, False),
+    (64, 180, 1152, 8, 23, False),   # BASELINE config 1 shape (k=8 as SURVEY 8d prescribes)
+    (150, 27, 1152, 10, 24, False),
+    (200, 8, 1152, 32, 25, True),
+    (600, 7, 1152, 8, 26, False),    # sweep corner: few large events
+    (600, 2, 1152, 128, 27, False),  # sweep corner: many small events
+]
+
+
+@pytest.mark.parametrize("T,P,D,k,seed,iid", CASES)
+def test_pipeline_vs_oracle(dev, T, P, D, k, seed, iid):
+    st = synthetic.make_stream(T, P, D, seed, C=48, iid=iid, near_threshold_frac=0.05)
+    kk = k if k is not None else math.ceil(T / 15)
+    ev, q = synthetic.make_embeddings(kk, 3584, seed)
+    g = torch.Generator().manual_seed(seed)
+    init = torch.randperm(T, generator=g)[:kk]
+    cfg = StreamConfig(cluster_num=k)
+    pool = torch.randint(0, T, (64,), generator=g)  # empty-cluster re-seeds (kmeans_with_time.py:118), same for both
+    p1 = orc.phase1(st.features, T, st.timestamps, cluster_num=k, init_indices=init.tolist(), reseed_indices=pool.tolist())
+    px = orc.phase1(st.features, T, st.timestamps, cluster_num=k, init_indices=init.tolist(), reseed_indices=pool.tolist(),
+                    exact=True)
+    assert torch.equal(px.assignments, p1.assignments), "test case is decided by the reference's own fp32 rounding noise"
+    p2 = orc.phase2(st.features, p1, ev, q, st.pixel_values, st.grid_sizes, st.merge_sizes, st.modals, st.input_ids,
+                    synthetic.IMAGE_TOKEN_INDEX, st.attention_mask)
+    W = st.pixel_values.numel() // (T * P)
+    sc = StreamCompressor(T, P, D, W, st.input_ids.numel(), device=dev, cfg=cfg)
+    d = st.to(dev)
+    sc.phase1(d.features, d.timestamps, init_indices=init.to(dev), reseed_pool=pool.to(dev))
+    sc.phase2(d.features, ev.to(dev), q.to(dev), d.pixel_values, d.input_ids, d.attention_mask)
+    r = sc.results()
+    assert r["status"]["n_reseed_used"] == len(p1.info.reseed_indices)
+    print(f"T={T} k={kk} reseeds={r['status']['n_reseed_used']} iters={r['status']['iterations']}/{p1.info.iterations} margin gpu {r['status']['min_margin']:.2e} "
+          f"cpu {p1.info.min_margin:.2e} minor={len(r['minor'])} kept={r['n_kept']}")
+    assert torch.equal(r["assignments"].cpu(), p1.assignments)
+    assert r["status"]["iterations"] == p1.info.iterations and r["status"]["converged"] == p1.info.converged
+    assert torch.equal(r["centroid_times"].cpu(), p1.centroid_times)
+    assert rel_err(r["centroids"], p1.centroids) < REL_TOL
+    assert all(torch.equal(a.cpu(), b) for a, b in zip(r["representatives"], p1.representatives))
+    assert torch.equal(torch.nonzero(r["low_flags"].cpu())[:, 0], p2.low_events) and torch.equal(r["cos"].cpu(), p2.cos)
+    assert r["minor"] == p2.minor
+    assert torch.equal(r["mask"].cpu(), p2.mask)
+    assert torch.equal(r["input_ids"].cpu(), p2.input_ids) and torch.equal(r["attention_mask"].cpu(), p2.attention_mask)
+    assert_bf16_close(r["features"], p2.features)
+    # chronological per-event gather (cogreasoner_chat.py:291-296)
+    off = r["event_offsets"].tolist()
+    packed = r["packed_events"].view(T, P, D).cpu()
+    for i in (0, kk // 2, kk - 1):
+        assert torch.equal(packed[off[i]: off[i + 1]].reshape(-1, D), p1.events[i])
+
+
+def test_pipeline_gate_closed(dev):
+    """T <= 135: no event compression, only the pixel-difference mask (cogreasoner_chat.py:281-282)."""
+    T, P, D = 60, 6, 128
+    st = synthetic.make_stream(T, P, D, 31, C=24)
+    p2 = orc.phase2(st.features, None, None, None, st.pixel_values, st.grid_sizes, st.merge_sizes, st.modals, st.input_ids,
+                    synthetic.IMAGE_TOKEN_INDEX, st.attention_mask)
+    sc = StreamCompressor(T, P, D, st.pixel_values.numel() // (T * P), st.input_ids.numel(), device=dev)
+    assert not sc.gate
+    d = st.to(dev)
+    sc.phase1(d.features, d.timestamps)
+    sc.phase2(d.features, None, None, d.pixel_values, d.input_ids, d.attention_mask)
+    r = sc.results()
+    assert r["minor"] == [] and torch.equal(r["mask"].cpu(), p2.mask) and torch.equal(r["features"].cpu(), p2.features)
+
+
+def test_drop_in_select_events_with_stub_llm(dev):
+    """select_events_based_on_summary end to end with a canned 'LLM' (cogreasoner_chat.py:278-333)."""
+    T, P, D = 150, 4, 64
+    st = synthetic.make_stream(T, P, D, 41, C=8)
+    k = math.ceil(T / 15)
+    ev, q = synthetic.make_embeddings(k, D, 41)
+
+    class FakeTok:
+        def __call__(self, text, **kw):
+            n_img = text.count("<image>")
+            ids = [7] * 3 + [synthetic.IMAGE_TOKEN_INDEX] * n_img + [9] * 2
+            return {"input_ids": torch.tensor([ids]), "attention_mask": torch.ones(1, len(ids), dtype=torch.long)}
+
+    class FakeLLM(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.embed_tokens = torch.nn.Embedding(synthetic.IMAGE_TOKEN_INDEX + 1, D).to(torch.bfloat16)
+            self.calls = 0
+
+        def forward(self, input_ids=None, position_ids=None, attention_mask=None, inputs_embeds=None):
+            import types
+            if inputs_embeds is not None:
+                h = ev[self.calls].to(inputs_embeds.device).view(1, 1, -1).expand(1, inputs_embeds.shape[1], -1)
+                self.calls += 1
+            else:
+                h = q.to(input_ids.device).view(1, 1, -1).expand(1, input_ids.shape[1], -1)
+            return types.SimpleNamespace(last_hidden_state=h)
+
+    def run(cls_base, device, km_kw):
+        llm = FakeLLM().to(device)
+
+        class M(cls_base):
+            config = _Stub.config
+            tokenizer = FakeTok()
+            current_question = "what happened?"
+
+            def get_model(self):
+                return llm
+
+        return M(), llm
+
+    # oracle side: same list logic on CPU with the same canned embeddings and an injected init
+    random.seed(5); torch.manual_seed(5)
+    model, llm = run(VisualStreamCompressionMixin, dev, {})
+    minor = model.select_events_based_on_summary(st.features.to(dev), T, st.timestamps.to(dev))
+    assert llm.calls == k and isinstance(minor, list) and all(isinstance(i, int) for i in minor)
+    assert minor == sorted(minor) and len(set(minor)) == len(minor) and all(0 <= i < T for i in minor)
+    # the run is deterministic given the seeds
+    random.seed(5); torch.manual_seed(5)
+    model2, _ = run(VisualStreamCompressionMixin, dev, {})
+    assert model2.select_events_based_on_summary(st.features.to(dev), T, st.timestamps.to(dev)) == minor
+    # gate: T=120 -> k=8 <= 9 -> []
+    assert model.select_events_based_on_summary(st.features[: 120 * P].to(dev), 120, st.timestamps[:120].to(dev)) == []
