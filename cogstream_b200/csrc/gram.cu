@@ -15,10 +15,12 @@ namespace csb {
 
 constexpr int kTile = 128;       // output tile edge
 constexpr int kChunk = 64;       // K elements per pipeline stage (128 bytes = one swizzle atom)
-constexpr int kMaxSlots = 5;     // distinct 128-row blocks resident per stage
+constexpr int kMaxSlots = 4;     // distinct 128-row blocks resident per stage
 constexpr int kMaxMma = 4;       // output tiles (TMEM 128-column groups) per CTA
-constexpr int kStages = 2;
+constexpr int kMaxStages = 8;
 constexpr int kBlockBytes = kTile * kChunk * 2;  // 16 KB
+constexpr int kStageBudget = 200 * 1024;         // shared memory spent on pipeline stages
+constexpr int kMaxParamUnits = 16;               // unit tables up to this size travel as a kernel parameter
 
 struct GramUnit {
   int n_slots;
@@ -29,60 +31,112 @@ struct GramUnit {
   int tile_id[kMaxMma];       // upper-triangular tile id (for the partial buffer)
 };
 
+struct GramUnitTable {
+  GramUnit u[kMaxParamUnits];
+};
+
 struct GramPlan {
   int nb;        // 128-row blocks
   int n_tiles;   // nb*(nb+1)/2
   int n_units;
   int n_kr;      // K ranges
   int n_chunks;  // ceil(K / 64)
+  int max_slots; // largest number of resident blocks any unit needs
+  int n_stages;  // pipeline depth that fits the shared-memory budget
 };
 
 static inline int tri_id(int bi, int bj, int nb) { return bi * nb - bi * (bi - 1) / 2 + (bj - bi); }
 
-// Pack the upper-triangular tiles into units of <= 4 tiles touching <= 5 distinct row blocks.
-static void plan_units(int nb, GramUnit* units, int* n_units) {
-  int n = 0;
-  GramUnit cur;
-  memset(&cur, 0, sizeof(cur));
-  auto flush = [&]() {
-    if (cur.n_tiles) {
-      if (units) units[n] = cur;
-      ++n;
-      memset(&cur, 0, sizeof(cur));
-    }
+// Pack the upper-triangular tiles into units of <= 4 tiles touching <= 4 distinct row blocks (fewer
+// resident blocks per stage = deeper TMA pipeline and less L2 traffic).  Small problems: greedy "seed +
+// the tile that adds the fewest new blocks"; large ones: 2x2 super-blocks (4 tiles / 4 blocks off the
+// diagonal, 3 tiles / 2 blocks on it).  T=600 (5 blocks, 15 tiles) packs into 4 units of 3 blocks each.
+static void unit_add(GramUnit& u, int bi, int bj, int nb) {
+  auto slot = [&](int blk) {
+    for (int s = 0; s < u.n_slots; ++s)
+      if (u.slot_block[s] == blk) return s;
+    u.slot_block[u.n_slots] = blk;
+    return u.n_slots++;
   };
-  auto slot_of = [&](int blk, bool add) -> int {
-    for (int s = 0; s < cur.n_slots; ++s)
-      if (cur.slot_block[s] == blk) return s;
-    if (!add || cur.n_slots == kMaxSlots) return -1;
-    cur.slot_block[cur.n_slots] = blk;
-    return cur.n_slots++;
-  };
-  for (int bi = 0; bi < nb; ++bi) {
-    for (int bj = bi; bj < nb; ++bj) {
-      int need = (slot_of(bi, false) < 0) + ((bj != bi) && slot_of(bj, false) < 0);
-      if (cur.n_tiles == kMaxMma || cur.n_slots + need > kMaxSlots) flush();
-      const int sa = slot_of(bi, true), sb = slot_of(bj, true);
-      cur.a_slot[cur.n_tiles] = sa;
-      cur.b_slot[cur.n_tiles] = sb;
-      cur.tile_id[cur.n_tiles] = tri_id(bi, bj, nb);
-      ++cur.n_tiles;
-    }
+  const int sa = slot(bi), sb = slot(bj);
+  u.a_slot[u.n_tiles] = sa;
+  u.b_slot[u.n_tiles] = sb;
+  u.tile_id[u.n_tiles] = tri_id(bi, bj, nb);
+  ++u.n_tiles;
+}
+
+static int unit_new_blocks(const GramUnit& u, int bi, int bj) {
+  bool ha = false, hb = false;
+  for (int s = 0; s < u.n_slots; ++s) {
+    ha |= u.slot_block[s] == bi;
+    hb |= u.slot_block[s] == bj;
   }
-  flush();
+  return (ha ? 0 : 1) + ((hb || bj == bi) ? 0 : 1);
+}
+
+static void plan_units(int nb, GramUnit* units, int* n_units, int* max_slots) {
+  int n = 0, ms = 0;
+  auto emit = [&](const GramUnit& u) {
+    if (units) units[n] = u;
+    ++n;
+    if (u.n_slots > ms) ms = u.n_slots;
+  };
+  if (nb <= 16) {
+    const int nt = nb * (nb + 1) / 2;
+    int tb[136][2];
+    bool done[136];
+    int c = 0;
+    for (int bi = 0; bi < nb; ++bi)
+      for (int bj = bi; bj < nb; ++bj) { tb[c][0] = bi; tb[c][1] = bj; done[c] = false; ++c; }
+    for (int seed = 0; seed < nt; ++seed) {
+      if (done[seed]) continue;
+      GramUnit u;
+      memset(&u, 0, sizeof(u));
+      unit_add(u, tb[seed][0], tb[seed][1], nb);
+      done[seed] = true;
+      while (u.n_tiles < kMaxMma) {
+        int best = -1, best_new = 99;
+        for (int t = 0; t < nt; ++t) {
+          if (done[t]) continue;
+          const int nw = unit_new_blocks(u, tb[t][0], tb[t][1]);
+          if (u.n_slots + nw <= kMaxSlots && nw < best_new) { best = t; best_new = nw; }
+        }
+        if (best < 0) break;
+        unit_add(u, tb[best][0], tb[best][1], nb);
+        done[best] = true;
+      }
+      emit(u);
+    }
+  } else {
+    const int ns = (nb + 1) / 2;
+    for (int I = 0; I < ns; ++I)
+      for (int J = I; J < ns; ++J) {
+        GramUnit u;
+        memset(&u, 0, sizeof(u));
+        for (int bi = 2 * I; bi < 2 * I + 2 && bi < nb; ++bi)
+          for (int bj = 2 * J; bj < 2 * J + 2 && bj < nb; ++bj)
+            if (bi <= bj) unit_add(u, bi, bj, nb);
+        if (u.n_tiles) emit(u);
+      }
+  }
   *n_units = n;
+  if (max_slots) *max_slots = ms;
 }
 
 static GramPlan make_plan(int64_t T, int64_t K) {
   GramPlan p;
   p.nb = (int)((T + kTile - 1) / kTile);
   p.n_tiles = p.nb * (p.nb + 1) / 2;
-  plan_units(p.nb, nullptr, &p.n_units);
+  plan_units(p.nb, nullptr, &p.n_units, &p.max_slots);
   p.n_chunks = (int)((K + kChunk - 1) / kChunk);
   int kr = kNumSMs / p.n_units;
   if (kr < 1) kr = 1;
   if (kr > p.n_chunks) kr = p.n_chunks;
   p.n_kr = kr;
+  int st = kStageBudget / (p.max_slots * kBlockBytes);
+  if (st > kMaxStages) st = kMaxStages;
+  if (st < 2) st = 2;
+  p.n_stages = st;
   return p;
 }
 
@@ -140,19 +194,37 @@ __global__ void __launch_bounds__(256) gram_simt_kernel(const __nv_bfloat16* __r
 // ---------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) gram_reduce_kernel(const float* __restrict__ partial, int T, int nb, int n_tiles,
                                                           int n_kr, double* __restrict__ G) {
+  // grid (n_tiles, 16): a thread owns 4 consecutive columns of one tile row; the K ranges are streamed with 8
+  // independent 128-bit loads in flight and added in ascending range order (fixed -> deterministic).
   int tid = blockIdx.x, bi = 0;
   while (tid >= nb - bi) { tid -= nb - bi; ++bi; }
   const int bj = bi + tid;
-  const float* base = partial + (int64_t)blockIdx.x * (kTile * kTile);
-  const int64_t kr_stride = (int64_t)n_tiles * kTile * kTile;
-  for (int e = threadIdx.x + blockIdx.y * 256; e < kTile * kTile; e += 256 * gridDim.y) {
-    const int r = e >> 7, c = e & 127;
-    const int gi = bi * kTile + r, gj = bj * kTile + c;
-    if (gi >= T || gj >= T) continue;
-    double s = 0.0;
-    for (int kr = 0; kr < n_kr; ++kr) s += (double)base[(int64_t)kr * kr_stride + e];
-    G[(int64_t)gi * T + gj] = s;
-    if (bi != bj) G[(int64_t)gj * T + gi] = s;
+  const int e4 = blockIdx.y * 256 + threadIdx.x;  // float4 index inside the tile, 4096 per tile
+  const int r = e4 >> 5, c = (e4 & 31) * 4;
+  const int gi = bi * kTile + r, gj = bj * kTile + c;
+  if (gi >= T || gj >= T) return;
+  const float4* base = reinterpret_cast<const float4*>(partial + (int64_t)blockIdx.x * (kTile * kTile)) + e4;
+  const int64_t kr_stride4 = (int64_t)n_tiles * kTile * kTile / 4;
+  double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+  int kr = 0;
+  for (; kr + 8 <= n_kr; kr += 8) {
+    float4 v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) v[u] = __ldcs(base + (int64_t)(kr + u) * kr_stride4);
+#pragma unroll
+    for (int u = 0; u < 8; ++u) { s0 += (double)v[u].x; s1 += (double)v[u].y; s2 += (double)v[u].z; s3 += (double)v[u].w; }
+  }
+  for (; kr < n_kr; ++kr) {
+    const float4 v = __ldcs(base + (int64_t)kr * kr_stride4);
+    s0 += (double)v.x; s1 += (double)v.y; s2 += (double)v.z; s3 += (double)v.w;
+  }
+  const double sv[4] = {s0, s1, s2, s3};
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    if (gj + u < T) {
+      G[(int64_t)gi * T + gj + u] = sv[u];
+      if (bi != bj) G[(int64_t)(gj + u) * T + gi] = sv[u];
+    }
   }
 }
 
@@ -233,19 +305,21 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
 }
 
 struct __align__(8) GramSmemCtl {
-  uint64_t full[kStages];
-  uint64_t empty[kStages];
+  uint64_t full[kMaxStages];
+  uint64_t empty[kMaxStages];
   uint64_t accum_done;
   uint32_t tmem_base;
 };
 
 __global__ void __launch_bounds__(128, 1) gram_tc_kernel(const __grid_constant__ CUtensorMap xmap,
+                                                         const __grid_constant__ GramUnitTable ptable,
                                                          const GramUnit* __restrict__ units, int n_tiles, int n_kr,
-                                                         int n_chunks, float* __restrict__ partial) {
+                                                         int n_chunks, int kStages, int stage_bytes,
+                                                         float* __restrict__ partial) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // stage buffers first (1024-byte aligned for SWIZZLE_128B), control block after
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  GramSmemCtl* ctl = reinterpret_cast<GramSmemCtl*>(smem + (size_t)kStages * kMaxSlots * kBlockBytes);
+  GramSmemCtl* ctl = reinterpret_cast<GramSmemCtl*>(smem + (size_t)kStages * stage_bytes);
   __shared__ GramUnit unit;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -253,7 +327,7 @@ __global__ void __launch_bounds__(128, 1) gram_tc_kernel(const __grid_constant__
   const int c0 = (int)((int64_t)kr * n_chunks / n_kr), c1 = (int)((int64_t)(kr + 1) * n_chunks / n_kr);
   const int nchunk = c1 - c0;
 
-  if (threadIdx.x == 0) unit = units[blockIdx.x];
+  if (threadIdx.x == 0) unit = units ? units[blockIdx.x] : ptable.u[blockIdx.x];
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < kStages; ++s) {
       ptx::mbar_init(&ctl->full[s], 1);
@@ -280,7 +354,7 @@ __global__ void __launch_bounds__(128, 1) gram_tc_kernel(const __grid_constant__
       const uint32_t ph = (uint32_t)(c / kStages) & 1u;
       ptx::mbar_wait(&ctl->empty[s], ph ^ 1u);
       ptx::mbar_expect_tx(&ctl->full[s], (uint32_t)(n_slots * kBlockBytes));
-      uint8_t* stage = smem + (size_t)s * kMaxSlots * kBlockBytes;
+      uint8_t* stage = smem + (size_t)s * stage_bytes;
       for (int q = 0; q < n_slots; ++q)
         ptx::tma_load_2d(stage + (size_t)q * kBlockBytes, &xmap, &ctl->full[s], (c0 + c) * kChunk, unit.slot_block[q] * kTile);
     }
@@ -292,7 +366,7 @@ __global__ void __launch_bounds__(128, 1) gram_tc_kernel(const __grid_constant__
       const uint32_t ph = (uint32_t)(c / kStages) & 1u;
       ptx::mbar_wait(&ctl->full[s], ph);
       ptx::tc_fence_after();
-      const uint32_t stage = ptx::smem_u32(smem + (size_t)s * kMaxSlots * kBlockBytes);
+      const uint32_t stage = ptx::smem_u32(smem + (size_t)s * stage_bytes);
       for (int t = 0; t < n_ut; ++t) {
         const uint32_t a_addr = stage + (uint32_t)unit.a_slot[t] * kBlockBytes;
         const uint32_t b_addr = stage + (uint32_t)unit.b_slot[t] * kBlockBytes;
@@ -346,7 +420,6 @@ static PFN_encodeTiled get_encode_fn() {
 }
 
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
-constexpr size_t kGramSmemBytes = (size_t)kStages * kMaxSlots * kBlockBytes + sizeof(GramSmemCtl) + 1024;
 
 }  // namespace csb
 
@@ -390,18 +463,27 @@ int csb_gram(const void* x, int64_t T, int64_t K, double* G, void* workspace, si
     int kr_simt = (2 * kNumSMs + p.n_tiles - 1) / p.n_tiles;
     if (kr_simt > p.n_chunks) kr_simt = p.n_chunks;
     const int kr_max = kr_simt > p.n_kr ? kr_simt : p.n_kr;
-    GramUnit* d_units = reinterpret_cast<GramUnit*>(reinterpret_cast<char*>(workspace) +
-                                                    align_up((size_t)kr_max * p.n_tiles * kTile * kTile * sizeof(float), 256));
-    // unit table: tiny, rebuilt per call from the shape (pageable host copy is stream ordered and synchronous w.r.t. the host buffer)
-    static thread_local GramUnit h_units_small[64];
-    GramUnit* h_units = h_units_small;
-    GramUnit* heap = nullptr;
-    if (p.n_units > 64) { heap = (GramUnit*)malloc(sizeof(GramUnit) * p.n_units); h_units = heap; }
-    int n_units = 0;
-    plan_units(p.nb, h_units, &n_units);
-    cudaError_t e = cudaMemcpyAsync(d_units, h_units, sizeof(GramUnit) * n_units, cudaMemcpyHostToDevice, s);
-    if (heap) { cudaStreamSynchronize(s); free(heap); }
-    if (e != cudaSuccess) { set_error("gram: unit table copy: %s", cudaGetErrorString(e)); return CSB_ERR_CUDA; }
+    GramUnit* d_units = nullptr;
+    static thread_local GramUnitTable table;  // plan for small problems, passed by value
+    cudaError_t e = cudaSuccess;
+    if (p.n_units <= kMaxParamUnits) {
+      static thread_local int table_nb = -1;
+      if (table_nb != p.nb) {
+        int nu = 0;
+        plan_units(p.nb, table.u, &nu, nullptr);
+        table_nb = p.nb;
+      }
+    } else {
+      d_units = reinterpret_cast<GramUnit*>(reinterpret_cast<char*>(workspace) +
+                                            align_up((size_t)kr_max * p.n_tiles * kTile * kTile * sizeof(float), 256));
+      GramUnit* h_units = (GramUnit*)malloc(sizeof(GramUnit) * p.n_units);
+      int nu = 0;
+      plan_units(p.nb, h_units, &nu, nullptr);
+      e = cudaMemcpyAsync(d_units, h_units, sizeof(GramUnit) * nu, cudaMemcpyHostToDevice, s);
+      cudaStreamSynchronize(s);  // pageable source buffer is freed below (large-T path only)
+      free(h_units);
+      if (e != cudaSuccess) { set_error("gram: unit table copy: %s", cudaGetErrorString(e)); return CSB_ERR_CUDA; }
+    }
 
     PFN_encodeTiled enc = get_encode_fn();
     if (!enc) { set_error("gram: cuTensorMapEncodeTiled unavailable"); return CSB_ERR_CUDA; }
@@ -414,17 +496,19 @@ int csb_gram(const void* x, int64_t T, int64_t K, double* G, void* workspace, si
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("gram: cuTensorMapEncodeTiled failed (%d)", (int)r); return CSB_ERR_CUDA; }
-    e = cudaFuncSetAttribute(gram_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGramSmemBytes);
+    const int stage_bytes = p.max_slots * kBlockBytes;
+    const size_t smem_bytes = (size_t)p.n_stages * stage_bytes + sizeof(GramSmemCtl) + 1024;
+    e = cudaFuncSetAttribute(gram_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
     if (e != cudaSuccess) { set_error("gram: smem attr: %s", cudaGetErrorString(e)); return CSB_ERR_CUDA; }
     dim3 grid((unsigned)p.n_units, (unsigned)n_kr);
-    gram_tc_kernel<<<grid, 128, kGramSmemBytes, s>>>(map, d_units, p.n_tiles, n_kr, p.n_chunks, partial);
+    gram_tc_kernel<<<grid, 128, smem_bytes, s>>>(map, table, d_units, p.n_tiles, n_kr, p.n_chunks, p.n_stages, stage_bytes, partial);
     int st = check_launch("gram_tc");
     if (st) return st;
   } else {
     set_error("gram: unknown impl %d", impl);
     return CSB_ERR_ARG;
   }
-  dim3 rgrid((unsigned)p.n_tiles, 8);
+  dim3 rgrid((unsigned)p.n_tiles, 16);
   gram_reduce_kernel<<<rgrid, 256, 0, s>>>(partial, (int)T, p.nb, p.n_tiles, n_kr, G);
   return check_launch("gram_reduce");
 }

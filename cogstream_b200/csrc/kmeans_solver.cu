@@ -10,8 +10,10 @@
 // [T, P*D] features 2*I + k - 1 times.  All sums are fp64 in a fixed order: deterministic, and
 // unchanged memberships give a centre shift of exactly 0, as in the reference.
 //
-// Grid: nb co-resident CTAs (cooperative launch) separated by a software grid barrier; the init and
-// the (tiny, order-sensitive) membership rebuild run on CTA 0, distances / assignment / S on all CTAs.
+// Grid: nb co-resident CTAs (cooperative launch) separated by a software grid barrier (2 per Lloyd
+// iteration).  k-means++ runs on CTA 0; in the loop every CTA rebuilds the membership CSR in its own
+// shared memory (identical by construction), so only the assignments and the S columns cross CTAs.
+// Columns of S are recomputed only for clusters whose membership changed (version stamps per buffer).
 #include "csb_common.cuh"
 
 namespace csb {
@@ -32,13 +34,13 @@ struct SolverArgs {
   int32_t* members;
   csb_kmeans_status* status;
   // workspace
-  float* nearest;     // [T]
+  double* diag;       // [T] Gram diagonal, compact copy
   double* S[2];       // [T,k]
-  double* ct[2];      // [k]
-  int32_t* offs[2];   // [k+1]
-  int32_t* memb[2];   // [T+k]
   unsigned* barrier;  // zeroed before launch
-  int32_t* used;      // reseeds consumed so far (zeroed)
+  int32_t* used;      // reseed-pool entries consumed by the init (written by CTA 0)
+  unsigned long long* tl;  // phase timeline (globaltimer ns), [0] = entries written; profiling aid
+  int diag_in_smem;   // 1: keep a shared-memory copy of the diagonal (T small enough)
+  int multiwarp_fill; // 1: per-warp cluster counters fit in shared memory
 };
 
 __device__ __forceinline__ void grid_sync(unsigned* counter, unsigned& target, unsigned nblocks) {
@@ -57,233 +59,340 @@ __device__ __forceinline__ void grid_sync(unsigned* counter, unsigned& target, u
   }
 }
 
+constexpr int kTimelineMax = 440;
+__device__ __forceinline__ void mark(const SolverArgs& a, int tag) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    const unsigned long long n = a.tl[0];
+    if (n < kTimelineMax) {
+      a.tl[1 + n] = (t << 8) | (unsigned long long)(tag & 0xff);
+      a.tl[0] = n + 1;
+    }
+  }
+}
+
 template <typename TS>
 __device__ __forceinline__ TS load_ts(const void* ts, int i) {
   return reinterpret_cast<const TS*>(ts)[i];
 }
 
-// ---- block-wide argmax with lowest-index tie break (scratch: 32 floats + 32 ints) ---------------
-__device__ __forceinline__ int block_argmax(float v, int idx, float* sv, int* si) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = (blockDim.x + 31) >> 5;
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    float ov = __shfl_xor_sync(0xffffffffu, v, o);
-    int oi = __shfl_xor_sync(0xffffffffu, idx, o);
-    if (ov > v || (ov == v && oi < idx)) { v = ov; idx = oi; }
-  }
-  __syncthreads();
-  if (lane == 0) { sv[warp] = v; si[warp] = idx; }
-  __syncthreads();
-  v = lane < nwarp ? sv[lane] : -1.f;
-  idx = lane < nwarp ? si[lane] : 0x7fffffff;
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    float ov = __shfl_xor_sync(0xffffffffu, v, o);
-    int oi = __shfl_xor_sync(0xffffffffu, idx, o);
-    if (ov > v || (ov == v && oi < idx)) { v = ov; idx = oi; }
-  }
-  return idx;
-}
+constexpr int kSolverThreads = 256;
+constexpr int kSolverWarps = kSolverThreads / 32;
 
 // ---- k-means++ on feature distance, CTA 0 only (kmeans_with_time.py:44-62) ------------------------
 // Sampling round: probs = nearest^2 / sum (:53-59), centre = argmax(probs / Exp(1) noise) -- the noise
 // rows are consumed one per SAMPLING round, like the torch generator in the reference.  A round whose
 // probs sum to 0 (:55-57) takes the next entry of the host-drawn random.randint pool instead.
-__device__ void kmeanspp_block(const SolverArgs& a, float* sf, int* si, int* n_noise_used, int* n_degenerate) {
+// Two block barriers and one L2 round trip (row c of G) per round: every warp forms the full sum itself
+// (same order in every warp), warps reduce their slice of the scores, 8 partial winners meet in smem.
+__device__ void kmeanspp_block(const SolverArgs& a, float* s_near, const double* diag, float* s_wv, int* s_wi, int* used_io,
+                               int* n_noise_used, int* n_degenerate) {
   const int T = a.T, k = a.k;
   const double* G = a.G;
-  __shared__ int s_pick;
-  for (int i = threadIdx.x; i < T; i += blockDim.x) a.nearest[i] = __int_as_float(0x7f800000);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int i = threadIdx.x; i < T; i += blockDim.x) s_near[i] = __int_as_float(0x7f800000);
   __syncthreads();
-  int noise_row = 0, degenerate = 0;
+  int noise_row = 0, degenerate = 0, used = *used_io;
   for (int m = 0; m < k; ++m) {
     int c;
     if (m < a.n_init_given) {
       c = (int)a.init_indices[m];
     } else {
       float part = 0.f;
-      for (int i = threadIdx.x; i < T; i += blockDim.x) {
-        const float nd = a.nearest[i];
-        part += __fmul_rn(nd, nd);
+      for (int i = lane; i < T; i += 32) {
+        const float nd = s_near[i];
+        part += __fmul_rn(nd, nd);  // :53
       }
-      const float sum = block_sum<float>(part, sf);
-      if (sum == 0.f) {
+      const float sum = warp_sum(part);  // :54 (identical in every warp)
+      if (sum == 0.f) {                  // :55-57
         ++degenerate;
-        if (threadIdx.x == 0) {
-          int used = *a.used, r = 0;
-          if (used < a.n_reseed_pool) r = (int)a.reseed_pool[used];
-          else a.status->reseed_overflow = 1;
-          *a.used = used + 1;
-          s_pick = r;
-        }
-        __syncthreads();
-        c = s_pick;
-        __syncthreads();
+        c = 0;
+        if (used < a.n_reseed_pool) c = (int)a.reseed_pool[used];
+        else if (threadIdx.x == 0) a.status->reseed_overflow = 1;
+        ++used;
       } else {
         const float* noise = a.exp_noise + (int64_t)noise_row * T;
         ++noise_row;
         float best = -1.f;
         int besti = 0x7fffffff;
         for (int i = threadIdx.x; i < T; i += blockDim.x) {
-          const float nd = a.nearest[i];
+          const float nd = s_near[i];
           const float p = __fdiv_rn(__fmul_rn(nd, nd), sum);  // :59
-          const float s = __fdiv_rn(p, noise[i]);              // multinomial: argmax(p / Exp(1))
-          if (s > best) { best = s; besti = i; }
+          const float sc = __fdiv_rn(p, __ldg(noise + i));     // multinomial: argmax(p / Exp(1)), first max
+          if (sc > best) { best = sc; besti = i; }
         }
-        c = block_argmax(best, besti, sf, si);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+          const int oi = __shfl_xor_sync(0xffffffffu, besti, o);
+          if (ov > best || (ov == best && oi < besti)) { best = ov; besti = oi; }
+        }
+        if (lane == 0) { s_wv[warp] = best; s_wi[warp] = besti; }
+        __syncthreads();
+        best = s_wv[0];
+        besti = s_wi[0];
+#pragma unroll
+        for (int w = 1; w < kSolverWarps; ++w) {
+          const float ov = s_wv[w];
+          const int oi = s_wi[w];
+          if (ov > best || (ov == best && oi < besti)) { best = ov; besti = oi; }
+        }
+        c = besti;
       }
       if (threadIdx.x == 0) a.init_indices[m] = c;
     }
-    if (m + 1 < k && a.n_init_given < k) {
-      const double gcc = G[(int64_t)c * T + c];
+    if (m + 1 < k) {
+      const double gcc = diag[c];
+      const double* gc = G + (int64_t)c * T;
       for (int i = threadIdx.x; i < T; i += blockDim.x) {
-        double d2 = G[(int64_t)i * T + i] + gcc - 2.0 * G[(int64_t)c * T + i];
-        float d = (float)sqrt(d2 > 0.0 ? d2 : 0.0);
-        a.nearest[i] = fminf(a.nearest[i], d);
+        const double d2 = diag[i] + gcc - 2.0 * gc[i];
+        const float d = (float)sqrt(d2 > 0.0 ? d2 : 0.0);
+        s_near[i] = fminf(s_near[i], d);
       }
       __syncthreads();
     }
   }
+  *used_io = used;
   *n_noise_used = noise_row;
   *n_degenerate = degenerate;
 }
 
-// ---- membership CSR from assignments, CTA 0 only (kmeans_with_time.py:110-120) --------------------
-// A warp owns a cluster: it sweeps the assignments 32 at a time, so members come out ascending.
-// Empty clusters take the next frame of the reseed pool (ascending cluster order, as :118 draws them).
+// ---- membership CSR in shared memory from the new assignments (kmeans_with_time.py:110-120) ---------
+// Every CTA builds its own copy (identical by construction).  Before the old CSR is overwritten it is used
+// to flag the clusters whose membership changed.  Stable fill (members ascending): each warp owns a
+// contiguous range of frames and ranks them with match.any on top of per-warp cluster counters; a single
+// warp does the whole range when those counters would not fit.  Empty clusters take the next frame of the
+// reseed pool in ascending cluster order (:118).
+struct MemberSmem {
+  int* assign;   // [T] new assignments
+  int* offs;     // [k+1]
+  int* memb;     // [T+k]
+  int* cursor;   // [k+1] scratch
+  int* cntw;     // [kSolverWarps][k] per-warp counters (multiwarp_fill) or [k]
+  int* changed;  // [k]
+  double* ct_new;
+};
+
 template <typename TS>
-__device__ void rebuild_members(const SolverArgs& a, const int64_t* assign, int32_t* offs, int32_t* memb, double* ct,
-                                int* s_cnt /* smem [k+1] */) {
+__device__ void rebuild_members_smem(const SolverArgs& a, const MemberSmem& m, int* used_io, bool force_all) {
   const int T = a.T, k = a.k;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
-  for (int j = warp; j < k; j += nwarp) {
-    int cnt = 0;
-    for (int i0 = 0; i0 < T; i0 += 32) {
-      const int i = i0 + lane;
-      const bool hit = i < T && (int)__ldcg(assign + i) == j;
-      cnt += __popc(__ballot_sync(0xffffffffu, hit));
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nw = a.multiwarp_fill ? kSolverWarps : 1;
+  // (1) changed flags from the OLD CSR vs the new assignments; zero the counters
+  // (the initial CSR lists only the k seed frames, so the first iteration treats every cluster as changed)
+  for (int j = threadIdx.x; j < k; j += blockDim.x) m.changed[j] = force_all ? 1 : 0;
+  for (int e = threadIdx.x; e < nw * k; e += blockDim.x) m.cntw[e] = 0;
+  __syncthreads();
+  for (int j = warp; j < k; j += kSolverWarps) {
+    const int beg = m.offs[j], end = m.offs[j + 1];
+    for (int e = beg + lane; e < end; e += 32) {
+      const int c = m.assign[m.memb[e]];
+      if (c != j) { m.changed[j] = 1; m.changed[c] = 1; }
     }
-    if (lane == 0) s_cnt[j] = cnt;
+  }
+  // (2) per-warp, per-cluster counts over the warp's frame range
+  const int range = ((T + nw - 1) / nw + 31) & ~31;
+  const int r0 = warp * range, r1 = min(T, r0 + range);
+  if (warp < nw) {
+    int* cw = m.cntw + warp * k;
+    for (int i0 = r0; i0 < r1; i0 += 32) {
+      const int i = i0 + lane;
+      const int c = i < r1 ? m.assign[i] : -1 - lane;
+      const unsigned peers = __match_any_sync(0xffffffffu, c);
+      if (i < r1 && (peers & ((1u << lane) - 1u)) == 0) cw[c] += __popc(peers);
+      __syncwarp();
+    }
   }
   __syncthreads();
-  if (threadIdx.x == 0) {
-    int used = *a.used, run = 0;
-    for (int j = 0; j < k; ++j) {
-      const int c = s_cnt[j];
-      offs[j] = run;
+  // (3) totals and exclusive per-warp bases
+  for (int j = threadIdx.x; j < k; j += blockDim.x) {
+    int run = 0;
+    for (int w = 0; w < nw; ++w) {
+      const int c = m.cntw[w * k + j];
+      m.cntw[w * k + j] = run;
+      run += c;
+    }
+    m.cursor[j] = run;  // member count of cluster j
+  }
+  __syncthreads();
+  // (4) offsets + re-seeds: warp 0, each lane owns a contiguous slice of clusters (exclusive warp scans of the
+  //     slot counts and of the number of empty clusters, so empties take pool entries in ascending cluster order)
+  int used = *used_io;
+  if (warp == 0) {
+    const int cpl = (k + 31) / 32;
+    const int j0 = min(k, lane * cpl), j1 = min(k, j0 + cpl);
+    int slots = 0, empties = 0;
+    for (int j = j0; j < j1; ++j) {
+      const int c = m.cursor[j];
+      slots += c > 0 ? c : 1;
+      empties += c == 0;
+    }
+    int s_inc = slots, e_inc = empties;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int vs = __shfl_up_sync(0xffffffffu, s_inc, o), ve = __shfl_up_sync(0xffffffffu, e_inc, o);
+      if (lane >= o) { s_inc += vs; e_inc += ve; }
+    }
+    int run = s_inc - slots, u = used + (e_inc - empties);
+    for (int j = j0; j < j1; ++j) {
+      const int c = m.cursor[j];
+      m.offs[j] = run;
       if (c == 0) {
         int r = 0;
-        if (used < a.n_reseed_pool) r = (int)a.reseed_pool[used];
+        if (u < a.n_reseed_pool) r = (int)a.reseed_pool[u];
         else a.status->reseed_overflow = 1;
-        ++used;
-        memb[run] = r;
-        ct[j] = (double)load_ts<TS>(a.ts, r);
+        ++u;
+        m.memb[run] = r;
+        m.changed[j] = 1;  // the centre jumps to a freshly drawn frame
         run += 1;
       } else {
         run += c;
       }
     }
-    offs[k] = run;
-    *a.used = used;
-  }
-  __syncthreads();
-  for (int j = warp; j < k; j += nwarp) {
-    if (s_cnt[j] == 0) continue;
-    int pos = offs[j];
-    TS tsum = TS(0);
-    for (int i0 = 0; i0 < T; i0 += 32) {
-      const int i = i0 + lane;
-      const bool hit = i < T && (int)__ldcg(assign + i) == j;
-      const unsigned bal = __ballot_sync(0xffffffffu, hit);
-      if (hit) memb[pos + __popc(bal & ((1u << lane) - 1u))] = i;
-      pos += __popc(bal);
-      // ascending sequential sum of member timestamps (:115)
-      unsigned b = bal;
-      while (b) {
-        const int l = __ffs(b) - 1;
-        b &= b - 1;
-        tsum += load_ts<TS>(a.ts, i0 + l);
-      }
+    if (lane == 31) {
+      m.offs[k] = s_inc;
+      m.cursor[k] = used + e_inc;
     }
-    if (lane == 0) ct[j] = (double)(TS)(tsum / (TS)s_cnt[j]);
   }
   __syncthreads();
+  used = m.cursor[k];
+  // (5) stable fill
+  if (warp < nw) {
+    int* cw = m.cntw + warp * k;
+    for (int i0 = r0; i0 < r1; i0 += 32) {
+      const int i = i0 + lane;
+      const int c = i < r1 ? m.assign[i] : -1 - lane;
+      const unsigned peers = __match_any_sync(0xffffffffu, c);
+      if (i < r1) {
+        const int rank = __popc(peers & ((1u << lane) - 1u));
+        const int base = cw[c];
+        m.memb[m.offs[c] + base + rank] = i;
+        __syncwarp(peers);
+        if (rank == 0) cw[c] = base + __popc(peers);
+      }
+      __syncwarp();
+    }
+  }
+  __syncthreads();
+  // (6) centre times (:115 mean of member timestamps ascending; :120 a seed alone gives ts[r])
+  for (int j = threadIdx.x; j < k; j += blockDim.x) {
+    const int beg = m.offs[j], end = m.offs[j + 1];
+    TS tsum = TS(0);
+    for (int e = beg; e < end; ++e) tsum += load_ts<TS>(a.ts, m.memb[e]);
+    m.ct_new[j] = (double)(TS)(tsum / (TS)(end - beg));
+  }
+  __syncthreads();
+  *used_io = used;
 }
 
-// S[i][j] = sum_{m in M_j} G[i][m]   (all CTAs)
-__device__ void compute_S(const SolverArgs& a, const int32_t* offs, const int32_t* memb, double* S) {
+// S[i][j] = sum_{m in M_j} G[i][m] for the listed columns j (all CTAs; column fastest so the stores coalesce)
+__device__ void compute_S(const SolverArgs& a, const int* s_offs, const int* s_memb, const int* cols, int ncols, double* S) {
   const int T = a.T, k = a.k;
-  const int64_t total = (int64_t)T * k;
+  const int64_t total = (int64_t)T * ncols;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += stride) {
-    const int i = (int)(idx / k), j = (int)(idx - (int64_t)i * k);
-    const int beg = __ldcg(offs + j), end = __ldcg(offs + j + 1);
+    const int i = (int)(idx / ncols);
+    const int j = cols[(int)(idx - (int64_t)i * ncols)];
+    const int beg = s_offs[j], end = s_offs[j + 1];
     const double* g = a.G + (int64_t)i * T;
     double s = 0.0;
-    for (int m = beg; m < end; ++m) s += g[__ldcg(memb + m)];
-    S[idx] = s;
+    int e = beg;
+    for (; e + 4 <= end; e += 4) {
+      const double g0 = __ldg(g + s_memb[e]), g1 = __ldg(g + s_memb[e + 1]), g2 = __ldg(g + s_memb[e + 2]),
+                   g3 = __ldg(g + s_memb[e + 3]);
+      s += g0; s += g1; s += g2; s += g3;
+    }
+    for (; e < end; ++e) s += __ldg(g + s_memb[e]);
+    S[(int64_t)i * k + j] = s;
   }
 }
 
 template <typename TS>
-__global__ void __launch_bounds__(256) kmeans_solver_kernel(SolverArgs a) {
+__global__ void __launch_bounds__(kSolverThreads) kmeans_solver_kernel(SolverArgs a) {
   extern __shared__ double smem_d[];
   const int T = a.T, k = a.k;
+  // doubles: q[2][k], ct[2][k], rn[k] (1/n), nn[k] (n), red[32], [diag[T]]
   double* s_q[2] = {smem_d, smem_d + k};
-  double* s_ct = smem_d + 2 * k;
-  double* s_n = smem_d + 3 * k;
-  double* s_red = smem_d + 4 * k;               // 32
-  int* s_cnt = reinterpret_cast<int*>(s_red + 32);  // k+1
-  __shared__ float sf[32];
-  __shared__ int si[32];
-  __shared__ int s_flag;
+  double* s_ctb[2] = {smem_d + 2 * k, smem_d + 3 * k};
+  double* s_rn = smem_d + 4 * k;
+  double* s_nn = smem_d + 5 * k;
+  double* s_red = smem_d + 6 * k;
+  double* s_diag = s_red + 32;
+  // ints: assign[T], offs[k+1], cursor[k+1], memb[T+k], changed[k], ver[k], verbuf[2][k], cols[k], cntw[nw*k]
+  int* s_assign = reinterpret_cast<int*>(s_diag + (a.diag_in_smem ? T : 0));
+  int* s_offs = s_assign + T;
+  int* s_cursor = s_offs + (k + 1);
+  int* s_memb = s_cursor + (k + 1);
+  int* s_changed = s_memb + (T + k);
+  int* s_ver = s_changed + k;
+  int* s_verbuf[2] = {s_ver + k, s_ver + 2 * k};
+  int* s_cols = s_ver + 3 * k;
+  int* s_cntw = s_cols + k;
+  float* s_near = reinterpret_cast<float*>(s_assign);  // [T], k-means++ only (CTA 0, before s_assign is used)
+  __shared__ float s_wv[kSolverWarps];
+  __shared__ int s_wi[kSolverWarps];
+  __shared__ int s_ncols;
 
   unsigned bar = 0;
   const unsigned nb = gridDim.x;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   csb_kmeans_status* st = a.status;
+  int used = 0;
+  const double* diag = a.diag_in_smem ? s_diag : a.diag;
 
-  // ---------------- init ----------------
+  // ---------------- init: k-means++ on CTA 0, the others wait at the barrier ----------------
   if (blockIdx.x == 0) {
     if (threadIdx.x == 0) {
       st->iterations = 0; st->converged = 0; st->n_reseed_used = 0; st->degenerate_rounds = 0;
       st->reseed_overflow = 0; st->n_noise_used = 0; st->min_margin = __int_as_float(0x7f800000); st->last_shift = 0.f;
     }
-    int n_noise = 0, n_deg = 0;
-    if (a.n_init_given < k) kmeanspp_block(a, sf, si, &n_noise, &n_deg);
-    if (threadIdx.x == 0) { st->n_noise_used = n_noise; st->degenerate_rounds = n_deg; }
+    mark(a, 1);
+    for (int i = threadIdx.x; i < T; i += blockDim.x) {
+      const double g = a.G[(int64_t)i * T + i];
+      a.diag[i] = g;
+      if (a.diag_in_smem) s_diag[i] = g;
+    }
     __syncthreads();
-    for (int j = threadIdx.x; j < k; j += blockDim.x) {
-      const int c = (int)a.init_indices[j];
-      a.offs[0][j] = j;
-      a.memb[0][j] = c;
-      a.ct[0][j] = (double)load_ts<TS>(a.ts, c);  // :66
+    int n_noise = 0, n_deg = 0;
+    if (a.n_init_given < k) kmeanspp_block(a, s_near, diag, s_wv, s_wi, &used, &n_noise, &n_deg);
+    if (threadIdx.x == 0) {
+      st->degenerate_rounds = n_deg;
+      st->n_noise_used = n_noise;
+      *a.used = used;  // pool entries consumed by degenerate rounds
     }
-    if (threadIdx.x == 0) a.offs[0][k] = k;
+    __syncthreads();
   }
+  mark(a, 2);
   grid_sync(a.barrier, bar, nb);
-  compute_S(a, a.offs[0], a.memb[0], a.S[0]);
-  grid_sync(a.barrier, bar, nb);
-
-  // q for the initial centres (every CTA keeps its own copy in smem)
-  int cur = 0;
-  {
-    const int32_t* offs = a.offs[cur];
-    const int32_t* memb = a.memb[cur];
-    for (int j = threadIdx.x; j < k; j += blockDim.x) {
-      const int beg = __ldcg(offs + j), end = __ldcg(offs + j + 1);
-      double s = 0.0;
-      for (int m = beg; m < end; ++m) s += __ldcg(a.S[cur] + (int64_t)__ldcg(memb + m) * k + j);
-      const double n = (double)(end - beg);
-      s_q[cur][j] = s / (n * n);
-      s_n[j] = n;
-      s_ct[j] = __ldcg(a.ct[cur] + j);
-    }
+  used = __ldcg(a.used);
+  if (blockIdx.x != 0 && a.diag_in_smem)
+    for (int i = threadIdx.x; i < T; i += blockDim.x) s_diag[i] = __ldcg(a.diag + i);
+  // initial centres: cluster j = { init[j] }
+  for (int j = threadIdx.x; j < k; j += blockDim.x) {
+    const int c = (int)__ldcg(a.init_indices + j);
+    s_offs[j] = j;
+    s_memb[j] = c;
+    s_ctb[0][j] = (double)load_ts<TS>(a.ts, c);  // :66
+    s_q[0][j] = __ldcg(a.diag + c);
+    s_rn[j] = 1.0;
+    s_nn[j] = 1.0;
+    s_ver[j] = 1;
+    s_verbuf[0][j] = 1;
+    s_verbuf[1][j] = 0;
+    s_cols[j] = j;
   }
+  if (threadIdx.x == 0) s_offs[k] = k;
   __syncthreads();
+  compute_S(a, s_offs, s_memb, s_cols, k, a.S[0]);
+  grid_sync(a.barrier, bar, nb);
+  mark(a, 3);
+
+  MemberSmem ms;
+  ms.assign = s_assign; ms.offs = s_offs; ms.memb = s_memb; ms.cursor = s_cursor; ms.cntw = s_cntw; ms.changed = s_changed;
 
   const TS alpha = (TS)a.alpha;
-  int it = 0;
+  int cur = 0, it = 0;
   bool converged = false;
   float last_shift = 0.f;
   float my_margin = __int_as_float(0x7f800000);
@@ -291,15 +400,31 @@ __global__ void __launch_bounds__(256) kmeans_solver_kernel(SolverArgs a) {
     ++it;
     // ---------- distances + assignment (:73-104), a warp per frame ----------
     const double* S = a.S[cur];
-    for (int i = blockIdx.x * nwarp + warp; i < T; i += nb * nwarp) {
-      const double gii = a.G[(int64_t)i * T + i];
+    const double* q = s_q[cur];
+    const double* ctc = s_ctb[cur];
+    for (int i = blockIdx.x * kSolverWarps + warp; i < T; i += nb * kSolverWarps) {
+      const double gii = diag[i];
       const TS ti = load_ts<TS>(a.ts, i);
       float fmin_ = __int_as_float(0x7f800000), fmax_ = -fmin_;
       TS tmin_ = (TS)__int_as_float(0x7f800000), tmax_ = -tmin_;
-      for (int j = lane; j < k; j += 32) {
-        double d2 = gii - 2.0 * (__ldcg(S + (int64_t)i * k + j) / s_n[j]) + s_q[cur][j];
+      float dc[4];
+      TS tc[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int j = lane + 32 * u;
+        if (j < k) {
+          const double d2 = gii - 2.0 * (__ldcg(S + (int64_t)i * k + j) * s_rn[j]) + q[j];
+          dc[u] = (float)sqrt(d2 > 0.0 ? d2 : 0.0);
+          TS dt = ti - (TS)ctc[j];
+          tc[u] = dt < TS(0) ? -dt : dt;
+          fmin_ = fminf(fmin_, dc[u]); fmax_ = fmaxf(fmax_, dc[u]);
+          tmin_ = tc[u] < tmin_ ? tc[u] : tmin_; tmax_ = tc[u] > tmax_ ? tc[u] : tmax_;
+        }
+      }
+      for (int j = lane + 128; j < k; j += 32) {
+        const double d2 = gii - 2.0 * (__ldcg(S + (int64_t)i * k + j) * s_rn[j]) + q[j];
         const float d = (float)sqrt(d2 > 0.0 ? d2 : 0.0);
-        TS dt = ti - (TS)s_ct[j];
+        TS dt = ti - (TS)ctc[j];
         dt = dt < TS(0) ? -dt : dt;
         fmin_ = fminf(fmin_, d); fmax_ = fmaxf(fmax_, d);
         tmin_ = dt < tmin_ ? dt : tmin_; tmax_ = dt > tmax_ ? dt : tmax_;
@@ -310,11 +435,7 @@ __global__ void __launch_bounds__(256) kmeans_solver_kernel(SolverArgs a) {
       const TS tspread = tmax_ - tmin_;
       float best = __int_as_float(0x7f800000), second = best;
       int bestj = 0x7fffffff;
-      for (int j = lane; j < k; j += 32) {
-        double d2 = gii - 2.0 * (__ldcg(S + (int64_t)i * k + j) / s_n[j]) + s_q[cur][j];
-        const float d = (float)sqrt(d2 > 0.0 ? d2 : 0.0);
-        TS dt = ti - (TS)s_ct[j];
-        dt = dt < TS(0) ? -dt : dt;
+      auto consider = [&](float d, TS dt, int j) {
         const float nf = (fmax_ > fmin_) ? __fdiv_rn(__fsub_rn(d, fmin_), fspread) : 0.f;  // :86-91
         const TS nt = (tmax_ > tmin_) ? (dt - tmin_) / tspread : TS(0);                        // :94-99
         float fin;                                                                               // :101
@@ -327,6 +448,18 @@ __global__ void __launch_bounds__(256) kmeans_solver_kernel(SolverArgs a) {
         }
         if (fin < best) { second = best; best = fin; bestj = j; }
         else if (fin < second) second = fin;
+      };
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int j = lane + 32 * u;
+        if (j < k) consider(dc[u], tc[u], j);
+      }
+      for (int j = lane + 128; j < k; j += 32) {
+        const double d2 = gii - 2.0 * (__ldcg(S + (int64_t)i * k + j) * s_rn[j]) + q[j];
+        const float d = (float)sqrt(d2 > 0.0 ? d2 : 0.0);
+        TS dt = ti - (TS)ctc[j];
+        dt = dt < TS(0) ? -dt : dt;
+        consider(d, dt, j);
       }
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) {
@@ -342,51 +475,80 @@ __global__ void __launch_bounds__(256) kmeans_solver_kernel(SolverArgs a) {
         if (k > 1) my_margin = fminf(my_margin, second - best);
       }
     }
+    mark(a, 10);
     grid_sync(a.barrier, bar, nb);
+    mark(a, 11);
 
-    // ---------- new centres: membership, times, re-seeds (CTA 0) ----------
+    // ---------- new centres: every CTA rebuilds the membership in its own shared memory ----------
     const int nxt = cur ^ 1;
-    if (blockIdx.x == 0) rebuild_members<TS>(a, a.assignments, a.offs[nxt], a.memb[nxt], a.ct[nxt], s_cnt);
+    for (int i = threadIdx.x; i < T; i += blockDim.x) s_assign[i] = (int)__ldcg(a.assignments + i);
+    __syncthreads();
+    ms.ct_new = s_ctb[nxt];
+    rebuild_members_smem<TS>(a, ms, &used, it == 1);
+    // version stamps: a changed cluster gets a new version; a column of S[nxt] is recomputed iff it is stale
+    if (warp == 0) {
+      int nc = 0;
+      for (int j0 = 0; j0 < k; j0 += 32) {
+        const int j = j0 + lane;
+        bool stale = false;
+        if (j < k) {
+          if (s_changed[j]) s_ver[j] += 1;
+          stale = s_verbuf[nxt][j] != s_ver[j];
+          if (stale) s_verbuf[nxt][j] = s_ver[j];
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, stale);
+        if (stale) s_cols[nc + __popc(bal & ((1u << lane) - 1u))] = j;
+        nc += __popc(bal);
+      }
+      if (lane == 0) s_ncols = nc;
+    }
+    __syncthreads();
+    mark(a, 12);
+    compute_S(a, s_offs, s_memb, s_cols, s_ncols, a.S[nxt]);
+    mark(a, 13);
     grid_sync(a.barrier, bar, nb);
-    compute_S(a, a.offs[nxt], a.memb[nxt], a.S[nxt]);
-    grid_sync(a.barrier, bar, nb);
+    mark(a, 14);
 
     // ---------- centre shift (:123-125); every CTA evaluates it identically ----------
+    // Only changed clusters move.  Lane e of the warp owning cluster j sums member e, e+32, ... of column j of the
+    // new and the old S (fixed order => an unchanged list would reproduce the same bits: shift exactly 0).
     double part = 0.0;
-    {
-      const int32_t* offs = a.offs[nxt];
-      const int32_t* memb = a.memb[nxt];
-      for (int j = threadIdx.x; j < k; j += blockDim.x) {
-        const int beg = __ldcg(offs + j), end = __ldcg(offs + j + 1);
-        double sn = 0.0, sc = 0.0;
-        for (int m = beg; m < end; ++m) {
-          const int64_t row = (int64_t)__ldcg(memb + m) * k + j;
-          sn += __ldcg(a.S[nxt] + row);
-          sc += __ldcg(a.S[cur] + row);
-        }
+    for (int j = warp; j < k; j += kSolverWarps) {
+      if (!s_changed[j]) {
+        if (lane == 0) s_q[nxt][j] = s_q[cur][j];
+        continue;
+      }
+      const int beg = s_offs[j], end = s_offs[j + 1];
+      double sn = 0.0, sc = 0.0;
+      for (int e = beg + lane; e < end; e += 32) {
+        const int64_t row = (int64_t)s_memb[e] * k + j;
+        const double vn = __ldcg(a.S[nxt] + row), vc = __ldcg(a.S[cur] + row);
+        sn += vn;
+        sc += vc;
+      }
+      sn = warp_sum(sn);
+      sc = warp_sum(sc);
+      if (lane == 0) {
         const double n = (double)(end - beg);
         const double qn = sn / (n * n);
-        const double cross = sc / (n * s_n[j]);
-        double sh2 = (qn + s_q[cur][j]) - 2.0 * cross;
-        part += sqrt(sh2 > 0.0 ? sh2 : 0.0);
+        const double cross = sc / (n * s_nn[j]);
+        const double sh2 = (qn + s_q[cur][j]) - 2.0 * cross;
         s_q[nxt][j] = qn;
+        s_rn[j] = 1.0 / n;  // cluster j's entries are owned by this warp until the barrier below
+        s_nn[j] = n;
+        part += sqrt(sh2 > 0.0 ? sh2 : 0.0);
       }
     }
     const double shift_feat = block_sum<double>(part, s_red);
     double tpart = 0.0;
     for (int j = threadIdx.x; j < k; j += blockDim.x) {
-      const double ctn = __ldcg(a.ct[nxt] + j);
-      const TS d = (TS)ctn - (TS)s_ct[j];
+      const TS d = (TS)s_ctb[nxt][j] - (TS)s_ctb[cur][j];
       tpart += (double)(d * d);
     }
     const double shift_time = sqrt(block_sum<double>(tpart, s_red));
     __syncthreads();
-    for (int j = threadIdx.x; j < k; j += blockDim.x) {
-      s_n[j] = (double)(__ldcg(a.offs[nxt] + j + 1) - __ldcg(a.offs[nxt] + j));
-      s_ct[j] = __ldcg(a.ct[nxt] + j);
-    }
-    __syncthreads();
     cur = nxt;
+    mark(a, 15);
     const double shift = shift_feat + shift_time;
     last_shift = (float)shift;
     if (shift <= a.tol) { converged = true; break; }  // :130
@@ -396,23 +558,40 @@ __global__ void __launch_bounds__(256) kmeans_solver_kernel(SolverArgs a) {
   if (lane == 0 && my_margin < __int_as_float(0x7f800000))
     atomicMin(reinterpret_cast<unsigned*>(&st->min_margin), __float_as_uint(fmaxf(my_margin, 0.f)));
   if (blockIdx.x == 0) {
-    for (int j = threadIdx.x; j <= k; j += blockDim.x) a.member_offsets[j] = __ldcg(a.offs[cur] + j);
-    const int nmem = __ldcg(a.offs[cur] + k);
-    for (int m = threadIdx.x; m < nmem; m += blockDim.x) a.members[m] = __ldcg(a.memb[cur] + m);
+    for (int j = threadIdx.x; j <= k; j += blockDim.x) a.member_offsets[j] = s_offs[j];
+    const int nmem = s_offs[k];
+    for (int m = threadIdx.x; m < nmem; m += blockDim.x) a.members[m] = s_memb[m];
     for (int j = threadIdx.x; j < k; j += blockDim.x) {
-      if (sizeof(TS) == 8) reinterpret_cast<double*>(a.ct_out)[j] = s_ct[j];
-      else reinterpret_cast<float*>(a.ct_out)[j] = (float)s_ct[j];
+      if (sizeof(TS) == 8) reinterpret_cast<double*>(a.ct_out)[j] = s_ctb[cur][j];
+      else reinterpret_cast<float*>(a.ct_out)[j] = (float)s_ctb[cur][j];
     }
     if (threadIdx.x == 0) {
       st->iterations = it;
       st->converged = converged ? 1 : 0;
-      st->n_reseed_used = *a.used;
+      st->n_reseed_used = used;
       st->last_shift = last_shift;
     }
   }
 }
 
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+struct SolverSmemPlan {
+  int diag_in_smem, multiwarp_fill;
+  size_t bytes;
+};
+
+static SolverSmemPlan plan_smem(int64_t T, int64_t k) {
+  SolverSmemPlan p;
+  const size_t base = sizeof(double) * (6 * k + 32) + sizeof(int) * (2 * T + 8 * k + 4) + 16;
+  const size_t budget = 200 * 1024;
+  p.multiwarp_fill = (base + sizeof(int) * kSolverWarps * k <= budget) ? 1 : 0;
+  size_t b = base + sizeof(int) * (p.multiwarp_fill ? kSolverWarps : 1) * k;
+  p.diag_in_smem = (b + sizeof(double) * T <= budget) ? 1 : 0;
+  if (p.diag_in_smem) b += sizeof(double) * T;
+  p.bytes = b;
+  return p;
+}
 
 }  // namespace csb
 
@@ -423,12 +602,9 @@ extern "C" {
 size_t csb_kmeans_workspace_bytes(int64_t T, int64_t k) {
   if (T <= 0 || k <= 0) return 0;
   size_t b = 0;
-  b += align_up(sizeof(float) * T, 256);               // nearest
+  b += align_up(sizeof(double) * T, 256);              // diag
   b += 2 * align_up(sizeof(double) * T * k, 256);      // S
-  b += 2 * align_up(sizeof(double) * k, 256);          // ct
-  b += 2 * align_up(sizeof(int32_t) * (k + 1), 256);   // offs
-  b += 2 * align_up(sizeof(int32_t) * (T + k), 256);   // memb
-  b += 256;                                            // barrier + used
+  b += 4096;                                           // barrier + used + phase timeline
   return b;
 }
 
@@ -448,45 +624,47 @@ int csb_kmeans_solve(const double* G, const void* timestamps, const csb_kmeans_p
   CSB_REQUIRE(p->n_init_given == p->k || exp_noise, "kmeans_solve: exp_noise required when centres are sampled");
   CSB_REQUIRE(p->n_reseed_pool == 0 || reseed_pool, "kmeans_solve: reseed_pool is null");
   CSB_REQUIRE(p->max_iteration >= 0, "kmeans_solve: max_iteration < 0");
-  if (workspace_bytes < csb_kmeans_workspace_bytes(p->T, p->k)) {
-    set_error("kmeans_solve: workspace %zu < %zu", workspace_bytes, csb_kmeans_workspace_bytes(p->T, p->k));
+  const int64_t T = p->T, k = p->k;
+  const SolverSmemPlan sp = plan_smem(T, k);
+  CSB_REQUIRE(sp.bytes <= 225 * 1024, "kmeans_solve: T=%lld k=%lld do not fit the shared-memory membership (T <= ~25k)", (long long)T,
+              (long long)k);
+  if (workspace_bytes < csb_kmeans_workspace_bytes(T, k)) {
+    set_error("kmeans_solve: workspace %zu < %zu", workspace_bytes, csb_kmeans_workspace_bytes(T, k));
     return CSB_ERR_WORKSPACE;
   }
-  const int64_t T = p->T, k = p->k;
   SolverArgs a;
   a.G = G; a.ts = timestamps; a.T = (int)T; a.k = (int)k; a.max_iter = p->max_iteration; a.alpha = p->alpha; a.tol = p->tol;
   a.n_init_given = (int)p->n_init_given; a.n_reseed_pool = (int)p->n_reseed_pool;
   a.init_indices = init_indices; a.exp_noise = exp_noise; a.reseed_pool = reseed_pool; a.assignments = assignments;
   a.ct_out = centroid_times; a.member_offsets = member_offsets; a.members = members; a.status = status;
+  a.diag_in_smem = sp.diag_in_smem; a.multiwarp_fill = sp.multiwarp_fill;
   char* w = reinterpret_cast<char*>(workspace);
-  a.nearest = reinterpret_cast<float*>(w); w += align_up(sizeof(float) * T, 256);
+  a.diag = reinterpret_cast<double*>(w); w += align_up(sizeof(double) * T, 256);
   for (int b = 0; b < 2; ++b) { a.S[b] = reinterpret_cast<double*>(w); w += align_up(sizeof(double) * T * k, 256); }
-  for (int b = 0; b < 2; ++b) { a.ct[b] = reinterpret_cast<double*>(w); w += align_up(sizeof(double) * k, 256); }
-  for (int b = 0; b < 2; ++b) { a.offs[b] = reinterpret_cast<int32_t*>(w); w += align_up(sizeof(int32_t) * (k + 1), 256); }
-  for (int b = 0; b < 2; ++b) { a.memb[b] = reinterpret_cast<int32_t*>(w); w += align_up(sizeof(int32_t) * (T + k), 256); }
   a.barrier = reinterpret_cast<unsigned*>(w);
   a.used = reinterpret_cast<int32_t*>(w + 128);
+  a.tl = reinterpret_cast<unsigned long long*>(w + 256);
   cudaStream_t s = as_stream(stream);
-  cudaError_t e = cudaMemsetAsync(w, 0, 256, s);
+  cudaError_t e = cudaMemsetAsync(w, 0, 264, s);
   if (e != cudaSuccess) { set_error("kmeans_solve: memset: %s", cudaGetErrorString(e)); return CSB_ERR_CUDA; }
 
-  const size_t smem = sizeof(double) * (4 * k + 32) + sizeof(int) * (k + 1) + 16;
+  const size_t smem = sp.bytes;
   auto kern = (p->ts_dtype == CSB_F64) ? kmeans_solver_kernel<double> : kmeans_solver_kernel<float>;
   if (smem > 48 * 1024) {
     e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { set_error("kmeans_solve: smem attr: %s", cudaGetErrorString(e)); return CSB_ERR_CUDA; }
   }
   int per_sm = 0;
-  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, smem);
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kSolverThreads, smem);
   if (e != cudaSuccess || per_sm < 1) { set_error("kmeans_solve: occupancy query failed"); return CSB_ERR_CUDA; }
   int dev = 0, sms = kNumSMs;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  int64_t nb = (T * k + 2047) / 2048;
+  int64_t nb = (T + kSolverWarps - 1) / kSolverWarps;  // a warp per frame in the assignment phase
   if (nb > sms) nb = sms;
   if (nb < 1) nb = 1;
   void* args[] = {&a};
-  e = cudaLaunchCooperativeKernel((const void*)kern, dim3((unsigned)nb), dim3(256), args, smem, s);
+  e = cudaLaunchCooperativeKernel((const void*)kern, dim3((unsigned)nb), dim3(kSolverThreads), args, smem, s);
   if (e != cudaSuccess) { set_error("kmeans_solve: launch: %s", cudaGetErrorString(e)); return CSB_ERR_CUDA; }
   count_launch(1);
   return CSB_OK;

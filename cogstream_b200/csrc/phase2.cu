@@ -288,6 +288,60 @@ __global__ void __launch_bounds__(256) pixel_diff_kernel(const void* __restrict_
   }
 }
 
+// Fast bf16 path: a warp owns token p over a run of F consecutive frames and keeps the previous frame's row
+// in registers, so every pixel row is read from HBM once (plus 1/F for the run boundary) instead of twice.
+template <int NV>
+__global__ void __launch_bounds__(256) pixel_diff_run_kernel(const uint4* __restrict__ pix, int t, int P, int Wv, int W, int F,
+                                                             float thr_cmp, float first_val, uint8_t* __restrict__ mask) {
+  const int lane = threadIdx.x & 31;
+  const int64_t wid = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int nrun = (t + F - 1) / F;
+  if (wid >= (int64_t)nrun * P) return;
+  const int run = (int)(wid / P), p = (int)(wid - (int64_t)run * P);
+  const int f0 = run * F, f1 = min(t, f0 + F);
+  const int64_t fstride = (int64_t)P * Wv;
+  const uint4* row = pix + (int64_t)p * Wv;
+  uint4 prev[NV];
+  int f = f0;
+  if (f0 == 0) {
+    if (lane == 0) mask[p] = first_val > thr_cmp ? 1 : 0;  // :411-412
+    f = 1;
+  }
+  {
+    const uint4* src = row + (int64_t)(f - 1) * fstride;
+#pragma unroll
+    for (int u = 0; u < NV; ++u) {
+      const int v = lane + 32 * u;
+      prev[u] = v < Wv ? ldg_stream(src + v) : make_uint4(0, 0, 0, 0);
+    }
+  }
+  for (; f < f1; ++f) {
+    const uint4* src = row + (int64_t)f * fstride;
+    uint4 cur[NV];
+#pragma unroll
+    for (int u = 0; u < NV; ++u) {
+      const int v = lane + 32 * u;
+      cur[u] = v < Wv ? ldg_stream(src + v) : make_uint4(0, 0, 0, 0);
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int u = 0; u < NV; ++u) {
+      float a[8], b[8];
+      unpack8(cur[u], a);
+      unpack8(prev[u], b);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) s += fabsf(round_bf16(__fsub_rn(a[e], b[e])));
+      prev[u] = cur[u];
+    }
+    s = warp_sum(s);
+    if (lane == 0) {
+      float m = round_bf16(__fdiv_rn(s, (float)W));
+      m = round_bf16(__fmul_rn(m, 255.f));
+      mask[(int64_t)f * P + p] = m > thr_cmp ? 1 : 0;
+    }
+  }
+}
+
 // per-frame rules: min_tokens padding (:413-414) then the minor-frame override (:416-422). A warp per frame.
 __global__ void __launch_bounds__(256) mask_finalize_kernel(uint8_t* __restrict__ mask, int t, int P, int min_tokens,
                                                             const uint8_t* __restrict__ minor_flags, int64_t frame0) {
@@ -309,20 +363,78 @@ __global__ void __launch_bounds__(256) mask_finalize_kernel(uint8_t* __restrict_
 // ------------------------------------------------------------------------------------------------
 // compaction: scan (single CTA), gather kept rows, emit pooled rows for pooled frames.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024) mask_scan_kernel(const uint8_t* __restrict__ mask, int64_t n, int32_t* __restrict__ pos,
-                                                         int32_t* __restrict__ kept_index, int64_t* __restrict__ n_kept) {
-  __shared__ int wt[32];
-  __shared__ int total;
-  const int64_t per = (n + blockDim.x - 1) / blockDim.x;
-  const int64_t beg = threadIdx.x * per, end = min(n, beg + per);
-  int cnt = 0;
-  for (int64_t i = beg; i < end; ++i) cnt += mask[i] ? 1 : 0;
-  int p = block_exclusive_scan(cnt, wt, &total);
-  for (int64_t i = beg; i < end; ++i) {
-    pos[i] = p;
-    if (mask[i]) kept_index[p++] = (int32_t)i;
+// Two-level scan: a CTA owns a chunk of 1024 elements (256 threads x 4); the last CTA to finish turns the
+// chunk counts into exclusive prefixes ("last block done"), so one launch yields counts + prefixes + total.
+constexpr int kScanThreads = 256;
+constexpr int kScanItems = 4;
+constexpr int kScanChunk = kScanThreads * kScanItems;
+
+__device__ void finish_chunk_scan(int* counts, int nchunks, unsigned* ticket, int64_t* total_out, int* wt, int* stotal) {
+  __shared__ int is_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) is_last = (atomicAdd(ticket, 1u) == gridDim.x - 1) ? 1 : 0;
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  int carry = 0;
+  for (int base = 0; base < nchunks; base += blockDim.x) {
+    const int b = base + threadIdx.x;
+    const int v = b < nchunks ? __ldcg(counts + b) : 0;
+    const int ex = block_exclusive_scan(v, wt, stotal);
+    if (b < nchunks) counts[b] = carry + ex;
+    carry += *stotal;
+    __syncthreads();
   }
-  if (threadIdx.x == 0) *n_kept = total;
+  if (threadIdx.x == 0) {
+    counts[nchunks] = carry;
+    if (total_out) *total_out = carry;
+    *ticket = 0;  // ready for the next scan on this workspace
+  }
+}
+
+__global__ void __launch_bounds__(kScanThreads) mask_chunk_count_kernel(const uint8_t* __restrict__ mask, int64_t n,
+                                                                         int* __restrict__ counts, int nchunks,
+                                                                         unsigned* ticket, int64_t* __restrict__ n_kept) {
+  __shared__ int wt[32];
+  __shared__ int stotal;
+  const int64_t base = (int64_t)blockIdx.x * kScanChunk + threadIdx.x * kScanItems;
+  int cnt = 0;
+#pragma unroll
+  for (int u = 0; u < kScanItems; ++u)
+    if (base + u < n) cnt += mask[base + u] ? 1 : 0;
+  cnt = warp_sum(cnt);
+  if ((threadIdx.x & 31) == 0) wt[threadIdx.x >> 5] = cnt;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int t = 0;
+    for (int w = 0; w < kScanThreads / 32; ++w) t += wt[w];
+    counts[blockIdx.x] = t;
+  }
+  finish_chunk_scan(counts, nchunks, ticket, n_kept, wt, &stotal);
+}
+
+// positions + kept_index of this chunk (the row copy itself is csb_gather_rows: many CTAs, 4 loads in flight)
+__global__ void __launch_bounds__(kScanThreads) compact_scatter_kernel(const uint8_t* __restrict__ mask, int64_t n,
+                                                                        const int* __restrict__ prefix, int32_t* __restrict__ pos,
+                                                                        int32_t* __restrict__ kept_index) {
+  __shared__ int wt[32];
+  __shared__ int stotal;
+  const int64_t base = (int64_t)blockIdx.x * kScanChunk + threadIdx.x * kScanItems;
+  int f[kScanItems], cnt = 0;
+#pragma unroll
+  for (int u = 0; u < kScanItems; ++u) {
+    f[u] = (base + u < n && mask[base + u]) ? 1 : 0;
+    cnt += f[u];
+  }
+  int lp = prefix[blockIdx.x] + block_exclusive_scan(cnt, wt, &stotal);
+#pragma unroll
+  for (int u = 0; u < kScanItems; ++u) {
+    if (base + u < n) {
+      pos[base + u] = lp;
+      if (f[u]) kept_index[lp++] = (int32_t)(base + u);
+    }
+  }
 }
 
 __global__ void __launch_bounds__(256) pool_emit_kernel(const uint4* __restrict__ x, int P, int Dv,
@@ -336,12 +448,12 @@ __global__ void __launch_bounds__(256) pool_emit_kernel(const uint4* __restrict_
   for (int c = threadIdx.x; c < Dv; c += blockDim.x) {
     float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     int p = 0;
-    for (; p + 4 <= P; p += 4) {
-      uint4 v[4];
+    for (; p + 12 <= P; p += 12) {
+      uint4 v[12];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) v[u] = ldg_stream(xf + (int64_t)(p + u) * Dv + c);
+      for (int u = 0; u < 12; ++u) v[u] = ldg_stream(xf + (int64_t)(p + u) * Dv + c);
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < 12; ++u) {
         float f[8];
         unpack8(v[u], f);
 #pragma unroll
@@ -367,7 +479,86 @@ __global__ void __launch_bounds__(256) pool_emit_kernel(const uint4* __restrict_
 }
 
 // ------------------------------------------------------------------------------------------------
-// input-id filtering (:459-474), single CTA.  keep[i] = !is_image[i] || mask[rank_of_image(i)].
+// input-id filtering (:459-474), chunked: (1) image-token prefix, (2) keep prefix, (3) scatter.
+// keep[i] = !is_image[i] || mask[rank_of_image(i)]
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kScanThreads) ids_image_count_kernel(const int64_t* __restrict__ ids, int64_t n, int64_t image_tok,
+                                                                        int* __restrict__ counts, int nchunks, unsigned* ticket) {
+  __shared__ int wt[32];
+  __shared__ int stotal;
+  const int64_t base = (int64_t)blockIdx.x * kScanChunk + threadIdx.x * kScanItems;
+  int cnt = 0;
+#pragma unroll
+  for (int u = 0; u < kScanItems; ++u)
+    if (base + u < n) cnt += ids[base + u] == image_tok;
+  cnt = warp_sum(cnt);
+  if ((threadIdx.x & 31) == 0) wt[threadIdx.x >> 5] = cnt;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int t = 0;
+    for (int w = 0; w < kScanThreads / 32; ++w) t += wt[w];
+    counts[blockIdx.x] = t;
+  }
+  finish_chunk_scan(counts, nchunks, ticket, nullptr, wt, &stotal);
+}
+
+template <bool SCATTER>
+__global__ void __launch_bounds__(kScanThreads) ids_keep_kernel(const int64_t* __restrict__ ids, int64_t n, int64_t image_tok,
+                                                                 const uint8_t* __restrict__ mask, int64_t n_mask,
+                                                                 const int* __restrict__ img_prefix, int* __restrict__ keep_counts,
+                                                                 int nchunks, unsigned* ticket, int64_t* __restrict__ n_out,
+                                                                 const int64_t* __restrict__ attn, const int64_t* __restrict__ labels,
+                                                                 int64_t* __restrict__ o_ids, int64_t* __restrict__ o_attn,
+                                                                 int64_t* __restrict__ o_labels) {
+  __shared__ int wt[32];
+  __shared__ int stotal;
+  const int64_t base = (int64_t)blockIdx.x * kScanChunk + threadIdx.x * kScanItems;
+  int64_t v[kScanItems];
+  int img[kScanItems], icnt = 0;
+#pragma unroll
+  for (int u = 0; u < kScanItems; ++u) {
+    v[u] = base + u < n ? ids[base + u] : 0;
+    img[u] = (base + u < n && v[u] == image_tok) ? 1 : 0;
+    icnt += img[u];
+  }
+  int r = img_prefix[blockIdx.x] + block_exclusive_scan(icnt, wt, &stotal);
+  int keep[kScanItems], kcnt = 0;
+#pragma unroll
+  for (int u = 0; u < kScanItems; ++u) {
+    keep[u] = base + u < n ? 1 : 0;
+    if (img[u]) {
+      keep[u] = (r < n_mask && mask[r]) ? 1 : 0;
+      ++r;
+    }
+    kcnt += keep[u];
+  }
+  if (!SCATTER) {
+    kcnt = warp_sum(kcnt);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) wt[threadIdx.x >> 5] = kcnt;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int t = 0;
+      for (int w = 0; w < kScanThreads / 32; ++w) t += wt[w];
+      keep_counts[blockIdx.x] = t;
+    }
+    finish_chunk_scan(keep_counts, nchunks, ticket, n_out, wt, &stotal);
+  } else {
+    int p = keep_counts[blockIdx.x] + block_exclusive_scan(kcnt, wt, &stotal);
+#pragma unroll
+    for (int u = 0; u < kScanItems; ++u) {
+      if (keep[u]) {
+        o_ids[p] = v[u];
+        if (attn) o_attn[p] = attn[base + u];
+        if (labels) o_labels[p] = labels[base + u];
+        ++p;
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// input-id filtering with position-id rebuild (training-side path, rare): single CTA.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024) filter_ids_kernel(const int64_t* __restrict__ ids, int64_t n, int64_t image_tok,
                                                           const uint8_t* __restrict__ mask, int64_t n_mask,
@@ -518,7 +709,18 @@ int csb_pixel_mask(const void* pixels, int64_t t, int64_t P, int64_t W, int32_t 
     CSB_REQUIRE((W % 8 != 0) || (reinterpret_cast<uintptr_t>(pixels) & 15u) == 0, "pixel_mask: pixels not 16-byte aligned");
     const float thr = __bfloat162float(__float2bfloat16_rn((float)threshold));
     const float first = __bfloat162float(__float2bfloat16_rn((float)(threshold + 1.0)));
-    pixel_diff_kernel<true><<<blocks, 256, 0, s>>>(pixels, (int)t, (int)P, (int)W, thr, first, mask);
+    const int64_t Wv = W / 8;
+    if (false && W % 8 == 0 && Wv <= 320 && t > 1) {  // run kernel disabled: slower than the L2-reuse kernel (see profiles/)
+      const int F = t >= 64 ? 12 : (t >= 8 ? 4 : 1);
+      const int64_t nwarp = ((t + F - 1) / F) * P;
+      const unsigned rb = (unsigned)((nwarp + 7) / 8);
+      const uint4* px = (const uint4*)pixels;
+      if (Wv <= 64) pixel_diff_run_kernel<2><<<rb, 256, 0, s>>>(px, (int)t, (int)P, (int)Wv, (int)W, F, thr, first, mask);
+      else if (Wv <= 192) pixel_diff_run_kernel<6><<<rb, 256, 0, s>>>(px, (int)t, (int)P, (int)Wv, (int)W, F, thr, first, mask);
+      else pixel_diff_run_kernel<10><<<rb, 256, 0, s>>>(px, (int)t, (int)P, (int)Wv, (int)W, F, thr, first, mask);
+    } else {
+      pixel_diff_kernel<true><<<blocks, 256, 0, s>>>(pixels, (int)t, (int)P, (int)W, thr, first, mask);
+    }
   } else if (dtype == CSB_F32) {
     pixel_diff_kernel<false><<<blocks, 256, 0, s>>>(pixels, (int)t, (int)P, (int)W, (float)threshold, (float)(threshold + 1.0), mask);
   } else {
@@ -531,9 +733,13 @@ int csb_pixel_mask(const void* pixels, int64_t t, int64_t P, int64_t W, int32_t 
   return check_launch("mask_finalize");
 }
 
+// layout: [pos / seg_start : n int32][chunk counts A : nchunks+1][chunk counts B : nchunks+1][ticket : 256 B]
+static inline int64_t ws_n(int64_t n_tokens, int64_t n_ids) { const int64_t n = n_tokens > n_ids ? n_tokens : n_ids; return n > 0 ? n : 1; }
+static inline int64_t ws_chunks(int64_t n) { return (n + kScanChunk - 1) / kScanChunk; }
+
 size_t csb_compact_workspace_bytes(int64_t n_tokens, int64_t n_ids) {
-  const int64_t n = n_tokens > n_ids ? n_tokens : n_ids;
-  return align_up(sizeof(int32_t) * (size_t)(n > 0 ? n : 1), 256);
+  const int64_t n = ws_n(n_tokens, n_ids);
+  return align_up(sizeof(int32_t) * (size_t)n, 256) + 2 * align_up(sizeof(int32_t) * (size_t)(ws_chunks(n) + 1), 256) + 256;
 }
 
 int csb_compact_tokens(const void* x, int64_t T, int64_t P, int64_t D, const uint8_t* mask, const uint8_t* pool_flags, void* out,
@@ -545,9 +751,19 @@ int csb_compact_tokens(const void* x, int64_t T, int64_t P, int64_t D, const uin
   CSB_REQUIRE(n < (1ll << 31), "compact_tokens: too many tokens");
   if (workspace_bytes < csb_compact_workspace_bytes(n, 0)) { set_error("compact_tokens: workspace too small"); return CSB_ERR_WORKSPACE; }
   cudaStream_t s = as_stream(stream);
-  int32_t* pos = reinterpret_cast<int32_t*>(workspace);
-  mask_scan_kernel<<<1, 1024, 0, s>>>(mask, n, pos, kept_index, n_kept);
-  int st = check_launch("mask_scan");
+  char* w = reinterpret_cast<char*>(workspace);
+  int32_t* pos = reinterpret_cast<int32_t*>(w);
+  int* counts = reinterpret_cast<int*>(w + align_up(sizeof(int32_t) * (size_t)n, 256));
+  const int nchunks = (int)ws_chunks(n);
+  unsigned* ticket = reinterpret_cast<unsigned*>(w + align_up(sizeof(int32_t) * (size_t)n, 256) +
+                                                 2 * align_up(sizeof(int32_t) * (size_t)(nchunks + 1), 256));
+  cudaError_t e = cudaMemsetAsync(ticket, 0, 4, s);
+  if (e != cudaSuccess) { set_error("compact_tokens: memset: %s", cudaGetErrorString(e)); return CSB_ERR_CUDA; }
+  mask_chunk_count_kernel<<<nchunks, kScanThreads, 0, s>>>(mask, n, counts, nchunks, ticket, n_kept);
+  int st = check_launch("mask_chunk_count");
+  if (st) return st;
+  compact_scatter_kernel<<<nchunks, kScanThreads, 0, s>>>(mask, n, counts, pos, kept_index);
+  st = check_launch("compact_scatter");
   if (st) return st;
   st = csb_gather_rows(x, D * 2, kept_index, 0, n_kept, n, out, stream);
   if (st) return st;
@@ -570,10 +786,35 @@ int csb_filter_ids(const int64_t* input_ids, int64_t n_ids, int64_t image_token_
   CSB_REQUIRE(!labels || out_labels, "filter_ids: labels given without output");
   CSB_REQUIRE(!position_ids || (out_position_ids && workspace), "filter_ids: position_ids given without output/workspace");
   CSB_REQUIRE(n_ids < (1ll << 31), "filter_ids: too many ids");
-  if (position_ids && workspace_bytes < csb_compact_workspace_bytes(0, n_ids)) { set_error("filter_ids: workspace too small"); return CSB_ERR_WORKSPACE; }
-  filter_ids_kernel<<<1, 1024, 0, as_stream(stream)>>>(input_ids, n_ids, image_token_index, mask, n_mask, attention_mask, labels,
-                                                       position_ids, out_ids, out_attention_mask, out_labels, out_position_ids,
-                                                       n_out, reinterpret_cast<int32_t*>(workspace));
+  CSB_REQUIRE(workspace, "filter_ids: null workspace");
+  if (workspace_bytes < csb_compact_workspace_bytes(0, n_ids)) { set_error("filter_ids: workspace too small"); return CSB_ERR_WORKSPACE; }
+  cudaStream_t s = as_stream(stream);
+  if (!position_ids) {
+    const int64_t n = ws_n(0, n_ids);
+    char* w = reinterpret_cast<char*>(workspace);
+    const int nchunks = (int)ws_chunks(n_ids);
+    const size_t cbytes = align_up(sizeof(int32_t) * (size_t)(ws_chunks(n) + 1), 256);
+    int* img_prefix = reinterpret_cast<int*>(w + align_up(sizeof(int32_t) * (size_t)n, 256));
+    int* keep_prefix = reinterpret_cast<int*>(reinterpret_cast<char*>(img_prefix) + cbytes);
+    unsigned* ticket = reinterpret_cast<unsigned*>(reinterpret_cast<char*>(keep_prefix) + cbytes);
+    cudaError_t e = cudaMemsetAsync(ticket, 0, 4, s);
+    if (e != cudaSuccess) { set_error("filter_ids: memset: %s", cudaGetErrorString(e)); return CSB_ERR_CUDA; }
+    ids_image_count_kernel<<<nchunks, kScanThreads, 0, s>>>(input_ids, n_ids, image_token_index, img_prefix, nchunks, ticket);
+    int st = check_launch("ids_image_count");
+    if (st) return st;
+    ids_keep_kernel<false><<<nchunks, kScanThreads, 0, s>>>(input_ids, n_ids, image_token_index, mask, n_mask, img_prefix, keep_prefix,
+                                                            nchunks, ticket, n_out, attention_mask, labels, out_ids,
+                                                            out_attention_mask, out_labels);
+    st = check_launch("ids_keep_count");
+    if (st) return st;
+    ids_keep_kernel<true><<<nchunks, kScanThreads, 0, s>>>(input_ids, n_ids, image_token_index, mask, n_mask, img_prefix, keep_prefix,
+                                                           nchunks, ticket, n_out, attention_mask, labels, out_ids,
+                                                           out_attention_mask, out_labels);
+    return check_launch("ids_keep_scatter");
+  }
+  filter_ids_kernel<<<1, 1024, 0, s>>>(input_ids, n_ids, image_token_index, mask, n_mask, attention_mask, labels,
+                                       position_ids, out_ids, out_attention_mask, out_labels, out_position_ids,
+                                       n_out, reinterpret_cast<int32_t*>(workspace));
   return check_launch("filter_ids");
 }
 

@@ -113,6 +113,14 @@ class KMeansBuffers:
         self.status = torch.zeros(STATUS_WORDS, dtype=torch.int32, device=device)
         self.workspace = torch.empty(kmeans_workspace_bytes(T, k), dtype=torch.uint8, device=device)
 
+    def timeline(self):
+        """Phase timeline of the last solve: list of (tag, ns since the first mark); profiling aid (synchronises)."""
+        tail = self.workspace[-4096 + 256:].view(torch.int64).cpu()
+        n = int(tail[0])
+        ev = [(int(v) & 0xFF, int(v) >> 8) for v in tail[1: 1 + n].tolist()]
+        t0 = ev[0][1] if ev else 0
+        return [(tag, t - t0) for tag, t in ev]
+
 
 def kmeans_solve(G: torch.Tensor, timestamps: torch.Tensor, buf: KMeansBuffers, *, n_init_given: int,
                  exp_noise: Optional[torch.Tensor], reseed_pool: Optional[torch.Tensor], alpha: float = 2.0,
