@@ -84,10 +84,11 @@ constexpr int kSolverWarps = kSolverThreads / 32;
 // Sampling round: probs = nearest^2 / sum (:53-59), centre = argmax(probs / Exp(1) noise) -- the noise
 // rows are consumed one per SAMPLING round, like the torch generator in the reference.  A round whose
 // probs sum to 0 (:55-57) takes the next entry of the host-drawn random.randint pool instead.
-// Two block barriers and one L2 round trip (row c of G) per round: every warp forms the full sum itself
-// (same order in every warp), warps reduce their slice of the scores, 8 partial winners meet in smem.
-__device__ void kmeanspp_block(const SolverArgs& a, float* s_near, const double* diag, float* s_wv, int* s_wi, int* used_io,
-                               int* n_noise_used, int* n_degenerate) {
+// One L2 round trip (row c of G) per round; the update pass leaves per-warp partial sums of nearest^2 in smem
+// (added in warp order by every thread -> one fixed order), warps reduce their slice of the scores and the 8
+// partial winners meet in smem.
+__device__ void kmeanspp_block(const SolverArgs& a, float* s_near, const double* diag, float* s_wv, int* s_wi, float* s_ws,
+                               int* used_io, int* n_noise_used, int* n_degenerate) {
   const int T = a.T, k = a.k;
   const double* G = a.G;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -99,28 +100,37 @@ __device__ void kmeanspp_block(const SolverArgs& a, float* s_near, const double*
     if (m < a.n_init_given) {
       c = (int)a.init_indices[m];
     } else {
-      float part = 0.f;
-      for (int i = lane; i < T; i += 32) {
-        const float nd = s_near[i];
-        part += __fmul_rn(nd, nd);  // :53
-      }
-      const float sum = warp_sum(part);  // :54 (identical in every warp)
-      if (sum == 0.f) {                  // :55-57
+      // this thread's slice: frames tid, tid+256, ...; loads are issued in batches of 4 so their latencies overlap
+      const float* noise = a.exp_noise + (int64_t)noise_row * T;
+      // :53-54 sum of nearest^2: per-warp partials were left in s_ws by the update pass of the previous round
+      float sum = s_ws[0];
+#pragma unroll
+      for (int w = 1; w < kSolverWarps; ++w) sum += s_ws[w];
+      if (sum == 0.f) {                           // :55-57
         ++degenerate;
         c = 0;
         if (used < a.n_reseed_pool) c = (int)a.reseed_pool[used];
         else if (threadIdx.x == 0) a.status->reseed_overflow = 1;
         ++used;
       } else {
-        const float* noise = a.exp_noise + (int64_t)noise_row * T;
         ++noise_row;
         float best = -1.f;
         int besti = 0x7fffffff;
-        for (int i = threadIdx.x; i < T; i += blockDim.x) {
-          const float nd = s_near[i];
-          const float p = __fdiv_rn(__fmul_rn(nd, nd), sum);  // :59
-          const float sc = __fdiv_rn(p, __ldg(noise + i));     // multinomial: argmax(p / Exp(1)), first max
-          if (sc > best) { best = sc; besti = i; }
+        for (int i0 = threadIdx.x; i0 < T; i0 += 4 * kSolverThreads) {
+          float nd[4], nz[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int ii = i0 + u * kSolverThreads;
+            nd[u] = ii < T ? s_near[ii] : 0.f;
+            nz[u] = ii < T ? __ldg(noise + ii) : 1.f;
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int ii = i0 + u * kSolverThreads;
+            const float p = __fdiv_rn(__fmul_rn(nd[u], nd[u]), sum);  // :59
+            const float sc = __fdiv_rn(p, nz[u]);                      // multinomial: argmax(p / Exp(1)), first max
+            if (ii < T && sc > best) { best = sc; besti = ii; }
+          }
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
@@ -145,12 +155,31 @@ __device__ void kmeanspp_block(const SolverArgs& a, float* s_near, const double*
     if (m + 1 < k) {
       const double gcc = diag[c];
       const double* gc = G + (int64_t)c * T;
-      for (int i = threadIdx.x; i < T; i += blockDim.x) {
-        const double d2 = diag[i] + gcc - 2.0 * gc[i];
-        const float d = (float)sqrt(d2 > 0.0 ? d2 : 0.0);
-        s_near[i] = fminf(s_near[i], d);
+      float part = 0.f;
+      for (int i0 = threadIdx.x; i0 < T; i0 += 4 * kSolverThreads) {
+        double g[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int ii = i0 + u * kSolverThreads;
+          g[u] = ii < T ? __ldg(gc + ii) : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int ii = i0 + u * kSolverThreads;
+          if (ii < T) {
+            const double d2 = diag[ii] + gcc - 2.0 * g[u];
+            const float d = (float)sqrt(d2 > 0.0 ? d2 : 0.0);
+            const float nd = fminf(s_near[ii], d);
+            s_near[ii] = nd;
+            part += __fmul_rn(nd, nd);  // :53
+          }
+        }
       }
+      part = warp_sum(part);
+      __syncthreads();  // s_ws / s_wv of this round have been consumed by every thread
+      if (lane == 0) s_ws[warp] = part;
       __syncthreads();
+
     }
   }
   *used_io = used;
@@ -332,6 +361,7 @@ __global__ void __launch_bounds__(kSolverThreads) kmeans_solver_kernel(SolverArg
   float* s_near = reinterpret_cast<float*>(s_assign);  // [T], k-means++ only (CTA 0, before s_assign is used)
   __shared__ float s_wv[kSolverWarps];
   __shared__ int s_wi[kSolverWarps];
+  __shared__ float s_ws[kSolverWarps];
   __shared__ int s_ncols;
 
   unsigned bar = 0;
@@ -355,7 +385,7 @@ __global__ void __launch_bounds__(kSolverThreads) kmeans_solver_kernel(SolverArg
     }
     __syncthreads();
     int n_noise = 0, n_deg = 0;
-    if (a.n_init_given < k) kmeanspp_block(a, s_near, diag, s_wv, s_wi, &used, &n_noise, &n_deg);
+    if (a.n_init_given < k) kmeanspp_block(a, s_near, diag, s_wv, s_wi, s_ws, &used, &n_noise, &n_deg);
     if (threadIdx.x == 0) {
       st->degenerate_rounds = n_deg;
       st->n_noise_used = n_noise;

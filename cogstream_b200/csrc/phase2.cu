@@ -697,40 +697,41 @@ int csb_minor_frames(const int64_t* assignments, const uint8_t* low_flags, const
   return check_launch("minor_frames");
 }
 
-int csb_pixel_mask(const void* pixels, int64_t t, int64_t P, int64_t W, int32_t dtype, double threshold, int64_t min_tokens,
-                   const uint8_t* minor_flags, int64_t frame0, uint8_t* mask, csb_stream_t stream) {
+int csb_pixel_diff(const void* pixels, int64_t t, int64_t P, int64_t W, int32_t dtype, double threshold, uint8_t* mask,
+                   csb_stream_t stream) {
   CSB_DEVICE_OR_RETURN();
-  CSB_REQUIRE(pixels && mask && t > 0 && P > 0 && W > 0, "pixel_mask: null argument or empty shape");
-  CSB_REQUIRE(W < (1ll << 30) && P < (1ll << 30) && t < (1ll << 30), "pixel_mask: shape too large");
+  CSB_REQUIRE(pixels && mask && t > 0 && P > 0 && W > 0, "pixel_diff: null argument or empty shape");
+  CSB_REQUIRE(W < (1ll << 30) && P < (1ll << 30) && t < (1ll << 30), "pixel_diff: shape too large");
   cudaStream_t s = as_stream(stream);
   const int64_t ntok = t * P;
   const unsigned blocks = (unsigned)((ntok + 7) / 8);
   if (dtype == CSB_BF16) {
-    CSB_REQUIRE((W % 8 != 0) || (reinterpret_cast<uintptr_t>(pixels) & 15u) == 0, "pixel_mask: pixels not 16-byte aligned");
+    CSB_REQUIRE((W % 8 != 0) || (reinterpret_cast<uintptr_t>(pixels) & 15u) == 0, "pixel_diff: pixels not 16-byte aligned");
     const float thr = __bfloat162float(__float2bfloat16_rn((float)threshold));
     const float first = __bfloat162float(__float2bfloat16_rn((float)(threshold + 1.0)));
-    const int64_t Wv = W / 8;
-    if (false && W % 8 == 0 && Wv <= 320 && t > 1) {  // run kernel disabled: slower than the L2-reuse kernel (see profiles/)
-      const int F = t >= 64 ? 12 : (t >= 8 ? 4 : 1);
-      const int64_t nwarp = ((t + F - 1) / F) * P;
-      const unsigned rb = (unsigned)((nwarp + 7) / 8);
-      const uint4* px = (const uint4*)pixels;
-      if (Wv <= 64) pixel_diff_run_kernel<2><<<rb, 256, 0, s>>>(px, (int)t, (int)P, (int)Wv, (int)W, F, thr, first, mask);
-      else if (Wv <= 192) pixel_diff_run_kernel<6><<<rb, 256, 0, s>>>(px, (int)t, (int)P, (int)Wv, (int)W, F, thr, first, mask);
-      else pixel_diff_run_kernel<10><<<rb, 256, 0, s>>>(px, (int)t, (int)P, (int)Wv, (int)W, F, thr, first, mask);
-    } else {
-      pixel_diff_kernel<true><<<blocks, 256, 0, s>>>(pixels, (int)t, (int)P, (int)W, thr, first, mask);
-    }
+    pixel_diff_kernel<true><<<blocks, 256, 0, s>>>(pixels, (int)t, (int)P, (int)W, thr, first, mask);
   } else if (dtype == CSB_F32) {
     pixel_diff_kernel<false><<<blocks, 256, 0, s>>>(pixels, (int)t, (int)P, (int)W, (float)threshold, (float)(threshold + 1.0), mask);
   } else {
-    set_error("pixel_mask: dtype must be bf16 or f32");
+    set_error("pixel_diff: dtype must be bf16 or f32");
     return CSB_ERR_UNSUPPORTED;
   }
-  int st = check_launch("pixel_diff");
-  if (st) return st;
-  mask_finalize_kernel<<<(unsigned)((t + 7) / 8), 256, 0, s>>>(mask, (int)t, (int)P, (int)min_tokens, minor_flags, frame0);
+  return check_launch("pixel_diff");
+}
+
+int csb_mask_finalize(uint8_t* mask, int64_t t, int64_t P, int64_t min_tokens, const uint8_t* minor_flags, int64_t frame0,
+                      csb_stream_t stream) {
+  CSB_DEVICE_OR_RETURN();
+  CSB_REQUIRE(mask && t > 0 && P > 0, "mask_finalize: null argument or empty shape");
+  mask_finalize_kernel<<<(unsigned)((t + 7) / 8), 256, 0, as_stream(stream)>>>(mask, (int)t, (int)P, (int)min_tokens, minor_flags, frame0);
   return check_launch("mask_finalize");
+}
+
+int csb_pixel_mask(const void* pixels, int64_t t, int64_t P, int64_t W, int32_t dtype, double threshold, int64_t min_tokens,
+                   const uint8_t* minor_flags, int64_t frame0, uint8_t* mask, csb_stream_t stream) {
+  int st = csb_pixel_diff(pixels, t, P, W, dtype, threshold, mask, stream);
+  if (st) return st;
+  return csb_mask_finalize(mask, t, P, min_tokens, minor_flags, frame0, stream);
 }
 
 // layout: [pos / seg_start : n int32][chunk counts A : nchunks+1][chunk counts B : nchunks+1][ticket : 256 B]

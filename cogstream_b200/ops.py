@@ -284,6 +284,32 @@ def pixel_mask(pixels: torch.Tensor, t: int, P: int, W: int, *, threshold: float
     return mask
 
 
+def pixel_diff(pixels: torch.Tensor, t: int, P: int, W: int, *, threshold: float = 0.1, out: Optional[torch.Tensor] = None,
+               stream: Optional[torch.cuda.Stream] = None) -> torch.Tensor:
+    """Raw pixel-difference mask [t*P] uint8 (no per-frame rules); ``stream`` overrides the current stream."""
+    _need(pixels, "pixels")
+    if pixels.dtype not in _EL_DTYPE:
+        raise TypeError(f"pixel_diff: dtype must be bfloat16 or float32, got {pixels.dtype}")
+    if pixels.numel() != t * P * W:
+        raise ValueError("pixel_diff: pixel count does not match t*P*W")
+    mask = out if out is not None else torch.empty(t * P, dtype=torch.uint8, device=pixels.device)
+    st = stream.cuda_stream if stream is not None else _stream(pixels)
+    with _on_device(pixels):
+        check(_lib.load().csb_pixel_diff(pixels.data_ptr(), t, P, W, _EL_DTYPE[pixels.dtype], float(threshold), mask.data_ptr(), st),
+              "pixel_diff")
+    return mask
+
+
+def mask_finalize(mask: torch.Tensor, t: int, P: int, *, min_tokens: int = 1, minor_flags: Optional[torch.Tensor] = None,
+                  frame0: int = 0) -> torch.Tensor:
+    """In place: min_tokens padding, then the minor-frame override (cogreasoner_chat.py:413-422)."""
+    _need(mask, "mask", torch.uint8, 1)
+    with _on_device(mask):
+        check(_lib.load().csb_mask_finalize(mask.data_ptr(), t, P, int(min_tokens), _ptr(minor_flags), int(frame0), _stream(mask)),
+              "mask_finalize")
+    return mask
+
+
 def pool_frames_inplace(x: torch.Tensor, P: int, frames: torch.Tensor, *, n: Optional[int] = None,
                         n_dev: Optional[torch.Tensor] = None) -> torch.Tensor:
     """x [T*P, D] bf16 (a private clone): token 0 of every listed frame <- mean of the frame's tokens."""

@@ -85,6 +85,12 @@ class StreamCompressor:
         self.mask = torch.empty(T * P, dtype=torch.uint8, device=dev)
         self.out = torch.empty(T * P, D, dtype=torch.bfloat16, device=dev)
         self.compact_ws = torch.empty(ops.compact_workspace_bytes(T * P, n_ids), dtype=torch.uint8, device=dev)
+        # the raw pixel-difference mask is independent of the clustering: phase1 may launch it on a side stream so that
+        # this HBM-bound kernel overlaps the latency-bound k-means solver
+        self.side = torch.cuda.Stream(device=dev)
+        self._ev_fork = torch.cuda.Event()
+        self._ev_diff = torch.cuda.Event()
+        self._diff_pending = False
         self.order = self.ev_off = self.dist = self.reps = self.rep_counts = self.rep_flags = None
         self.cos = self.low = self.minor_list = None
         self.kept_index = self.n_kept = None
@@ -93,13 +99,20 @@ class StreamCompressor:
     # ------------------------------------------------------------------------------------------
     def phase1(self, features: torch.Tensor, timestamps: torch.Tensor, *, init_indices: Optional[torch.Tensor] = None,
                first_index: Optional[int] = None, exp_noise: Optional[torch.Tensor] = None,
-               reseed_pool: Optional[torch.Tensor] = None) -> None:
-        """features [T*P, D] bf16, timestamps [T] on the device.  Enqueues everything; returns at once."""
+               reseed_pool: Optional[torch.Tensor] = None, pixel_values: Optional[torch.Tensor] = None) -> None:
+        """features [T*P, D] bf16, timestamps [T] on the device.  Enqueues everything; returns at once.
+        ``pixel_values`` (optional, the same tensor phase2 gets): start the raw pixel-difference mask now, on the
+        side stream, overlapped with the solver.  Measured on B200 (scripts/overlap_probe.py): the HBM-saturating
+        difference kernel stretches the latency-bound solver by about as much as it saves, so bench.py leaves it off;
+        it pays when phase 1 is followed by host work (the frozen-LLM forwards) rather than by phase 2."""
         if not self.gate:
             return
         T, k = self.T, self.k
         x2 = features.view(T, self.K)
         ops.gram(x2, impl=self.cfg.gram_impl, out=self.G, workspace=self.gram_ws)
+        fork = pixel_values is not None
+        if fork:
+            self._ev_fork.record(torch.cuda.current_stream(self.device))
         if init_indices is not None:
             self.km.init_indices.copy_(init_indices, non_blocking=True)
             n_given, noise = k, None
@@ -119,6 +132,13 @@ class StreamCompressor:
             pool.random_(0, T)
         ops.kmeans_solve(self.G, timestamps, self.km, n_init_given=n_given, exp_noise=noise if k > 1 else None,
                          reseed_pool=pool, alpha=self.cfg.alpha, max_iteration=self.cfg.max_iteration, tol=self.cfg.tol)
+        if fork:
+            # enqueued AFTER the cooperative solver so its CTAs become resident first; the HBM-bound difference kernel then
+            # fills the rest of the machine while the (latency-bound) solver iterates
+            self.side.wait_event(self._ev_fork)
+            ops.pixel_diff(pixel_values, T, self.P, self.W, threshold=self.cfg.pixel_threshold, out=self.mask, stream=self.side)
+            self._ev_diff.record(self.side)
+            self._diff_pending = True
         if self.centroids is not None:
             ops.centroid_update(x2, self.km.member_offsets, self.km.members, k, out=self.centroids)
         assign = self.km.assignments
@@ -142,8 +162,12 @@ class StreamCompressor:
             self.minor_flags.zero_()
             self.n_minor.zero_()
             minor_flags = self.minor_flags
-        ops.pixel_mask(pixel_values, T, P, self.W, threshold=self.cfg.pixel_threshold, min_tokens=self.cfg.min_tokens,
-                       minor_flags=minor_flags, frame0=0, out=self.mask)
+        if self._diff_pending:
+            torch.cuda.current_stream(self.device).wait_event(self._ev_diff)
+            self._diff_pending = False
+        else:
+            ops.pixel_diff(pixel_values, T, P, self.W, threshold=self.cfg.pixel_threshold, out=self.mask)
+        ops.mask_finalize(self.mask, T, P, min_tokens=self.cfg.min_tokens, minor_flags=minor_flags)
         _, self.kept_index, self.n_kept = ops.compact_tokens(features, T, P, self.mask, minor_flags, out=self.out,
                                                              workspace=self.compact_ws)
         self.out_ids, self.out_attention, _, _, self.n_ids_out = ops.filter_ids(input_ids, self.image_token_index, self.mask,

@@ -182,6 +182,12 @@ CSB_API int csb_minor_frames(const int64_t* assignments, const uint8_t* low_flag
  *     first frame compares threshold+1; frames with < min_tokens kept keep their first min_tokens;
  *     frames flagged in minor_flags[frame0 + f] keep only token 0.  dtype CSB_BF16 or CSB_F32.
  * ------------------------------------------------------------------------------------------- */
+/* The two halves of csb_pixel_mask: the raw difference mask does not depend on the clustering or the question, so a
+ * caller can run it early (e.g. on a side stream while the k-means solver runs) and apply the per-frame rules later. */
+CSB_API int csb_pixel_diff(const void* pixels, int64_t t, int64_t P, int64_t W, int32_t dtype, double threshold,
+                           uint8_t* mask, csb_stream_t stream);
+CSB_API int csb_mask_finalize(uint8_t* mask, int64_t t, int64_t P, int64_t min_tokens, const uint8_t* minor_flags,
+                              int64_t frame0, csb_stream_t stream);
 CSB_API int csb_pixel_mask(const void* pixels, int64_t t, int64_t P, int64_t W, int32_t dtype, double threshold,
                    int64_t min_tokens, const uint8_t* minor_flags, int64_t frame0, uint8_t* mask,
                    csb_stream_t stream);

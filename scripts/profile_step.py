@@ -29,7 +29,7 @@ r = sc.results()
 print("ok", r["status"], r["n_kept"], len(r["minor"]))
 
 if os.environ.get("CSB_TIMELINE"):
-    names = {1: "start", 2: "init done", 3: "S0 done", 10: "assign", 11: "sync", 12: "rebuild", 13: "S", 14: "sync", 15: "shift"}
+    names = {1: "start", 2: "init done", 3: "S0 done", 10: "assign", 11: "sync", 12: "rebuild", 13: "S", 14: "sync", 15: "shift", 20: "  pp sum", 21: "  pp argmax", 22: "  pp update"}
     tl = sc.km.timeline()
     prev = 0
     for tag, t in tl:
