@@ -223,52 +223,78 @@ def run_ours(args):
     d = st.to(dev)
     ev_d, q_d = ev.to(dev), q.to(dev)
     W = st.pixel_values.numel() // (T * P)
-    sc = StreamCompressor(T, P, D, W, st.input_ids.numel(), device=dev)
     torch.manual_seed(1234 + rank)
     random.seed(1234 + rank)
-
-    def step_resident():
-        sc.phase1(d.features, d.timestamps)
-        sc.phase2(d.features, ev_d, q_d, d.pixel_values, d.input_ids, d.attention_mask)
-
-    # e2e staging buffers (device side of the H2D copies) + pinned result buffers
-    e_feat = torch.empty_like(d.features); e_pix = torch.empty_like(d.pixel_values); e_ts = torch.empty_like(d.timestamps)
-    e_ids = torch.empty_like(d.input_ids); e_am = torch.empty_like(d.attention_mask)
-    e_ev = torch.empty_like(ev_d); e_q = torch.empty_like(q_d)
-    r_stats = torch.empty(len(STATS_FIELDS), dtype=torch.int64).pin_memory()
-    r_mask = torch.empty(T * P, dtype=torch.uint8).pin_memory()
     h2d = sum(t.numel() * t.element_size() for t in (host.features, host.pixel_values, host.timestamps, host.input_ids,
                                                      host.attention_mask, ev_h, q_h))
-    d2h = r_stats.numel() * 8 + r_mask.numel()
+    d2h = len(STATS_FIELDS) * 8 + T * P
 
-    def step_e2e():
-        e_feat.copy_(host.features, non_blocking=True)
-        e_ts.copy_(host.timestamps, non_blocking=True)
-        sc.phase1(e_feat, e_ts)
-        e_pix.copy_(host.pixel_values, non_blocking=True)
-        e_ids.copy_(host.input_ids, non_blocking=True)
-        e_am.copy_(host.attention_mask, non_blocking=True)
-        e_ev.copy_(ev_h, non_blocking=True)
-        e_q.copy_(q_h, non_blocking=True)
-        sc.phase2(e_feat, e_ev, e_q, e_pix, e_ids, e_am)
-        r_stats.copy_(sc.stats_row(), non_blocking=True)
-        r_mask.copy_(sc.mask, non_blocking=True)
+    class Lane:
+        """One in-flight step: its own CUDA stream, workspaces and (for e2e) staging / pinned result buffers.  Successive
+        steps are independent streams of the workload, so `depth` of them are kept in flight (double buffering)."""
+
+        def __init__(self):
+            self.stream = torch.cuda.Stream(device=dev)
+            self.sc = StreamCompressor(T, P, D, W, st.input_ids.numel(), device=dev)
+            self.staged = False
+
+        def stage(self):
+            if self.staged:
+                return
+            self.e_feat = torch.empty_like(d.features); self.e_pix = torch.empty_like(d.pixel_values)
+            self.e_ts = torch.empty_like(d.timestamps); self.e_ids = torch.empty_like(d.input_ids)
+            self.e_am = torch.empty_like(d.attention_mask); self.e_ev = torch.empty_like(ev_d); self.e_q = torch.empty_like(q_d)
+            self.r_stats = torch.empty(len(STATS_FIELDS), dtype=torch.int64).pin_memory()
+            self.r_mask = torch.empty(T * P, dtype=torch.uint8).pin_memory()
+            self.staged = True
+
+    lanes = [Lane() for _ in range(max(1, args.depth))]
+    sc = lanes[0].sc
+
+    def step_resident(L):
+        L.sc.phase1(d.features, d.timestamps)
+        L.sc.phase2(d.features, ev_d, q_d, d.pixel_values, d.input_ids, d.attention_mask)
+
+    def step_e2e(L):
+        L.stage()
+        L.e_feat.copy_(host.features, non_blocking=True)
+        L.e_ts.copy_(host.timestamps, non_blocking=True)
+        L.sc.phase1(L.e_feat, L.e_ts)
+        L.e_pix.copy_(host.pixel_values, non_blocking=True)
+        L.e_ids.copy_(host.input_ids, non_blocking=True)
+        L.e_am.copy_(host.attention_mask, non_blocking=True)
+        L.e_ev.copy_(ev_h, non_blocking=True)
+        L.e_q.copy_(q_h, non_blocking=True)
+        L.sc.phase2(L.e_feat, L.e_ev, L.e_q, L.e_pix, L.e_ids, L.e_am)
+        L.r_stats.copy_(L.sc.stats_row(), non_blocking=True)
+        L.r_mask.copy_(L.sc.mask, non_blocking=True)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps, warmup):
-        for _ in range(warmup):
-            fn()
+    def timed(fn, steps, warmup, use_lanes):
+        main = torch.cuda.current_stream(dev)
+        for i in range(warmup * len(use_lanes)):
+            L = use_lanes[i % len(use_lanes)]
+            with torch.cuda.stream(L.stream):
+                fn(L)
         barrier()
         l0 = lib.csb_kernel_launches()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(steps):
-            fn()
-        e1.record()
+        e0.record(main)
+        for L in use_lanes:
+            L.stream.wait_event(e0)
+        for i in range(steps):
+            L = use_lanes[i % len(use_lanes)]
+            with torch.cuda.stream(L.stream):
+                fn(L)
+        for L in use_lanes:
+            done = torch.cuda.Event()
+            done.record(L.stream)
+            main.wait_event(done)
+        e1.record(main)
         barrier()
         ms = e0.elapsed_time(e1)
         launches = lib.csb_kernel_launches() - l0
@@ -281,10 +307,11 @@ def run_ours(args):
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler:
         sampler.start()
-    ms_total, launches = timed(step_resident, args.steps, max(args.warmup, 3))
+    ms_total, launches = timed(step_resident, args.steps, max(args.warmup, 3), lanes)
     clocks = sampler.stop() if sampler else None
     iters_row = sc.stats_row().cpu()
-    ms_e2e, _ = timed(step_e2e, args.steps, max(args.warmup, 3))
+    ms_single, _ = timed(step_resident, args.steps, max(args.warmup, 3), lanes[:1])  # latency of one step, nothing overlapped
+    ms_e2e, _ = timed(step_e2e, args.steps, max(args.warmup, 3), lanes)
 
     # the one collective: all-gather of the per-stream stats rows
     rows = gather_stats(sc.stats_row().unsqueeze(0))
@@ -314,6 +341,9 @@ def run_ours(args):
                 e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
                          ms_per_step=ms_e2e / args.steps),
                 gpu_launches=int(launches), roofline=roofline, stages_ms=stages,
+                pipeline=dict(depth=len(lanes), note="successive steps are independent streams; `depth` of them are in flight on "
+                              "separate CUDA streams with their own workspaces", single_step_latency_ms=ms_single / args.steps,
+                              frames_per_s_depth1=world * T / (ms_single / args.steps * 1e-3)),
                 stream_stats=dict(zip(STATS_FIELDS, [int(v) for v in iters_row.tolist()])),
                 all_gathered_stats_shape=list(rows.shape))
     if cpu is not None:
@@ -405,6 +435,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--depth", type=int, default=3, help="steps (independent streams) kept in flight per GPU")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

@@ -20,6 +20,7 @@ constexpr int kMaxMma = 4;       // output tiles (TMEM 128-column groups) per CT
 constexpr int kMaxStages = 8;
 constexpr int kBlockBytes = kTile * kChunk * 2;  // 16 KB
 constexpr int kStageBudget = 200 * 1024;         // shared memory spent on pipeline stages
+constexpr int kPrefetch = 8;                     // chunks of L2 prefetch distance (148 CTAs x 8 x 48 KB = 57 MB < L2)
 constexpr int kMaxParamUnits = 16;               // unit tables up to this size travel as a kernel parameter
 
 struct GramUnit {
@@ -258,6 +259,9 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
       "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
+__device__ __forceinline__ void tma_prefetch_l2_2d(const CUtensorMap* map, int c0, int c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(map), "r"(c0), "r"(c1) : "memory");
+}
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t cols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(cols) : "memory");
 }
@@ -349,7 +353,14 @@ __global__ void __launch_bounds__(128, 1) gram_tc_kernel(const __grid_constant__
   if (warp == 0 && lane == 0) {
     // ===== TMA producer =====
     asm volatile("prefetch.tensormap [%0];" ::"l"(&xmap) : "memory");
+    // L2 prefetch runs kPrefetch chunks ahead of the shared-memory ring: the ring then only has to cover L2-hit
+    // latency, the (longer) DRAM latency is hidden without spending shared memory on it.
+    for (int c = 0; c < kPrefetch && c < nchunk; ++c)
+      for (int q = 0; q < n_slots; ++q) ptx::tma_prefetch_l2_2d(&xmap, (c0 + c) * kChunk, unit.slot_block[q] * kTile);
     for (int c = 0; c < nchunk; ++c) {
+      if (c + kPrefetch < nchunk)
+        for (int q = 0; q < n_slots; ++q)
+          ptx::tma_prefetch_l2_2d(&xmap, (c0 + c + kPrefetch) * kChunk, unit.slot_block[q] * kTile);
       const int s = c % kStages;
       const uint32_t ph = (uint32_t)(c / kStages) & 1u;
       ptx::mbar_wait(&ctl->empty[s], ph ^ 1u);

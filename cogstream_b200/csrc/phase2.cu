@@ -246,6 +246,25 @@ __global__ void __launch_bounds__(1024) minor_frames_kernel(const int64_t* __res
 // (d) pixel-difference mask.  A warp owns one (frame, token): W contiguous elements of the current and
 // the previous frame, 128-bit loads; the previous frame's copy is an L2 hit (frames are swept in order).
 // ------------------------------------------------------------------------------------------------
+// sum over 8 bf16 lanes of | bf16(a - b) |, accumulated in fp32 in lane order
+__device__ __forceinline__ float absdiff8_bf16(const uint4& a, const uint4& b) {
+  const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w};
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    __nv_bfloat162 x, y;
+    memcpy(&x, &aw[i], 4);
+    memcpy(&y, &bw[i], 4);
+    const __nv_bfloat162 d = __hsub2(x, y);
+    uint32_t bits;
+    memcpy(&bits, &d, 4);
+    bits &= 0x7fff7fffu;
+    s += __uint_as_float(bits << 16);
+    s += __uint_as_float(bits & 0xffff0000u);
+  }
+  return s;
+}
+
 template <bool BF16>
 __global__ void __launch_bounds__(256) pixel_diff_kernel(const void* __restrict__ pix, int t, int P, int W, float thr_cmp,
                                                          float first_val, uint8_t* __restrict__ mask) {
@@ -264,13 +283,16 @@ __global__ void __launch_bounds__(256) pixel_diff_kernel(const void* __restrict_
       const uint4* c4 = reinterpret_cast<const uint4*>(cur);
       const uint4* p4 = reinterpret_cast<const uint4*>(prv);
       const int Wv = W >> 3;
-      for (int v = lane; v < Wv; v += 32) {
-        float a[8], b[8];
-        unpack8(ldg_stream(c4 + v), a);
-        unpack8(__ldg(p4 + v), b);
-#pragma unroll
-        for (int e = 0; e < 8; ++e) s += fabsf(round_bf16(__fsub_rn(a[e], b[e])));
+      // packed bf16x2 subtract (one RN to bf16, == ATen's fp32 subtract + cast for bf16 operands), |.| by masking the
+      // sign bits, fp32 accumulation; two vectors per lane in flight
+      int v = lane;
+      for (; v + 32 < Wv; v += 64) {
+        const uint4 a0 = ldg_stream(c4 + v), a1 = ldg_stream(c4 + v + 32);
+        const uint4 b0 = __ldg(p4 + v), b1 = __ldg(p4 + v + 32);
+        s += absdiff8_bf16(a0, b0);
+        s += absdiff8_bf16(a1, b1);
       }
+      if (v < Wv) s += absdiff8_bf16(ldg_stream(c4 + v), __ldg(p4 + v));
     } else {
       for (int v = lane; v < W; v += 32) s += fabsf(round_bf16(__fsub_rn(bf16_bits_to_float(cur[v]), bf16_bits_to_float(prv[v]))));
     }
