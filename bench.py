@@ -209,6 +209,7 @@ def run_ours(args):
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the one JSON line (NCCL_DEBUG=VERSION prints a banner there)
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.load()
     w = WORKLOAD

@@ -1,6 +1,8 @@
 // Selection / masking / compaction kernels (reference: model/cogreasoner_chat.py:50-64, :285-296,
 // :325-333, :383-432, :449-476).  Integer and byte work is exact; bf16 arithmetic reproduces ATen's
 // op-by-op rounding (fp32 math, one round-to-nearest-even per reference op).
+#include <stdlib.h>
+
 #include "csb_common.cuh"
 
 namespace csb {
@@ -258,9 +260,8 @@ __device__ __forceinline__ float absdiff8_bf16(const uint4& a, const uint4& b) {
     const __nv_bfloat162 d = __hsub2(x, y);
     uint32_t bits;
     memcpy(&bits, &d, 4);
-    bits &= 0x7fff7fffu;
-    s += __uint_as_float(bits << 16);
-    s += __uint_as_float(bits & 0xffff0000u);
+    s += fabsf(__uint_as_float(bits << 16));        // |.| folds into the FADD operand modifier
+    s += fabsf(__uint_as_float(bits & 0xffff0000u));
   }
   return s;
 }
@@ -310,57 +311,94 @@ __global__ void __launch_bounds__(256) pixel_diff_kernel(const void* __restrict_
   }
 }
 
-// Fast bf16 path: a warp owns token p over a run of F consecutive frames and keeps the previous frame's row
-// in registers, so every pixel row is read from HBM once (plus 1/F for the run boundary) instead of twice.
-template <int NV>
-__global__ void __launch_bounds__(256) pixel_diff_run_kernel(const uint4* __restrict__ pix, int t, int P, int Wv, int W, int F,
-                                                             float thr_cmp, float first_val, uint8_t* __restrict__ mask) {
-  const int lane = threadIdx.x & 31;
-  const int64_t wid = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+// Fast bf16 path (TMA staging): a warp owns token p over a run of F consecutive frames.  Lane 0 streams the rows
+// [f0-1, f1) of that token into a private 3-deep shared-memory ring (12 warps per CTA, one CTA per SM) with bulk async copies (cp.async.bulk ->
+// mbarrier complete_tx), every lane pulls its 16-byte slices of the landed row into registers and the previous
+// frame's row stays in registers, so each pixel row crosses L2->SM once (plus 1/F for the run boundary) instead
+// of twice, with up to 3 rows per warp in flight independent of register pressure.
+constexpr int kPixWarpsDefault = 12;
+constexpr int kPixStagesDefault = 3;
+
+__device__ __forceinline__ uint32_t pix_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+template <int NV, int kPixWarps, int kPixStages>
+__global__ void __launch_bounds__(kPixWarps * 32, 1) pixel_diff_tma_kernel(const uint8_t* __restrict__ pix, int t, int P, int Wv,
+                                                                           int W, int F, float thr_cmp, float first_val,
+                                                                           uint8_t* __restrict__ mask) {
+  extern __shared__ __align__(128) uint8_t pix_smem[];
+  __shared__ __align__(8) uint64_t bars[kPixWarps][kPixStages];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t row_bytes = (uint32_t)Wv * 16u;
+  uint8_t* ring = pix_smem + (size_t)warp * kPixStages * row_bytes;
+  if (lane == 0) {
+    for (int s = 0; s < kPixStages; ++s)
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(pix_smem_u32(&bars[warp][s])));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
   const int nrun = (t + F - 1) / F;
-  if (wid >= (int64_t)nrun * P) return;
-  const int run = (int)(wid / P), p = (int)(wid - (int64_t)run * P);
-  const int f0 = run * F, f1 = min(t, f0 + F);
-  const int64_t fstride = (int64_t)P * Wv;
-  const uint4* row = pix + (int64_t)p * Wv;
-  uint4 prev[NV];
-  int f = f0;
-  if (f0 == 0) {
-    if (lane == 0) mask[p] = first_val > thr_cmp ? 1 : 0;  // :411-412
-    f = 1;
-  }
-  {
-    const uint4* src = row + (int64_t)(f - 1) * fstride;
+  const int64_t nitems = (int64_t)nrun * P;
+  const int64_t fstride = (int64_t)P * row_bytes;
+  uint32_t it_base = 0;  // rows consumed by this warp so far (ring position / parity bookkeeping)
+  for (int64_t item = (int64_t)blockIdx.x * kPixWarps + warp; item < nitems; item += (int64_t)gridDim.x * kPixWarps) {
+    const int run = (int)(item / P), p = (int)(item - (int64_t)run * P);
+    const int f0 = run * F, f1 = min(t, f0 + F);
+    const int fa = f0 == 0 ? 0 : f0 - 1;
+    const int nrows = f1 - fa;
+    const uint8_t* src0 = pix + (int64_t)p * row_bytes + (int64_t)fa * fstride;
+    auto issue = [&](int i) {  // lane 0 only
+      const uint32_t slot = (it_base + (uint32_t)i) % kPixStages;
+      const uint32_t bar = pix_smem_u32(&bars[warp][slot]);
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(row_bytes) : "memory");
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                       pix_smem_u32(ring + (size_t)slot * row_bytes)),
+                   "l"(src0 + (int64_t)i * fstride), "r"(row_bytes), "r"(bar)
+                   : "memory");
+    };
+    if (lane == 0)
+      for (int i = 0; i < kPixStages && i < nrows; ++i) issue(i);
+    uint4 prev[NV];
+    for (int i = 0; i < nrows; ++i) {
+      const uint32_t pos = it_base + (uint32_t)i;
+      const uint32_t slot = pos % kPixStages, parity = (pos / kPixStages) & 1u;
+      const uint32_t bar = pix_smem_u32(&bars[warp][slot]);
+      asm volatile(
+          "{\n\t.reg .pred p;\n\t"
+          "PW_%=:\n\t"
+          "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+          "@p bra PD_%=;\n\t"
+          "bra PW_%=;\n\t"
+          "PD_%=:\n\t}" ::"r"(bar),
+          "r"(parity)
+          : "memory");
+      const uint4* row = reinterpret_cast<const uint4*>(ring + (size_t)slot * row_bytes);
+      uint4 cur[NV];
 #pragma unroll
-    for (int u = 0; u < NV; ++u) {
-      const int v = lane + 32 * u;
-      prev[u] = v < Wv ? ldg_stream(src + v) : make_uint4(0, 0, 0, 0);
-    }
-  }
-  for (; f < f1; ++f) {
-    const uint4* src = row + (int64_t)f * fstride;
-    uint4 cur[NV];
+      for (int u = 0; u < NV; ++u) {
+        const int v = lane + 32 * u;
+        cur[u] = v < Wv ? row[v] : make_uint4(0, 0, 0, 0);
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // our reads of the slot precede the next bulk write to it
+      __syncwarp();
+      if (lane == 0 && i + kPixStages < nrows) issue(i + kPixStages);
+      const int f = fa + i;
+      if (i == 0 && f0 == 0) {
+        if (lane == 0) mask[p] = first_val > thr_cmp ? 1 : 0;  // :411-412
+      } else if (i > 0) {
+        float sacc = 0.f;
 #pragma unroll
-    for (int u = 0; u < NV; ++u) {
-      const int v = lane + 32 * u;
-      cur[u] = v < Wv ? ldg_stream(src + v) : make_uint4(0, 0, 0, 0);
-    }
-    float s = 0.f;
+        for (int u = 0; u < NV; ++u) sacc += absdiff8_bf16(cur[u], prev[u]);
+        sacc = warp_sum(sacc);
+        if (lane == 0) {
+          float m = round_bf16(__fdiv_rn(sacc, (float)W));
+          m = round_bf16(__fmul_rn(m, 255.f));
+          mask[(int64_t)f * P + p] = m > thr_cmp ? 1 : 0;
+        }
+      }
 #pragma unroll
-    for (int u = 0; u < NV; ++u) {
-      float a[8], b[8];
-      unpack8(cur[u], a);
-      unpack8(prev[u], b);
-#pragma unroll
-      for (int e = 0; e < 8; ++e) s += fabsf(round_bf16(__fsub_rn(a[e], b[e])));
-      prev[u] = cur[u];
+      for (int u = 0; u < NV; ++u) prev[u] = cur[u];
     }
-    s = warp_sum(s);
-    if (lane == 0) {
-      float m = round_bf16(__fdiv_rn(s, (float)W));
-      m = round_bf16(__fmul_rn(m, 255.f));
-      mask[(int64_t)f * P + p] = m > thr_cmp ? 1 : 0;
-    }
+    it_base += (uint32_t)nrows;
   }
 }
 
@@ -731,6 +769,33 @@ int csb_pixel_diff(const void* pixels, int64_t t, int64_t P, int64_t W, int32_t 
     CSB_REQUIRE((W % 8 != 0) || (reinterpret_cast<uintptr_t>(pixels) & 15u) == 0, "pixel_diff: pixels not 16-byte aligned");
     const float thr = __bfloat162float(__float2bfloat16_rn((float)threshold));
     const float first = __bfloat162float(__float2bfloat16_rn((float)(threshold + 1.0)));
+    const int64_t Wv = W / 8;
+    // (warps, stages) per CTA: CSB_PIX_CFG=<warps>x<stages> overrides the default for tuning runs
+    int pw = kPixWarpsDefault, ps = kPixStagesDefault;
+    if (const char* cfg = getenv("CSB_PIX_CFG")) sscanf(cfg, "%dx%d", &pw, &ps);
+    const size_t ring_bytes = (size_t)pw * ps * Wv * 16;
+    if (W % 8 == 0 && Wv <= 320 && t >= 8 && ring_bytes <= 200 * 1024) {
+      const int F = t >= 96 ? 12 : 4;
+      const int64_t nitems = ((t + F - 1) / F) * P;
+      int64_t gb = (nitems + pw - 1) / pw;
+      if (gb > kNumSMs) gb = kNumSMs;  // persistent: one CTA per SM, warps stride over the work items
+      auto launch = [&](auto kern) -> int {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring_bytes);
+        if (e != cudaSuccess) { set_error("pixel_diff: smem attr: %s", cudaGetErrorString(e)); return CSB_ERR_CUDA; }
+        kern<<<(unsigned)gb, pw * 32, ring_bytes, s>>>((const uint8_t*)pixels, (int)t, (int)P, (int)Wv, (int)W, F, thr, first, mask);
+        return check_launch("pixel_diff_tma");
+      };
+#define CSB_PIX_DISPATCH(NVV)                                                       \
+      if (pw == 8 && ps == 4) return launch(pixel_diff_tma_kernel<NVV, 8, 4>);      \
+      if (pw == 12 && ps == 3) return launch(pixel_diff_tma_kernel<NVV, 12, 3>);    \
+      if (pw == 16 && ps == 2) return launch(pixel_diff_tma_kernel<NVV, 16, 2>);    \
+      if (pw == 16 && ps == 3) return launch(pixel_diff_tma_kernel<NVV, 16, 3>);    \
+      if (pw == 4 && ps == 8) return launch(pixel_diff_tma_kernel<NVV, 4, 8>);
+      if (Wv <= 64) { CSB_PIX_DISPATCH(2) }
+      else if (Wv <= 192) { CSB_PIX_DISPATCH(6) }
+      else { CSB_PIX_DISPATCH(10) }
+#undef CSB_PIX_DISPATCH
+    }
     pixel_diff_kernel<true><<<blocks, 256, 0, s>>>(pixels, (int)t, (int)P, (int)W, thr, first, mask);
   } else if (dtype == CSB_F32) {
     pixel_diff_kernel<false><<<blocks, 256, 0, s>>>(pixels, (int)t, (int)P, (int)W, (float)threshold, (float)(threshold + 1.0), mask);
