@@ -12,6 +12,7 @@ library; calling any op does (there is no CPU fallback).
 """
 from .compression import (VisualStreamCompressionMixin, create_visual_summary_prompt, install,  # noqa: F401
                           select_additional_frames)
+from . import custom_ops  # noqa: F401  (registers torch.ops.cogstream_b200.*)
 from .kmeans_with_time import kmeans_with_time_min_max  # noqa: F401
 from .pipeline import STATS_FIELDS, StreamCompressor, StreamConfig, gather_stats, pad_rows, shard_streams  # noqa: F401
 

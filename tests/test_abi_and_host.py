@@ -102,3 +102,17 @@ def test_synthetic_is_deterministic():
     assert torch.equal(a.features, b.features) and torch.equal(a.pixel_values, b.pixel_values)
     assert a.features.dtype == torch.bfloat16 and a.timestamps.dtype == torch.float64
     assert a.pixel_values.shape == (40 * 3 * 4, 4) and a.input_ids.eq(synthetic.IMAGE_TOKEN_INDEX).sum() == 120
+
+
+def test_custom_ops_registered_and_shape_inference():
+    """The torch custom-op layer exists, infers shapes on meta tensors and has no CPU kernel."""
+    import cogstream_b200  # noqa: F401
+
+    for name in ("gram", "centroid_update", "dist_to_assigned", "pool_norm", "cosine_flags", "pixel_mask", "compact_tokens"):
+        assert hasattr(torch.ops.cogstream_b200, name), name
+    x = torch.empty(10, 64, dtype=torch.bfloat16, device="meta")
+    assert torch.ops.cogstream_b200.gram(x).shape == (10, 10)
+    out, kept, n = torch.ops.cogstream_b200.compact_tokens(x, 5, 2, torch.empty(10, dtype=torch.uint8, device="meta"))
+    assert out.shape == (10, 64) and kept.dtype == torch.int32 and n.shape == (1,)
+    with pytest.raises((NotImplementedError, RuntimeError)):
+        torch.ops.cogstream_b200.gram(torch.zeros(4, 8, dtype=torch.bfloat16))
