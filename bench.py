@@ -252,7 +252,27 @@ def run_ours(args):
     lanes = [Lane() for _ in range(max(1, args.depth))]
     sc = lanes[0].sc
 
+    use_graphs = False
+    launches_per_step = None
+    if args.graphs:
+        try:
+            c0 = lib.csb_kernel_launches()
+            for L in lanes:
+                with torch.cuda.stream(L.stream):
+                    L.sc.capture(d.features, d.timestamps, ev_d, q_d, d.pixel_values, d.input_ids, d.attention_mask)
+            torch.cuda.synchronize()
+            # capture() runs one eager pass + one captured pass per lane: launches of our kernels per step
+            launches_per_step = (lib.csb_kernel_launches() - c0) // (2 * len(lanes))
+            use_graphs = True
+        except Exception as exc:  # capture is an optimisation of the launch path only
+            print(f"bench.py: CUDA graph capture unavailable ({type(exc).__name__}: {exc}); running eager", file=sys.stderr)
+            torch.cuda.synchronize()
+
     def step_resident(L):
+        if use_graphs:
+            L.sc.replay1()
+            L.sc.replay2()
+            return
         L.sc.phase1(d.features, d.timestamps)
         L.sc.phase2(d.features, ev_d, q_d, d.pixel_values, d.input_ids, d.attention_mask)
 
@@ -299,6 +319,8 @@ def run_ours(args):
         barrier()
         ms = e0.elapsed_time(e1)
         launches = lib.csb_kernel_launches() - l0
+        if use_graphs and fn is step_resident:
+            launches = launches_per_step * steps  # graph replays re-launch the captured kernels without the host-side counter
         if world > 1:
             t = torch.tensor([ms], dtype=torch.float64, device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -342,7 +364,7 @@ def run_ours(args):
                 e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
                          ms_per_step=ms_e2e / args.steps),
                 gpu_launches=int(launches), roofline=roofline, stages_ms=stages,
-                pipeline=dict(depth=len(lanes), note="successive steps are independent streams; `depth` of them are in flight on "
+                pipeline=dict(depth=len(lanes), cuda_graphs=use_graphs, note="successive steps are independent streams; `depth` of them are in flight on "
                               "separate CUDA streams with their own workspaces", single_step_latency_ms=ms_single / args.steps,
                               frames_per_s_depth1=world * T / (ms_single / args.steps * 1e-3)),
                 stream_stats=dict(zip(STATS_FIELDS, [int(v) for v in iters_row.tolist()])),
@@ -376,11 +398,11 @@ def _stage_times(sc, d, ev_d, q_d, reps=5):
         sc.pool.random_(0, T)
         rec("kmeans_solve", lambda: ops.kmeans_solve(sc.G, d.timestamps, sc.km, n_init_given=1, exp_noise=noise, reseed_pool=sc.pool,
                                                      alpha=sc.cfg.alpha, max_iteration=sc.cfg.max_iteration, tol=sc.cfg.tol))
-        rec("centroid_update", lambda: ops.centroid_update(x2, sc.km.member_offsets, sc.km.members, k, out=sc.centroids))
-        order, off = rec("event_order", lambda: ops.event_order(sc.km.assignments, k))
+        rec("centroid_gather", lambda: ops.centroid_gather(x2, sc.km.member_offsets, sc.km.members, sc.km.event_offsets, k,
+                                                           sc.centroids, sc.packed))
+        order, off = sc.km.event_order, sc.km.event_offsets
         dist = rec("dist_gram", lambda: ops.dist_to_assigned_gram(sc.G, sc.km.assignments, off, order, k))
         _, _, rflags = rec("select_reps", lambda: ops.select_representatives(dist, sc.km.assignments, k, 2))
-        rec("event_gather", lambda: ops.gather_rows(x2, order, sc.packed, n=T))
         _, low = rec("cosine_flags", lambda: ops.cosine_flags(q_d.view(-1), ev_d, 0.45))
         mflags, _, _ = rec("minor_frames", lambda: ops.minor_frames(sc.km.assignments, low, rflags))
         rec("pixel_mask", lambda: ops.pixel_mask(d.pixel_values, T, P, sc.W, minor_flags=mflags, out=sc.mask))
@@ -399,8 +421,7 @@ def _roofline(stages, sc, d):
     BX = 2 * T * K
     alg_bytes = {
         "gram": BX,
-        "centroid_update": BX + 4 * k * K,
-        "event_gather": 2 * BX,
+        "centroid_gather": 2 * BX + 4 * k * K,
         "pixel_mask": 2 * T * P * sc.W,
         "compact_tokens": 2 * 2 * n_kept * D + 2 * n_minor * P * D,
     }
@@ -436,6 +457,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--graphs", type=int, default=1, help="replay each phase as a CUDA graph (device-resident run)")
     ap.add_argument("--depth", type=int, default=3, help="steps (independent streams) kept in flight per GPU")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -46,8 +46,9 @@ PROTOTYPES = {
     "csb_gram_workspace_bytes": (_sz, [_i64, _i64]),
     "csb_gram": (C.c_int, [_p, _i64, _i64, _p, _p, _sz, C.c_int, _p]),
     "csb_kmeans_workspace_bytes": (_sz, [_i64, _i64]),
-    "csb_kmeans_solve": (C.c_int, [_p, _p, C.POINTER(KMeansParams), _p, _p, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
+    "csb_kmeans_solve": (C.c_int, [_p, _p, C.POINTER(KMeansParams), _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
     "csb_centroid_update": (C.c_int, [_p, _i64, _i64, _p, _p, _i64, _p, _p]),
+    "csb_centroid_gather": (C.c_int, [_p, _i64, _i64, _p, _p, _p, _i64, _p, _p, _p]),
     "csb_dist_to_assigned": (C.c_int, [_p, _i64, _i64, _p, _i64, _p, _p, _p]),
     "csb_dist_to_assigned_gram": (C.c_int, [_p, _i64, _i64, _p, _p, _p, _p, _p, _p]),
     "csb_select_representatives": (C.c_int, [_p, _p, _i64, _i64, _i64, _p, _p, _p, _p]),

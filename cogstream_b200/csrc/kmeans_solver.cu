@@ -32,6 +32,8 @@ struct SolverArgs {
   void* ct_out;
   int32_t* member_offsets;
   int32_t* members;
+  int32_t* event_order;    // nullable
+  int32_t* event_offsets;  // nullable
   csb_kmeans_status* status;
   // workspace
   double* diag;       // [T] Gram diagonal, compact copy
@@ -595,6 +597,36 @@ __global__ void __launch_bounds__(kSolverThreads) kmeans_solver_kernel(SolverArg
       if (sizeof(TS) == 8) reinterpret_cast<double*>(a.ct_out)[j] = s_ctb[cur][j];
       else reinterpret_cast<float*>(a.ct_out)[j] = (float)s_ctb[cur][j];
     }
+    // chronological per-event order: the member lists minus the seed frames of re-seeded (empty) clusters.
+    // After rebuild_members_smem, cntw[w][j] holds warp w's running cursor == exclusive base + its count, so the
+    // last warp's cursor is the real member count of cluster j.
+    if (a.event_offsets && a.event_order && it > 0) {
+      const int nw = a.multiwarp_fill ? kSolverWarps : 1;
+      if (warp == 0) {
+        const int cpl = (k + 31) / 32;
+        const int j0 = min(k, lane * cpl), j1 = min(k, j0 + cpl);
+        int mine = 0;
+        for (int j = j0; j < j1; ++j) mine += s_cntw[(nw - 1) * k + j];
+        int inc = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int v = __shfl_up_sync(0xffffffffu, inc, o);
+          if (lane >= o) inc += v;
+        }
+        int run = inc - mine;
+        for (int j = j0; j < j1; ++j) {
+          s_cursor[j] = run;
+          a.event_offsets[j] = run;
+          run += s_cntw[(nw - 1) * k + j];
+        }
+        if (lane == 31) a.event_offsets[k] = inc;
+      }
+      __syncthreads();
+      for (int j = warp; j < k; j += kSolverWarps) {
+        const int n = s_cntw[(nw - 1) * k + j], src = s_offs[j], dst = s_cursor[j];
+        for (int e = lane; e < n; e += 32) a.event_order[dst + e] = s_memb[src + e];
+      }
+    }
     if (threadIdx.x == 0) {
       st->iterations = it;
       st->converged = converged ? 1 : 0;
@@ -640,8 +672,8 @@ size_t csb_kmeans_workspace_bytes(int64_t T, int64_t k) {
 
 int csb_kmeans_solve(const double* G, const void* timestamps, const csb_kmeans_params* p, int64_t* init_indices,
                      const float* exp_noise, const int64_t* reseed_pool, int64_t* assignments, void* centroid_times,
-                     int32_t* member_offsets, int32_t* members, csb_kmeans_status* status, void* workspace,
-                     size_t workspace_bytes, csb_stream_t stream) {
+                     int32_t* member_offsets, int32_t* members, int32_t* event_order, int32_t* event_offsets,
+                     csb_kmeans_status* status, void* workspace, size_t workspace_bytes, csb_stream_t stream) {
   CSB_DEVICE_OR_RETURN();
   CSB_REQUIRE(p, "kmeans_solve: null params");
   CSB_REQUIRE(G && timestamps && init_indices && assignments && centroid_times && member_offsets && members && status && workspace,
@@ -667,6 +699,7 @@ int csb_kmeans_solve(const double* G, const void* timestamps, const csb_kmeans_p
   a.n_init_given = (int)p->n_init_given; a.n_reseed_pool = (int)p->n_reseed_pool;
   a.init_indices = init_indices; a.exp_noise = exp_noise; a.reseed_pool = reseed_pool; a.assignments = assignments;
   a.ct_out = centroid_times; a.member_offsets = member_offsets; a.members = members; a.status = status;
+  a.event_order = event_order; a.event_offsets = event_offsets;
   a.diag_in_smem = sp.diag_in_smem; a.multiwarp_fill = sp.multiwarp_fill;
   char* w = reinterpret_cast<char*>(workspace);
   a.diag = reinterpret_cast<double*>(w); w += align_up(sizeof(double) * T, 256);

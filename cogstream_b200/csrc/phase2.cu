@@ -497,44 +497,70 @@ __global__ void __launch_bounds__(kScanThreads) compact_scatter_kernel(const uin
   }
 }
 
-__global__ void __launch_bounds__(256) pool_emit_kernel(const uint4* __restrict__ x, int P, int Dv,
-                                                        const uint8_t* __restrict__ pool_flags,
-                                                        const uint8_t* __restrict__ mask, const int32_t* __restrict__ pos,
-                                                        uint4* __restrict__ out) {
+// Pooled token of every pooled frame, written straight into its slot of the compacted output.  A CTA owns a frame;
+// kPoolGroups thread groups each add a contiguous quarter of the frame's tokens (ascending) so that enough loads are
+// in flight, then group 0 adds the four partial sums in order: fp32 accumulation, one round-to-nearest to bf16.
+constexpr int kPoolGroups = 4;
+
+__global__ void __launch_bounds__(1024) pool_emit_kernel(const uint4* __restrict__ x, int P, int Dv,
+                                                         const uint8_t* __restrict__ pool_flags,
+                                                         const uint8_t* __restrict__ mask, const int32_t* __restrict__ pos,
+                                                         uint4* __restrict__ out) {
+  extern __shared__ float pool_part[];  // [kPoolGroups - 1][blockDim.x][8]
   const int64_t t = blockIdx.x;
   if (!pool_flags[t] || !mask[t * P]) return;
+  const int g = threadIdx.y;
+  const int per = (P + kPoolGroups - 1) / kPoolGroups;
+  const int p0 = min(P, g * per), p1 = min(P, p0 + per);
   const uint4* xf = x + t * (int64_t)P * Dv;
-  uint4* dst = out + (int64_t)pos[t * P] * Dv;
-  for (int c = threadIdx.x; c < Dv; c += blockDim.x) {
+  for (int c0 = 0; c0 < Dv; c0 += blockDim.x) {  // uniform trip count: barriers inside are safe
+    const int c = c0 + threadIdx.x;
     float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    int p = 0;
-    for (; p + 12 <= P; p += 12) {
-      uint4 v[12];
+    if (c < Dv) {
+      int p = p0;
+      for (; p + 8 <= p1; p += 8) {
+        uint4 v[8];
 #pragma unroll
-      for (int u = 0; u < 12; ++u) v[u] = ldg_stream(xf + (int64_t)(p + u) * Dv + c);
+        for (int u = 0; u < 8; ++u) v[u] = ldg_stream(xf + (int64_t)(p + u) * Dv + c);
 #pragma unroll
-      for (int u = 0; u < 12; ++u) {
+        for (int u = 0; u < 8; ++u) {
+          float f[8];
+          unpack8(v[u], f);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) acc[e] += f[e];
+        }
+      }
+      for (; p < p1; ++p) {
         float f[8];
-        unpack8(v[u], f);
+        unpack8(ldg_stream(xf + (int64_t)p * Dv + c), f);
 #pragma unroll
         for (int e = 0; e < 8; ++e) acc[e] += f[e];
       }
-    }
-    for (; p < P; ++p) {
-      float f[8];
-      unpack8(ldg_stream(xf + (int64_t)p * Dv + c), f);
+      if (g > 0) {
+        float* dst = pool_part + ((size_t)(g - 1) * blockDim.x + threadIdx.x) * 8;
 #pragma unroll
-      for (int e = 0; e < 8; ++e) acc[e] += f[e];
+        for (int e = 0; e < 8; ++e) dst[e] = acc[e];
+      }
     }
-    float m[8];
+    __syncthreads();
+    if (g == 0 && c < Dv) {
 #pragma unroll
-    for (int e = 0; e < 8; ++e) m[e] = __fdiv_rn(acc[e], (float)P);
-    uint4 o;
-    o.x = float_to_bf16_bits(m[0]) | (float_to_bf16_bits(m[1]) << 16);
-    o.y = float_to_bf16_bits(m[2]) | (float_to_bf16_bits(m[3]) << 16);
-    o.z = float_to_bf16_bits(m[4]) | (float_to_bf16_bits(m[5]) << 16);
-    o.w = float_to_bf16_bits(m[6]) | (float_to_bf16_bits(m[7]) << 16);
-    dst[c] = o;
+      for (int gg = 1; gg < kPoolGroups; ++gg) {
+        const float* src = pool_part + ((size_t)(gg - 1) * blockDim.x + threadIdx.x) * 8;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[e] += src[e];
+      }
+      float m[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) m[e] = __fdiv_rn(acc[e], (float)P);
+      uint4 o;
+      o.x = float_to_bf16_bits(m[0]) | (float_to_bf16_bits(m[1]) << 16);
+      o.y = float_to_bf16_bits(m[2]) | (float_to_bf16_bits(m[3]) << 16);
+      o.z = float_to_bf16_bits(m[4]) | (float_to_bf16_bits(m[5]) << 16);
+      o.w = float_to_bf16_bits(m[6]) | (float_to_bf16_bits(m[7]) << 16);
+      out[(int64_t)pos[t * P] * Dv + c] = o;
+    }
+    __syncthreads();
   }
 }
 
@@ -857,8 +883,9 @@ int csb_compact_tokens(const void* x, int64_t T, int64_t P, int64_t D, const uin
   if (st) return st;
   if (pool_flags) {
     const int Dv = (int)(D / 8);
-    const int threads = Dv >= 256 ? 256 : ((Dv + 31) / 32) * 32;
-    pool_emit_kernel<<<(unsigned)T, threads, 0, s>>>((const uint4*)x, (int)P, Dv, pool_flags, mask, pos, (uint4*)out);
+    const int tx = Dv >= 256 ? 256 : ((Dv + 31) / 32) * 32;
+    const size_t smem = (size_t)(kPoolGroups - 1) * tx * 8 * sizeof(float);
+    pool_emit_kernel<<<(unsigned)T, dim3(tx, kPoolGroups), smem, s>>>((const uint4*)x, (int)P, Dv, pool_flags, mask, pos, (uint4*)out);
     st = check_launch("pool_emit");
   }
   return st;

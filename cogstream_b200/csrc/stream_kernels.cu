@@ -111,6 +111,54 @@ __global__ void __launch_bounds__(256) centroid_update_kernel(const uint4* __res
 }
 
 // ------------------------------------------------------------------------------------------------
+// centroid update fused with the per-event token gather: the member rows of cluster j are read once, added in
+// ascending order AND stored to their event-major position.  Bytes: 2*T*K read + 2*T*K + 4*k*K written.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) centroid_gather_kernel(const uint4* __restrict__ x, int64_t Kv,
+                                                              const int32_t* __restrict__ offsets,
+                                                              const int32_t* __restrict__ members,
+                                                              const int32_t* __restrict__ ev_offsets, float4* __restrict__ C,
+                                                              uint4* __restrict__ packed) {
+  const int j = blockIdx.y;
+  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= Kv) return;
+  const int beg = offsets[j], end = offsets[j + 1];
+  const int ev0 = ev_offsets[j], nev = ev_offsets[j + 1] - ev0;  // rows that belong to the event (0 for a re-seeded centre)
+  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  int m = beg;
+  for (; m + 4 <= end; m += 4) {
+    uint4 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) v[u] = ldg_stream(x + (int64_t)members[m + u] * Kv + c);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      float f[8];
+      unpack8(v[u], f);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[e] += f[e];
+      if (packed && m + u - beg < nev) packed[(int64_t)(ev0 + m + u - beg) * Kv + c] = v[u];
+    }
+  }
+  for (; m < end; ++m) {
+    const uint4 v = ldg_stream(x + (int64_t)members[m] * Kv + c);
+    float f[8];
+    unpack8(v, f);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] += f[e];
+    if (packed && m - beg < nev) packed[(int64_t)(ev0 + m - beg) * Kv + c] = v;
+  }
+  if (C) {
+    const float n = (float)(end - beg);
+    float r[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) r[e] = (end > beg) ? __fdiv_rn(acc[e], n) : 0.f;
+    float4* out = C + ((int64_t)j * Kv + c) * 2;
+    out[0] = make_float4(r[0], r[1], r[2], r[3]);
+    out[1] = make_float4(r[4], r[5], r[6], r[7]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // distance of every frame to its own centroid: one CTA per frame, fp32 lanes, fp64 block reduce.
 // Bytes: 2*T*K (x) + 4*K per frame of centroid (L2-resident across the ~T/k frames of an event).
 // ------------------------------------------------------------------------------------------------
@@ -242,6 +290,20 @@ int csb_centroid_update(const void* x, int64_t T, int64_t K, const int32_t* offs
   dim3 grid((unsigned)((Kv + 255) / 256), (unsigned)k);
   centroid_update_kernel<<<grid, 256, 0, as_stream(stream)>>>((const uint4*)x, Kv, offsets, members, (float4*)centroids);
   return check_launch("centroid_update");
+}
+
+int csb_centroid_gather(const void* x, int64_t T, int64_t K, const int32_t* offsets, const int32_t* members,
+                        const int32_t* event_offsets, int64_t k, float* centroids, void* packed, csb_stream_t stream) {
+  CSB_DEVICE_OR_RETURN();
+  CSB_REQUIRE(x && offsets && members && event_offsets && (centroids || packed) && T > 0 && k > 0, "centroid_gather: null argument");
+  CSB_REQUIRE(K % 8 == 0 && aligned16(x) && (!centroids || aligned16(centroids)) && (!packed || aligned16(packed)),
+              "centroid_gather: K %% 8 != 0 or misaligned");
+  CSB_REQUIRE(k <= 65535, "centroid_gather: k > 65535");
+  const int64_t Kv = K / 8;
+  dim3 grid((unsigned)((Kv + 255) / 256), (unsigned)k);
+  centroid_gather_kernel<<<grid, 256, 0, as_stream(stream)>>>((const uint4*)x, Kv, offsets, members, event_offsets,
+                                                               (float4*)centroids, (uint4*)packed);
+  return check_launch("centroid_gather");
 }
 
 int csb_dist_to_assigned(const void* x, int64_t T, int64_t K, const float* centroids, int64_t k, const int64_t* assignments,

@@ -110,6 +110,8 @@ class KMeansBuffers:
         self.member_offsets = torch.empty(k + 1, dtype=torch.int32, device=device)
         self.members = torch.empty(T + k, dtype=torch.int32, device=device)
         self.init_indices = torch.empty(k, dtype=torch.int64, device=device)
+        self.event_order = torch.empty(T, dtype=torch.int32, device=device)  # frames sorted by (event, frame)
+        self.event_offsets = torch.empty(k + 1, dtype=torch.int32, device=device)
         self.status = torch.zeros(STATUS_WORDS, dtype=torch.int32, device=device)
         self.workspace = torch.empty(kmeans_workspace_bytes(T, k), dtype=torch.uint8, device=device)
 
@@ -146,7 +148,7 @@ def kmeans_solve(G: torch.Tensor, timestamps: torch.Tensor, buf: KMeansBuffers, 
         check(_lib.load().csb_kmeans_solve(
             G.data_ptr(), timestamps.data_ptr(), C.byref(p), buf.init_indices.data_ptr(), _ptr(exp_noise), _ptr(reseed_pool),
             buf.assignments.data_ptr(), buf.centroid_times.data_ptr(), buf.member_offsets.data_ptr(), buf.members.data_ptr(),
-            buf.status.data_ptr(), buf.workspace.data_ptr(), buf.workspace.numel(), _stream(G)), "kmeans_solve")
+            buf.event_order.data_ptr(), buf.event_offsets.data_ptr(), buf.status.data_ptr(), buf.workspace.data_ptr(), buf.workspace.numel(), _stream(G)), "kmeans_solve")
 
 
 def decode_status(status_host: torch.Tensor) -> dict:
@@ -170,6 +172,18 @@ def centroid_update(x: torch.Tensor, member_offsets: torch.Tensor, members: torc
         check(_lib.load().csb_centroid_update(x.data_ptr(), T, K, member_offsets.data_ptr(), members.data_ptr(), k,
                                               Cn.data_ptr(), _stream(x)), "centroid_update")
     return Cn
+
+
+def centroid_gather(x: torch.Tensor, member_offsets: torch.Tensor, members: torch.Tensor, event_offsets: torch.Tensor, k: int,
+                    centroids: Optional[torch.Tensor] = None, packed: Optional[torch.Tensor] = None):
+    """One pass over x [T,K] bf16: centroids [k,K] fp32 and/or the event-major packed copy [T,K] bf16 (outputs given by the caller)."""
+    _need(x, "x", torch.bfloat16, 2)
+    T, K = x.shape
+    with _on_device(x):
+        check(_lib.load().csb_centroid_gather(x.data_ptr(), T, K, member_offsets.data_ptr(), members.data_ptr(),
+                                              event_offsets.data_ptr(), k, _ptr(centroids), _ptr(packed), _stream(x)),
+              "centroid_gather")
+    return centroids, packed
 
 
 def dist_to_assigned(x: torch.Tensor, centroids: torch.Tensor, assignments: torch.Tensor) -> torch.Tensor:

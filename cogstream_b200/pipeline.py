@@ -80,6 +80,7 @@ class StreamCompressor:
             self.pool = torch.zeros(self.cfg.reseed_pool, dtype=torch.int64, device=dev)
             self.centroids = torch.empty(k, self.K, dtype=torch.float32, device=dev) if self.cfg.compute_centroids else None
             self.packed = torch.empty(T, self.K, dtype=torch.bfloat16, device=dev) if self.cfg.gather_events else None
+        self._row_base = torch.tensor([T, self.k if self.gate else 0, 0, 0, 0, 0, 0, 0], dtype=torch.int64, device=dev)
         self.minor_flags = torch.zeros(T, dtype=torch.uint8, device=dev)
         self.n_minor = torch.zeros(1, dtype=torch.int64, device=dev)
         self.mask = torch.empty(T * P, dtype=torch.uint8, device=dev)
@@ -117,8 +118,11 @@ class StreamCompressor:
             self.km.init_indices.copy_(init_indices, non_blocking=True)
             n_given, noise = k, None
         else:
-            first = random.randint(0, T - 1) if first_index is None else first_index  # kmeans_with_time.py:41
-            self.km.init_indices[:1].fill_(first)
+            if first_index == "device":  # drawn by the CUDA generator: no host value baked into a captured graph
+                torch.randint(0, T, (1,), device=self.device, out=self.km.init_indices[:1])
+            else:
+                first = random.randint(0, T - 1) if first_index is None else first_index  # kmeans_with_time.py:41
+                self.km.init_indices[:1].fill_(first)
             n_given = 1
             if exp_noise is not None:
                 noise = exp_noise
@@ -139,14 +143,13 @@ class StreamCompressor:
             ops.pixel_diff(pixel_values, T, self.P, self.W, threshold=self.cfg.pixel_threshold, out=self.mask, stream=self.side)
             self._ev_diff.record(self.side)
             self._diff_pending = True
-        if self.centroids is not None:
-            ops.centroid_update(x2, self.km.member_offsets, self.km.members, k, out=self.centroids)
+        # one pass over X: fp32 centroids + the event-major packed token copy (the solver already emitted the order)
+        if self.centroids is not None or self.packed is not None:
+            ops.centroid_gather(x2, self.km.member_offsets, self.km.members, self.km.event_offsets, k, self.centroids, self.packed)
         assign = self.km.assignments
-        self.order, self.ev_off = ops.event_order(assign, k)
+        self.order, self.ev_off = self.km.event_order, self.km.event_offsets
         self.dist = ops.dist_to_assigned_gram(self.G, assign, self.ev_off, self.order, k)
         self.reps, self.rep_counts, self.rep_flags = ops.select_representatives(self.dist, assign, k, self.cfg.n_representatives)
-        if self.packed is not None:
-            ops.gather_rows(x2, self.order, self.packed, n=T)
 
     # ------------------------------------------------------------------------------------------
     def phase2(self, features: torch.Tensor, events_repr: Optional[torch.Tensor], question: Optional[torch.Tensor],
@@ -174,17 +177,40 @@ class StreamCompressor:
                                                                                 attention_mask)
 
     # ------------------------------------------------------------------------------------------
+    def capture(self, features, timestamps, events_repr, question, pixel_values, input_ids, attention_mask=None):
+        """Capture both phases into CUDA graphs bound to these input tensors (refill them in place, then ``replay1()`` /
+        ``replay2()``).  The first centre is drawn on the device; everything else is identical to the eager path."""
+        cur = torch.cuda.current_stream(self.device)
+        warm = torch.cuda.Stream(device=self.device)
+        warm.wait_stream(cur)
+        with torch.cuda.stream(warm):  # one eager pass: lazy initialisation must not happen inside the capture
+            self.phase1(features, timestamps, first_index="device")
+            self.phase2(features, events_repr, question, pixel_values, input_ids, attention_mask)
+        cur.wait_stream(warm)
+        torch.cuda.synchronize(self.device)
+        self.graph1, self.graph2 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph1):
+            self.phase1(features, timestamps, first_index="device")
+        with torch.cuda.graph(self.graph2, pool=self.graph1.pool()):
+            self.phase2(features, events_repr, question, pixel_values, input_ids, attention_mask)
+            self._stats_static = self.stats_row()
+        return self
+
+    def replay1(self):
+        self.graph1.replay()
+
+    def replay2(self):
+        self.graph2.replay()
+
+    # ------------------------------------------------------------------------------------------
     def stats_row(self) -> torch.Tensor:
-        """[len(STATS_FIELDS)] int64 on the device (no sync): the per-stream row that ranks all-gather."""
-        dev = self.device
-        row = torch.zeros(len(STATS_FIELDS), dtype=torch.int64, device=dev)
-        row[0] = self.T
-        row[1] = self.k if self.gate else 0
+        """[len(STATS_FIELDS)] int64 on the device (no sync, capture-safe): the per-stream row that ranks all-gather."""
+        row = self._row_base.clone()
         if self.gate:
             st = self.km.status
-            row[2] = st[0]
-            row[3] = st[2]
-            row[7] = st[1]
+            row[2:3] = st[0:1]
+            row[3:4] = st[2:3]
+            row[7:8] = st[1:2]
         row[4:5] = self.n_minor
         row[5:6] = self.n_kept
         row[6:7] = self.n_ids_out

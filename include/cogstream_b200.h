@@ -127,17 +127,29 @@ CSB_API size_t csb_kmeans_workspace_bytes(int64_t T, int64_t k);
  *   centroid_times[k]   ts_dtype out (:115/:120)
  *   member_offsets[k+1] int32 out, members [T+k] int32 out: CSR of the frames that DEFINE each returned
  *                  centre (its assigned frames ascending; a re-seeded empty cluster lists its seed frame)
+ *   event_order   [T] int32 out or NULL, event_offsets [k+1] int32 out or NULL: frames sorted by (event, frame) and
+ *                  the per-event ranges -- the chronological per-event gather order of cogreasoner_chat.py:291-296
+ *                  (same as csb_event_order on the returned assignments; a re-seeded empty cluster has an empty range)
  *   status        device csb_kmeans_status
  */
 CSB_API int csb_kmeans_solve(const double* G, const void* timestamps, const csb_kmeans_params* params /* host */,
                      int64_t* init_indices, const float* exp_noise, const int64_t* reseed_pool,
                      int64_t* assignments, void* centroid_times, int32_t* member_offsets, int32_t* members,
-                     csb_kmeans_status* status, void* workspace, size_t workspace_bytes, csb_stream_t stream);
+                     int32_t* event_order, int32_t* event_offsets, csb_kmeans_status* status, void* workspace,
+                     size_t workspace_bytes, csb_stream_t stream);
 
 /* Centroid features from the defining members: C[j] = (sum of member rows, ascending, fp32) / n_j.
  * kmeans_with_time.py:110-120, one pass over the member rows; atomic-free and deterministic. */
 CSB_API int csb_centroid_update(const void* x_bf16, int64_t T, int64_t K, const int32_t* member_offsets,
                         const int32_t* members, int64_t k, float* centroids /* [k,K] */, csb_stream_t stream);
+
+/* csb_centroid_update fused with the chronological per-event token gather (cogreasoner_chat.py:291-296): one pass
+ * over x produces the centroids AND the event-major packed copy packed[event_offsets[j] + r] = x[members of j][r].
+ * Members of a centre beyond its event range (the seed frame of a re-seeded empty cluster) only feed the centroid.
+ * centroids or packed may be NULL. */
+CSB_API int csb_centroid_gather(const void* x_bf16, int64_t T, int64_t K, const int32_t* member_offsets,
+                                const int32_t* members, const int32_t* event_offsets, int64_t k, float* centroids,
+                                void* packed_bf16, csb_stream_t stream);
 
 /* dist[i] = || x_i - C[assign[i]] ||_2 (fp32), one pass over x.  cogreasoner_chat.py:57-61. */
 CSB_API int csb_dist_to_assigned(const void* x_bf16, int64_t T, int64_t K, const float* centroids, int64_t k,
