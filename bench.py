@@ -331,10 +331,10 @@ def run_ours(args):
     if sampler:
         sampler.start()
     ms_total, launches = timed(step_resident, args.steps, max(args.warmup, 3), lanes)
-    clocks = sampler.stop() if sampler else None
     iters_row = sc.stats_row().cpu()
     ms_single, _ = timed(step_resident, args.steps, max(args.warmup, 3), lanes[:1])  # latency of one step, nothing overlapped
     ms_e2e, _ = timed(step_e2e, args.steps, max(args.warmup, 3), lanes)
+    clocks = sampler.stop() if sampler else None  # sampled across the three timed regions (100 ms period)
 
     # the one collective: all-gather of the per-stream stats rows
     rows = gather_stats(sc.stats_row().unsqueeze(0))
@@ -458,7 +458,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--graphs", type=int, default=1, help="replay each phase as a CUDA graph (device-resident run)")
-    ap.add_argument("--depth", type=int, default=3, help="steps (independent streams) kept in flight per GPU")
+    ap.add_argument("--depth", type=int, default=4, help="steps (independent streams) kept in flight per GPU")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

@@ -20,6 +20,7 @@ constexpr int kMaxMma = 4;       // output tiles (TMEM 128-column groups) per CT
 constexpr int kMaxStages = 8;
 constexpr int kBlockBytes = kTile * kChunk * 2;  // 16 KB
 constexpr int kStageBudget = 200 * 1024;         // shared memory spent on pipeline stages
+constexpr int kSegChunks = 96;                   // accumulator chain length (chunks) between drains
 constexpr int kPrefetch = 8;                     // chunks of L2 prefetch distance (148 CTAs x 8 x 48 KB = 57 MB < L2)
 constexpr int kMaxParamUnits = 16;               // unit tables up to this size travel as a kernel parameter
 
@@ -315,11 +316,11 @@ struct __align__(8) GramSmemCtl {
   uint32_t tmem_base;
 };
 
-__global__ void __launch_bounds__(128, 1) gram_tc_kernel(const __grid_constant__ CUtensorMap xmap,
+__global__ void __launch_bounds__(160, 1) gram_tc_kernel(const __grid_constant__ CUtensorMap xmap,
                                                          const __grid_constant__ GramUnitTable ptable,
                                                          const GramUnit* __restrict__ units, int n_tiles, int n_kr,
                                                          int n_chunks, int kStages, int stage_bytes,
-                                                         float* __restrict__ partial) {
+                                                         float* __restrict__ partial, int dbg) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // stage buffers first (1024-byte aligned for SWIZZLE_128B), control block after
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -350,64 +351,94 @@ __global__ void __launch_bounds__(128, 1) gram_tc_kernel(const __grid_constant__
   const uint32_t tmem_base = ctl->tmem_base;
   const int n_slots = unit.n_slots, n_ut = unit.n_tiles;
 
-  if (warp == 0 && lane == 0) {
-    // ===== TMA producer =====
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&xmap) : "memory");
-    // L2 prefetch runs kPrefetch chunks ahead of the shared-memory ring: the ring then only has to cover L2-hit
-    // latency, the (longer) DRAM latency is hidden without spending shared memory on it.
-    for (int c = 0; c < kPrefetch && c < nchunk; ++c)
-      for (int q = 0; q < n_slots; ++q) ptx::tma_prefetch_l2_2d(&xmap, (c0 + c) * kChunk, unit.slot_block[q] * kTile);
-    for (int c = 0; c < nchunk; ++c) {
-      if (c + kPrefetch < nchunk)
+  if (warp == 4) {
+    if (lane == 0) {
+      // ===== TMA producer (dedicated warp: it may run ahead across accumulator drains) =====
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&xmap) : "memory");
+      // L2 prefetch runs kPrefetch chunks ahead of the shared-memory ring: the ring then only has to cover L2-hit
+      // latency, the (longer) DRAM latency is hidden without spending shared memory on it.
+      for (int c = 0; c < kPrefetch && c < nchunk && !(dbg & 2); ++c)
+        for (int q = 0; q < n_slots; ++q) ptx::tma_prefetch_l2_2d(&xmap, (c0 + c) * kChunk, unit.slot_block[q] * kTile);
+      for (int c = 0; c < nchunk; ++c) {
+        if (!(dbg & 2) && c + kPrefetch < nchunk)
+          for (int q = 0; q < n_slots; ++q)
+            ptx::tma_prefetch_l2_2d(&xmap, (c0 + c + kPrefetch) * kChunk, unit.slot_block[q] * kTile);
+        const int s = c % kStages;
+        const uint32_t ph = (uint32_t)(c / kStages) & 1u;
+        ptx::mbar_wait(&ctl->empty[s], ph ^ 1u);
+        if (dbg & 2) {  // profiling aid: no loads, the MMAs run on whatever is in shared memory
+          ptx::mbar_expect_tx(&ctl->full[s], 0);
+          continue;
+        }
+        ptx::mbar_expect_tx(&ctl->full[s], (uint32_t)(n_slots * kBlockBytes));
+        uint8_t* stage = smem + (size_t)s * stage_bytes;
         for (int q = 0; q < n_slots; ++q)
-          ptx::tma_prefetch_l2_2d(&xmap, (c0 + c + kPrefetch) * kChunk, unit.slot_block[q] * kTile);
-      const int s = c % kStages;
-      const uint32_t ph = (uint32_t)(c / kStages) & 1u;
-      ptx::mbar_wait(&ctl->empty[s], ph ^ 1u);
-      ptx::mbar_expect_tx(&ctl->full[s], (uint32_t)(n_slots * kBlockBytes));
-      uint8_t* stage = smem + (size_t)s * stage_bytes;
-      for (int q = 0; q < n_slots; ++q)
-        ptx::tma_load_2d(stage + (size_t)q * kBlockBytes, &xmap, &ctl->full[s], (c0 + c) * kChunk, unit.slot_block[q] * kTile);
+          ptx::tma_load_2d(stage + (size_t)q * kBlockBytes, &xmap, &ctl->full[s], (c0 + c) * kChunk, unit.slot_block[q] * kTile);
+      }
     }
-  } else if (warp == 1 && lane == 0) {
-    // ===== MMA issuer =====
+  } else {
+    // ===== warps 0-3: MMA issue (warp 1, lane 0) + accumulator drain (all four; warp w owns TMEM lanes 32w..32w+31) =====
+    // The tensor core accumulates in fp32 with truncation, so a chain of n MMAs drifts by up to ~n * 2^-24 relative.  Chains
+    // are cut every kSegChunks chunks: the accumulators are drained and added (round-to-nearest fp32) into the partial
+    // tile, then restarted from zero.  Short K ranges (config 2: 88 chunks per CTA) are a single segment.
     constexpr uint32_t idesc = make_idesc(128, 128);
-    for (int c = 0; c < nchunk; ++c) {
-      const int s = c % kStages;
-      const uint32_t ph = (uint32_t)(c / kStages) & 1u;
-      ptx::mbar_wait(&ctl->full[s], ph);
-      ptx::tc_fence_after();
-      const uint32_t stage = ptx::smem_u32(smem + (size_t)s * stage_bytes);
-      for (int t = 0; t < n_ut; ++t) {
-        const uint32_t a_addr = stage + (uint32_t)unit.a_slot[t] * kBlockBytes;
-        const uint32_t b_addr = stage + (uint32_t)unit.b_slot[t] * kBlockBytes;
+    const int nseg = (nchunk + kSegChunks - 1) / kSegChunks;
+    for (int seg = 0; seg < nseg; ++seg) {
+      const int cs = seg * kSegChunks, ce = min(nchunk, cs + kSegChunks);
+      if (warp == 1 && lane == 0) {
+        for (int c = cs; c < ce; ++c) {
+          const int s = c % kStages;
+          const uint32_t ph = (uint32_t)(c / kStages) & 1u;
+          ptx::mbar_wait(&ctl->full[s], ph);
+          ptx::tc_fence_after();
+          const uint32_t stage = ptx::smem_u32(smem + (size_t)s * stage_bytes);
+          for (int t = 0; t < n_ut && !(dbg & 1); ++t) {  // dbg&1: profiling aid, loads only
+            const uint32_t a_addr = stage + (uint32_t)unit.a_slot[t] * kBlockBytes;
+            const uint32_t b_addr = stage + (uint32_t)unit.b_slot[t] * kBlockBytes;
 #pragma unroll
-        for (int ks = 0; ks < kChunk / 16; ++ks) {
-          ptx::umma_bf16(tmem_base + (uint32_t)t * 128u, make_smem_desc(a_addr + ks * 32), make_smem_desc(b_addr + ks * 32),
-                         idesc, (c > 0 || ks > 0) ? 1u : 0u);
+            for (int ks = 0; ks < kChunk / 16; ++ks) {
+              ptx::umma_bf16(tmem_base + (uint32_t)t * 128u, make_smem_desc(a_addr + ks * 32), make_smem_desc(b_addr + ks * 32),
+                             idesc, (c > cs || ks > 0) ? 1u : 0u);
+            }
+          }
+          ptx::umma_commit(&ctl->empty[s]);  // frees the stage once these MMAs have read it
+        }
+        ptx::umma_commit(&ctl->accum_done);
+      }
+      __syncwarp();
+      ptx::mbar_wait(&ctl->accum_done, (uint32_t)seg & 1u);
+      ptx::tc_fence_after();
+      for (int t = 0; t < n_ut; ++t) {
+        float* out = partial + ((int64_t)kr * n_tiles + unit.tile_id[t]) * (kTile * kTile) + (int64_t)(warp * 32 + lane) * kTile;
+#pragma unroll 1
+        for (int cb = 0; cb < 4; ++cb) {
+          uint32_t r[32];
+          ptx::tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(t * 128 + cb * 32), r);
+          ptx::tmem_ld_wait();
+          float4* o4 = reinterpret_cast<float4*>(out + cb * 32);
+          if (seg == 0) {
+#pragma unroll
+            for (int v = 0; v < 8; ++v)
+              o4[v] = make_float4(__uint_as_float(r[4 * v]), __uint_as_float(r[4 * v + 1]), __uint_as_float(r[4 * v + 2]),
+                                  __uint_as_float(r[4 * v + 3]));
+          } else {
+#pragma unroll
+            for (int v = 0; v < 8; ++v) {
+              float4 o = o4[v];
+              o.x = __fadd_rn(o.x, __uint_as_float(r[4 * v]));
+              o.y = __fadd_rn(o.y, __uint_as_float(r[4 * v + 1]));
+              o.z = __fadd_rn(o.z, __uint_as_float(r[4 * v + 2]));
+              o.w = __fadd_rn(o.w, __uint_as_float(r[4 * v + 3]));
+              o4[v] = o;
+            }
+          }
         }
       }
-      ptx::umma_commit(&ctl->empty[s]);  // frees the stage once these MMAs have read it
-    }
-    ptx::umma_commit(&ctl->accum_done);
-  }
-  __syncwarp();
-
-  // ===== epilogue: TMEM -> registers -> fp32 partial tiles (all 4 warps; warp w owns lanes 32w..32w+31) =====
-  ptx::mbar_wait(&ctl->accum_done, 0);
-  ptx::tc_fence_after();
-  for (int t = 0; t < n_ut; ++t) {
-    float* out = partial + ((int64_t)kr * n_tiles + unit.tile_id[t]) * (kTile * kTile) + (int64_t)(warp * 32 + lane) * kTile;
-#pragma unroll 1
-    for (int cb = 0; cb < 4; ++cb) {
-      uint32_t r[32];
-      ptx::tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(t * 128 + cb * 32), r);
-      ptx::tmem_ld_wait();
-      float4* o4 = reinterpret_cast<float4*>(out + cb * 32);
-#pragma unroll
-      for (int v = 0; v < 8; ++v)
-        o4[v] = make_float4(__uint_as_float(r[4 * v]), __uint_as_float(r[4 * v + 1]), __uint_as_float(r[4 * v + 2]),
-                            __uint_as_float(r[4 * v + 3]));
+      if (seg + 1 < nseg) {
+        ptx::tc_fence_before();
+        asm volatile("bar.sync 1, 128;" ::: "memory");  // every accumulator has been read before the next segment overwrites TMEM
+        ptx::tc_fence_after();
+      }
     }
   }
   ptx::tc_fence_before();
@@ -469,7 +500,7 @@ int csb_gram(const void* x, int64_t T, int64_t K, double* G, void* workspace, si
     gram_simt_kernel<<<grid, 256, 0, s>>>((const __nv_bfloat16*)x, (int)T, K, p.nb, p.n_tiles, n_kr, p.n_chunks, partial);
     int st = check_launch("gram_simt");
     if (st) return st;
-  } else if (impl == 0) {
+  } else if ((impl & 15) == 0) {
     n_kr = p.n_kr;
     int kr_simt = (2 * kNumSMs + p.n_tiles - 1) / p.n_tiles;
     if (kr_simt > p.n_chunks) kr_simt = p.n_chunks;
@@ -512,7 +543,8 @@ int csb_gram(const void* x, int64_t T, int64_t K, double* G, void* workspace, si
     e = cudaFuncSetAttribute(gram_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
     if (e != cudaSuccess) { set_error("gram: smem attr: %s", cudaGetErrorString(e)); return CSB_ERR_CUDA; }
     dim3 grid((unsigned)p.n_units, (unsigned)n_kr);
-    gram_tc_kernel<<<grid, 128, smem_bytes, s>>>(map, table, d_units, p.n_tiles, n_kr, p.n_chunks, p.n_stages, stage_bytes, partial);
+    gram_tc_kernel<<<grid, 160, smem_bytes, s>>>(map, table, d_units, p.n_tiles, n_kr, p.n_chunks, p.n_stages, stage_bytes, partial,
+                                                     impl >> 4);
     int st = check_launch("gram_tc");
     if (st) return st;
   } else {
