@@ -78,7 +78,14 @@ static int unit_new_blocks(const GramUnit& u, int bi, int bj) {
 
 static void plan_units(int nb, GramUnit* units, int* n_units, int* max_slots) {
   int n = 0, ms = 0;
-  auto emit = [&](const GramUnit& u) {
+  auto emit = [&](GramUnit u) {
+    for (int i = 1; i < u.n_tiles; ++i)  // stable insertion sort by A slot (collector reuse wants equal-A tiles adjacent)
+      for (int j = i; j > 0 && u.a_slot[j - 1] > u.a_slot[j]; --j) {
+        int x;
+        x = u.a_slot[j]; u.a_slot[j] = u.a_slot[j - 1]; u.a_slot[j - 1] = x;
+        x = u.b_slot[j]; u.b_slot[j] = u.b_slot[j - 1]; u.b_slot[j - 1] = x;
+        x = u.tile_id[j]; u.tile_id[j] = u.tile_id[j - 1]; u.tile_id[j - 1] = x;
+      }
     if (units) units[n] = u;
     ++n;
     if (u.n_slots > ms) ms = u.n_slots;
@@ -392,6 +399,9 @@ __global__ void __launch_bounds__(160, 1) gram_tc_kernel(const __grid_constant__
           ptx::mbar_wait(&ctl->full[s], ph);
           ptx::tc_fence_after();
           const uint32_t stage = ptx::smem_u32(smem + (size_t)s * stage_bytes);
+          // tile-outer / k-step-inner: four back-to-back MMAs accumulate into the same TMEM tile.  (Measured: the k-step-outer
+          // order, which would let tiles that share A reuse it through the A collector, runs 2x slower -- alternating the
+          // accumulator between consecutive MMAs costs far more than the saved shared-memory reads.)
           for (int t = 0; t < n_ut && !(dbg & 1); ++t) {  // dbg&1: profiling aid, loads only
             const uint32_t a_addr = stage + (uint32_t)unit.a_slot[t] * kBlockBytes;
             const uint32_t b_addr = stage + (uint32_t)unit.b_slot[t] * kBlockBytes;
