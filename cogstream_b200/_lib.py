@@ -27,6 +27,7 @@ class KMeansParams(C.Structure):
         ("tol", C.c_double),
         ("n_init_given", C.c_int64),
         ("n_reseed_pool", C.c_int64),
+        ("ldg", C.c_int64),
     ]
 
 
@@ -45,12 +46,13 @@ PROTOTYPES = {
     "csb_pool_norm": (C.c_int, [_p, _i64, _i64, _i64, _p, _p, _p, _p]),
     "csb_gram_workspace_bytes": (_sz, [_i64, _i64]),
     "csb_gram": (C.c_int, [_p, _i64, _i64, _p, _p, _sz, C.c_int, _p]),
+    "csb_gram_extend": (C.c_int, [_p, _i64, _i64, _i64, _p, _i64, _p, _sz, C.c_int, _p]),
     "csb_kmeans_workspace_bytes": (_sz, [_i64, _i64]),
     "csb_kmeans_solve": (C.c_int, [_p, _p, C.POINTER(KMeansParams), _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
     "csb_centroid_update": (C.c_int, [_p, _i64, _i64, _p, _p, _i64, _p, _p]),
     "csb_centroid_gather": (C.c_int, [_p, _i64, _i64, _p, _p, _p, _i64, _p, _p, _p]),
     "csb_dist_to_assigned": (C.c_int, [_p, _i64, _i64, _p, _i64, _p, _p, _p]),
-    "csb_dist_to_assigned_gram": (C.c_int, [_p, _i64, _i64, _p, _p, _p, _p, _p, _p]),
+    "csb_dist_to_assigned_gram": (C.c_int, [_p, _i64, _i64, _i64, _p, _p, _p, _p, _p, _p]),
     "csb_select_representatives": (C.c_int, [_p, _p, _i64, _i64, _i64, _p, _p, _p, _p]),
     "csb_event_order": (C.c_int, [_p, _i64, _i64, _p, _p, _p]),
     "csb_gather_rows": (C.c_int, [_p, _i64, _p, _i64, _p, _i64, _p, _p]),

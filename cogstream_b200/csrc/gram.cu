@@ -39,6 +39,7 @@ struct GramUnitTable {
 
 struct GramPlan {
   int nb;        // 128-row blocks
+  int b0;        // first column block to compute (0 = whole matrix)
   int n_tiles;   // nb*(nb+1)/2
   int n_units;
   int n_kr;      // K ranges
@@ -47,13 +48,16 @@ struct GramPlan {
   int n_stages;  // pipeline depth that fits the shared-memory budget
 };
 
-static inline int tri_id(int bi, int bj, int nb) { return bi * nb - bi * (bi - 1) / 2 + (bj - bi); }
+// Upper-triangular tiles (bi <= bj) of the column blocks bj >= b0, column-major: id = sum_{c=b0}^{bj-1} (c+1) + bi.
+// b0 = 0 is the whole Gram matrix; b0 > 0 is the extension by new frames (old columns are already known).
+static inline int tri_id(int bi, int bj, int b0) { return bj * (bj + 1) / 2 - b0 * (b0 + 1) / 2 + bi; }
+static inline int tri_count(int nb, int b0) { return nb * (nb + 1) / 2 - b0 * (b0 + 1) / 2; }
 
 // Pack the upper-triangular tiles into units of <= 4 tiles touching <= 4 distinct row blocks (fewer
 // resident blocks per stage = deeper TMA pipeline and less L2 traffic).  Small problems: greedy "seed +
 // the tile that adds the fewest new blocks"; large ones: 2x2 super-blocks (4 tiles / 4 blocks off the
 // diagonal, 3 tiles / 2 blocks on it).  T=600 (5 blocks, 15 tiles) packs into 4 units of 3 blocks each.
-static void unit_add(GramUnit& u, int bi, int bj, int nb) {
+static void unit_add(GramUnit& u, int bi, int bj, int b0) {
   auto slot = [&](int blk) {
     for (int s = 0; s < u.n_slots; ++s)
       if (u.slot_block[s] == blk) return s;
@@ -63,7 +67,7 @@ static void unit_add(GramUnit& u, int bi, int bj, int nb) {
   const int sa = slot(bi), sb = slot(bj);
   u.a_slot[u.n_tiles] = sa;
   u.b_slot[u.n_tiles] = sb;
-  u.tile_id[u.n_tiles] = tri_id(bi, bj, nb);
+  u.tile_id[u.n_tiles] = tri_id(bi, bj, b0);
   ++u.n_tiles;
 }
 
@@ -76,7 +80,7 @@ static int unit_new_blocks(const GramUnit& u, int bi, int bj) {
   return (ha ? 0 : 1) + ((hb || bj == bi) ? 0 : 1);
 }
 
-static void plan_units(int nb, GramUnit* units, int* n_units, int* max_slots) {
+static void plan_units(int nb, int b0, GramUnit* units, int* n_units, int* max_slots) {
   int n = 0, ms = 0;
   auto emit = [&](GramUnit u) {
     for (int i = 1; i < u.n_tiles; ++i)  // stable insertion sort by A slot (collector reuse wants equal-A tiles adjacent)
@@ -90,18 +94,18 @@ static void plan_units(int nb, GramUnit* units, int* n_units, int* max_slots) {
     ++n;
     if (u.n_slots > ms) ms = u.n_slots;
   };
-  if (nb <= 16) {
-    const int nt = nb * (nb + 1) / 2;
+  if (tri_count(nb, b0) <= 136) {
+    const int nt = tri_count(nb, b0);
     int tb[136][2];
     bool done[136];
     int c = 0;
     for (int bi = 0; bi < nb; ++bi)
-      for (int bj = bi; bj < nb; ++bj) { tb[c][0] = bi; tb[c][1] = bj; done[c] = false; ++c; }
+      for (int bj = (bi > b0 ? bi : b0); bj < nb; ++bj) { tb[c][0] = bi; tb[c][1] = bj; done[c] = false; ++c; }
     for (int seed = 0; seed < nt; ++seed) {
       if (done[seed]) continue;
       GramUnit u;
       memset(&u, 0, sizeof(u));
-      unit_add(u, tb[seed][0], tb[seed][1], nb);
+      unit_add(u, tb[seed][0], tb[seed][1], b0);
       done[seed] = true;
       while (u.n_tiles < kMaxMma) {
         int best = -1, best_new = 99;
@@ -111,7 +115,7 @@ static void plan_units(int nb, GramUnit* units, int* n_units, int* max_slots) {
           if (u.n_slots + nw <= kMaxSlots && nw < best_new) { best = t; best_new = nw; }
         }
         if (best < 0) break;
-        unit_add(u, tb[best][0], tb[best][1], nb);
+        unit_add(u, tb[best][0], tb[best][1], b0);
         done[best] = true;
       }
       emit(u);
@@ -124,7 +128,7 @@ static void plan_units(int nb, GramUnit* units, int* n_units, int* max_slots) {
         memset(&u, 0, sizeof(u));
         for (int bi = 2 * I; bi < 2 * I + 2 && bi < nb; ++bi)
           for (int bj = 2 * J; bj < 2 * J + 2 && bj < nb; ++bj)
-            if (bi <= bj) unit_add(u, bi, bj, nb);
+            if (bi <= bj && bj >= b0) unit_add(u, bi, bj, b0);
         if (u.n_tiles) emit(u);
       }
   }
@@ -132,11 +136,12 @@ static void plan_units(int nb, GramUnit* units, int* n_units, int* max_slots) {
   if (max_slots) *max_slots = ms;
 }
 
-static GramPlan make_plan(int64_t T, int64_t K) {
+static GramPlan make_plan(int64_t T, int64_t K, int64_t T_old = 0) {
   GramPlan p;
   p.nb = (int)((T + kTile - 1) / kTile);
-  p.n_tiles = p.nb * (p.nb + 1) / 2;
-  plan_units(p.nb, nullptr, &p.n_units, &p.max_slots);
+  p.b0 = (int)(T_old / kTile);
+  p.n_tiles = tri_count(p.nb, p.b0);
+  plan_units(p.nb, p.b0, nullptr, &p.n_units, &p.max_slots);
   p.n_chunks = (int)((K + kChunk - 1) / kChunk);
   int kr = kNumSMs / p.n_units;
   if (kr < 1) kr = 1;
@@ -152,14 +157,14 @@ static GramPlan make_plan(int64_t T, int64_t K) {
 // ---------------------------------------------------------------------------------------------------
 // impl 1: CUDA cores.  CTA = one 128x128 tile x one K range; 256 threads, 8x8 register tile.
 // ---------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) gram_simt_kernel(const __nv_bfloat16* __restrict__ X, int T, int64_t K, int nb,
+__global__ void __launch_bounds__(256) gram_simt_kernel(const __nv_bfloat16* __restrict__ X, int T, int64_t K, int nb, int b0,
                                                         int n_tiles, int n_kr, int n_chunks, float* __restrict__ partial) {
   __shared__ float sA[32][kTile + 4];
   __shared__ float sB[32][kTile + 4];
   // decode tile id -> (bi, bj)
-  int tid = blockIdx.x, bi = 0;
-  while (tid >= nb - bi) { tid -= nb - bi; ++bi; }
-  const int bj = bi + tid;
+  int tid = blockIdx.x, bj = b0;
+  while (tid >= bj + 1) { tid -= bj + 1; ++bj; }
+  const int bi = tid;
   const int kr = blockIdx.y;
   const int c0 = (int)((int64_t)kr * n_chunks / n_kr), c1 = (int)((int64_t)(kr + 1) * n_chunks / n_kr);
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
@@ -201,13 +206,13 @@ __global__ void __launch_bounds__(256) gram_simt_kernel(const __nv_bfloat16* __r
 // ---------------------------------------------------------------------------------------------------
 // Sum the K ranges in fp64 (fixed order) and write both triangles of G.
 // ---------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) gram_reduce_kernel(const float* __restrict__ partial, int T, int nb, int n_tiles,
-                                                          int n_kr, double* __restrict__ G) {
+__global__ void __launch_bounds__(256) gram_reduce_kernel(const float* __restrict__ partial, int T, int nb, int b0, int n_tiles,
+                                                          int n_kr, double* __restrict__ G, int64_t ldg) {
   // grid (n_tiles, 16): a thread owns 4 consecutive columns of one tile row; the K ranges are streamed with 8
   // independent 128-bit loads in flight and added in ascending range order (fixed -> deterministic).
-  int tid = blockIdx.x, bi = 0;
-  while (tid >= nb - bi) { tid -= nb - bi; ++bi; }
-  const int bj = bi + tid;
+  int tid = blockIdx.x, bj = b0;
+  while (tid >= bj + 1) { tid -= bj + 1; ++bj; }
+  const int bi = tid;
   const int e4 = blockIdx.y * 256 + threadIdx.x;  // float4 index inside the tile, 4096 per tile
   const int r = e4 >> 5, c = (e4 & 31) * 4;
   const int gi = bi * kTile + r, gj = bj * kTile + c;
@@ -231,8 +236,8 @@ __global__ void __launch_bounds__(256) gram_reduce_kernel(const float* __restric
 #pragma unroll
   for (int u = 0; u < 4; ++u) {
     if (gj + u < T) {
-      G[(int64_t)gi * T + gj + u] = sv[u];
-      if (bi != bj) G[(int64_t)(gj + u) * T + gi] = sv[u];
+      G[(int64_t)gi * ldg + gj + u] = sv[u];
+      if (bi != bj) G[(int64_t)(gj + u) * ldg + gi] = sv[u];
     }
   }
 }
@@ -479,9 +484,7 @@ using namespace csb;
 
 extern "C" {
 
-size_t csb_gram_workspace_bytes(int64_t T, int64_t K) {
-  if (T <= 0 || K <= 0) return 0;
-  GramPlan p = make_plan(T, K);
+static size_t gram_ws_bytes(const GramPlan& p) {
   // the CUDA-core path may use more K ranges than the tensor path; size for the larger
   int kr_simt = (2 * kNumSMs + p.n_tiles - 1) / p.n_tiles;
   if (kr_simt > p.n_chunks) kr_simt = p.n_chunks;
@@ -489,25 +492,32 @@ size_t csb_gram_workspace_bytes(int64_t T, int64_t K) {
   return align_up((size_t)kr * p.n_tiles * kTile * kTile * sizeof(float), 256) + align_up(sizeof(GramUnit) * p.n_units, 256);
 }
 
-int csb_gram(const void* x, int64_t T, int64_t K, double* G, void* workspace, size_t workspace_bytes, int impl,
-             csb_stream_t stream) {
+size_t csb_gram_workspace_bytes(int64_t T, int64_t K) {
+  if (T <= 0 || K <= 0) return 0;
+  return gram_ws_bytes(make_plan(T, K, 0));  // the whole matrix is the largest job for a given T
+}
+
+int csb_gram_extend(const void* x, int64_t T_old, int64_t T, int64_t K, double* G, int64_t ldg, void* workspace,
+                    size_t workspace_bytes, int impl, csb_stream_t stream) {
   CSB_DEVICE_OR_RETURN();
   CSB_REQUIRE(x && G && workspace && T > 0 && K > 0, "gram: null argument or empty shape");
+  CSB_REQUIRE(T_old >= 0 && T_old < T && ldg >= T, "gram: need 0 <= T_old < T <= ldg (T_old=%lld T=%lld ldg=%lld)", (long long)T_old,
+              (long long)T, (long long)ldg);
   CSB_REQUIRE(K % 8 == 0 && (reinterpret_cast<uintptr_t>(x) & 15u) == 0, "gram: K %% 8 != 0 or x not 16-byte aligned");
   CSB_REQUIRE(T < (1 << 24), "gram: T too large");
-  if (workspace_bytes < csb_gram_workspace_bytes(T, K)) {
-    set_error("gram: workspace %zu < %zu", workspace_bytes, csb_gram_workspace_bytes(T, K));
+  GramPlan p = make_plan(T, K, T_old);
+  if (workspace_bytes < gram_ws_bytes(p)) {
+    set_error("gram: workspace %zu < %zu", workspace_bytes, gram_ws_bytes(p));
     return CSB_ERR_WORKSPACE;
   }
-  GramPlan p = make_plan(T, K);
   cudaStream_t s = as_stream(stream);
   float* partial = reinterpret_cast<float*>(workspace);
   int n_kr;
-  if (impl == 1) {
+  if ((impl & 15) == 1) {
     n_kr = (2 * kNumSMs + p.n_tiles - 1) / p.n_tiles;
     if (n_kr > p.n_chunks) n_kr = p.n_chunks;
     dim3 grid((unsigned)p.n_tiles, (unsigned)n_kr);
-    gram_simt_kernel<<<grid, 256, 0, s>>>((const __nv_bfloat16*)x, (int)T, K, p.nb, p.n_tiles, n_kr, p.n_chunks, partial);
+    gram_simt_kernel<<<grid, 256, 0, s>>>((const __nv_bfloat16*)x, (int)T, K, p.nb, p.b0, p.n_tiles, n_kr, p.n_chunks, partial);
     int st = check_launch("gram_simt");
     if (st) return st;
   } else if ((impl & 15) == 0) {
@@ -519,18 +529,19 @@ int csb_gram(const void* x, int64_t T, int64_t K, double* G, void* workspace, si
     static thread_local GramUnitTable table;  // plan for small problems, passed by value
     cudaError_t e = cudaSuccess;
     if (p.n_units <= kMaxParamUnits) {
-      static thread_local int table_nb = -1;
-      if (table_nb != p.nb) {
+      static thread_local int table_nb = -1, table_b0 = -1;
+      if (table_nb != p.nb || table_b0 != p.b0) {
         int nu = 0;
-        plan_units(p.nb, table.u, &nu, nullptr);
+        plan_units(p.nb, p.b0, table.u, &nu, nullptr);
         table_nb = p.nb;
+        table_b0 = p.b0;
       }
     } else {
       d_units = reinterpret_cast<GramUnit*>(reinterpret_cast<char*>(workspace) +
                                             align_up((size_t)kr_max * p.n_tiles * kTile * kTile * sizeof(float), 256));
       GramUnit* h_units = (GramUnit*)malloc(sizeof(GramUnit) * p.n_units);
       int nu = 0;
-      plan_units(p.nb, h_units, &nu, nullptr);
+      plan_units(p.nb, p.b0, h_units, &nu, nullptr);
       e = cudaMemcpyAsync(d_units, h_units, sizeof(GramUnit) * nu, cudaMemcpyHostToDevice, s);
       cudaStreamSynchronize(s);  // pageable source buffer is freed below (large-T path only)
       free(h_units);
@@ -562,8 +573,13 @@ int csb_gram(const void* x, int64_t T, int64_t K, double* G, void* workspace, si
     return CSB_ERR_ARG;
   }
   dim3 rgrid((unsigned)p.n_tiles, 16);
-  gram_reduce_kernel<<<rgrid, 256, 0, s>>>(partial, (int)T, p.nb, p.n_tiles, n_kr, G);
+  gram_reduce_kernel<<<rgrid, 256, 0, s>>>(partial, (int)T, p.nb, p.b0, p.n_tiles, n_kr, G, ldg);
   return check_launch("gram_reduce");
+}
+
+int csb_gram(const void* x, int64_t T, int64_t K, double* G, void* workspace, size_t workspace_bytes, int impl,
+             csb_stream_t stream) {
+  return csb_gram_extend(x, 0, T, K, G, T, workspace, workspace_bytes, impl, stream);
 }
 
 }  // extern "C"

@@ -20,6 +20,7 @@ namespace csb {
 
 struct SolverArgs {
   const double* G;
+  int64_t ldg;  // leading dimension of G
   const void* ts;
   int T, k;
   int max_iter;
@@ -156,7 +157,7 @@ __device__ void kmeanspp_block(const SolverArgs& a, float* s_near, const double*
     }
     if (m + 1 < k) {
       const double gcc = diag[c];
-      const double* gc = G + (int64_t)c * T;
+      const double* gc = G + (int64_t)c * a.ldg;
       float part = 0.f;
       for (int i0 = threadIdx.x; i0 < T; i0 += 4 * kSolverThreads) {
         double g[4];
@@ -326,7 +327,7 @@ __device__ void compute_S(const SolverArgs& a, const int* s_offs, const int* s_m
     const int i = (int)(idx / ncols);
     const int j = cols[(int)(idx - (int64_t)i * ncols)];
     const int beg = s_offs[j], end = s_offs[j + 1];
-    const double* g = a.G + (int64_t)i * T;
+    const double* g = a.G + (int64_t)i * a.ldg;
     double s = 0.0;
     int e = beg;
     for (; e + 4 <= end; e += 4) {
@@ -381,7 +382,7 @@ __global__ void __launch_bounds__(kSolverThreads) kmeans_solver_kernel(SolverArg
     }
     mark(a, 1);
     for (int i = threadIdx.x; i < T; i += blockDim.x) {
-      const double g = a.G[(int64_t)i * T + i];
+      const double g = a.G[(int64_t)i * a.ldg + i];
       a.diag[i] = g;
       if (a.diag_in_smem) s_diag[i] = g;
     }
@@ -686,6 +687,7 @@ int csb_kmeans_solve(const double* G, const void* timestamps, const csb_kmeans_p
   CSB_REQUIRE(p->n_init_given == p->k || exp_noise, "kmeans_solve: exp_noise required when centres are sampled");
   CSB_REQUIRE(p->n_reseed_pool == 0 || reseed_pool, "kmeans_solve: reseed_pool is null");
   CSB_REQUIRE(p->max_iteration >= 0, "kmeans_solve: max_iteration < 0");
+  CSB_REQUIRE(p->ldg == 0 || p->ldg >= p->T, "kmeans_solve: ldg < T");
   const int64_t T = p->T, k = p->k;
   const SolverSmemPlan sp = plan_smem(T, k);
   CSB_REQUIRE(sp.bytes <= 225 * 1024, "kmeans_solve: T=%lld k=%lld do not fit the shared-memory membership (T <= ~25k)", (long long)T,
@@ -695,7 +697,7 @@ int csb_kmeans_solve(const double* G, const void* timestamps, const csb_kmeans_p
     return CSB_ERR_WORKSPACE;
   }
   SolverArgs a;
-  a.G = G; a.ts = timestamps; a.T = (int)T; a.k = (int)k; a.max_iter = p->max_iteration; a.alpha = p->alpha; a.tol = p->tol;
+  a.G = G; a.ldg = p->ldg > 0 ? p->ldg : T; a.ts = timestamps; a.T = (int)T; a.k = (int)k; a.max_iter = p->max_iteration; a.alpha = p->alpha; a.tol = p->tol;
   a.n_init_given = (int)p->n_init_given; a.n_reseed_pool = (int)p->n_reseed_pool;
   a.init_indices = init_indices; a.exp_noise = exp_noise; a.reseed_pool = reseed_pool; a.assignments = assignments;
   a.ct_out = centroid_times; a.member_offsets = member_offsets; a.members = members; a.status = status;

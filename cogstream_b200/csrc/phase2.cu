@@ -39,7 +39,7 @@ __device__ __forceinline__ int block_exclusive_scan(int v, int* warp_tot /* smem
 //   rowsum_i = sum_{m in M} G_im                     (M = members of assign[i])
 //   dist_i^2 = G_ii - (2/n) rowsum_i + (1/n^2) sum_{m in M} rowsum_m
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) gram_rowsum_kernel(const double* __restrict__ G, int T, const int64_t* __restrict__ assign,
+__global__ void __launch_bounds__(256) gram_rowsum_kernel(const double* __restrict__ G, int64_t ldg, int T, const int64_t* __restrict__ assign,
                                                           const int32_t* __restrict__ offs, const int32_t* __restrict__ memb,
                                                           double* __restrict__ rowsum) {
   const int lane = threadIdx.x & 31;
@@ -47,14 +47,14 @@ __global__ void __launch_bounds__(256) gram_rowsum_kernel(const double* __restri
   if (i >= T) return;
   const int j = (int)assign[i];
   const int beg = offs[j], end = offs[j + 1];
-  const double* gi = G + (int64_t)i * T;
+  const double* gi = G + (int64_t)i * ldg;
   double s = 0.0;
   for (int m = beg + lane; m < end; m += 32) s += gi[memb[m]];
   s = warp_sum(s);
   if (lane == 0) rowsum[i] = s;
 }
 
-__global__ void __launch_bounds__(256) dist_gram_kernel(const double* __restrict__ G, int T, const int64_t* __restrict__ assign,
+__global__ void __launch_bounds__(256) dist_gram_kernel(const double* __restrict__ G, int64_t ldg, int T, const int64_t* __restrict__ assign,
                                                         const int32_t* __restrict__ offs, const int32_t* __restrict__ memb,
                                                         const double* __restrict__ rowsum, float* __restrict__ dist) {
   const int lane = threadIdx.x & 31;
@@ -67,7 +67,7 @@ __global__ void __launch_bounds__(256) dist_gram_kernel(const double* __restrict
   q = warp_sum(q);
   if (lane == 0) {
     const double nn = (double)(end - beg);
-    const double d2 = G[(int64_t)i * T + i] - 2.0 * (rowsum[i] / nn) + q / (nn * nn);
+    const double d2 = G[(int64_t)i * ldg + i] - 2.0 * (rowsum[i] / nn) + q / (nn * nn);
     dist[i] = (float)sqrt(d2 > 0.0 ? d2 : 0.0);
   }
 }
@@ -727,14 +727,14 @@ using namespace csb;
 
 extern "C" {
 
-int csb_dist_to_assigned_gram(const double* G, int64_t T, int64_t k, const int64_t* assignments, const int32_t* offs,
+int csb_dist_to_assigned_gram(const double* G, int64_t ldg, int64_t T, int64_t k, const int64_t* assignments, const int32_t* offs,
                               const int32_t* memb, float* dist, double* rowsum_ws, csb_stream_t stream) {
   CSB_DEVICE_OR_RETURN();
-  CSB_REQUIRE(G && assignments && offs && memb && dist && rowsum_ws && T > 0 && k > 0, "dist_to_assigned_gram: null argument");
+  CSB_REQUIRE(G && assignments && offs && memb && dist && rowsum_ws && T > 0 && k > 0 && ldg >= T, "dist_to_assigned_gram: null argument or ldg < T");
   cudaStream_t s = as_stream(stream);
-  gram_rowsum_kernel<<<(unsigned)((T + 7) / 8), 256, 0, s>>>(G, (int)T, assignments, offs, memb, rowsum_ws);
+  gram_rowsum_kernel<<<(unsigned)((T + 7) / 8), 256, 0, s>>>(G, ldg, (int)T, assignments, offs, memb, rowsum_ws);
   count_launch(1);
-  dist_gram_kernel<<<(unsigned)((T + 7) / 8), 256, 0, s>>>(G, (int)T, assignments, offs, memb, rowsum_ws, dist);
+  dist_gram_kernel<<<(unsigned)((T + 7) / 8), 256, 0, s>>>(G, ldg, (int)T, assignments, offs, memb, rowsum_ws, dist);
   return check_launch("dist_to_assigned_gram");
 }
 

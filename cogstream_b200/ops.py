@@ -96,6 +96,32 @@ def gram(x: torch.Tensor, *, impl: int = 0, out: Optional[torch.Tensor] = None,
     return G
 
 
+def _gram_view(G: torch.Tensor, name: str = "G"):
+    """G may be the leading [T,T] corner of a larger row-major buffer: returns (T, leading dimension)."""
+    if not (isinstance(G, torch.Tensor) and G.is_cuda and G.dtype == torch.float64 and G.dim() == 2 and G.shape[0] == G.shape[1]):
+        raise TypeError(f"{name}: expected a square float64 CUDA matrix")
+    if G.stride(1) != 1 or G.stride(0) < G.shape[1]:
+        raise ValueError(f"{name}: rows must be contiguous (stride {G.stride()})")
+    return G.shape[0], G.stride(0)
+
+
+def gram_extend(x: torch.Tensor, T_old: int, G_buf: torch.Tensor, *, impl: int = 0, workspace: Optional[torch.Tensor] = None):
+    """x [T,K] bf16 (ALL frames so far), G_buf [T_max,T_max] f64 whose [:T_old,:T_old] corner is valid:
+    fills rows / columns [T_old, T) in place and returns the [T,T] view."""
+    _need(x, "x", torch.bfloat16, 2)
+    T, K = x.shape
+    _need(G_buf, "G_buf", torch.float64, 2)
+    ldg = G_buf.shape[1]
+    if G_buf.shape[0] < T or ldg < T:
+        raise ValueError("gram_extend: G_buf too small")
+    need = gram_workspace_bytes(T, K)
+    ws = workspace if workspace is not None and workspace.numel() >= need else torch.empty(need, dtype=torch.uint8, device=x.device)
+    with _on_device(x):
+        check(_lib.load().csb_gram_extend(x.data_ptr(), int(T_old), T, K, G_buf.data_ptr(), ldg, ws.data_ptr(), ws.numel(), impl,
+                                          _stream(x)), "gram_extend")
+    return G_buf[:T, :T]
+
+
 def kmeans_workspace_bytes(T: int, k: int) -> int:
     return int(_lib.load().csb_kmeans_workspace_bytes(T, k))
 
@@ -128,7 +154,7 @@ def kmeans_solve(G: torch.Tensor, timestamps: torch.Tensor, buf: KMeansBuffers, 
                  exp_noise: Optional[torch.Tensor], reseed_pool: Optional[torch.Tensor], alpha: float = 2.0,
                  max_iteration: int = 30, tol: float = 1e-4) -> None:
     """k-means++ + Lloyd on the Gram matrix.  ``buf.init_indices[:n_init_given]`` must be filled."""
-    _need(G, "G", torch.float64, 2)
+    _, ldg = _gram_view(G)
     _need(timestamps, "timestamps", None, 1)
     if timestamps.dtype not in _TS_DTYPE:
         raise TypeError(f"timestamps must be float32 or float64, got {timestamps.dtype}")
@@ -143,7 +169,7 @@ def kmeans_solve(G: torch.Tensor, timestamps: torch.Tensor, buf: KMeansBuffers, 
     if reseed_pool is not None:
         _need(reseed_pool, "reseed_pool", torch.int64, 1)
         n_pool = reseed_pool.numel()
-    p = KMeansParams(T, k, _TS_DTYPE[timestamps.dtype], int(max_iteration), float(alpha), float(tol), int(n_init_given), n_pool)
+    p = KMeansParams(T, k, _TS_DTYPE[timestamps.dtype], int(max_iteration), float(alpha), float(tol), int(n_init_given), n_pool, ldg)
     with _on_device(G):
         check(_lib.load().csb_kmeans_solve(
             G.data_ptr(), timestamps.data_ptr(), C.byref(p), buf.init_indices.data_ptr(), _ptr(exp_noise), _ptr(reseed_pool),
@@ -200,12 +226,11 @@ def dist_to_assigned(x: torch.Tensor, centroids: torch.Tensor, assignments: torc
 
 def dist_to_assigned_gram(G: torch.Tensor, assignments: torch.Tensor, event_offsets: torch.Tensor, order: torch.Tensor,
                           k: int) -> torch.Tensor:
-    _need(G, "G", torch.float64, 2)
-    T = G.shape[0]
+    T, ldg = _gram_view(G)
     dist = torch.empty(T, dtype=torch.float32, device=G.device)
     ws = torch.empty(T, dtype=torch.float64, device=G.device)
     with _on_device(G):
-        check(_lib.load().csb_dist_to_assigned_gram(G.data_ptr(), T, k, assignments.data_ptr(), event_offsets.data_ptr(),
+        check(_lib.load().csb_dist_to_assigned_gram(G.data_ptr(), ldg, T, k, assignments.data_ptr(), event_offsets.data_ptr(),
                                                     order.data_ptr(), dist.data_ptr(), ws.data_ptr(), _stream(G)),
               "dist_to_assigned_gram")
     return dist

@@ -85,6 +85,12 @@ CSB_API size_t csb_gram_workspace_bytes(int64_t T, int64_t K);
 CSB_API int csb_gram(const void* x_bf16, int64_t T, int64_t K, double* G, void* workspace, size_t workspace_bytes,
              int impl, csb_stream_t stream);
 
+/* Incremental form for an append-only stream (the reference re-clusters the whole history for every new
+ * question, evaluate/answer_generate.py:120-135): frames [0,T_old) are already in G (leading dimension ldg >= T); only the
+ * tiles that touch frames [T_old,T) are computed -- work ~ (T - T_old) * T * K instead of T^2 * K.  x holds all T frames. */
+CSB_API int csb_gram_extend(const void* x_bf16, int64_t T_old, int64_t T, int64_t K, double* G, int64_t ldg, void* workspace,
+                            size_t workspace_bytes, int impl, csb_stream_t stream);
+
 typedef struct csb_kmeans_params {
   int64_t T;              /* frames */
   int64_t k;              /* clusters, T > k >= 1 (T <= k is the caller's early return, :30-32) */
@@ -95,6 +101,7 @@ typedef struct csb_kmeans_params {
   int64_t n_init_given;   /* how many entries of init_indices are prescribed (>=1: the first centre is
                              always drawn by the host, :41); the remaining k - n are sampled k-means++ */
   int64_t n_reseed_pool;  /* entries available in reseed_pool (host random.randint(0, T-1) draws) */
+  int64_t ldg;            /* leading dimension of G (elements); 0 means T */
 } csb_kmeans_params;
 
 /* Device-side result block, written by csb_kmeans_solve (read it after a stream sync). */
@@ -156,7 +163,7 @@ CSB_API int csb_dist_to_assigned(const void* x_bf16, int64_t T, int64_t K, const
                          const int64_t* assignments, float* dist, csb_stream_t stream);
 /* Same distances from the Gram matrix and the event CSR of csb_event_order (no pass over x).
  *   rowsum_ws [T] fp64 scratch. */
-CSB_API int csb_dist_to_assigned_gram(const double* G, int64_t T, int64_t k, const int64_t* assignments,
+CSB_API int csb_dist_to_assigned_gram(const double* G, int64_t ldg, int64_t T, int64_t k, const int64_t* assignments,
                               const int32_t* event_offsets, const int32_t* order, float* dist,
                               double* rowsum_ws, csb_stream_t stream);
 /* Per event the n_rep members with the smallest dist (ascending dist, lowest index on ties); events with

@@ -520,3 +520,34 @@ def test_stream_pool_batch_matches_single_streams(dev):
             row = dict(zip(STATS_FIELDS, rows[i].tolist()))
             assert row["T"] == T and row["k"] == k and row["n_kept"] == int(p2.mask.sum()) and row["n_minor"] == len(p2.minor)
             assert row["iterations"] == p1.info.iterations
+
+
+def test_stream_cache_incremental_reclustering(dev):
+    """Appending segments and re-clustering on the cached Gram matrix == a from-scratch run on all frames so far
+    (config 4 in miniature: new question -> new k -> fresh k-means, but only the new frames' Gram tiles are computed)."""
+    from cogstream_b200 import StreamCache
+    P, D = 6, 256
+    T_total = 420
+    st = synthetic.make_stream(T_total, P, D, 77, C=8)
+    f3 = st.features.view(T_total, P, D)
+    cache = StreamCache(512, P, D, device=dev)
+    g = torch.Generator().manual_seed(1)
+    done = 0
+    for seg in (150, 130, 140):  # ragged segment lengths: block boundaries at 128 / 256 / 384 are crossed mid-segment
+        cache.append(f3[done: done + seg].to(dev), st.timestamps[done: done + seg].to(dev))
+        done += seg
+        T = done
+        x = f3[:T].reshape(T, -1).to(dev)
+        Gfull = ops.gram(x)
+        assert float((cache.gram - Gfull).abs().max() / Gfull.diagonal().max()) < 2e-6
+        assert torch.equal(cache.gram, cache.gram.T)
+        k = math.ceil(T / 15)
+        init = torch.randperm(T, generator=g)[:k].tolist()
+        pool = torch.randint(0, T, (64,), generator=g)
+        buf, kk = cache.cluster(init_indices=init, reseed_pool=pool.to(dev))
+        assert kk == k
+        info = orc.KMeansInfo()
+        c, ct, a = orc.kmeans_with_time_min_max(f3[:T], st.timestamps[:T], k, init_indices=init, reseed_indices=pool.tolist(), info=info)
+        assert torch.equal(buf.assignments.cpu(), a) and torch.equal(buf.centroid_times.cpu(), ct)
+        assert ops.decode_status(buf.status)["iterations"] == info.iterations
+        assert rel_err(cache.centroids(buf, k), c) < 1e-6
