@@ -14,6 +14,8 @@
 // iteration).  k-means++ runs on CTA 0; in the loop every CTA rebuilds the membership CSR in its own
 // shared memory (identical by construction), so only the assignments and the S columns cross CTAs.
 // Columns of S are recomputed only for clusters whose membership changed (version stamps per buffer).
+#include <stdlib.h>
+
 #include "csb_common.cuh"
 
 namespace csb {
@@ -90,8 +92,10 @@ constexpr int kSolverWarps = kSolverThreads / 32;
 // One L2 round trip (row c of G) per round; the update pass leaves per-warp partial sums of nearest^2 in smem
 // (added in warp order by every thread -> one fixed order), warps reduce their slice of the scores and the 8
 // partial winners meet in smem.
+template <int NT>
 __device__ void kmeanspp_block(const SolverArgs& a, float* s_near, const double* diag, float* s_wv, int* s_wi, float* s_ws,
                                int* used_io, int* n_noise_used, int* n_degenerate) {
+  constexpr int NW = NT / 32;
   const int T = a.T, k = a.k;
   const double* G = a.G;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -108,7 +112,7 @@ __device__ void kmeanspp_block(const SolverArgs& a, float* s_near, const double*
       // :53-54 sum of nearest^2: per-warp partials were left in s_ws by the update pass of the previous round
       float sum = s_ws[0];
 #pragma unroll
-      for (int w = 1; w < kSolverWarps; ++w) sum += s_ws[w];
+      for (int w = 1; w < NW; ++w) sum += s_ws[w];
       if (sum == 0.f) {                           // :55-57
         ++degenerate;
         c = 0;
@@ -119,17 +123,17 @@ __device__ void kmeanspp_block(const SolverArgs& a, float* s_near, const double*
         ++noise_row;
         float best = -1.f;
         int besti = 0x7fffffff;
-        for (int i0 = threadIdx.x; i0 < T; i0 += 4 * kSolverThreads) {
+        for (int i0 = threadIdx.x; i0 < T; i0 += 4 * NT) {
           float nd[4], nz[4];
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
-            const int ii = i0 + u * kSolverThreads;
+            const int ii = i0 + u * NT;
             nd[u] = ii < T ? s_near[ii] : 0.f;
             nz[u] = ii < T ? __ldg(noise + ii) : 1.f;
           }
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
-            const int ii = i0 + u * kSolverThreads;
+            const int ii = i0 + u * NT;
             const float p = __fdiv_rn(__fmul_rn(nd[u], nd[u]), sum);  // :59
             const float sc = __fdiv_rn(p, nz[u]);                      // multinomial: argmax(p / Exp(1)), first max
             if (ii < T && sc > best) { best = sc; besti = ii; }
@@ -146,7 +150,7 @@ __device__ void kmeanspp_block(const SolverArgs& a, float* s_near, const double*
         best = s_wv[0];
         besti = s_wi[0];
 #pragma unroll
-        for (int w = 1; w < kSolverWarps; ++w) {
+        for (int w = 1; w < NW; ++w) {
           const float ov = s_wv[w];
           const int oi = s_wi[w];
           if (ov > best || (ov == best && oi < besti)) { best = ov; besti = oi; }
@@ -159,16 +163,16 @@ __device__ void kmeanspp_block(const SolverArgs& a, float* s_near, const double*
       const double gcc = diag[c];
       const double* gc = G + (int64_t)c * a.ldg;
       float part = 0.f;
-      for (int i0 = threadIdx.x; i0 < T; i0 += 4 * kSolverThreads) {
+      for (int i0 = threadIdx.x; i0 < T; i0 += 4 * NT) {
         double g[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-          const int ii = i0 + u * kSolverThreads;
+          const int ii = i0 + u * NT;
           g[u] = ii < T ? __ldg(gc + ii) : 0.0;
         }
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-          const int ii = i0 + u * kSolverThreads;
+          const int ii = i0 + u * NT;
           if (ii < T) {
             const double d2 = diag[ii] + gcc - 2.0 * g[u];
             const float d = (float)sqrt(d2 > 0.0 ? d2 : 0.0);
@@ -340,6 +344,40 @@ __device__ void compute_S(const SolverArgs& a, const int* s_offs, const int* s_m
   }
 }
 
+// ---- k-means++ as its own single-CTA launch: while the 39 dependent sampling rounds run, the other SMs stay free for
+// other streams' kernels (inside the cooperative kernel they would sit spinning at the grid barrier for >100 us) ----
+template <typename TS, int kInitThreads>
+__global__ void __launch_bounds__(kInitThreads) kmeanspp_kernel(SolverArgs a) {
+  extern __shared__ double smem_init[];
+  const int T = a.T;
+  double* s_diag = smem_init;                                                   // [T] if diag_in_smem
+  float* s_near = reinterpret_cast<float*>(smem_init + (a.diag_in_smem ? T : 0));  // [T]
+  __shared__ float s_wv[kInitThreads / 32];
+  __shared__ int s_wi[kInitThreads / 32];
+  __shared__ float s_ws[kInitThreads / 32];
+  csb_kmeans_status* st = a.status;
+  if (threadIdx.x == 0) {
+    st->iterations = 0; st->converged = 0; st->n_reseed_used = 0; st->degenerate_rounds = 0;
+    st->reseed_overflow = 0; st->n_noise_used = 0; st->min_margin = __int_as_float(0x7f800000); st->last_shift = 0.f;
+  }
+  mark(a, 1);
+  for (int i = threadIdx.x; i < T; i += blockDim.x) {
+    const double g = a.G[(int64_t)i * a.ldg + i];
+    a.diag[i] = g;
+    if (a.diag_in_smem) s_diag[i] = g;
+  }
+  __syncthreads();
+  int used = 0, n_noise = 0, n_deg = 0;
+  if (a.n_init_given < a.k)
+    kmeanspp_block<kInitThreads>(a, s_near, a.diag_in_smem ? s_diag : a.diag, s_wv, s_wi, s_ws, &used, &n_noise, &n_deg);
+  if (threadIdx.x == 0) {
+    st->degenerate_rounds = n_deg;
+    st->n_noise_used = n_noise;
+    *a.used = used;  // pool entries consumed by degenerate rounds
+  }
+  mark(a, 2);
+}
+
 template <typename TS>
 __global__ void __launch_bounds__(kSolverThreads) kmeans_solver_kernel(SolverArgs a) {
   extern __shared__ double smem_d[];
@@ -361,10 +399,6 @@ __global__ void __launch_bounds__(kSolverThreads) kmeans_solver_kernel(SolverArg
   int* s_verbuf[2] = {s_ver + k, s_ver + 2 * k};
   int* s_cols = s_ver + 3 * k;
   int* s_cntw = s_cols + k;
-  float* s_near = reinterpret_cast<float*>(s_assign);  // [T], k-means++ only (CTA 0, before s_assign is used)
-  __shared__ float s_wv[kSolverWarps];
-  __shared__ int s_wi[kSolverWarps];
-  __shared__ float s_ws[kSolverWarps];
   __shared__ int s_ncols;
 
   unsigned bar = 0;
@@ -374,40 +408,17 @@ __global__ void __launch_bounds__(kSolverThreads) kmeans_solver_kernel(SolverArg
   int used = 0;
   const double* diag = a.diag_in_smem ? s_diag : a.diag;
 
-  // ---------------- init: k-means++ on CTA 0, the others wait at the barrier ----------------
-  if (blockIdx.x == 0) {
-    if (threadIdx.x == 0) {
-      st->iterations = 0; st->converged = 0; st->n_reseed_used = 0; st->degenerate_rounds = 0;
-      st->reseed_overflow = 0; st->n_noise_used = 0; st->min_margin = __int_as_float(0x7f800000); st->last_shift = 0.f;
-    }
-    mark(a, 1);
-    for (int i = threadIdx.x; i < T; i += blockDim.x) {
-      const double g = a.G[(int64_t)i * a.ldg + i];
-      a.diag[i] = g;
-      if (a.diag_in_smem) s_diag[i] = g;
-    }
-    __syncthreads();
-    int n_noise = 0, n_deg = 0;
-    if (a.n_init_given < k) kmeanspp_block(a, s_near, diag, s_wv, s_wi, s_ws, &used, &n_noise, &n_deg);
-    if (threadIdx.x == 0) {
-      st->degenerate_rounds = n_deg;
-      st->n_noise_used = n_noise;
-      *a.used = used;  // pool entries consumed by degenerate rounds
-    }
-    __syncthreads();
-  }
-  mark(a, 2);
-  grid_sync(a.barrier, bar, nb);
-  used = __ldcg(a.used);
-  if (blockIdx.x != 0 && a.diag_in_smem)
-    for (int i = threadIdx.x; i < T; i += blockDim.x) s_diag[i] = __ldcg(a.diag + i);
+  // ---------------- the k-means++ kernel ran before this launch: centres, diagonal and pool usage are in global memory ------
+  used = *a.used;
+  if (a.diag_in_smem)
+    for (int i = threadIdx.x; i < T; i += blockDim.x) s_diag[i] = a.diag[i];
   // initial centres: cluster j = { init[j] }
   for (int j = threadIdx.x; j < k; j += blockDim.x) {
-    const int c = (int)__ldcg(a.init_indices + j);
+    const int c = (int)a.init_indices[j];
     s_offs[j] = j;
     s_memb[j] = c;
     s_ctb[0][j] = (double)load_ts<TS>(a.ts, c);  // :66
-    s_q[0][j] = __ldcg(a.diag + c);
+    s_q[0][j] = a.diag[c];
     s_rn[j] = 1.0;
     s_nn[j] = 1.0;
     s_ver[j] = 1;
@@ -725,7 +736,29 @@ int csb_kmeans_solve(const double* G, const void* timestamps, const csb_kmeans_p
   int dev = 0, sms = kNumSMs;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  int64_t nb = (T + kSolverWarps - 1) / kSolverWarps;  // a warp per frame in the assignment phase
+  // k-means++ (or just the diagonal / status reset when every centre is prescribed): one CTA
+  {
+    // few warps = cheap block barriers: the rounds are a dependent chain, each about (frames / threads) elements of work
+    int nt = T <= 1024 ? 256 : (T <= 4096 ? 512 : 1024);
+    if (const char* o = getenv("CSB_INIT_THREADS")) nt = atoi(o);
+    const bool f64 = p->ts_dtype == CSB_F64;
+    void (*ikern)(SolverArgs) = nullptr;
+    if (nt <= 128) { nt = 128; ikern = f64 ? kmeanspp_kernel<double, 128> : kmeanspp_kernel<float, 128>; }
+    else if (nt <= 256) { nt = 256; ikern = f64 ? kmeanspp_kernel<double, 256> : kmeanspp_kernel<float, 256>; }
+    else if (nt <= 512) { nt = 512; ikern = f64 ? kmeanspp_kernel<double, 512> : kmeanspp_kernel<float, 512>; }
+    else { nt = 1024; ikern = f64 ? kmeanspp_kernel<double, 1024> : kmeanspp_kernel<float, 1024>; }
+    const size_t ismem = sizeof(float) * T + (sp.diag_in_smem ? sizeof(double) * T : 0) + 16;
+    if (ismem > 48 * 1024) {
+      e = cudaFuncSetAttribute(ikern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ismem);
+      if (e != cudaSuccess) { set_error("kmeans_solve: init smem attr: %s", cudaGetErrorString(e)); return CSB_ERR_CUDA; }
+    }
+    ikern<<<1, nt, ismem, s>>>(a);
+    int st = check_launch("kmeanspp");
+    if (st) return st;
+  }
+  // Lloyd loop: two frames per warp in the assignment phase -- the loop is latency-bound, so fewer resident CTAs cost little
+  // time and leave the other SMs to the bandwidth-bound kernels of the streams that run concurrently
+  int64_t nb = (T + 2 * kSolverWarps - 1) / (2 * kSolverWarps);
   if (nb > sms) nb = sms;
   if (nb < 1) nb = 1;
   void* args[] = {&a};
