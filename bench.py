@@ -375,41 +375,61 @@ def run_ours(args):
 
 
 def _stage_times(sc, d, ev_d, q_d, reps=5):
-    """Average device time of every launcher of the path, CUDA events on the launching stream."""
+    """Device time of every launcher of the path: each stage is launched `reps` times back to back between two CUDA events on
+    the launching stream (so host launch latency is not in the number), after one in-order pass has set up its inputs."""
     from cogstream_b200 import ops
 
     T, P, k = sc.T, sc.P, sc.k
     x2 = d.features.view(T, sc.K)
-    acc = {}
+    noise = sc.noise[: k - 1]
+    state = {}
 
-    def rec(name, fn):
+    def solve():
+        ops.kmeans_solve(sc.G, d.timestamps, sc.km, n_init_given=1, exp_noise=noise, reseed_pool=sc.pool, alpha=sc.cfg.alpha,
+                         max_iteration=sc.cfg.max_iteration, tol=sc.cfg.tol)
+
+    def dist():
+        state["dist"] = ops.dist_to_assigned_gram(sc.G, sc.km.assignments, sc.km.event_offsets, sc.km.event_order, k)
+
+    def reps_():
+        state["rflags"] = ops.select_representatives(state["dist"], sc.km.assignments, k, 2)[2]
+
+    def cos():
+        state["low"] = ops.cosine_flags(q_d.view(-1), ev_d, 0.45)[1]
+
+    def minor():
+        state["mflags"] = ops.minor_frames(sc.km.assignments, state["low"], state["rflags"])[0]
+
+    stages = [
+        ("gram", lambda: ops.gram(x2, out=sc.G, workspace=sc.gram_ws)),
+        ("rng_noise", lambda: noise.exponential_(1)),
+        ("kmeans_solve", solve),
+        ("centroid_gather", lambda: ops.centroid_gather(x2, sc.km.member_offsets, sc.km.members, sc.km.event_offsets, k,
+                                                        sc.centroids, sc.packed)),
+        ("dist_gram", dist),
+        ("select_reps", reps_),
+        ("cosine_flags", cos),
+        ("minor_frames", minor),
+        ("pixel_mask", lambda: ops.pixel_mask(d.pixel_values, T, P, sc.W, minor_flags=state["mflags"], out=sc.mask)),
+        ("compact_tokens", lambda: ops.compact_tokens(d.features, T, P, sc.mask, state["mflags"], out=sc.out, workspace=sc.compact_ws)),
+        ("filter_ids", lambda: ops.filter_ids(d.input_ids, sc.image_token_index, sc.mask, d.attention_mask)),
+    ]
+    sc.km.init_indices[:1].fill_(random.randint(0, T - 1))
+    sc.pool.random_(0, T)
+    for _, fn in stages:  # in-order pass: every stage sees valid inputs
+        fn()
+    out = {}
+    for name, fn in stages:
+        fn()
+        torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        out = fn()
+        for _ in range(reps):
+            fn()
         e1.record()
-        acc.setdefault(name, []).append((e0, e1))
-        return out
-
-    for _ in range(reps + 1):
-        rec("gram", lambda: ops.gram(x2, out=sc.G, workspace=sc.gram_ws))
-        sc.km.init_indices[:1].fill_(random.randint(0, T - 1))
-        noise = sc.noise[: k - 1]
-        rec("rng_noise", lambda: noise.exponential_(1))
-        sc.pool.random_(0, T)
-        rec("kmeans_solve", lambda: ops.kmeans_solve(sc.G, d.timestamps, sc.km, n_init_given=1, exp_noise=noise, reseed_pool=sc.pool,
-                                                     alpha=sc.cfg.alpha, max_iteration=sc.cfg.max_iteration, tol=sc.cfg.tol))
-        rec("centroid_gather", lambda: ops.centroid_gather(x2, sc.km.member_offsets, sc.km.members, sc.km.event_offsets, k,
-                                                           sc.centroids, sc.packed))
-        order, off = sc.km.event_order, sc.km.event_offsets
-        dist = rec("dist_gram", lambda: ops.dist_to_assigned_gram(sc.G, sc.km.assignments, off, order, k))
-        _, _, rflags = rec("select_reps", lambda: ops.select_representatives(dist, sc.km.assignments, k, 2))
-        _, low = rec("cosine_flags", lambda: ops.cosine_flags(q_d.view(-1), ev_d, 0.45))
-        mflags, _, _ = rec("minor_frames", lambda: ops.minor_frames(sc.km.assignments, low, rflags))
-        rec("pixel_mask", lambda: ops.pixel_mask(d.pixel_values, T, P, sc.W, minor_flags=mflags, out=sc.mask))
-        rec("compact_tokens", lambda: ops.compact_tokens(d.features, T, P, sc.mask, mflags, out=sc.out, workspace=sc.compact_ws))
-        rec("filter_ids", lambda: ops.filter_ids(d.input_ids, sc.image_token_index, sc.mask, d.attention_mask))
-    torch.cuda.synchronize()
-    return {n: round(statistics.mean(a.elapsed_time(b) for a, b in ev[1:]), 5) for n, ev in acc.items()}
+        torch.cuda.synchronize()
+        out[name] = round(e0.elapsed_time(e1) / reps, 5)
+    return out
 
 
 def _roofline(stages, sc, d):
@@ -466,7 +486,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--graphs", type=int, default=1, help="replay each phase as a CUDA graph (device-resident run)")
-    ap.add_argument("--depth", type=int, default=4, help="steps (independent streams) kept in flight per GPU")
+    ap.add_argument("--depth", type=int, default=6, help="steps (independent streams) kept in flight per GPU")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)
