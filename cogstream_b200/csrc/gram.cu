@@ -31,6 +31,7 @@ struct GramUnit {
   int a_slot[kMaxMma];        // per tile: smem slot of the A (row) block
   int b_slot[kMaxMma];        // per tile: smem slot of the B (column) block
   int tile_id[kMaxMma];       // upper-triangular tile id (for the partial buffer)
+  int pair[kMaxMma];          // 1: head of an N=256 MMA that also covers tile t+1 (same A, adjacent B slots); 2: covered; 0: N=128
 };
 
 struct GramUnitTable {
@@ -83,13 +84,27 @@ static int unit_new_blocks(const GramUnit& u, int bi, int bj) {
 static void plan_units(int nb, int b0, GramUnit* units, int* n_units, int* max_slots) {
   int n = 0, ms = 0;
   auto emit = [&](GramUnit u) {
-    for (int i = 1; i < u.n_tiles; ++i)  // stable insertion sort by A slot (collector reuse wants equal-A tiles adjacent)
-      for (int j = i; j > 0 && u.a_slot[j - 1] > u.a_slot[j]; --j) {
+    // (1) slots in ascending block order, so that neighbouring column blocks sit in neighbouring 16 KB slots
+    int order[kMaxSlots], inv[kMaxSlots];
+    for (int i = 0; i < u.n_slots; ++i) order[i] = i;
+    for (int i = 1; i < u.n_slots; ++i)
+      for (int j = i; j > 0 && u.slot_block[order[j - 1]] > u.slot_block[order[j]]; --j) { int x = order[j]; order[j] = order[j - 1]; order[j - 1] = x; }
+    int nb_sorted[kMaxSlots];
+    for (int i = 0; i < u.n_slots; ++i) { nb_sorted[i] = u.slot_block[order[i]]; inv[order[i]] = i; }
+    for (int i = 0; i < u.n_slots; ++i) u.slot_block[i] = nb_sorted[i];
+    for (int t = 0; t < u.n_tiles; ++t) { u.a_slot[t] = inv[u.a_slot[t]]; u.b_slot[t] = inv[u.b_slot[t]]; }
+    // (2) tiles sorted by (A slot, B slot)
+    for (int i = 1; i < u.n_tiles; ++i)
+      for (int j = i; j > 0 && (u.a_slot[j - 1] > u.a_slot[j] || (u.a_slot[j - 1] == u.a_slot[j] && u.b_slot[j - 1] > u.b_slot[j])); --j) {
         int x;
         x = u.a_slot[j]; u.a_slot[j] = u.a_slot[j - 1]; u.a_slot[j - 1] = x;
         x = u.b_slot[j]; u.b_slot[j] = u.b_slot[j - 1]; u.b_slot[j - 1] = x;
         x = u.tile_id[j]; u.tile_id[j] = u.tile_id[j - 1]; u.tile_id[j - 1] = x;
       }
+    // (3) same A + adjacent B slots -> one N=256 MMA (A is read from shared memory once for both tiles)
+    for (int t = 0; t < kMaxMma; ++t) u.pair[t] = 0;
+    for (int t = 0; t + 1 < u.n_tiles; ++t)
+      if (u.pair[t] == 0 && u.a_slot[t] == u.a_slot[t + 1] && u.b_slot[t + 1] == u.b_slot[t] + 1) { u.pair[t] = 1; u.pair[t + 1] = 2; }
     if (units) units[n] = u;
     ++n;
     if (u.n_slots > ms) ms = u.n_slots;
@@ -393,7 +408,7 @@ __global__ void __launch_bounds__(160, 1) gram_tc_kernel(const __grid_constant__
     // The tensor core accumulates in fp32 with truncation, so a chain of n MMAs drifts by up to ~n * 2^-24 relative.  Chains
     // are cut every kSegChunks chunks: the accumulators are drained and added (round-to-nearest fp32) into the partial
     // tile, then restarted from zero.  Short K ranges (config 2: 88 chunks per CTA) are a single segment.
-    constexpr uint32_t idesc = make_idesc(128, 128);
+    constexpr uint32_t idesc = make_idesc(128, 128), idesc256 = make_idesc(128, 256);
     const int nseg = (nchunk + kSegChunks - 1) / kSegChunks;
     for (int seg = 0; seg < nseg; ++seg) {
       const int cs = seg * kSegChunks, ce = min(nchunk, cs + kSegChunks);
@@ -408,12 +423,15 @@ __global__ void __launch_bounds__(160, 1) gram_tc_kernel(const __grid_constant__
           // order, which would let tiles that share A reuse it through the A collector, runs 2x slower -- alternating the
           // accumulator between consecutive MMAs costs far more than the saved shared-memory reads.)
           for (int t = 0; t < n_ut && !(dbg & 1); ++t) {  // dbg&1: profiling aid, loads only
+            const int pr = (dbg & 4) ? 0 : unit.pair[t];
+            if (pr == 2) continue;  // covered by the N=256 MMA of tile t-1
             const uint32_t a_addr = stage + (uint32_t)unit.a_slot[t] * kBlockBytes;
             const uint32_t b_addr = stage + (uint32_t)unit.b_slot[t] * kBlockBytes;
+            const uint32_t id = pr == 1 ? idesc256 : idesc;
 #pragma unroll
             for (int ks = 0; ks < kChunk / 16; ++ks) {
               ptx::umma_bf16(tmem_base + (uint32_t)t * 128u, make_smem_desc(a_addr + ks * 32), make_smem_desc(b_addr + ks * 32),
-                             idesc, (c > cs || ks > 0) ? 1u : 0u);
+                             id, (c > cs || ks > 0) ? 1u : 0u);
             }
           }
           ptx::umma_commit(&ctl->empty[s]);  // frees the stage once these MMAs have read it
