@@ -388,17 +388,11 @@ def _stage_times(sc, d, ev_d, q_d, reps=5):
         ops.kmeans_solve(sc.G, d.timestamps, sc.km, n_init_given=1, exp_noise=noise, reseed_pool=sc.pool, alpha=sc.cfg.alpha,
                          max_iteration=sc.cfg.max_iteration, tol=sc.cfg.tol)
 
-    def dist():
-        state["dist"] = ops.dist_to_assigned_gram(sc.G, sc.km.assignments, sc.km.event_offsets, sc.km.event_order, k)
-
     def reps_():
-        state["rflags"] = ops.select_representatives(state["dist"], sc.km.assignments, k, 2)[2]
+        state["rflags"] = ops.representatives_gram(sc.G, sc.km.event_offsets, sc.km.event_order, k, 2)[3]
 
-    def cos():
-        state["low"] = ops.cosine_flags(q_d.view(-1), ev_d, 0.45)[1]
-
-    def minor():
-        state["mflags"] = ops.minor_frames(sc.km.assignments, state["low"], state["rflags"])[0]
+    def relevance():
+        state["mflags"] = ops.relevance_minor(q_d.view(-1), ev_d, sc.km.assignments, state["rflags"], sc._ticket, 0.45)[2]
 
     stages = [
         ("gram", lambda: ops.gram(x2, out=sc.G, workspace=sc.gram_ws)),
@@ -406,10 +400,8 @@ def _stage_times(sc, d, ev_d, q_d, reps=5):
         ("kmeans_solve", solve),
         ("centroid_gather", lambda: ops.centroid_gather(x2, sc.km.member_offsets, sc.km.members, sc.km.event_offsets, k,
                                                         sc.centroids, sc.packed)),
-        ("dist_gram", dist),
-        ("select_reps", reps_),
-        ("cosine_flags", cos),
-        ("minor_frames", minor),
+        ("representatives", reps_),
+        ("relevance_minor", relevance),
         ("pixel_mask", lambda: ops.pixel_mask(d.pixel_values, T, P, sc.W, minor_flags=state["mflags"], out=sc.mask)),
         ("compact_tokens", lambda: ops.compact_tokens(d.features, T, P, sc.mask, state["mflags"], out=sc.out, workspace=sc.compact_ws)),
         ("filter_ids", lambda: ops.filter_ids(d.input_ids, sc.image_token_index, sc.mask, d.attention_mask)),

@@ -54,6 +54,8 @@ PROTOTYPES = {
     "csb_dist_to_assigned": (C.c_int, [_p, _i64, _i64, _p, _i64, _p, _p, _p]),
     "csb_dist_to_assigned_gram": (C.c_int, [_p, _i64, _i64, _i64, _p, _p, _p, _p, _p, _p]),
     "csb_select_representatives": (C.c_int, [_p, _p, _i64, _i64, _i64, _p, _p, _p, _p]),
+    "csb_representatives_gram": (C.c_int, [_p, _i64, _i64, _i64, _p, _p, _i64, _p, _p, _p, _p, _p]),
+    "csb_relevance_minor": (C.c_int, [_p, _p, _i64, _i64, _i32, _dbl, _p, _p, _i64, _p, _p, _p, _p, _p, _p, _p]),
     "csb_event_order": (C.c_int, [_p, _i64, _i64, _p, _p, _p]),
     "csb_gather_rows": (C.c_int, [_p, _i64, _p, _i64, _p, _i64, _p, _p]),
     "csb_cosine_flags": (C.c_int, [_p, _p, _i64, _i64, _i32, _dbl, _p, _p, _p]),

@@ -137,6 +137,75 @@ __global__ void __launch_bounds__(256) select_reps_kernel(const float* __restric
 }
 
 // ------------------------------------------------------------------------------------------------
+// Fused: distance of every member to its own centroid (from the Gram matrix) + the n_rep nearest members.
+// A warp per event; the event's members are event_order[off[j] .. off[j+1]) (ascending frame index).
+//   rowsum_m = sum_{m'} G[m][m'],  q = sum_m rowsum_m / n^2,  dist_m^2 = G_mm - 2 rowsum_m / n + q
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) reps_gram_kernel(const double* __restrict__ G, int64_t ldg, int k, int n_rep,
+                                                        const int32_t* __restrict__ ev_off, const int32_t* __restrict__ order,
+                                                        float* __restrict__ dist, int64_t* __restrict__ reps,
+                                                        int32_t* __restrict__ rep_counts, uint8_t* __restrict__ rep_flags) {
+  const int lane = threadIdx.x & 31;
+  const int j = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (j >= k) return;
+  const int beg = ev_off[j], n = ev_off[j + 1] - beg;
+  const int32_t* mem = order + beg;
+  int64_t* out = reps + (int64_t)j * n_rep;
+  // distances (also for small events: the dist output is complete)
+  double qpart = 0.0;
+  for (int a = lane; a < n; a += 32) {
+    const double* ga = G + (int64_t)mem[a] * ldg;
+    double rs = 0.0;
+    for (int b = 0; b < n; ++b) rs += ga[mem[b]];
+    qpart += rs;
+  }
+  const double nn = (double)n;
+  const double q = warp_sum(qpart) / (nn * nn);
+  // second pass recomputes the (short) row sums instead of parking fp64 values: n is ~T/k
+  for (int a = lane; a < n; a += 32) {
+    const int m = mem[a];
+    const double* ga = G + (int64_t)m * ldg;
+    double rs = 0.0;
+    for (int b = 0; b < n; ++b) rs += ga[mem[b]];
+    const double d2 = ga[m] - 2.0 * (rs / nn) + q;
+    dist[m] = (float)sqrt(d2 > 0.0 ? d2 : 0.0);
+    rep_flags[m] = 0;
+  }
+  __syncwarp();
+  if (n <= n_rep) {  // all members, ascending (cogreasoner_chat.py:58-59)
+    for (int a = lane; a < n; a += 32) { out[a] = mem[a]; rep_flags[mem[a]] = 1; }
+    for (int r = n + lane; r < n_rep; r += 32) out[r] = -1;
+    if (lane == 0) rep_counts[j] = n;
+    return;
+  }
+  float last_d = -1.f;
+  int last_i = -1;
+  for (int r = 0; r < n_rep; ++r) {
+    float bd = __int_as_float(0x7f800000);
+    int bi = 0x7fffffff;
+    for (int a = lane; a < n; a += 32) {
+      const int i = mem[a];
+      const float d = dist[i];
+      const bool after = d > last_d || (d == last_d && i > last_i);
+      if (after && (d < bd || (d == bd && i < bi))) { bd = d; bi = i; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float od = __shfl_xor_sync(0xffffffffu, bd, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (od < bd || (od == bd && oi < bi)) { bd = od; bi = oi; }
+    }
+    if (lane == 0) {
+      out[r] = bi == 0x7fffffff ? -1 : bi;
+      if (bi != 0x7fffffff) rep_flags[bi] = 1;
+    }
+    last_d = bd;
+    last_i = bi;
+  }
+  if (lane == 0) rep_counts[j] = n_rep;
+}
+
+// ------------------------------------------------------------------------------------------------
 // chronological per-event order: a warp per event sweeps the assignments (stable, ascending).
 // Single CTA (offsets need a scan over k counts).
 // ------------------------------------------------------------------------------------------------
@@ -220,6 +289,67 @@ __global__ void __launch_bounds__(256) cosine_flags_kernel(const void* __restric
     if (BF16) reinterpret_cast<uint16_t*>(cos_out)[j] = (uint16_t)float_to_bf16_bits(c);
     else reinterpret_cast<float*>(cos_out)[j] = c;
     low[j] = c < threshold ? 1 : 0;  // strict, threshold already rounded to the dtype (:329-330)
+  }
+}
+
+// Fused relevance step: the k cosine CTAs, and the last one to finish derives the minor-frame list
+// (cogreasoner_chat.py:325-333 in one launch).  `ticket` is a zero-initialised counter that the last CTA resets.
+template <bool BF16>
+__global__ void __launch_bounds__(256) relevance_minor_kernel(const void* __restrict__ q, const void* __restrict__ ev, int Dl,
+                                                              float threshold, void* __restrict__ cos_out, uint8_t* __restrict__ low,
+                                                              const int64_t* __restrict__ assign, const uint8_t* __restrict__ rep,
+                                                              int T, uint8_t* __restrict__ flags, int32_t* __restrict__ list,
+                                                              int64_t* __restrict__ n_minor, unsigned* ticket) {
+  __shared__ float red[32];
+  __shared__ int wt[32];
+  __shared__ int total;
+  __shared__ int is_last;
+  const int j = blockIdx.x;
+  const void* e = BF16 ? (const void*)(reinterpret_cast<const uint16_t*>(ev) + (int64_t)j * Dl)
+                       : (const void*)(reinterpret_cast<const float*>(ev) + (int64_t)j * Dl);
+  float sq = 0.f, se = 0.f;
+  for (int i = threadIdx.x; i < Dl; i += blockDim.x) {
+    const float a = ld_elem<BF16>(q, i), b = ld_elem<BF16>(e, i);
+    sq = fmaf(a, a, sq);
+    se = fmaf(b, b, se);
+  }
+  sq = block_sum<float>(sq, red);
+  se = block_sum<float>(se, red);
+  const float eps = rnd<BF16>(1e-8f);
+  const float qn = fmaxf(rnd<BF16>(__fsqrt_rn(sq)), eps);
+  const float en = fmaxf(rnd<BF16>(__fsqrt_rn(se)), eps);
+  float dot = 0.f;
+  for (int i = threadIdx.x; i < Dl; i += blockDim.x) {
+    const float a = rnd<BF16>(__fdiv_rn(ld_elem<BF16>(q, i), qn));
+    const float b = rnd<BF16>(__fdiv_rn(ld_elem<BF16>(e, i), en));
+    dot += rnd<BF16>(__fmul_rn(a, b));
+  }
+  dot = block_sum<float>(dot, red);
+  if (threadIdx.x == 0) {
+    const float c = rnd<BF16>(dot);
+    if (BF16) reinterpret_cast<uint16_t*>(cos_out)[j] = (uint16_t)float_to_bf16_bits(c);
+    else reinterpret_cast<float*>(cos_out)[j] = c;
+    low[j] = c < threshold ? 1 : 0;
+    __threadfence();
+    is_last = (atomicAdd(ticket, 1u) == gridDim.x - 1) ? 1 : 0;
+  }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  const int per = (T + blockDim.x - 1) / blockDim.x;
+  const int beg = threadIdx.x * per, end = min(T, beg + per);
+  int cnt = 0;
+  for (int i = beg; i < end; ++i) {
+    const uint8_t f = (__ldcg(low + assign[i]) && !rep[i]) ? 1 : 0;
+    flags[i] = f;
+    cnt += f;
+  }
+  int pos = block_exclusive_scan(cnt, wt, &total);
+  for (int i = beg; i < end; ++i)
+    if (flags[i]) list[pos++] = i;
+  if (threadIdx.x == 0) {
+    *n_minor = total;
+    *ticket = 0;
   }
 }
 
@@ -736,6 +866,39 @@ int csb_dist_to_assigned_gram(const double* G, int64_t ldg, int64_t T, int64_t k
   count_launch(1);
   dist_gram_kernel<<<(unsigned)((T + 7) / 8), 256, 0, s>>>(G, ldg, (int)T, assignments, offs, memb, rowsum_ws, dist);
   return check_launch("dist_to_assigned_gram");
+}
+
+int csb_representatives_gram(const double* G, int64_t ldg, int64_t T, int64_t k, const int32_t* event_offsets,
+                             const int32_t* order, int64_t n_rep, float* dist, int64_t* reps, int32_t* rep_counts,
+                             uint8_t* rep_flags, csb_stream_t stream) {
+  CSB_DEVICE_OR_RETURN();
+  CSB_REQUIRE(G && event_offsets && order && dist && reps && rep_counts && rep_flags && T > 0 && k > 0 && n_rep > 0 && ldg >= T,
+              "representatives_gram: null argument or ldg < T");
+  reps_gram_kernel<<<(unsigned)((k + 7) / 8), 256, 0, as_stream(stream)>>>(G, ldg, (int)k, (int)n_rep, event_offsets, order, dist, reps,
+                                                                            rep_counts, rep_flags);
+  return check_launch("representatives_gram");
+}
+
+int csb_relevance_minor(const void* question, const void* events, int64_t k, int64_t Dl, int32_t dtype, double threshold,
+                        const int64_t* assignments, const uint8_t* rep_flags, int64_t T, void* cos_out, uint8_t* low_flags,
+                        uint8_t* minor_flags, int32_t* minor_list, int64_t* n_minor, uint32_t* ticket, csb_stream_t stream) {
+  CSB_DEVICE_OR_RETURN();
+  CSB_REQUIRE(question && events && cos_out && low_flags && assignments && rep_flags && minor_flags && minor_list && n_minor && ticket &&
+                  k > 0 && Dl > 0 && T > 0,
+              "relevance_minor: null argument");
+  cudaStream_t s = as_stream(stream);
+  if (dtype == CSB_BF16) {
+    const float thr = __bfloat162float(__float2bfloat16_rn((float)threshold));
+    relevance_minor_kernel<true><<<(unsigned)k, 256, 0, s>>>(question, events, (int)Dl, thr, cos_out, low_flags, assignments, rep_flags,
+                                                            (int)T, minor_flags, minor_list, n_minor, ticket);
+  } else if (dtype == CSB_F32) {
+    relevance_minor_kernel<false><<<(unsigned)k, 256, 0, s>>>(question, events, (int)Dl, (float)threshold, cos_out, low_flags, assignments,
+                                                             rep_flags, (int)T, minor_flags, minor_list, n_minor, ticket);
+  } else {
+    set_error("relevance_minor: dtype must be bf16 or f32");
+    return CSB_ERR_UNSUPPORTED;
+  }
+  return check_launch("relevance_minor");
 }
 
 int csb_select_representatives(const float* dist, const int64_t* assignments, int64_t T, int64_t k, int64_t n_rep, int64_t* reps,

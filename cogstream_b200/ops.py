@@ -251,6 +251,45 @@ def select_representatives(dist: torch.Tensor, assignments: torch.Tensor, k: int
     return reps, counts, flags
 
 
+def representatives_gram(G: torch.Tensor, event_offsets: torch.Tensor, order: torch.Tensor, k: int, n_rep: int):
+    """Fused dist_to_assigned_gram + select_representatives -> (dist [T] f32, reps [k,n_rep] i64, rep_counts [k] i32, rep_flags [T] u8)."""
+    T, ldg = _gram_view(G)
+    dev = G.device
+    dist = torch.empty(T, dtype=torch.float32, device=dev)
+    reps = torch.empty(k, n_rep, dtype=torch.int64, device=dev)
+    counts = torch.empty(k, dtype=torch.int32, device=dev)
+    flags = torch.empty(T, dtype=torch.uint8, device=dev)
+    with _on_device(G):
+        check(_lib.load().csb_representatives_gram(G.data_ptr(), ldg, T, k, event_offsets.data_ptr(), order.data_ptr(), n_rep,
+                                                   dist.data_ptr(), reps.data_ptr(), counts.data_ptr(), flags.data_ptr(), _stream(G)),
+              "representatives_gram")
+    return dist, reps, counts, flags
+
+
+def relevance_minor(question: torch.Tensor, events: torch.Tensor, assignments: torch.Tensor, rep_flags: torch.Tensor,
+                    ticket: torch.Tensor, threshold: float = 0.45):
+    """Fused cosine_flags + minor_frames -> (cos [k], low [k] u8, minor_flags [T] u8, minor_list [T] i32, n_minor [1] i64).
+    ``ticket``: a zeroed int32[1] tensor owned by the caller (one per in-flight stream)."""
+    _need(events, "events", None, 2)
+    _need(question, "question", events.dtype, 1)
+    if events.dtype not in _EL_DTYPE:
+        raise TypeError(f"relevance_minor: dtype must be bfloat16 or float32, got {events.dtype}")
+    k, Dl = events.shape
+    T = assignments.shape[0]
+    dev = events.device
+    cos = torch.empty(k, dtype=events.dtype, device=dev)
+    low = torch.empty(k, dtype=torch.uint8, device=dev)
+    flags = torch.empty(T, dtype=torch.uint8, device=dev)
+    lst = torch.empty(T, dtype=torch.int32, device=dev)
+    n = torch.empty(1, dtype=torch.int64, device=dev)
+    with _on_device(events):
+        check(_lib.load().csb_relevance_minor(question.data_ptr(), events.data_ptr(), k, Dl, _EL_DTYPE[events.dtype], float(threshold),
+                                              assignments.data_ptr(), rep_flags.data_ptr(), T, cos.data_ptr(), low.data_ptr(),
+                                              flags.data_ptr(), lst.data_ptr(), n.data_ptr(), ticket.data_ptr(), _stream(events)),
+              "relevance_minor")
+    return cos, low, flags, lst, n
+
+
 def event_order(assignments: torch.Tensor, k: int):
     """-> (order [T] int32: frames sorted by (event, frame), event_offsets [k+1] int32)."""
     _need(assignments, "assignments", torch.int64, 1)

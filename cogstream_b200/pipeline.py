@@ -81,6 +81,7 @@ class StreamCompressor:
             self.centroids = torch.empty(k, self.K, dtype=torch.float32, device=dev) if self.cfg.compute_centroids else None
             self.packed = torch.empty(T, self.K, dtype=torch.bfloat16, device=dev) if self.cfg.gather_events else None
         self._row_base = torch.tensor([T, self.k if self.gate else 0, 0, 0, 0, 0, 0, 0], dtype=torch.int64, device=dev)
+        self._ticket = torch.zeros(1, dtype=torch.int32, device=dev)
         self.minor_flags = torch.zeros(T, dtype=torch.uint8, device=dev)
         self.n_minor = torch.zeros(1, dtype=torch.int64, device=dev)
         self.mask = torch.empty(T * P, dtype=torch.uint8, device=dev)
@@ -148,8 +149,12 @@ class StreamCompressor:
             ops.centroid_gather(x2, self.km.member_offsets, self.km.members, self.km.event_offsets, k, self.centroids, self.packed)
         assign = self.km.assignments
         self.order, self.ev_off = self.km.event_order, self.km.event_offsets
-        self.dist = ops.dist_to_assigned_gram(self.G, assign, self.ev_off, self.order, k)
-        self.reps, self.rep_counts, self.rep_flags = ops.select_representatives(self.dist, assign, k, self.cfg.n_representatives)
+        if T <= 256 * k:  # one fused launch (a warp per event, quadratic in the event size)
+            self.dist, self.reps, self.rep_counts, self.rep_flags = ops.representatives_gram(self.G, self.ev_off, self.order, k,
+                                                                                             self.cfg.n_representatives)
+        else:
+            self.dist = ops.dist_to_assigned_gram(self.G, assign, self.ev_off, self.order, k)
+            self.reps, self.rep_counts, self.rep_flags = ops.select_representatives(self.dist, assign, k, self.cfg.n_representatives)
 
     # ------------------------------------------------------------------------------------------
     def phase2(self, features: torch.Tensor, events_repr: Optional[torch.Tensor], question: Optional[torch.Tensor],
@@ -158,8 +163,8 @@ class StreamCompressor:
         T, P = self.T, self.P
         minor_flags = None
         if self.gate:
-            self.cos, self.low = ops.cosine_flags(question.view(-1), events_repr, self.cfg.relevance_threshold)
-            self.minor_flags, self.minor_list, self.n_minor = ops.minor_frames(self.km.assignments, self.low, self.rep_flags)
+            self.cos, self.low, self.minor_flags, self.minor_list, self.n_minor = ops.relevance_minor(
+                question.view(-1), events_repr, self.km.assignments, self.rep_flags, self._ticket, self.cfg.relevance_threshold)
             minor_flags = self.minor_flags
         else:
             self.minor_flags.zero_()

@@ -172,6 +172,12 @@ CSB_API int csb_dist_to_assigned_gram(const double* G, int64_t ldg, int64_t T, i
 CSB_API int csb_select_representatives(const float* dist, const int64_t* assignments, int64_t T, int64_t k, int64_t n_rep,
                                int64_t* reps, int32_t* rep_counts, uint8_t* rep_flags, csb_stream_t stream);
 
+/* Both of the above from the Gram matrix in ONE launch (a warp per event; meant for events of up to a few hundred frames --
+ * the work per event is quadratic in its size): dist [T] is filled as by csb_dist_to_assigned_gram. */
+CSB_API int csb_representatives_gram(const double* G, int64_t ldg, int64_t T, int64_t k, const int32_t* event_offsets,
+                                     const int32_t* order, int64_t n_rep, float* dist, int64_t* reps,
+                                     int32_t* rep_counts, uint8_t* rep_flags, csb_stream_t stream);
+
 /* Chronological per-event order (cogreasoner_chat.py:291-296): order[] lists frame indices sorted by
  * (event, frame); event_offsets [k+1].  Then csb_gather_rows(order) packs the event tokens. */
 CSB_API int csb_event_order(const int64_t* assignments, int64_t T, int64_t k, int32_t* order, int32_t* event_offsets,
@@ -192,6 +198,13 @@ CSB_API int csb_cosine_flags(const void* question, const void* events, int64_t k
  *   minor_flags [T] uint8, minor_list [T] int32 ascending, n_minor device int64 */
 CSB_API int csb_minor_frames(const int64_t* assignments, const uint8_t* low_flags, const uint8_t* rep_flags, int64_t T,
                      uint8_t* minor_flags, int32_t* minor_list, int64_t* n_minor, csb_stream_t stream);
+
+/* csb_cosine_flags + csb_minor_frames in one launch (the last cosine CTA to finish builds the list).
+ *   ticket: a zero-initialised uint32 the library resets after use (one per concurrently running stream). */
+CSB_API int csb_relevance_minor(const void* question, const void* events, int64_t k, int64_t Dl, int32_t dtype,
+                                double threshold, const int64_t* assignments, const uint8_t* rep_flags, int64_t T,
+                                void* cos_out, uint8_t* low_flags, uint8_t* minor_flags, int32_t* minor_list,
+                                int64_t* n_minor, uint32_t* ticket, csb_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * (d) token mask, pooling of minor frames, chronological compaction.
