@@ -551,3 +551,30 @@ def test_stream_cache_incremental_reclustering(dev):
         assert torch.equal(buf.assignments.cpu(), a) and torch.equal(buf.centroid_times.cpu(), ct)
         assert ops.decode_status(buf.status)["iterations"] == info.iterations
         assert rel_err(cache.centroids(buf, k), c) < 1e-6
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_fused_selection_kernels_match_unfused(dev, name):
+    """representatives_gram == dist_to_assigned_gram + select_representatives; relevance_minor == cosine_flags + minor_frames."""
+    g = load_golden(name)
+    s = g["spec"]
+    T, P, D, k = s["T"], s["P"], s["D"], s["k"]
+    f3 = g["features"].view(T, P, D).to(dev)
+    assign = g["assignments"].to(dev)
+    G = ops.gram(f3.view(T, -1))
+    order, off = ops.event_order(assign, k)
+    dist = ops.dist_to_assigned_gram(G, assign, off, order, k)
+    r1, c1, fl1 = ops.select_representatives(dist, assign, k, 2)
+    dist2, r2, c2, fl2 = ops.representatives_gram(G, off, order, k, 2)
+    assert torch.equal(r1, r2) and torch.equal(c1, c2) and torch.equal(fl1, fl2)
+    assert rel_err(dist2, dist) < 1e-6
+    assert all(torch.equal(r2[i, : int(c2[i])].cpu(), g["representatives"][i]) for i in range(k))
+    q, ev = g["question"][0].to(dev), g["events_repr"].to(dev)
+    cos, low = ops.cosine_flags(q, ev, 0.45)
+    mf, ml, nm = ops.minor_frames(assign, low, fl1)
+    ticket = torch.zeros(1, dtype=torch.int32, device=dev)
+    for _ in range(2):  # twice: the ticket must have been reset by the first call
+        cos2, low2, mf2, ml2, nm2 = ops.relevance_minor(q, ev, assign, fl1, ticket, 0.45)
+        assert torch.equal(cos, cos2) and torch.equal(low, low2) and torch.equal(mf, mf2) and int(nm) == int(nm2)
+        assert torch.equal(ml[: int(nm)], ml2[: int(nm2)]) and ml2[: int(nm2)].tolist() == g["minor"]
+    assert int(ticket) == 0
