@@ -578,3 +578,66 @@ def test_fused_selection_kernels_match_unfused(dev, name):
         assert torch.equal(cos, cos2) and torch.equal(low, low2) and torch.equal(mf, mf2) and int(nm) == int(nm2)
         assert torch.equal(ml[: int(nm)], ml2[: int(nm2)]) and ml2[: int(nm2)].tolist() == g["minor"]
     assert int(ticket) == 0
+
+
+ODD = [  # T, P, D, k, C   -- awkward shapes: tiny D, P = 1, T below / across warp and tile boundaries, k close to T
+    (17, 1, 8, 3, 2), (33, 2, 40, 5, 6), (130, 5, 136, 9, 10), (129, 3, 8, 40, 2), (65, 1, 1152, 7, 588), (257, 2, 24, 17, 4),
+]
+
+
+@pytest.mark.parametrize("T,P,D,k,C", ODD)
+def test_pipeline_odd_shapes(dev, T, P, D, k, C):
+    st = synthetic.make_stream(T, P, D, T + P + D, C=C, near_threshold_frac=0.1)
+    ev, q = synthetic.make_embeddings(k, 72, T)
+    g = torch.Generator().manual_seed(T)
+    init = torch.randperm(T, generator=g)[:k]
+    pool = torch.randint(0, T, (64,), generator=g)
+    p1 = orc.phase1(st.features, T, st.timestamps, cluster_num=k, init_indices=init.tolist(), reseed_indices=pool.tolist())
+    p2 = orc.phase2(st.features, p1, ev, q, st.pixel_values, st.grid_sizes, st.merge_sizes, st.modals, st.input_ids,
+                    synthetic.IMAGE_TOKEN_INDEX, st.attention_mask)
+    W = st.pixel_values.numel() // (T * P)
+    sc = StreamCompressor(T, P, D, W, st.input_ids.numel(), device=dev, cfg=StreamConfig(cluster_num=k))
+    d = st.to(dev)
+    sc.phase1(d.features, d.timestamps, init_indices=init.to(dev), reseed_pool=pool.to(dev))
+    sc.phase2(d.features, ev.to(dev), q.to(dev), d.pixel_values, d.input_ids, d.attention_mask)
+    r = sc.results()
+    assert torch.equal(r["assignments"].cpu(), p1.assignments) and r["status"]["iterations"] == p1.info.iterations
+    assert all(torch.equal(a.cpu(), b) for a, b in zip(r["representatives"], p1.representatives))
+    assert r["minor"] == p2.minor and torch.equal(r["mask"].cpu(), p2.mask)
+    assert torch.equal(r["input_ids"].cpu(), p2.input_ids)
+    assert_bf16_close(r["features"], p2.features)
+    assert rel_err(r["centroids"], p1.centroids) < REL_TOL
+    off = r["event_offsets"].tolist()
+    packed = r["packed_events"].view(T, P, D).cpu()
+    for i in range(k):
+        assert torch.equal(packed[off[i]: off[i + 1]].reshape(-1, D), p1.events[i])
+
+
+def test_cuda_graph_replay(dev):
+    """Both phases captured into CUDA graphs (cooperative solver launch included) and replayed: valid, self-consistent and
+    reproducible results; the masks / ids agree with an eager run on the same assignments."""
+    T, P, D = 300, 6, 128
+    k = math.ceil(T / 15)
+    st = synthetic.make_stream(T, P, D, 91, C=16)
+    ev, q = synthetic.make_embeddings(k, 256, 91)
+    d = st.to(dev)
+    evd, qd = ev.to(dev), q.to(dev)
+    W = st.pixel_values.numel() // (T * P)
+    sc = StreamCompressor(T, P, D, W, st.input_ids.numel(), device=dev)
+    sc.capture(d.features, d.timestamps, evd, qd, d.pixel_values, d.input_ids, d.attention_mask)
+    outs = []
+    for _ in range(2):
+        torch.manual_seed(4242)
+        sc.replay1(); sc.replay2()
+        r = sc.results()
+        outs.append((r["assignments"].clone(), r["mask"].clone(), r["features"].clone(), list(r["minor"]), r["status"]))
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1]) and torch.equal(outs[0][2], outs[1][2])
+    assign, mask, feats, minor, status = outs[1]
+    assert status["converged"] and 0 <= int(assign.min()) and int(assign.max()) < k
+    # oracle phase 2 on the GPU's own assignments / representatives (phase 1 of the replay used device-drawn randomness)
+    reps = [t.cpu() for t in sc.results()["representatives"]]
+    p1 = orc.Phase1Result(k, None, None, assign.cpu(), reps, [], [], orc.KMeansInfo())
+    p2 = orc.phase2(st.features, p1, ev, q, st.pixel_values, st.grid_sizes, st.merge_sizes, st.modals, st.input_ids,
+                    synthetic.IMAGE_TOKEN_INDEX, st.attention_mask)
+    assert minor == p2.minor and torch.equal(mask.cpu(), p2.mask)
+    assert_bf16_close(feats, p2.features)
