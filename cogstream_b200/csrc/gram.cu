@@ -27,15 +27,26 @@ constexpr int kMaxParamUnits = 16;               // unit tables up to this size 
 struct GramUnit {
   int n_slots;
   int n_tiles;
+  int n_ops;
   int slot_block[kMaxSlots];  // row block loaded into each smem slot
-  int a_slot[kMaxMma];        // per tile: smem slot of the A (row) block
-  int b_slot[kMaxMma];        // per tile: smem slot of the B (column) block
+  // output tiles = TMEM 128-column groups, in op order
   int tile_id[kMaxMma];       // upper-triangular tile id (for the partial buffer)
-  int pair[kMaxMma];          // 1: head of an N=256 MMA that also covers tile t+1 (same A, adjacent B slots); 2: covered; 0: N=128
+  int tile_rows[kMaxMma];     // valid rows / columns of the stored tile (the drain skips the rest)
+  int tile_cols[kMaxMma];
+  // MMA ops: D[128 x n] (+)= A(slot a)[128 x 64] * B(slots b, b+1 ...)[n x 64]^T; n <= 256 covers one or two adjacent B slots,
+  // i.e. one or two output tiles starting at TMEM tile t0.  An N=256 MMA runs at the tensor-pipe floor (64 cycles per
+  // 128x128x16), two N=128 MMAs take 84 each: shared-memory operand bandwidth (scripts/ubench/mma_rate.cu).
+  int op_a[kMaxMma], op_b[kMaxMma], op_n[kMaxMma], op_t0[kMaxMma];
 };
 
 struct GramUnitTable {
   GramUnit u[kMaxParamUnits];
+};
+
+// Tiles whose op had A = the higher block are stored flipped ([bj rows][bi cols]); bit = upper-triangular tile id.
+// Only the small-problem planner produces them (tile ids < 136).
+struct GramFlipMask {
+  unsigned long long w[3];
 };
 
 struct GramPlan {
@@ -54,97 +65,207 @@ struct GramPlan {
 static inline int tri_id(int bi, int bj, int b0) { return bj * (bj + 1) / 2 - b0 * (b0 + 1) / 2 + bi; }
 static inline int tri_count(int nb, int b0) { return nb * (nb + 1) / 2 - b0 * (b0 + 1) / 2; }
 
-// Pack the upper-triangular tiles into units of <= 4 tiles touching <= 4 distinct row blocks (fewer
-// resident blocks per stage = deeper TMA pipeline and less L2 traffic).  Small problems: greedy "seed +
-// the tile that adds the fewest new blocks"; large ones: 2x2 super-blocks (4 tiles / 4 blocks off the
-// diagonal, 3 tiles / 2 blocks on it).  T=600 (5 blocks, 15 tiles) packs into 4 units of 3 blocks each.
-static void unit_add(GramUnit& u, int bi, int bj, int b0) {
-  auto slot = [&](int blk) {
-    for (int s = 0; s < u.n_slots; ++s)
-      if (u.slot_block[s] == blk) return s;
-    u.slot_block[u.n_slots] = blk;
-    return u.n_slots++;
+// ---- planner -------------------------------------------------------------------------------------------------------------
+// An op is "row block a against one or two column blocks"; G is symmetric, so a tile (bi, bj) may be produced by either
+// orientation (A = bi or A = bj).  Ops are packed into units of <= 4 tiles touching <= 4 distinct row blocks (fewer resident
+// blocks per stage = deeper TMA ring, less L2 traffic); inside a unit the two B blocks of a pair sit in adjacent 16 KB slots.
+struct PlanOp {
+  int a, nbk, b[2];
+};
+
+static int op_blocks(const PlanOp& o, int* out) {
+  int n = 0;
+  auto add = [&](int v) {
+    for (int i = 0; i < n; ++i)
+      if (out[i] == v) return;
+    out[n++] = v;
   };
-  const int sa = slot(bi), sb = slot(bj);
-  u.a_slot[u.n_tiles] = sa;
-  u.b_slot[u.n_tiles] = sb;
-  u.tile_id[u.n_tiles] = tri_id(bi, bj, b0);
-  ++u.n_tiles;
+  add(o.a);
+  for (int i = 0; i < o.nbk; ++i) add(o.b[i]);
+  return n;
 }
 
-static int unit_new_blocks(const GramUnit& u, int bi, int bj) {
-  bool ha = false, hb = false;
-  for (int s = 0; s < u.n_slots; ++s) {
-    ha |= u.slot_block[s] == bi;
-    hb |= u.slot_block[s] == bj;
-  }
-  return (ha ? 0 : 1) + ((hb || bj == bi) ? 0 : 1);
-}
-
-static void plan_units(int nb, int b0, GramUnit* units, int* n_units, int* max_slots) {
-  int n = 0, ms = 0;
-  auto emit = [&](GramUnit u) {
-    // (1) slots in ascending block order, so that neighbouring column blocks sit in neighbouring 16 KB slots
-    int order[kMaxSlots], inv[kMaxSlots];
-    for (int i = 0; i < u.n_slots; ++i) order[i] = i;
-    for (int i = 1; i < u.n_slots; ++i)
-      for (int j = i; j > 0 && u.slot_block[order[j - 1]] > u.slot_block[order[j]]; --j) { int x = order[j]; order[j] = order[j - 1]; order[j - 1] = x; }
-    int nb_sorted[kMaxSlots];
-    for (int i = 0; i < u.n_slots; ++i) { nb_sorted[i] = u.slot_block[order[i]]; inv[order[i]] = i; }
-    for (int i = 0; i < u.n_slots; ++i) u.slot_block[i] = nb_sorted[i];
-    for (int t = 0; t < u.n_tiles; ++t) { u.a_slot[t] = inv[u.a_slot[t]]; u.b_slot[t] = inv[u.b_slot[t]]; }
-    // (2) tiles sorted by (A slot, B slot)
-    for (int i = 1; i < u.n_tiles; ++i)
-      for (int j = i; j > 0 && (u.a_slot[j - 1] > u.a_slot[j] || (u.a_slot[j - 1] == u.a_slot[j] && u.b_slot[j - 1] > u.b_slot[j])); --j) {
-        int x;
-        x = u.a_slot[j]; u.a_slot[j] = u.a_slot[j - 1]; u.a_slot[j - 1] = x;
-        x = u.b_slot[j]; u.b_slot[j] = u.b_slot[j - 1]; u.b_slot[j - 1] = x;
-        x = u.tile_id[j]; u.tile_id[j] = u.tile_id[j - 1]; u.tile_id[j - 1] = x;
+// Slot order for the blocks of a unit such that every pair's B blocks are adjacent (b[0] then b[1]); false if impossible.
+static bool unit_slot_order(const PlanOp* ops, int n_ops, int* blocks, int n_blocks) {
+  int perm[kMaxSlots];
+  for (int i = 0; i < n_blocks; ++i) perm[i] = i;
+  // blocks[] is ascending on entry; enumerate permutations in lexicographic order (deterministic choice)
+  for (;;) {
+    bool ok = true;
+    for (int o = 0; o < n_ops && ok; ++o) {
+      if (ops[o].nbk != 2) continue;
+      int p0 = -1, p1 = -1;
+      for (int i = 0; i < n_blocks; ++i) {
+        if (blocks[perm[i]] == ops[o].b[0]) p0 = i;
+        if (blocks[perm[i]] == ops[o].b[1]) p1 = i;
       }
-    // (3) same A + adjacent B slots -> one N=256 MMA (A is read from shared memory once for both tiles)
-    for (int t = 0; t < kMaxMma; ++t) u.pair[t] = 0;
-    for (int t = 0; t + 1 < u.n_tiles; ++t)
-      if (u.pair[t] == 0 && u.a_slot[t] == u.a_slot[t + 1] && u.b_slot[t + 1] == u.b_slot[t] + 1) { u.pair[t] = 1; u.pair[t + 1] = 2; }
+      ok = p1 == p0 + 1;
+    }
+    if (ok) {
+      int tmp[kMaxSlots];
+      for (int i = 0; i < n_blocks; ++i) tmp[i] = blocks[perm[i]];
+      for (int i = 0; i < n_blocks; ++i) blocks[i] = tmp[i];
+      return true;
+    }
+    // next permutation
+    int i = n_blocks - 2;
+    while (i >= 0 && perm[i] > perm[i + 1]) --i;
+    if (i < 0) return false;
+    int j = n_blocks - 1;
+    while (perm[j] < perm[i]) --j;
+    int x = perm[i]; perm[i] = perm[j]; perm[j] = x;
+    for (int l = i + 1, r = n_blocks - 1; l < r; ++l, --r) { x = perm[l]; perm[l] = perm[r]; perm[r] = x; }
+  }
+}
+
+static int union_blocks(const PlanOp* ops, int n_ops, int* out) {
+  int n = 0;
+  for (int o = 0; o < n_ops; ++o) {
+    int b[3];
+    const int m = op_blocks(ops[o], b);
+    for (int i = 0; i < m; ++i) {
+      bool have = false;
+      for (int j = 0; j < n; ++j) have |= out[j] == b[i];
+      if (!have) out[n++] = b[i];
+    }
+  }
+  for (int i = 1; i < n; ++i)
+    for (int j = i; j > 0 && out[j - 1] > out[j]; --j) { int x = out[j]; out[j] = out[j - 1]; out[j - 1] = x; }
+  return n;
+}
+
+static bool unit_feasible(const PlanOp* ops, int n_ops) {
+  int tiles = 0;
+  for (int o = 0; o < n_ops; ++o) tiles += ops[o].nbk;
+  if (tiles > kMaxMma) return false;
+  int blocks[3 * (kMaxMma + 1)];
+  const int nbk = union_blocks(ops, n_ops, blocks);
+  if (nbk > kMaxSlots) return false;
+  return unit_slot_order(ops, n_ops, blocks, nbk);
+}
+
+static void plan_units(int nb, int b0, int64_t T, GramUnit* units, int* n_units, int* max_slots, GramFlipMask* flips) {
+  int n = 0, ms = 0;
+  if (flips) flips->w[0] = flips->w[1] = flips->w[2] = 0;
+  const int last_rows = (int)(T - (int64_t)(nb - 1) * kTile);  // valid rows of the last block
+  auto block_rows = [&](int blk) { return blk == nb - 1 ? last_rows : kTile; };
+  auto emit = [&](const PlanOp* ops_in, int n_ops) {
+    // pairs first (their accumulators start at even TMEM tiles), then singles
+    PlanOp ops[kMaxMma];
+    int m = 0;
+    for (int pass = 2; pass >= 1; --pass)
+      for (int o = 0; o < n_ops; ++o)
+        if (ops_in[o].nbk == pass) ops[m++] = ops_in[o];
+    GramUnit u;
+    memset(&u, 0, sizeof(u));
+    int blocks[3 * (kMaxMma + 1)];
+    u.n_slots = union_blocks(ops, n_ops, blocks);
+    unit_slot_order(ops, n_ops, blocks, u.n_slots);
+    for (int i = 0; i < u.n_slots; ++i) u.slot_block[i] = blocks[i];
+    auto slot_of = [&](int blk) {
+      for (int i = 0; i < u.n_slots; ++i)
+        if (u.slot_block[i] == blk) return i;
+      return -1;
+    };
+    for (int o = 0; o < n_ops; ++o) {
+      u.op_a[o] = slot_of(ops[o].a);
+      u.op_b[o] = slot_of(ops[o].b[0]);
+      u.op_t0[o] = u.n_tiles;
+      int ncols = 0;
+      for (int i = 0; i < ops[o].nbk; ++i) {
+        const int a = ops[o].a, b = ops[o].b[i];
+        const int bi = a < b ? a : b, bj = a < b ? b : a;
+        const int id = tri_id(bi, bj, b0);
+        u.tile_id[u.n_tiles] = id;
+        u.tile_rows[u.n_tiles] = block_rows(a);
+        u.tile_cols[u.n_tiles] = block_rows(b);
+        if (a > b && flips && id < 192) flips->w[id >> 6] |= 1ull << (id & 63);
+        ++u.n_tiles;
+        // MMA N: full 128 for a leading block, the valid rows rounded up to 16 for the trailing one
+        ncols += (i + 1 < ops[o].nbk) ? kTile : ((block_rows(b) + 15) / 16) * 16;
+      }
+      u.op_n[o] = ncols;
+    }
+    u.n_ops = n_ops;
     if (units) units[n] = u;
     ++n;
     if (u.n_slots > ms) ms = u.n_slots;
   };
-  if (tri_count(nb, b0) <= 136) {
-    const int nt = tri_count(nb, b0);
-    int tb[136][2];
+  if (nb <= 16) {  // <= 136 tiles
+    // (1) ops: per row block a, its not-yet-covered tiles (a, b >= a) plus tiles (x, a), x < a, that star x left over, paired
+    //     up in ascending block order.  An odd tile out is handed to the star of its other block when there is one.
+    PlanOp ops[136];
+    int n_ops = 0;
+    int deferred[17][17], n_def[17];
+    for (int i = 0; i < 17; ++i) n_def[i] = 0;
+    for (int a = 0; a < nb; ++a) {
+      int ent[40], ne = 0;
+      for (int i = 0; i < n_def[a]; ++i) ent[ne++] = deferred[a][i];
+      for (int b = (a > b0 ? a : b0); b < nb; ++b) ent[ne++] = b;
+      if (ne & 1) {
+        if (ent[ne - 1] > a) {  // largest entry is a block with a star still to come
+          const int x = ent[--ne];
+          deferred[x][n_def[x]++] = a;
+        }
+      }
+      int single = -1;
+      if (ne & 1) {  // nothing to hand on: the diagonal tile (cheapest single: one operand fetch) or the last entry stays alone
+        int pos = ne - 1;
+        for (int i = 0; i < ne; ++i)
+          if (ent[i] == a) pos = i;
+        single = ent[pos];
+        for (int i = pos; i + 1 < ne; ++i) ent[i] = ent[i + 1];
+        --ne;
+      }
+      for (int i = 0; i + 1 < ne; i += 2) { ops[n_ops].a = a; ops[n_ops].nbk = 2; ops[n_ops].b[0] = ent[i]; ops[n_ops].b[1] = ent[i + 1]; ++n_ops; }
+      if (single >= 0) {
+        // orientation of a single is free: keep A = the lower block so that a trailing partial block is the (trimmed) B
+        const int lo = single < a ? single : a, hi = single < a ? a : single;
+        ops[n_ops].a = lo; ops[n_ops].nbk = 1; ops[n_ops].b[0] = hi; ops[n_ops].b[1] = -1; ++n_ops;
+      }
+    }
+    // (2) units: seed + the op that adds the fewest new blocks while the unit stays feasible
     bool done[136];
-    int c = 0;
-    for (int bi = 0; bi < nb; ++bi)
-      for (int bj = (bi > b0 ? bi : b0); bj < nb; ++bj) { tb[c][0] = bi; tb[c][1] = bj; done[c] = false; ++c; }
-    for (int seed = 0; seed < nt; ++seed) {
+    for (int i = 0; i < n_ops; ++i) done[i] = false;
+    for (int seed = 0; seed < n_ops; ++seed) {
       if (done[seed]) continue;
-      GramUnit u;
-      memset(&u, 0, sizeof(u));
-      unit_add(u, tb[seed][0], tb[seed][1], b0);
+      PlanOp uo[kMaxMma + 1];
+      int nu = 0;
+      uo[nu++] = ops[seed];
       done[seed] = true;
-      while (u.n_tiles < kMaxMma) {
+      for (;;) {
+        int cur[3 * (kMaxMma + 1)];
+        const int ncur = union_blocks(uo, nu, cur);
         int best = -1, best_new = 99;
-        for (int t = 0; t < nt; ++t) {
-          if (done[t]) continue;
-          const int nw = unit_new_blocks(u, tb[t][0], tb[t][1]);
-          if (u.n_slots + nw <= kMaxSlots && nw < best_new) { best = t; best_new = nw; }
+        for (int o = 0; o < n_ops; ++o) {
+          if (done[o]) continue;
+          uo[nu] = ops[o];
+          if (!unit_feasible(uo, nu + 1)) continue;
+          int tmp[3 * (kMaxMma + 1)];
+          const int nw = union_blocks(uo, nu + 1, tmp) - ncur;
+          if (nw < best_new) { best = o; best_new = nw; }
         }
         if (best < 0) break;
-        unit_add(u, tb[best][0], tb[best][1], b0);
+        uo[nu++] = ops[best];
         done[best] = true;
       }
-      emit(u);
+      emit(uo, nu);
     }
   } else {
+    // 2x2 super-blocks: rows {2I, 2I+1} x columns {2J, 2J+1}; each row block against its (one or two) column blocks
     const int ns = (nb + 1) / 2;
     for (int I = 0; I < ns; ++I)
       for (int J = I; J < ns; ++J) {
-        GramUnit u;
-        memset(&u, 0, sizeof(u));
-        for (int bi = 2 * I; bi < 2 * I + 2 && bi < nb; ++bi)
+        PlanOp uo[kMaxMma];
+        int nu = 0;
+        for (int bi = 2 * I; bi < 2 * I + 2 && bi < nb; ++bi) {
+          PlanOp o;
+          o.a = bi; o.nbk = 0; o.b[0] = o.b[1] = -1;
           for (int bj = 2 * J; bj < 2 * J + 2 && bj < nb; ++bj)
-            if (bi <= bj && bj >= b0) unit_add(u, bi, bj, b0);
-        if (u.n_tiles) emit(u);
+            if (bi <= bj && bj >= b0) o.b[o.nbk++] = bj;
+          if (o.nbk) uo[nu++] = o;
+        }
+        if (nu) emit(uo, nu);
       }
   }
   *n_units = n;
@@ -156,7 +277,7 @@ static GramPlan make_plan(int64_t T, int64_t K, int64_t T_old = 0) {
   p.nb = (int)((T + kTile - 1) / kTile);
   p.b0 = (int)(T_old / kTile);
   p.n_tiles = tri_count(p.nb, p.b0);
-  plan_units(p.nb, p.b0, nullptr, &p.n_units, &p.max_slots);
+  plan_units(p.nb, p.b0, T, nullptr, &p.n_units, &p.max_slots, nullptr);
   p.n_chunks = (int)((K + kChunk - 1) / kChunk);
   int kr = kNumSMs / p.n_units;
   if (kr < 1) kr = 1;
@@ -222,37 +343,57 @@ __global__ void __launch_bounds__(256) gram_simt_kernel(const __nv_bfloat16* __r
 // Sum the K ranges in fp64 (fixed order) and write both triangles of G.
 // ---------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) gram_reduce_kernel(const float* __restrict__ partial, int T, int nb, int b0, int n_tiles,
-                                                          int n_kr, double* __restrict__ G, int64_t ldg) {
-  // grid (n_tiles, 16): a thread owns 4 consecutive columns of one tile row; the K ranges are streamed with 8
-  // independent 128-bit loads in flight and added in ascending range order (fixed -> deterministic).
+                                                          int n_kr, double* __restrict__ G, int64_t ldg,
+                                                          const __grid_constant__ GramFlipMask flips, int transposed_store) {
   int tid = blockIdx.x, bj = b0;
   while (tid >= bj + 1) { tid -= bj + 1; ++bj; }
-  const int bi = tid;
-  const int e4 = blockIdx.y * 256 + threadIdx.x;  // float4 index inside the tile, 4096 per tile
+  int bi = tid;
+  // Stored tile S[x][y]: the CUDA-core kernel writes rows = block bi, columns = block bj.  The tensor kernel stores its
+  // accumulators transposed (rows = the op's B block), and an op of the small-problem planner may have used A = the higher
+  // block (flip bit): rows = block bj unless both or neither apply.
+  const int flipped = (blockIdx.x < 192) ? (int)((flips.w[blockIdx.x >> 6] >> (blockIdx.x & 63)) & 1ull) : 0;
+  if (flipped != transposed_store) { const int x = bi; bi = bj; bj = x; }
+  // grid (n_tiles, 32) x 256 threads: a lane pair owns 4 consecutive columns of one tile row; the even lane sums the even K
+  // ranges, the odd lane the odd ones (each in ascending order, all loads of a thread in flight at once), and the two halves
+  // are added even + odd: a fixed order, so G is deterministic.
+  const int half = threadIdx.x & 1;
+  const int e4 = blockIdx.y * 128 + (threadIdx.x >> 1);  // float4 index inside the tile, 4096 per tile
   const int r = e4 >> 5, c = (e4 & 31) * 4;
   const int gi = bi * kTile + r, gj = bj * kTile + c;
-  if (gi >= T || gj >= T) return;
+  const bool valid = gi < T && gj < T;  // no early return: the pair exchange below is a full-warp shuffle
+  // launched with programmatic stream serialization: the blocks are resident before the Gram kernel ends; wait for its
+  // completion (and the visibility of its partial tiles) here
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   const float4* base = reinterpret_cast<const float4*>(partial + (int64_t)blockIdx.x * (kTile * kTile)) + e4;
   const int64_t kr_stride4 = (int64_t)n_tiles * kTile * kTile / 4;
   double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-  int kr = 0;
-  for (; kr + 8 <= n_kr; kr += 8) {
+  int kr = valid ? half : n_kr;
+  for (; kr + 2 * 7 < n_kr; kr += 2 * 8) {
     float4 v[8];
 #pragma unroll
-    for (int u = 0; u < 8; ++u) v[u] = __ldcs(base + (int64_t)(kr + u) * kr_stride4);
+    for (int u = 0; u < 8; ++u) v[u] = __ldcs(base + (int64_t)(kr + 2 * u) * kr_stride4);
 #pragma unroll
     for (int u = 0; u < 8; ++u) { s0 += (double)v[u].x; s1 += (double)v[u].y; s2 += (double)v[u].z; s3 += (double)v[u].w; }
   }
-  for (; kr < n_kr; ++kr) {
+  for (; kr < n_kr; kr += 2) {
     const float4 v = __ldcs(base + (int64_t)kr * kr_stride4);
     s0 += (double)v.x; s1 += (double)v.y; s2 += (double)v.z; s3 += (double)v.w;
+  }
+  {
+    const double o0 = __shfl_xor_sync(0xffffffffu, s0, 1), o1 = __shfl_xor_sync(0xffffffffu, s1, 1);
+    const double o2 = __shfl_xor_sync(0xffffffffu, s2, 1), o3 = __shfl_xor_sync(0xffffffffu, s3, 1);
+    // even + odd on both lanes (commutative, so both lanes hold the same bits)
+    s0 = half ? o0 + s0 : s0 + o0;
+    s1 = half ? o1 + s1 : s1 + o1;
+    s2 = half ? o2 + s2 : s2 + o2;
+    s3 = half ? o3 + s3 : s3 + o3;
   }
   const double sv[4] = {s0, s1, s2, s3};
 #pragma unroll
   for (int u = 0; u < 4; ++u) {
-    if (gj + u < T) {
-      G[(int64_t)gi * ldg + gj + u] = sv[u];
-      if (bi != bj) G[(int64_t)(gj + u) * ldg + gi] = sv[u];
+    if (valid && gj + u < T) {
+      if (!half) G[(int64_t)gi * ldg + gj + u] = sv[u];
+      else if (bi != bj) G[(int64_t)(gj + u) * ldg + gi] = sv[u];
     }
   }
 }
@@ -322,6 +463,11 @@ __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)
       : "r"(taddr)
       : "memory");
 }
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 }  // namespace ptx
 
@@ -347,19 +493,40 @@ __global__ void __launch_bounds__(160, 1) gram_tc_kernel(const __grid_constant__
                                                          const __grid_constant__ GramUnitTable ptable,
                                                          const GramUnit* __restrict__ units, int n_tiles, int n_kr,
                                                          int n_chunks, int kStages, int stage_bytes,
-                                                         float* __restrict__ partial, int dbg) {
+                                                         float* __restrict__ partial, int dbg,
+                                                         unsigned long long* __restrict__ tl) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // stage buffers first (1024-byte aligned for SWIZZLE_128B), control block after
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   GramSmemCtl* ctl = reinterpret_cast<GramSmemCtl*>(smem + (size_t)kStages * stage_bytes);
   __shared__ GramUnit unit;
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // warp index through a shuffle: provably warp-uniform, so the role branches and everything derived from them stay on the
+  // uniform datapath (no per-MMA "elect + R2UR" waterfall in the issue loop)
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const int kr = blockIdx.y;
+  // profiling aid (dbg & 8): 8 globaltimer marks per CTA -- entry, setup done, first operands landed, last MMA issued,
+  // accumulators complete, drain done, last TMA issued, SM id
+  unsigned long long* mark = tl ? tl + (size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 8 : nullptr;
+  auto stamp = [&](int i) {
+    if (mark) {
+      unsigned long long t;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+      mark[i] = t;
+    }
+  };
+  if (threadIdx.x == 0) {
+    stamp(0);
+    if (mark) { unsigned sm; asm volatile("mov.u32 %0, %%smid;" : "=r"(sm)); mark[7] = sm; }
+  }
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // the reduce kernel may be scheduled; it waits for our end
   const int c0 = (int)((int64_t)kr * n_chunks / n_kr), c1 = (int)((int64_t)(kr + 1) * n_chunks / n_kr);
   const int nchunk = c1 - c0;
 
-  if (threadIdx.x == 0) unit = units ? units[blockIdx.x] : ptable.u[blockIdx.x];
+  if (threadIdx.x < (int)(sizeof(GramUnit) / sizeof(int))) {
+    const int* src = units ? reinterpret_cast<const int*>(units + blockIdx.x) : reinterpret_cast<const int*>(&ptable.u[blockIdx.x]);
+    reinterpret_cast<int*>(&unit)[threadIdx.x] = src[threadIdx.x];
+  }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < kStages; ++s) {
       ptx::mbar_init(&ctl->full[s], 1);
@@ -377,19 +544,16 @@ __global__ void __launch_bounds__(160, 1) gram_tc_kernel(const __grid_constant__
   ptx::tc_fence_after();
   const uint32_t tmem_base = ctl->tmem_base;
   const int n_slots = unit.n_slots, n_ut = unit.n_tiles;
+  if (threadIdx.x == 0) stamp(1);
 
   if (warp == 4) {
     if (lane == 0) {
       // ===== TMA producer (dedicated warp: it may run ahead across accumulator drains) =====
       asm volatile("prefetch.tensormap [%0];" ::"l"(&xmap) : "memory");
       // L2 prefetch runs kPrefetch chunks ahead of the shared-memory ring: the ring then only has to cover L2-hit
-      // latency, the (longer) DRAM latency is hidden without spending shared memory on it.
-      for (int c = 0; c < kPrefetch && c < nchunk && !(dbg & 2); ++c)
-        for (int q = 0; q < n_slots; ++q) ptx::tma_prefetch_l2_2d(&xmap, (c0 + c) * kChunk, unit.slot_block[q] * kTile);
+      // latency, the (longer) DRAM latency is hidden without spending shared memory on it.  The first ring fill is issued
+      // before the first prefetches so that it is not queued behind them.
       for (int c = 0; c < nchunk; ++c) {
-        if (!(dbg & 2) && c + kPrefetch < nchunk)
-          for (int q = 0; q < n_slots; ++q)
-            ptx::tma_prefetch_l2_2d(&xmap, (c0 + c + kPrefetch) * kChunk, unit.slot_block[q] * kTile);
         const int s = c % kStages;
         const uint32_t ph = (uint32_t)(c / kStages) & 1u;
         ptx::mbar_wait(&ctl->empty[s], ph ^ 1u);
@@ -401,69 +565,96 @@ __global__ void __launch_bounds__(160, 1) gram_tc_kernel(const __grid_constant__
         uint8_t* stage = smem + (size_t)s * stage_bytes;
         for (int q = 0; q < n_slots; ++q)
           ptx::tma_load_2d(stage + (size_t)q * kBlockBytes, &xmap, &ctl->full[s], (c0 + c) * kChunk, unit.slot_block[q] * kTile);
+        if (c == kStages - 1 || (nchunk < kStages && c == nchunk - 1)) {
+          // ring filled once: now start the L2 prefetch stream, kPrefetch chunks deep
+          for (int f = c + 1; f < c + 1 + kPrefetch && f < nchunk; ++f)
+            for (int q = 0; q < n_slots; ++q) ptx::tma_prefetch_l2_2d(&xmap, (c0 + f) * kChunk, unit.slot_block[q] * kTile);
+        } else if (c >= kStages && c + kPrefetch < nchunk) {
+          for (int q = 0; q < n_slots; ++q) ptx::tma_prefetch_l2_2d(&xmap, (c0 + c + kPrefetch) * kChunk, unit.slot_block[q] * kTile);
+        }
       }
+      stamp(6);
     }
   } else {
-    // ===== warps 0-3: MMA issue (warp 1, lane 0) + accumulator drain (all four; warp w owns TMEM lanes 32w..32w+31) =====
+    // ===== warps 0-3: MMA issue (warp 1, one elected lane) + accumulator drain (all four; warp w owns TMEM lanes 32w..32w+31) =====
     // The tensor core accumulates in fp32 with truncation, so a chain of n MMAs drifts by up to ~n * 2^-24 relative.  Chains
     // are cut every kSegChunks chunks: the accumulators are drained and added (round-to-nearest fp32) into the partial
     // tile, then restarted from zero.  Short K ranges (config 2: 88 chunks per CTA) are a single segment.
-    constexpr uint32_t idesc = make_idesc(128, 128), idesc256 = make_idesc(128, 256);
     const int nseg = (nchunk + kSegChunks - 1) / kSegChunks;
+    // per-op constants of the issue loop, made warp-uniform (shuffle) and hoisted: descriptor low words without the stage
+    // offset, instruction descriptor, accumulator column
+    uint32_t op_alo[kMaxMma], op_blo[kMaxMma], op_idesc[kMaxMma], op_col[kMaxMma];
+    const int n_ops = __shfl_sync(0xffffffffu, unit.n_ops, 0);
+#pragma unroll
+    for (int o = 0; o < kMaxMma; ++o) {
+      const int a = __shfl_sync(0xffffffffu, unit.op_a[o], 0), b = __shfl_sync(0xffffffffu, unit.op_b[o], 0);
+      const int n = __shfl_sync(0xffffffffu, unit.op_n[o], 0), t0 = __shfl_sync(0xffffffffu, unit.op_t0[o], 0);
+      op_alo[o] = ((uint32_t)(a * kBlockBytes) >> 4) | (1u << 16);
+      op_blo[o] = ((uint32_t)(b * kBlockBytes) >> 4) | (1u << 16);
+      op_idesc[o] = make_idesc(128, n);
+      op_col[o] = tmem_base + (uint32_t)t0 * 128u;
+    }
+    constexpr uint32_t kDescHi = 64u | (1u << 14) | (2u << 29);  // SBO = 1024 B, version 1, SWIZZLE_128B
+    const uint32_t smem_lo = ptx::smem_u32(smem) >> 4;
     for (int seg = 0; seg < nseg; ++seg) {
       const int cs = seg * kSegChunks, ce = min(nchunk, cs + kSegChunks);
-      if (warp == 1 && lane == 0) {
+      if (warp == 1) {
         for (int c = cs; c < ce; ++c) {
           const int s = c % kStages;
           const uint32_t ph = (uint32_t)(c / kStages) & 1u;
           ptx::mbar_wait(&ctl->full[s], ph);
           ptx::tc_fence_after();
-          const uint32_t stage = ptx::smem_u32(smem + (size_t)s * stage_bytes);
-          // tile-outer / k-step-inner: four back-to-back MMAs accumulate into the same TMEM tile.  (Measured: the k-step-outer
-          // order, which would let tiles that share A reuse it through the A collector, runs 2x slower -- alternating the
-          // accumulator between consecutive MMAs costs far more than the saved shared-memory reads.)
-          for (int t = 0; t < n_ut && !(dbg & 1); ++t) {  // dbg&1: profiling aid, loads only
-            const int pr = (dbg & 4) ? 0 : unit.pair[t];
-            if (pr == 2) continue;  // covered by the N=256 MMA of tile t-1
-            const uint32_t a_addr = stage + (uint32_t)unit.a_slot[t] * kBlockBytes;
-            const uint32_t b_addr = stage + (uint32_t)unit.b_slot[t] * kBlockBytes;
-            const uint32_t id = pr == 1 ? idesc256 : idesc;
+          if (ptx::elect_one()) {
+            if (c == 0) stamp(2);
+            const uint32_t so = smem_lo + (uint32_t)(s * stage_bytes >> 4);
+            // op-outer / k-step-inner: four back-to-back MMAs accumulate into the same TMEM tile(s)
 #pragma unroll
-            for (int ks = 0; ks < kChunk / 16; ++ks) {
-              ptx::umma_bf16(tmem_base + (uint32_t)t * 128u, make_smem_desc(a_addr + ks * 32), make_smem_desc(b_addr + ks * 32),
-                             id, (c > cs || ks > 0) ? 1u : 0u);
+            for (int o = 0; o < kMaxMma; ++o) {
+              if (o < n_ops && !(dbg & 1)) {  // dbg&1: profiling aid, loads only
+#pragma unroll
+                for (int ks = 0; ks < kChunk / 16; ++ks) {
+                  const uint64_t ad = ((uint64_t)kDescHi << 32) | (uint64_t)(op_alo[o] + so + 2u * ks);
+                  const uint64_t bd = ((uint64_t)kDescHi << 32) | (uint64_t)(op_blo[o] + so + 2u * ks);
+                  ptx::umma_bf16(op_col[o], ad, bd, op_idesc[o], (c > cs || ks > 0) ? 1u : 0u);
+                }
+              }
+            }
+            ptx::umma_commit(&ctl->empty[s]);  // frees the stage once these MMAs have read it
+            if (c == ce - 1) {
+              ptx::umma_commit(&ctl->accum_done);
+              stamp(3);
             }
           }
-          ptx::umma_commit(&ctl->empty[s]);  // frees the stage once these MMAs have read it
+          __syncwarp();
         }
-        ptx::umma_commit(&ctl->accum_done);
       }
-      __syncwarp();
       ptx::mbar_wait(&ctl->accum_done, (uint32_t)seg & 1u);
       ptx::tc_fence_after();
+      if (threadIdx.x == 0) stamp(4);
+      // Drain: lane = accumulator row.  The tile is stored TRANSPOSED ([column][row]): for a fixed column the 32 lanes of a
+      // warp write 32 consecutive floats = one full 128-byte line per store instruction (row-major float4 stores would touch
+      // 32 different lines per instruction and serialise in the LSU: measured 10 us for 38 MB).  The reduce kernel undoes it.
+      const int row = warp * 32 + lane;
       for (int t = 0; t < n_ut; ++t) {
-        float* out = partial + ((int64_t)kr * n_tiles + unit.tile_id[t]) * (kTile * kTile) + (int64_t)(warp * 32 + lane) * kTile;
+        float* out = partial + ((int64_t)kr * n_tiles + unit.tile_id[t]) * (kTile * kTile) + row;
+        const bool row_ok = row < unit.tile_rows[t];
+        const int ncols = unit.tile_cols[t];
+        const int ncb = (ncols + 31) >> 5;  // 32-column groups that hold valid columns
 #pragma unroll 1
-        for (int cb = 0; cb < 4; ++cb) {
+        for (int cb = 0; cb < ncb; ++cb) {
           uint32_t r[32];
           ptx::tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(t * 128 + cb * 32), r);
           ptx::tmem_ld_wait();
-          float4* o4 = reinterpret_cast<float4*>(out + cb * 32);
+          if (!row_ok) continue;
+          float* o = out + (int64_t)(cb * 32) * kTile;
           if (seg == 0) {
 #pragma unroll
-            for (int v = 0; v < 8; ++v)
-              o4[v] = make_float4(__uint_as_float(r[4 * v]), __uint_as_float(r[4 * v + 1]), __uint_as_float(r[4 * v + 2]),
-                                  __uint_as_float(r[4 * v + 3]));
+            for (int j = 0; j < 32; ++j)
+              if (cb * 32 + j < ncols) o[j * kTile] = __uint_as_float(r[j]);
           } else {
 #pragma unroll
-            for (int v = 0; v < 8; ++v) {
-              float4 o = o4[v];
-              o.x = __fadd_rn(o.x, __uint_as_float(r[4 * v]));
-              o.y = __fadd_rn(o.y, __uint_as_float(r[4 * v + 1]));
-              o.z = __fadd_rn(o.z, __uint_as_float(r[4 * v + 2]));
-              o.w = __fadd_rn(o.w, __uint_as_float(r[4 * v + 3]));
-              o4[v] = o;
-            }
+            for (int j = 0; j < 32; ++j)
+              if (cb * 32 + j < ncols) o[j * kTile] = __fadd_rn(o[j * kTile], __uint_as_float(r[j]));
           }
         }
       }
@@ -476,6 +667,7 @@ __global__ void __launch_bounds__(160, 1) gram_tc_kernel(const __grid_constant__
   }
   ptx::tc_fence_before();
   __syncthreads();
+  if (threadIdx.x == 0) stamp(5);
   if (warp == 2) ptx::tmem_dealloc(tmem_base, 512);
 }
 
@@ -530,6 +722,8 @@ int csb_gram_extend(const void* x, int64_t T_old, int64_t T, int64_t K, double* 
   }
   cudaStream_t s = as_stream(stream);
   float* partial = reinterpret_cast<float*>(workspace);
+  GramFlipMask flips;
+  flips.w[0] = flips.w[1] = flips.w[2] = 0;
   int n_kr;
   if ((impl & 15) == 1) {
     n_kr = (2 * kNumSMs + p.n_tiles - 1) / p.n_tiles;
@@ -545,21 +739,24 @@ int csb_gram_extend(const void* x, int64_t T_old, int64_t T, int64_t K, double* 
     const int kr_max = kr_simt > p.n_kr ? kr_simt : p.n_kr;
     GramUnit* d_units = nullptr;
     static thread_local GramUnitTable table;  // plan for small problems, passed by value
+    static thread_local GramFlipMask table_flips;
     cudaError_t e = cudaSuccess;
     if (p.n_units <= kMaxParamUnits) {
-      static thread_local int table_nb = -1, table_b0 = -1;
-      if (table_nb != p.nb || table_b0 != p.b0) {
+      static thread_local int64_t table_T = -1;
+      static thread_local int table_b0 = -1;
+      if (table_T != T || table_b0 != p.b0) {
         int nu = 0;
-        plan_units(p.nb, p.b0, table.u, &nu, nullptr);
-        table_nb = p.nb;
+        plan_units(p.nb, p.b0, T, table.u, &nu, nullptr, &table_flips);
+        table_T = T;
         table_b0 = p.b0;
       }
+      flips = table_flips;
     } else {
       d_units = reinterpret_cast<GramUnit*>(reinterpret_cast<char*>(workspace) +
                                             align_up((size_t)kr_max * p.n_tiles * kTile * kTile * sizeof(float), 256));
       GramUnit* h_units = (GramUnit*)malloc(sizeof(GramUnit) * p.n_units);
       int nu = 0;
-      plan_units(p.nb, p.b0, h_units, &nu, nullptr);
+      plan_units(p.nb, p.b0, T, h_units, &nu, nullptr, &flips);
       e = cudaMemcpyAsync(d_units, h_units, sizeof(GramUnit) * nu, cudaMemcpyHostToDevice, s);
       cudaStreamSynchronize(s);  // pageable source buffer is freed below (large-T path only)
       free(h_units);
@@ -582,16 +779,34 @@ int csb_gram_extend(const void* x, int64_t T_old, int64_t T, int64_t K, double* 
     e = cudaFuncSetAttribute(gram_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
     if (e != cudaSuccess) { set_error("gram: smem attr: %s", cudaGetErrorString(e)); return CSB_ERR_CUDA; }
     dim3 grid((unsigned)p.n_units, (unsigned)n_kr);
-    gram_tc_kernel<<<grid, 160, smem_bytes, s>>>(map, table, d_units, p.n_tiles, n_kr, p.n_chunks, p.n_stages, stage_bytes, partial,
-                                                     impl >> 4);
+    // profiling aid: impl bit 7 (dbg & 8) + a workspace with room behind the documented size -> per-CTA time marks there
+    unsigned long long* tl = nullptr;
+    const size_t tl_bytes = (size_t)p.n_units * n_kr * 8 * sizeof(unsigned long long);
+    if (((impl >> 4) & 8) && workspace_bytes >= gram_ws_bytes(p) + tl_bytes)
+      tl = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(workspace) + gram_ws_bytes(p));
+    if (!((impl >> 4) & 16))  // profiling aid: impl bit 8 = reduce kernel only
+      gram_tc_kernel<<<grid, 160, smem_bytes, s>>>(map, table, d_units, p.n_tiles, n_kr, p.n_chunks, p.n_stages, stage_bytes, partial,
+                                                     impl >> 4, tl);
     int st = check_launch("gram_tc");
     if (st) return st;
   } else {
     set_error("gram: unknown impl %d", impl);
     return CSB_ERR_ARG;
   }
-  dim3 rgrid((unsigned)p.n_tiles, 16);
-  gram_reduce_kernel<<<rgrid, 256, 0, s>>>(partial, (int)T, p.nb, p.b0, p.n_tiles, n_kr, G, ldg);
+  dim3 rgrid((unsigned)p.n_tiles, 32);
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = rgrid;
+  cfg.blockDim = dim3(256);
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t le = cudaLaunchKernelEx(&cfg, gram_reduce_kernel, (const float*)partial, (int)T, p.nb, p.b0, p.n_tiles, n_kr, G, ldg,
+                                      flips, (impl & 15) == 0 ? 1 : 0);
+  if (le != cudaSuccess) { set_error("gram_reduce: launch: %s", cudaGetErrorString(le)); return CSB_ERR_CUDA; }
   return check_launch("gram_reduce");
 }
 
