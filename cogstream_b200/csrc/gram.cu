@@ -420,6 +420,22 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       "r"(parity)
       : "memory");
 }
+// long waits (the drain warps sit out the whole main loop): poll with a sleep in between instead of spinning on the barrier,
+// so that the idle warps do not take issue slots / shared-memory cycles from the MMA operand fetch and from co-resident CTAs
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
+  for (;;) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    if (done) break;
+    __nanosleep(500);
+  }
+}
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
   asm volatile(
@@ -628,7 +644,7 @@ __global__ void __launch_bounds__(160, 1) gram_tc_kernel(const __grid_constant__
           __syncwarp();
         }
       }
-      ptx::mbar_wait(&ctl->accum_done, (uint32_t)seg & 1u);
+      ptx::mbar_wait_relaxed(&ctl->accum_done, (uint32_t)seg & 1u);
       ptx::tc_fence_after();
       if (threadIdx.x == 0) stamp(4);
       // Drain: lane = accumulator row.  The tile is stored TRANSPOSED ([column][row]): for a fixed column the 32 lanes of a
