@@ -60,6 +60,14 @@ def select_additional_frames(cls_feature, long_memory, cluster_assignments, addi
     return [reps[i, : counts_h[i]] for i in range(k)]
 
 
+def _mean_pool(hidden: torch.Tensor, cu_seqlens: torch.Tensor) -> torch.Tensor:
+    """``torch.mean(last_hidden_state, dim=1)`` (:317, :322) of the sequences of a packed ``[sum(len), Dl]`` tensor."""
+    if hidden.is_cuda and hidden.dtype in (torch.bfloat16, torch.float32) and hidden.shape[1] % 8 == 0:
+        return ops.seq_mean_pool(hidden.contiguous(), cu_seqlens)
+    cu = cu_seqlens.tolist()  # unusual dtype / width: the reference's op, on the device the LLM produced it on
+    return torch.stack([torch.mean(hidden[cu[j]: cu[j + 1]], dim=0) for j in range(len(cu) - 1)])
+
+
 def create_visual_summary_prompt(P, timestamps, image_token="<image>"):
     """Prompt of the per-event summary forward (text layout of cogreasoner_chat.py:93-119; it has to match
     token for token, since the frozen LLM's pooled hidden state is the event embedding)."""
@@ -103,35 +111,67 @@ class VisualStreamCompressionMixin:
         dev = feats.device
         ts = timestamps if isinstance(timestamps, torch.Tensor) else torch.tensor(timestamps)
         ts = ts.to(dev)
-        _, _, assign, info = kmeans_with_time_min_max(features, ts, k, return_info=True)  # :283
+        # csb_kmeans_kwargs: optional keyword-only extras of the drop-in k-means (init / reseed injection for tests)
+        _, _, assign, info = kmeans_with_time_min_max(features, ts, k, return_info=True,
+                                                      **getattr(self, "csb_kmeans_kwargs", {}))  # :283
         order, ev_off = ops.event_order(assign, k)
         dist = ops.dist_to_assigned_gram(info.gram, assign, ev_off, order, k)  # :284 (distances from the Gram matrix)
         _, _, rep_flags = ops.select_representatives(dist, assign, k, self.csb_n_representatives)
 
-        # chronological per-event gather (:286-296): one row-gather into a packed buffer, events are views
+        # chronological per-event gather (:286-296): one row-gather into a packed, event-major buffer
         packed = torch.empty_like(features)
         ops.gather_rows(features.view(T, P * D), order, packed.view(T, P * D), n=T)
         off_h = ev_off.tolist()
         ts_sorted = ts[order.long()].tolist()
-        events_repr = []
-        for i in range(k):  # :294-316, the frozen LLM is called exactly like the reference does
+        # prompts of all events first (:294-301), packed back to back (cu_seqlens layout)
+        ids_list, am_list = [], []
+        for i in range(k):
             lo, hi = off_h[i], off_h[i + 1]
-            ev = packed[lo:hi].reshape(-1, D)
-            prompt = create_visual_summary_prompt(ev.shape[0], ts_sorted[lo:hi])
+            prompt = create_visual_summary_prompt((hi - lo) * P, ts_sorted[lo:hi])
             inputs = self.tokenizer(prompt, return_tensors="pt")
-            input_ids = inputs["input_ids"].to(dev)
-            attention_mask = inputs["attention_mask"].to(dev)
-            inputs_embeds = self.get_model().embed_tokens(input_ids).clone()
-            image_selected = input_ids == self.config.image_token_index
-            inputs_embeds[image_selected] = inputs_embeds[image_selected] * 0.0 + ev.to(inputs_embeds.dtype)
-            out = self.get_model()(position_ids=None, attention_mask=attention_mask.view(1, -1),
-                                   inputs_embeds=inputs_embeds.reshape(1, -1, inputs_embeds.shape[-1]))
-            events_repr.append(torch.mean(out.last_hidden_state, dim=1))  # :317
-        events_repr = torch.cat(events_repr, dim=0)  # :318
+            ids_list.append(inputs["input_ids"].view(-1))
+            am_list.append(inputs["attention_mask"])
+        lens = [int(t.numel()) for t in ids_list]
+        cu_h = [0]
+        for n_i in lens:
+            cu_h.append(cu_h[-1] + n_i)
+        ids_all = torch.cat(ids_list).to(dev)
+        llm = self.get_model()
+        emb_w = getattr(getattr(llm, "embed_tokens", None), "weight", None)
+        fused = isinstance(emb_w, torch.Tensor) and emb_w.is_cuda and emb_w.dtype in (torch.bfloat16, torch.float32) \
+            and emb_w.shape[1] == D and emb_w.is_contiguous()
+        if fused:
+            # :303-305 for all k prompts in ONE pass: the j-th <image> id overall takes packed token row j
+            embeds_all, _ = ops.embed_scatter(ids_all, self.config.image_token_index, emb_w, packed.view(T * P, D))
+        else:  # a wrapped / sharded embedding module: the reference's own three torch ops, still on the device
+            embeds_all = llm.embed_tokens(ids_all).clone()
+            sel = ids_all == self.config.image_token_index
+            embeds_all[sel] = embeds_all[sel] * 0.0 + packed.view(T * P, D).to(embeds_all.dtype)
+        cu_pairs = torch.tensor([[0, n_i] for n_i in lens] + [[0, 0]], dtype=torch.int32).to(dev)  # per-call [0, L_i] rows
+        batched = getattr(self, "csb_batched_summary_forward", None)
+        if callable(batched):
+            # one var-len forward of the frozen LLM over the packed prompts (user-supplied, e.g. flash-attn
+            # varlen); returns the packed last hidden states [sum(len), Dl]
+            cu_all = torch.tensor(cu_h, dtype=torch.int32).to(dev)
+            hidden_all = batched(embeds_all, cu_all)
+            events_repr = _mean_pool(hidden_all, cu_all)
+        else:
+            events_repr = []
+            for i in range(k):  # :306-317, the frozen LLM is called exactly like the reference does
+                e_i = embeds_all[cu_h[i]: cu_h[i + 1]]
+                out = llm(position_ids=None, attention_mask=am_list[i].to(dev).view(1, -1),
+                          inputs_embeds=e_i.reshape(1, -1, e_i.shape[-1]))
+                events_repr.append(_mean_pool(out.last_hidden_state[0], cu_pairs[i]))  # :317
+            events_repr = torch.cat(events_repr, dim=0)  # :318
         inputs = self.tokenizer(self.current_question, padding=True, truncation=True, return_tensors="pt", max_length=128)
-        model_device = next(self.get_model().parameters()).device
+        model_device = next(llm.parameters()).device
         inputs = {kk: v.to(model_device) for kk, v in inputs.items()}
-        question = torch.mean(self.get_model()(**inputs).last_hidden_state, dim=1)  # :319-323
+        q_hidden = llm(**inputs).last_hidden_state  # :319-322
+        if q_hidden.shape[0] == 1:
+            q_cu = torch.tensor([0, q_hidden.shape[1]], dtype=torch.int32).to(q_hidden.device)
+            question = _mean_pool(q_hidden[0], q_cu)
+        else:
+            question = torch.mean(q_hidden, dim=1)
 
         ev_c = events_repr.to(dev).contiguous()
         q_c = question[0].to(device=dev, dtype=ev_c.dtype).contiguous()

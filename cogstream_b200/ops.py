@@ -454,3 +454,59 @@ def filter_ids(input_ids: torch.Tensor, image_token_index: int, mask: torch.Tens
                                          _ptr(am), _ptr(lb), _ptr(ps), o_ids.data_ptr(), _ptr(o_am), _ptr(o_lb), _ptr(o_ps),
                                          n_out.data_ptr(), ws.data_ptr(), ws.numel(), _stream(input_ids)), "filter_ids")
     return o_ids, o_am, o_lb, o_ps, n_out
+
+
+def embed_scatter(input_ids: torch.Tensor, image_token_index: int, embed_weight: torch.Tensor, features: Optional[torch.Tensor],
+                  *, out: Optional[torch.Tensor] = None, check_count: bool = True):
+    """``embed_tokens(input_ids)`` with the rows of the <image> ids replaced by ``embeds * 0.0 + features``
+    (cogreasoner_chat.py:303-305, :567-572) in one pass.  ``input_ids`` [n] int64 may be several prompts packed back to back;
+    ``features`` [n_image, D] are consumed in order.  -> (inputs_embeds [n, D], status [2] int32 = {n_image, n_bad_ids}).
+
+    ``check_count=True`` reads the status back (one sync) and raises like the reference's index assignment would when the
+    number of <image> ids differs from the number of feature rows, or an id is outside the table."""
+    _need(input_ids, "input_ids", torch.int64, 1)
+    _need(embed_weight, "embed_weight", None, 2)
+    if embed_weight.dtype not in _EL_DTYPE:
+        raise TypeError("embed_scatter: embedding table must be bf16 or f32")
+    n, (vocab, D) = input_ids.shape[0], embed_weight.shape
+    dev = input_ids.device
+    if features is None:
+        features = torch.empty(0, D, dtype=embed_weight.dtype, device=dev)
+    if features.dtype != embed_weight.dtype:  # `.to(inputs_embeds.dtype)` of the reference
+        features = features.to(embed_weight.dtype)
+    _need(features, "features", embed_weight.dtype, 2)
+    if features.shape[1] != D:
+        raise ValueError(f"embed_scatter: feature width {features.shape[1]} != embedding width {D}")
+    o = out if out is not None else torch.empty(n, D, dtype=embed_weight.dtype, device=dev)
+    status = torch.empty(2, dtype=torch.int32, device=dev)
+    ws = torch.empty(int(_lib.load().csb_embed_scatter_workspace_bytes(n)), dtype=torch.uint8, device=dev)
+    with _on_device(input_ids):
+        check(_lib.load().csb_embed_scatter(input_ids.data_ptr(), n, int(image_token_index), embed_weight.data_ptr(), vocab,
+                                            features.data_ptr() if features.shape[0] else None, features.shape[0], D,
+                                            _EL_DTYPE[embed_weight.dtype], o.data_ptr(), status.data_ptr(), ws.data_ptr(),
+                                            ws.numel(), _stream(input_ids)), "embed_scatter")
+    if check_count:
+        n_img, n_bad = status.tolist()
+        if n_bad:
+            raise IndexError(f"embed_scatter: {n_bad} input ids outside the embedding table [0, {vocab})")
+        if n_img != features.shape[0]:
+            raise RuntimeError(f"shape mismatch: value tensor of shape [{features.shape[0]}, {D}] cannot be broadcast to "
+                               f"indexing result of shape [{n_img}, {D}]")
+    return o, status
+
+
+def seq_mean_pool(hidden: torch.Tensor, cu_seqlens: torch.Tensor, *, out: Optional[torch.Tensor] = None):
+    """``torch.mean(last_hidden_state, dim=1)`` of every sequence of a packed var-len batch (cogreasoner_chat.py:317-318, :322):
+    ``hidden`` [sum(len), Dl] bf16 / f32, ``cu_seqlens`` [n_seq + 1] int32 -> [n_seq, Dl]."""
+    _need(hidden, "hidden", None, 2)
+    if hidden.dtype not in _EL_DTYPE:
+        raise TypeError("seq_mean_pool: hidden must be bf16 or f32")
+    _need(cu_seqlens, "cu_seqlens", torch.int32, 1)
+    n_seq, Dl = cu_seqlens.shape[0] - 1, hidden.shape[1]
+    dev = hidden.device
+    o = out if out is not None else torch.empty(n_seq, Dl, dtype=hidden.dtype, device=dev)
+    ws = torch.empty(int(_lib.load().csb_seq_mean_pool_workspace_bytes(n_seq, Dl)), dtype=torch.uint8, device=dev)
+    with _on_device(hidden):
+        check(_lib.load().csb_seq_mean_pool(hidden.data_ptr(), cu_seqlens.data_ptr(), n_seq, Dl, _EL_DTYPE[hidden.dtype],
+                                            o.data_ptr(), ws.data_ptr(), ws.numel(), _stream(hidden)), "seq_mean_pool")
+    return o

@@ -245,6 +245,31 @@ CSB_API int csb_filter_ids(const int64_t* input_ids, int64_t n_ids, int64_t imag
                    int64_t* out_labels, int64_t* out_position_ids, int64_t* n_out, void* workspace,
                    size_t workspace_bytes, csb_stream_t stream);
 
+/* ---- between the two phases, and the last step of the call site ------------- */
+
+CSB_API size_t csb_embed_scatter_workspace_bytes(int64_t n_ids);
+/* cogreasoner_chat.py:303-305 (event-summary prompts) and :567-572 (final prompt), fused into one pass:
+ *     inputs_embeds = embed_tokens(input_ids).clone()
+ *     inputs_embeds[input_ids == image_token_index] = inputs_embeds[...] * 0.0 + features
+ * out[i] = embed_table[input_ids[i]] for a text id, (embed_table[image_token_index] * 0.0 + features[j]) for the
+ * j-th <image> id (both ops rounded in `dtype`, so NaN / signed-zero behaviour is the reference's).
+ * input_ids may be several prompts packed back to back (the k event prompts): features are consumed in order,
+ * which is the event-major `packed` buffer of csb_centroid_gather.
+ *   embed_table [vocab, D], features [n_features, D], out [n_ids, D], all `dtype` (CSB_BF16 / CSB_F32), 16-byte
+ *   aligned rows; status device int32[2]: {number of <image> ids, number of ids outside [0, vocab)} -- the caller
+ *   checks status[0] == n_features (the reference raises a shape error otherwise) ; rows without a source are 0. */
+CSB_API int csb_embed_scatter(const int64_t* input_ids, int64_t n_ids, int64_t image_token_index, const void* embed_table,
+                      int64_t vocab, const void* features, int64_t n_features, int64_t D, int dtype, void* out,
+                      int32_t* status, void* workspace, size_t workspace_bytes, csb_stream_t stream);
+
+CSB_API size_t csb_seq_mean_pool_workspace_bytes(int64_t n_seq, int64_t Dl);
+/* cogreasoner_chat.py:317-318 and :322: torch.mean(last_hidden_state, dim=1) of every sequence of a packed
+ * var-len batch in one launch: out[j] = mean(hidden[cu_seqlens[j] : cu_seqlens[j+1]]) with fp32 accumulation in
+ * row order, one division, one rounding to `dtype`.
+ *   hidden [cu_seqlens[n_seq], Dl] `dtype`, cu_seqlens device int32 [n_seq + 1], out [n_seq, Dl] `dtype`. */
+CSB_API int csb_seq_mean_pool(const void* hidden, const int32_t* cu_seqlens, int64_t n_seq, int64_t Dl, int dtype, void* out,
+                      void* workspace, size_t workspace_bytes, csb_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -238,6 +238,22 @@ def cosine_low_events(question_embedding: torch.Tensor, events_repr: torch.Tenso
     return cos, torch.where(cos < threshold)[0]
 
 
+def embed_scatter(input_ids: torch.Tensor, image_token_index: int, embed_weight: torch.Tensor, features: torch.Tensor):
+    """model/cogreasoner_chat.py:303-305 (event-summary prompt) and :567-572 (final prompt) --
+    ``embed_tokens(input_ids).clone()``, then the rows of the <image> ids become ``embeds * 0.0 + features`` (two ATen ops,
+    each rounding in the embedding dtype).  ``input_ids`` 1-D."""
+    inputs_embeds = torch.nn.functional.embedding(input_ids, embed_weight).clone()
+    image_selected = input_ids == image_token_index
+    inputs_embeds[image_selected] = inputs_embeds[image_selected] * 0.0 + features.to(inputs_embeds.dtype)
+    return inputs_embeds
+
+
+def event_pool(hidden_states: Sequence[torch.Tensor]) -> torch.Tensor:
+    """model/cogreasoner_chat.py:317-318 (and :322 for the question) -- ``torch.mean(last_hidden_state, dim=1)`` of every
+    ``[1, L_i, Dl]`` output, concatenated to ``[k, Dl]``."""
+    return torch.cat([torch.mean(h, dim=1) for h in hidden_states], dim=0)
+
+
 def minor_frames(assignments: torch.Tensor, low_events: torch.Tensor, representatives: List[torch.Tensor]) -> List[int]:
     """model/cogreasoner_chat.py:285, :331-333 -- frames of low-relevance events that are not
     representatives, ascending."""

@@ -209,6 +209,126 @@ def edge_cases():
     return out
 
 
+class _GoldTokenizer:
+    """Deterministic stand-in for the Qwen2 tokenizer: every "<image>" becomes the image id, every other run of characters
+    up to the next "<image>" / "," / newline becomes ONE text id (a hash of the run), so text and image ids interleave
+    like they do in the real prompts."""
+
+    def __init__(self, image_id, vocab):
+        self.image_id, self.vocab = image_id, vocab
+
+    def encode(self, text):
+        import re, zlib
+        ids = []
+        for piece in re.split(r"(<image>|,|\n)", text):
+            if not piece:
+                continue
+            ids.append(self.image_id if piece == "<image>" else 10 + zlib.crc32(piece.encode()) % (self.vocab - 20))
+        return ids
+
+    def __call__(self, text, **kw):
+        ids = self.encode(text)
+        return {"input_ids": torch.tensor([ids]), "attention_mask": torch.ones(1, len(ids), dtype=torch.long)}
+
+
+def summary_case(T=150, P=4, D=64, Dl=96, seed=77, vocab=512):
+    """Runs the reference's ``select_events_based_on_summary`` (cogreasoner_chat.py:278-333) UNMODIFIED on a recording
+    stand-in for the frozen LLM: golden vectors for the embed-scatter (:303-305), the hidden-state mean pool (:317-318,
+    :322) and the returned minor-frame list."""
+    import types
+    cc = ref_loader.chat_module()
+    M = cc.Videollama3MetaForCausalLM
+    image_id = vocab - 1
+    st = synthetic.make_stream(T, P, D, seed, C=12)
+    k = math.ceil(T / 15)
+    g = torch.Generator().manual_seed(seed)
+    embed_w = (0.5 * torch.randn(vocab, D, generator=g)).to(torch.bfloat16)
+    embed_w[3] = float("inf")  # never indexed by the tokenizer; guards nothing but documents the table is arbitrary
+    proj = (torch.randn(D, Dl, generator=g) / math.sqrt(D)).to(torch.bfloat16)
+    q_bias = (0.05 * torch.randn(Dl, generator=g)).to(torch.bfloat16)
+
+    class RecLLM(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.embed_tokens = torch.nn.Embedding(vocab, D, _weight=embed_w.clone())
+            self.rec_embeds, self.rec_hidden, self.rec_question_hidden = [], [], None
+
+        def forward(self, input_ids=None, position_ids=None, attention_mask=None, inputs_embeds=None):
+            if inputs_embeds is not None:  # an event-summary forward
+                h = torch.tanh(inputs_embeds @ proj)
+                self.rec_embeds.append(inputs_embeds[0].clone())
+                self.rec_hidden.append(h.clone())
+            else:  # the question: text hidden states pulled towards a few of the events, so that the relevance test splits them
+                pooled = torch.cat([torch.mean(x.float(), dim=1) for x in self.rec_hidden], dim=0)
+                centred = pooled - pooled.mean(dim=0, keepdim=True)
+                target = pooled.mean(dim=0) + 3.0 * centred[[0, 3, 4, 8]].mean(dim=0)
+                h = (0.2 * torch.tanh(self.embed_tokens(input_ids) @ proj + q_bias).float() + target).to(torch.bfloat16)
+                self.rec_question_hidden = h.clone()
+            return types.SimpleNamespace(last_hidden_state=h)
+
+    llm = RecLLM()
+    tok = _GoldTokenizer(image_id, vocab)
+    rec_ids = []
+
+    class RecTok:
+        def __call__(self, text, **kw):
+            out = tok(text, **kw)
+            rec_ids.append(out["input_ids"][0].clone())
+            return out
+
+    stub = types.SimpleNamespace(config=types.SimpleNamespace(image_token_index=image_id), tokenizer=RecTok(),
+                                 current_question="what is the person doing, and where?", get_model=lambda: llm)
+    cos_rec = {}
+    F_real = cc.F
+
+    class FProxy:
+        def __getattr__(self, name):
+            return getattr(F_real, name)
+
+        def cosine_similarity(self, a, b, dim=1):
+            cos_rec["question"], cos_rec["events"] = a.clone(), b.clone()
+            return F_real.cosine_similarity(a, b, dim=dim)
+
+    random.seed(1000 + seed)
+    torch.manual_seed(1000 + seed)
+    cc.F = FProxy()
+    try:
+        with torch.no_grad():
+            minor = M.select_events_based_on_summary(stub, st.features, T, st.timestamps)
+    finally:
+        cc.F = F_real
+    # the same clustering through the oracle under the same seeding: init + reseed pool for the GPU replay
+    random.seed(1000 + seed)
+    torch.manual_seed(1000 + seed)
+    info = orc.KMeansInfo()
+    _, _, assign = orc.kmeans_with_time_min_max(st.features.view(T, P, D), st.timestamps, k, info=info)
+    # oracle restatements against what the reference computed inside the method
+    events, _ = orc.event_gather(st.features.view(T, P, D), st.timestamps, assign, k)
+    assert len(llm.rec_embeds) == k and len(rec_ids) == k + 1
+    for i in range(k):
+        e = orc.embed_scatter(rec_ids[i], image_id, embed_w, events[i])
+        assert _tensor_eq(e, llm.rec_embeds[i]), f"embed_scatter event {i}"
+    pooled = orc.event_pool(llm.rec_hidden)
+    assert _tensor_eq(pooled, cos_rec["events"])
+    assert _tensor_eq(orc.event_pool([llm.rec_question_hidden])[0], cos_rec["question"])
+    reps = orc.select_additional_frames(st.features.view(T, P, D), orc.kmeans_with_time_min_max(
+        st.features.view(T, P, D), st.timestamps, k, init_indices=info.init_indices, reseed_indices=info.reseed_indices)[0], assign, 2)
+    _, low = orc.cosine_low_events(cos_rec["question"].view(1, -1), cos_rec["events"], 0.45)
+    assert orc.minor_frames(assign, low, reps) == minor
+    cu = [0]
+    for i in range(k):
+        cu.append(cu[-1] + rec_ids[i].numel())
+    return dict(
+        spec=dict(T=T, P=P, D=D, Dl=Dl, k=k, seed=seed, vocab=vocab, image_id=image_id),
+        features=st.features, timestamps=st.timestamps, embed_weight=embed_w, proj=proj, q_bias=q_bias,
+        init=info.init_indices, reseeds=info.reseed_indices, assignments=assign,
+        event_ids=torch.cat(rec_ids[:k]), cu_seqlens=torch.tensor(cu, dtype=torch.int32), question_ids=rec_ids[k],
+        inputs_embeds=torch.cat(llm.rec_embeds, dim=0), hidden=torch.cat([h[0] for h in llm.rec_hidden], dim=0),
+        question_hidden=llm.rec_question_hidden[0], events_pooled=cos_rec["events"], question_pooled=cos_rec["question"],
+        minor=minor,
+    )
+
+
 def main():
     assert ref_loader.available(), "reference not mounted"
     os.makedirs(GOLDEN_DIR, exist_ok=True)
@@ -224,6 +344,11 @@ def main():
     path = os.path.join(GOLDEN_DIR, "edge_cases.pt")
     torch.save(edges, path)
     print("edge_cases:", list(edges), f"-> {os.path.getsize(path) / 1024:.0f} KB")
+    summ = summary_case()
+    path = os.path.join(GOLDEN_DIR, "summary_case.pt")
+    torch.save(summ, path)
+    print(f"summary_case: k={summ['spec']['k']} ids={summ['event_ids'].numel()} minor={len(summ['minor'])} "
+          f"-> {os.path.getsize(path) / 1024:.0f} KB")
     print("oracle == reference on every case (bit-for-bit)")
 
 

@@ -641,3 +641,152 @@ def test_cuda_graph_replay(dev):
                     synthetic.IMAGE_TOKEN_INDEX, st.attention_mask)
     assert minor == p2.minor and torch.equal(mask.cpu(), p2.mask)
     assert_bf16_close(feats, p2.features)
+
+
+# ---- embed-scatter / hidden-state mean pool (cogreasoner_chat.py:303-305, :317-318, :322, :567-572) ------------------------
+def _summary_inputs(dev):
+    g = load_golden("summary_case")
+    s = g["spec"]
+    f3 = g["features"].view(s["T"], s["P"], s["D"])
+    events, _ = orc.event_gather(f3, g["timestamps"], g["assignments"], s["k"])
+    return g, s, torch.cat(events, dim=0)
+
+
+def test_embed_scatter_matches_reference_golden(dev):
+    """One launch over the k packed event prompts == the reference's k x (embed, mask, mul, add, index_put), bit for bit."""
+    g, s, packed = _summary_inputs(dev)
+    out, status = ops.embed_scatter(g["event_ids"].to(dev), s["image_id"], g["embed_weight"].to(dev), packed.to(dev))
+    assert status.tolist() == [packed.shape[0], 0]
+    assert torch.equal(out.cpu().view(torch.int16), g["inputs_embeds"].view(torch.int16))
+    # one prompt at a time gives the same rows
+    cu = g["cu_seqlens"].tolist()
+    n_img = 0
+    for i in (0, 3, s["k"] - 1):
+        ids = g["event_ids"][cu[i]: cu[i + 1]]
+        cnt = int((ids == s["image_id"]).sum())
+        first = int((g["event_ids"][: cu[i]] == s["image_id"]).sum())
+        o, _ = ops.embed_scatter(ids.to(dev), s["image_id"], g["embed_weight"].to(dev), packed[first: first + cnt].to(dev))
+        assert torch.equal(o.cpu().view(torch.int16), g["inputs_embeds"][cu[i]: cu[i + 1]].view(torch.int16))
+        n_img += cnt
+    assert n_img > 0
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+@pytest.mark.parametrize("n,D,vocab", [(1, 8, 3), (31, 8, 5), (33, 40, 7), (1025, 64, 50), (4099, 1152, 300), (2048, 3584, 64)])
+def test_embed_scatter_vs_oracle_ragged(dev, dtype, n, D, vocab):
+    gen = torch.Generator().manual_seed(n * 31 + D)
+    img = vocab - 1
+    ids = torch.randint(0, vocab, (n,), generator=gen)
+    ids[torch.rand(n, generator=gen) < 0.6] = img
+    w = torch.randn(vocab, D, generator=gen).to(dtype)
+    w[img, 0] = float("inf")  # inf * 0 = NaN poisons column 0 of every <image> row
+    w[img, 1::2] = -w[img, 1::2].abs()  # negative embedding: (-0) + f
+    n_img = int((ids == img).sum())
+    f = torch.randn(n_img, D, generator=gen).to(dtype)
+    if n_img:
+        f[0, :] = -0.0
+    ref = orc.embed_scatter(ids, img, w, f)
+    out, status = ops.embed_scatter(ids.to(dev), img, w.to(dev), f.to(dev))
+    assert status.tolist() == [n_img, 0]
+    iv = torch.int16 if dtype == torch.bfloat16 else torch.int32
+    o, r = out.cpu(), ref
+    nan_o, nan_r = o.isnan(), r.isnan()
+    assert torch.equal(nan_o, nan_r)
+    assert torch.equal(torch.where(nan_o, torch.zeros_like(o), o).view(iv), torch.where(nan_r, torch.zeros_like(r), r).view(iv))
+
+
+def test_embed_scatter_errors(dev):
+    w = torch.randn(10, 16).to(torch.bfloat16).to(dev)
+    ids = torch.tensor([1, 9, 9, 2, 9], device=dev)
+    f = torch.randn(2, 16).to(torch.bfloat16).to(dev)
+    with pytest.raises(RuntimeError, match="shape mismatch"):  # 3 <image> ids, 2 feature rows
+        ops.embed_scatter(ids, 9, w, f)
+    with pytest.raises(IndexError):
+        ops.embed_scatter(torch.tensor([1, 11, 9, 9], device=dev), 9, w, f)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        ops.embed_scatter(ids.cpu(), 9, w, f)
+    out, status = ops.embed_scatter(torch.tensor([1, 2, 3], device=dev), 9, w, None)  # text only
+    assert status.tolist() == [0, 0] and torch.equal(out, w[1:4])
+
+
+def test_seq_mean_pool_matches_reference_golden(dev):
+    g, s, _ = _summary_inputs(dev)
+    out = ops.seq_mean_pool(g["hidden"].to(dev), g["cu_seqlens"].to(dev))
+    assert out.shape == g["events_pooled"].shape and out.dtype == torch.bfloat16
+    assert_bf16_close(out, g["events_pooled"])
+    exact = float((out.cpu().view(torch.int16) == g["events_pooled"].view(torch.int16)).float().mean())
+    assert exact > 0.98, exact  # fp32 accumulation order differs from ATen's; almost every element rounds identically
+    q = ops.seq_mean_pool(g["question_hidden"].to(dev), torch.tensor([0, g["question_hidden"].shape[0]], dtype=torch.int32, device=dev))
+    assert_bf16_close(q[0], g["question_pooled"])
+    # the relevance decision taken from the pooled vectors is the reference's
+    _, low_ref = orc.cosine_low_events(g["question_pooled"].view(1, -1), g["events_pooled"], 0.45)
+    _, low = ops.cosine_flags(q[0].contiguous(), out, 0.45)
+    assert torch.nonzero(low.cpu()).view(-1).tolist() == low_ref.tolist()
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+@pytest.mark.parametrize("lens,Dl", [([1], 8), ([3, 1, 7], 8), ([5, 0, 9], 16), ([1000, 17, 333, 2], 96), ([2700] * 5, 3584)])
+def test_seq_mean_pool_vs_torch(dev, dtype, lens, Dl):
+    gen = torch.Generator().manual_seed(sum(lens) + Dl)
+    h = torch.randn(max(sum(lens), 1), Dl, generator=gen).to(dtype)
+    cu = [0]
+    for n_i in lens:
+        cu.append(cu[-1] + n_i)
+    out = ops.seq_mean_pool(h.to(dev), torch.tensor(cu, dtype=torch.int32, device=dev)).cpu()
+    for j, n_i in enumerate(lens):
+        if n_i == 0:
+            assert bool(out[j].isnan().all())  # torch.mean over an empty dim
+            continue
+        ref = torch.mean(h[cu[j]: cu[j + 1]].unsqueeze(0), dim=1)[0]
+        if dtype == torch.bfloat16:
+            assert_bf16_close(out[j], ref)
+        else:
+            assert torch.allclose(out[j], ref, rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("batched", [False, True])
+def test_drop_in_summary_method_matches_reference(dev, batched):
+    """The whole method (:278-333) on the B200 path with the canned LLM of the golden: the LLM must be handed bit-identical
+    inputs_embeds for every event (checked inside the stand-in), and the returned minor-frame list is the reference's."""
+    import types
+    from oracle.make_golden import _GoldTokenizer
+    g, s, _ = _summary_inputs(dev)
+    k, cu = s["k"], g["cu_seqlens"].tolist()
+    seen = []
+
+    class CannedLLM(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.embed_tokens = torch.nn.Embedding(s["vocab"], s["D"], _weight=g["embed_weight"].clone())
+
+        def forward(self, input_ids=None, position_ids=None, attention_mask=None, inputs_embeds=None):
+            if inputs_embeds is not None:
+                i = len(seen)
+                want = g["inputs_embeds"][cu[i]: cu[i + 1]]
+                assert torch.equal(inputs_embeds[0].cpu().view(torch.int16), want.view(torch.int16)), f"event {i}"
+                seen.append(i)
+                return types.SimpleNamespace(last_hidden_state=g["hidden"][cu[i]: cu[i + 1]].to(inputs_embeds.device).unsqueeze(0))
+            assert torch.equal(input_ids.cpu()[0], g["question_ids"])
+            return types.SimpleNamespace(last_hidden_state=g["question_hidden"].to(input_ids.device).unsqueeze(0))
+
+    llm = CannedLLM().to(dev)
+
+    class Model(VisualStreamCompressionMixin):
+        config = types.SimpleNamespace(image_token_index=s["image_id"])
+        tokenizer = _GoldTokenizer(s["image_id"], s["vocab"])
+        current_question = "what is the person doing, and where?"
+        csb_kmeans_kwargs = dict(init_indices=g["init"], reseed_indices=g["reseeds"])
+
+        def get_model(self):
+            return llm
+
+    m = Model()
+    if batched:
+        def forward_packed(embeds_all, cu_all):  # stands in for one flash-attn var-len forward of the frozen LLM
+            assert torch.equal(embeds_all.cpu().view(torch.int16), g["inputs_embeds"].view(torch.int16))
+            assert cu_all.tolist() == cu
+            return g["hidden"].to(embeds_all.device)
+        m.csb_batched_summary_forward = forward_packed
+    minor = m.select_events_based_on_summary(g["features"].to(dev), s["T"], g["timestamps"].to(dev))
+    assert minor == g["minor"]
+    assert batched or seen == list(range(k))
