@@ -257,17 +257,102 @@ class VisualStreamCompressionMixin:
         return mm, o_ids[:no], _cut(o_am, attention_mask), _cut(o_ps, position_ids), _cut(o_lb, labels)
 
 
+    # ------------------------------------------------------------------------------------------
+    def prepare_inputs_labels_for_multimodal(self, input_ids=None, attention_mask=None, position_ids=None, past_key_values=None,
+                                             labels=None, pixel_values=None, grid_sizes=None, merge_sizes=None, modals=None,
+                                             total_image_num=0, if_visual=True):
+        """The call site (cogreasoner_chat.py:509-585) with the same signature and return tuple.  The vision encoder,
+        ``_get_valid_visual_tokens`` and ``_maybe_truncate_visual_tokens`` are the host class's own; everything between them
+        runs on the B200 kernels, with two fusions the method-by-method drop-in cannot make: token-0 pooling of the minor
+        frames happens inside the compaction (no 249 MB clone, :551 + :562), and ``embed_tokens`` + the <image>-row
+        replacement (:567-572) is one pass."""
+        vision_encoder = self.get_vision_encoder()
+        if vision_encoder is None or pixel_values is None or input_ids.shape[1] == 1:  # :524-526 text-only
+            return input_ids, attention_mask, position_ids, past_key_values, None, labels
+        B, N = input_ids.shape  # :529-541
+        input_ids = input_ids.reshape(B * N)
+        attention_mask = attention_mask.reshape(B * N) if attention_mask is not None else None
+        position_ids = position_ids.reshape(B * N) if position_ids is not None else None
+        labels = labels.reshape(B * N) if labels is not None else None
+        img_id = self.config.image_token_index
+        mm_features = None
+        if if_visual:
+            batched_num_patches = grid_sizes.prod(dim=1).div(merge_sizes ** 2).long()  # :545
+            mm_features = self.encode_images(pixel_values, grid_sizes, merge_sizes)  # :546 (untouched encoder + projector)
+            mm_features = self._get_valid_visual_tokens(mm_features, batched_num_patches, modals)  # :547
+            assert mm_features.shape[0] % total_image_num == 0, \
+                f"mm_features.shape[0] % patch_num != 0, {mm_features.shape[0]} % {total_image_num} != 0"  # :549
+            frame_indices = self.select_events_based_on_summary(mm_features, total_image_num, self.all_timestamps)  # :550
+            n_image_ids = None
+            if position_ids is not None:
+                n_image_ids = int(input_ids.eq(img_id).sum())
+            no_truncation = position_ids is None or mm_features.shape[0] == n_image_ids  # :358-359
+            if self.config.use_token_compression and no_truncation and input_ids.is_cuda:
+                assert B == 1, "Token compression is only supported for batch_size=1"  # :561
+                feats = _frames_bf16(mm_features)
+                T = int(total_image_num)
+                P = feats.shape[0] // T
+                mask = self._get_compression_mask(pixel_values, batched_num_patches, grid_sizes, merge_sizes, modals,
+                                                  minor_frame_indices=frame_indices)  # :552
+                mask_u8 = mask.contiguous().view(torch.uint8)
+                minor_flags = torch.zeros(T, dtype=torch.uint8, device=feats.device)
+                if len(frame_indices):
+                    minor_flags[torch.tensor(list(frame_indices), dtype=torch.int64, device=feats.device)] = 1
+                # :551 + :562: x[mask] where token 0 of a minor frame is emitted as the frame's pooled mean
+                out, _, n_kept = ops.compact_tokens(feats, T, P, mask_u8, minor_flags)
+                o_ids, o_am, o_lb, o_ps, n_out = ops.filter_ids(input_ids.contiguous(), img_id, mask_u8, attention_mask, labels,
+                                                                position_ids)  # :459-474
+                nk, no = int(n_kept.item()), int(n_out.item())
+                mm_features = out[:nk] if out.dtype == mm_features.dtype else out[:nk].to(mm_features.dtype)
+                input_ids = o_ids[:no]
+                attention_mask = None if o_am is None else o_am[:no].to(attention_mask.dtype)
+                labels = None if o_lb is None else o_lb[:no].to(labels.dtype)
+                position_ids = None if o_ps is None else o_ps[:no].to(position_ids.dtype)
+            else:  # the reference's own sequence, method by method (:551-564)
+                mm_features = self.compress_unimportant_events(mm_features, mm_features.shape[0] // total_image_num,
+                                                               frame_indices)
+                compression_mask = self._get_compression_mask(pixel_values, batched_num_patches, grid_sizes, merge_sizes,
+                                                              modals, minor_frame_indices=frame_indices)
+                mm_features, compression_mask = self._maybe_truncate_visual_tokens(
+                    mm_features, compression_mask, batched_num_patches, modals, input_ids, position_ids)
+                if self.config.use_token_compression:
+                    assert B == 1, "Token compression is only supported for batch_size=1"
+                    mm_features, input_ids, attention_mask, position_ids, labels = self._compress_visual_tokens(
+                        compression_mask, mm_features, input_ids, attention_mask, position_ids, labels)
+        # 4./5. embed text tokens, replace the <image> rows (:567-572)
+        emb = self.get_model().embed_tokens
+        emb_w = getattr(emb, "weight", None)
+        fused = isinstance(emb_w, torch.Tensor) and emb_w.is_cuda and input_ids.is_cuda and emb_w.is_contiguous() \
+            and emb_w.dtype in (torch.bfloat16, torch.float32) and (mm_features is None or mm_features.shape[1] == emb_w.shape[1])
+        if fused:
+            inputs_embeds, _ = ops.embed_scatter(input_ids.contiguous(), img_id if if_visual else -1, emb_w,
+                                                 mm_features.contiguous() if if_visual else None)
+        else:
+            inputs_embeds = emb(input_ids).clone()
+            if if_visual:
+                image_selected = input_ids == img_id
+                inputs_embeds[image_selected] = inputs_embeds[image_selected] * 0.0 + mm_features.to(inputs_embeds.dtype)
+        C = inputs_embeds.shape[-1]  # :575-583
+        inputs_embeds = inputs_embeds.reshape(B, -1, C)
+        attention_mask = attention_mask.view(B, -1) if attention_mask is not None else None
+        labels = labels.view(B, -1) if labels is not None else None
+        position_ids = position_ids.view(B, -1) if position_ids is not None else None
+        return None, attention_mask, position_ids, past_key_values, inputs_embeds, labels
+
+
 _METHODS = ("select_events_based_on_summary", "compress_unimportant_events", "_get_compression_mask",
             "_compress_visual_tokens")
 
 
-def install(chat_module, *, model_class_name: str = "Videollama3MetaForCausalLM"):
-    """Rebind the hot path of an imported reference ``model.cogreasoner_chat`` module onto the B200 kernels."""
+def install(chat_module, *, model_class_name: str = "Videollama3MetaForCausalLM", call_site: bool = True):
+    """Rebind the hot path of an imported reference ``model.cogreasoner_chat`` module onto the B200 kernels.
+    ``call_site=True`` also replaces ``prepare_inputs_labels_for_multimodal`` (:509-585) by the fused version; with
+    ``False`` only the four methods and two functions it calls are swapped."""
     chat_module.kmeans_with_time_min_max = kmeans_with_time_min_max  # imported at cogreasoner_chat.py:32
     chat_module.select_additional_frames = select_additional_frames
     chat_module.create_visual_summary_prompt = create_visual_summary_prompt
     cls = getattr(chat_module, model_class_name)
-    for name in _METHODS:
+    for name in _METHODS + (("prepare_inputs_labels_for_multimodal",) if call_site else ()):
         setattr(cls, name, getattr(VisualStreamCompressionMixin, name))
     for name in ("csb_frames_per_event", "csb_min_events", "csb_n_representatives", "csb_relevance_threshold"):
         setattr(cls, name, getattr(VisualStreamCompressionMixin, name))

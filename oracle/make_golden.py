@@ -318,7 +318,54 @@ def summary_case(T=150, P=4, D=64, Dl=96, seed=77, vocab=512):
     cu = [0]
     for i in range(k):
         cu.append(cu[-1] + rec_ids[i].numel())
+
+    # ---- the call site (:509-585) unmodified: encode_images is stubbed to hand back the features, everything after it
+    #      (:545-583: valid-token filter, select -> pool -> mask -> truncate (no-op) -> compact, embed + scatter, reshape) runs
+    llm2 = RecLLM()
+
+    class Ref(M):
+        config = types.SimpleNamespace(image_token_index=image_id, use_token_compression=True)
+        tokenizer = tok
+        current_question = stub.current_question
+        all_timestamps = st.timestamps
+
+        def get_model(self):
+            return llm2
+
+        def get_vision_encoder(self):
+            return object()
+
+        def encode_images(self, pixel_values, grid_sizes, merge_sizes):
+            return st.features
+
+    head = torch.randint(10, vocab - 20, (14,), generator=g)
+    tail = torch.randint(10, vocab - 20, (23,), generator=g)
+    final_ids = torch.cat([head, torch.full((T * P,), image_id, dtype=torch.long), tail]).view(1, -1)
+    final_am = torch.ones_like(final_ids)
+    final_labels = torch.where(final_ids == image_id, torch.full_like(final_ids, -100), final_ids)
+    random.seed(1000 + seed)
+    torch.manual_seed(1000 + seed)
+    with torch.no_grad():
+        r = Ref().prepare_inputs_labels_for_multimodal(
+            input_ids=final_ids, attention_mask=final_am, position_ids=None, past_key_values=None, labels=final_labels,
+            pixel_values=st.pixel_values, grid_sizes=st.grid_sizes, merge_sizes=st.merge_sizes, modals=st.modals,
+            total_image_num=T)
+    assert r[0] is None and r[2] is None and r[3] is None
+    cs_am, cs_embeds, cs_labels = r[1], r[4], r[5]
+    # the oracle's whole-path drivers + embed_scatter reproduce it
+    p1 = orc.phase1(st.features, T, st.timestamps, cluster_num=k, init_indices=info.init_indices,
+                    reseed_indices=info.reseed_indices)
+    p2 = orc.phase2(st.features, p1, cos_rec["events"], cos_rec["question"].view(1, -1), st.pixel_values, st.grid_sizes,
+                    st.merge_sizes, st.modals, final_ids.view(-1), image_id, final_am.view(-1))
+    lab2 = orc.compress_visual_tokens(p2.mask, st.features, final_ids.view(-1), image_id, final_am.view(-1), None,
+                                      final_labels.view(-1))[4]
+    assert p2.minor == minor
+    assert _tensor_eq(orc.embed_scatter(p2.input_ids, image_id, embed_w, p2.features), cs_embeds[0])
+    assert _tensor_eq(p2.attention_mask.view(1, -1), cs_am) and _tensor_eq(lab2.view(1, -1), cs_labels)
     return dict(
+        pixel_values=st.pixel_values, grid_sizes=st.grid_sizes, merge_sizes=st.merge_sizes, modals=st.modals,
+        final_ids=final_ids, final_attention_mask=final_am, final_labels=final_labels,
+        callsite_inputs_embeds=cs_embeds, callsite_attention_mask=cs_am, callsite_labels=cs_labels,
         spec=dict(T=T, P=P, D=D, Dl=Dl, k=k, seed=seed, vocab=vocab, image_id=image_id),
         features=st.features, timestamps=st.timestamps, embed_weight=embed_w, proj=proj, q_bias=q_bias,
         init=info.init_indices, reseeds=info.reseed_indices, assignments=assign,

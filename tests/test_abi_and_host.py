@@ -116,3 +116,41 @@ def test_custom_ops_registered_and_shape_inference():
     assert out.shape == (10, 64) and kept.dtype == torch.int32 and n.shape == (1,)
     with pytest.raises((NotImplementedError, RuntimeError)):
         torch.ops.cogstream_b200.gram(torch.zeros(4, 8, dtype=torch.bfloat16))
+
+
+def test_install_rebinds_reference_names():
+    """install() swaps exactly the names the reference's hot path resolves at call time (cogreasoner_chat.py:32, :50, :93,
+    :278, :383, :434, :449 and, with call_site=True, :509)."""
+    import types
+    from cogstream_b200 import compression, kmeans_with_time
+
+    def fake_module():
+        mod = types.ModuleType("fake_chat")
+
+        class Videollama3MetaForCausalLM:
+            def select_events_based_on_summary(self): return "ref"
+            def compress_unimportant_events(self): return "ref"
+            def _get_compression_mask(self): return "ref"
+            def _compress_visual_tokens(self): return "ref"
+            def prepare_inputs_labels_for_multimodal(self): return "ref"
+            def _maybe_truncate_visual_tokens(self): return "ref"
+
+        mod.Videollama3MetaForCausalLM = Videollama3MetaForCausalLM
+        mod.kmeans_with_time_min_max = mod.select_additional_frames = mod.create_visual_summary_prompt = lambda *a: "ref"
+        return mod
+
+    mod = fake_module()
+    cls = compression.install(mod)
+    assert mod.kmeans_with_time_min_max is kmeans_with_time.kmeans_with_time_min_max
+    assert mod.select_additional_frames is compression.select_additional_frames
+    for name in ("select_events_based_on_summary", "compress_unimportant_events", "_get_compression_mask",
+                 "_compress_visual_tokens", "prepare_inputs_labels_for_multimodal"):
+        assert getattr(cls, name) is getattr(compression.VisualStreamCompressionMixin, name)
+    assert cls._maybe_truncate_visual_tokens(None) == "ref"  # not on the path: untouched
+    mod2 = fake_module()
+    cls2 = compression.install(mod2, call_site=False)
+    assert cls2.prepare_inputs_labels_for_multimodal(None) == "ref"
+    import inspect
+    sig = inspect.signature(compression.VisualStreamCompressionMixin.prepare_inputs_labels_for_multimodal)
+    assert list(sig.parameters) == ["self", "input_ids", "attention_mask", "position_ids", "past_key_values", "labels",
+                                    "pixel_values", "grid_sizes", "merge_sizes", "modals", "total_image_num", "if_visual"]

@@ -790,3 +790,67 @@ def test_drop_in_summary_method_matches_reference(dev, batched):
     minor = m.select_events_based_on_summary(g["features"].to(dev), s["T"], g["timestamps"].to(dev))
     assert minor == g["minor"]
     assert batched or seen == list(range(k))
+
+
+@pytest.mark.parametrize("fused_embed", [True, False])
+def test_drop_in_call_site_matches_reference(dev, fused_embed):
+    """prepare_inputs_labels_for_multimodal (:509-585): the golden holds what the UNMODIFIED reference method returned on
+    the same inputs (encode_images stubbed to hand back the features); inputs_embeds, attention mask and labels must match
+    bit for bit."""
+    import types
+    from oracle.make_golden import _GoldTokenizer
+    g, s, _ = _summary_inputs(dev)
+    cu = g["cu_seqlens"].tolist()
+    calls = []
+
+    class CannedLLM(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.embed_tokens = torch.nn.Embedding(s["vocab"], s["D"], _weight=g["embed_weight"].clone())
+            if not fused_embed:  # a wrapped embedding without a plain .weight: the method falls back to the module call
+                inner = self.embed_tokens
+                self.embed_tokens = torch.nn.Sequential(inner)
+
+        def forward(self, input_ids=None, position_ids=None, attention_mask=None, inputs_embeds=None):
+            if inputs_embeds is not None:
+                i = len(calls)
+                calls.append(i)
+                return types.SimpleNamespace(last_hidden_state=g["hidden"][cu[i]: cu[i + 1]].to(inputs_embeds.device).unsqueeze(0))
+            return types.SimpleNamespace(last_hidden_state=g["question_hidden"].to(input_ids.device).unsqueeze(0))
+
+    llm = CannedLLM().to(dev)
+
+    class Model(VisualStreamCompressionMixin):
+        config = types.SimpleNamespace(image_token_index=s["image_id"], use_token_compression=True)
+        tokenizer = _GoldTokenizer(s["image_id"], s["vocab"])
+        current_question = "what is the person doing, and where?"
+        csb_kmeans_kwargs = dict(init_indices=g["init"], reseed_indices=g["reseeds"])
+        all_timestamps = g["timestamps"].to(dev)
+
+        def get_model(self):
+            return llm
+
+        def get_vision_encoder(self):
+            return object()
+
+        def encode_images(self, pixel_values, grid_sizes, merge_sizes):
+            return g["features"].to(dev)
+
+        def _get_valid_visual_tokens(self, mm_features, batched_num_patches, modals):  # :336-347, all items are videos here
+            assert all(m != "text" for m in modals)
+            return mm_features
+
+    m = Model()
+    r = m.prepare_inputs_labels_for_multimodal(
+        input_ids=g["final_ids"].to(dev), attention_mask=g["final_attention_mask"].to(dev), position_ids=None,
+        past_key_values=None, labels=g["final_labels"].to(dev), pixel_values=g["pixel_values"].to(dev),
+        grid_sizes=g["grid_sizes"].to(dev), merge_sizes=g["merge_sizes"].to(dev), modals=g["modals"], total_image_num=s["T"])
+    assert r[0] is None and r[2] is None and r[3] is None
+    assert len(calls) == s["k"]
+    assert r[4].shape == g["callsite_inputs_embeds"].shape
+    assert torch.equal(r[4].cpu().view(torch.int16), g["callsite_inputs_embeds"].view(torch.int16))
+    assert torch.equal(r[1].cpu(), g["callsite_attention_mask"]) and torch.equal(r[5].cpu(), g["callsite_labels"])
+    # text-only shortcut (:524-526) hands everything back untouched
+    ids1 = g["final_ids"][:, :1].to(dev)
+    r1 = m.prepare_inputs_labels_for_multimodal(input_ids=ids1, pixel_values=g["pixel_values"].to(dev))
+    assert r1[0] is ids1 and r1[4] is None
