@@ -351,6 +351,7 @@ def run_ours(args):
     if rank == 0:
         stages = _stage_times(sc, d, ev_d, q_d, reps=max(3, min(args.steps, 10)))
         roofline = _roofline(stages, sc, d, ms_step=ms_step, ms_single=ms_single / args.steps)
+        roofline["neighbour_ops"] = _neighbour_ops(sc, d)
         if world == 1 and not args.no_cpu_baseline:
             cpu, _ = cpu_baseline(budget_s=20.0)
     if world > 1:
@@ -421,6 +422,48 @@ def _stage_times(sc, d, ev_d, q_d, reps=5):
         e1.record()
         torch.cuda.synchronize()
         out[name] = round(e0.elapsed_time(e1) / reps, 5)
+    return out
+
+
+def _neighbour_ops(sc, d, reps=5):
+    """The two ops on either side of the timed path (NOT inside `value`): the fused
+    embed_tokens + <image>-row replacement on the compacted prompt, and the var-len mean pool of the k event-summary hidden
+    states (k prompts of ~T*P/k image tokens, LLM width 3584).  HBM-bound; reported against the measured copy peak."""
+    from cogstream_b200 import ops
+    pk = _peaks()
+    dev = d.features.device
+    out = {}
+
+    def timed(fn):
+        fn(); torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record(); torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+
+    D = sc.D
+    n_kept = int(sc.n_kept.item())
+    vocab = 8192
+    table = torch.randn(vocab, D, device=dev).to(torch.bfloat16)
+    ids = torch.cat([torch.randint(0, vocab - 1, (14,), device=dev), torch.full((n_kept,), vocab - 1, device=dev, dtype=torch.int64),
+                     torch.randint(0, vocab - 1, (23,), device=dev)])
+    feats = sc.out[:n_kept]
+    o = torch.empty(ids.numel(), D, dtype=torch.bfloat16, device=dev)
+    ms = timed(lambda: ops.embed_scatter(ids, vocab - 1, table, feats, out=o, check_count=False))
+    b = 2 * 2 * ids.numel() * D
+    out["embed_scatter"] = dict(ms=round(ms, 5), rows=int(ids.numel()), D=D, algorithmic_bytes=b, gbs=round(b / ms / 1e6, 1),
+                                frac=round(b / ms / 1e6 / pk["hbm_gbs"], 3))
+    Dl, k = WORKLOAD["Dl"], sc.k
+    lens = [sc.T * sc.P // k + 40] * k
+    cu = torch.tensor([0] + list(torch.tensor(lens).cumsum(0)), dtype=torch.int32, device=dev)
+    hidden = torch.randn(sum(lens), Dl, device=dev, dtype=torch.bfloat16)
+    po = torch.empty(k, Dl, dtype=torch.bfloat16, device=dev)
+    ms = timed(lambda: ops.seq_mean_pool(hidden, cu, out=po))
+    b = 2 * sum(lens) * Dl
+    out["seq_mean_pool"] = dict(ms=round(ms, 5), rows=int(sum(lens)), Dl=Dl, algorithmic_bytes=b, gbs=round(b / ms / 1e6, 1),
+                                frac=round(b / ms / 1e6 / pk["hbm_gbs"], 3))
     return out
 
 
