@@ -33,6 +33,8 @@ struct GramUnit {
   int tile_id[kMaxMma];       // upper-triangular tile id (for the partial buffer)
   int tile_rows[kMaxMma];     // valid rows / columns of the stored tile (the drain skips the rest)
   int tile_cols[kMaxMma];
+  int tile_ablk[kMaxMma];     // row block of the accumulator rows (A) and of its columns (B): used when the drain writes G itself
+  int tile_bblk[kMaxMma];
   // MMA ops: D[128 x n] (+)= A(slot a)[128 x 64] * B(slots b, b+1 ...)[n x 64]^T; n <= 256 covers one or two adjacent B slots,
   // i.e. one or two output tiles starting at TMEM tile t0.  An N=256 MMA runs at the tensor-pipe floor (64 cycles per
   // 128x128x16), two N=128 MMAs take 84 each: shared-memory operand bandwidth (scripts/ubench/mma_rate.cu).
@@ -179,6 +181,8 @@ static void plan_units(int nb, int b0, int64_t T, GramUnit* units, int* n_units,
         u.tile_id[u.n_tiles] = id;
         u.tile_rows[u.n_tiles] = block_rows(a);
         u.tile_cols[u.n_tiles] = block_rows(b);
+        u.tile_ablk[u.n_tiles] = a;
+        u.tile_bblk[u.n_tiles] = b;
         if (a > b && flips && id < 192) flips->w[id >> 6] |= 1ull << (id & 63);
         ++u.n_tiles;
         // MMA N: full 128 for a leading block, the valid rows rounded up to 16 for the trailing one
@@ -252,21 +256,27 @@ static void plan_units(int nb, int b0, int64_t T, GramUnit* units, int* n_units,
       emit(uo, nu);
     }
   } else {
-    // 2x2 super-blocks: rows {2I, 2I+1} x columns {2J, 2J+1}; each row block against its (one or two) column blocks
+    // 2x2 super-blocks: rows {2I, 2I+1} x columns {2J, 2J+1}; each row block against its (one or two) column blocks.
+    // Units are emitted macro-tile by macro-tile (12 x 12 super-blocks = 144 units ~ one wave of CTAs): the CTAs that run
+    // concurrently then share 24 + 24 row blocks instead of ~300, so a block's K chunk is fetched from HBM once per wave and
+    // served to its 12 users out of L2 (X does not fit in L2 for long streams: 531 MB at config 4).
     const int ns = (nb + 1) / 2;
-    for (int I = 0; I < ns; ++I)
-      for (int J = I; J < ns; ++J) {
-        PlanOp uo[kMaxMma];
-        int nu = 0;
-        for (int bi = 2 * I; bi < 2 * I + 2 && bi < nb; ++bi) {
-          PlanOp o;
-          o.a = bi; o.nbk = 0; o.b[0] = o.b[1] = -1;
-          for (int bj = 2 * J; bj < 2 * J + 2 && bj < nb; ++bj)
-            if (bi <= bj && bj >= b0) o.b[o.nbk++] = bj;
-          if (o.nbk) uo[nu++] = o;
-        }
-        if (nu) emit(uo, nu);
-      }
+    constexpr int kMacro = 12;
+    for (int MI = 0; MI < ns; MI += kMacro)
+      for (int MJ = MI; MJ < ns; MJ += kMacro)
+        for (int I = MI; I < MI + kMacro && I < ns; ++I)
+          for (int J = (MJ > I ? MJ : I); J < MJ + kMacro && J < ns; ++J) {
+            PlanOp uo[kMaxMma];
+            int nu = 0;
+            for (int bi = 2 * I; bi < 2 * I + 2 && bi < nb; ++bi) {
+              PlanOp o;
+              o.a = bi; o.nbk = 0; o.b[0] = o.b[1] = -1;
+              for (int bj = 2 * J; bj < 2 * J + 2 && bj < nb; ++bj)
+                if (bi <= bj && bj >= b0) o.b[o.nbk++] = bj;
+              if (o.nbk) uo[nu++] = o;
+            }
+            if (nu) emit(uo, nu);
+          }
   }
   *n_units = n;
   if (max_slots) *max_slots = ms;
@@ -510,7 +520,8 @@ __global__ void __launch_bounds__(160, 1) gram_tc_kernel(const __grid_constant__
                                                          const GramUnit* __restrict__ units, int n_tiles, int n_kr,
                                                          int n_chunks, int kStages, int stage_bytes,
                                                          float* __restrict__ partial, int dbg,
-                                                         unsigned long long* __restrict__ tl) {
+                                                         unsigned long long* __restrict__ tl, double* __restrict__ Gout,
+                                                         int64_t ldg) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // stage buffers first (1024-byte aligned for SWIZZLE_128B), control block after
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -663,14 +674,39 @@ __global__ void __launch_bounds__(160, 1) gram_tc_kernel(const __grid_constant__
           ptx::tmem_ld_wait();
           if (!row_ok) continue;
           float* o = out + (int64_t)(cb * 32) * kTile;
+          float val[32];
           if (seg == 0) {
 #pragma unroll
+            for (int j = 0; j < 32; ++j) val[j] = __uint_as_float(r[j]);
+          } else {
+            // all 32 loads first (independent L2 round trips), then the adds: a load -> add -> store chain per element
+            // serialises 32 round trips per column group (measured: 230 us per drain at config 4)
+            float prev[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) prev[j] = (cb * 32 + j < ncols) ? __ldcg(o + j * kTile) : 0.f;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) val[j] = __fadd_rn(prev[j], __uint_as_float(r[j]));
+          }
+          if (Gout && seg == nseg - 1) {
+            // single K range (long streams): the last drain writes G itself -- both triangles -- and no reduce kernel runs.
+            // Same value the reduce kernel would produce: (double) of the fp32 segment sum.
+            const int64_t ga = (int64_t)unit.tile_ablk[t] * kTile + row;
+            const int64_t gb0 = (int64_t)unit.tile_bblk[t] * kTile + cb * 32;
+            const bool diag = unit.tile_ablk[t] == unit.tile_bblk[t];
+            double* grow = Gout + ga * ldg + gb0;  // 32 consecutive doubles of this thread's row
+#pragma unroll
             for (int j = 0; j < 32; ++j)
-              if (cb * 32 + j < ncols) o[j * kTile] = __uint_as_float(r[j]);
+              if (cb * 32 + j < ncols) grow[j] = (double)val[j];
+            if (!diag) {
+              double* gcol = Gout + gb0 * ldg + ga;  // mirror: for a fixed column the warp writes 32 consecutive doubles
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (cb * 32 + j < ncols) gcol[(int64_t)j * ldg] = (double)val[j];
+            }
           } else {
 #pragma unroll
             for (int j = 0; j < 32; ++j)
-              if (cb * 32 + j < ncols) o[j * kTile] = __fadd_rn(o[j * kTile], __uint_as_float(r[j]));
+              if (cb * 32 + j < ncols) o[j * kTile] = val[j];
           }
         }
       }
@@ -800,11 +836,14 @@ int csb_gram_extend(const void* x, int64_t T_old, int64_t T, int64_t K, double* 
     const size_t tl_bytes = (size_t)p.n_units * n_kr * 8 * sizeof(unsigned long long);
     if (((impl >> 4) & 8) && workspace_bytes >= gram_ws_bytes(p) + tl_bytes)
       tl = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(workspace) + gram_ws_bytes(p));
+    // one K range per tile (more units than SMs): the kernel's last drain writes G directly, no reduce pass
+    const bool direct = n_kr == 1 && !((impl >> 4) & 32);  // impl bit 9: force the partial + reduce path (validation)
     if (!((impl >> 4) & 16))  // profiling aid: impl bit 8 = reduce kernel only
       gram_tc_kernel<<<grid, 160, smem_bytes, s>>>(map, table, d_units, p.n_tiles, n_kr, p.n_chunks, p.n_stages, stage_bytes, partial,
-                                                     impl >> 4, tl);
+                                                     impl >> 4, tl, direct ? G : nullptr, ldg);
     int st = check_launch("gram_tc");
     if (st) return st;
+    if (direct) return CSB_OK;
   } else {
     set_error("gram: unknown impl %d", impl);
     return CSB_ERR_ARG;

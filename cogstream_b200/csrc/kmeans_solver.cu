@@ -322,25 +322,50 @@ __device__ void rebuild_members_smem(const SolverArgs& a, const MemberSmem& m, i
   *used_io = used;
 }
 
-// S[i][j] = sum_{m in M_j} G[i][m] for the listed columns j (all CTAs; column fastest so the stores coalesce)
+// S[i][j] = sum_{m in M_j} G[i][m] for the listed columns j (all CTAs; column fastest so the stores coalesce).
+// A thread works on kSE entries at once, 4 Gram loads each in flight (the loop is pure L2 / HBM latency: member addresses come
+// from shared memory, 8 warps per SM); every entry is still summed in ascending member order.
+constexpr int kSE = 4;
 __device__ void compute_S(const SolverArgs& a, const int* s_offs, const int* s_memb, const int* cols, int ncols, double* S) {
   const int T = a.T, k = a.k;
   const int64_t total = (int64_t)T * ncols;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += stride) {
-    const int i = (int)(idx / ncols);
-    const int j = cols[(int)(idx - (int64_t)i * ncols)];
-    const int beg = s_offs[j], end = s_offs[j + 1];
-    const double* g = a.G + (int64_t)i * a.ldg;
-    double s = 0.0;
-    int e = beg;
-    for (; e + 4 <= end; e += 4) {
-      const double g0 = __ldg(g + s_memb[e]), g1 = __ldg(g + s_memb[e + 1]), g2 = __ldg(g + s_memb[e + 2]),
-                   g3 = __ldg(g + s_memb[e + 3]);
-      s += g0; s += g1; s += g2; s += g3;
+  for (int64_t idx0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx0 < total; idx0 += kSE * stride) {
+    const double* g[kSE];
+    int beg[kSE], len[kSE];
+    int64_t out[kSE];
+    double s[kSE];
+    int maxlen = 0;
+#pragma unroll
+    for (int u = 0; u < kSE; ++u) {
+      const int64_t idx = idx0 + u * stride;
+      s[u] = 0.0;
+      len[u] = 0; beg[u] = 0; g[u] = a.G; out[u] = -1;
+      if (idx < total) {
+        const int i = (int)(idx / ncols);
+        const int j = cols[(int)(idx - (int64_t)i * ncols)];
+        beg[u] = s_offs[j];
+        len[u] = s_offs[j + 1] - beg[u];
+        g[u] = a.G + (int64_t)i * a.ldg;
+        out[u] = (int64_t)i * k + j;
+        maxlen = max(maxlen, len[u]);
+      }
     }
-    for (; e < end; ++e) s += __ldg(g + s_memb[e]);
-    S[(int64_t)i * k + j] = s;
+    for (int e = 0; e < maxlen; e += 4) {
+      double v[kSE][4];
+#pragma unroll
+      for (int u = 0; u < kSE; ++u)
+#pragma unroll
+        for (int w = 0; w < 4; ++w) v[u][w] = (e + w < len[u]) ? __ldg(g[u] + s_memb[beg[u] + e + w]) : 0.0;
+#pragma unroll
+      for (int u = 0; u < kSE; ++u)
+#pragma unroll
+        for (int w = 0; w < 4; ++w)
+          if (e + w < len[u]) s[u] += v[u][w];
+    }
+#pragma unroll
+    for (int u = 0; u < kSE; ++u)
+      if (out[u] >= 0) S[out[u]] = s[u];
   }
 }
 
@@ -374,6 +399,172 @@ __global__ void __launch_bounds__(kInitThreads) kmeanspp_kernel(SolverArgs a) {
     st->degenerate_rounds = n_deg;
     st->n_noise_used = n_noise;
     *a.used = used;  // pool entries consumed by degenerate rounds
+  }
+  mark(a, 2);
+}
+
+// ---- k-means++ over many CTAs (long streams: T > kGridInitMinT) ---------------------------------------------------------
+// The single-CTA kernel above spends ~17 us per round at T = 14,400 (one SM pulls a 115 KB Gram row and a 58 KB noise row
+// and reduces 14,400 candidates), 16.5 ms for the 959 rounds of BASELINE config 4.  Here every thread owns <= kGridInitU
+// frames (nearest distance and diagonal in registers), a round is: update with row c + per-CTA partial sums of nearest^2
+// -> grid barrier -> total (CTA order, identical in every CTA) -> scores + per-CTA argmax -> grid barrier -> global argmax
+// (score, then lowest index).  Same arithmetic per frame as kmeanspp_block; only the (deterministic) order of the fp32 sum
+// differs, which is a common factor of all scores.  Cooperative launch (co-residency for the software barrier).
+constexpr int kGridInitThreads = 512;
+constexpr int kGridInitU = 4;
+constexpr int kGridInitMinT = 2048;
+
+struct GridInitBufs {
+  unsigned* barrier;  // zeroed before launch
+  float* part;        // [2][nb]
+  float* cand_v;      // [2][nb]
+  int* cand_i;        // [2][nb]
+};
+
+__global__ void __launch_bounds__(kGridInitThreads) kmeanspp_grid_kernel(SolverArgs a, GridInitBufs b) {
+  __shared__ float s_wv[kGridInitThreads / 32];
+  __shared__ int s_wi[kGridInitThreads / 32];
+  __shared__ float s_ws[kGridInitThreads / 32];
+  __shared__ int s_c;
+  __shared__ float s_sum;
+  const int T = a.T, k = a.k;
+  const unsigned nb = gridDim.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  constexpr int NW = kGridInitThreads / 32;
+  csb_kmeans_status* st = a.status;
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    st->iterations = 0; st->converged = 0; st->n_reseed_used = 0; st->degenerate_rounds = 0;
+    st->reseed_overflow = 0; st->n_noise_used = 0; st->min_margin = __int_as_float(0x7f800000); st->last_shift = 0.f;
+  }
+  mark(a, 1);
+  // frames of this thread: base + u * kGridInitThreads, u < kGridInitU, inside the CTA's contiguous slice
+  const int per_cta = (T + (int)nb - 1) / (int)nb;
+  const int cta0 = blockIdx.x * per_cta, cta1 = min(T, cta0 + per_cta);
+  int fi[kGridInitU];
+  float near[kGridInitU];
+  double dg[kGridInitU];
+#pragma unroll
+  for (int u = 0; u < kGridInitU; ++u) {
+    const int i = cta0 + threadIdx.x + u * kGridInitThreads;
+    fi[u] = i < cta1 ? i : -1;
+    near[u] = __int_as_float(0x7f800000);
+    dg[u] = 0.0;
+    if (fi[u] >= 0) {
+      dg[u] = a.G[(int64_t)i * a.ldg + i];
+      a.diag[i] = dg[u];
+    }
+  }
+  unsigned bar = 0;
+  int noise_row = 0, degenerate = 0, used = 0;
+  int c = 0;
+  for (int m = 0; m < k; ++m) {
+    if (m < a.n_init_given) {
+      c = (int)a.init_indices[m];
+    } else {
+      // ---- total of nearest^2 (partials of the previous update pass), identical in every CTA ----
+      // (warp 0: one L2 round trip for all partials, then a fixed shuffle tree -- the same bits in every CTA)
+      if (warp == 0) {
+        const float* part = b.part + ((m - 1) & 1) * nb;
+        float v = 0.f;
+        for (unsigned q = lane; q < nb; q += 32) v += __ldcg(part + q);
+        v = warp_sum(v);
+        if (lane == 0) s_sum = v;
+      }
+      __syncthreads();
+      const float sum = s_sum;
+      if (sum == 0.f) {  // :55-57 every frame coincides with a centre: host-drawn index
+        ++degenerate;
+        c = 0;
+        if (used < a.n_reseed_pool) c = (int)a.reseed_pool[used];
+        else if (blockIdx.x == 0 && threadIdx.x == 0) st->reseed_overflow = 1;
+        ++used;
+      } else {
+        const float* noise = a.exp_noise + (int64_t)noise_row * T;
+        ++noise_row;
+        float best = -1.f;
+        int besti = 0x7fffffff;
+#pragma unroll
+        for (int u = 0; u < kGridInitU; ++u) {
+          if (fi[u] >= 0) {
+            const float p = __fdiv_rn(__fmul_rn(near[u], near[u]), sum);  // :59
+            const float sc = __fdiv_rn(p, __ldg(noise + fi[u]));          // multinomial: argmax(p / Exp(1)), first max
+            if (sc > best) { best = sc; besti = fi[u]; }                  // fi ascending in u: first max kept
+          }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+          const int oi = __shfl_xor_sync(0xffffffffu, besti, o);
+          if (ov > best || (ov == best && oi < besti)) { best = ov; besti = oi; }
+        }
+        if (lane == 0) { s_wv[warp] = best; s_wi[warp] = besti; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+          best = s_wv[0]; besti = s_wi[0];
+          for (int w = 1; w < NW; ++w) {
+            const float ov = s_wv[w];
+            const int oi = s_wi[w];
+            if (ov > best || (ov == best && oi < besti)) { best = ov; besti = oi; }
+          }
+          b.cand_v[(m & 1) * nb + blockIdx.x] = best;
+          b.cand_i[(m & 1) * nb + blockIdx.x] = besti;
+        }
+        grid_sync(b.barrier, bar, nb);
+        if (warp == 0) {
+          float gb = -1.f;
+          int gi = 0x7fffffff;
+          for (unsigned q = lane; q < nb; q += 32) {
+            const float ov = __ldcg(b.cand_v + (m & 1) * nb + q);
+            const int oi = __ldcg(b.cand_i + (m & 1) * nb + q);
+            if (ov > gb || (ov == gb && oi < gi)) { gb = ov; gi = oi; }
+          }
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) {
+            const float ov = __shfl_xor_sync(0xffffffffu, gb, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, gi, o);
+            if (ov > gb || (ov == gb && oi < gi)) { gb = ov; gi = oi; }
+          }
+          if (lane == 0) s_c = gi;
+        }
+        __syncthreads();
+        c = s_c;
+      }
+      if (blockIdx.x == 0 && threadIdx.x == 0) a.init_indices[m] = c;
+    }
+    if (m + 1 < k) {
+      // ---- update the nearest distances with centre c; per-CTA partial of sum nearest^2 (:45-53) ----
+      const double gcc = __ldg(a.G + (int64_t)c * a.ldg + c);
+      const double* gc = a.G + (int64_t)c * a.ldg;
+      double g[kGridInitU];
+#pragma unroll
+      for (int u = 0; u < kGridInitU; ++u) g[u] = fi[u] >= 0 ? __ldg(gc + fi[u]) : 0.0;
+      float part = 0.f;
+#pragma unroll
+      for (int u = 0; u < kGridInitU; ++u) {
+        if (fi[u] >= 0) {
+          const double d2 = dg[u] + gcc - 2.0 * g[u];
+          const float d = (float)sqrt(d2 > 0.0 ? d2 : 0.0);
+          near[u] = fminf(near[u], d);
+          part += __fmul_rn(near[u], near[u]);  // :53
+        }
+      }
+      if (m + 1 >= a.n_init_given) {  // the next round samples: it needs the total
+        part = warp_sum(part);
+        if (lane == 0) s_ws[warp] = part;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+          float t = s_ws[0];
+          for (int w = 1; w < NW; ++w) t += s_ws[w];
+          b.part[(m & 1) * nb + blockIdx.x] = t;
+        }
+        grid_sync(b.barrier, bar, nb);
+      }
+    }
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    st->degenerate_rounds = degenerate;
+    st->n_noise_used = noise_row;
+    *a.used = used;
   }
   mark(a, 2);
 }
@@ -736,8 +927,25 @@ int csb_kmeans_solve(const double* G, const void* timestamps, const csb_kmeans_p
   int dev = 0, sms = kNumSMs;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  // k-means++ (or just the diagonal / status reset when every centre is prescribed): one CTA
-  {
+  // k-means++ (or just the diagonal / status reset when every centre is prescribed): one CTA, or a cooperative grid for
+  // long streams (CSB_INIT_GRID=0/1 forces either: profiling aid)
+  bool grid_init = T > kGridInitMinT && p->n_init_given < k;
+  if (const char* o = getenv("CSB_INIT_GRID")) grid_init = atoi(o) != 0 && T <= (int64_t)sms * kGridInitThreads * kGridInitU;
+  if (grid_init) {
+    int64_t nbi = (T + kGridInitThreads - 1) / kGridInitThreads;
+    if (nbi > sms) nbi = sms;
+    GridInitBufs gb;
+    gb.barrier = reinterpret_cast<unsigned*>(w + 64);
+    // scratch inside S[0]: the Lloyd kernel (re)builds S[0] from scratch after the init
+    char* sc0 = reinterpret_cast<char*>(a.S[0]);
+    gb.part = reinterpret_cast<float*>(sc0);
+    gb.cand_v = reinterpret_cast<float*>(sc0 + align_up(sizeof(float) * 2 * nbi, 256));
+    gb.cand_i = reinterpret_cast<int*>(sc0 + 2 * align_up(sizeof(float) * 2 * nbi, 256));
+    void* iargs[] = {&a, &gb};
+    e = cudaLaunchCooperativeKernel((const void*)kmeanspp_grid_kernel, dim3((unsigned)nbi), dim3(kGridInitThreads), iargs, 0, s);
+    if (e != cudaSuccess) { set_error("kmeans_solve: init launch: %s", cudaGetErrorString(e)); return CSB_ERR_CUDA; }
+    count_launch(1);
+  } else {
     // few warps = cheap block barriers: the rounds are a dependent chain, each about (frames / threads) elements of work
     int nt = T <= 1024 ? 256 : (T <= 4096 ? 512 : 1024);
     if (const char* o = getenv("CSB_INIT_THREADS")) nt = atoi(o);

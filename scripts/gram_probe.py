@@ -2,7 +2,7 @@ import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT)
 import torch
 from cogstream_b200 import ops, synthetic
-T, P, D = 600, 180, 1152
+T, P, D = int(os.environ.get('T', 600)), int(os.environ.get('P', 180)), 1152
 x = synthetic.make_features(T, P, D, 0)[0].view(T, -1).cuda()
 G = torch.empty(T, T, dtype=torch.float64, device="cuda")
 ws = torch.empty(ops.gram_workspace_bytes(T, P * D), dtype=torch.uint8, device="cuda")
@@ -17,7 +17,7 @@ for name, impl in [("full", 0), ("no-mma (loads only)", 16), ("no-tma (mma only)
 
 # per-CTA time marks (impl bit 7): where the kernel time goes
 import numpy as np
-n_units, n_kr = 4, 37
+n_units, n_kr = int(os.environ.get('NU', 4)), int(os.environ.get('NKR', 37))
 wsz = ops.gram_workspace_bytes(T, P * D)
 ws2 = torch.zeros(wsz + n_units * n_kr * 64, dtype=torch.uint8, device="cuda")
 for _ in range(3): ops.gram(x, impl=128, out=G, workspace=ws2)
@@ -29,8 +29,11 @@ print("marks relative to the first CTA's entry, us: min / median / max over the 
 for i, n in enumerate(names):
     v = (m[:, i] - t0) / 1e3
     print(f"  {n:18s} {v.min():7.2f} {np.median(v):7.2f} {v.max():7.2f}")
-for u in range(n_units):
+for u in range(min(n_units, 4)):
     rows = m[u::n_units] if True else None
     v = (rows[:, 4] - rows[:, 2]) / 1e3
     print(f"  unit {u}: mainloop (first operands -> accum complete) median {np.median(v):.2f} us, max {v.max():.2f}")
+life = (m[:, 5] - m[:, 0]) / 1e3
+main = (m[:, 3] - m[:, 2]) / 1e3
+print(f"  CTA lifetime median {np.median(life):.1f} us (min {life.min():.1f}, max {life.max():.1f}); first operands -> last MMA issued median {np.median(main):.1f} us; drain after last accum median {np.median((m[:,5]-m[:,4])/1e3):.1f} us")
 print("  distinct SMs:", len(set(m[:, 7].tolist())))

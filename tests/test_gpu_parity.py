@@ -72,6 +72,24 @@ def test_gram_matches_fp64(dev, T, K, impl):
     assert torch.equal(G, G.T)
 
 
+@pytest.mark.parametrize("T,K", [(3100, 256), (3000, 12352), (4099, 6208)])
+def test_gram_long_stream_direct_write(dev, T, K):
+    """More units than SMs -> one K range per tile: the kernel's last drain writes G (both triangles) itself.  Same bits as
+    the partial + reduce path (impl bit 9 forces it), incl. K long enough for several accumulator segments (read-add-write
+    drains) and T % 128 != 0."""
+    g = torch.Generator().manual_seed(T + K)
+    x = (torch.randn(T, K, generator=g) + 0.5).to(torch.bfloat16).to(dev)
+    G = ops.gram(x, impl=0)
+    G2 = ops.gram(x, impl=512)
+    assert torch.equal(G, G2)
+    assert torch.equal(G, G.T)
+    idx = torch.randperm(T, generator=g)[:96].to(dev)
+    sub = x[idx].double()
+    ref = sub @ sub.T
+    assert float((G[idx][:, idx] - ref).abs().max() / ref.diagonal().abs().max()) < 4e-5  # tensor-core truncation drift
+    assert torch.equal(ops.gram(x, impl=0), G)
+
+
 def test_gram_tensor_core_equals_cuda_core_on_structured_data(dev):
     st = synthetic.make_stream(600, 8, 1152, seed=11, C=4)
     x = st.features.view(600, -1).to(dev)
@@ -854,3 +872,35 @@ def test_drop_in_call_site_matches_reference(dev, fused_embed):
     ids1 = g["final_ids"][:, :1].to(dev)
     r1 = m.prepare_inputs_labels_for_multimodal(input_ids=ids1, pixel_values=g["pixel_values"].to(dev))
     assert r1[0] is ids1 and r1[4] is None
+
+
+@pytest.mark.parametrize("T,P,D,seed", [(2300, 2, 32, 0), (4100, 1, 64, 1)])
+def test_kmeanspp_long_stream_grid_init(dev, monkeypatch, T, P, D, seed):
+    """Long streams (T > 2048) run k-means++ on a cooperative grid; the centres, assignments and iteration count equal the
+    single-CTA kernel's and the CPU oracle's for the same injected Exp(1) noise."""
+    import os
+    k = math.ceil(T / 15)
+    feats, _ = synthetic.make_features(T, P, D, seed)
+    ts = torch.arange(T, dtype=torch.float64) / 2.0
+    g = torch.Generator().manual_seed(seed + 5)
+    noise = torch.empty(k - 1, T).exponential_(1, generator=g)
+    first = int(torch.randint(0, T, (1,), generator=g))
+    pool = [int(v) for v in torch.randint(0, T, (64,), generator=g)]
+    f3 = feats.view(T, P, D)
+    res = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("CSB_INIT_GRID", mode)
+        _, _, assign, info = kmeans_with_time_min_max(f3.to(dev), ts.to(dev), k, first_index=first, exp_noise=noise,
+                                                      reseed_indices=pool, return_info=True)
+        res[mode] = (info.init_indices.tolist(), assign.cpu(), info.iterations, info.n_reseed_used, info.n_noise_used)
+    monkeypatch.delenv("CSB_INIT_GRID")
+    assert res["1"][0] == res["0"][0] and torch.equal(res["1"][1], res["0"][1]) and res["1"][2:] == res["0"][2:]
+    info_o = orc.KMeansInfo()
+    orig = random.randint
+    try:
+        random.randint = lambda a, b: first
+        _, _, as_o = orc.kmeans_with_time_min_max(f3, ts, k, exp_noise=noise, reseed_indices=pool, info=info_o)
+    finally:
+        random.randint = orig
+    assert res["1"][0] == info_o.init_indices
+    assert torch.equal(res["1"][1], as_o) and res["1"][2] == info_o.iterations
