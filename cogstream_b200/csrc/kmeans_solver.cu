@@ -326,9 +326,64 @@ __device__ void rebuild_members_smem(const SolverArgs& a, const MemberSmem& m, i
 // A thread works on kSE entries at once, 4 Gram loads each in flight (the loop is pure L2 / HBM latency: member addresses come
 // from shared memory, 8 warps per SM); every entry is still summed in ascending member order.
 constexpr int kSE = 4;
+// Large problems: the same sums read through the symmetry of G, S[i][j] = sum_{m in M_j} G[m][i].  A thread owns frame i, a
+// CTA a slab of 256 consecutive frames and a group of 32 listed columns: every load instruction of a warp reads 256
+// contiguous bytes of Gram row m (the entry-per-thread gather below touches one 8-byte value per 32-byte sector once G no
+// longer fits in L2: 1.66 GB at T = 14,400).  Same values added in the same ascending member order -> the same bits.
+constexpr int kSRowGroup = 32;
+constexpr int kSR = 4;  // columns in flight per thread in the row-streaming variant (x 4 member loads each)
+constexpr int64_t kSRowMinEntries = 1 << 20;
+__device__ void compute_S_rows(const SolverArgs& a, const int* s_offs, const int* s_memb, const int* cols, int ncols, double* S) {
+  const int T = a.T, k = a.k;
+  const int n_slabs = (T + (int)blockDim.x - 1) / (int)blockDim.x;
+  const int n_groups = (ncols + kSRowGroup - 1) / kSRowGroup;
+  const int n_items = n_slabs * n_groups;
+  for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+    const int slab = item % n_slabs, c0 = (item / n_slabs) * kSRowGroup;
+    const int i = slab * blockDim.x + threadIdx.x;
+    if (i >= T) continue;
+    const double* gi = a.G + i;
+    const int c1 = min(ncols, c0 + kSRowGroup);
+    for (int cc = c0; cc < c1; cc += kSR) {
+      int beg[kSR], len[kSR], col[kSR];
+      double s[kSR];
+      int maxlen = 0;
+#pragma unroll
+      for (int u = 0; u < kSR; ++u) {
+        s[u] = 0.0; len[u] = 0; beg[u] = 0; col[u] = -1;
+        if (cc + u < c1) {
+          col[u] = cols[cc + u];
+          beg[u] = s_offs[col[u]];
+          len[u] = s_offs[col[u] + 1] - beg[u];
+          maxlen = max(maxlen, len[u]);
+        }
+      }
+      for (int e = 0; e < maxlen; e += 4) {
+        double v[kSR][4];
+#pragma unroll
+        for (int u = 0; u < kSR; ++u)
+#pragma unroll
+          for (int w = 0; w < 4; ++w) v[u][w] = (e + w < len[u]) ? __ldg(gi + (int64_t)s_memb[beg[u] + e + w] * a.ldg) : 0.0;
+#pragma unroll
+        for (int u = 0; u < kSR; ++u)
+#pragma unroll
+          for (int w = 0; w < 4; ++w)
+            if (e + w < len[u]) s[u] += v[u][w];
+      }
+#pragma unroll
+      for (int u = 0; u < kSR; ++u)
+        if (col[u] >= 0) S[(int64_t)i * k + col[u]] = s[u];
+    }
+  }
+}
+
 __device__ void compute_S(const SolverArgs& a, const int* s_offs, const int* s_memb, const int* cols, int ncols, double* S) {
   const int T = a.T, k = a.k;
   const int64_t total = (int64_t)T * ncols;
+  if (total >= kSRowMinEntries) {
+    compute_S_rows(a, s_offs, s_memb, cols, ncols, S);
+    return;
+  }
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t idx0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx0 < total; idx0 += kSE * stride) {
     const double* g[kSE];
