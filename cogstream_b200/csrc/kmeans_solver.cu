@@ -461,31 +461,44 @@ __global__ void __launch_bounds__(kInitThreads) kmeanspp_kernel(SolverArgs a) {
 // ---- k-means++ over many CTAs (long streams: T > kGridInitMinT) ---------------------------------------------------------
 // The single-CTA kernel above spends ~17 us per round at T = 14,400 (one SM pulls a 115 KB Gram row and a 58 KB noise row
 // and reduces 14,400 candidates), 16.5 ms for the 959 rounds of BASELINE config 4.  Here every thread owns <= kGridInitU
-// frames (nearest distance and diagonal in registers), a round is: update with row c + per-CTA partial sums of nearest^2
-// -> grid barrier -> total (CTA order, identical in every CTA) -> scores + per-CTA argmax -> grid barrier -> global argmax
-// (score, then lowest index).  Same arithmetic per frame as kmeanspp_block; only the (deterministic) order of the fp32 sum
-// differs, which is a common factor of all scores.  Cooperative launch (co-residency for the software barrier).
+// frames (nearest distance and diagonal in registers) and a round costs ONE grid barrier:
+//   update with row c, per-CTA partial of sum nearest^2, per-CTA CANDIDATES for the next centre  -> grid barrier ->
+//   total (fixed tree, identical in every CTA), exact scores of the candidates, global argmax (score, then lowest index).
+// The exact score is RN(RN(n2 / sum) / noise) and needs the total; candidates are chosen from u = RN(n2 / noise), which
+// orders the frames like the exact score up to two roundings: the true winner i* of a CTA satisfies
+// u(i*) >= u_max * (1 - 2^-21), so keeping every frame with u >= u_max * (1 - 2^-20) cannot lose it.  Almost always that is
+// one frame; more than kGridInitCand of them (or the force flag) falls back to an exact second pass + a second barrier.
+// Same arithmetic per frame as kmeanspp_block; only the (deterministic) order of the fp32 sum differs, which is a common
+// factor of all scores.  Cooperative launch (co-residency for the software barrier).
 constexpr int kGridInitThreads = 512;
 constexpr int kGridInitU = 4;
 constexpr int kGridInitMinT = 2048;
+constexpr int kGridInitCand = 4;
 
 struct GridInitBufs {
   unsigned* barrier;  // zeroed before launch
   float* part;        // [2][nb]
-  float* cand_v;      // [2][nb]
-  int* cand_i;        // [2][nb]
+  int* cnt;           // [2][nb] candidates published by the CTA (> kGridInitCand: overflow)
+  float* cand_n2;     // [2][nb][kGridInitCand] nearest^2
+  float* cand_nz;     // [2][nb][kGridInitCand] noise
+  int* cand_i;        // [2][nb][kGridInitCand] frame
+  float* best_v;      // [nb] exact fallback: per-CTA best score / frame
+  int* best_i;
+  int force_exact;    // profiling / test aid: always take the two-barrier exact path
 };
 
 __global__ void __launch_bounds__(kGridInitThreads) kmeanspp_grid_kernel(SolverArgs a, GridInitBufs b) {
-  __shared__ float s_wv[kGridInitThreads / 32];
-  __shared__ int s_wi[kGridInitThreads / 32];
-  __shared__ float s_ws[kGridInitThreads / 32];
-  __shared__ int s_c;
-  __shared__ float s_sum;
+  constexpr int NW = kGridInitThreads / 32;
+  __shared__ float s_wv[NW];
+  __shared__ int s_wi[NW];
+  __shared__ float s_ws[NW];
+  __shared__ float s_cn2[kGridInitCand], s_cnz[kGridInitCand];
+  __shared__ int s_ci[kGridInitCand];
+  __shared__ int s_cnt, s_c, s_ovf;
+  __shared__ float s_sum, s_umax;
   const int T = a.T, k = a.k;
   const unsigned nb = gridDim.x;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  constexpr int NW = kGridInitThreads / 32;
   csb_kmeans_status* st = a.status;
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     st->iterations = 0; st->converged = 0; st->n_reseed_used = 0; st->degenerate_rounds = 0;
@@ -513,37 +526,138 @@ __global__ void __launch_bounds__(kGridInitThreads) kmeanspp_grid_kernel(SolverA
   int noise_row = 0, degenerate = 0, used = 0;
   int c = 0;
   for (int m = 0; m < k; ++m) {
-    if (m < a.n_init_given) {
-      c = (int)a.init_indices[m];
-    } else {
-      // ---- total of nearest^2 (partials of the previous update pass), identical in every CTA ----
-      // (warp 0: one L2 round trip for all partials, then a fixed shuffle tree -- the same bits in every CTA)
-      if (warp == 0) {
-        const float* part = b.part + ((m - 1) & 1) * nb;
-        float v = 0.f;
-        for (unsigned q = lane; q < nb; q += 32) v += __ldcg(part + q);
-        v = warp_sum(v);
-        if (lane == 0) s_sum = v;
+    if (m < a.n_init_given) c = (int)a.init_indices[m];  // else: c was chosen at the end of the previous iteration
+    if (m + 1 >= k) break;
+    // ---- update the nearest distances with centre c; per-CTA partial of sum nearest^2 (:45-53) ----
+    const bool sample_next = m + 1 >= a.n_init_given;
+    const float* noise = a.exp_noise + (int64_t)noise_row * T;  // the row the next round consumes if it samples
+    const double gcc = __ldg(a.G + (int64_t)c * a.ldg + c);
+    const double* gc = a.G + (int64_t)c * a.ldg;
+    double g[kGridInitU];
+    float nz[kGridInitU];
+#pragma unroll
+    for (int u = 0; u < kGridInitU; ++u) {
+      g[u] = fi[u] >= 0 ? __ldg(gc + fi[u]) : 0.0;
+      nz[u] = (sample_next && fi[u] >= 0) ? __ldg(noise + fi[u]) : 1.f;
+    }
+    float part = 0.f, n2[kGridInitU], uq[kGridInitU], umax = 0.f;
+#pragma unroll
+    for (int u = 0; u < kGridInitU; ++u) {
+      n2[u] = 0.f; uq[u] = 0.f;
+      if (fi[u] >= 0) {
+        const double d2 = dg[u] + gcc - 2.0 * g[u];
+        const float d = (float)sqrt(d2 > 0.0 ? d2 : 0.0);
+        near[u] = fminf(near[u], d);
+        n2[u] = __fmul_rn(near[u], near[u]);  // :53
+        part += n2[u];
+        uq[u] = __fdiv_rn(n2[u], nz[u]);
+        umax = fmaxf(umax, uq[u]);
       }
-      __syncthreads();
-      const float sum = s_sum;
-      if (sum == 0.f) {  // :55-57 every frame coincides with a centre: host-drawn index
-        ++degenerate;
-        c = 0;
-        if (used < a.n_reseed_pool) c = (int)a.reseed_pool[used];
-        else if (blockIdx.x == 0 && threadIdx.x == 0) st->reseed_overflow = 1;
-        ++used;
+    }
+    if (!sample_next) continue;  // the next centre is prescribed too: no total needed
+    part = warp_sum(part);
+    umax = warp_max(umax);
+    if (lane == 0) { s_ws[warp] = part; s_wv[warp] = umax; }
+    if (threadIdx.x == 0) { s_cnt = 0; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float t = s_ws[0], um = s_wv[0];
+      for (int w = 1; w < NW; ++w) { t += s_ws[w]; um = fmaxf(um, s_wv[w]); }
+      b.part[(m & 1) * nb + blockIdx.x] = t;
+      s_umax = um;
+    }
+    __syncthreads();
+    {
+      const float um = s_umax;
+      const float thr = um - um * 9.5367431640625e-7f;  // u_max * (1 - 2^-20)
+      if (um > 0.f) {
+#pragma unroll
+        for (int u = 0; u < kGridInitU; ++u) {
+          if (fi[u] >= 0 && uq[u] >= thr) {
+            const int slot = atomicAdd(&s_cnt, 1);
+            if (slot < kGridInitCand) { s_cn2[slot] = n2[u]; s_cnz[slot] = nz[u]; s_ci[slot] = fi[u]; }
+          }
+        }
+      }
+    }
+    __syncthreads();
+    {
+      const int cnt = s_cnt;
+      if (threadIdx.x == 0) b.cnt[(m & 1) * nb + blockIdx.x] = b.force_exact ? kGridInitCand + 1 : cnt;
+      if (threadIdx.x < min(cnt, kGridInitCand)) {
+        const int64_t o = ((int64_t)(m & 1) * nb + blockIdx.x) * kGridInitCand + threadIdx.x;
+        b.cand_n2[o] = s_cn2[threadIdx.x]; b.cand_nz[o] = s_cnz[threadIdx.x]; b.cand_i[o] = s_ci[threadIdx.x];
+      }
+    }
+    grid_sync(b.barrier, bar, nb);
+    // ---- total (fixed shuffle tree: the same bits in every CTA), overflow flag, candidates ----
+    // lane q takes CTA q (q += 32): its partial, count and all candidate slots are loaded together -- one L2 round trip
+    if (warp == 0) {
+      float v = 0.f;
+      int ovf = 0;
+      float gb = -1.f;
+      int gi = 0x7fffffff;
+      constexpr int kMaxQ = 5;  // ceil(148 / 32) CTAs per lane at most
+      float cn2[kMaxQ][kGridInitCand], cnz[kMaxQ][kGridInitCand];
+      int cix[kMaxQ][kGridInitCand], ccnt[kMaxQ];
+#pragma unroll
+      for (int r = 0; r < kMaxQ; ++r) {
+        const unsigned q = lane + 32 * r;
+        ccnt[r] = 0;
+        if (q < nb) {
+          v += __ldcg(b.part + (m & 1) * nb + q);
+          ccnt[r] = __ldcg(b.cnt + (m & 1) * nb + q);
+          const int64_t o = ((int64_t)(m & 1) * nb + q) * kGridInitCand;
+#pragma unroll
+          for (int sl = 0; sl < kGridInitCand; ++sl) {
+            cn2[r][sl] = __ldcg(b.cand_n2 + o + sl); cnz[r][sl] = __ldcg(b.cand_nz + o + sl); cix[r][sl] = __ldcg(b.cand_i + o + sl);
+          }
+        }
+        ovf |= ccnt[r] > kGridInitCand;
+      }
+      v = warp_sum(v);
+      ovf = __any_sync(0xffffffffu, ovf);
+      if (v != 0.f && !ovf) {
+#pragma unroll
+        for (int r = 0; r < kMaxQ; ++r)
+#pragma unroll
+          for (int sl = 0; sl < kGridInitCand; ++sl)
+            if (sl < ccnt[r]) {
+              const float p = __fdiv_rn(cn2[r][sl], v);       // :59
+              const float sc = __fdiv_rn(p, cnz[r][sl]);      // multinomial: argmax(p / Exp(1)), first max
+              const int oi = cix[r][sl];
+              if (sc > gb || (sc == gb && oi < gi)) { gb = sc; gi = oi; }
+            }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          const float ov = __shfl_xor_sync(0xffffffffu, gb, o);
+          const int oi = __shfl_xor_sync(0xffffffffu, gi, o);
+          if (ov > gb || (ov == gb && oi < gi)) { gb = ov; gi = oi; }
+        }
+      }
+      if (lane == 0) { s_sum = v; s_ovf = ovf; s_c = gi; }
+    }
+    __syncthreads();
+    const float sum = s_sum;
+    if (sum == 0.f) {  // :55-57 every frame coincides with a centre: host-drawn index, no noise row consumed
+      ++degenerate;
+      c = 0;
+      if (used < a.n_reseed_pool) c = (int)a.reseed_pool[used];
+      else if (blockIdx.x == 0 && threadIdx.x == 0) st->reseed_overflow = 1;
+      ++used;
+    } else {
+      ++noise_row;
+      if (!s_ovf) {
+        c = s_c;
       } else {
-        const float* noise = a.exp_noise + (int64_t)noise_row * T;
-        ++noise_row;
+        // ---- exact fallback: scores of all frames with the known total, per-CTA argmax, second barrier ----
         float best = -1.f;
         int besti = 0x7fffffff;
 #pragma unroll
         for (int u = 0; u < kGridInitU; ++u) {
           if (fi[u] >= 0) {
-            const float p = __fdiv_rn(__fmul_rn(near[u], near[u]), sum);  // :59
-            const float sc = __fdiv_rn(p, __ldg(noise + fi[u]));          // multinomial: argmax(p / Exp(1)), first max
-            if (sc > best) { best = sc; besti = fi[u]; }                  // fi ascending in u: first max kept
+            const float sc = __fdiv_rn(__fdiv_rn(n2[u], sum), nz[u]);
+            if (sc > best) { best = sc; besti = fi[u]; }  // fi ascending in u: first max kept
           }
         }
 #pragma unroll
@@ -561,16 +675,16 @@ __global__ void __launch_bounds__(kGridInitThreads) kmeanspp_grid_kernel(SolverA
             const int oi = s_wi[w];
             if (ov > best || (ov == best && oi < besti)) { best = ov; besti = oi; }
           }
-          b.cand_v[(m & 1) * nb + blockIdx.x] = best;
-          b.cand_i[(m & 1) * nb + blockIdx.x] = besti;
+          b.best_v[blockIdx.x] = best;
+          b.best_i[blockIdx.x] = besti;
         }
         grid_sync(b.barrier, bar, nb);
         if (warp == 0) {
           float gb = -1.f;
           int gi = 0x7fffffff;
           for (unsigned q = lane; q < nb; q += 32) {
-            const float ov = __ldcg(b.cand_v + (m & 1) * nb + q);
-            const int oi = __ldcg(b.cand_i + (m & 1) * nb + q);
+            const float ov = __ldcg(b.best_v + q);
+            const int oi = __ldcg(b.best_i + q);
             if (ov > gb || (ov == gb && oi < gi)) { gb = ov; gi = oi; }
           }
 #pragma unroll
@@ -584,37 +698,9 @@ __global__ void __launch_bounds__(kGridInitThreads) kmeanspp_grid_kernel(SolverA
         __syncthreads();
         c = s_c;
       }
-      if (blockIdx.x == 0 && threadIdx.x == 0) a.init_indices[m] = c;
     }
-    if (m + 1 < k) {
-      // ---- update the nearest distances with centre c; per-CTA partial of sum nearest^2 (:45-53) ----
-      const double gcc = __ldg(a.G + (int64_t)c * a.ldg + c);
-      const double* gc = a.G + (int64_t)c * a.ldg;
-      double g[kGridInitU];
-#pragma unroll
-      for (int u = 0; u < kGridInitU; ++u) g[u] = fi[u] >= 0 ? __ldg(gc + fi[u]) : 0.0;
-      float part = 0.f;
-#pragma unroll
-      for (int u = 0; u < kGridInitU; ++u) {
-        if (fi[u] >= 0) {
-          const double d2 = dg[u] + gcc - 2.0 * g[u];
-          const float d = (float)sqrt(d2 > 0.0 ? d2 : 0.0);
-          near[u] = fminf(near[u], d);
-          part += __fmul_rn(near[u], near[u]);  // :53
-        }
-      }
-      if (m + 1 >= a.n_init_given) {  // the next round samples: it needs the total
-        part = warp_sum(part);
-        if (lane == 0) s_ws[warp] = part;
-        __syncthreads();
-        if (threadIdx.x == 0) {
-          float t = s_ws[0];
-          for (int w = 1; w < NW; ++w) t += s_ws[w];
-          b.part[(m & 1) * nb + blockIdx.x] = t;
-        }
-        grid_sync(b.barrier, bar, nb);
-      }
-    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) a.init_indices[m + 1] = c;
+    __syncthreads();  // s_c / s_sum are rewritten in the next round
   }
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     st->degenerate_rounds = degenerate;
@@ -711,13 +797,26 @@ __global__ void __launch_bounds__(kSolverThreads) kmeans_solver_kernel(SolverArg
           tmin_ = tc[u] < tmin_ ? tc[u] : tmin_; tmax_ = tc[u] > tmax_ ? tc[u] : tmax_;
         }
       }
-      for (int j = lane + 128; j < k; j += 32) {
-        const double d2 = gii - 2.0 * (__ldcg(S + (int64_t)i * k + j) * s_rn[j]) + q[j];
-        const float d = (float)sqrt(d2 > 0.0 ? d2 : 0.0);
-        TS dt = ti - (TS)ctc[j];
-        dt = dt < TS(0) ? -dt : dt;
-        fmin_ = fminf(fmin_, d); fmax_ = fmaxf(fmax_, d);
-        tmin_ = dt < tmin_ ? dt : tmin_; tmax_ = dt > tmax_ ? dt : tmax_;
+      // k > 128: further blocks of 128 columns, 4 independent S loads per lane in flight (the row of S is an L2 / HBM read)
+      for (int j0 = 128; j0 < k; j0 += 128) {
+        double sv[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int j = j0 + lane + 32 * u;
+          sv[u] = j < k ? __ldcg(S + (int64_t)i * k + j) : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int j = j0 + lane + 32 * u;
+          if (j < k) {
+            const double d2 = gii - 2.0 * (sv[u] * s_rn[j]) + q[j];
+            const float d = (float)sqrt(d2 > 0.0 ? d2 : 0.0);
+            TS dt = ti - (TS)ctc[j];
+            dt = dt < TS(0) ? -dt : dt;
+            fmin_ = fminf(fmin_, d); fmax_ = fmaxf(fmax_, d);
+            tmin_ = dt < tmin_ ? dt : tmin_; tmax_ = dt > tmax_ ? dt : tmax_;
+          }
+        }
       }
       fmin_ = warp_min(fmin_); fmax_ = warp_max(fmax_);
       tmin_ = warp_min(tmin_); tmax_ = warp_max(tmax_);
@@ -744,12 +843,24 @@ __global__ void __launch_bounds__(kSolverThreads) kmeans_solver_kernel(SolverArg
         const int j = lane + 32 * u;
         if (j < k) consider(dc[u], tc[u], j);
       }
-      for (int j = lane + 128; j < k; j += 32) {
-        const double d2 = gii - 2.0 * (__ldcg(S + (int64_t)i * k + j) * s_rn[j]) + q[j];
-        const float d = (float)sqrt(d2 > 0.0 ? d2 : 0.0);
-        TS dt = ti - (TS)ctc[j];
-        dt = dt < TS(0) ? -dt : dt;
-        consider(d, dt, j);
+      for (int j0 = 128; j0 < k; j0 += 128) {
+        double sv[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int j = j0 + lane + 32 * u;
+          sv[u] = j < k ? __ldcg(S + (int64_t)i * k + j) : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int j = j0 + lane + 32 * u;
+          if (j < k) {
+            const double d2 = gii - 2.0 * (sv[u] * s_rn[j]) + q[j];
+            const float d = (float)sqrt(d2 > 0.0 ? d2 : 0.0);
+            TS dt = ti - (TS)ctc[j];
+            dt = dt < TS(0) ? -dt : dt;
+            consider(d, dt, j);
+          }
+        }
       }
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) {
@@ -993,9 +1104,15 @@ int csb_kmeans_solve(const double* G, const void* timestamps, const csb_kmeans_p
     gb.barrier = reinterpret_cast<unsigned*>(w + 64);
     // scratch inside S[0]: the Lloyd kernel (re)builds S[0] from scratch after the init
     char* sc0 = reinterpret_cast<char*>(a.S[0]);
-    gb.part = reinterpret_cast<float*>(sc0);
-    gb.cand_v = reinterpret_cast<float*>(sc0 + align_up(sizeof(float) * 2 * nbi, 256));
-    gb.cand_i = reinterpret_cast<int*>(sc0 + 2 * align_up(sizeof(float) * 2 * nbi, 256));
+    auto carve = [&](size_t bytes) { char* r = sc0; sc0 += align_up(bytes, 256); return r; };
+    gb.part = reinterpret_cast<float*>(carve(sizeof(float) * 2 * nbi));
+    gb.cnt = reinterpret_cast<int*>(carve(sizeof(int) * 2 * nbi));
+    gb.cand_n2 = reinterpret_cast<float*>(carve(sizeof(float) * 2 * nbi * kGridInitCand));
+    gb.cand_nz = reinterpret_cast<float*>(carve(sizeof(float) * 2 * nbi * kGridInitCand));
+    gb.cand_i = reinterpret_cast<int*>(carve(sizeof(int) * 2 * nbi * kGridInitCand));
+    gb.best_v = reinterpret_cast<float*>(carve(sizeof(float) * nbi));
+    gb.best_i = reinterpret_cast<int*>(carve(sizeof(int) * nbi));
+    gb.force_exact = getenv("CSB_INIT_EXACT") ? 1 : 0;
     void* iargs[] = {&a, &gb};
     e = cudaLaunchCooperativeKernel((const void*)kmeanspp_grid_kernel, dim3((unsigned)nbi), dim3(kGridInitThreads), iargs, 0, s);
     if (e != cudaSuccess) { set_error("kmeans_solve: init launch: %s", cudaGetErrorString(e)); return CSB_ERR_CUDA; }

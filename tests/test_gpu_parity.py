@@ -888,13 +888,17 @@ def test_kmeanspp_long_stream_grid_init(dev, monkeypatch, T, P, D, seed):
     pool = [int(v) for v in torch.randint(0, T, (64,), generator=g)]
     f3 = feats.view(T, P, D)
     res = {}
-    for mode in ("1", "0"):
-        monkeypatch.setenv("CSB_INIT_GRID", mode)
+    for mode in ("1", "0", "exact"):  # grid (one barrier per round), single CTA, grid with the exact two-barrier fallback
+        monkeypatch.setenv("CSB_INIT_GRID", "0" if mode == "0" else "1")
+        if mode == "exact":
+            monkeypatch.setenv("CSB_INIT_EXACT", "1")
         _, _, assign, info = kmeans_with_time_min_max(f3.to(dev), ts.to(dev), k, first_index=first, exp_noise=noise,
                                                       reseed_indices=pool, return_info=True)
         res[mode] = (info.init_indices.tolist(), assign.cpu(), info.iterations, info.n_reseed_used, info.n_noise_used)
     monkeypatch.delenv("CSB_INIT_GRID")
-    assert res["1"][0] == res["0"][0] and torch.equal(res["1"][1], res["0"][1]) and res["1"][2:] == res["0"][2:]
+    monkeypatch.delenv("CSB_INIT_EXACT")
+    for other in ("0", "exact"):
+        assert res["1"][0] == res[other][0] and torch.equal(res["1"][1], res[other][1]) and res["1"][2:] == res[other][2:]
     info_o = orc.KMeansInfo()
     orig = random.randint
     try:
