@@ -102,6 +102,11 @@ __device__ void kmeanspp_block(const SolverArgs& a, float* s_near, const double*
   for (int i = threadIdx.x; i < T; i += blockDim.x) s_near[i] = __int_as_float(0x7f800000);
   __syncthreads();
   int noise_row = 0, degenerate = 0, used = *used_io;
+  // T <= 4 * NT (one frame batch per thread): the Exp(1) row of the NEXT sampling round is fetched together with the Gram row
+  // of the update pass, one L2 round trip per round instead of two dependent ones
+  const bool prefetch_noise = T <= 4 * NT;
+  float nzp[4] = {1.f, 1.f, 1.f, 1.f};
+  bool nzp_valid = false;
   for (int m = 0; m < k; ++m) {
     int c;
     if (m < a.n_init_given) {
@@ -121,6 +126,9 @@ __device__ void kmeanspp_block(const SolverArgs& a, float* s_near, const double*
         ++used;
       } else {
         ++noise_row;
+#ifdef CSB_PP_MARKS
+        if (m < 40) mark(a, 24);
+#endif
         float best = -1.f;
         int besti = 0x7fffffff;
         for (int i0 = threadIdx.x; i0 < T; i0 += 4 * NT) {
@@ -129,40 +137,64 @@ __device__ void kmeanspp_block(const SolverArgs& a, float* s_near, const double*
           for (int u = 0; u < 4; ++u) {
             const int ii = i0 + u * NT;
             nd[u] = ii < T ? s_near[ii] : 0.f;
-            nz[u] = ii < T ? __ldg(noise + ii) : 1.f;
+            nz[u] = nzp_valid ? nzp[u] : (ii < T ? __ldg(noise + ii) : 1.f);
           }
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
             const int ii = i0 + u * NT;
-            const float p = __fdiv_rn(__fmul_rn(nd[u], nd[u]), sum);  // :59
-            const float sc = __fdiv_rn(p, nz[u]);                      // multinomial: argmax(p / Exp(1)), first max
+            // a frame that coincides with a centre scores +0 exactly (0 / sum / noise); feeding the zero to the IEEE division
+            // sends the whole warp down its slow path, so it is substituted and the result selected afterwards
+            const float n2 = __fmul_rn(nd[u], nd[u]);
+            const float p = __fdiv_rn(n2 == 0.f ? 1.f : n2, sum);  // :59
+            float sc = __fdiv_rn(p, nz[u]);                          // multinomial: argmax(p / Exp(1)), first max
+            sc = n2 == 0.f ? 0.f : sc;
             if (ii < T && sc > best) { best = sc; besti = ii; }
           }
         }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-          const float ov = __shfl_xor_sync(0xffffffffu, best, o);
-          const int oi = __shfl_xor_sync(0xffffffffu, besti, o);
-          if (ov > best || (ov == best && oi < besti)) { best = ov; besti = oi; }
+#ifdef CSB_PP_MARKS
+        if (m < 40) mark(a, 25);
+#endif
+        // argmax (score, then lowest frame) with the hardware warp reductions: scores are >= +0, so their bit patterns order
+        // like unsigned integers (-1 = "no frame" maps to 0); two REDUX per level instead of ten shuffles + compares
+        {
+          const unsigned bits = best > 0.f ? __float_as_uint(best) : 0u;
+          const unsigned wmax = __reduce_max_sync(0xffffffffu, bits);
+          const unsigned widx = __reduce_min_sync(0xffffffffu, bits == wmax ? (unsigned)besti : 0x7fffffffu);
+          if (lane == 0) { s_wv[warp] = __uint_as_float(wmax); s_wi[warp] = (int)widx; }
         }
-        if (lane == 0) { s_wv[warp] = best; s_wi[warp] = besti; }
+#ifdef CSB_PP_MARKS
+        if (m < 40) mark(a, 26);
+#endif
         __syncthreads();
-        best = s_wv[0];
-        besti = s_wi[0];
-#pragma unroll
-        for (int w = 1; w < NW; ++w) {
-          const float ov = s_wv[w];
-          const int oi = s_wi[w];
-          if (ov > best || (ov == best && oi < besti)) { best = ov; besti = oi; }
+#ifdef CSB_PP_MARKS
+        if (m < 40) mark(a, 27);
+#endif
+        {
+          const unsigned bits = lane < NW ? __float_as_uint(s_wv[lane]) : 0u;
+          const unsigned idx = lane < NW ? (unsigned)s_wi[lane] : 0x7fffffffu;
+          const unsigned bmax = __reduce_max_sync(0xffffffffu, bits);
+          besti = (int)__reduce_min_sync(0xffffffffu, bits == bmax ? idx : 0x7fffffffu);
         }
         c = besti;
       }
       if (threadIdx.x == 0) a.init_indices[m] = c;
+#ifdef CSB_PP_MARKS
+      if (m < 40) mark(a, 21);
+#endif
     }
     if (m + 1 < k) {
       const double gcc = diag[c];
       const double* gc = G + (int64_t)c * a.ldg;
       float part = 0.f;
+      if (prefetch_noise && m + 1 >= a.n_init_given) {
+        const float* nn = a.exp_noise + (int64_t)noise_row * T;  // row of the next sampling round (rows are consumed in order)
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int ii = threadIdx.x + u * NT;
+          nzp[u] = ii < T ? __ldg(nn + ii) : 1.f;
+        }
+        nzp_valid = true;
+      }
       for (int i0 = threadIdx.x; i0 < T; i0 += 4 * NT) {
         double g[4];
 #pragma unroll
@@ -182,10 +214,16 @@ __device__ void kmeanspp_block(const SolverArgs& a, float* s_near, const double*
           }
         }
       }
+#ifdef CSB_PP_MARKS
+      if (m < 40) mark(a, 22);
+#endif
       part = warp_sum(part);
       __syncthreads();  // s_ws / s_wv of this round have been consumed by every thread
       if (lane == 0) s_ws[warp] = part;
       __syncthreads();
+#ifdef CSB_PP_MARKS
+      if (m < 40) mark(a, 23);
+#endif
 
     }
   }

@@ -29,9 +29,9 @@ r = sc.results()
 print("ok", r["status"], r["n_kept"], len(r["minor"]))
 
 if os.environ.get("CSB_TIMELINE"):
-    names = {1: "start", 2: "init done", 3: "S0 done", 10: "assign", 11: "sync", 12: "rebuild", 13: "S", 14: "sync", 15: "shift", 20: "  pp sum", 21: "  pp argmax", 22: "  pp update"}
+    names = {1: "start", 2: "init done", 3: "S0 done", 10: "assign", 11: "sync", 12: "rebuild", 13: "S", 14: "sync", 15: "shift", 21: "  pp centre chosen", 22: "  pp row landed, near updated", 23: "  pp partial sums published", 24: "  pp total summed", 25: "  pp own scores done", 26: "  pp warp argmax done", 27: "  pp block sync passed"}
     tl = sc.km.timeline()
     prev = 0
     for tag, t in tl:
-        print(f"  {names.get(tag, tag):10s} +{(t - prev) / 1e3:8.2f} us   (t={t / 1e3:8.2f})")
+        print(f"  {str(names.get(tag, tag)):10s} +{(t - prev) / 1e3:8.2f} us   (t={t / 1e3:8.2f})")
         prev = t
