@@ -588,7 +588,7 @@ __global__ void __launch_bounds__(kGridInitThreads) kmeanspp_grid_kernel(SolverA
         near[u] = fminf(near[u], d);
         n2[u] = __fmul_rn(near[u], near[u]);  // :53
         part += n2[u];
-        uq[u] = __fdiv_rn(n2[u], nz[u]);
+        uq[u] = n2[u] == 0.f ? 0.f : __fdiv_rn(n2[u] == 0.f ? 1.f : n2[u], nz[u]);  // (zero numerators: see kmeanspp_block)
         umax = fmaxf(umax, uq[u]);
       }
     }
@@ -748,8 +748,10 @@ __global__ void __launch_bounds__(kGridInitThreads) kmeanspp_grid_kernel(SolverA
   mark(a, 2);
 }
 
-template <typename TS>
-__global__ void __launch_bounds__(kSolverThreads) kmeans_solver_kernel(SolverArgs a) {
+// WIDE (128 < k <= 1024): the assignment pass keeps a frame's whole row of S in registers (one L2 / HBM round trip per frame
+// instead of one per 128 columns and per pass); its own instantiation so that the small-k kernel keeps its register budget.
+template <typename TS, bool WIDE>
+__global__ void __launch_bounds__(kSolverThreads, WIDE ? 1 : 2) kmeans_solver_kernel(SolverArgs a) {
   extern __shared__ double smem_d[];
   const int T = a.T, k = a.k;
   // doubles: q[2][k], ct[2][k], rn[k] (1/n), nn[k] (n), red[32], [diag[T]]
@@ -821,8 +823,33 @@ __global__ void __launch_bounds__(kSolverThreads) kmeans_solver_kernel(SolverArg
       const TS ti = load_ts<TS>(a.ts, i);
       float fmin_ = __int_as_float(0x7f800000), fmax_ = -fmin_;
       TS tmin_ = (TS)__int_as_float(0x7f800000), tmax_ = -tmin_;
+      constexpr int kWB = WIDE ? 8 : 1;  // 128-column blocks held in registers
+      double sv[kWB][4];
       float dc[4];
       TS tc[4];
+      if (WIDE) {
+#pragma unroll
+        for (int bk = 0; bk < kWB; ++bk)
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int j = bk * 128 + lane + 32 * u;
+            sv[bk][u] = j < k ? __ldcg(S + (int64_t)i * k + j) : 0.0;
+          }
+#pragma unroll
+        for (int bk = 0; bk < kWB; ++bk)
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int j = bk * 128 + lane + 32 * u;
+            if (j < k) {
+              const double d2 = gii - 2.0 * (sv[bk][u] * s_rn[j]) + q[j];
+              const float d = (float)sqrt(d2 > 0.0 ? d2 : 0.0);
+              TS dt = ti - (TS)ctc[j];
+              dt = dt < TS(0) ? -dt : dt;
+              fmin_ = fminf(fmin_, d); fmax_ = fmaxf(fmax_, d);
+              tmin_ = dt < tmin_ ? dt : tmin_; tmax_ = dt > tmax_ ? dt : tmax_;
+            }
+          }
+      } else {
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         const int j = lane + 32 * u;
@@ -856,6 +883,7 @@ __global__ void __launch_bounds__(kSolverThreads) kmeans_solver_kernel(SolverArg
           }
         }
       }
+      }
       fmin_ = warp_min(fmin_); fmax_ = warp_max(fmax_);
       tmin_ = warp_min(tmin_); tmax_ = warp_max(tmax_);
       const float fspread = __fsub_rn(fmax_, fmin_);
@@ -863,8 +891,14 @@ __global__ void __launch_bounds__(kSolverThreads) kmeans_solver_kernel(SolverArg
       float best = __int_as_float(0x7f800000), second = best;
       int bestj = 0x7fffffff;
       auto consider = [&](float d, TS dt, int j) {
-        const float nf = (fmax_ > fmin_) ? __fdiv_rn(__fsub_rn(d, fmin_), fspread) : 0.f;  // :86-91
-        const TS nt = (tmax_ > tmin_) ? (dt - tmin_) / tspread : TS(0);                        // :94-99
+        // 0 / spread is exactly +0; a zero numerator (the row minimum: one lane of every warp) would send the warp down the
+        // IEEE division's slow path, so it is substituted and the quotient selected afterwards
+        const float fnum = __fsub_rn(d, fmin_);
+        float nf = (fmax_ > fmin_) ? __fdiv_rn(fnum == 0.f ? 1.f : fnum, fspread) : 0.f;  // :86-91
+        nf = fnum == 0.f ? 0.f : nf;
+        const TS tnum = dt - tmin_;
+        TS nt = (tmax_ > tmin_) ? (tnum == TS(0) ? TS(1) : tnum) / tspread : TS(0);          // :94-99
+        nt = tnum == TS(0) ? TS(0) : nt;
         float fin;                                                                               // :101
         if (sizeof(TS) == 8) {
           const double v = __dadd_rn((double)__fmul_rn(nf, nf), __dmul_rn((double)alpha, __dmul_rn((double)nt, (double)nt)));
@@ -876,6 +910,21 @@ __global__ void __launch_bounds__(kSolverThreads) kmeans_solver_kernel(SolverArg
         if (fin < best) { second = best; best = fin; bestj = j; }
         else if (fin < second) second = fin;
       };
+      if (WIDE) {
+#pragma unroll
+        for (int bk = 0; bk < kWB; ++bk)
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int j = bk * 128 + lane + 32 * u;
+            if (j < k) {  // same arithmetic as the first pass: the same d, dt bits
+              const double d2 = gii - 2.0 * (sv[bk][u] * s_rn[j]) + q[j];
+              const float d = (float)sqrt(d2 > 0.0 ? d2 : 0.0);
+              TS dt = ti - (TS)ctc[j];
+              dt = dt < TS(0) ? -dt : dt;
+              consider(d, dt, j);
+            }
+          }
+      } else {
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         const int j = lane + 32 * u;
@@ -899,6 +948,7 @@ __global__ void __launch_bounds__(kSolverThreads) kmeans_solver_kernel(SolverArg
             consider(d, dt, j);
           }
         }
+      }
       }
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) {
@@ -1120,7 +1170,9 @@ int csb_kmeans_solve(const double* G, const void* timestamps, const csb_kmeans_p
   if (e != cudaSuccess) { set_error("kmeans_solve: memset: %s", cudaGetErrorString(e)); return CSB_ERR_CUDA; }
 
   const size_t smem = sp.bytes;
-  auto kern = (p->ts_dtype == CSB_F64) ? kmeans_solver_kernel<double> : kmeans_solver_kernel<float>;
+  const bool wide = k > 128 && k <= 1024;
+  auto kern = (p->ts_dtype == CSB_F64) ? (wide ? kmeans_solver_kernel<double, true> : kmeans_solver_kernel<double, false>)
+                                       : (wide ? kmeans_solver_kernel<float, true> : kmeans_solver_kernel<float, false>);
   if (smem > 48 * 1024) {
     e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { set_error("kmeans_solve: smem attr: %s", cudaGetErrorString(e)); return CSB_ERR_CUDA; }
