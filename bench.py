@@ -181,7 +181,7 @@ def run_reference_arm(args):
                 cpu_baseline=dict(value=value, unit=UNIT, cores=torch.get_num_threads(), kind="port", sample=sample,
                                   value_full_P_estimate=w["T"] / (dt * w["P"] / P_s)),
                 e2e=dict(value=value, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
-    print(json.dumps(line), flush=True)
+    _emit(line)
 
 
 def _config_dict(P=None):
@@ -209,7 +209,7 @@ def run_ours(args):
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the one JSON line (NCCL_DEBUG=VERSION prints a banner there)
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # NCCL's banner / warnings never go to stdout
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.load()
     w = WORKLOAD
@@ -372,7 +372,7 @@ def run_ours(args):
                 all_gathered_stats_shape=list(rows.shape))
     if cpu is not None:
         line["cpu_baseline"] = cpu
-    print(json.dumps(line), flush=True)
+    _emit(line)
 
 
 def _stage_times(sc, d, ev_d, q_d, reps=5):
@@ -521,7 +521,29 @@ def _roofline(stages, sc, d, ms_step=None, ms_single=None):
     return roof
 
 
+_REAL_STDOUT = None
+
+
+def _claim_stdout():
+    """The driver reads ONE JSON line from stdout.  Native libraries (NCCL's version banner, ...) print to fd 1 directly, so the
+    process-wide fd 1 is pointed at stderr for the whole run and the JSON line is written to the saved descriptor."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def _emit(line: dict):
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
+    _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
