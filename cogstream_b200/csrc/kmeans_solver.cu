@@ -246,6 +246,7 @@ struct MemberSmem {
   int* cntw;     // [kSolverWarps][k] per-warp counters (multiwarp_fill) or [k]
   int* changed;  // [k]
   double* ct_new;
+  const void* ts_smem;  // shared-memory copy of the timestamps (nullptr: read them from global memory)
 };
 
 template <typename TS>
@@ -353,7 +354,8 @@ __device__ void rebuild_members_smem(const SolverArgs& a, const MemberSmem& m, i
   for (int j = threadIdx.x; j < k; j += blockDim.x) {
     const int beg = m.offs[j], end = m.offs[j + 1];
     TS tsum = TS(0);
-    for (int e = beg; e < end; ++e) tsum += load_ts<TS>(a.ts, m.memb[e]);
+    const void* tsrc = m.ts_smem ? m.ts_smem : a.ts;  // k threads x ~T/k dependent reads: shared memory when it fits
+    for (int e = beg; e < end; ++e) tsum += load_ts<TS>(tsrc, m.memb[e]);
     m.ct_new[j] = (double)(TS)(tsum / (TS)(end - beg));
   }
   __syncthreads();
@@ -762,7 +764,8 @@ __global__ void __launch_bounds__(kSolverThreads, WIDE ? 1 : 2) kmeans_solver_ke
   double* s_red = smem_d + 6 * k;
   double* s_diag = s_red + 32;
   // ints: assign[T], offs[k+1], cursor[k+1], memb[T+k], changed[k], ver[k], verbuf[2][k], cols[k], cntw[nw*k]
-  int* s_assign = reinterpret_cast<int*>(s_diag + (a.diag_in_smem ? T : 0));
+  TS* s_ts = reinterpret_cast<TS*>(s_diag + T);  // [T] (8-byte slots) next to the diagonal, same condition
+  int* s_assign = reinterpret_cast<int*>(s_diag + (a.diag_in_smem ? 2 * T : 0));
   int* s_offs = s_assign + T;
   int* s_cursor = s_offs + (k + 1);
   int* s_memb = s_cursor + (k + 1);
@@ -783,7 +786,7 @@ __global__ void __launch_bounds__(kSolverThreads, WIDE ? 1 : 2) kmeans_solver_ke
   // ---------------- the k-means++ kernel ran before this launch: centres, diagonal and pool usage are in global memory ------
   used = *a.used;
   if (a.diag_in_smem)
-    for (int i = threadIdx.x; i < T; i += blockDim.x) s_diag[i] = a.diag[i];
+    for (int i = threadIdx.x; i < T; i += blockDim.x) { s_diag[i] = a.diag[i]; s_ts[i] = load_ts<TS>(a.ts, i); }
   // initial centres: cluster j = { init[j] }
   for (int j = threadIdx.x; j < k; j += blockDim.x) {
     const int c = (int)a.init_indices[j];
@@ -806,6 +809,7 @@ __global__ void __launch_bounds__(kSolverThreads, WIDE ? 1 : 2) kmeans_solver_ke
 
   MemberSmem ms;
   ms.assign = s_assign; ms.offs = s_offs; ms.memb = s_memb; ms.cursor = s_cursor; ms.cntw = s_cntw; ms.changed = s_changed;
+  ms.ts_smem = a.diag_in_smem ? s_ts : nullptr;
 
   const TS alpha = (TS)a.alpha;
   int cur = 0, it = 0;
@@ -820,7 +824,7 @@ __global__ void __launch_bounds__(kSolverThreads, WIDE ? 1 : 2) kmeans_solver_ke
     const double* ctc = s_ctb[cur];
     for (int i = blockIdx.x * kSolverWarps + warp; i < T; i += nb * kSolverWarps) {
       const double gii = diag[i];
-      const TS ti = load_ts<TS>(a.ts, i);
+      const TS ti = a.diag_in_smem ? s_ts[i] : load_ts<TS>(a.ts, i);
       float fmin_ = __int_as_float(0x7f800000), fmax_ = -fmin_;
       TS tmin_ = (TS)__int_as_float(0x7f800000), tmax_ = -tmin_;
       constexpr int kWB = WIDE ? 8 : 1;  // 128-column blocks held in registers
@@ -1106,8 +1110,8 @@ static SolverSmemPlan plan_smem(int64_t T, int64_t k) {
   const size_t budget = 200 * 1024;
   p.multiwarp_fill = (base + sizeof(int) * kSolverWarps * k <= budget) ? 1 : 0;
   size_t b = base + sizeof(int) * (p.multiwarp_fill ? kSolverWarps : 1) * k;
-  p.diag_in_smem = (b + sizeof(double) * T <= budget) ? 1 : 0;
-  if (p.diag_in_smem) b += sizeof(double) * T;
+  p.diag_in_smem = (b + 2 * sizeof(double) * T <= budget) ? 1 : 0;  // Gram diagonal + timestamps
+  if (p.diag_in_smem) b += 2 * sizeof(double) * T;
   p.bytes = b;
   return p;
 }
