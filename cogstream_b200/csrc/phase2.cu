@@ -967,7 +967,12 @@ int csb_pixel_diff(const void* pixels, int64_t t, int64_t P, int64_t W, int32_t 
       const int F = t >= 96 ? 12 : 4;
       const int64_t nitems = ((t + F - 1) / F) * P;
       int64_t gb = (nitems + pw - 1) / pw;
-      if (gb > kNumSMs) gb = kNumSMs;  // persistent: one CTA per SM, warps stride over the work items
+      // up to 4 CTAs per SM's worth of grid (one resident at a time: the ring takes the shared memory): CTAs that find their SM
+      // taken by a long-running kernel of another stream are simply picked up by the SMs that finish first
+      // (CSB_PIX_WAVES overrides for tuning runs; 1 = one persistent CTA per SM)
+      int waves = 4;
+      if (const char* o = getenv("CSB_PIX_WAVES")) waves = atoi(o) > 0 ? atoi(o) : 4;
+      if (gb > (int64_t)kNumSMs * waves) gb = (int64_t)kNumSMs * waves;
       auto launch = [&](auto kern) -> int {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring_bytes);
         if (e != cudaSuccess) { set_error("pixel_diff: smem attr: %s", cudaGetErrorString(e)); return CSB_ERR_CUDA; }
