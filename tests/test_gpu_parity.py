@@ -603,6 +603,24 @@ ODD = [  # T, P, D, k, C   -- awkward shapes: tiny D, P = 1, T below / across wa
 ]
 
 
+def _random_shapes(n, seed=2026):
+    """Seeded sweep over (T, P, D, k, C): every Gram tiling from 1 to 4 row blocks, k from 2 up to more than 128 (the WIDE
+    assignment instantiation), token counts whose grid is not square, widths down to one 128-bit vector."""
+    g = random.Random(seed)
+    out = []
+    for _ in range(n):
+        T = g.choice([g.randint(12, 64), g.randint(65, 200), g.randint(201, 520)])
+        P = g.choice([1, 2, 3, 4, 6, 8, 9])
+        D = 8 * g.randint(1, 33)
+        k = g.randint(2, min(T - 1, g.choice([8, 40, 160])))
+        C = g.choice([2, 4, 6, 12])
+        out.append((T, P, D, k, C))
+    return out
+
+
+ODD = ODD + _random_shapes(18) + [(300, 2, 64, 150, 4), (520, 1, 32, 200, 2)]  # + k > 128: WIDE assignment kernel
+
+
 @pytest.mark.parametrize("T,P,D,k,C", ODD)
 def test_pipeline_odd_shapes(dev, T, P, D, k, C):
     st = synthetic.make_stream(T, P, D, T + P + D, C=C, near_threshold_frac=0.1)
