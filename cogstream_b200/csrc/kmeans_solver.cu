@@ -15,6 +15,7 @@
 // shared memory (identical by construction), so only the assignments and the S columns cross CTAs.
 // Columns of S are recomputed only for clusters whose membership changed (version stamps per buffer).
 #include <stdlib.h>
+#include <string.h>
 
 #include "csb_common.cuh"
 
@@ -750,6 +751,62 @@ __global__ void __launch_bounds__(kGridInitThreads) kmeanspp_grid_kernel(SolverA
   mark(a, 2);
 }
 
+// ---- outputs shared by the grid and the cluster solver: CSR, centre times, chronological event order, status (CTA 0) ----
+template <typename TS>
+__device__ void solver_outputs(const SolverArgs& a, const int* s_offs, const int* s_memb, const double* ct_cur, const int* s_cntw,
+                               int* s_cursor, float my_margin, int it, bool converged, int used, float last_shift) {
+  const int k = a.k;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  csb_kmeans_status* st = a.status;
+  if (lane == 0 && my_margin < __int_as_float(0x7f800000))
+    atomicMin(reinterpret_cast<unsigned*>(&st->min_margin), __float_as_uint(fmaxf(my_margin, 0.f)));
+  if (blockIdx.x == 0) {
+    for (int j = threadIdx.x; j <= k; j += blockDim.x) a.member_offsets[j] = s_offs[j];
+    const int nmem = s_offs[k];
+    for (int m = threadIdx.x; m < nmem; m += blockDim.x) a.members[m] = s_memb[m];
+    for (int j = threadIdx.x; j < k; j += blockDim.x) {
+      if (sizeof(TS) == 8) reinterpret_cast<double*>(a.ct_out)[j] = ct_cur[j];
+      else reinterpret_cast<float*>(a.ct_out)[j] = (float)ct_cur[j];
+    }
+    // chronological per-event order: the member lists minus the seed frames of re-seeded (empty) clusters.
+    // After rebuild_members_smem, cntw[w][j] holds warp w's running cursor == exclusive base + its count, so the
+    // last warp's cursor is the real member count of cluster j.
+    if (a.event_offsets && a.event_order && it > 0) {
+      const int nw = a.multiwarp_fill ? kSolverWarps : 1;
+      if (warp == 0) {
+        const int cpl = (k + 31) / 32;
+        const int j0 = min(k, lane * cpl), j1 = min(k, j0 + cpl);
+        int mine = 0;
+        for (int j = j0; j < j1; ++j) mine += s_cntw[(nw - 1) * k + j];
+        int inc = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int v = __shfl_up_sync(0xffffffffu, inc, o);
+          if (lane >= o) inc += v;
+        }
+        int run = inc - mine;
+        for (int j = j0; j < j1; ++j) {
+          s_cursor[j] = run;
+          a.event_offsets[j] = run;
+          run += s_cntw[(nw - 1) * k + j];
+        }
+        if (lane == 31) a.event_offsets[k] = inc;
+      }
+      __syncthreads();
+      for (int j = warp; j < k; j += kSolverWarps) {
+        const int n = s_cntw[(nw - 1) * k + j], src = s_offs[j], dst = s_cursor[j];
+        for (int e = lane; e < n; e += 32) a.event_order[dst + e] = s_memb[src + e];
+      }
+    }
+    if (threadIdx.x == 0) {
+      st->iterations = it;
+      st->converged = converged ? 1 : 0;
+      st->n_reseed_used = used;
+      st->last_shift = last_shift;
+    }
+  }
+}
+
 // WIDE (128 < k <= 1024): the assignment pass keeps a frame's whole row of S in registers (one L2 / HBM round trip per frame
 // instead of one per 128 columns and per pass); its own instantiation so that the small-k kernel keeps its register budget.
 template <typename TS, bool WIDE>
@@ -1048,53 +1105,7 @@ __global__ void __launch_bounds__(kSolverThreads, WIDE ? 1 : 2) kmeans_solver_ke
   }
 
   // ---------------- outputs ----------------
-  if (lane == 0 && my_margin < __int_as_float(0x7f800000))
-    atomicMin(reinterpret_cast<unsigned*>(&st->min_margin), __float_as_uint(fmaxf(my_margin, 0.f)));
-  if (blockIdx.x == 0) {
-    for (int j = threadIdx.x; j <= k; j += blockDim.x) a.member_offsets[j] = s_offs[j];
-    const int nmem = s_offs[k];
-    for (int m = threadIdx.x; m < nmem; m += blockDim.x) a.members[m] = s_memb[m];
-    for (int j = threadIdx.x; j < k; j += blockDim.x) {
-      if (sizeof(TS) == 8) reinterpret_cast<double*>(a.ct_out)[j] = s_ctb[cur][j];
-      else reinterpret_cast<float*>(a.ct_out)[j] = (float)s_ctb[cur][j];
-    }
-    // chronological per-event order: the member lists minus the seed frames of re-seeded (empty) clusters.
-    // After rebuild_members_smem, cntw[w][j] holds warp w's running cursor == exclusive base + its count, so the
-    // last warp's cursor is the real member count of cluster j.
-    if (a.event_offsets && a.event_order && it > 0) {
-      const int nw = a.multiwarp_fill ? kSolverWarps : 1;
-      if (warp == 0) {
-        const int cpl = (k + 31) / 32;
-        const int j0 = min(k, lane * cpl), j1 = min(k, j0 + cpl);
-        int mine = 0;
-        for (int j = j0; j < j1; ++j) mine += s_cntw[(nw - 1) * k + j];
-        int inc = mine;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-          const int v = __shfl_up_sync(0xffffffffu, inc, o);
-          if (lane >= o) inc += v;
-        }
-        int run = inc - mine;
-        for (int j = j0; j < j1; ++j) {
-          s_cursor[j] = run;
-          a.event_offsets[j] = run;
-          run += s_cntw[(nw - 1) * k + j];
-        }
-        if (lane == 31) a.event_offsets[k] = inc;
-      }
-      __syncthreads();
-      for (int j = warp; j < k; j += kSolverWarps) {
-        const int n = s_cntw[(nw - 1) * k + j], src = s_offs[j], dst = s_cursor[j];
-        for (int e = lane; e < n; e += 32) a.event_order[dst + e] = s_memb[src + e];
-      }
-    }
-    if (threadIdx.x == 0) {
-      st->iterations = it;
-      st->converged = converged ? 1 : 0;
-      st->n_reseed_used = used;
-      st->last_shift = last_shift;
-    }
-  }
+  solver_outputs<TS>(a, s_offs, s_memb, s_ctb[cur], s_cntw, s_cursor, my_margin, it, converged, used, last_shift);
 }
 
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
