@@ -806,12 +806,35 @@ int csb_gram_extend(const void* x, int64_t T_old, int64_t T, int64_t K, double* 
     } else {
       d_units = reinterpret_cast<GramUnit*>(reinterpret_cast<char*>(workspace) +
                                             align_up((size_t)kr_max * p.n_tiles * kTile * kTile * sizeof(float), 256));
-      GramUnit* h_units = (GramUnit*)malloc(sizeof(GramUnit) * p.n_units);
-      int nu = 0;
-      plan_units(p.nb, p.b0, T, h_units, &nu, nullptr, &flips);
-      e = cudaMemcpyAsync(d_units, h_units, sizeof(GramUnit) * nu, cudaMemcpyHostToDevice, s);
-      cudaStreamSynchronize(s);  // pageable source buffer is freed below (large-T path only)
-      free(h_units);
+      // The plans of the first kPlanCache long-stream shapes a thread sees are kept on the host for good, so their copy can stay
+      // asynchronous: no stream synchronisation on the call path, and the call can be captured into a CUDA graph (the memcpy
+      // node re-reads the same, unchanged host table at every replay).  Further shapes (e.g. a cache that grows frame by
+      // frame) take the synchronous path: plan, copy, wait, free.
+      constexpr int kPlanCache = 16;
+      struct PlanCache { int64_t T, T_old; int n; GramUnit* units; GramFlipMask flips; };
+      static thread_local PlanCache cache[kPlanCache];
+      static thread_local int cache_n = 0;
+      PlanCache* pc = nullptr;
+      for (int i = 0; i < cache_n; ++i)
+        if (cache[i].T == T && cache[i].T_old == T_old) pc = &cache[i];
+      if (!pc && cache_n < kPlanCache) {
+        pc = &cache[cache_n++];
+        pc->T = T; pc->T_old = T_old;
+        pc->units = (GramUnit*)malloc(sizeof(GramUnit) * p.n_units);
+        pc->n = 0;
+        plan_units(p.nb, p.b0, T, pc->units, &pc->n, nullptr, &pc->flips);
+      }
+      if (pc) {
+        flips = pc->flips;
+        e = cudaMemcpyAsync(d_units, pc->units, sizeof(GramUnit) * pc->n, cudaMemcpyHostToDevice, s);
+      } else {
+        GramUnit* h_units = (GramUnit*)malloc(sizeof(GramUnit) * p.n_units);
+        int nu = 0;
+        plan_units(p.nb, p.b0, T, h_units, &nu, nullptr, &flips);
+        e = cudaMemcpyAsync(d_units, h_units, sizeof(GramUnit) * nu, cudaMemcpyHostToDevice, s);
+        cudaStreamSynchronize(s);  // pageable source buffer is freed right below
+        free(h_units);
+      }
       if (e != cudaSuccess) { set_error("gram: unit table copy: %s", cudaGetErrorString(e)); return CSB_ERR_CUDA; }
     }
 

@@ -649,10 +649,10 @@ def test_pipeline_odd_shapes(dev, T, P, D, k, C):
         assert torch.equal(packed[off[i]: off[i + 1]].reshape(-1, D), p1.events[i])
 
 
-def test_cuda_graph_replay(dev):
+@pytest.mark.parametrize("T,P,D", [(300, 6, 128), (2300, 2, 32)])  # the second: long-stream path (unit table upload, grid k-means++)
+def test_cuda_graph_replay(dev, T, P, D):
     """Both phases captured into CUDA graphs (cooperative solver launch included) and replayed: valid, self-consistent and
     reproducible results; the masks / ids agree with an eager run on the same assignments."""
-    T, P, D = 300, 6, 128
     k = math.ceil(T / 15)
     st = synthetic.make_stream(T, P, D, 91, C=16)
     ev, q = synthetic.make_embeddings(k, 256, 91)
