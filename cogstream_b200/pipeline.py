@@ -44,6 +44,11 @@ class StreamConfig:
     reseed_pool: int = 64
     compute_centroids: bool = True
     gather_events: bool = True
+    # independent kernels of one stream run on a side CUDA stream (parallel branches of the captured graphs): the Exp(1) /
+    # pool draws next to the Gram kernel, the representative selection next to centroid_gather, the relevance test next to
+    # the pixel-difference kernel.  Measured at config 2: one stream alone 0.609 -> 0.593 ms, but 6 streams in flight
+    # 0.31 -> 0.34 ms per stream (twice the CUDA streams fighting for the same SMs), so it is off unless latency is the goal.
+    parallel_branches: bool = False
 
     def clusters_for(self, T: int) -> int:
         if self.cluster_num is not None:
@@ -92,11 +97,26 @@ class StreamCompressor:
         self.side = torch.cuda.Stream(device=dev)
         self._ev_fork = torch.cuda.Event()
         self._ev_diff = torch.cuda.Event()
+        self._ev_branch = torch.cuda.Event()
+        self._ev_join = torch.cuda.Event()
         self._diff_pending = False
         self.order = self.ev_off = self.dist = self.reps = self.rep_counts = self.rep_flags = None
         self.cos = self.low = self.minor_list = None
         self.kept_index = self.n_kept = None
         self.out_ids = self.out_attention = self.n_ids_out = None
+
+    # ------------------------------------------------------------------------------------------
+    def _branch(self):
+        """Context manager: run the body on the side stream, ordered after everything enqueued so far on the current stream;
+        ``_join()`` makes the current stream wait for it.  Inside a graph capture this becomes a parallel branch."""
+        cur = torch.cuda.current_stream(self.device)
+        self._ev_branch.record(cur)
+        self.side.wait_event(self._ev_branch)
+        return torch.cuda.stream(self.side)
+
+    def _join(self):
+        self._ev_join.record(self.side)
+        torch.cuda.current_stream(self.device).wait_event(self._ev_join)
 
     # ------------------------------------------------------------------------------------------
     def phase1(self, features: torch.Tensor, timestamps: torch.Tensor, *, init_indices: Optional[torch.Tensor] = None,
@@ -111,30 +131,46 @@ class StreamCompressor:
             return
         T, k = self.T, self.k
         x2 = features.view(T, self.K)
-        ops.gram(x2, impl=self.cfg.gram_impl, out=self.G, workspace=self.gram_ws)
+        par = self.cfg.parallel_branches and pixel_values is None
         fork = pixel_values is not None
-        if fork:
-            self._ev_fork.record(torch.cuda.current_stream(self.device))
-        if init_indices is not None:
-            self.km.init_indices.copy_(init_indices, non_blocking=True)
-            n_given, noise = k, None
+
+        def draws():
+            nonlocal_out = {}
+            if init_indices is not None:
+                self.km.init_indices.copy_(init_indices, non_blocking=True)
+                nonlocal_out["n_given"], nonlocal_out["noise"] = k, None
+            else:
+                if first_index == "device":  # drawn by the CUDA generator: no host value baked into a captured graph
+                    torch.randint(0, T, (1,), device=self.device, out=self.km.init_indices[:1])
+                else:
+                    first = random.randint(0, T - 1) if first_index is None else first_index  # kmeans_with_time.py:41
+                    self.km.init_indices[:1].fill_(first)
+                nonlocal_out["n_given"] = 1
+                if exp_noise is not None:
+                    nonlocal_out["noise"] = exp_noise
+                else:
+                    nz = self.noise[: k - 1]
+                    if k > 1:
+                        nz.exponential_(1)  # one batched draw (the drop-in function draws per round like ATen does)
+                    nonlocal_out["noise"] = nz
+            pl = reseed_pool
+            if pl is None:
+                pl = self.pool
+                pl.random_(0, T)
+            nonlocal_out["pool"] = pl
+            return nonlocal_out
+
+        if par:  # the draws do not depend on the Gram matrix: a parallel branch
+            with self._branch():
+                d_ = draws()
+            ops.gram(x2, impl=self.cfg.gram_impl, out=self.G, workspace=self.gram_ws)
+            self._join()
         else:
-            if first_index == "device":  # drawn by the CUDA generator: no host value baked into a captured graph
-                torch.randint(0, T, (1,), device=self.device, out=self.km.init_indices[:1])
-            else:
-                first = random.randint(0, T - 1) if first_index is None else first_index  # kmeans_with_time.py:41
-                self.km.init_indices[:1].fill_(first)
-            n_given = 1
-            if exp_noise is not None:
-                noise = exp_noise
-            else:
-                noise = self.noise[: k - 1]
-                if k > 1:
-                    noise.exponential_(1)  # one batched draw (the drop-in function draws per round like ATen does)
-        pool = reseed_pool
-        if pool is None:
-            pool = self.pool
-            pool.random_(0, T)
+            ops.gram(x2, impl=self.cfg.gram_impl, out=self.G, workspace=self.gram_ws)
+            if fork:
+                self._ev_fork.record(torch.cuda.current_stream(self.device))
+            d_ = draws()
+        n_given, noise, pool = d_["n_given"], d_["noise"], d_["pool"]
         ops.kmeans_solve(self.G, timestamps, self.km, n_init_given=n_given, exp_noise=noise if k > 1 else None,
                          reseed_pool=pool, alpha=self.cfg.alpha, max_iteration=self.cfg.max_iteration, tol=self.cfg.tol)
         if fork:
@@ -144,17 +180,29 @@ class StreamCompressor:
             ops.pixel_diff(pixel_values, T, self.P, self.W, threshold=self.cfg.pixel_threshold, out=self.mask, stream=self.side)
             self._ev_diff.record(self.side)
             self._diff_pending = True
-        # one pass over X: fp32 centroids + the event-major packed token copy (the solver already emitted the order)
-        if self.centroids is not None or self.packed is not None:
-            ops.centroid_gather(x2, self.km.member_offsets, self.km.members, self.km.event_offsets, k, self.centroids, self.packed)
         assign = self.km.assignments
         self.order, self.ev_off = self.km.event_order, self.km.event_offsets
-        if T <= 256 * k:  # one fused launch (a warp per event, quadratic in the event size)
-            self.dist, self.reps, self.rep_counts, self.rep_flags = ops.representatives_gram(self.G, self.ev_off, self.order, k,
-                                                                                             self.cfg.n_representatives)
+
+        def representatives():
+            if T <= 256 * k:  # one fused launch (a warp per event, quadratic in the event size)
+                self.dist, self.reps, self.rep_counts, self.rep_flags = ops.representatives_gram(
+                    self.G, self.ev_off, self.order, k, self.cfg.n_representatives)
+            else:
+                self.dist = ops.dist_to_assigned_gram(self.G, assign, self.ev_off, self.order, k)
+                self.reps, self.rep_counts, self.rep_flags = ops.select_representatives(self.dist, assign, k,
+                                                                                      self.cfg.n_representatives)
+
+        gather = self.centroids is not None or self.packed is not None
+        if par and gather:  # the selection reads G and the CSR, the gather reads X: independent
+            with self._branch():
+                representatives()
+        # one pass over X: fp32 centroids + the event-major packed token copy (the solver already emitted the order)
+        if gather:
+            ops.centroid_gather(x2, self.km.member_offsets, self.km.members, self.km.event_offsets, k, self.centroids, self.packed)
+        if par and gather:
+            self._join()
         else:
-            self.dist = ops.dist_to_assigned_gram(self.G, assign, self.ev_off, self.order, k)
-            self.reps, self.rep_counts, self.rep_flags = ops.select_representatives(self.dist, assign, k, self.cfg.n_representatives)
+            representatives()
 
     # ------------------------------------------------------------------------------------------
     def phase2(self, features: torch.Tensor, events_repr: Optional[torch.Tensor], question: Optional[torch.Tensor],
@@ -162,6 +210,10 @@ class StreamCompressor:
         """events_repr [k, Dl], question [1, Dl] (frozen-LLM outputs); pixel_values [T*P*m*m, C]; ids [n_ids]."""
         T, P = self.T, self.P
         minor_flags = None
+        par = self.cfg.parallel_branches and self.gate and not self._diff_pending
+        if par:  # the raw pixel-difference mask does not depend on the relevance test: a parallel branch
+            with self._branch():
+                ops.pixel_diff(pixel_values, T, P, self.W, threshold=self.cfg.pixel_threshold, out=self.mask)
         if self.gate:
             self.cos, self.low, self.minor_flags, self.minor_list, self.n_minor = ops.relevance_minor(
                 question.view(-1), events_repr, self.km.assignments, self.rep_flags, self._ticket, self.cfg.relevance_threshold)
@@ -170,7 +222,9 @@ class StreamCompressor:
             self.minor_flags.zero_()
             self.n_minor.zero_()
             minor_flags = self.minor_flags
-        if self._diff_pending:
+        if par:
+            self._join()
+        elif self._diff_pending:
             torch.cuda.current_stream(self.device).wait_event(self._ev_diff)
             self._diff_pending = False
         else:

@@ -659,7 +659,8 @@ def test_cuda_graph_replay(dev, T, P, D):
     d = st.to(dev)
     evd, qd = ev.to(dev), q.to(dev)
     W = st.pixel_values.numel() // (T * P)
-    sc = StreamCompressor(T, P, D, W, st.input_ids.numel(), device=dev)
+    # parallel_branches: the independent kernels of a stream become parallel branches of the captured graphs
+    sc = StreamCompressor(T, P, D, W, st.input_ids.numel(), device=dev, cfg=StreamConfig(parallel_branches=(T == 300)))
     sc.capture(d.features, d.timestamps, evd, qd, d.pixel_values, d.input_ids, d.attention_mask)
     outs = []
     for _ in range(2):
