@@ -774,6 +774,129 @@ __global__ void __launch_bounds__(kScanThreads) ids_keep_kernel(const int64_t* _
 }
 
 // ------------------------------------------------------------------------------------------------
+// Fused variants (one cooperative launch instead of 2-3 dependent launches): the chunk counts are published, the CTAs meet at
+// a software grid barrier (co-residency guaranteed by the cooperative launch; the grid is ceil(n / 1024) CTAs) and every
+// CTA sums the counts of its predecessors itself.  Same outputs as the kernels above, bit for bit (integer work).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void scan_grid_sync(unsigned* counter, unsigned& target) {
+  __syncthreads();
+  if (gridDim.x > 1) {
+    if (threadIdx.x == 0) {
+      target += gridDim.x;
+      __threadfence();
+      atomicAdd(counter, 1u);
+      unsigned v;
+      do {
+        asm volatile("ld.acquire.gpu.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
+      } while (v < target);
+    }
+    __syncthreads();
+  }
+}
+
+// sum of counts[0 .. blockIdx.x) by the whole CTA (fixed tree; integers, so the order is irrelevant)
+__device__ __forceinline__ int chunk_prefix(const int* counts, int* wt, int* stotal) {
+  int v = 0;
+  for (int b = threadIdx.x; b < (int)blockIdx.x; b += blockDim.x) v += __ldcg(counts + b);
+  block_exclusive_scan(v, wt, stotal);
+  const int t = *stotal;
+  __syncthreads();
+  return t;
+}
+
+__global__ void __launch_bounds__(kScanThreads) ids_filter_coop_kernel(const int64_t* __restrict__ ids, int64_t n, int64_t image_tok,
+                                                                        const uint8_t* __restrict__ mask, int64_t n_mask,
+                                                                        int* __restrict__ img_counts, int* __restrict__ keep_counts,
+                                                                        unsigned* barrier, int64_t* __restrict__ n_out,
+                                                                        const int64_t* __restrict__ attn,
+                                                                        const int64_t* __restrict__ labels,
+                                                                        int64_t* __restrict__ o_ids, int64_t* __restrict__ o_attn,
+                                                                        int64_t* __restrict__ o_labels) {
+  __shared__ int wt[32];
+  __shared__ int stotal;
+  unsigned bar = 0;
+  const int64_t base = (int64_t)blockIdx.x * kScanChunk + threadIdx.x * kScanItems;
+  int64_t v[kScanItems];
+  int img[kScanItems], icnt = 0;
+#pragma unroll
+  for (int u = 0; u < kScanItems; ++u) {
+    v[u] = base + u < n ? ids[base + u] : 0;
+    img[u] = (base + u < n && v[u] == image_tok) ? 1 : 0;
+    icnt += img[u];
+  }
+  const int iex = block_exclusive_scan(icnt, wt, &stotal);
+  if (threadIdx.x == 0) img_counts[blockIdx.x] = stotal;
+  scan_grid_sync(barrier, bar);
+  int r = chunk_prefix(img_counts, wt, &stotal) + iex;  // rank of this thread's first <image> id
+  int keep[kScanItems], kcnt = 0;
+#pragma unroll
+  for (int u = 0; u < kScanItems; ++u) {
+    keep[u] = base + u < n ? 1 : 0;
+    if (img[u]) {
+      keep[u] = (r < n_mask && mask[r]) ? 1 : 0;
+      ++r;
+    }
+    kcnt += keep[u];
+  }
+  const int kex = block_exclusive_scan(kcnt, wt, &stotal);
+  const int ktot = stotal;
+  if (threadIdx.x == 0) keep_counts[blockIdx.x] = ktot;
+  scan_grid_sync(barrier, bar);
+  const int kpre = chunk_prefix(keep_counts, wt, &stotal);
+  if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) *n_out = (int64_t)kpre + ktot;
+  int p = kpre + kex;
+#pragma unroll
+  for (int u = 0; u < kScanItems; ++u) {
+    if (keep[u]) {
+      o_ids[p] = v[u];
+      if (attn) o_attn[p] = attn[base + u];
+      if (labels) o_labels[p] = labels[base + u];
+      ++p;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kScanThreads) compact_scan_coop_kernel(const uint8_t* __restrict__ mask, int64_t n,
+                                                                          int* __restrict__ counts, unsigned* barrier,
+                                                                          int64_t* __restrict__ n_kept, int32_t* __restrict__ pos,
+                                                                          int32_t* __restrict__ kept_index) {
+  __shared__ int wt[32];
+  __shared__ int stotal;
+  unsigned bar = 0;
+  const int64_t base = (int64_t)blockIdx.x * kScanChunk + threadIdx.x * kScanItems;
+  int f[kScanItems], cnt = 0;
+#pragma unroll
+  for (int u = 0; u < kScanItems; ++u) {
+    f[u] = (base + u < n && mask[base + u]) ? 1 : 0;
+    cnt += f[u];
+  }
+  const int ex = block_exclusive_scan(cnt, wt, &stotal);
+  const int tot = stotal;
+  if (threadIdx.x == 0) counts[blockIdx.x] = tot;
+  scan_grid_sync(barrier, bar);
+  const int pre = chunk_prefix(counts, wt, &stotal);
+  if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) *n_kept = (int64_t)pre + tot;
+  int lp = pre + ex;
+#pragma unroll
+  for (int u = 0; u < kScanItems; ++u) {
+    if (base + u < n) {
+      pos[base + u] = lp;
+      if (f[u]) kept_index[lp++] = (int32_t)(base + u);
+    }
+  }
+}
+
+// number of CTAs of `kernel` (kScanThreads threads, no dynamic shared memory) that can be co-resident on the current device
+template <typename K>
+static int coop_capacity(K kernel) {
+  int per_sm = 0, dev = 0, sms = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kScanThreads, 0) != cudaSuccess) return 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  return per_sm * sms;
+}
+
+// ------------------------------------------------------------------------------------------------
 // input-id filtering with position-id rebuild (training-side path, rare): single CTA.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024) filter_ids_kernel(const int64_t* __restrict__ ids, int64_t n, int64_t image_tok,
@@ -1041,12 +1164,23 @@ int csb_compact_tokens(const void* x, int64_t T, int64_t P, int64_t D, const uin
                                                  2 * align_up(sizeof(int32_t) * (size_t)(nchunks + 1), 256));
   cudaError_t e = cudaMemsetAsync(ticket, 0, 4, s);
   if (e != cudaSuccess) { set_error("compact_tokens: memset: %s", cudaGetErrorString(e)); return CSB_ERR_CUDA; }
-  mask_chunk_count_kernel<<<nchunks, kScanThreads, 0, s>>>(mask, n, counts, nchunks, ticket, n_kept);
-  int st = check_launch("mask_chunk_count");
-  if (st) return st;
-  compact_scatter_kernel<<<nchunks, kScanThreads, 0, s>>>(mask, n, counts, pos, kept_index);
-  st = check_launch("compact_scatter");
-  if (st) return st;
+  int st;
+  static thread_local int cap_compact = -1;
+  if (cap_compact < 0) cap_compact = coop_capacity(compact_scan_coop_kernel);
+  if (nchunks <= cap_compact && !getenv("CSB_NO_COOP_SCAN")) {  // count + barrier + scatter in one cooperative launch
+    int64_t n_arg = n;
+    void* args[] = {(void*)&mask, (void*)&n_arg, (void*)&counts, (void*)&ticket, (void*)&n_kept, (void*)&pos, (void*)&kept_index};
+    e = cudaLaunchCooperativeKernel((const void*)compact_scan_coop_kernel, dim3((unsigned)nchunks), dim3(kScanThreads), args, 0, s);
+    if (e != cudaSuccess) { set_error("compact_tokens: cooperative launch: %s", cudaGetErrorString(e)); return CSB_ERR_CUDA; }
+    count_launch(1);
+  } else {
+    mask_chunk_count_kernel<<<nchunks, kScanThreads, 0, s>>>(mask, n, counts, nchunks, ticket, n_kept);
+    st = check_launch("mask_chunk_count");
+    if (st) return st;
+    compact_scatter_kernel<<<nchunks, kScanThreads, 0, s>>>(mask, n, counts, pos, kept_index);
+    st = check_launch("compact_scatter");
+    if (st) return st;
+  }
   st = csb_gather_rows(x, D * 2, kept_index, 0, n_kept, n, out, stream);
   if (st) return st;
   if (pool_flags) {
@@ -1082,6 +1216,17 @@ int csb_filter_ids(const int64_t* input_ids, int64_t n_ids, int64_t image_token_
     unsigned* ticket = reinterpret_cast<unsigned*>(reinterpret_cast<char*>(keep_prefix) + cbytes);
     cudaError_t e = cudaMemsetAsync(ticket, 0, 4, s);
     if (e != cudaSuccess) { set_error("filter_ids: memset: %s", cudaGetErrorString(e)); return CSB_ERR_CUDA; }
+    static thread_local int cap_ids = -1;
+    if (cap_ids < 0) cap_ids = coop_capacity(ids_filter_coop_kernel);
+    if (nchunks <= cap_ids && !getenv("CSB_NO_COOP_SCAN")) {  // the three dependent passes in one cooperative launch
+      void* args[] = {(void*)&input_ids, (void*)&n_ids, (void*)&image_token_index, (void*)&mask, (void*)&n_mask, (void*)&img_prefix,
+                      (void*)&keep_prefix, (void*)&ticket, (void*)&n_out, (void*)&attention_mask, (void*)&labels, (void*)&out_ids,
+                      (void*)&out_attention_mask, (void*)&out_labels};
+      e = cudaLaunchCooperativeKernel((const void*)ids_filter_coop_kernel, dim3((unsigned)nchunks), dim3(kScanThreads), args, 0, s);
+      if (e != cudaSuccess) { set_error("filter_ids: cooperative launch: %s", cudaGetErrorString(e)); return CSB_ERR_CUDA; }
+      count_launch(1);
+      return CSB_OK;
+    }
     ids_image_count_kernel<<<nchunks, kScanThreads, 0, s>>>(input_ids, n_ids, image_token_index, img_prefix, nchunks, ticket);
     int st = check_launch("ids_image_count");
     if (st) return st;
