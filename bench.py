@@ -405,7 +405,9 @@ def _stage_times(sc, d, ev_d, q_d, reps=5):
                                                         sc.centroids, sc.packed)),
         ("representatives", reps_),
         ("relevance_minor", relevance),
-        ("pixel_mask", lambda: ops.pixel_mask(d.pixel_values, T, P, sc.W, minor_flags=state["mflags"], out=sc.mask)),
+        # the two launches of csb_pixel_mask timed separately: the HBM-bound difference kernel and the tiny per-frame fix-up
+        ("pixel_diff", lambda: ops.pixel_diff(d.pixel_values, T, P, sc.W, out=sc.mask)),
+        ("mask_finalize", lambda: ops.mask_finalize(sc.mask, T, P, minor_flags=state["mflags"])),
         ("compact_tokens", lambda: ops.compact_tokens(d.features, T, P, sc.mask, state["mflags"], out=sc.out, workspace=sc.compact_ws)),
         ("filter_ids", lambda: ops.filter_ids(d.input_ids, sc.image_token_index, sc.mask, d.attention_mask)),
     ]
@@ -479,7 +481,7 @@ def _roofline(stages, sc, d, ms_step=None, ms_single=None):
     alg_bytes = {
         "gram": BX,
         "centroid_gather": 2 * BX + 4 * k * K,
-        "pixel_mask": 2 * T * P * sc.W,
+        "pixel_diff": 2 * T * P * sc.W,
         "compact_tokens": 2 * 2 * n_kept * D + 2 * n_minor * P * D,
     }
     hbm = {n: dict(ms=stages[n], gbs=alg_bytes[n] / (stages[n] * 1e-3) / 1e9, frac=alg_bytes[n] / (stages[n] * 1e-3) / 1e9 / pk["hbm_gbs"])
@@ -498,7 +500,9 @@ def _roofline(stages, sc, d, ms_step=None, ms_single=None):
                     frac=gram_tf / pk["bf16_tflops"], traffic=traffic.get("gram"),
                     hbm_view=dict(achieved=hbm["gram"]["gbs"], peak=pk["hbm_gbs"], unit="GB/s", frac=hbm["gram"]["frac"]))
     elif dom in hbm:
-        roof = dict(bound="hbm", kernel=dom, achieved=hbm[dom]["gbs"], peak=pk["hbm_gbs"], unit="GB/s", frac=hbm[dom]["frac"],
+        kname = {"pixel_diff": "pixel_diff_tma_kernel", "centroid_gather": "centroid_gather_kernel",
+                 "compact_tokens": "compact_scan_coop_kernel + gather_rows_kernel + pool_emit_kernel"}.get(dom, dom)
+        roof = dict(bound="hbm", kernel=kname, stage=dom, achieved=hbm[dom]["gbs"], peak=pk["hbm_gbs"], unit="GB/s", frac=hbm[dom]["frac"],
                     traffic=traffic.get(dom))
     roof["peaks"] = pk["source"]
     roof["algorithmic_bytes"] = alg_bytes.get(dom)
