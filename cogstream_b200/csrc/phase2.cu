@@ -151,22 +151,33 @@ __global__ void __launch_bounds__(256) reps_gram_kernel(const double* __restrict
   const int beg = ev_off[j], n = ev_off[j + 1] - beg;
   const int32_t* mem = order + beg;
   int64_t* out = reps + (int64_t)j * n_rep;
-  // distances (also for small events: the dist output is complete)
-  double qpart = 0.0;
-  for (int a = lane; a < n; a += 32) {
+  // distances (also for small events: the dist output is complete).  The row sums of the first two rows of a lane (events of up
+  // to 64 frames: all of them) stay in registers for the second pass; longer events recompute the rest.
+  double qpart = 0.0, rs_keep[2] = {0.0, 0.0};
+  for (int a = lane, it = 0; a < n; a += 32, ++it) {
     const double* ga = G + (int64_t)mem[a] * ldg;
     double rs = 0.0;
-    for (int b = 0; b < n; ++b) rs += ga[mem[b]];
+    int b = 0;
+    for (; b + 4 <= n; b += 4) {  // 4 independent loads in flight, added in member order
+      const double g0 = ga[mem[b]], g1 = ga[mem[b + 1]], g2 = ga[mem[b + 2]], g3 = ga[mem[b + 3]];
+      rs += g0; rs += g1; rs += g2; rs += g3;
+    }
+    for (; b < n; ++b) rs += ga[mem[b]];
+    if (it < 2) rs_keep[it] = rs;
     qpart += rs;
   }
   const double nn = (double)n;
   const double q = warp_sum(qpart) / (nn * nn);
-  // second pass recomputes the (short) row sums instead of parking fp64 values: n is ~T/k
-  for (int a = lane; a < n; a += 32) {
+  for (int a = lane, it = 0; a < n; a += 32, ++it) {
     const int m = mem[a];
     const double* ga = G + (int64_t)m * ldg;
-    double rs = 0.0;
-    for (int b = 0; b < n; ++b) rs += ga[mem[b]];
+    double rs;
+    if (it < 2) {
+      rs = it == 0 ? rs_keep[0] : rs_keep[1];
+    } else {
+      rs = 0.0;
+      for (int b = 0; b < n; ++b) rs += ga[mem[b]];
+    }
     const double d2 = ga[m] - 2.0 * (rs / nn) + q;
     dist[m] = (float)sqrt(d2 > 0.0 ? d2 : 0.0);
     rep_flags[m] = 0;
