@@ -83,6 +83,8 @@ def test_gram_long_stream_direct_write(dev, T, K):
     G2 = ops.gram(x, impl=512)
     assert torch.equal(G, G2)
     assert torch.equal(G, G.T)
+    G3 = ops.gram(x, impl=1024)  # opt-in 2-SM UMMA kernel (cta_group::2 pairs): the same bits
+    assert torch.equal(G, G3)
     idx = torch.randperm(T, generator=g)[:96].to(dev)
     sub = x[idx].double()
     ref = sub @ sub.T
