@@ -929,3 +929,27 @@ def test_kmeanspp_long_stream_grid_init(dev, monkeypatch, T, P, D, seed):
         random.randint = orig
     assert res["1"][0] == info_o.init_indices
     assert torch.equal(res["1"][1], as_o) and res["1"][2] == info_o.iterations
+
+
+def test_scan_fallback_paths_agree(dev, monkeypatch):
+    """The compaction / id-filter scans are single cooperative launches; grids beyond co-residency use the multi-launch
+    "last block done" scans (forced here with CSB_NO_COOP_SCAN): identical outputs."""
+    T, P, D = 333, 7, 64
+    st = synthetic.make_stream(T, P, D, 5, C=6)
+    d = st.to(dev)
+    g = torch.Generator().manual_seed(9)
+    mask = (torch.rand(T * P, generator=g) < 0.35).to(torch.uint8).to(dev)
+    flags = (torch.rand(T, generator=g) < 0.2).to(torch.uint8).to(dev)
+    outs = []
+    for force in (False, True):
+        if force:
+            monkeypatch.setenv("CSB_NO_COOP_SCAN", "1")
+        o, kept, nk = ops.compact_tokens(d.features, T, P, mask, flags)
+        ids, am, _, _, no = ops.filter_ids(d.input_ids, synthetic.IMAGE_TOKEN_INDEX, mask, d.attention_mask)
+        n1, n2 = int(nk.item()), int(no.item())
+        outs.append((n1, n2, o[:n1].clone(), kept[:n1].clone(), ids[:n2].clone(), am[:n2].clone()))
+    monkeypatch.delenv("CSB_NO_COOP_SCAN")
+    a, b = outs
+    assert a[0] == b[0] and a[1] == b[1] and a[0] == int(mask.sum())
+    for x, y in zip(a[2:], b[2:]):
+        assert torch.equal(x, y)
