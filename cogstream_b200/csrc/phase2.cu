@@ -643,11 +643,42 @@ __global__ void __launch_bounds__(kScanThreads) compact_scatter_kernel(const uin
 // in flight, then group 0 adds the four partial sums in order: fp32 accumulation, one round-to-nearest to bf16.
 constexpr int kPoolGroups = 4;
 
+// Blocks [0, T) pool one flagged frame each; with `kept_index` given, blocks [T, gridDim.x) copy the kept rows (the row gather
+// of the compaction) in the same launch -- the small gather rides under the HBM-bound pooling pass.  The gather blocks skip
+// token 0 of a pooled frame: that output row belongs to the pooling block.
 __global__ void __launch_bounds__(1024) pool_emit_kernel(const uint4* __restrict__ x, int P, int Dv,
                                                          const uint8_t* __restrict__ pool_flags,
                                                          const uint8_t* __restrict__ mask, const int32_t* __restrict__ pos,
-                                                         uint4* __restrict__ out) {
+                                                         uint4* __restrict__ out, int T, const int32_t* __restrict__ kept_index,
+                                                         const int64_t* __restrict__ n_kept) {
   extern __shared__ float pool_part[];  // [kPoolGroups - 1][blockDim.x][8]
+  if ((int)blockIdx.x >= T) {
+    const int64_t nthreads = (int64_t)blockDim.x * blockDim.y;
+    const int64_t nblk = gridDim.x - T;
+    const int64_t tid = ((int64_t)blockIdx.x - T) * nthreads + threadIdx.y * blockDim.x + threadIdx.x;
+    const int64_t total = *n_kept * Dv;
+    const int64_t stride = nblk * nthreads;
+    for (int64_t g0 = tid; g0 < total; g0 += 4 * stride) {
+      uint4 v[4];
+      bool ok[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int64_t g = g0 + u * stride;
+        ok[u] = false;
+        if (g < total) {
+          const int64_t r = g / Dv, c = g - r * Dv;
+          const int tok = kept_index[r];
+          const int f = tok / P;
+          ok[u] = !(pool_flags[f] && tok == f * P);
+          if (ok[u]) v[u] = ldg_stream(x + (int64_t)tok * Dv + c);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (ok[u]) out[g0 + u * stride] = v[u];
+    }
+    return;
+  }
   const int64_t t = blockIdx.x;
   if (!pool_flags[t] || !mask[t * P]) return;
   const int g = threadIdx.y;
@@ -1192,16 +1223,19 @@ int csb_compact_tokens(const void* x, int64_t T, int64_t P, int64_t D, const uin
     st = check_launch("compact_scatter");
     if (st) return st;
   }
-  st = csb_gather_rows(x, D * 2, kept_index, 0, n_kept, n, out, stream);
-  if (st) return st;
   if (pool_flags) {
+    // pooled tokens + the row gather of the kept tokens in ONE launch (the gather blocks follow the T pooling blocks)
     const int Dv = (int)(D / 8);
     const int tx = Dv >= 256 ? 256 : ((Dv + 31) / 32) * 32;
     const size_t smem = (size_t)(kPoolGroups - 1) * tx * 8 * sizeof(float);
-    pool_emit_kernel<<<(unsigned)T, dim3(tx, kPoolGroups), smem, s>>>((const uint4*)x, (int)P, Dv, pool_flags, mask, pos, (uint4*)out);
-    st = check_launch("pool_emit");
+    int64_t gblocks = (n * Dv + (int64_t)tx * kPoolGroups * 4 - 1) / ((int64_t)tx * kPoolGroups * 4);
+    if (gblocks > kNumSMs * 4) gblocks = kNumSMs * 4;
+    if (gblocks < 1) gblocks = 1;
+    pool_emit_kernel<<<(unsigned)(T + gblocks), dim3(tx, kPoolGroups), smem, s>>>((const uint4*)x, (int)P, Dv, pool_flags, mask, pos,
+                                                                                   (uint4*)out, (int)T, kept_index, n_kept);
+    return check_launch("pool_emit");
   }
-  return st;
+  return csb_gather_rows(x, D * 2, kept_index, 0, n_kept, n, out, stream);
 }
 
 int csb_filter_ids(const int64_t* input_ids, int64_t n_ids, int64_t image_token_index, const uint8_t* mask, int64_t n_mask,
