@@ -895,14 +895,15 @@ def test_drop_in_call_site_matches_reference(dev, fused_embed):
     assert r1[0] is ids1 and r1[4] is None
 
 
-@pytest.mark.parametrize("T,P,D,seed", [(2300, 2, 32, 0), (4100, 1, 64, 1)])
-def test_kmeanspp_long_stream_grid_init(dev, monkeypatch, T, P, D, seed):
+@pytest.mark.parametrize("T,P,D,seed,ts_dtype", [(2300, 2, 32, 0, torch.float64), (4100, 1, 64, 1, torch.float64),
+                                                 (2200, 2, 32, 2, torch.float32)])  # the last: float32 timestamps (WIDE<float>)
+def test_kmeanspp_long_stream_grid_init(dev, monkeypatch, T, P, D, seed, ts_dtype):
     """Long streams (T > 2048) run k-means++ on a cooperative grid; the centres, assignments and iteration count equal the
     single-CTA kernel's and the CPU oracle's for the same injected Exp(1) noise."""
     import os
     k = math.ceil(T / 15)
     feats, _ = synthetic.make_features(T, P, D, seed)
-    ts = torch.arange(T, dtype=torch.float64) / 2.0
+    ts = (torch.arange(T, dtype=torch.float64) / 2.0).to(ts_dtype)
     g = torch.Generator().manual_seed(seed + 5)
     noise = torch.empty(k - 1, T).exponential_(1, generator=g)
     first = int(torch.randint(0, T, (1,), generator=g))
