@@ -662,11 +662,14 @@ __global__ void __launch_bounds__(160, 1) gram_tc_kernel(const __grid_constant__
       // warp write 32 consecutive floats = one full 128-byte line per store instruction (row-major float4 stores would touch
       // 32 different lines per instruction and serialise in the LSU: measured 10 us for 38 MB).  The reduce kernel undoes it.
       const int row = warp * 32 + lane;
+      const bool direct = Gout != nullptr && seg == nseg - 1;
+      float* stile = reinterpret_cast<float*>(smem);  // [128][129] fp32 staging tile (the operand ring is idle by now)
       for (int t = 0; t < n_ut; ++t) {
         float* out = partial + ((int64_t)kr * n_tiles + unit.tile_id[t]) * (kTile * kTile) + row;
         const bool row_ok = row < unit.tile_rows[t];
         const int ncols = unit.tile_cols[t];
         const int ncb = (ncols + 31) >> 5;  // 32-column groups that hold valid columns
+        const bool diag = unit.tile_ablk[t] == unit.tile_bblk[t];
 #pragma unroll 1
         for (int cb = 0; cb < ncb; ++cb) {
           uint32_t r[32];
@@ -687,27 +690,39 @@ __global__ void __launch_bounds__(160, 1) gram_tc_kernel(const __grid_constant__
 #pragma unroll
             for (int j = 0; j < 32; ++j) val[j] = __fadd_rn(prev[j], __uint_as_float(r[j]));
           }
-          if (Gout && seg == nseg - 1) {
+          if (direct) {
             // single K range (long streams): the last drain writes G itself -- both triangles -- and no reduce kernel runs.
-            // Same value the reduce kernel would produce: (double) of the fp32 segment sum.
+            // Same value the reduce kernel would produce: (double) of the fp32 segment sum.  The mirror triangle goes out
+            // straight from registers (for a fixed column the warp's 32 rows are 32 consecutive doubles); the other
+            // orientation is staged through shared memory so that it is written in full 256-byte runs as well (one thread
+            // per row would touch 32 lines per store instruction).
             const int64_t ga = (int64_t)unit.tile_ablk[t] * kTile + row;
             const int64_t gb0 = (int64_t)unit.tile_bblk[t] * kTile + cb * 32;
-            const bool diag = unit.tile_ablk[t] == unit.tile_bblk[t];
-            double* grow = Gout + ga * ldg + gb0;  // 32 consecutive doubles of this thread's row
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (cb * 32 + j < ncols) grow[j] = (double)val[j];
             if (!diag) {
-              double* gcol = Gout + gb0 * ldg + ga;  // mirror: for a fixed column the warp writes 32 consecutive doubles
+              double* gcol = Gout + gb0 * ldg + ga;
 #pragma unroll
               for (int j = 0; j < 32; ++j)
                 if (cb * 32 + j < ncols) gcol[(int64_t)j * ldg] = (double)val[j];
             }
+            float* srow = stile + row * (kTile + 1) + cb * 32;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) srow[j] = val[j];  // bank = (row + column) mod 32: conflict-free
           } else {
 #pragma unroll
             for (int j = 0; j < 32; ++j)
               if (cb * 32 + j < ncols) o[j * kTile] = val[j];
           }
+        }
+        if (direct) {
+          asm volatile("bar.sync 1, 128;" ::: "memory");  // the tile is staged
+          const int nrows = unit.tile_rows[t];
+          double* gbase = Gout + ((int64_t)unit.tile_ablk[t] * kTile) * ldg + (int64_t)unit.tile_bblk[t] * kTile;
+          for (int rr = warp; rr < nrows; rr += 4) {
+            const float* sr = stile + rr * (kTile + 1);
+            double* grow = gbase + (int64_t)rr * ldg;
+            for (int c = lane; c < ncols; c += 32) grow[c] = (double)sr[c];
+          }
+          asm volatile("bar.sync 1, 128;" ::: "memory");  // before the next tile overwrites the staging buffer
         }
       }
       if (seg + 1 < nseg) {
