@@ -896,7 +896,8 @@ def test_drop_in_call_site_matches_reference(dev, fused_embed):
 
 
 @pytest.mark.parametrize("T,P,D,seed,ts_dtype", [(2300, 2, 32, 0, torch.float64), (4100, 1, 64, 1, torch.float64),
-                                                 (2200, 2, 32, 2, torch.float32)])  # the last: float32 timestamps (WIDE<float>)
+                                                 (2200, 2, 32, 2, torch.float32),  # float32 timestamps (WIDE<float>)
+                                                 (2300, 8, 1152, 3, torch.float64)])  # K = 9216: two accumulator segments
 def test_kmeanspp_long_stream_grid_init(dev, monkeypatch, T, P, D, seed, ts_dtype):
     """Long streams (T > 2048) run k-means++ on a cooperative grid; the centres, assignments and iteration count equal the
     single-CTA kernel's and the CPU oracle's for the same injected Exp(1) noise."""
