@@ -49,7 +49,7 @@ class StreamCache:
 
     def cluster(self, cluster_num: Optional[int] = None, *, alpha=2, max_iteration=30, tol=1e-4,
                 init_indices: Optional[Sequence[int]] = None, first_index: Optional[int] = None,
-                exp_noise: Optional[torch.Tensor] = None, reseed_pool: Optional[torch.Tensor] = None):
+                exp_noise: Optional[torch.Tensor] = None, reseed_pool: Optional[torch.Tensor] = None, validate: bool = False):
         """k-means over all cached frames on the cached Gram matrix (k = ceil(T/15) by default, cogreasoner_chat.py:280).
         Returns ``(KMeansBuffers, k)``: assignments, centre CSR, event order etc. stay on the device (no host sync)."""
         T = self.T
@@ -67,9 +67,14 @@ class StreamCache:
             n_given = 1
             if k > 1:
                 noise = exp_noise if exp_noise is not None else torch.empty(k - 1, T, dtype=torch.float32, device=self.device).exponential_(1)
-        pool = reseed_pool if reseed_pool is not None else torch.randint(0, T, (64,), dtype=torch.int64, device=self.device)
+        # default pool = the strict upper bound on draws (k - 1 degenerate init rounds + k empty clusters per iteration): it
+        # cannot run out.  With a caller-supplied pool, `validate=True` reads the status back (one sync) and raises on overflow.
+        pool = reseed_pool if reseed_pool is not None else \
+            torch.randint(0, T, (k * (int(max_iteration) + 1),), dtype=torch.int64, device=self.device)
         ops.kmeans_solve(self.gram, self.ts[:T], buf, n_init_given=n_given, exp_noise=noise, reseed_pool=pool, alpha=float(alpha),
                          max_iteration=int(max_iteration), tol=float(tol))
+        if validate and ops.decode_status(buf.status)["reseed_overflow"]:
+            raise RuntimeError("StreamCache.cluster: reseed_pool exhausted; the clustering is not the reference's")
         return buf, k
 
     def centroids(self, buf: ops.KMeansBuffers, k: int) -> torch.Tensor:

@@ -29,26 +29,30 @@ int check_launch(const char* what) {
 }
 
 int device_ok() {
-  // cached per device id; the kernels are compiled for sm_100a only and there is no fallback
-  static int cached_dev = -1, cached_status = CSB_ERR_ARCH;
+  // cached per host thread and device id; the kernels are compiled for sm_100a only (an arch-specific cubin does not load on
+  // other 10.x parts such as sm_103) and there is no fallback
+  static thread_local int cached_dev = -1, cached_status = CSB_ERR_ARCH;
   int dev = -1;
   cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess) {
     set_error("cudaGetDevice: %s (a CUDA device is required; there is no CPU fallback)", cudaGetErrorString(e));
     return CSB_ERR_CUDA;
   }
-  if (dev == cached_dev) return cached_status;
+  if (dev == cached_dev) {
+    if (cached_status != CSB_OK) set_error("device %d is not sm_100; cogstream_b200 kernels are built for sm_100a only", dev);
+    return cached_status;
+  }
   int major = 0, minor = 0;
   cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
   cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev);
-  cached_dev = dev;
-  if (major == 10) {
-    cached_status = CSB_OK;
-  } else {
+  int status = CSB_OK;
+  if (!(major == 10 && minor == 0)) {
     set_error("device %d is sm_%d%d; cogstream_b200 kernels are built for sm_100a only", dev, major, minor);
-    cached_status = CSB_ERR_ARCH;
+    status = CSB_ERR_ARCH;
   }
-  return cached_status;
+  cached_status = status;
+  cached_dev = dev;
+  return status;
 }
 
 }  // namespace csb

@@ -23,7 +23,7 @@ import torch
 
 from . import ops
 
-STATS_FIELDS = ("T", "k", "iterations", "n_reseed", "n_minor", "n_kept", "n_ids_out", "converged")
+STATS_FIELDS = ("T", "k", "iterations", "n_reseed", "n_minor", "n_kept", "n_ids_out", "converged", "reseed_overflow")
 
 
 @dataclass
@@ -41,7 +41,11 @@ class StreamConfig:
     tol: float = 1e-4
     cluster_num: Optional[int] = None  # override k = ceil(T / frames_per_event) and its gate
     gram_impl: int = 0
-    reseed_pool: int = 64
+    # entries of the device-drawn re-seed pool (random.randint draws of kmeans_with_time.py:57 / :118).  None = the strict upper
+    # bound k * (max_iteration + 1): at most k - 1 degenerate init rounds plus k empty clusters per iteration, so the pool can
+    # never run out.  A caller-supplied smaller pool that does run out sets `reseed_overflow` in the stats row and makes
+    # results() raise (the kernel has substituted frame 0, which is not what the reference would have drawn).
+    reseed_pool: Optional[int] = None
     compute_centroids: bool = True
     gather_events: bool = True
     # independent kernels of one stream run on a side CUDA stream (parallel branches of the captured graphs): the Exp(1) /
@@ -82,10 +86,11 @@ class StreamCompressor:
             self.gram_ws = torch.empty(ops.gram_workspace_bytes(T, self.K), dtype=torch.uint8, device=dev)
             self.km = ops.KMeansBuffers(T, k, ts_dtype, dev)
             self.noise = torch.empty(max(k - 1, 1), T, dtype=torch.float32, device=dev)
-            self.pool = torch.zeros(self.cfg.reseed_pool, dtype=torch.int64, device=dev)
+            n_pool = self.cfg.reseed_pool if self.cfg.reseed_pool is not None else k * (self.cfg.max_iteration + 1)
+            self.pool = torch.zeros(max(1, n_pool), dtype=torch.int64, device=dev)
             self.centroids = torch.empty(k, self.K, dtype=torch.float32, device=dev) if self.cfg.compute_centroids else None
             self.packed = torch.empty(T, self.K, dtype=torch.bfloat16, device=dev) if self.cfg.gather_events else None
-        self._row_base = torch.tensor([T, self.k if self.gate else 0, 0, 0, 0, 0, 0, 0], dtype=torch.int64, device=dev)
+        self._row_base = torch.tensor([T, self.k if self.gate else 0, 0, 0, 0, 0, 0, 0, 0], dtype=torch.int64, device=dev)
         self._ticket = torch.zeros(1, dtype=torch.int32, device=dev)
         self.minor_flags = torch.zeros(T, dtype=torch.uint8, device=dev)
         self.n_minor = torch.zeros(1, dtype=torch.int64, device=dev)
@@ -121,8 +126,11 @@ class StreamCompressor:
     # ------------------------------------------------------------------------------------------
     def phase1(self, features: torch.Tensor, timestamps: torch.Tensor, *, init_indices: Optional[torch.Tensor] = None,
                first_index: Optional[int] = None, exp_noise: Optional[torch.Tensor] = None,
-               reseed_pool: Optional[torch.Tensor] = None, pixel_values: Optional[torch.Tensor] = None) -> None:
+               reseed_pool: Optional[torch.Tensor] = None, pixel_values: Optional[torch.Tensor] = None,
+               gram: Optional[torch.Tensor] = None) -> None:
         """features [T*P, D] bf16, timestamps [T] on the device.  Enqueues everything; returns at once.
+        ``gram`` (optional): a ready [T,T] fp64 Gram matrix of these frames (e.g. ``StreamCache.gram``, kept up to date
+        incrementally); the Gram kernel is then skipped.
         ``pixel_values`` (optional, the same tensor phase2 gets): start the raw pixel-difference mask now, on the
         side stream, overlapped with the solver.  Measured on B200 (scripts/overlap_probe.py): the HBM-saturating
         difference kernel stretches the latency-bound solver by about as much as it saves, so bench.py leaves it off;
@@ -160,18 +168,22 @@ class StreamCompressor:
             nonlocal_out["pool"] = pl
             return nonlocal_out
 
+        G = self.G if gram is None else gram
         if par:  # the draws do not depend on the Gram matrix: a parallel branch
             with self._branch():
                 d_ = draws()
-            ops.gram(x2, impl=self.cfg.gram_impl, out=self.G, workspace=self.gram_ws)
+            if gram is None:
+                ops.gram(x2, impl=self.cfg.gram_impl, out=self.G, workspace=self.gram_ws)
             self._join()
         else:
-            ops.gram(x2, impl=self.cfg.gram_impl, out=self.G, workspace=self.gram_ws)
+            if gram is None:
+                ops.gram(x2, impl=self.cfg.gram_impl, out=self.G, workspace=self.gram_ws)
             if fork:
                 self._ev_fork.record(torch.cuda.current_stream(self.device))
             d_ = draws()
         n_given, noise, pool = d_["n_given"], d_["noise"], d_["pool"]
-        ops.kmeans_solve(self.G, timestamps, self.km, n_init_given=n_given, exp_noise=noise if k > 1 else None,
+        self._G_used = G
+        ops.kmeans_solve(G, timestamps, self.km, n_init_given=n_given, exp_noise=noise if k > 1 else None,
                          reseed_pool=pool, alpha=self.cfg.alpha, max_iteration=self.cfg.max_iteration, tol=self.cfg.tol)
         if fork:
             # enqueued AFTER the cooperative solver so its CTAs become resident first; the HBM-bound difference kernel then
@@ -186,9 +198,9 @@ class StreamCompressor:
         def representatives():
             if T <= 256 * k:  # one fused launch (a warp per event, quadratic in the event size)
                 self.dist, self.reps, self.rep_counts, self.rep_flags = ops.representatives_gram(
-                    self.G, self.ev_off, self.order, k, self.cfg.n_representatives)
+                    G, self.ev_off, self.order, k, self.cfg.n_representatives)
             else:
-                self.dist = ops.dist_to_assigned_gram(self.G, assign, self.ev_off, self.order, k)
+                self.dist = ops.dist_to_assigned_gram(G, assign, self.ev_off, self.order, k)
                 self.reps, self.rep_counts, self.rep_flags = ops.select_representatives(self.dist, assign, k,
                                                                                       self.cfg.n_representatives)
 
@@ -270,6 +282,7 @@ class StreamCompressor:
             row[2:3] = st[0:1]
             row[3:4] = st[2:3]
             row[7:8] = st[1:2]
+            row[8:9] = st[4:5]
         row[4:5] = self.n_minor
         row[5:6] = self.n_kept
         row[6:7] = self.n_ids_out
@@ -285,8 +298,13 @@ class StreamCompressor:
         if self.gate:
             nm = int(self.n_minor.item())
             cnt = self.rep_counts.tolist()
+            status = ops.decode_status(self.km.status)
+            if status["reseed_overflow"]:
+                raise RuntimeError(
+                    f"StreamCompressor: the re-seed pool ran out ({status['n_reseed_used']} draws needed); the clustering is not the "
+                    "reference's.  Pass a larger reseed_pool (StreamConfig.reseed_pool=None sizes it to the upper bound)")
             res.update(
-                status=ops.decode_status(self.km.status), assignments=self.km.assignments, init_indices=self.km.init_indices,
+                status=status, assignments=self.km.assignments, init_indices=self.km.init_indices,
                 centroid_times=self.km.centroid_times,
                 centroids=None if self.centroids is None else self.centroids.view(self.k, self.P, self.D),
                 representatives=[self.reps[i, : cnt[i]] for i in range(self.k)], minor=self.minor_list[:nm].tolist(),

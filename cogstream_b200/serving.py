@@ -64,16 +64,19 @@ class StreamPool:
         Host (pinned) inputs are copied to per-lane staging buffers on the lane's stream; device inputs are used in place.
         Returns ``(results, stats_rows [n, len(STATS_FIELDS)] int64 on the device)``; ``results[i]`` is
         ``StreamCompressor.results()`` of stream i (cloned, so the lane can be reused) or ``None`` when
-        ``keep_outputs=False`` (throughput runs: only the stats rows are kept).
+        ``keep_outputs=False`` (throughput runs: only the stats rows are kept; their ``reseed_overflow`` column is non-zero
+        for a stream whose caller-supplied re-seed pool ran out -- ``check_rows`` raises on it).
         """
         n = len(streams)
         main = torch.cuda.current_stream(self.device)
+        results: List[Optional[Dict[str, object]]] = [None] * n
+        # allocated and zero-filled on `main` BEFORE the start event: the lanes (which wait on it) write their rows after the fill
+        rows = torch.zeros(n, len(STATS_FIELDS), dtype=torch.int64, device=self.device)
         start = torch.cuda.Event()
         start.record(main)
-        results: List[Optional[Dict[str, object]]] = [None] * n
-        rows = torch.zeros(n, len(STATS_FIELDS), dtype=torch.int64, device=self.device)
         for L in self.lanes:
             L.stream.wait_event(start)
+            rows.record_stream(L.stream)
             L.busy_with = None
 
         def finish(L: _Lane):
@@ -116,6 +119,16 @@ class StreamPool:
         return results, rows
 
 
+def check_rows(rows: torch.Tensor) -> torch.Tensor:
+    """Raise if any stats row (``[..., len(STATS_FIELDS)]``) reports an exhausted re-seed pool (synchronises)."""
+    col = STATS_FIELDS.index("reseed_overflow")
+    bad = torch.nonzero(rows[..., col].reshape(-1))[:, 0].tolist()
+    if bad:
+        raise RuntimeError(f"re-seed pool exhausted for stream rows {bad}: their clustering is not the reference's; rerun them "
+                           "with a larger reseed_pool")
+    return rows
+
+
 def run_sharded(pool: StreamPool, all_streams: Sequence[StreamInputs], embed: EmbedFn, rank: int, world_size: int, *,
                 keep_outputs: bool = False):
     """Rank ``rank`` of ``world_size`` processes streams ``rank, rank + W, ...``; one all-gather of the stats rows follows.
@@ -126,4 +139,4 @@ def run_sharded(pool: StreamPool, all_streams: Sequence[StreamInputs], embed: Em
     res, rows = pool.run_batch([all_streams[i] for i in mine], embed, keep_outputs=keep_outputs)
     per_rank = (len(all_streams) + world_size - 1) // world_size
     padded = pad_rows(list(rows), per_rank, rows.device)
-    return dict(zip(mine, res)), gather_stats(padded, world_size)
+    return dict(zip(mine, res)), check_rows(gather_stats(padded, world_size))

@@ -58,7 +58,8 @@ typedef void* csb_stream_t; /* cudaStream_t */
 
 CSB_API int csb_abi_version(void);
 CSB_API const char* csb_last_error(void);
-/* 0 if the current device can run the kernels (compute capability 10.x), else CSB_ERR_ARCH. */
+/* 0 if the current device can run the kernels (compute capability 10.0 exactly: the cubins are sm_100a), else
+ * CSB_ERR_ARCH. */
 CSB_API int csb_check_device(void);
 /* Kernels this library has launched in this process so far (bench.py reports the count per timed region). */
 CSB_API uint64_t csb_kernel_launches(void);

@@ -7,7 +7,7 @@ import pytest
 import torch
 
 from conftest import ROOT
-from cogstream_b200 import StreamConfig, _lib, ops, pad_rows, shard_streams, synthetic
+from cogstream_b200 import STATS_FIELDS, StreamConfig, _lib, ops, pad_rows, shard_streams, synthetic
 from cogstream_b200.compression import VisualStreamCompressionMixin, create_visual_summary_prompt
 from cogstream_b200.kmeans_with_time import kmeans_with_time_min_max
 
@@ -87,8 +87,10 @@ def test_gate_and_cluster_count():
 def test_shard_and_pad():
     assert shard_streams(10, 1, 4) == [1, 5, 9]
     assert sorted(sum((shard_streams(256, r, 8) for r in range(8)), [])) == list(range(256))
-    rows = pad_rows([torch.arange(8), torch.arange(8) + 1], 3, "cpu")
-    assert rows.shape == (3, 8) and rows[2].sum() == 0 and rows[1, 0] == 1
+    F = len(STATS_FIELDS)
+    rows = pad_rows([torch.arange(F), torch.arange(F) + 1], 3, "cpu")
+    assert rows.shape == (3, F) and rows[2].sum() == 0 and rows[1, 0] == 1
+    assert "reseed_overflow" in STATS_FIELDS
 
 
 def test_prompt_layout():

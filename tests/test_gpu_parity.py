@@ -277,6 +277,7 @@ CASES = [  # T, P, D, k, seed, iid  -- sizes the oracle finishes in seconds
     (200, 8, 1152, 32, 25, True),
     (600, 7, 1152, 8, 26, False),    # sweep corner: few large events
     (600, 2, 1152, 128, 27, False),  # sweep corner: many small events
+    (300, 27, 3584, None, 28, False),  # production LLM width (D = 3584) at K = 96,768
 ]
 
 
@@ -495,6 +496,79 @@ def test_full_size_config2_kmeans_parity(dev, seed):
     print(f"seed {seed}: reference margin {info.min_margin:.2e}, gpu margin {ig.min_margin:.2e}, iterations {info.iterations}")
     assert torch.equal(ag.cpu(), a) and ig.iterations == info.iterations and ig.converged == info.converged
     assert torch.equal(ctg.cpu(), ct) and rel_err(cg, c) < 1e-6
+
+
+def test_full_size_config2_pipeline_vs_oracle(dev):
+    """BASELINE config 2 at FULL size (T=600, P=180, D=1152, W=2352, k=40), the whole path through the C ABI against the
+    CPU oracle on the same inputs, init and re-seed pool: k-means (kmeans_with_time.py:71-131), representatives, relevance,
+    pixel mask with the minor-frame override, pooling, compaction and id filtering (cogreasoner_chat.py:383-476)."""
+    T, P, D = 600, 180, 1152
+    k = math.ceil(T / 15)
+    seed = 11
+    st = synthetic.make_stream(T, P, D, seed, near_threshold_frac=0.05)
+    ev, q = synthetic.make_embeddings(k, 3584, seed)
+    g = torch.Generator().manual_seed(seed)
+    init = torch.randperm(T, generator=g)[:k]
+    pool = torch.randint(0, T, (k * 31,), generator=g)
+    p1 = orc.phase1(st.features, T, st.timestamps, init_indices=init.tolist(), reseed_indices=pool.tolist())
+    p2 = orc.phase2(st.features, p1, ev, q, st.pixel_values, st.grid_sizes, st.merge_sizes, st.modals, st.input_ids,
+                    synthetic.IMAGE_TOKEN_INDEX, st.attention_mask)
+    W = st.pixel_values.numel() // (T * P)
+    assert W == 2352
+    sc = StreamCompressor(T, P, D, W, st.input_ids.numel(), device=dev)
+    d = st.to(dev)
+    sc.phase1(d.features, d.timestamps, init_indices=init.to(dev), reseed_pool=pool.to(dev))
+    sc.phase2(d.features, ev.to(dev), q.to(dev), d.pixel_values, d.input_ids, d.attention_mask)
+    r = sc.results()
+    print(f"config 2 full: iters={r['status']['iterations']}/{p1.info.iterations} reseeds={r['status']['n_reseed_used']} "
+          f"margin gpu {r['status']['min_margin']:.2e} cpu {p1.info.min_margin:.2e} minor={len(r['minor'])} kept={r['n_kept']}")
+    assert torch.equal(r["assignments"].cpu(), p1.assignments)
+    assert r["status"]["iterations"] == p1.info.iterations and r["status"]["converged"] == p1.info.converged
+    assert r["status"]["n_reseed_used"] == len(p1.info.reseed_indices)
+    assert torch.equal(r["centroid_times"].cpu(), p1.centroid_times)
+    assert rel_err(r["centroids"], p1.centroids) < REL_TOL
+    assert all(torch.equal(a.cpu(), b) for a, b in zip(r["representatives"], p1.representatives))
+    assert torch.equal(r["cos"].cpu(), p2.cos) and torch.equal(torch.nonzero(r["low_flags"].cpu())[:, 0], p2.low_events)
+    assert r["minor"] == p2.minor and len(p2.minor) > 0
+    assert torch.equal(r["mask"].cpu(), p2.mask)
+    assert r["n_kept"] == int(p2.mask.sum())
+    assert torch.equal(r["kept_index"].cpu().long(), torch.nonzero(p2.mask)[:, 0])
+    assert torch.equal(r["input_ids"].cpu(), p2.input_ids) and torch.equal(r["attention_mask"].cpu(), p2.attention_mask)
+    assert_bf16_close(r["features"], p2.features)
+    # rows that are plain copies (everything but token 0 of a minor frame) are bit-identical
+    pooled_rows = torch.zeros(T * P, dtype=torch.bool)
+    pooled_rows[[f * P for f in p2.minor]] = True
+    plain = ~pooled_rows[torch.nonzero(p2.mask)[:, 0]]
+    assert torch.equal(r["features"].cpu()[plain], p2.features[plain])
+
+
+def test_full_size_config4_kmeans_parity(dev):
+    """BASELINE config 4 at FULL size (T=14,400 frames at 2 fps, P=16, D=1152, k=960): Lloyd loop with injected init and
+    re-seed pool vs the CPU oracle (kmeans_with_time.py:71-131).  Many centres start as (or are re-seeded to) frames of the
+    same scene, so empty clusters and exact ties (lowest index wins, :104) are hot here: 60+ re-seeds in 6 iterations.
+    Assignments, iteration count, re-seed count, centre times bit-exact; centroids within 1e-6 relative."""
+    T, P, D, k = 14400, 16, 1152, 960
+    feats, _ = synthetic.make_features(T, P, D, 0)
+    ts = torch.arange(T, dtype=torch.float64) / 2.0
+    g = torch.Generator().manual_seed(0)
+    init = torch.randperm(T, generator=g)[:k].tolist()
+    pool = torch.randint(0, T, (4096,), generator=g).tolist()
+    info = orc.KMeansInfo()
+    c, ct, a = orc.kmeans_with_time_min_max(feats.view(T, P, D), ts, k, init_indices=init, reseed_indices=pool, info=info)
+    cg, ctg, ag, ig = kmeans_with_time_min_max(feats.view(T, P, D).to(dev), ts.to(dev), k, init_indices=init, reseed_indices=pool,
+                                               return_info=True)
+    print(f"config 4 full: iterations {ig.iterations}/{info.iterations} reseeds {ig.n_reseed_used}/{len(info.reseed_indices)} "
+          f"margin cpu {info.min_margin:.2e} gpu {ig.min_margin:.2e}")
+    assert len(info.reseed_indices) > 0, "the case is meant to exercise the empty-cluster path"
+    assert ig.iterations == info.iterations and ig.converged == info.converged
+    assert ig.n_reseed_used == len(info.reseed_indices)
+    assert torch.equal(ag.cpu(), a)
+    assert torch.equal(ctg.cpu(), ct)
+    assert rel_err(cg, c) < 1e-6
+    # representatives on the long-stream path (dist from the Gram matrix, cogreasoner_chat.py:50-64)
+    reps_ref = orc.select_additional_frames(feats.view(T, P, D), c, a, 2)
+    reps = select_additional_frames(feats.view(T, P, D).to(dev), cg, ag, 2)
+    assert all(torch.equal(x.cpu(), y) for x, y in zip(reps, reps_ref))
 
 
 def test_stream_pool_batch_matches_single_streams(dev):
