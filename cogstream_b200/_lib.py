@@ -31,6 +31,33 @@ class KMeansParams(C.Structure):
     ]
 
 
+class CompactArgs(C.Structure):
+    """csb_compact_args (include/cogstream_b200.h)."""
+    _fields_ = [
+        ("x_bf16", C.c_void_p), ("T", C.c_int64), ("P", C.c_int64), ("D", C.c_int64),
+        ("mask", C.c_void_p), ("minor_flags", C.c_void_p), ("min_tokens", C.c_int64),
+        ("finalize", C.c_int32), ("pool_minor", C.c_int32),
+        ("input_ids", C.c_void_p), ("n_ids", C.c_int64), ("image_token_index", C.c_int64),
+        ("attention_mask", C.c_void_p), ("labels", C.c_void_p),
+        ("out_bf16", C.c_void_p), ("kept_index", C.c_void_p), ("n_kept", C.c_void_p),
+        ("out_ids", C.c_void_p), ("out_attention_mask", C.c_void_p), ("out_labels", C.c_void_p), ("n_out", C.c_void_p),
+        ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
+    ]
+
+
+class RelevanceArgs(C.Structure):
+    """csb_relevance_args (include/cogstream_b200.h)."""
+    _fields_ = [
+        ("question", C.c_void_p), ("events", C.c_void_p), ("hidden", C.c_void_p), ("cu_seqlens", C.c_void_p),
+        ("k", C.c_int64), ("Dl", C.c_int64), ("dtype", C.c_int32), ("reserved", C.c_int32), ("threshold", C.c_double),
+        ("gram", C.c_void_p), ("ldg", C.c_int64), ("event_offsets", C.c_void_p), ("event_order", C.c_void_p), ("n_rep", C.c_int64),
+        ("assignments", C.c_void_p), ("T", C.c_int64),
+        ("events_out", C.c_void_p), ("cos_out", C.c_void_p), ("low_flags", C.c_void_p), ("dist", C.c_void_p), ("reps", C.c_void_p),
+        ("rep_counts", C.c_void_p), ("rep_flags", C.c_void_p), ("minor_flags", C.c_void_p), ("minor_list", C.c_void_p),
+        ("n_minor", C.c_void_p), ("ticket", C.c_void_p), ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
+    ]
+
+
 # layout of the device-side csb_kmeans_status (8 x 4 bytes); read back as an int32[8] tensor
 STATUS_WORDS = 8
 ST_ITER, ST_CONV, ST_RESEED, ST_DEGEN, ST_OVERFLOW, ST_NOISE, ST_MARGIN, ST_SHIFT = range(8)
@@ -67,7 +94,12 @@ PROTOTYPES = {
     "csb_compact_workspace_bytes": (_sz, [_i64, _i64]),
     "csb_compact_tokens": (C.c_int, [_p, _i64, _i64, _i64, _p, _p, _p, _p, _p, _p, _sz, _p]),
     "csb_filter_ids": (C.c_int, [_p, _i64, _i64, _p, _i64, _p, _p, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
+    "csb_compact_stream_workspace_bytes": (_sz, [_i64, _i64]),
+    "csb_compact_stream": (C.c_int, [C.POINTER(CompactArgs), _p]),
+    "csb_relevance_select_workspace_bytes": (_sz, [_i64, _i64]),
+    "csb_relevance_select": (C.c_int, [C.POINTER(RelevanceArgs), _p]),
     "csb_embed_scatter_workspace_bytes": (_sz, [_i64]),
+    "csb_embed_scatter_ordered": (C.c_int, [_p, _i64, _i64, _p, _i64, _p, _p, _i64, _i64, _i64, _i32, _p, _p, _p, _sz, _p]),
     "csb_embed_scatter": (C.c_int, [_p, _i64, _i64, _p, _i64, _p, _i64, _i64, _i32, _p, _p, _p, _sz, _p]),
     "csb_seq_mean_pool_workspace_bytes": (_sz, [_i64, _i64]),
     "csb_seq_mean_pool": (C.c_int, [_p, _p, _i64, _i64, _i32, _p, _p, _sz, _p]),

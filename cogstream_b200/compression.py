@@ -62,10 +62,23 @@ def select_additional_frames(cls_feature, long_memory, cluster_assignments, addi
 
 def _mean_pool(hidden: torch.Tensor, cu_seqlens: torch.Tensor) -> torch.Tensor:
     """``torch.mean(last_hidden_state, dim=1)`` (:317, :322) of the sequences of a packed ``[sum(len), Dl]`` tensor."""
-    if hidden.is_cuda and hidden.dtype in (torch.bfloat16, torch.float32) and hidden.shape[1] % 8 == 0:
-        return ops.seq_mean_pool(hidden.contiguous(), cu_seqlens)
-    cu = cu_seqlens.tolist()  # unusual dtype / width: the reference's op, on the device the LLM produced it on
-    return torch.stack([torch.mean(hidden[cu[j]: cu[j + 1]], dim=0) for j in range(len(cu) - 1)])
+    if not hidden.is_cuda:
+        raise RuntimeError("cogstream_b200: the LLM's hidden states are on the CPU; there is no CPU fallback")
+    if hidden.dtype not in (torch.bfloat16, torch.float32) or hidden.shape[1] % 8 != 0:
+        raise TypeError(f"cogstream_b200: hidden states must be bf16 / fp32 with a width that is a multiple of 8, got "
+                        f"{hidden.dtype} x {hidden.shape[1]}")
+    return ops.seq_mean_pool(hidden.contiguous(), cu_seqlens)
+
+
+def _embed_weight(llm, D: int) -> torch.Tensor:
+    """The frozen LLM's embedding table as a plain tensor (the fused embed + <image>-row replacement reads it directly)."""
+    w = getattr(getattr(llm, "embed_tokens", None), "weight", None)
+    if not (isinstance(w, torch.Tensor) and w.is_cuda and w.dtype in (torch.bfloat16, torch.float32) and w.is_contiguous()):
+        raise TypeError("cogstream_b200: get_model().embed_tokens must be an nn.Embedding with a contiguous bf16 / fp32 CUDA weight "
+                        "(wrapped or sharded embedding modules are not supported; there is no eager fallback)")
+    if D is not None and w.shape[1] != D:
+        raise ValueError(f"cogstream_b200: feature width {D} != embedding width {w.shape[1]}")
+    return w
 
 
 def create_visual_summary_prompt(P, timestamps, image_token="<image>"):
@@ -112,15 +125,11 @@ class VisualStreamCompressionMixin:
         ts = timestamps if isinstance(timestamps, torch.Tensor) else torch.tensor(timestamps)
         ts = ts.to(dev)
         # csb_kmeans_kwargs: optional keyword-only extras of the drop-in k-means (init / reseed injection for tests)
-        _, _, assign, info = kmeans_with_time_min_max(features, ts, k, return_info=True,
+        _, _, assign, info = kmeans_with_time_min_max(features, ts, k, return_info=True, return_centroids=False,
                                                       **getattr(self, "csb_kmeans_kwargs", {}))  # :283
         order, ev_off = ops.event_order(assign, k)
-        dist = ops.dist_to_assigned_gram(info.gram, assign, ev_off, order, k)  # :284 (distances from the Gram matrix)
-        _, _, rep_flags = ops.select_representatives(dist, assign, k, self.csb_n_representatives)
-
-        # chronological per-event gather (:286-296): one row-gather into a packed, event-major buffer
-        packed = torch.empty_like(features)
-        ops.gather_rows(features.view(T, P * D), order, packed.view(T, P * D), n=T)
+        # chronological per-event gather (:286-296): NOT materialised; the embedding pass below reads the frame tokens through
+        # `order` (event-major, ascending frame index inside an event)
         off_h = ev_off.tolist()
         ts_sorted = ts[order.long()].tolist()
         # prompts of all events first (:294-301), packed back to back (cu_seqlens layout)
@@ -137,25 +146,22 @@ class VisualStreamCompressionMixin:
             cu_h.append(cu_h[-1] + n_i)
         ids_all = torch.cat(ids_list).to(dev)
         llm = self.get_model()
-        emb_w = getattr(getattr(llm, "embed_tokens", None), "weight", None)
-        fused = isinstance(emb_w, torch.Tensor) and emb_w.is_cuda and emb_w.dtype in (torch.bfloat16, torch.float32) \
-            and emb_w.shape[1] == D and emb_w.is_contiguous()
-        if fused:
-            # :303-305 for all k prompts in ONE pass: the j-th <image> id overall takes packed token row j
-            embeds_all, _ = ops.embed_scatter(ids_all, self.config.image_token_index, emb_w, packed.view(T * P, D))
-        else:  # a wrapped / sharded embedding module: the reference's own three torch ops, still on the device
-            embeds_all = llm.embed_tokens(ids_all).clone()
-            sel = ids_all == self.config.image_token_index
-            embeds_all[sel] = embeds_all[sel] * 0.0 + packed.view(T * P, D).to(embeds_all.dtype)
-        cu_pairs = torch.tensor([[0, n_i] for n_i in lens] + [[0, 0]], dtype=torch.int32).to(dev)  # per-call [0, L_i] rows
+        # :303-305 for all k prompts in ONE pass: the j-th <image> id overall takes token j of the event-major frame order
+        embeds_all, _ = ops.embed_scatter(ids_all, self.config.image_token_index, _embed_weight(llm, D), feats, frame_order=order,
+                                          tokens_per_frame=P)
+        cu_all = torch.tensor(cu_h, dtype=torch.int32).to(dev)
+        hidden_all = None
+        events_repr = None
         batched = getattr(self, "csb_batched_summary_forward", None)
         if callable(batched):
-            # one var-len forward of the frozen LLM over the packed prompts (user-supplied, e.g. flash-attn
-            # varlen); returns the packed last hidden states [sum(len), Dl]
-            cu_all = torch.tensor(cu_h, dtype=torch.int32).to(dev)
+            # one var-len forward of the frozen LLM over the packed prompts (cogstream_b200.summary_forward
+            # builds one for HF Qwen2-style models; any callable (inputs_embeds [sum(len), D], cu_seqlens) -> [sum(len), Dl] works)
             hidden_all = batched(embeds_all, cu_all)
-            events_repr = _mean_pool(hidden_all, cu_all)
+            if not hidden_all.is_cuda:
+                raise RuntimeError("cogstream_b200: csb_batched_summary_forward returned a CPU tensor; there is no CPU fallback")
+            hidden_all = hidden_all.contiguous()
         else:
+            cu_pairs = torch.tensor([[0, n_i] for n_i in lens] + [[0, 0]], dtype=torch.int32).to(dev)  # per-call [0, L_i] rows
             events_repr = []
             for i in range(k):  # :306-317, the frozen LLM is called exactly like the reference does
                 e_i = embeds_all[cu_h[i]: cu_h[i + 1]]
@@ -173,13 +179,29 @@ class VisualStreamCompressionMixin:
         else:
             question = torch.mean(q_hidden, dim=1)
 
-        ev_c = events_repr.to(dev).contiguous()
-        q_c = question[0].to(device=dev, dtype=ev_c.dtype).contiguous()
-        if ev_c.dtype not in (torch.bfloat16, torch.float32):
-            ev_c, q_c = ev_c.float(), q_c.float()
-        _, low = ops.cosine_flags(q_c, ev_c, self.csb_relevance_threshold)  # :325-330
-        assert low.shape[0] == k  # :327
-        _, minor_list, n_minor = ops.minor_frames(assign, low, rep_flags)  # :331-332
+        # :284 representatives + :325-333 relevance + minor list: one launch (the event mean pool :317-318 fused in when the hidden
+        # states came back packed)
+        src = hidden_all if hidden_all is not None else events_repr.to(dev).contiguous()
+        if src.dtype not in (torch.bfloat16, torch.float32):
+            src = src.float()
+        q_c = question[0].to(device=dev, dtype=src.dtype).contiguous()
+        ticket = torch.zeros(1, dtype=torch.int32, device=dev)
+        if T <= 256 * k:
+            if hidden_all is not None:
+                b = ops.relevance_select(q_c, None, info.gram, ev_off, order, assign, ticket, k=k, n_rep=self.csb_n_representatives,
+                                         threshold=self.csb_relevance_threshold, hidden=src, cu_seqlens=cu_all)
+            else:
+                b = ops.relevance_select(q_c, src, info.gram, ev_off, order, assign, ticket, k=k, n_rep=self.csb_n_representatives,
+                                         threshold=self.csb_relevance_threshold)
+            assert b["low"].shape[0] == k  # :327
+            minor_list, n_minor = b["minor_list"], b["n_minor"]
+        else:  # events of many hundreds of frames: the two-pass distance kernels
+            ev_c = src if hidden_all is None else _mean_pool(src, cu_all)
+            dist = ops.dist_to_assigned_gram(info.gram, assign, ev_off, order, k)
+            _, _, rep_flags = ops.select_representatives(dist, assign, k, self.csb_n_representatives)
+            _, low = ops.cosine_flags(q_c, ev_c, self.csb_relevance_threshold)
+            assert low.shape[0] == k  # :327
+            _, minor_list, n_minor = ops.minor_frames(assign, low, rep_flags)
         return minor_list[: int(n_minor.item())].tolist()  # :333
 
     # ------------------------------------------------------------------------------------------
@@ -243,7 +265,11 @@ class VisualStreamCompressionMixin:
         ids = input_ids.contiguous()
         o_ids, o_am, o_lb, o_ps, n_out = ops.filter_ids(ids, self.config.image_token_index, mask_u8, attention_mask, labels,
                                                         position_ids)  # :459-474
-        nk, no = int(n_kept.item()), int(n_out.item())
+        nk = int(n_kept.item())
+        no, n_img = (int(v) for v in n_out.tolist())
+        if n_img != mask_u8.numel():  # `text_masks[image_selected] = compression_mask` (:463) raises in the reference
+            raise RuntimeError(f"shape mismatch: value tensor of shape [{mask_u8.numel()}] cannot be broadcast to indexing result of "
+                               f"shape [{n_img}]")
         mm = out[:nk]
         if mm.dtype != mm_features.dtype:
             mm = mm.to(mm_features.dtype)
@@ -287,7 +313,7 @@ class VisualStreamCompressionMixin:
             if position_ids is not None:
                 n_image_ids = int(input_ids.eq(img_id).sum())
             no_truncation = position_ids is None or mm_features.shape[0] == n_image_ids  # :358-359
-            if self.config.use_token_compression and no_truncation and input_ids.is_cuda:
+            if self.config.use_token_compression and no_truncation:
                 assert B == 1, "Token compression is only supported for batch_size=1"  # :561
                 feats = _frames_bf16(mm_features)
                 T = int(total_image_num)
@@ -298,17 +324,27 @@ class VisualStreamCompressionMixin:
                 minor_flags = torch.zeros(T, dtype=torch.uint8, device=feats.device)
                 if len(frame_indices):
                     minor_flags[torch.tensor(list(frame_indices), dtype=torch.int64, device=feats.device)] = 1
-                # :551 + :562: x[mask] where token 0 of a minor frame is emitted as the frame's pooled mean
-                out, _, n_kept = ops.compact_tokens(feats, T, P, mask_u8, minor_flags)
-                o_ids, o_am, o_lb, o_ps, n_out = ops.filter_ids(input_ids.contiguous(), img_id, mask_u8, attention_mask, labels,
-                                                                position_ids)  # :459-474
-                nk, no = int(n_kept.item()), int(n_out.item())
+                # :551 + :562: x[mask] where token 0 of a minor frame is emitted as the frame's pooled mean, + :459-474
+                if position_ids is None:
+                    b = ops.compact_stream(feats, T, P, mask_u8, minor_flags, finalize=False, input_ids=input_ids.contiguous(),
+                                           image_token_index=img_id, attention_mask=attention_mask, labels=labels)
+                    out, n_kept, n_out = b["out"], b["n_kept"], b["n_out"]
+                    o_ids, o_am, o_lb, o_ps = b["out_ids"], b.get("out_attention"), b.get("out_labels"), None
+                else:
+                    out, _, n_kept = ops.compact_tokens(feats, T, P, mask_u8, minor_flags)
+                    o_ids, o_am, o_lb, o_ps, n_out = ops.filter_ids(input_ids.contiguous(), img_id, mask_u8, attention_mask, labels,
+                                                                    position_ids)
+                nk = int(n_kept.item())
+                no, n_img = (int(v) for v in n_out.tolist())
+                if n_img != mask_u8.numel():  # :463 raises in the reference
+                    raise RuntimeError(f"shape mismatch: value tensor of shape [{mask_u8.numel()}] cannot be broadcast to indexing "
+                                       f"result of shape [{n_img}]")
                 mm_features = out[:nk] if out.dtype == mm_features.dtype else out[:nk].to(mm_features.dtype)
                 input_ids = o_ids[:no]
                 attention_mask = None if o_am is None else o_am[:no].to(attention_mask.dtype)
                 labels = None if o_lb is None else o_lb[:no].to(labels.dtype)
                 position_ids = None if o_ps is None else o_ps[:no].to(position_ids.dtype)
-            else:  # the reference's own sequence, method by method (:551-564)
+            else:  # truncated visual tokens / compression switched off: the same kernels, method by method (:551-564)
                 mm_features = self.compress_unimportant_events(mm_features, mm_features.shape[0] // total_image_num,
                                                                frame_indices)
                 compression_mask = self._get_compression_mask(pixel_values, batched_num_patches, grid_sizes, merge_sizes,
@@ -319,19 +355,12 @@ class VisualStreamCompressionMixin:
                     assert B == 1, "Token compression is only supported for batch_size=1"
                     mm_features, input_ids, attention_mask, position_ids, labels = self._compress_visual_tokens(
                         compression_mask, mm_features, input_ids, attention_mask, position_ids, labels)
-        # 4./5. embed text tokens, replace the <image> rows (:567-572)
-        emb = self.get_model().embed_tokens
-        emb_w = getattr(emb, "weight", None)
-        fused = isinstance(emb_w, torch.Tensor) and emb_w.is_cuda and input_ids.is_cuda and emb_w.is_contiguous() \
-            and emb_w.dtype in (torch.bfloat16, torch.float32) and (mm_features is None or mm_features.shape[1] == emb_w.shape[1])
-        if fused:
-            inputs_embeds, _ = ops.embed_scatter(input_ids.contiguous(), img_id if if_visual else -1, emb_w,
-                                                 mm_features.contiguous() if if_visual else None)
-        else:
-            inputs_embeds = emb(input_ids).clone()
-            if if_visual:
-                image_selected = input_ids == img_id
-                inputs_embeds[image_selected] = inputs_embeds[image_selected] * 0.0 + mm_features.to(inputs_embeds.dtype)
+        # 4./5. embed text tokens, replace the <image> rows (:567-572): one pass
+        emb_w = _embed_weight(self.get_model(), None if mm_features is None else mm_features.shape[1])
+        if not input_ids.is_cuda:
+            raise RuntimeError("cogstream_b200: input_ids are on the CPU; there is no CPU fallback")
+        inputs_embeds, _ = ops.embed_scatter(input_ids.contiguous(), img_id if if_visual else -1, emb_w,
+                                             mm_features.contiguous() if if_visual else None)
         C = inputs_embeds.shape[-1]  # :575-583
         inputs_embeds = inputs_embeds.reshape(B, -1, C)
         attention_mask = attention_mask.view(B, -1) if attention_mask is not None else None

@@ -15,6 +15,9 @@ void set_error(const char* fmt, ...);
 int check_launch(const char* what);  // counts one launch; cudaGetLastError -> CSB_OK / CSB_ERR_CUDA
 void count_launch(int n);            // launches that do not go through check_launch
 int device_ok();                     // cached compute-capability check
+// split partial sums of the var-len mean pool (embed_pool.cu): partial [n_seq][8][Dl] fp32; shared with the fused relevance step
+int launch_seq_pool_partial(const void* hidden, const int32_t* cu_seqlens, int64_t n_seq, int64_t Dl, int dtype, float* partial,
+                            cudaStream_t s);
 
 #define CSB_REQUIRE(cond, ...)        \
   do {                                \

@@ -81,7 +81,8 @@ template <bool BF16>
 __global__ void __launch_bounds__(256) embed_scatter_kernel(const int64_t* __restrict__ ids, int64_t n, int64_t image_token,
                                                             int64_t vocab, const uint4* __restrict__ table,
                                                             const uint4* __restrict__ feats, int64_t n_feats, int Dv,
-                                                            const int32_t* __restrict__ chunk_prefix, uint4* __restrict__ out) {
+                                                            const int32_t* __restrict__ chunk_prefix, uint4* __restrict__ out,
+                                                            const int32_t* __restrict__ frame_order, int tokens_per_frame) {
   __shared__ const uint4* s_src[kRowsPerCta];
   __shared__ int s_img[kRowsPerCta];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -94,7 +95,14 @@ __global__ void __launch_bounds__(256) embed_scatter_kernel(const int64_t* __res
     const int64_t rank = (int64_t)chunk_prefix[blockIdx.x] + __popc(bal & ((1u << lane) - 1u));
     const uint4* src = nullptr;  // nullptr -> zeros (id out of range, or more <image> ids than feature rows: flagged in status)
     if (img) {
-      if (rank < n_feats) src = feats + rank * Dv;
+      if (rank < n_feats) {
+        int64_t row = rank;
+        if (frame_order) {  // chronological per-event gather folded into the read (cogreasoner_chat.py:291-296)
+          const int64_t fr = rank / tokens_per_frame;
+          row = (int64_t)frame_order[fr] * tokens_per_frame + (rank - fr * tokens_per_frame);
+        }
+        src = feats + row * Dv;
+      }
     } else if (id >= 0 && id < vocab) {
       src = table + id * Dv;
     }
@@ -209,6 +217,21 @@ __global__ void __launch_bounds__(256) seq_pool_final_kernel(const float* __rest
 
 static inline size_t align_up256(size_t v) { return (v + 255) / 256 * 256; }
 
+int launch_seq_pool_partial(const void* hidden, const int32_t* cu_seqlens, int64_t n_seq, int64_t Dl, int dtype, float* partial,
+                            cudaStream_t s) {
+  const int per = dtype == CSB_BF16 ? 8 : 4;
+  if (Dl % per != 0 || (reinterpret_cast<uintptr_t>(hidden) & 15u) != 0) {
+    set_error("seq_mean_pool: rows must be 128-bit multiples, 16-byte aligned");
+    return CSB_ERR_ARG;
+  }
+  if (n_seq > 65535) { set_error("seq_mean_pool: more than 65535 sequences"); return CSB_ERR_ARG; }
+  const int Dv = (int)(Dl / per);
+  dim3 g1((unsigned)((Dv + 127) / 128), (unsigned)n_seq, kPoolSplits);
+  if (dtype == CSB_BF16) seq_pool_partial_kernel<true><<<g1, 128, 0, s>>>((const uint4*)hidden, cu_seqlens, Dv, partial);
+  else seq_pool_partial_kernel<false><<<g1, 128, 0, s>>>((const uint4*)hidden, cu_seqlens, Dv, partial);
+  return check_launch("seq_pool_partial");
+}
+
 }  // namespace csb
 
 using namespace csb;
@@ -220,9 +243,9 @@ size_t csb_embed_scatter_workspace_bytes(int64_t n_ids) {
   return align_up256(sizeof(int32_t) * (size_t)((n_ids + 31) / 32 + 2));
 }
 
-int csb_embed_scatter(const int64_t* input_ids, int64_t n_ids, int64_t image_token_index, const void* embed_table, int64_t vocab,
-                      const void* features, int64_t n_features, int64_t D, int dtype, void* out, int32_t* status, void* workspace,
-                      size_t workspace_bytes, csb_stream_t stream) {
+static int embed_scatter_impl(const int64_t* input_ids, int64_t n_ids, int64_t image_token_index, const void* embed_table, int64_t vocab,
+                              const void* features, int64_t n_features, const int32_t* frame_order, int64_t tokens_per_frame, int64_t D,
+                              int dtype, void* out, int32_t* status, void* workspace, size_t workspace_bytes, csb_stream_t stream) {
   CSB_DEVICE_OR_RETURN();
   CSB_REQUIRE(input_ids && embed_table && out && status && workspace && n_ids > 0 && vocab > 0 && D > 0,
               "embed_scatter: null argument or empty shape");
@@ -246,11 +269,29 @@ int csb_embed_scatter(const int64_t* input_ids, int64_t n_ids, int64_t image_tok
   const int Dv = (int)(D / per);
   if (dtype == CSB_BF16)
     embed_scatter_kernel<true><<<grid, 256, 0, s>>>(input_ids, n_ids, image_token_index, vocab, (const uint4*)embed_table,
-                                                     (const uint4*)features, n_features, Dv, prefix, (uint4*)out);
+                                                     (const uint4*)features, n_features, Dv, prefix, (uint4*)out, frame_order,
+                                                     (int)tokens_per_frame);
   else
     embed_scatter_kernel<false><<<grid, 256, 0, s>>>(input_ids, n_ids, image_token_index, vocab, (const uint4*)embed_table,
-                                                      (const uint4*)features, n_features, Dv, prefix, (uint4*)out);
+                                                      (const uint4*)features, n_features, Dv, prefix, (uint4*)out, frame_order,
+                                                      (int)tokens_per_frame);
   return check_launch("embed_scatter");
+}
+
+int csb_embed_scatter(const int64_t* input_ids, int64_t n_ids, int64_t image_token_index, const void* embed_table, int64_t vocab,
+                      const void* features, int64_t n_features, int64_t D, int dtype, void* out, int32_t* status, void* workspace,
+                      size_t workspace_bytes, csb_stream_t stream) {
+  return embed_scatter_impl(input_ids, n_ids, image_token_index, embed_table, vocab, features, n_features, nullptr, 1, D, dtype, out,
+                            status, workspace, workspace_bytes, stream);
+}
+
+int csb_embed_scatter_ordered(const int64_t* input_ids, int64_t n_ids, int64_t image_token_index, const void* embed_table, int64_t vocab,
+                              const void* features, const int32_t* frame_order, int64_t n_frames, int64_t tokens_per_frame, int64_t D,
+                              int dtype, void* out, int32_t* status, void* workspace, size_t workspace_bytes, csb_stream_t stream) {
+  CSB_REQUIRE(frame_order && n_frames > 0 && tokens_per_frame > 0 && tokens_per_frame < (1ll << 31),
+              "embed_scatter_ordered: null frame order or empty shape");
+  return embed_scatter_impl(input_ids, n_ids, image_token_index, embed_table, vocab, features, n_frames * tokens_per_frame, frame_order,
+                            tokens_per_frame, D, dtype, out, status, workspace, workspace_bytes, stream);
 }
 
 size_t csb_seq_mean_pool_workspace_bytes(int64_t n_seq, int64_t Dl) {

@@ -47,6 +47,8 @@ struct SolverArgs {
   unsigned long long* tl;  // phase timeline (globaltimer ns), [0] = entries written; profiling aid
   int diag_in_smem;   // 1: keep a shared-memory copy of the diagonal (T small enough)
   int multiwarp_fill; // 1: per-warp cluster counters fit in shared memory
+  int fused_init;     // 1: CTA 0 of the solver runs the k-means++ init itself (no separate kmeanspp launch)
+  int32_t* assign32;  // [T] compact copy of the assignments (what every CTA reloads after the barrier)
 };
 
 __device__ __forceinline__ void grid_sync(unsigned* counter, unsigned& target, unsigned nblocks) {
@@ -60,6 +62,26 @@ __device__ __forceinline__ void grid_sync(unsigned* counter, unsigned& target, u
       do {
         asm volatile("ld.acquire.gpu.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
       } while (v < target);
+    }
+    __syncthreads();
+  }
+}
+
+// the same barrier with a sleeping poll: for the long wait while CTA 0 runs the fused k-means++ init (tens of microseconds),
+// so that the other CTAs' pollers do not compete with CTA 0 for the L2
+__device__ __forceinline__ void grid_sync_backoff(unsigned* counter, unsigned& target, unsigned nblocks) {
+  __syncthreads();
+  if (nblocks > 1) {
+    if (threadIdx.x == 0) {
+      target += nblocks;
+      __threadfence();
+      atomicAdd(counter, 1u);
+      unsigned v;
+      for (;;) {
+        asm volatile("ld.acquire.gpu.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
+        if (v >= target) break;
+        __nanosleep(256);
+      }
     }
     __syncthreads();
   }
@@ -840,17 +862,50 @@ __global__ void __launch_bounds__(kSolverThreads, WIDE ? 1 : 2) kmeans_solver_ke
   int used = 0;
   const double* diag = a.diag_in_smem ? s_diag : a.diag;
 
-  // ---------------- the k-means++ kernel ran before this launch: centres, diagonal and pool usage are in global memory ------
-  used = *a.used;
-  if (a.diag_in_smem)
-    for (int i = threadIdx.x; i < T; i += blockDim.x) { s_diag[i] = a.diag[i]; s_ts[i] = load_ts<TS>(a.ts, i); }
+  __shared__ float s_wv[kSolverWarps];
+  __shared__ int s_wi[kSolverWarps];
+  __shared__ float s_ws[kSolverWarps];
+  if (a.fused_init) {
+    // ---------------- k-means++ inside this launch: CTA 0 samples the centres while the other CTAs preload and wait ------------
+    for (int i = threadIdx.x; i < T; i += blockDim.x) {
+      const double g = a.G[(int64_t)i * a.ldg + i];
+      s_diag[i] = g;
+      s_ts[i] = load_ts<TS>(a.ts, i);
+      if (blockIdx.x == 0) a.diag[i] = g;
+    }
+    if (blockIdx.x == 0) {
+      if (threadIdx.x == 0) {
+        st->iterations = 0; st->converged = 0; st->n_reseed_used = 0; st->degenerate_rounds = 0;
+        st->reseed_overflow = 0; st->n_noise_used = 0; st->min_margin = __int_as_float(0x7f800000); st->last_shift = 0.f;
+      }
+      mark(a, 1);
+      __syncthreads();
+      int n_noise = 0, n_deg = 0;
+      if (a.n_init_given < k)  // s_near aliases s_assign: the assignments are not needed before the first iteration
+        kmeanspp_block<kSolverThreads>(a, reinterpret_cast<float*>(s_assign), s_diag, s_wv, s_wi, s_ws, &used, &n_noise, &n_deg);
+      if (threadIdx.x == 0) {
+        st->degenerate_rounds = n_deg;
+        st->n_noise_used = n_noise;
+        *a.used = used;
+      }
+      mark(a, 2);
+    }
+    grid_sync_backoff(a.barrier, bar, nb);
+    used = __ldcg(a.used);
+  } else {
+    // ---------------- the k-means++ kernel ran before this launch: centres, diagonal and pool usage are in global memory ------
+    used = *a.used;
+    if (a.diag_in_smem)
+      for (int i = threadIdx.x; i < T; i += blockDim.x) { s_diag[i] = a.diag[i]; s_ts[i] = load_ts<TS>(a.ts, i); }
+  }
   // initial centres: cluster j = { init[j] }
+  __syncthreads();
   for (int j = threadIdx.x; j < k; j += blockDim.x) {
-    const int c = (int)a.init_indices[j];
+    const int c = (int)__ldcg(a.init_indices + j);
     s_offs[j] = j;
     s_memb[j] = c;
     s_ctb[0][j] = (double)load_ts<TS>(a.ts, c);  // :66
-    s_q[0][j] = a.diag[c];
+    s_q[0][j] = diag[c];
     s_rn[j] = 1.0;
     s_nn[j] = 1.0;
     s_ver[j] = 1;
@@ -1022,6 +1077,7 @@ __global__ void __launch_bounds__(kSolverThreads, WIDE ? 1 : 2) kmeans_solver_ke
       }
       if (lane == 0) {
         a.assignments[i] = bestj;  // :104 lowest index on ties
+        a.assign32[i] = bestj;
         if (k > 1) my_margin = fminf(my_margin, second - best);
       }
     }
@@ -1031,7 +1087,7 @@ __global__ void __launch_bounds__(kSolverThreads, WIDE ? 1 : 2) kmeans_solver_ke
 
     // ---------- new centres: every CTA rebuilds the membership in its own shared memory ----------
     const int nxt = cur ^ 1;
-    for (int i = threadIdx.x; i < T; i += blockDim.x) s_assign[i] = (int)__ldcg(a.assignments + i);
+    for (int i = threadIdx.x; i < T; i += blockDim.x) s_assign[i] = __ldcg(a.assign32 + i);
     __syncthreads();
     ms.ct_new = s_ctb[nxt];
     rebuild_members_smem<TS>(a, ms, &used, it == 1);
@@ -1063,30 +1119,49 @@ __global__ void __launch_bounds__(kSolverThreads, WIDE ? 1 : 2) kmeans_solver_ke
     // Only changed clusters move.  Lane e of the warp owning cluster j sums member e, e+32, ... of column j of the
     // new and the old S (fixed order => an unchanged list would reproduce the same bits: shift exactly 0).
     double part = 0.0;
-    for (int j = warp; j < k; j += kSolverWarps) {
-      if (!s_changed[j]) {
-        if (lane == 0) s_q[nxt][j] = s_q[cur][j];
-        continue;
+    constexpr int kSB = 4;  // clusters of a warp whose member loads are issued together (one L2 round trip instead of kSB)
+    for (int j0 = warp; j0 < k; j0 += kSolverWarps * kSB) {
+      int jj[kSB], beg[kSB], end[kSB];
+      double sn[kSB], sc[kSB];
+#pragma unroll
+      for (int u = 0; u < kSB; ++u) {
+        const int j = j0 + u * kSolverWarps;
+        jj[u] = -1; beg[u] = 0; end[u] = 0; sn[u] = 0.0; sc[u] = 0.0;
+        if (j < k) {
+          if (!s_changed[j]) {
+            if (lane == 0) s_q[nxt][j] = s_q[cur][j];
+          } else {
+            jj[u] = j; beg[u] = s_offs[j]; end[u] = s_offs[j + 1];
+            const int e = beg[u] + lane;
+            if (e < end[u]) {
+              const int64_t row = (int64_t)s_memb[e] * k + j;
+              sn[u] = __ldcg(a.S[nxt] + row);
+              sc[u] = __ldcg(a.S[cur] + row);
+            }
+          }
+        }
       }
-      const int beg = s_offs[j], end = s_offs[j + 1];
-      double sn = 0.0, sc = 0.0;
-      for (int e = beg + lane; e < end; e += 32) {
-        const int64_t row = (int64_t)s_memb[e] * k + j;
-        const double vn = __ldcg(a.S[nxt] + row), vc = __ldcg(a.S[cur] + row);
-        sn += vn;
-        sc += vc;
-      }
-      sn = warp_sum(sn);
-      sc = warp_sum(sc);
-      if (lane == 0) {
-        const double n = (double)(end - beg);
-        const double qn = sn / (n * n);
-        const double cross = sc / (n * s_nn[j]);
-        const double sh2 = (qn + s_q[cur][j]) - 2.0 * cross;
-        s_q[nxt][j] = qn;
-        s_rn[j] = 1.0 / n;  // cluster j's entries are owned by this warp until the barrier below
-        s_nn[j] = n;
-        part += sqrt(sh2 > 0.0 ? sh2 : 0.0);
+#pragma unroll
+      for (int u = 0; u < kSB; ++u) {
+        if (jj[u] < 0) continue;  // warp-uniform
+        const int j = jj[u];
+        for (int e = beg[u] + lane + 32; e < end[u]; e += 32) {  // clusters of more than 32 members (same per-lane order)
+          const int64_t row = (int64_t)s_memb[e] * k + j;
+          const double vn = __ldcg(a.S[nxt] + row), vc = __ldcg(a.S[cur] + row);
+          sn[u] += vn;
+          sc[u] += vc;
+        }
+        const double tn = warp_sum(sn[u]), tc = warp_sum(sc[u]);
+        if (lane == 0) {
+          const double n = (double)(end[u] - beg[u]);
+          const double qn = tn / (n * n);
+          const double cross = tc / (n * s_nn[j]);
+          const double sh2 = (qn + s_q[cur][j]) - 2.0 * cross;
+          s_q[nxt][j] = qn;
+          s_rn[j] = 1.0 / n;  // cluster j's entries are owned by this warp until the barrier below
+          s_nn[j] = n;
+          part += sqrt(sh2 > 0.0 ? sh2 : 0.0);
+        }
       }
     }
     const double shift_feat = block_sum<double>(part, s_red);
@@ -1138,6 +1213,7 @@ size_t csb_kmeans_workspace_bytes(int64_t T, int64_t k) {
   size_t b = 0;
   b += align_up(sizeof(double) * T, 256);              // diag
   b += 2 * align_up(sizeof(double) * T * k, 256);      // S
+  b += align_up(sizeof(int32_t) * T, 256);             // compact assignments
   b += 4096;                                           // barrier + used + phase timeline
   return b;
 }
@@ -1177,6 +1253,7 @@ int csb_kmeans_solve(const double* G, const void* timestamps, const csb_kmeans_p
   char* w = reinterpret_cast<char*>(workspace);
   a.diag = reinterpret_cast<double*>(w); w += align_up(sizeof(double) * T, 256);
   for (int b = 0; b < 2; ++b) { a.S[b] = reinterpret_cast<double*>(w); w += align_up(sizeof(double) * T * k, 256); }
+  a.assign32 = reinterpret_cast<int32_t*>(w); w += align_up(sizeof(int32_t) * T, 256);
   a.barrier = reinterpret_cast<unsigned*>(w);
   a.used = reinterpret_cast<int32_t*>(w + 128);
   a.tl = reinterpret_cast<unsigned long long*>(w + 256);
@@ -1202,7 +1279,12 @@ int csb_kmeans_solve(const double* G, const void* timestamps, const csb_kmeans_p
   // long streams (CSB_INIT_GRID=0/1 forces either: profiling aid)
   bool grid_init = T > kGridInitMinT && p->n_init_given < k;
   if (const char* o = getenv("CSB_INIT_GRID")) grid_init = atoi(o) != 0 && T <= (int64_t)sms * kGridInitThreads * kGridInitU;
-  if (grid_init) {
+  // short streams (one init thread per <= 4 frames at the solver's block size): the init runs on CTA 0 of the solver launch
+  a.fused_init = (!grid_init && T <= 1024 && sp.diag_in_smem && !getenv("CSB_INIT_THREADS")) ? 1 : 0;
+  if (const char* o = getenv("CSB_FUSED_INIT")) a.fused_init = a.fused_init && atoi(o) != 0;
+  if (a.fused_init) {
+    // nothing to launch here
+  } else if (grid_init) {
     int64_t nbi = (T + kGridInitThreads - 1) / kGridInitThreads;
     if (nbi > sms) nbi = sms;
     GridInitBufs gb;
@@ -1243,7 +1325,9 @@ int csb_kmeans_solve(const double* G, const void* timestamps, const csb_kmeans_p
   }
   // Lloyd loop: two frames per warp in the assignment phase -- the loop is latency-bound, so fewer resident CTAs cost little
   // time and leave the other SMs to the bandwidth-bound kernels of the streams that run concurrently
-  int64_t nb = (T + 2 * kSolverWarps - 1) / (2 * kSolverWarps);
+  int fpw = 2;  // frames per warp in the assignment pass (CSB_SOLVER_FPW: tuning runs)
+  if (const char* o = getenv("CSB_SOLVER_FPW")) fpw = atoi(o) > 0 ? atoi(o) : 2;
+  int64_t nb = (T + fpw * kSolverWarps - 1) / (fpw * kSolverWarps);
   if (nb > sms) nb = sms;
   if (nb < 1) nb = 1;
   void* args[] = {&a};

@@ -141,13 +141,11 @@ __global__ void __launch_bounds__(256) select_reps_kernel(const float* __restric
 // A warp per event; the event's members are event_order[off[j] .. off[j+1]) (ascending frame index).
 //   rowsum_m = sum_{m'} G[m][m'],  q = sum_m rowsum_m / n^2,  dist_m^2 = G_mm - 2 rowsum_m / n + q
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) reps_gram_kernel(const double* __restrict__ G, int64_t ldg, int k, int n_rep,
-                                                        const int32_t* __restrict__ ev_off, const int32_t* __restrict__ order,
-                                                        float* __restrict__ dist, int64_t* __restrict__ reps,
-                                                        int32_t* __restrict__ rep_counts, uint8_t* __restrict__ rep_flags) {
+__device__ __forceinline__ void reps_of_event(const double* __restrict__ G, int64_t ldg, int j, int n_rep,
+                                              const int32_t* __restrict__ ev_off, const int32_t* __restrict__ order,
+                                              float* __restrict__ dist, int64_t* __restrict__ reps,
+                                              int32_t* __restrict__ rep_counts, uint8_t* __restrict__ rep_flags) {
   const int lane = threadIdx.x & 31;
-  const int j = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (j >= k) return;
   const int beg = ev_off[j], n = ev_off[j + 1] - beg;
   const int32_t* mem = order + beg;
   int64_t* out = reps + (int64_t)j * n_rep;
@@ -214,6 +212,15 @@ __global__ void __launch_bounds__(256) reps_gram_kernel(const double* __restrict
     last_i = bi;
   }
   if (lane == 0) rep_counts[j] = n_rep;
+}
+
+__global__ void __launch_bounds__(256) reps_gram_kernel(const double* __restrict__ G, int64_t ldg, int k, int n_rep,
+                                                        const int32_t* __restrict__ ev_off, const int32_t* __restrict__ order,
+                                                        float* __restrict__ dist, int64_t* __restrict__ reps,
+                                                        int32_t* __restrict__ rep_counts, uint8_t* __restrict__ rep_flags) {
+  const int j = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (j >= k) return;
+  reps_of_event(G, ldg, j, n_rep, ev_off, order, dist, reps, rep_counts, rep_flags);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -364,6 +371,129 @@ __global__ void __launch_bounds__(256) relevance_minor_kernel(const void* __rest
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// The whole selection step of phase 2 in ONE launch (cogreasoner_chat.py:284 + :317-318 + :325-333):
+//   CTAs [0, k)            cosine of event j against the question; with `partials` the event embedding is first finished from
+//                          the split partial sums of the var-len mean pool (sum in split order, one IEEE division, one rounding:
+//                          the bits of csb_seq_mean_pool) -- the pooled row never makes a round trip through HBM
+//   CTAs [k, k + ceil(k/8)) a warp per event: the n_rep members nearest to the centroid, from the Gram matrix
+//   the last CTA to finish derives the minor-frame flags and the ascending list.
+// ------------------------------------------------------------------------------------------------
+constexpr int kRelSplits = 8;  // == kPoolSplits of embed_pool.cu
+
+struct RelevanceArgs {
+  const void* q;
+  const void* ev;          // [k, Dl] or nullptr
+  const float* partials;   // [k][kRelSplits][Dl] or nullptr
+  const int32_t* cu;       // [k + 1] with partials
+  int k, Dl;
+  float threshold;
+  const double* G;
+  int64_t ldg;
+  const int32_t* ev_off;
+  const int32_t* order;
+  int n_rep;
+  const int64_t* assign;
+  int T;
+  void* ev_out;  // [k, Dl] with partials (nullable)
+  void* cos_out;
+  uint8_t* low;
+  float* dist;
+  int64_t* reps;
+  int32_t* rep_counts;
+  uint8_t* rep_flags;
+  uint8_t* minor_flags;
+  int32_t* minor_list;
+  int64_t* n_minor;
+  unsigned* ticket;
+};
+
+template <bool BF16>
+__global__ void __launch_bounds__(256) relevance_select_kernel(RelevanceArgs a) {
+  extern __shared__ float s_row[];  // [Dl] with partials
+  __shared__ float red[32];
+  __shared__ int wt[32];
+  __shared__ int total;
+  __shared__ int is_last;
+  const int b = blockIdx.x;
+  if (b < a.k) {
+    const int Dl = a.Dl;
+    const void* e = nullptr;
+    if (a.partials) {
+      const int len = a.cu[b + 1] - a.cu[b];
+      const float* pp = a.partials + (int64_t)b * kRelSplits * Dl;
+      for (int d = threadIdx.x; d < Dl; d += blockDim.x) {
+        float v[kRelSplits];
+#pragma unroll
+        for (int sp = 0; sp < kRelSplits; ++sp) v[sp] = pp[(int64_t)sp * Dl + d];
+        float sum = 0.f;
+#pragma unroll
+        for (int sp = 0; sp < kRelSplits; ++sp) sum += v[sp];
+        const float m = rnd<BF16>(__fdiv_rn(sum, (float)len));  // torch.mean: fp32 sum, one division, one rounding
+        s_row[d] = m;
+        if (a.ev_out) {
+          if (BF16) reinterpret_cast<uint16_t*>(a.ev_out)[(int64_t)b * Dl + d] = (uint16_t)float_to_bf16_bits(m);
+          else reinterpret_cast<float*>(a.ev_out)[(int64_t)b * Dl + d] = m;
+        }
+      }
+      __syncthreads();
+    } else {
+      e = BF16 ? (const void*)(reinterpret_cast<const uint16_t*>(a.ev) + (int64_t)b * Dl)
+               : (const void*)(reinterpret_cast<const float*>(a.ev) + (int64_t)b * Dl);
+    }
+    auto ev_at = [&](int i) -> float { return e ? ld_elem<BF16>(e, i) : s_row[i]; };
+    float sq = 0.f, se = 0.f;
+    for (int i = threadIdx.x; i < Dl; i += blockDim.x) {
+      const float x = ld_elem<BF16>(a.q, i), y = ev_at(i);
+      sq = fmaf(x, x, sq);
+      se = fmaf(y, y, se);
+    }
+    sq = block_sum<float>(sq, red);
+    se = block_sum<float>(se, red);
+    const float eps = rnd<BF16>(1e-8f);
+    const float qn = fmaxf(rnd<BF16>(__fsqrt_rn(sq)), eps);
+    const float en = fmaxf(rnd<BF16>(__fsqrt_rn(se)), eps);
+    float dot = 0.f;
+    for (int i = threadIdx.x; i < Dl; i += blockDim.x) {
+      const float x = rnd<BF16>(__fdiv_rn(ld_elem<BF16>(a.q, i), qn));
+      const float y = rnd<BF16>(__fdiv_rn(ev_at(i), en));
+      dot += rnd<BF16>(__fmul_rn(x, y));
+    }
+    dot = block_sum<float>(dot, red);
+    if (threadIdx.x == 0) {
+      const float c = rnd<BF16>(dot);
+      if (BF16) reinterpret_cast<uint16_t*>(a.cos_out)[b] = (uint16_t)float_to_bf16_bits(c);
+      else reinterpret_cast<float*>(a.cos_out)[b] = c;
+      a.low[b] = c < a.threshold ? 1 : 0;
+    }
+  } else {
+    const int j = (b - a.k) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (j < a.k) reps_of_event(a.G, a.ldg, j, a.n_rep, a.ev_off, a.order, a.dist, a.reps, a.rep_counts, a.rep_flags);
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) is_last = (atomicAdd(a.ticket, 1u) == gridDim.x - 1) ? 1 : 0;
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  const int T = a.T;
+  const int per = (T + blockDim.x - 1) / blockDim.x;
+  const int beg = threadIdx.x * per, end = min(T, beg + per);
+  int cnt = 0;
+  for (int i = beg; i < end; ++i) {
+    const uint8_t f = (__ldcg(a.low + a.assign[i]) && !__ldcg(a.rep_flags + i)) ? 1 : 0;
+    a.minor_flags[i] = f;
+    cnt += f;
+  }
+  int pos = block_exclusive_scan(cnt, wt, &total);
+  for (int i = beg; i < end; ++i)
+    if (a.minor_flags[i]) a.minor_list[pos++] = i;
+  if (threadIdx.x == 0) {
+    *a.n_minor = total;
+    *a.ticket = 0;
+  }
+}
+
 // minor frames: flags + ascending list (single CTA scan)
 __global__ void __launch_bounds__(1024) minor_frames_kernel(const int64_t* __restrict__ assign, const uint8_t* __restrict__ low,
                                                             const uint8_t* __restrict__ rep, int T,
@@ -465,8 +595,12 @@ __device__ __forceinline__ uint32_t pix_smem_u32(const void* p) { return (uint32
 template <int NV, int kPixWarps, int kPixStages>
 __global__ void __launch_bounds__(kPixWarps * 32, 1) pixel_diff_tma_kernel(const uint8_t* __restrict__ pix, int t, int P, int Wv,
                                                                            int W, int F, float thr_cmp, float first_val,
-                                                                           uint8_t* __restrict__ mask) {
+                                                                           uint8_t* __restrict__ mask, int evict_first) {
   extern __shared__ __align__(128) uint8_t pix_smem[];
+  // the pixels are read exactly once: with `evict_first` their L2 lines are the first to go, so a latency-bound kernel of the same
+  // stream that runs concurrently (the k-means solver on its 2.9 MB Gram matrix) keeps its working set in L2
+  uint64_t l2_policy = 0;
+  if (evict_first) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(l2_policy));
   __shared__ __align__(8) uint64_t bars[kPixWarps][kPixStages];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint32_t row_bytes = (uint32_t)Wv * 16u;
@@ -491,10 +625,16 @@ __global__ void __launch_bounds__(kPixWarps * 32, 1) pixel_diff_tma_kernel(const
       const uint32_t slot = (it_base + (uint32_t)i) % kPixStages;
       const uint32_t bar = pix_smem_u32(&bars[warp][slot]);
       asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(row_bytes) : "memory");
-      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                       pix_smem_u32(ring + (size_t)slot * row_bytes)),
-                   "l"(src0 + (int64_t)i * fstride), "r"(row_bytes), "r"(bar)
-                   : "memory");
+      if (evict_first)
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+                         pix_smem_u32(ring + (size_t)slot * row_bytes)),
+                     "l"(src0 + (int64_t)i * fstride), "r"(row_bytes), "r"(bar), "l"(l2_policy)
+                     : "memory");
+      else
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                         pix_smem_u32(ring + (size_t)slot * row_bytes)),
+                     "l"(src0 + (int64_t)i * fstride), "r"(row_bytes), "r"(bar)
+                     : "memory");
     };
     if (lane == 0)
       for (int i = 0; i < kPixStages && i < nrows; ++i) issue(i);
@@ -741,7 +881,8 @@ __global__ void __launch_bounds__(1024) pool_emit_kernel(const uint4* __restrict
 // keep[i] = !is_image[i] || mask[rank_of_image(i)]
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kScanThreads) ids_image_count_kernel(const int64_t* __restrict__ ids, int64_t n, int64_t image_tok,
-                                                                        int* __restrict__ counts, int nchunks, unsigned* ticket) {
+                                                                        int* __restrict__ counts, int nchunks, unsigned* ticket,
+                                                                        int64_t* __restrict__ n_image) {
   __shared__ int wt[32];
   __shared__ int stotal;
   const int64_t base = (int64_t)blockIdx.x * kScanChunk + threadIdx.x * kScanItems;
@@ -757,7 +898,7 @@ __global__ void __launch_bounds__(kScanThreads) ids_image_count_kernel(const int
     for (int w = 0; w < kScanThreads / 32; ++w) t += wt[w];
     counts[blockIdx.x] = t;
   }
-  finish_chunk_scan(counts, nchunks, ticket, nullptr, wt, &stotal);
+  finish_chunk_scan(counts, nchunks, ticket, n_image, wt, &stotal);
 }
 
 template <bool SCATTER>
@@ -867,9 +1008,12 @@ __global__ void __launch_bounds__(kScanThreads) ids_filter_coop_kernel(const int
     icnt += img[u];
   }
   const int iex = block_exclusive_scan(icnt, wt, &stotal);
-  if (threadIdx.x == 0) img_counts[blockIdx.x] = stotal;
+  const int itot = stotal;
+  if (threadIdx.x == 0) img_counts[blockIdx.x] = itot;
   scan_grid_sync(barrier, bar);
-  int r = chunk_prefix(img_counts, wt, &stotal) + iex;  // rank of this thread's first <image> id
+  const int ipre = chunk_prefix(img_counts, wt, &stotal);
+  if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) n_out[1] = (int64_t)ipre + itot;  // <image> ids seen
+  int r = ipre + iex;  // rank of this thread's first <image> id
   int keep[kScanItems], kcnt = 0;
 #pragma unroll
   for (int u = 0; u < kScanItems; ++u) {
@@ -928,6 +1072,169 @@ __global__ void __launch_bounds__(kScanThreads) compact_scan_coop_kernel(const u
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Phase-2 tail in ONE cooperative launch (cogreasoner_chat.py:413-422 + :458-474): per-frame mask rules (min_tokens padding,
+// minor-frame override), the token scan (positions, kept_index, n_kept) and the id filter (image rank -> keep -> scatter).
+// Token chunks are whole frames (fpc = 1024 / P frames per CTA) so that the per-frame rules are CTA-local; id chunks are 1024
+// ids.  Two grid barriers; the barrier word is never reset: every launch starts from the epoch the previous one left behind
+// (block 0 publishes it after the last barrier), so no memset node precedes the kernel.
+// ------------------------------------------------------------------------------------------------
+struct CompactStreamArgs {
+  uint8_t* mask;  // [T*P] in: raw difference mask, out: final mask
+  int T, P, fpc, n_tok_chunks, min_tokens, finalize;
+  const uint8_t* minor;  // [T] or nullptr
+  int* counts;
+  int32_t* pos;
+  int32_t* kept_index;
+  int64_t* n_kept;
+  const int64_t* ids;
+  int64_t n_ids;
+  int64_t image_tok;
+  int n_id_chunks;
+  const int64_t* attn;
+  const int64_t* labels;
+  int* img_counts;
+  int* keep_counts;
+  int64_t* o_ids;
+  int64_t* o_attn;
+  int64_t* o_labels;
+  int64_t* n_out;  // [2]: kept ids, <image> ids seen
+  unsigned* barrier;  // [0] arrival counter, [1] epoch (value of the counter when the launch started)
+};
+
+__device__ __forceinline__ void epoch_grid_sync(unsigned* counter, unsigned& target) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    target += gridDim.x;
+    __threadfence();
+    atomicAdd(counter, 1u);
+    unsigned v;
+    do {
+      asm volatile("ld.acquire.gpu.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
+    } while ((int)(v - target) < 0);
+  }
+  __syncthreads();
+}
+
+// sum of counts[0 .. c) by the whole CTA
+__device__ __forceinline__ int chunk_prefix_to(const int* counts, int c, int* wt, int* stotal) {
+  int v = 0;
+  for (int b = threadIdx.x; b < c; b += blockDim.x) v += __ldcg(counts + b);
+  block_exclusive_scan(v, wt, stotal);
+  const int t = *stotal;
+  __syncthreads();
+  return t;
+}
+
+__global__ void __launch_bounds__(kScanThreads) compact_stream_coop_kernel(CompactStreamArgs a) {
+  __shared__ int wt[32];
+  __shared__ int stotal;
+  __shared__ uint8_t s_m[kScanChunk];
+  const int c = blockIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  unsigned bar = *reinterpret_cast<volatile unsigned*>(a.barrier + 1);
+  const bool tok = c < a.n_tok_chunks, idc = c < a.n_id_chunks;
+  const int P = a.P;
+  // ---- A. per-frame rules + chunk counts ----
+  const int f0 = c * a.fpc, f1 = min(a.T, f0 + a.fpc);
+  const int64_t tbase = (int64_t)f0 * P;
+  const int ntok = tok ? (f1 - f0) * P : 0;
+  int f[kScanItems], cnt = 0, ex = 0, tot = 0;
+  if (tok) {
+    for (int fr = f0 + warp; fr < f1; fr += kScanThreads / 32) {
+      uint8_t* m = a.mask + (int64_t)fr * P;
+      uint8_t* sm = s_m + (fr - f0) * P;
+      if (!a.finalize) {
+        for (int p = lane; p < P; p += 32) sm[p] = m[p] ? 1 : 0;
+      } else if (a.minor && a.minor[fr]) {  // :416-422 minor frames keep only token 0
+        for (int p = lane; p < P; p += 32) { const uint8_t v = p == 0 ? 1 : 0; sm[p] = v; m[p] = v; }
+      } else {
+        int kept = 0;
+        for (int p = lane; p < P; p += 32) { const uint8_t v = m[p] ? 1 : 0; sm[p] = v; kept += v; }
+        kept = warp_sum(kept);
+        if (kept < a.min_tokens)  // :413-414
+          for (int p = lane; p < a.min_tokens && p < P; p += 32) { sm[p] = 1; m[p] = 1; }
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int u = 0; u < kScanItems; ++u) {
+      const int sl = threadIdx.x * kScanItems + u;
+      f[u] = (sl < ntok && s_m[sl]) ? 1 : 0;
+      cnt += f[u];
+    }
+    ex = block_exclusive_scan(cnt, wt, &stotal);
+    tot = stotal;
+    if (threadIdx.x == 0) a.counts[c] = tot;
+    __syncthreads();
+  }
+  const int64_t ibase = (int64_t)c * kScanChunk + threadIdx.x * kScanItems;
+  int64_t v[kScanItems];
+  int img[kScanItems], icnt = 0, iex = 0, itot = 0;
+  if (idc) {
+#pragma unroll
+    for (int u = 0; u < kScanItems; ++u) {
+      v[u] = ibase + u < a.n_ids ? a.ids[ibase + u] : 0;
+      img[u] = (ibase + u < a.n_ids && v[u] == a.image_tok) ? 1 : 0;
+      icnt += img[u];
+    }
+    iex = block_exclusive_scan(icnt, wt, &stotal);
+    itot = stotal;
+    if (threadIdx.x == 0) a.img_counts[c] = itot;
+  }
+  epoch_grid_sync(a.barrier, bar);
+  // ---- B. token positions; id keep flags ----
+  if (tok) {
+    const int pre = chunk_prefix_to(a.counts, c, wt, &stotal);
+    if (c == a.n_tok_chunks - 1 && threadIdx.x == 0) *a.n_kept = (int64_t)pre + tot;
+    int lp = pre + ex;
+#pragma unroll
+    for (int u = 0; u < kScanItems; ++u) {
+      const int sl = threadIdx.x * kScanItems + u;
+      if (sl < ntok) {
+        a.pos[tbase + sl] = lp;
+        if (f[u]) a.kept_index[lp++] = (int32_t)(tbase + sl);
+      }
+    }
+  }
+  int keep[kScanItems], kcnt = 0, kex = 0, ktot = 0;
+  if (idc) {
+    const int ipre = chunk_prefix_to(a.img_counts, c, wt, &stotal);
+    if (c == a.n_id_chunks - 1 && threadIdx.x == 0) a.n_out[1] = (int64_t)ipre + itot;
+    int r = ipre + iex;
+    const int64_t n_mask = (int64_t)a.T * P;
+#pragma unroll
+    for (int u = 0; u < kScanItems; ++u) {
+      keep[u] = ibase + u < a.n_ids ? 1 : 0;
+      if (img[u]) {
+        keep[u] = (r < n_mask && __ldcg(a.mask + r)) ? 1 : 0;  // the final mask was written by other CTAs: read it from L2
+        ++r;
+      }
+      kcnt += keep[u];
+    }
+    kex = block_exclusive_scan(kcnt, wt, &stotal);
+    ktot = stotal;
+    if (threadIdx.x == 0) a.keep_counts[c] = ktot;
+  }
+  epoch_grid_sync(a.barrier, bar);
+  if (c == 0 && threadIdx.x == 0) a.barrier[1] = bar;  // every CTA has read the old epoch long ago: publish the next one
+  // ---- C. id scatter ----
+  if (idc) {
+    const int kpre = chunk_prefix_to(a.keep_counts, c, wt, &stotal);
+    if (c == a.n_id_chunks - 1 && threadIdx.x == 0) a.n_out[0] = (int64_t)kpre + ktot;
+    int p = kpre + kex;
+#pragma unroll
+    for (int u = 0; u < kScanItems; ++u) {
+      if (keep[u]) {
+        a.o_ids[p] = v[u];
+        if (a.attn) a.o_attn[p] = a.attn[ibase + u];
+        if (a.labels) a.o_labels[p] = a.labels[ibase + u];
+        ++p;
+      }
+    }
+  }
+}
+
 // number of CTAs of `kernel` (kScanThreads threads, no dynamic shared memory) that can be co-resident on the current device
 template <typename K>
 static int coop_capacity(K kernel) {
@@ -956,6 +1263,7 @@ __global__ void __launch_bounds__(1024) filter_ids_kernel(const int64_t* __restr
   int cnt = 0;
   for (int64_t i = beg; i < end; ++i) cnt += ids[i] == image_tok;
   int irank = block_exclusive_scan(cnt, wt, &total);
+  const int img_total = total;
   // pass 2: kept count
   int kept = 0, r = irank;
   for (int64_t i = beg; i < end; ++i) {
@@ -977,7 +1285,7 @@ __global__ void __launch_bounds__(1024) filter_ids_kernel(const int64_t* __restr
       ++opos;
     }
   }
-  if (threadIdx.x == 0) *n_out = out_total;
+  if (threadIdx.x == 0) { n_out[0] = out_total; n_out[1] = img_total; }
   if (!posids) return;
   // position ids restart at every kept element whose old position id was 0 (:472-474): running max of starts
   __syncthreads();
@@ -1138,10 +1446,12 @@ int csb_pixel_diff(const void* pixels, int64_t t, int64_t P, int64_t W, int32_t 
       int waves = 4;
       if (const char* o = getenv("CSB_PIX_WAVES")) waves = atoi(o) > 0 ? atoi(o) : 4;
       if (gb > (int64_t)kNumSMs * waves) gb = (int64_t)kNumSMs * waves;
+      if (const char* o = getenv("CSB_PIX_CTAS")) { if (atoi(o) > 0 && gb > atoi(o)) gb = atoi(o); }  // throttled grid (overlap experiments)
+      const int evict_first = getenv("CSB_PIX_EVICT") ? atoi(getenv("CSB_PIX_EVICT")) : 0;
       auto launch = [&](auto kern) -> int {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring_bytes);
         if (e != cudaSuccess) { set_error("pixel_diff: smem attr: %s", cudaGetErrorString(e)); return CSB_ERR_CUDA; }
-        kern<<<(unsigned)gb, pw * 32, ring_bytes, s>>>((const uint8_t*)pixels, (int)t, (int)P, (int)Wv, (int)W, F, thr, first, mask);
+        kern<<<(unsigned)gb, pw * 32, ring_bytes, s>>>((const uint8_t*)pixels, (int)t, (int)P, (int)Wv, (int)W, F, thr, first, mask, evict_first);
         return check_launch("pixel_diff_tma");
       };
 #define CSB_PIX_DISPATCH(NVV)                                                       \
@@ -1238,6 +1548,123 @@ int csb_compact_tokens(const void* x, int64_t T, int64_t P, int64_t D, const uin
   return csb_gather_rows(x, D * 2, kept_index, 0, n_kept, n, out, stream);
 }
 
+size_t csb_compact_stream_workspace_bytes(int64_t n_tokens, int64_t n_ids) {
+  const int64_t n = ws_n(n_tokens, n_ids);
+  const size_t own = align_up(sizeof(int32_t) * (size_t)n, 256) + 3 * align_up(sizeof(int32_t) * (size_t)(n + 1), 256) + 256;
+  const size_t fallback = csb_compact_workspace_bytes(n_tokens, n_ids);
+  return own > fallback ? own : fallback;
+}
+
+int csb_compact_stream(const csb_compact_args* p, csb_stream_t stream) {
+  CSB_DEVICE_OR_RETURN();
+  CSB_REQUIRE(p, "compact_stream: null args");
+  CSB_REQUIRE(p->x_bf16 && p->mask && p->out_bf16 && p->kept_index && p->n_kept && p->workspace && p->T > 0 && p->P > 0 && p->D > 0,
+              "compact_stream: null argument or empty shape");
+  CSB_REQUIRE(p->D % 8 == 0, "compact_stream: D %% 8 != 0");
+  CSB_REQUIRE(!p->input_ids || (p->out_ids && p->n_out && p->n_ids > 0), "compact_stream: input_ids given without outputs");
+  CSB_REQUIRE(!p->attention_mask || p->out_attention_mask, "compact_stream: attention_mask given without output");
+  CSB_REQUIRE(!p->labels || p->out_labels, "compact_stream: labels given without output");
+  CSB_REQUIRE(!p->pool_minor || p->minor_flags, "compact_stream: pool_minor needs minor_flags");
+  const int64_t T = p->T, P = p->P, n = T * P, n_ids = p->input_ids ? p->n_ids : 0;
+  CSB_REQUIRE(n < (1ll << 31) && n_ids < (1ll << 31), "compact_stream: too many tokens / ids");
+  if (p->workspace_bytes < csb_compact_stream_workspace_bytes(n, n_ids)) { set_error("compact_stream: workspace too small"); return CSB_ERR_WORKSPACE; }
+  cudaStream_t s = as_stream(stream);
+  const int fpc = P <= kScanChunk ? (int)(kScanChunk / P) : 0;
+  const int n_tok_chunks = fpc ? (int)((T + fpc - 1) / fpc) : 0;
+  const int n_id_chunks = (int)ws_chunks(n_ids);
+  const int grid = n_tok_chunks > n_id_chunks ? n_tok_chunks : n_id_chunks;
+  static thread_local int cap = -1;
+  if (cap < 0) cap = coop_capacity(compact_stream_coop_kernel);
+  const uint8_t* pool_flags = p->pool_minor ? p->minor_flags : nullptr;
+  if (!fpc || grid > cap || getenv("CSB_NO_COOP_SCAN")) {  // frames longer than a chunk, or more chunks than co-resident CTAs
+    int st = CSB_OK;
+    if (p->finalize) st = csb_mask_finalize(p->mask, T, P, p->min_tokens, p->minor_flags, 0, stream);
+    if (st) return st;
+    st = csb_compact_tokens(p->x_bf16, T, P, p->D, p->mask, pool_flags, p->out_bf16, p->kept_index, p->n_kept, p->workspace,
+                            p->workspace_bytes, stream);
+    if (st || !p->input_ids) return st;
+    // (csb_compact_tokens has consumed its part of the workspace by the time the id filter runs: same stream)
+    return csb_filter_ids(p->input_ids, n_ids, p->image_token_index, p->mask, n, p->attention_mask, p->labels, nullptr, p->out_ids,
+                          p->out_attention_mask, p->out_labels, nullptr, p->n_out, p->workspace, p->workspace_bytes, stream);
+  }
+  const int64_t nn = ws_n(n, n_ids);
+  char* w = reinterpret_cast<char*>(p->workspace);
+  const size_t cbytes = align_up(sizeof(int32_t) * (size_t)(nn + 1), 256);
+  CompactStreamArgs a;
+  a.mask = p->mask; a.T = (int)T; a.P = (int)P; a.fpc = fpc; a.n_tok_chunks = n_tok_chunks; a.min_tokens = (int)p->min_tokens;
+  a.finalize = p->finalize; a.minor = p->minor_flags;
+  a.pos = reinterpret_cast<int32_t*>(w);
+  w += align_up(sizeof(int32_t) * (size_t)nn, 256);
+  a.counts = reinterpret_cast<int*>(w); a.img_counts = reinterpret_cast<int*>(w + cbytes); a.keep_counts = reinterpret_cast<int*>(w + 2 * cbytes);
+  a.barrier = reinterpret_cast<unsigned*>(w + 3 * cbytes);
+  a.kept_index = p->kept_index; a.n_kept = p->n_kept;
+  a.ids = p->input_ids; a.n_ids = n_ids; a.image_tok = p->image_token_index; a.n_id_chunks = n_id_chunks;
+  a.attn = p->attention_mask; a.labels = p->labels; a.o_ids = p->out_ids; a.o_attn = p->out_attention_mask; a.o_labels = p->out_labels;
+  a.n_out = p->n_out;
+  void* args[] = {(void*)&a};
+  cudaError_t e = cudaLaunchCooperativeKernel((const void*)compact_stream_coop_kernel, dim3((unsigned)grid), dim3(kScanThreads), args, 0, s);
+  if (e != cudaSuccess) { set_error("compact_stream: cooperative launch: %s", cudaGetErrorString(e)); return CSB_ERR_CUDA; }
+  count_launch(1);
+  if (pool_flags) {
+    const int Dv = (int)(p->D / 8);
+    const int tx = Dv >= 256 ? 256 : ((Dv + 31) / 32) * 32;
+    const size_t smem = (size_t)(kPoolGroups - 1) * tx * 8 * sizeof(float);
+    int64_t gblocks = (n * Dv + (int64_t)tx * kPoolGroups * 4 - 1) / ((int64_t)tx * kPoolGroups * 4);
+    if (gblocks > kNumSMs * 4) gblocks = kNumSMs * 4;
+    if (gblocks < 1) gblocks = 1;
+    pool_emit_kernel<<<(unsigned)(T + gblocks), dim3(tx, kPoolGroups), smem, s>>>((const uint4*)p->x_bf16, (int)P, Dv, pool_flags, p->mask, a.pos,
+                                                                                   (uint4*)p->out_bf16, (int)T, p->kept_index, p->n_kept);
+    return check_launch("pool_emit");
+  }
+  return csb_gather_rows(p->x_bf16, p->D * 2, p->kept_index, 0, p->n_kept, n, p->out_bf16, stream);
+}
+
+size_t csb_relevance_select_workspace_bytes(int64_t k, int64_t Dl) {
+  if (k <= 0 || Dl <= 0) return 256;
+  return align_up(sizeof(float) * (size_t)k * kRelSplits * (size_t)Dl, 256);
+}
+
+int csb_relevance_select(const csb_relevance_args* p, csb_stream_t stream) {
+  CSB_DEVICE_OR_RETURN();
+  CSB_REQUIRE(p, "relevance_select: null args");
+  CSB_REQUIRE(p->question && p->cos_out && p->low_flags && p->assignments && p->minor_flags && p->minor_list && p->n_minor && p->ticket &&
+                  p->k > 0 && p->Dl > 0 && p->T > 0,
+              "relevance_select: null argument");
+  CSB_REQUIRE(p->gram && p->event_offsets && p->event_order && p->dist && p->reps && p->rep_counts && p->rep_flags && p->n_rep > 0 &&
+                  p->ldg >= p->T,
+              "relevance_select: null selection argument or ldg < T");
+  CSB_REQUIRE((p->events != nullptr) != (p->hidden != nullptr), "relevance_select: give either events [k,Dl] or the packed hidden states");
+  CSB_REQUIRE(p->dtype == CSB_BF16 || p->dtype == CSB_F32, "relevance_select: dtype must be bf16 or f32");
+  cudaStream_t s = as_stream(stream);
+  RelevanceArgs a;
+  a.q = p->question; a.ev = p->events; a.partials = nullptr; a.cu = p->cu_seqlens; a.k = (int)p->k; a.Dl = (int)p->Dl;
+  a.threshold = p->dtype == CSB_BF16 ? __bfloat162float(__float2bfloat16_rn((float)p->threshold)) : (float)p->threshold;
+  a.G = p->gram; a.ldg = p->ldg; a.ev_off = p->event_offsets; a.order = p->event_order; a.n_rep = (int)p->n_rep;
+  a.assign = p->assignments; a.T = (int)p->T; a.ev_out = p->events_out; a.cos_out = p->cos_out; a.low = p->low_flags; a.dist = p->dist;
+  a.reps = p->reps; a.rep_counts = p->rep_counts; a.rep_flags = p->rep_flags; a.minor_flags = p->minor_flags; a.minor_list = p->minor_list;
+  a.n_minor = p->n_minor; a.ticket = p->ticket;
+  size_t smem = 0;
+  if (p->hidden) {
+    CSB_REQUIRE(p->cu_seqlens && p->workspace, "relevance_select: hidden states need cu_seqlens and a workspace");
+    if (p->workspace_bytes < csb_relevance_select_workspace_bytes(p->k, p->Dl)) { set_error("relevance_select: workspace too small"); return CSB_ERR_WORKSPACE; }
+    int st = launch_seq_pool_partial(p->hidden, p->cu_seqlens, p->k, p->Dl, p->dtype, reinterpret_cast<float*>(p->workspace), s);
+    if (st) return st;
+    a.partials = reinterpret_cast<const float*>(p->workspace);
+    smem = sizeof(float) * (size_t)p->Dl;
+    CSB_REQUIRE(smem <= 200 * 1024, "relevance_select: Dl too large for the fused pool (Dl <= 51200)");
+  }
+  const unsigned grid = (unsigned)(p->k + (p->k + 7) / 8);
+  auto launch = [&](auto kern) -> int {
+    if (smem > 48 * 1024) {
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) { set_error("relevance_select: smem attr: %s", cudaGetErrorString(e)); return CSB_ERR_CUDA; }
+    }
+    kern<<<grid, 256, smem, s>>>(a);
+    return check_launch("relevance_select");
+  };
+  return p->dtype == CSB_BF16 ? launch(relevance_select_kernel<true>) : launch(relevance_select_kernel<false>);
+}
+
 int csb_filter_ids(const int64_t* input_ids, int64_t n_ids, int64_t image_token_index, const uint8_t* mask, int64_t n_mask,
                    const int64_t* attention_mask, const int64_t* labels, const int64_t* position_ids, int64_t* out_ids,
                    int64_t* out_attention_mask, int64_t* out_labels, int64_t* out_position_ids, int64_t* n_out, void* workspace,
@@ -1272,7 +1699,7 @@ int csb_filter_ids(const int64_t* input_ids, int64_t n_ids, int64_t image_token_
       count_launch(1);
       return CSB_OK;
     }
-    ids_image_count_kernel<<<nchunks, kScanThreads, 0, s>>>(input_ids, n_ids, image_token_index, img_prefix, nchunks, ticket);
+    ids_image_count_kernel<<<nchunks, kScanThreads, 0, s>>>(input_ids, n_ids, image_token_index, img_prefix, nchunks, ticket, n_out + 1);
     int st = check_launch("ids_image_count");
     if (st) return st;
     ids_keep_kernel<false><<<nchunks, kScanThreads, 0, s>>>(input_ids, n_ids, image_token_index, mask, n_mask, img_prefix, keep_prefix,

@@ -72,8 +72,10 @@ def _as_bf16_frames(features: torch.Tensor) -> torch.Tensor:
 def kmeans_with_time_min_max(features, timestamp, cluster_num, alpha=2, max_iteration=30, tol=1e-4, *,
                              init_indices: Optional[Sequence[int]] = None, exp_noise: Optional[torch.Tensor] = None,
                              reseed_indices: Optional[Sequence[int]] = None, first_index: Optional[int] = None,
-                             gram_impl: int = 0, return_info: bool = False):
-    """See module docstring.  Extra keyword-only arguments default to the reference behaviour."""
+                             gram_impl: int = 0, return_info: bool = False, return_centroids: bool = True):
+    """See module docstring.  Extra keyword-only arguments default to the reference behaviour.  ``return_centroids=False``
+    skips the streaming pass that produces the fp32 centroids (first element ``None``): callers that select from the Gram matrix
+    (``select_events_based_on_summary``) never read them."""
     x3 = _as_bf16_frames(features)
     dev = x3.device
     if not isinstance(timestamp, torch.Tensor):  # kmeans_with_time.py:26-27
@@ -146,7 +148,7 @@ def kmeans_with_time_min_max(features, timestamp, cluster_num, alpha=2, max_iter
         for _ in range(st["n_noise_used"]):
             scratch.exponential_(1)
 
-    centroids = ops.centroid_update(x2, buf.member_offsets, buf.members, k).view(k, P, D)  # :134
+    centroids = ops.centroid_update(x2, buf.member_offsets, buf.members, k).view(k, P, D) if return_centroids else None  # :134
     out = (centroids, buf.centroid_times, buf.assignments)
     if return_info:
         info = KMeansRunInfo(buf.init_indices, st["iterations"], st["converged"], st["n_reseed_used"], st["degenerate_rounds"],

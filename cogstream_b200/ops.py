@@ -12,7 +12,7 @@ from typing import Optional, Tuple
 import torch
 
 from . import _lib
-from ._lib import CSB_BF16, CSB_F32, CSB_F64, KMeansParams, STATUS_WORDS, check
+from ._lib import CSB_BF16, CSB_F32, CSB_F64, CompactArgs, KMeansParams, RelevanceArgs, STATUS_WORDS, check
 
 _TS_DTYPE = {torch.float32: CSB_F32, torch.float64: CSB_F64}
 _EL_DTYPE = {torch.float32: CSB_F32, torch.bfloat16: CSB_BF16}
@@ -429,7 +429,8 @@ def compact_tokens(x: torch.Tensor, T: int, P: int, mask: torch.Tensor, pool_fla
 def filter_ids(input_ids: torch.Tensor, image_token_index: int, mask: torch.Tensor,
                attention_mask: Optional[torch.Tensor] = None, labels: Optional[torch.Tensor] = None,
                position_ids: Optional[torch.Tensor] = None):
-    """-> (out_ids, out_attention_mask, out_labels, out_position_ids, n_out [1] int64); outputs sized like the inputs."""
+    """-> (out_ids, out_attention_mask, out_labels, out_position_ids, n_out [2] int64 = {ids kept, <image> ids seen}); outputs
+    sized like the inputs.  The caller compares ``n_out[1]`` with ``mask.numel()`` (the reference raises when they differ)."""
     _need(input_ids, "input_ids", torch.int64, 1)
     _need(mask, "mask", torch.uint8, 1)
     n = input_ids.shape[0]
@@ -447,7 +448,7 @@ def filter_ids(input_ids: torch.Tensor, image_token_index: int, mask: torch.Tens
     lb, o_lb = _opt(labels, "labels")
     ps, o_ps = _opt(position_ids, "position_ids")
     o_ids = torch.empty_like(input_ids)
-    n_out = torch.empty(1, dtype=torch.int64, device=dev)
+    n_out = torch.empty(2, dtype=torch.int64, device=dev)
     ws = torch.empty(compact_workspace_bytes(0, n), dtype=torch.uint8, device=dev)
     with _on_device(input_ids):
         check(_lib.load().csb_filter_ids(input_ids.data_ptr(), n, int(image_token_index), mask.data_ptr(), mask.shape[0],
@@ -456,11 +457,124 @@ def filter_ids(input_ids: torch.Tensor, image_token_index: int, mask: torch.Tens
     return o_ids, o_am, o_lb, o_ps, n_out
 
 
+def compact_stream_workspace(n_tokens: int, n_ids: int, device) -> torch.Tensor:
+    """Zero-filled workspace of :func:`compact_stream` (it carries the barrier epoch from launch to launch: one per CUDA stream)."""
+    return torch.zeros(int(_lib.load().csb_compact_stream_workspace_bytes(n_tokens, n_ids)), dtype=torch.uint8, device=device)
+
+
+def compact_stream(x: torch.Tensor, T: int, P: int, mask: torch.Tensor, minor_flags: Optional[torch.Tensor], *, min_tokens: int = 1,
+                   finalize: bool = True, pool_minor: bool = True, input_ids: Optional[torch.Tensor] = None,
+                   image_token_index: int = -1, attention_mask: Optional[torch.Tensor] = None, labels: Optional[torch.Tensor] = None,
+                   out: Optional[torch.Tensor] = None, workspace: Optional[torch.Tensor] = None, bufs: Optional[dict] = None):
+    """Phase-2 tail in one entry point: per-frame mask rules (in place on ``mask``), token compaction with the pooled token of the
+    minor frames, id filtering.  -> dict(out [T*P, D], kept_index [T*P] i32, n_kept [1] i64, out_ids, out_attention, out_labels,
+    n_out [2] i64 = {ids kept, <image> ids seen}).  ``bufs``: a dict of pre-allocated outputs to reuse (same keys)."""
+    _need(x, "x", torch.bfloat16, 2)
+    _need(mask, "mask", torch.uint8, 1)
+    D = x.shape[1]
+    n = T * P
+    dev = x.device
+    b = bufs if bufs is not None else {}
+
+    def buf(name, shape, dtype):
+        t = b.get(name)
+        if t is None:
+            t = torch.empty(shape, dtype=dtype, device=dev)
+            b[name] = t
+        return t
+
+    o = out if out is not None else buf("out", (n, D), torch.bfloat16)
+    b["out"] = o
+    kept = buf("kept_index", (n,), torch.int32)
+    n_kept = buf("n_kept", (1,), torch.int64)
+    n_ids = 0
+    o_ids = o_am = o_lb = n_out = None
+    if input_ids is not None:
+        _need(input_ids, "input_ids", torch.int64, 1)
+        n_ids = input_ids.shape[0]
+        o_ids = buf("out_ids", (n_ids,), torch.int64)
+        n_out = buf("n_out", (2,), torch.int64)
+        if attention_mask is not None:
+            if attention_mask.dtype != torch.int64:
+                attention_mask = attention_mask.to(torch.int64)
+            o_am = buf("out_attention", (n_ids,), torch.int64)
+        if labels is not None:
+            if labels.dtype != torch.int64:
+                labels = labels.to(torch.int64)
+            o_lb = buf("out_labels", (n_ids,), torch.int64)
+    need = int(_lib.load().csb_compact_stream_workspace_bytes(n, n_ids))
+    ws = workspace if workspace is not None and workspace.numel() >= need else torch.zeros(need, dtype=torch.uint8, device=dev)
+    a = CompactArgs(x.data_ptr(), T, P, D, mask.data_ptr(), _ptr(minor_flags), int(min_tokens), 1 if finalize else 0,
+                    1 if (pool_minor and minor_flags is not None) else 0, _ptr(input_ids), n_ids, int(image_token_index),
+                    _ptr(attention_mask), _ptr(labels), o.data_ptr(), kept.data_ptr(), n_kept.data_ptr(), _ptr(o_ids), _ptr(o_am),
+                    _ptr(o_lb), _ptr(n_out), ws.data_ptr(), ws.numel())
+    with _on_device(x):
+        check(_lib.load().csb_compact_stream(C.byref(a), _stream(x)), "compact_stream")
+    return b
+
+
+def relevance_select(question: torch.Tensor, events: Optional[torch.Tensor], G: torch.Tensor, event_offsets: torch.Tensor,
+                     event_order: torch.Tensor, assignments: torch.Tensor, ticket: torch.Tensor, *, k: int, n_rep: int = 2,
+                     threshold: float = 0.45, hidden: Optional[torch.Tensor] = None, cu_seqlens: Optional[torch.Tensor] = None,
+                     bufs: Optional[dict] = None):
+    """Selection step of phase 2 in one launch: cosine flags of the k events, representatives from the Gram matrix, minor-frame
+    list.  Event embeddings: ``events`` [k, Dl], or the packed ``hidden`` states + ``cu_seqlens`` of the k summary forwards (their
+    mean pool is then fused in; the pooled rows are returned as ``events``).
+    -> dict(cos, low, dist, reps, rep_counts, rep_flags, minor_flags, minor_list, n_minor[, events])."""
+    T, ldg = _gram_view(G)
+    src = events if events is not None else hidden
+    _need(src, "events / hidden", None, 2)
+    if src.dtype not in _EL_DTYPE:
+        raise TypeError(f"relevance_select: dtype must be bfloat16 or float32, got {src.dtype}")
+    _need(question, "question", src.dtype, 1)
+    Dl = src.shape[1]
+    dev = src.device
+    b = bufs if bufs is not None else {}
+
+    def buf(name, shape, dtype):
+        t = b.get(name)
+        if t is None:
+            t = torch.empty(shape, dtype=dtype, device=dev)
+            b[name] = t
+        return t
+
+    cos = buf("cos", (k,), src.dtype)
+    low = buf("low", (k,), torch.uint8)
+    dist = buf("dist", (T,), torch.float32)
+    reps = buf("reps", (k, n_rep), torch.int64)
+    counts = buf("rep_counts", (k,), torch.int32)
+    rflags = buf("rep_flags", (T,), torch.uint8)
+    mflags = buf("minor_flags", (T,), torch.uint8)
+    mlist = buf("minor_list", (T,), torch.int32)
+    n_minor = buf("n_minor", (1,), torch.int64)
+    ev_out = ws = None
+    if events is None:
+        _need(cu_seqlens, "cu_seqlens", torch.int32, 1)
+        if cu_seqlens.shape[0] != k + 1:
+            raise ValueError("relevance_select: cu_seqlens must have k + 1 entries")
+        ev_out = buf("events", (k, Dl), src.dtype)
+        ws = buf("pool_ws", (int(_lib.load().csb_relevance_select_workspace_bytes(k, Dl)),), torch.uint8)
+    elif events.shape[0] != k:
+        raise ValueError("relevance_select: events must have k rows")
+    a = RelevanceArgs(question.data_ptr(), _ptr(events), _ptr(hidden) if events is None else None, _ptr(cu_seqlens) if events is None else None,
+                      k, Dl, _EL_DTYPE[src.dtype], 0, float(threshold), G.data_ptr(), ldg, event_offsets.data_ptr(), event_order.data_ptr(),
+                      int(n_rep), assignments.data_ptr(), T, _ptr(ev_out), cos.data_ptr(), low.data_ptr(), dist.data_ptr(), reps.data_ptr(),
+                      counts.data_ptr(), rflags.data_ptr(), mflags.data_ptr(), mlist.data_ptr(), n_minor.data_ptr(), ticket.data_ptr(),
+                      _ptr(ws), 0 if ws is None else ws.numel())
+    with _on_device(src):
+        check(_lib.load().csb_relevance_select(C.byref(a), _stream(src)), "relevance_select")
+    return b
+
+
 def embed_scatter(input_ids: torch.Tensor, image_token_index: int, embed_weight: torch.Tensor, features: Optional[torch.Tensor],
-                  *, out: Optional[torch.Tensor] = None, check_count: bool = True):
+                  *, out: Optional[torch.Tensor] = None, check_count: bool = True, frame_order: Optional[torch.Tensor] = None,
+                  tokens_per_frame: int = 1):
     """``embed_tokens(input_ids)`` with the rows of the <image> ids replaced by ``embeds * 0.0 + features``
     (cogreasoner_chat.py:303-305, :567-572) in one pass.  ``input_ids`` [n] int64 may be several prompts packed back to back;
     ``features`` [n_image, D] are consumed in order.  -> (inputs_embeds [n, D], status [2] int32 = {n_image, n_bad_ids}).
+
+    ``frame_order`` [T] int32 + ``tokens_per_frame``: read the feature rows through the chronological per-event frame order
+    (the j-th <image> id takes row ``frame_order[j // P] * P + j % P``) -- the event gather of :286-296 folded into this pass.
 
     ``check_count=True`` reads the status back (one sync) and raises like the reference's index assignment would when the
     number of <image> ids differs from the number of feature rows, or an id is outside the table."""
@@ -481,10 +595,20 @@ def embed_scatter(input_ids: torch.Tensor, image_token_index: int, embed_weight:
     status = torch.empty(2, dtype=torch.int32, device=dev)
     ws = torch.empty(int(_lib.load().csb_embed_scatter_workspace_bytes(n)), dtype=torch.uint8, device=dev)
     with _on_device(input_ids):
-        check(_lib.load().csb_embed_scatter(input_ids.data_ptr(), n, int(image_token_index), embed_weight.data_ptr(), vocab,
-                                            features.data_ptr() if features.shape[0] else None, features.shape[0], D,
-                                            _EL_DTYPE[embed_weight.dtype], o.data_ptr(), status.data_ptr(), ws.data_ptr(),
-                                            ws.numel(), _stream(input_ids)), "embed_scatter")
+        if frame_order is not None:
+            _need(frame_order, "frame_order", torch.int32, 1)
+            if frame_order.shape[0] * int(tokens_per_frame) != features.shape[0]:
+                raise ValueError("embed_scatter: frame_order x tokens_per_frame does not cover the feature rows")
+            check(_lib.load().csb_embed_scatter_ordered(input_ids.data_ptr(), n, int(image_token_index), embed_weight.data_ptr(), vocab,
+                                                        features.data_ptr(), frame_order.data_ptr(), frame_order.shape[0],
+                                                        int(tokens_per_frame), D, _EL_DTYPE[embed_weight.dtype], o.data_ptr(),
+                                                        status.data_ptr(), ws.data_ptr(), ws.numel(), _stream(input_ids)),
+                  "embed_scatter_ordered")
+        else:
+            check(_lib.load().csb_embed_scatter(input_ids.data_ptr(), n, int(image_token_index), embed_weight.data_ptr(), vocab,
+                                                features.data_ptr() if features.shape[0] else None, features.shape[0], D,
+                                                _EL_DTYPE[embed_weight.dtype], o.data_ptr(), status.data_ptr(), ws.data_ptr(),
+                                                ws.numel(), _stream(input_ids)), "embed_scatter")
     if check_count:
         n_img, n_bad = status.tolist()
         if n_bad:

@@ -47,7 +47,7 @@ class StreamConfig:
     # results() raise (the kernel has substituted frame 0, which is not what the reference would have drawn).
     reseed_pool: Optional[int] = None
     compute_centroids: bool = True
-    gather_events: bool = True
+    gather_events: bool = False  # also materialise the event-major packed token copy (csb_embed_scatter_ordered makes it unnecessary)
     # independent kernels of one stream run on a side CUDA stream (parallel branches of the captured graphs): the Exp(1) /
     # pool draws next to the Gram kernel, the representative selection next to centroid_gather, the relevance test next to
     # the pixel-difference kernel.  Measured at config 2: one stream alone 0.609 -> 0.593 ms, but 6 streams in flight
@@ -96,7 +96,8 @@ class StreamCompressor:
         self.n_minor = torch.zeros(1, dtype=torch.int64, device=dev)
         self.mask = torch.empty(T * P, dtype=torch.uint8, device=dev)
         self.out = torch.empty(T * P, D, dtype=torch.bfloat16, device=dev)
-        self.compact_ws = torch.empty(ops.compact_workspace_bytes(T * P, n_ids), dtype=torch.uint8, device=dev)
+        self.compact_ws = ops.compact_stream_workspace(T * P, n_ids, dev)  # zero-filled: carries the scan kernel's barrier epoch
+        self._sel, self._cmp = {}, {}  # output buffers of the selection / compaction launches, allocated on first use
         # the raw pixel-difference mask is independent of the clustering: phase1 may launch it on a side stream so that
         # this HBM-bound kernel overlaps the latency-bound k-means solver
         self.side = torch.cuda.Stream(device=dev)
@@ -106,9 +107,10 @@ class StreamCompressor:
         self._ev_join = torch.cuda.Event()
         self._diff_pending = False
         self.order = self.ev_off = self.dist = self.reps = self.rep_counts = self.rep_flags = None
-        self.cos = self.low = self.minor_list = None
+        self.cos = self.low = self.minor_list = self.events_repr = None
         self.kept_index = self.n_kept = None
-        self.out_ids = self.out_attention = self.n_ids_out = None
+        self.out_ids = self.out_attention = self.n_ids_out = self.n_image_ids = None
+        self._G_used = None
 
     # ------------------------------------------------------------------------------------------
     def _branch(self):
@@ -192,48 +194,53 @@ class StreamCompressor:
             ops.pixel_diff(pixel_values, T, self.P, self.W, threshold=self.cfg.pixel_threshold, out=self.mask, stream=self.side)
             self._ev_diff.record(self.side)
             self._diff_pending = True
-        assign = self.km.assignments
         self.order, self.ev_off = self.km.event_order, self.km.event_offsets
-
-        def representatives():
-            if T <= 256 * k:  # one fused launch (a warp per event, quadratic in the event size)
-                self.dist, self.reps, self.rep_counts, self.rep_flags = ops.representatives_gram(
-                    G, self.ev_off, self.order, k, self.cfg.n_representatives)
-            else:
-                self.dist = ops.dist_to_assigned_gram(G, assign, self.ev_off, self.order, k)
-                self.reps, self.rep_counts, self.rep_flags = ops.select_representatives(self.dist, assign, k,
-                                                                                      self.cfg.n_representatives)
-
-        gather = self.centroids is not None or self.packed is not None
-        if par and gather:  # the selection reads G and the CSR, the gather reads X: independent
-            with self._branch():
-                representatives()
-        # one pass over X: fp32 centroids + the event-major packed token copy (the solver already emitted the order)
-        if gather:
+        # one pass over X: the fp32 centroids the reference returns (kmeans_with_time.py:134); the chronological per-event
+        # token gather (cogreasoner_chat.py:291-296) is NOT materialised: csb_embed_scatter_ordered reads the feature rows
+        # through `event_order` when the summary prompts are embedded (cfg.gather_events=True restores the packed copy)
+        if self.centroids is not None or self.packed is not None:
             ops.centroid_gather(x2, self.km.member_offsets, self.km.members, self.km.event_offsets, k, self.centroids, self.packed)
-        if par and gather:
-            self._join()
-        else:
-            representatives()
 
     # ------------------------------------------------------------------------------------------
+    def _select(self, events_repr, question, hidden, cu_seqlens):
+        """cogreasoner_chat.py:284 + :317-318 + :325-333: representatives, relevance flags, minor frames."""
+        T, k = self.T, self.k
+        G = self._G_used
+        q = question.view(-1)
+        if T <= 256 * k:  # one fused launch (a warp per event for the representatives, quadratic in the event size)
+            b = ops.relevance_select(q, events_repr, G, self.ev_off, self.order, self.km.assignments, self._ticket, k=k,
+                                     n_rep=self.cfg.n_representatives, threshold=self.cfg.relevance_threshold, hidden=hidden,
+                                     cu_seqlens=cu_seqlens, bufs=self._sel)
+            self.dist, self.reps, self.rep_counts, self.rep_flags = b["dist"], b["reps"], b["rep_counts"], b["rep_flags"]
+            self.cos, self.low, self.minor_flags, self.minor_list, self.n_minor = b["cos"], b["low"], b["minor_flags"], b["minor_list"], b["n_minor"]
+            if events_repr is None:
+                self.events_repr = b["events"]
+            return
+        if events_repr is None:
+            events_repr = ops.seq_mean_pool(hidden, cu_seqlens)
+            self.events_repr = events_repr
+        assign = self.km.assignments
+        self.dist = ops.dist_to_assigned_gram(G, assign, self.ev_off, self.order, k)
+        self.reps, self.rep_counts, self.rep_flags = ops.select_representatives(self.dist, assign, k, self.cfg.n_representatives)
+        self.cos, self.low, self.minor_flags, self.minor_list, self.n_minor = ops.relevance_minor(
+            q, events_repr, assign, self.rep_flags, self._ticket, self.cfg.relevance_threshold)
+
     def phase2(self, features: torch.Tensor, events_repr: Optional[torch.Tensor], question: Optional[torch.Tensor],
-               pixel_values: torch.Tensor, input_ids: torch.Tensor, attention_mask: Optional[torch.Tensor] = None) -> None:
-        """events_repr [k, Dl], question [1, Dl] (frozen-LLM outputs); pixel_values [T*P*m*m, C]; ids [n_ids]."""
+               pixel_values: torch.Tensor, input_ids: torch.Tensor, attention_mask: Optional[torch.Tensor] = None, *,
+               hidden: Optional[torch.Tensor] = None, cu_seqlens: Optional[torch.Tensor] = None) -> None:
+        """events_repr [k, Dl], question [1, Dl] (frozen-LLM outputs); pixel_values [T*P*m*m, C]; ids [n_ids].
+        Instead of ``events_repr`` the packed last hidden states of the k summary forwards can be given (``hidden``
+        [sum(len), Dl] + ``cu_seqlens`` [k+1] int32): their mean pool (:317-318) is then fused into the selection launch."""
         T, P = self.T, self.P
-        minor_flags = None
         par = self.cfg.parallel_branches and self.gate and not self._diff_pending
         if par:  # the raw pixel-difference mask does not depend on the relevance test: a parallel branch
             with self._branch():
                 ops.pixel_diff(pixel_values, T, P, self.W, threshold=self.cfg.pixel_threshold, out=self.mask)
         if self.gate:
-            self.cos, self.low, self.minor_flags, self.minor_list, self.n_minor = ops.relevance_minor(
-                question.view(-1), events_repr, self.km.assignments, self.rep_flags, self._ticket, self.cfg.relevance_threshold)
-            minor_flags = self.minor_flags
+            self._select(events_repr, question, hidden, cu_seqlens)
         else:
             self.minor_flags.zero_()
             self.n_minor.zero_()
-            minor_flags = self.minor_flags
         if par:
             self._join()
         elif self._diff_pending:
@@ -241,11 +248,13 @@ class StreamCompressor:
             self._diff_pending = False
         else:
             ops.pixel_diff(pixel_values, T, P, self.W, threshold=self.cfg.pixel_threshold, out=self.mask)
-        ops.mask_finalize(self.mask, T, P, min_tokens=self.cfg.min_tokens, minor_flags=minor_flags)
-        _, self.kept_index, self.n_kept = ops.compact_tokens(features, T, P, self.mask, minor_flags, out=self.out,
-                                                             workspace=self.compact_ws)
-        self.out_ids, self.out_attention, _, _, self.n_ids_out = ops.filter_ids(input_ids, self.image_token_index, self.mask,
-                                                                                attention_mask)
+        # per-frame mask rules + scan + compaction (minor frames emitted as their pooled token) + id filter
+        b = ops.compact_stream(features, T, P, self.mask, self.minor_flags, min_tokens=self.cfg.min_tokens, input_ids=input_ids,
+                               image_token_index=self.image_token_index, attention_mask=attention_mask, out=self.out,
+                               workspace=self.compact_ws, bufs=self._cmp)
+        self.kept_index, self.n_kept = b["kept_index"], b["n_kept"]
+        self.out_ids, self.out_attention = b["out_ids"], b.get("out_attention")
+        self.n_ids_out, self.n_image_ids = b["n_out"][0:1], b["n_out"][1:2]
 
     # ------------------------------------------------------------------------------------------
     def capture(self, features, timestamps, events_repr, question, pixel_values, input_ids, attention_mask=None):
@@ -292,6 +301,9 @@ class StreamCompressor:
         """Host view of the outputs (synchronises)."""
         nk = int(self.n_kept.item())
         no = int(self.n_ids_out.item())
+        n_img = int(self.n_image_ids.item())
+        if n_img != self.T * self.P:  # the reference's `text_masks[image_selected] = compression_mask` raises here (:463)
+            raise RuntimeError(f"shape mismatch: {n_img} <image> ids for a compression mask of {self.T * self.P} tokens")
         res = dict(n_kept=nk, mask=self.mask.view(torch.bool), features=self.out[:nk], kept_index=self.kept_index[:nk],
                    input_ids=self.out_ids[:no],
                    attention_mask=None if self.out_attention is None else self.out_attention[:no])

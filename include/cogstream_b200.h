@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define CSB_ABI_VERSION 1
+#define CSB_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define CSB_API __attribute__((visibility("default")))
@@ -240,12 +240,90 @@ CSB_API int csb_compact_tokens(const void* x_bf16, int64_t T, int64_t P, int64_t
 /* cogreasoner_chat.py:459-474: keep every text id and the <image> ids whose mask bit is set (the j-th image
  * id pairs with mask[j]); optional attention_mask / labels / position_ids (int64) are filtered alike and
  * position_ids are rebuilt as 0..len-1 per sequence (a sequence starts where the filtered id is 0).
- *   n_out device int64.  Any optional in/out pair may be NULL. */
+ *   n_out device int64[2]: {ids kept, <image> ids seen}.  The caller compares n_out[1] with n_mask: the reference's
+ *   `text_masks[image_selected] = compression_mask` (:463) raises when they differ, this entry point does not (image ids past
+ *   n_mask are dropped).  Any optional in/out pair may be NULL. */
 CSB_API int csb_filter_ids(const int64_t* input_ids, int64_t n_ids, int64_t image_token_index, const uint8_t* mask,
                    int64_t n_mask, const int64_t* attention_mask, const int64_t* labels,
                    const int64_t* position_ids, int64_t* out_ids, int64_t* out_attention_mask,
                    int64_t* out_labels, int64_t* out_position_ids, int64_t* n_out, void* workspace,
                    size_t workspace_bytes, csb_stream_t stream);
+
+/* The phase-2 tail as ONE entry point (cogreasoner_chat.py:413-422, :444-446, :458-474): per-frame mask rules (csb_mask_finalize),
+ * token scan + compaction with the pooled token of the minor frames (csb_compact_tokens) and the id filter (csb_filter_ids without
+ * position ids).  Two launches: one cooperative kernel whose token chunks are whole frames (so the per-frame rules are CTA-local)
+ * and whose barrier word is carried from launch to launch (no memset), then the pooling + row-gather kernel.  Shapes the fused
+ * kernel cannot take (P > 1024, more chunks than co-resident CTAs) run the three separate entry points -- same results.
+ *   mask        [T*P] uint8, in: the raw csb_pixel_diff mask (or a final mask with finalize = 0), out: the final mask
+ *   minor_flags [T] uint8 or NULL; pool_minor != 0 emits token 0 of a flagged frame as the frame's pooled mean
+ *   input_ids   [n_ids] int64 or NULL (then no id filtering); n_out int64[2] = {ids kept, <image> ids seen}
+ *   workspace   csb_compact_stream_workspace_bytes(T*P, n_ids) bytes, ZERO-FILLED ONCE by the caller before its first use and
+ *               private to one CUDA stream at a time (it holds the carried barrier state). */
+typedef struct csb_compact_args {
+  const void* x_bf16;      /* [T*P, D] */
+  int64_t T, P, D;
+  uint8_t* mask;
+  const uint8_t* minor_flags;
+  int64_t min_tokens;
+  int32_t finalize;
+  int32_t pool_minor;
+  const int64_t* input_ids;
+  int64_t n_ids;
+  int64_t image_token_index;
+  const int64_t* attention_mask;
+  const int64_t* labels;
+  void* out_bf16;          /* [T*P, D], first n_kept rows valid */
+  int32_t* kept_index;     /* [T*P] */
+  int64_t* n_kept;         /* device int64 */
+  int64_t* out_ids;
+  int64_t* out_attention_mask;
+  int64_t* out_labels;
+  int64_t* n_out;          /* device int64[2] */
+  void* workspace;
+  size_t workspace_bytes;
+} csb_compact_args;
+CSB_API size_t csb_compact_stream_workspace_bytes(int64_t n_tokens, int64_t n_ids);
+CSB_API int csb_compact_stream(const csb_compact_args* args /* host */, csb_stream_t stream);
+
+/* The selection step of phase 2 as ONE launch (cogreasoner_chat.py:284 select_additional_frames, :317-318 event mean pool,
+ * :325-333 cosine / threshold / minor list): k CTAs score the events against the question, ceil(k/8) CTAs pick the
+ * representatives from the Gram matrix (csb_representatives_gram), the last CTA to finish builds the minor-frame list.
+ * Event embeddings come either ready (`events` [k,Dl]) or as the packed last hidden states of the k summary forwards
+ * (`hidden` [cu_seqlens[k], Dl] + cu_seqlens): then a split partial-sum pass runs first and every cosine CTA finishes the mean
+ * of its own event in shared memory (the bits of csb_seq_mean_pool; the pooled rows are also stored to events_out if given).
+ * Meant for events of up to a few hundred frames (T <= 256 k), like csb_representatives_gram. */
+typedef struct csb_relevance_args {
+  const void* question;        /* [Dl] */
+  const void* events;          /* [k, Dl] or NULL */
+  const void* hidden;          /* [cu_seqlens[k], Dl] or NULL */
+  const int32_t* cu_seqlens;   /* [k + 1] with hidden */
+  int64_t k, Dl;
+  int32_t dtype;               /* CSB_BF16 / CSB_F32 */
+  int32_t reserved;
+  double threshold;
+  const double* gram;          /* [T, T], leading dimension ldg */
+  int64_t ldg;
+  const int32_t* event_offsets;
+  const int32_t* event_order;
+  int64_t n_rep;
+  const int64_t* assignments;  /* [T] */
+  int64_t T;
+  void* events_out;            /* [k, Dl] or NULL (with hidden) */
+  void* cos_out;               /* [k] dtype */
+  uint8_t* low_flags;          /* [k] */
+  float* dist;                 /* [T] */
+  int64_t* reps;               /* [k, n_rep] */
+  int32_t* rep_counts;         /* [k] */
+  uint8_t* rep_flags;          /* [T] */
+  uint8_t* minor_flags;        /* [T] */
+  int32_t* minor_list;         /* [T] */
+  int64_t* n_minor;            /* device int64 */
+  uint32_t* ticket;            /* zero-initialised, reset by the library (one per concurrently running stream) */
+  void* workspace;             /* csb_relevance_select_workspace_bytes(k, Dl) with hidden, else may be NULL */
+  size_t workspace_bytes;
+} csb_relevance_args;
+CSB_API size_t csb_relevance_select_workspace_bytes(int64_t k, int64_t Dl);
+CSB_API int csb_relevance_select(const csb_relevance_args* args /* host */, csb_stream_t stream);
 
 /* ---- between the two phases, and the last step of the call site ------------- */
 
@@ -263,6 +341,14 @@ CSB_API size_t csb_embed_scatter_workspace_bytes(int64_t n_ids);
 CSB_API int csb_embed_scatter(const int64_t* input_ids, int64_t n_ids, int64_t image_token_index, const void* embed_table,
                       int64_t vocab, const void* features, int64_t n_features, int64_t D, int dtype, void* out,
                       int32_t* status, void* workspace, size_t workspace_bytes, csb_stream_t stream);
+/* Same, reading the feature rows THROUGH the chronological per-event frame order (cogreasoner_chat.py:286-305 in one pass, with
+ * no event-major copy of the features in between): the j-th <image> id takes feature row
+ *     frame_order[j / tokens_per_frame] * tokens_per_frame + j % tokens_per_frame,
+ * frame_order [n_frames] int32 being csb_kmeans_solve's event_order.  features [n_frames * tokens_per_frame, D]. */
+CSB_API int csb_embed_scatter_ordered(const int64_t* input_ids, int64_t n_ids, int64_t image_token_index, const void* embed_table,
+                              int64_t vocab, const void* features, const int32_t* frame_order, int64_t n_frames,
+                              int64_t tokens_per_frame, int64_t D, int dtype, void* out, int32_t* status, void* workspace,
+                              size_t workspace_bytes, csb_stream_t stream);
 
 CSB_API size_t csb_seq_mean_pool_workspace_bytes(int64_t n_seq, int64_t Dl);
 /* cogreasoner_chat.py:317-318 and :322: torch.mean(last_hidden_state, dim=1) of every sequence of a packed

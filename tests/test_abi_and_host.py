@@ -29,7 +29,7 @@ def test_header_symbols_exported(built_lib):
 
 
 def test_abi_version_and_sizes(built_lib):
-    assert built_lib.csb_abi_version() == 1
+    assert built_lib.csb_abi_version() == 2
     # pure host arithmetic (no GPU): workspace sizes are positive and monotone
     a = built_lib.csb_gram_workspace_bytes(600, 207360)
     b = built_lib.csb_gram_workspace_bytes(64, 4608)

@@ -315,11 +315,12 @@ def test_pipeline_vs_oracle(dev, T, P, D, k, seed, iid):
     assert torch.equal(r["mask"].cpu(), p2.mask)
     assert torch.equal(r["input_ids"].cpu(), p2.input_ids) and torch.equal(r["attention_mask"].cpu(), p2.attention_mask)
     assert_bf16_close(r["features"], p2.features)
-    # chronological per-event gather (cogreasoner_chat.py:291-296)
+    # chronological per-event gather (cogreasoner_chat.py:291-296): the event order the summary prompts are embedded through
     off = r["event_offsets"].tolist()
-    packed = r["packed_events"].view(T, P, D).cpu()
+    order = r["event_order"].cpu().long()
+    f3 = st.features.view(T, P, D)
     for i in (0, kk // 2, kk - 1):
-        assert torch.equal(packed[off[i]: off[i + 1]].reshape(-1, D), p1.events[i])
+        assert torch.equal(f3[order[off[i]: off[i + 1]]].reshape(-1, D), p1.events[i])
 
 
 def test_pipeline_gate_closed(dev):
@@ -565,10 +566,31 @@ def test_full_size_config4_kmeans_parity(dev):
     assert torch.equal(ag.cpu(), a)
     assert torch.equal(ctg.cpu(), ct)
     assert rel_err(cg, c) < 1e-6
-    # representatives on the long-stream path (dist from the Gram matrix, cogreasoner_chat.py:50-64)
+    # representatives (cogreasoner_chat.py:50-64).  At K = 18,432 the members of an event are nearly equidistant from its centroid
+    # (relative spread ~1/sqrt(K)); the reference's own fp32 cdist noise (~3e-6 relative) decides a few of the 960 top-2 picks, so
+    # the check is against the exact (fp64) order, excusing pairs closer than 1e-5 relative.
     reps_ref = orc.select_additional_frames(feats.view(T, P, D), c, a, 2)
     reps = select_additional_frames(feats.view(T, P, D).to(dev), cg, ag, 2)
-    assert all(torch.equal(x.cpu(), y) for x, y in zip(reps, reps_ref))
+    X = feats.view(T, -1).double()
+    C = c.view(k, -1).double()
+    n_ref_diff = 0
+    for j in range(k):
+        idx = torch.nonzero(a == j)[:, 0]
+        got = reps[j].cpu()
+        n_ref_diff += int(not torch.equal(got, reps_ref[j]))
+        if idx.numel() <= 2:
+            assert torch.equal(got, idx)
+            continue
+        d = (X[idx] - C[j]).norm(dim=1)
+        ordr = torch.argsort(d, stable=True)
+        want = idx[ordr[:2]]
+        if torch.equal(got, want):
+            continue
+        dg = (X[got] - C[j]).norm(dim=1)
+        assert got.numel() == 2 and bool(torch.isin(got, idx).all())
+        assert float((dg - d[ordr[:2]]).abs().max() / d[ordr[0]]) < 1e-5, f"event {j}: {got.tolist()} vs exact {want.tolist()}"
+    print(f"config 4 representatives: {n_ref_diff} of {k} events differ from the fp32 reference order (near ties)")
+    assert n_ref_diff <= 8
 
 
 def test_stream_pool_batch_matches_single_streams(dev):
@@ -920,7 +942,7 @@ def test_drop_in_call_site_matches_reference(dev, fused_embed):
         def __init__(self):
             super().__init__()
             self.embed_tokens = torch.nn.Embedding(s["vocab"], s["D"], _weight=g["embed_weight"].clone())
-            if not fused_embed:  # a wrapped embedding without a plain .weight: the method falls back to the module call
+            if not fused_embed:  # a wrapped embedding without a plain .weight
                 inner = self.embed_tokens
                 self.embed_tokens = torch.nn.Sequential(inner)
 
@@ -954,10 +976,14 @@ def test_drop_in_call_site_matches_reference(dev, fused_embed):
             return mm_features
 
     m = Model()
-    r = m.prepare_inputs_labels_for_multimodal(
-        input_ids=g["final_ids"].to(dev), attention_mask=g["final_attention_mask"].to(dev), position_ids=None,
-        past_key_values=None, labels=g["final_labels"].to(dev), pixel_values=g["pixel_values"].to(dev),
-        grid_sizes=g["grid_sizes"].to(dev), merge_sizes=g["merge_sizes"].to(dev), modals=g["modals"], total_image_num=s["T"])
+    kw = dict(input_ids=g["final_ids"].to(dev), attention_mask=g["final_attention_mask"].to(dev), position_ids=None,
+              past_key_values=None, labels=g["final_labels"].to(dev), pixel_values=g["pixel_values"].to(dev),
+              grid_sizes=g["grid_sizes"].to(dev), merge_sizes=g["merge_sizes"].to(dev), modals=g["modals"], total_image_num=s["T"])
+    if not fused_embed:  # no eager-torch fallback: an embedding module without a plain weight is refused
+        with pytest.raises(TypeError, match="embed_tokens"):
+            m.prepare_inputs_labels_for_multimodal(**kw)
+        return
+    r = m.prepare_inputs_labels_for_multimodal(**kw)
     assert r[0] is None and r[2] is None and r[3] is None
     assert len(calls) == s["k"]
     assert r[4].shape == g["callsite_inputs_embeds"].shape
@@ -1022,10 +1048,131 @@ def test_scan_fallback_paths_agree(dev, monkeypatch):
             monkeypatch.setenv("CSB_NO_COOP_SCAN", "1")
         o, kept, nk = ops.compact_tokens(d.features, T, P, mask, flags)
         ids, am, _, _, no = ops.filter_ids(d.input_ids, synthetic.IMAGE_TOKEN_INDEX, mask, d.attention_mask)
-        n1, n2 = int(nk.item()), int(no.item())
+        n1, n2 = int(nk.item()), int(no[0].item())
+        assert int(no[1].item()) == T * P  # <image> ids seen
         outs.append((n1, n2, o[:n1].clone(), kept[:n1].clone(), ids[:n2].clone(), am[:n2].clone()))
     monkeypatch.delenv("CSB_NO_COOP_SCAN")
     a, b = outs
     assert a[0] == b[0] and a[1] == b[1] and a[0] == int(mask.sum())
     for x, y in zip(a[2:], b[2:]):
         assert torch.equal(x, y)
+
+
+# ---- round 2: fused phase-2 launches -----------------------------------------------------------------------------------------
+@pytest.mark.parametrize("T,P,D,n_head", [(333, 7, 64, 14), (600, 180, 64, 14), (50, 1, 8, 0), (97, 300, 8, 3), (40, 1500, 8, 5)])
+def test_compact_stream_matches_separate_launches(dev, monkeypatch, T, P, D, n_head):
+    """csb_compact_stream (finalize + scan + id filter in one cooperative launch, then pooling + gather) == csb_mask_finalize +
+    csb_compact_tokens + csb_filter_ids, bit for bit; P > 1024 and CSB_NO_COOP_SCAN take the separate launches internally.
+    The workspace carries the barrier epoch: the second and third call reuse it."""
+    st = synthetic.make_stream(T, P, D, 5, C=4, n_text_head=n_head)
+    d = st.to(dev)
+    g = torch.Generator().manual_seed(T + P)
+    raw = (torch.rand(T * P, generator=g) < 0.3).to(torch.uint8)
+    raw.view(T, P)[torch.rand(T, generator=g) < 0.2] = 0  # static frames: the min_tokens rule fires
+    minor = (torch.rand(T, generator=g) < 0.25).to(torch.uint8).to(dev)
+    labels = torch.arange(st.input_ids.numel(), dtype=torch.int64).to(dev)
+    want_mask = raw.clone().to(dev)
+    ops.mask_finalize(want_mask, T, P, min_tokens=2, minor_flags=minor)
+    o, kept, nk = ops.compact_tokens(d.features, T, P, want_mask, minor)
+    ids, am, lb, _, no = ops.filter_ids(d.input_ids, synthetic.IMAGE_TOKEN_INDEX, want_mask, d.attention_mask, labels)
+    n1, n2 = int(nk.item()), int(no[0].item())
+    ws = ops.compact_stream_workspace(T * P, st.input_ids.numel(), dev)
+    for rep in range(3):
+        if rep == 2:
+            monkeypatch.setenv("CSB_NO_COOP_SCAN", "1")
+        mask = raw.clone().to(dev)
+        b = ops.compact_stream(d.features, T, P, mask, minor, min_tokens=2, input_ids=d.input_ids,
+                               image_token_index=synthetic.IMAGE_TOKEN_INDEX, attention_mask=d.attention_mask, labels=labels, workspace=ws)
+        assert torch.equal(mask, want_mask)
+        assert int(b["n_kept"].item()) == n1 and b["n_out"].tolist() == [n2, T * P]
+        assert torch.equal(b["kept_index"][:n1], kept[:n1]) and torch.equal(b["out"][:n1], o[:n1])
+        assert torch.equal(b["out_ids"][:n2], ids[:n2]) and torch.equal(b["out_attention"][:n2], am[:n2])
+        assert torch.equal(b["out_labels"][:n2], lb[:n2])
+    monkeypatch.delenv("CSB_NO_COOP_SCAN")
+    # finalize=False leaves a ready mask alone; no ids -> no id outputs
+    mask = want_mask.clone()
+    b = ops.compact_stream(d.features, T, P, mask, minor, finalize=False, workspace=ws)
+    assert torch.equal(mask, want_mask) and int(b["n_kept"].item()) == n1 and torch.equal(b["out"][:n1], o[:n1])
+
+
+@pytest.mark.parametrize("name", golden_names())
+@pytest.mark.parametrize("from_hidden", [False, True])
+def test_relevance_select_matches_unfused(dev, name, from_hidden):
+    """csb_relevance_select (cosine + representatives + minor list [+ the event mean pool] in one launch) == the separate entry
+    points, bit for bit."""
+    g = load_golden(name)
+    T, P, D, k = g["spec"]["T"], g["spec"]["P"], g["spec"]["D"], g["spec"]["k"]
+    x = g["features"].view(T, P * D).to(dev)
+    assign = g["assignments"].to(dev)
+    G = ops.gram(x)
+    order, off = ops.event_order(assign, k)
+    Dl = 136
+    gen = torch.Generator().manual_seed(k)
+    q = torch.randn(Dl, generator=gen).to(torch.bfloat16).to(dev)
+    ticket = torch.zeros(1, dtype=torch.int32, device=dev)
+    if from_hidden:
+        lens = [int(v) for v in torch.randint(1, 40, (k,), generator=gen)]
+        cu = torch.tensor([0] + list(torch.tensor(lens).cumsum(0)), dtype=torch.int32).to(dev)
+        hidden = (torch.randn(sum(lens), Dl, generator=gen) + 0.5 * q.float().cpu()).to(torch.bfloat16).to(dev)
+        ev = ops.seq_mean_pool(hidden, cu)
+        b = ops.relevance_select(q, None, G, off, order, assign, ticket, k=k, hidden=hidden, cu_seqlens=cu)
+        assert torch.equal(b["events"], ev)
+    else:
+        ev = (torch.randn(k, Dl, generator=gen) + 0.5 * q.float().cpu()).to(torch.bfloat16).to(dev)
+        b = ops.relevance_select(q, ev, G, off, order, assign, ticket, k=k)
+    dist, reps, counts, rflags = ops.representatives_gram(G, off, order, k, 2)
+    cos, low, mflags, mlist, nm = ops.relevance_minor(q, ev, assign, rflags, ticket, 0.45)
+    n = int(nm.item())
+    assert 0 < int(low.sum()) < k, "the case should have both relevant and irrelevant events"
+    assert torch.equal(b["dist"], dist) and torch.equal(b["reps"], reps) and torch.equal(b["rep_counts"], counts)
+    assert torch.equal(b["rep_flags"], rflags) and torch.equal(b["cos"], cos) and torch.equal(b["low"], low)
+    assert torch.equal(b["minor_flags"], mflags) and int(b["n_minor"].item()) == n and torch.equal(b["minor_list"][:n], mlist[:n])
+    assert int(ticket.item()) == 0
+
+
+def test_embed_scatter_ordered_matches_packed_gather(dev):
+    """csb_embed_scatter_ordered (feature rows read through the event order) == csb_embed_scatter on the packed event-major copy
+    == the reference's per-event embed / mask / mul / add / index_put (golden), bit for bit."""
+    g, s, packed = _summary_inputs(dev)
+    T, P, D, k = s["T"], s["P"], s["D"], s["k"]
+    order, off = ops.event_order(g["assignments"].to(dev), k)
+    out, status = ops.embed_scatter(g["event_ids"].to(dev), s["image_id"], g["embed_weight"].to(dev), g["features"].to(dev),
+                                    frame_order=order, tokens_per_frame=P)
+    assert status.tolist() == [T * P, 0]
+    assert torch.equal(out.cpu().view(torch.int16), g["inputs_embeds"].view(torch.int16))
+
+
+def test_filter_ids_reports_image_id_count(dev):
+    """The reference raises when the number of <image> ids differs from the mask length (cogreasoner_chat.py:463); the drop-in
+    method does too (the C entry point reports the count)."""
+    T, P, D = 20, 3, 16
+    st = synthetic.make_stream(T, P, D, 1, C=4)
+    d = st.to(dev)
+    mask = torch.ones(T * P - 5, dtype=torch.bool, device=dev)
+    with pytest.raises(RuntimeError, match="shape mismatch"):
+        _Stub()._compress_visual_tokens(mask, d.features[: T * P - 5], d.input_ids, d.attention_mask)
+    *_, n_out = ops.filter_ids(d.input_ids, synthetic.IMAGE_TOKEN_INDEX, torch.ones(T * P, dtype=torch.uint8, device=dev))
+    assert n_out.tolist() == [st.input_ids.numel(), T * P]
+
+
+def test_reseed_pool_overflow_is_reported(dev):
+    """A caller-supplied re-seed pool that runs out is flagged in the stats row and makes results() raise (the default pool is
+    sized to the upper bound and cannot run out)."""
+    from cogstream_b200 import STATS_FIELDS
+    T, P, D, k = 120, 2, 32, 10
+    st = synthetic.make_stream(T, P, D, 3, C=4)
+    ev, q = synthetic.make_embeddings(k, 64, 3)
+    d = st.to(dev)
+    W = st.pixel_values.numel() // (T * P)
+    sc = StreamCompressor(T, P, D, W, st.input_ids.numel(), device=dev, cfg=StreamConfig(cluster_num=k))
+    assert sc.pool.numel() == k * 31
+    init = torch.zeros(k, dtype=torch.int64, device=dev)  # k identical centres: ties go to cluster 0, the other k - 1 are empty (:117)
+    sc.phase1(d.features, d.timestamps, init_indices=init, reseed_pool=torch.zeros(2, dtype=torch.int64, device=dev))
+    sc.phase2(d.features, ev.to(dev), q.to(dev), d.pixel_values, d.input_ids, d.attention_mask)
+    row = dict(zip(STATS_FIELDS, sc.stats_row().tolist()))
+    assert row["reseed_overflow"] == 1
+    with pytest.raises(RuntimeError, match="re-seed pool"):
+        sc.results()
+    sc.phase1(d.features, d.timestamps, init_indices=init)  # default pool: fine
+    sc.phase2(d.features, ev.to(dev), q.to(dev), d.pixel_values, d.input_ids, d.attention_mask)
+    assert sc.results()["status"]["reseed_overflow"] is False
