@@ -372,7 +372,8 @@ class Lane:
     def capture(self):
         with torch.cuda.stream(self.stream):
             d = self.d
-            self.sc.capture(d.features, d.timestamps, self.ev_d, self.q_d, d.pixel_values, d.input_ids, d.attention_mask)
+            self.sc.capture(d.features, d.timestamps, self.ev_d, self.q_d, d.pixel_values, d.input_ids, d.attention_mask,
+                            early_pixel=bool(self.ctx.args.early_pixel))
         self.graphs = True
 
     def run_resident(self):
@@ -381,7 +382,7 @@ class Lane:
             self.sc.replay2()
             return self.sc._stats_static
         d = self.d
-        self.sc.phase1(d.features, d.timestamps)
+        self.sc.phase1(d.features, d.timestamps, pixel_values=d.pixel_values if self.ctx.args.early_pixel else None)
         self.sc.phase2(d.features, self.ev_d, self.q_d, d.pixel_values, d.input_ids, d.attention_mask)
         return self.sc.stats_row()
 
@@ -413,8 +414,8 @@ class Lane:
         h = self.host
         self.e_feat.copy_(h.features, non_blocking=True)
         self.e_ts.copy_(h.timestamps, non_blocking=True)
-        self.sc.phase1(self.e_feat, self.e_ts)
         self.e_pix.copy_(h.pixel_values, non_blocking=True)
+        self.sc.phase1(self.e_feat, self.e_ts, pixel_values=self.e_pix if self.ctx.args.early_pixel else None)
         self.e_ids.copy_(h.input_ids, non_blocking=True)
         self.e_am.copy_(h.attention_mask, non_blocking=True)
         self.e_ev.copy_(self.ev_h, non_blocking=True)
@@ -588,7 +589,7 @@ def run_streams_workload(ctx: Ctx, args):
                 single_stream=dict(ms=ms_single, value=T / (ms_single * 1e-3), unit=UNIT,
                                    hbm_frac=roofline["whole_path"]["single_stream"]["frac"] if roofline else None,
                                    note="one stream at a time on one CUDA stream (BASELINE config 2 read literally): latency of the path"),
-                pipeline=dict(depth=len(lanes), cuda_graphs=use_graphs, streams_per_step=S, ms_per_stream=ms_step / S,
+                pipeline=dict(depth=len(lanes), cuda_graphs=use_graphs, early_pixel_diff=bool(args.early_pixel), streams_per_step=S, ms_per_stream=ms_step / S,
                               timed_region_ms=ms_total, launches_per_stream=launches_per_stream,
                               note="successive streams are independent; `depth` of them are in flight on separate CUDA streams with their own "
                                    "inputs and workspaces; no synchronisation between steps other than the stats all-gather"),
@@ -777,7 +778,8 @@ def run_config5(ctx: Ctx, args):
             c0 = ctx.lib.csb_kernel_launches()
             for L in lanes:
                 d = L.d
-                L.sc.capture(d.features, d.timestamps, L.ev_d, L.q_d, d.pixel_values, d.input_ids, d.attention_mask)
+                L.sc.capture(d.features, d.timestamps, L.ev_d, L.q_d, d.pixel_values, d.input_ids, d.attention_mask,
+                             early_pixel=bool(args.early_pixel))
                 L.graphs = True
             launches_per_step = (ctx.lib.csb_kernel_launches() - c0) // 2  # one eager + one captured pass per point
             use_graphs = True
@@ -1028,6 +1030,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--graphs", type=int, default=1, help="replay each phase as a CUDA graph (device-resident run)")
     ap.add_argument("--depth", type=int, default=6, help="independent streams kept in flight per GPU")
+    ap.add_argument("--early-pixel", type=int, default=1, help="start the pixel-difference mask in phase 1, next to the k-means solver")
     ap.add_argument("--streams-per-step", type=int, default=32, help="config2: streams per rank per step")
     ap.add_argument("--e2e-steps", type=int, default=4, help="timed e2e steps (each moves streams_per_step x 759 MB over PCIe)")
     ap.add_argument("--segment", type=int, default=120, help="config4: new frames per question (120 = 60 s at 2 fps)")

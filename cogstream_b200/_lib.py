@@ -88,6 +88,7 @@ PROTOTYPES = {
     "csb_cosine_flags": (C.c_int, [_p, _p, _i64, _i64, _i32, _dbl, _p, _p, _p]),
     "csb_minor_frames": (C.c_int, [_p, _p, _p, _i64, _p, _p, _p, _p]),
     "csb_pixel_diff": (C.c_int, [_p, _i64, _i64, _i64, _i32, _dbl, _p, _p]),
+    "csb_pixel_diff_ex": (C.c_int, [_p, _i64, _i64, _i64, _i32, _dbl, _p, _i64, _i32, _p]),
     "csb_mask_finalize": (C.c_int, [_p, _i64, _i64, _i64, _p, _i64, _p]),
     "csb_pixel_mask": (C.c_int, [_p, _i64, _i64, _i64, _i32, _dbl, _i64, _p, _i64, _p, _p]),
     "csb_pool_frames_inplace": (C.c_int, [_p, _i64, _i64, _i64, _p, _i64, _p, _p]),

@@ -1421,6 +1421,11 @@ int csb_minor_frames(const int64_t* assignments, const uint8_t* low_flags, const
 
 int csb_pixel_diff(const void* pixels, int64_t t, int64_t P, int64_t W, int32_t dtype, double threshold, uint8_t* mask,
                    csb_stream_t stream) {
+  return csb_pixel_diff_ex(pixels, t, P, W, dtype, threshold, mask, 0, CSB_PIXEL_EVICT_FIRST, stream);
+}
+
+int csb_pixel_diff_ex(const void* pixels, int64_t t, int64_t P, int64_t W, int32_t dtype, double threshold, uint8_t* mask,
+                      int64_t max_ctas, int32_t flags, csb_stream_t stream) {
   CSB_DEVICE_OR_RETURN();
   CSB_REQUIRE(pixels && mask && t > 0 && P > 0 && W > 0, "pixel_diff: null argument or empty shape");
   CSB_REQUIRE(W < (1ll << 30) && P < (1ll << 30) && t < (1ll << 30), "pixel_diff: shape too large");
@@ -1446,8 +1451,10 @@ int csb_pixel_diff(const void* pixels, int64_t t, int64_t P, int64_t W, int32_t 
       int waves = 4;
       if (const char* o = getenv("CSB_PIX_WAVES")) waves = atoi(o) > 0 ? atoi(o) : 4;
       if (gb > (int64_t)kNumSMs * waves) gb = (int64_t)kNumSMs * waves;
-      if (const char* o = getenv("CSB_PIX_CTAS")) { if (atoi(o) > 0 && gb > atoi(o)) gb = atoi(o); }  // throttled grid (overlap experiments)
-      const int evict_first = getenv("CSB_PIX_EVICT") ? atoi(getenv("CSB_PIX_EVICT")) : 0;
+      if (max_ctas > 0 && gb > max_ctas) gb = max_ctas;  // throttled grid: the caller overlaps the kernel with a latency-bound one
+      if (const char* o = getenv("CSB_PIX_CTAS")) { if (atoi(o) > 0 && gb > atoi(o)) gb = atoi(o); }  // (tuning runs)
+      int evict_first = (flags & CSB_PIXEL_EVICT_FIRST) ? 1 : 0;
+      if (const char* o = getenv("CSB_PIX_EVICT")) evict_first = atoi(o);
       auto launch = [&](auto kern) -> int {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring_bytes);
         if (e != cudaSuccess) { set_error("pixel_diff: smem attr: %s", cudaGetErrorString(e)); return CSB_ERR_CUDA; }

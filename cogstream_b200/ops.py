@@ -363,8 +363,9 @@ def pixel_mask(pixels: torch.Tensor, t: int, P: int, W: int, *, threshold: float
 
 
 def pixel_diff(pixels: torch.Tensor, t: int, P: int, W: int, *, threshold: float = 0.1, out: Optional[torch.Tensor] = None,
-               stream: Optional[torch.cuda.Stream] = None) -> torch.Tensor:
-    """Raw pixel-difference mask [t*P] uint8 (no per-frame rules); ``stream`` overrides the current stream."""
+               stream: Optional[torch.cuda.Stream] = None, max_ctas: int = 0, evict_first: bool = True) -> torch.Tensor:
+    """Raw pixel-difference mask [t*P] uint8 (no per-frame rules); ``stream`` overrides the current stream.  ``max_ctas`` > 0
+    throttles the grid (for running next to the latency-bound k-means solver), ``evict_first`` = L2 evict-first pixel loads."""
     _need(pixels, "pixels")
     if pixels.dtype not in _EL_DTYPE:
         raise TypeError(f"pixel_diff: dtype must be bfloat16 or float32, got {pixels.dtype}")
@@ -373,8 +374,8 @@ def pixel_diff(pixels: torch.Tensor, t: int, P: int, W: int, *, threshold: float
     mask = out if out is not None else torch.empty(t * P, dtype=torch.uint8, device=pixels.device)
     st = stream.cuda_stream if stream is not None else _stream(pixels)
     with _on_device(pixels):
-        check(_lib.load().csb_pixel_diff(pixels.data_ptr(), t, P, W, _EL_DTYPE[pixels.dtype], float(threshold), mask.data_ptr(), st),
-              "pixel_diff")
+        check(_lib.load().csb_pixel_diff_ex(pixels.data_ptr(), t, P, W, _EL_DTYPE[pixels.dtype], float(threshold), mask.data_ptr(),
+                                            int(max_ctas), 1 if evict_first else 0, st), "pixel_diff")
     return mask
 
 

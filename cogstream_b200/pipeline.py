@@ -53,6 +53,11 @@ class StreamConfig:
     # the pixel-difference kernel.  Measured at config 2: one stream alone 0.609 -> 0.593 ms, but 6 streams in flight
     # 0.31 -> 0.34 ms per stream (twice the CUDA streams fighting for the same SMs), so it is off unless latency is the goal.
     parallel_branches: bool = False
+    # phase1(pixel_values=...) starts the raw pixel-difference mask on a side stream right after the Gram kernel, next to the
+    # k-means solver.  Measured at config 2 (scripts/overlap_probe2.py): with L2 evict-first pixel loads and the grid capped at
+    # `early_pixel_ctas` CTAs the 508 MB pass (160 us on 64 SMs) hides completely under the ~190 us latency-bound solver without
+    # slowing it (solver + pixel back to back 321 us, overlapped 207 us); an uncapped grid stretches the solver by ~15 us.
+    early_pixel_ctas: int = 64
 
     def clusters_for(self, T: int) -> int:
         if self.cluster_num is not None:
@@ -133,10 +138,9 @@ class StreamCompressor:
         """features [T*P, D] bf16, timestamps [T] on the device.  Enqueues everything; returns at once.
         ``gram`` (optional): a ready [T,T] fp64 Gram matrix of these frames (e.g. ``StreamCache.gram``, kept up to date
         incrementally); the Gram kernel is then skipped.
-        ``pixel_values`` (optional, the same tensor phase2 gets): start the raw pixel-difference mask now, on the
-        side stream, overlapped with the solver.  Measured on B200 (scripts/overlap_probe.py): the HBM-saturating
-        difference kernel stretches the latency-bound solver by about as much as it saves, so bench.py leaves it off;
-        it pays when phase 1 is followed by host work (the frozen-LLM forwards) rather than by phase 2."""
+        ``pixel_values`` (optional, the same tensor phase2 gets): start the raw pixel-difference mask now, on the side stream,
+        overlapped with the k-means solver (throttled grid + L2 evict-first loads, see ``StreamConfig.early_pixel_ctas``); the
+        mask does not depend on the clustering or the question.  phase1 joins the side stream before it returns."""
         if not self.gate:
             return
         T, k = self.T, self.k
@@ -191,7 +195,8 @@ class StreamCompressor:
             # enqueued AFTER the cooperative solver so its CTAs become resident first; the HBM-bound difference kernel then
             # fills the rest of the machine while the (latency-bound) solver iterates
             self.side.wait_event(self._ev_fork)
-            ops.pixel_diff(pixel_values, T, self.P, self.W, threshold=self.cfg.pixel_threshold, out=self.mask, stream=self.side)
+            ops.pixel_diff(pixel_values, T, self.P, self.W, threshold=self.cfg.pixel_threshold, out=self.mask, stream=self.side,
+                           max_ctas=self.cfg.early_pixel_ctas)
             self._ev_diff.record(self.side)
             self._diff_pending = True
         self.order, self.ev_off = self.km.event_order, self.km.event_offsets
@@ -200,6 +205,8 @@ class StreamCompressor:
         # through `event_order` when the summary prompts are embedded (cfg.gather_events=True restores the packed copy)
         if self.centroids is not None or self.packed is not None:
             ops.centroid_gather(x2, self.km.member_offsets, self.km.members, self.km.event_offsets, k, self.centroids, self.packed)
+        if fork:  # join: everything phase 1 started is ordered before whatever follows on this stream (and a capture can end)
+            torch.cuda.current_stream(self.device).wait_event(self._ev_diff)
 
     # ------------------------------------------------------------------------------------------
     def _select(self, events_repr, question, hidden, cu_seqlens):
@@ -243,8 +250,7 @@ class StreamCompressor:
             self.n_minor.zero_()
         if par:
             self._join()
-        elif self._diff_pending:
-            torch.cuda.current_stream(self.device).wait_event(self._ev_diff)
+        elif self._diff_pending:  # phase 1 computed (and joined) the raw mask of these pixels
             self._diff_pending = False
         else:
             ops.pixel_diff(pixel_values, T, P, self.W, threshold=self.cfg.pixel_threshold, out=self.mask)
@@ -257,21 +263,25 @@ class StreamCompressor:
         self.n_ids_out, self.n_image_ids = b["n_out"][0:1], b["n_out"][1:2]
 
     # ------------------------------------------------------------------------------------------
-    def capture(self, features, timestamps, events_repr, question, pixel_values, input_ids, attention_mask=None):
+    def capture(self, features, timestamps, events_repr, question, pixel_values, input_ids, attention_mask=None, *,
+                early_pixel: bool = True):
         """Capture both phases into CUDA graphs bound to these input tensors (refill them in place, then ``replay1()`` /
-        ``replay2()``).  The first centre is drawn on the device; everything else is identical to the eager path."""
+        ``replay2()``).  The first centre is drawn on the device; everything else is identical to the eager path.
+        ``early_pixel``: the raw pixel-difference mask is a parallel branch of the phase-1 graph (next to the solver)."""
+        pv1 = pixel_values if (early_pixel and self.gate) else None
         cur = torch.cuda.current_stream(self.device)
         warm = torch.cuda.Stream(device=self.device)
         warm.wait_stream(cur)
         with torch.cuda.stream(warm):  # one eager pass: lazy initialisation must not happen inside the capture
-            self.phase1(features, timestamps, first_index="device")
+            self.phase1(features, timestamps, first_index="device", pixel_values=pv1)
             self.phase2(features, events_repr, question, pixel_values, input_ids, attention_mask)
         cur.wait_stream(warm)
         torch.cuda.synchronize(self.device)
         self.graph1, self.graph2 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph1):
-            self.phase1(features, timestamps, first_index="device")
+            self.phase1(features, timestamps, first_index="device", pixel_values=pv1)
         with torch.cuda.graph(self.graph2, pool=self.graph1.pool()):
+            self._diff_pending = pv1 is not None  # graph 1 always leaves the raw mask behind
             self.phase2(features, events_repr, question, pixel_values, input_ids, attention_mask)
             self._stats_static = self.stats_row()
         return self

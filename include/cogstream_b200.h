@@ -220,6 +220,13 @@ CSB_API int csb_relevance_minor(const void* question, const void* events, int64_
  * caller can run it early (e.g. on a side stream while the k-means solver runs) and apply the per-frame rules later. */
 CSB_API int csb_pixel_diff(const void* pixels, int64_t t, int64_t P, int64_t W, int32_t dtype, double threshold,
                            uint8_t* mask, csb_stream_t stream);
+/* Same with two scheduling knobs for a caller that runs the kernel NEXT TO a latency-bound one of the same stream (the k-means
+ * solver): max_ctas > 0 caps the grid (64 CTAs stream the 508 MB of config 2 in ~160 us, hidden under the ~190 us solver, and
+ * leave the solver's L2 latency alone; 0 = the full grid), flags & CSB_PIXEL_EVICT_FIRST loads the pixels with an L2 evict-first
+ * policy (they are read exactly once; the solver's 2.9 MB Gram matrix then stays L2-resident).  csb_pixel_diff = (0, EVICT_FIRST). */
+#define CSB_PIXEL_EVICT_FIRST 1
+CSB_API int csb_pixel_diff_ex(const void* pixels, int64_t t, int64_t P, int64_t W, int32_t dtype, double threshold,
+                              uint8_t* mask, int64_t max_ctas, int32_t flags, csb_stream_t stream);
 CSB_API int csb_mask_finalize(uint8_t* mask, int64_t t, int64_t P, int64_t min_tokens, const uint8_t* minor_flags,
                               int64_t frame0, csb_stream_t stream);
 CSB_API int csb_pixel_mask(const void* pixels, int64_t t, int64_t P, int64_t W, int32_t dtype, double threshold,

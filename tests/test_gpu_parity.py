@@ -730,7 +730,7 @@ def test_pipeline_odd_shapes(dev, T, P, D, k, C):
     p2 = orc.phase2(st.features, p1, ev, q, st.pixel_values, st.grid_sizes, st.merge_sizes, st.modals, st.input_ids,
                     synthetic.IMAGE_TOKEN_INDEX, st.attention_mask)
     W = st.pixel_values.numel() // (T * P)
-    sc = StreamCompressor(T, P, D, W, st.input_ids.numel(), device=dev, cfg=StreamConfig(cluster_num=k))
+    sc = StreamCompressor(T, P, D, W, st.input_ids.numel(), device=dev, cfg=StreamConfig(cluster_num=k, gather_events=True))
     d = st.to(dev)
     sc.phase1(d.features, d.timestamps, init_indices=init.to(dev), reseed_pool=pool.to(dev))
     sc.phase2(d.features, ev.to(dev), q.to(dev), d.pixel_values, d.input_ids, d.attention_mask)
@@ -742,9 +742,12 @@ def test_pipeline_odd_shapes(dev, T, P, D, k, C):
     assert_bf16_close(r["features"], p2.features)
     assert rel_err(r["centroids"], p1.centroids) < REL_TOL
     off = r["event_offsets"].tolist()
-    packed = r["packed_events"].view(T, P, D).cpu()
+    order = r["event_order"].cpu().long()
+    packed = r["packed_events"].view(T, P, D).cpu()  # gather_events=True: the optional event-major packed copy
+    f3 = st.features.view(T, P, D)
     for i in range(k):
         assert torch.equal(packed[off[i]: off[i + 1]].reshape(-1, D), p1.events[i])
+        assert torch.equal(f3[order[off[i]: off[i + 1]]].reshape(-1, D), p1.events[i])
 
 
 @pytest.mark.parametrize("T,P,D", [(300, 6, 128), (2300, 2, 32)])  # the second: long-stream path (unit table upload, grid k-means++)
@@ -1176,3 +1179,68 @@ def test_reseed_pool_overflow_is_reported(dev):
     sc.phase1(d.features, d.timestamps, init_indices=init)  # default pool: fine
     sc.phase2(d.features, ev.to(dev), q.to(dev), d.pixel_values, d.input_ids, d.attention_mask)
     assert sc.results()["status"]["reseed_overflow"] is False
+
+
+@pytest.mark.parametrize("T,P,D,k", [(600, 4, 64, 40), (1000, 2, 32, 67), (1500, 2, 32, 100), (333, 3, 64, 23)])
+def test_kmeanspp_approximate_score_filter_equals_exact(dev, monkeypatch, T, P, D, k):
+    """Single-CTA k-means++ (fused into the solver launch for T <= 1024, its own kernel up to T = 2048): the argmax found from
+    the approximate scores (no IEEE division) == the exact two-division scores of every round (CSB_INIT_EXACT) == the CPU oracle,
+    also on data with many exact duplicates (ties -> lowest index) and for the unfused launch (CSB_FUSED_INIT=0)."""
+    feats, _ = synthetic.make_features(T, P, D, T)
+    f3 = feats.view(T, P, D).clone()
+    f3[T // 3: T // 3 + 40] = f3[T // 3]  # 40 identical frames
+    ts = torch.arange(T, dtype=torch.float64)
+    g = torch.Generator().manual_seed(T + 1)
+    noise = torch.empty(k - 1, T).exponential_(1, generator=g)
+    noise[3] = noise[3, 0]  # a constant noise row: the score order is the distance order, duplicates tie exactly
+    first = int(torch.randint(0, T, (1,), generator=g))
+    pool = [int(v) for v in torch.randint(0, T, (k * 31,), generator=g)]
+    res = {}
+    for mode in ("fast", "exact", "unfused"):
+        if mode == "exact":
+            monkeypatch.setenv("CSB_INIT_EXACT", "1")
+        if mode == "unfused":
+            monkeypatch.setenv("CSB_FUSED_INIT", "0")
+        _, _, assign, info = kmeans_with_time_min_max(f3.to(dev), ts.to(dev), k, first_index=first, exp_noise=noise,
+                                                      reseed_indices=pool, return_info=True)
+        res[mode] = (info.init_indices.tolist(), assign.cpu(), info.iterations, info.n_reseed_used, info.n_noise_used)
+        monkeypatch.delenv("CSB_INIT_EXACT", raising=False)
+        monkeypatch.delenv("CSB_FUSED_INIT", raising=False)
+    for other in ("exact", "unfused"):
+        assert res["fast"][0] == res[other][0] and torch.equal(res["fast"][1], res[other][1]) and res["fast"][2:] == res[other][2:]
+    info_o = orc.KMeansInfo()
+    orig = random.randint
+    try:
+        random.randint = lambda a, b: first
+        _, _, as_o = orc.kmeans_with_time_min_max(f3, ts, k, exp_noise=noise, reseed_indices=pool, info=info_o)
+    finally:
+        random.randint = orig
+    assert res["fast"][0] == info_o.init_indices
+    assert torch.equal(res["fast"][1], as_o) and res["fast"][2] == info_o.iterations
+
+
+def test_early_pixel_diff_overlapped_with_solver(dev):
+    """phase1(pixel_values=...) computes the raw pixel mask on the side stream next to the solver (throttled grid, L2 evict-first):
+    identical results to the serial order, eager and as captured graphs."""
+    T, P, D = 300, 12, 128
+    k = math.ceil(T / 15)
+    st = synthetic.make_stream(T, P, D, 7, C=32, near_threshold_frac=0.1)
+    ev, q = synthetic.make_embeddings(k, 256, 7)
+    d = st.to(dev)
+    evd, qd = ev.to(dev), q.to(dev)
+    W = st.pixel_values.numel() // (T * P)
+    g = torch.Generator().manual_seed(7)
+    init = torch.randperm(T, generator=g)[:k].to(dev)
+    outs = []
+    for early in (False, True):
+        sc = StreamCompressor(T, P, D, W, st.input_ids.numel(), device=dev, cfg=StreamConfig(early_pixel_ctas=8))
+        sc.phase1(d.features, d.timestamps, init_indices=init, pixel_values=d.pixel_values if early else None)
+        sc.phase2(d.features, evd, qd, d.pixel_values, d.input_ids, d.attention_mask)
+        r = sc.results()
+        outs.append((r["assignments"].clone(), r["mask"].clone(), r["features"].clone(), r["input_ids"].clone(), list(r["minor"])))
+    for x, y in zip(outs[0][:4], outs[1][:4]):
+        assert torch.equal(x, y)
+    assert outs[0][4] == outs[1][4]
+    raw = ops.pixel_diff(d.pixel_values, T, P, W)
+    for ctas, ef in ((1, True), (3, False), (0, True)):
+        assert torch.equal(ops.pixel_diff(d.pixel_values, T, P, W, max_ctas=ctas, evict_first=ef), raw)
