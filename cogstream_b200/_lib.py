@@ -28,6 +28,7 @@ class KMeansParams(C.Structure):
         ("n_init_given", C.c_int64),
         ("n_reseed_pool", C.c_int64),
         ("ldg", C.c_int64),
+        ("frames_per_warp", C.c_int64),
     ]
 
 
@@ -35,7 +36,7 @@ class CompactArgs(C.Structure):
     """csb_compact_args (include/cogstream_b200.h)."""
     _fields_ = [
         ("x_bf16", C.c_void_p), ("T", C.c_int64), ("P", C.c_int64), ("D", C.c_int64),
-        ("mask", C.c_void_p), ("minor_flags", C.c_void_p), ("min_tokens", C.c_int64),
+        ("mask", C.c_void_p), ("minor_flags", C.c_void_p), ("frame_kind", C.c_void_p), ("min_tokens", C.c_int64),
         ("finalize", C.c_int32), ("pool_minor", C.c_int32),
         ("input_ids", C.c_void_p), ("n_ids", C.c_int64), ("image_token_index", C.c_int64),
         ("attention_mask", C.c_void_p), ("labels", C.c_void_p),

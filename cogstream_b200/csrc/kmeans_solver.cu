@@ -1359,10 +1359,11 @@ int csb_kmeans_solve(const double* G, const void* timestamps, const csb_kmeans_p
     int st = check_launch("kmeanspp");
     if (st) return st;
   }
-  // Lloyd loop: one frame per warp in the assignment phase (T = 600: 75 CTAs).  The loop is latency-bound: two frames per warp
-  // (half the CTAs) cost ~2 us per iteration and, measured, leave the throughput of concurrent streams unchanged
-  int fpw = 1;  // frames per warp in the assignment pass (CSB_SOLVER_FPW: tuning runs)
-  if (const char* o = getenv("CSB_SOLVER_FPW")) fpw = atoi(o) > 0 ? atoi(o) : 1;
+  // Lloyd loop: frames_per_warp frames per warp in the assignment phase (default 2; T = 600: 38 CTAs).  The loop is
+  // latency-bound: one frame per warp (75 CTAs) saves ~2 us per iteration for a stream that runs alone, but with six streams in
+  // flight the extra co-resident CTAs cost the bandwidth-bound kernels of the other streams 7 % (measured: 2.15 vs 2.00 M frames/s)
+  int fpw = p->frames_per_warp > 0 ? (int)p->frames_per_warp : 2;  // (CSB_SOLVER_FPW overrides: tuning runs)
+  if (const char* o = getenv("CSB_SOLVER_FPW")) fpw = atoi(o) > 0 ? atoi(o) : fpw;
   int64_t nb = (T + fpw * kSolverWarps - 1) / (fpw * kSolverWarps);
   if (nb > sms) nb = sms;
   if (nb < 1) nb = 1;

@@ -685,11 +685,16 @@ __global__ void __launch_bounds__(kPixWarps * 32, 1) pixel_diff_tma_kernel(const
 
 // per-frame rules: min_tokens padding (:413-414) then the minor-frame override (:416-422). A warp per frame.
 __global__ void __launch_bounds__(256) mask_finalize_kernel(uint8_t* __restrict__ mask, int t, int P, int min_tokens,
-                                                            const uint8_t* __restrict__ minor_flags, int64_t frame0) {
+                                                            const uint8_t* __restrict__ minor_flags, int64_t frame0,
+                                                            const uint8_t* __restrict__ kind) {
   const int lane = threadIdx.x & 31;
   const int f = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (f >= t) return;
   uint8_t* m = mask + (int64_t)f * P;
+  if (kind && kind[frame0 + f]) {  // image item / single-frame video: all tokens kept
+    for (int p = lane; p < P; p += 32) m[p] = 1;
+    return;
+  }
   if (minor_flags && minor_flags[frame0 + f]) {
     for (int p = lane; p < P; p += 32) m[p] = (p == 0) ? 1 : 0;
     return;
@@ -1083,6 +1088,7 @@ struct CompactStreamArgs {
   uint8_t* mask;  // [T*P] in: raw difference mask, out: final mask
   int T, P, fpc, n_tok_chunks, min_tokens, finalize;
   const uint8_t* minor;  // [T] or nullptr
+  const uint8_t* kind;   // [T] or nullptr: 1 = image-like frame (all tokens kept)
   int* counts;
   int32_t* pos;
   int32_t* kept_index;
@@ -1146,6 +1152,8 @@ __global__ void __launch_bounds__(kScanThreads) compact_stream_coop_kernel(Compa
       uint8_t* sm = s_m + (fr - f0) * P;
       if (!a.finalize) {
         for (int p = lane; p < P; p += 32) sm[p] = m[p] ? 1 : 0;
+      } else if (a.kind && a.kind[fr]) {  // :401-403 image / single-frame video: every token kept, no per-frame rule
+        for (int p = lane; p < P; p += 32) { sm[p] = 1; m[p] = 1; }
       } else if (a.minor && a.minor[fr]) {  // :416-422 minor frames keep only token 0
         for (int p = lane; p < P; p += 32) { const uint8_t v = p == 0 ? 1 : 0; sm[p] = v; m[p] = v; }
       } else {
@@ -1486,7 +1494,8 @@ int csb_mask_finalize(uint8_t* mask, int64_t t, int64_t P, int64_t min_tokens, c
                       csb_stream_t stream) {
   CSB_DEVICE_OR_RETURN();
   CSB_REQUIRE(mask && t > 0 && P > 0, "mask_finalize: null argument or empty shape");
-  mask_finalize_kernel<<<(unsigned)((t + 7) / 8), 256, 0, as_stream(stream)>>>(mask, (int)t, (int)P, (int)min_tokens, minor_flags, frame0);
+  mask_finalize_kernel<<<(unsigned)((t + 7) / 8), 256, 0, as_stream(stream)>>>(mask, (int)t, (int)P, (int)min_tokens, minor_flags, frame0,
+                                                                               nullptr);
   return check_launch("mask_finalize");
 }
 
@@ -1585,7 +1594,10 @@ int csb_compact_stream(const csb_compact_args* p, csb_stream_t stream) {
   const uint8_t* pool_flags = p->pool_minor ? p->minor_flags : nullptr;
   if (!fpc || grid > cap || getenv("CSB_NO_COOP_SCAN")) {  // frames longer than a chunk, or more chunks than co-resident CTAs
     int st = CSB_OK;
-    if (p->finalize) st = csb_mask_finalize(p->mask, T, P, p->min_tokens, p->minor_flags, 0, stream);
+    if (p->finalize) {
+      mask_finalize_kernel<<<(unsigned)((T + 7) / 8), 256, 0, s>>>(p->mask, (int)T, (int)P, (int)p->min_tokens, p->minor_flags, 0, p->frame_kind);
+      st = check_launch("mask_finalize");
+    }
     if (st) return st;
     st = csb_compact_tokens(p->x_bf16, T, P, p->D, p->mask, pool_flags, p->out_bf16, p->kept_index, p->n_kept, p->workspace,
                             p->workspace_bytes, stream);
@@ -1599,7 +1611,7 @@ int csb_compact_stream(const csb_compact_args* p, csb_stream_t stream) {
   const size_t cbytes = align_up(sizeof(int32_t) * (size_t)(nn + 1), 256);
   CompactStreamArgs a;
   a.mask = p->mask; a.T = (int)T; a.P = (int)P; a.fpc = fpc; a.n_tok_chunks = n_tok_chunks; a.min_tokens = (int)p->min_tokens;
-  a.finalize = p->finalize; a.minor = p->minor_flags;
+  a.finalize = p->finalize; a.minor = p->minor_flags; a.kind = p->frame_kind;
   a.pos = reinterpret_cast<int32_t*>(w);
   w += align_up(sizeof(int32_t) * (size_t)nn, 256);
   a.counts = reinterpret_cast<int*>(w); a.img_counts = reinterpret_cast<int*>(w + cbytes); a.keep_counts = reinterpret_cast<int*>(w + 2 * cbytes);

@@ -152,7 +152,7 @@ class KMeansBuffers:
 
 def kmeans_solve(G: torch.Tensor, timestamps: torch.Tensor, buf: KMeansBuffers, *, n_init_given: int,
                  exp_noise: Optional[torch.Tensor], reseed_pool: Optional[torch.Tensor], alpha: float = 2.0,
-                 max_iteration: int = 30, tol: float = 1e-4) -> None:
+                 max_iteration: int = 30, tol: float = 1e-4, frames_per_warp: int = 0) -> None:
     """k-means++ + Lloyd on the Gram matrix.  ``buf.init_indices[:n_init_given]`` must be filled."""
     _, ldg = _gram_view(G)
     _need(timestamps, "timestamps", None, 1)
@@ -169,7 +169,8 @@ def kmeans_solve(G: torch.Tensor, timestamps: torch.Tensor, buf: KMeansBuffers, 
     if reseed_pool is not None:
         _need(reseed_pool, "reseed_pool", torch.int64, 1)
         n_pool = reseed_pool.numel()
-    p = KMeansParams(T, k, _TS_DTYPE[timestamps.dtype], int(max_iteration), float(alpha), float(tol), int(n_init_given), n_pool, ldg)
+    p = KMeansParams(T, k, _TS_DTYPE[timestamps.dtype], int(max_iteration), float(alpha), float(tol), int(n_init_given), n_pool, ldg,
+                     int(frames_per_warp))
     with _on_device(G):
         check(_lib.load().csb_kmeans_solve(
             G.data_ptr(), timestamps.data_ptr(), C.byref(p), buf.init_indices.data_ptr(), _ptr(exp_noise), _ptr(reseed_pool),
@@ -466,10 +467,12 @@ def compact_stream_workspace(n_tokens: int, n_ids: int, device) -> torch.Tensor:
 def compact_stream(x: torch.Tensor, T: int, P: int, mask: torch.Tensor, minor_flags: Optional[torch.Tensor], *, min_tokens: int = 1,
                    finalize: bool = True, pool_minor: bool = True, input_ids: Optional[torch.Tensor] = None,
                    image_token_index: int = -1, attention_mask: Optional[torch.Tensor] = None, labels: Optional[torch.Tensor] = None,
-                   out: Optional[torch.Tensor] = None, workspace: Optional[torch.Tensor] = None, bufs: Optional[dict] = None):
+                   out: Optional[torch.Tensor] = None, workspace: Optional[torch.Tensor] = None, bufs: Optional[dict] = None,
+                   frame_kind: Optional[torch.Tensor] = None):
     """Phase-2 tail in one entry point: per-frame mask rules (in place on ``mask``), token compaction with the pooled token of the
     minor frames, id filtering.  -> dict(out [T*P, D], kept_index [T*P] i32, n_kept [1] i64, out_ids, out_attention, out_labels,
-    n_out [2] i64 = {ids kept, <image> ids seen}).  ``bufs``: a dict of pre-allocated outputs to reuse (same keys)."""
+    n_out [2] i64 = {ids kept, <image> ids seen}).  ``bufs``: a dict of pre-allocated outputs to reuse (same keys).
+    ``frame_kind`` [T] uint8: 1 marks the frames of image items / single-frame videos (all tokens kept, no per-frame rule)."""
     _need(x, "x", torch.bfloat16, 2)
     _need(mask, "mask", torch.uint8, 1)
     D = x.shape[1]
@@ -505,7 +508,7 @@ def compact_stream(x: torch.Tensor, T: int, P: int, mask: torch.Tensor, minor_fl
             o_lb = buf("out_labels", (n_ids,), torch.int64)
     need = int(_lib.load().csb_compact_stream_workspace_bytes(n, n_ids))
     ws = workspace if workspace is not None and workspace.numel() >= need else torch.zeros(need, dtype=torch.uint8, device=dev)
-    a = CompactArgs(x.data_ptr(), T, P, D, mask.data_ptr(), _ptr(minor_flags), int(min_tokens), 1 if finalize else 0,
+    a = CompactArgs(x.data_ptr(), T, P, D, mask.data_ptr(), _ptr(minor_flags), _ptr(frame_kind), int(min_tokens), 1 if finalize else 0,
                     1 if (pool_minor and minor_flags is not None) else 0, _ptr(input_ids), n_ids, int(image_token_index),
                     _ptr(attention_mask), _ptr(labels), o.data_ptr(), kept.data_ptr(), n_kept.data_ptr(), _ptr(o_ids), _ptr(o_am),
                     _ptr(o_lb), _ptr(n_out), ws.data_ptr(), ws.numel())

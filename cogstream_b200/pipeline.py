@@ -58,6 +58,9 @@ class StreamConfig:
     # `early_pixel_ctas` CTAs the 508 MB pass (160 us on 64 SMs) hides completely under the ~190 us latency-bound solver without
     # slowing it (solver + pixel back to back 321 us, overlapped 207 us); an uncapped grid stretches the solver by ~15 us.
     early_pixel_ctas: int = 64
+    # frames per warp in the solver's assignment pass (csb_kmeans_params.frames_per_warp): 2 = fewer co-resident CTAs, best
+    # throughput with several streams in flight; 1 = ~2 us less per Lloyd iteration for a stream that runs alone
+    solver_frames_per_warp: int = 2
 
     def clusters_for(self, T: int) -> int:
         if self.cluster_num is not None:
@@ -75,7 +78,12 @@ class StreamCompressor:
     """Buffers + launch sequence for streams of one shape (T frames, P tokens, D channels, W pixel width)."""
 
     def __init__(self, T: int, P: int, D: int, W: int, n_ids: int, *, device, cfg: Optional[StreamConfig] = None,
-                 ts_dtype=torch.float64, embed_dim: int = 3584, embed_dtype=torch.bfloat16, image_token_index: int = 151665):
+                 ts_dtype=torch.float64, embed_dim: int = 3584, embed_dtype=torch.bfloat16, image_token_index: int = 151665,
+                 items: Optional[Sequence] = None):
+        """``items``: the visual items of the prompt in order, ``[(n_frames, modal), ...]`` with modal "video" / "image"
+        (cogreasoner_chat.py:392-430 iterates over them); default = one video item of T frames.  All items share P tokens per
+        frame (the reference's ``features.view(total_image_num, P, D)``, :279, needs that too).  Every video item is its own
+        pixel-difference segment (its first frame is fully kept); image items and single-frame videos keep every token."""
         self.cfg = cfg or StreamConfig()
         self.T, self.P, self.D, self.W, self.n_ids = T, P, D, W, n_ids
         self.K = P * D
@@ -95,6 +103,19 @@ class StreamCompressor:
             self.pool = torch.zeros(max(1, n_pool), dtype=torch.int64, device=dev)
             self.centroids = torch.empty(k, self.K, dtype=torch.float32, device=dev) if self.cfg.compute_centroids else None
             self.packed = torch.empty(T, self.K, dtype=torch.bfloat16, device=dev) if self.cfg.gather_events else None
+        self.items = [(int(t), str(m)) for t, m in items] if items is not None else [(T, "video")]
+        if sum(t for t, _ in self.items) != T or any(t < 1 or m not in ("video", "image") for t, m in self.items):
+            raise ValueError(f"items {self.items} do not add up to T = {T} frames of modal 'video' / 'image'")
+        kind = torch.zeros(T, dtype=torch.uint8)
+        self._segments = []  # (first frame, frames) of the video items that go through the pixel-difference kernel
+        f0 = 0
+        for t, m in self.items:
+            if m == "image" or t == 1:  # :401-403
+                kind[f0: f0 + t] = 1
+            else:
+                self._segments.append((f0, t))
+            f0 += t
+        self.frame_kind = kind.to(dev) if bool(kind.any()) else None
         self._row_base = torch.tensor([T, self.k if self.gate else 0, 0, 0, 0, 0, 0, 0, 0], dtype=torch.int64, device=dev)
         self._ticket = torch.zeros(1, dtype=torch.int32, device=dev)
         self.minor_flags = torch.zeros(T, dtype=torch.uint8, device=dev)
@@ -129,6 +150,15 @@ class StreamCompressor:
     def _join(self):
         self._ev_join.record(self.side)
         torch.cuda.current_stream(self.device).wait_event(self._ev_join)
+
+    def _pixel_diff(self, pixel_values: torch.Tensor, stream=None, max_ctas: int = 0) -> None:
+        """Raw pixel-difference mask of every video item (each item is its own segment, :405-412) into ``self.mask``; the rows of
+        image-like frames are filled by the compaction kernel (``frame_kind``)."""
+        P, W = self.P, self.W
+        rows_per_frame = pixel_values.shape[0] // self.T
+        for f0, t in self._segments:
+            ops.pixel_diff(pixel_values[f0 * rows_per_frame: (f0 + t) * rows_per_frame], t, P, W, threshold=self.cfg.pixel_threshold,
+                           out=self.mask[f0 * P: (f0 + t) * P], stream=stream, max_ctas=max_ctas)
 
     # ------------------------------------------------------------------------------------------
     def phase1(self, features: torch.Tensor, timestamps: torch.Tensor, *, init_indices: Optional[torch.Tensor] = None,
@@ -190,13 +220,13 @@ class StreamCompressor:
         n_given, noise, pool = d_["n_given"], d_["noise"], d_["pool"]
         self._G_used = G
         ops.kmeans_solve(G, timestamps, self.km, n_init_given=n_given, exp_noise=noise if k > 1 else None,
-                         reseed_pool=pool, alpha=self.cfg.alpha, max_iteration=self.cfg.max_iteration, tol=self.cfg.tol)
+                         reseed_pool=pool, alpha=self.cfg.alpha, max_iteration=self.cfg.max_iteration, tol=self.cfg.tol,
+                         frames_per_warp=self.cfg.solver_frames_per_warp)
         if fork:
             # enqueued AFTER the cooperative solver so its CTAs become resident first; the HBM-bound difference kernel then
             # fills the rest of the machine while the (latency-bound) solver iterates
             self.side.wait_event(self._ev_fork)
-            ops.pixel_diff(pixel_values, T, self.P, self.W, threshold=self.cfg.pixel_threshold, out=self.mask, stream=self.side,
-                           max_ctas=self.cfg.early_pixel_ctas)
+            self._pixel_diff(pixel_values, stream=self.side, max_ctas=self.cfg.early_pixel_ctas)
             self._ev_diff.record(self.side)
             self._diff_pending = True
         self.order, self.ev_off = self.km.event_order, self.km.event_offsets
@@ -242,7 +272,7 @@ class StreamCompressor:
         par = self.cfg.parallel_branches and self.gate and not self._diff_pending
         if par:  # the raw pixel-difference mask does not depend on the relevance test: a parallel branch
             with self._branch():
-                ops.pixel_diff(pixel_values, T, P, self.W, threshold=self.cfg.pixel_threshold, out=self.mask)
+                self._pixel_diff(pixel_values)
         if self.gate:
             self._select(events_repr, question, hidden, cu_seqlens)
         else:
@@ -253,11 +283,11 @@ class StreamCompressor:
         elif self._diff_pending:  # phase 1 computed (and joined) the raw mask of these pixels
             self._diff_pending = False
         else:
-            ops.pixel_diff(pixel_values, T, P, self.W, threshold=self.cfg.pixel_threshold, out=self.mask)
+            self._pixel_diff(pixel_values)
         # per-frame mask rules + scan + compaction (minor frames emitted as their pooled token) + id filter
         b = ops.compact_stream(features, T, P, self.mask, self.minor_flags, min_tokens=self.cfg.min_tokens, input_ids=input_ids,
                                image_token_index=self.image_token_index, attention_mask=attention_mask, out=self.out,
-                               workspace=self.compact_ws, bufs=self._cmp)
+                               workspace=self.compact_ws, bufs=self._cmp, frame_kind=self.frame_kind)
         self.kept_index, self.n_kept = b["kept_index"], b["n_kept"]
         self.out_ids, self.out_attention = b["out_ids"], b.get("out_attention")
         self.n_ids_out, self.n_image_ids = b["n_out"][0:1], b["n_out"][1:2]

@@ -143,16 +143,21 @@ def make_embeddings(k: int, Dl: int = 3584, seed: int = 0, *, low_frac: float = 
 
 def make_stream(T: int, P: int, D: int, seed: int = 0, *, fps: float = 1.0, merge: int = 2, C: int = 588,
                 iid: bool = False, ts_dtype=torch.float64, n_text_head: int = 14, n_text_tail: int = 23,
-                change_frac: float = 0.2, near_threshold_frac: float = 0.0) -> SyntheticStream:
+                change_frac: float = 0.2, near_threshold_frac: float = 0.0, items: Optional[List] = None) -> SyntheticStream:
+    """``items``: optional ``[(n_frames, modal), ...]`` split of the T frames into visual items (several video segments, images,
+    single-frame videos: what ``grid_sizes`` / ``modals`` carry for multi-item prompts, cogreasoner_chat.py:392-430)."""
     feats, scene = make_features(T, P, D, seed, iid=iid)
     ts = (torch.arange(T, dtype=torch.float64) / fps).to(ts_dtype)
     pix = make_pixels(T, P, merge, C, seed, change_frac=change_frac, near_threshold_frac=near_threshold_frac)
     gh, gw = _grid_for_tokens(P)
-    grid = torch.tensor([[T, gh * merge, gw * merge]], dtype=torch.long)
+    if items is None:
+        items = [(T, "video")]
+    assert sum(t for t, _ in items) == T
+    grid = torch.tensor([[t, gh * merge, gw * merge] for t, _ in items], dtype=torch.long)
     ids = torch.cat([
         torch.arange(1000, 1000 + n_text_head, dtype=torch.long),
         torch.full((T * P,), IMAGE_TOKEN_INDEX, dtype=torch.long),
         torch.arange(2000, 2000 + n_text_tail, dtype=torch.long),
     ])
-    return SyntheticStream(T, P, D, feats, ts, pix, grid, torch.tensor([merge], dtype=torch.long), ["video"],
-                           ids, torch.ones_like(ids), scene)
+    return SyntheticStream(T, P, D, feats, ts, pix, grid, torch.tensor([merge] * len(items), dtype=torch.long),
+                           [m for _, m in items], ids, torch.ones_like(ids), scene)

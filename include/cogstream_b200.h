@@ -104,6 +104,9 @@ typedef struct csb_kmeans_params {
                              always drawn by the host, :41); the remaining k - n are sampled k-means++ */
   int64_t n_reseed_pool;  /* entries available in reseed_pool (host random.randint(0, T-1) draws) */
   int64_t ldg;            /* leading dimension of G (elements); 0 means T */
+  int64_t frames_per_warp; /* assignment pass: frames a warp takes per Lloyd iteration = how many CTAs the cooperative launch
+                             uses (T / (8 * frames_per_warp)).  0 = default (2).  1 shortens an iteration by ~2 us at T = 600
+                             (single-stream latency); 2 leaves more SMs to the kernels of concurrent streams (throughput). */
 } csb_kmeans_params;
 
 /* Device-side result block, written by csb_kmeans_solve (read it after a stream sync). */
@@ -263,6 +266,7 @@ CSB_API int csb_filter_ids(const int64_t* input_ids, int64_t n_ids, int64_t imag
  * kernel cannot take (P > 1024, more chunks than co-resident CTAs) run the three separate entry points -- same results.
  *   mask        [T*P] uint8, in: the raw csb_pixel_diff mask (or a final mask with finalize = 0), out: the final mask
  *   minor_flags [T] uint8 or NULL; pool_minor != 0 emits token 0 of a flagged frame as the frame's pooled mean
+ *   frame_kind  [T] uint8 or NULL: multi-item inputs (:392-430), see the field
  *   input_ids   [n_ids] int64 or NULL (then no id filtering); n_out int64[2] = {ids kept, <image> ids seen}
  *   workspace   csb_compact_stream_workspace_bytes(T*P, n_ids) bytes, ZERO-FILLED ONCE by the caller before its first use and
  *               private to one CUDA stream at a time (it holds the carried barrier state). */
@@ -271,6 +275,8 @@ typedef struct csb_compact_args {
   int64_t T, P, D;
   uint8_t* mask;
   const uint8_t* minor_flags;
+  const uint8_t* frame_kind; /* [T] uint8 or NULL: 1 = frame of an image item / single-frame video (cogreasoner_chat.py:401-403:
+                                all tokens kept, no per-frame rule; only looked at with finalize != 0), 0 = video frame */
   int64_t min_tokens;
   int32_t finalize;
   int32_t pool_minor;

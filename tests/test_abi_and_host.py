@@ -110,8 +110,22 @@ def test_custom_ops_registered_and_shape_inference():
     """The torch custom-op layer exists, infers shapes on meta tensors and has no CPU kernel."""
     import cogstream_b200  # noqa: F401
 
-    for name in ("gram", "centroid_update", "dist_to_assigned", "pool_norm", "cosine_flags", "pixel_mask", "compact_tokens"):
+    names = ("gram", "gram_extend", "kmeans_solve", "centroid_update", "centroid_gather", "dist_to_assigned", "dist_to_assigned_gram",
+             "select_representatives", "representatives_gram", "event_order", "gather_rows", "cosine_flags", "minor_frames",
+             "relevance_minor", "relevance_select", "relevance_select_hidden", "pool_norm", "pool_frames_inplace", "pixel_diff",
+             "mask_finalize", "pixel_mask", "compact_tokens", "filter_ids", "compact_stream", "embed_scatter", "embed_scatter_ordered",
+             "seq_mean_pool")
+    for name in names:
         assert hasattr(torch.ops.cogstream_b200, name), name
+    # every compute entry point of the header is reachable through the dispatcher (plumbing / workspace-size queries aside)
+    covered = {"csb_" + n.replace("_hidden", "").replace("embed_scatter_ordered", "embed_scatter_ordered") for n in names}
+    plumbing = {"csb_abi_version", "csb_last_error", "csb_check_device", "csb_kernel_launches", "csb_pixel_diff_ex"}
+    missing = [d for d in _declared() if d not in covered and d not in plumbing and not d.endswith("_workspace_bytes")]
+    assert missing == [], missing
+    m = torch.empty(12, dtype=torch.uint8, device="meta")
+    ids = torch.empty(20, dtype=torch.int64, device="meta")
+    o = torch.ops.cogstream_b200.compact_stream(torch.empty(12, 64, dtype=torch.bfloat16, device="meta"), 6, 2, m, None, ids, 7)
+    assert o[0].shape == (12, 64) and o[3].shape == (20,) and o[5].shape == (2,)
     x = torch.empty(10, 64, dtype=torch.bfloat16, device="meta")
     assert torch.ops.cogstream_b200.gram(x).shape == (10, 10)
     out, kept, n = torch.ops.cogstream_b200.compact_tokens(x, 5, 2, torch.empty(10, dtype=torch.uint8, device="meta"))

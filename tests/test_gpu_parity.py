@@ -406,6 +406,43 @@ def test_custom_op_layer(dev):
     assert torch.equal(pb, pb2) and torch.equal(sq, sq2)
 
 
+def test_custom_op_layer_whole_path(dev):
+    """The whole hot path driven through torch.ops.cogstream_b200.* only == the fused StreamCompressor pipeline."""
+    co = torch.ops.cogstream_b200
+    T, P, D = 180, 5, 64
+    k = math.ceil(T / 15)
+    st = synthetic.make_stream(T, P, D, 13, C=8)
+    ev, q = synthetic.make_embeddings(k, 128, 13)
+    d = st.to(dev)
+    evd, qd = ev.to(dev), q.to(dev)
+    W = st.pixel_values.numel() // (T * P)
+    init = torch.randperm(T, generator=torch.Generator().manual_seed(13))[:k].to(dev)
+    sc = StreamCompressor(T, P, D, W, st.input_ids.numel(), device=dev)
+    sc.phase1(d.features, d.timestamps, init_indices=init)
+    sc.phase2(d.features, evd, qd, d.pixel_values, d.input_ids, d.attention_mask)
+    want = sc.results()
+    x2 = d.features.view(T, P * D)
+    G = co.gram(x2)
+    b = ops.KMeansBuffers(T, k, torch.float64, dev)
+    b.init_indices.copy_(init)
+    pool = torch.zeros(k * 31, dtype=torch.int64, device=dev)
+    co.kmeans_solve(G, d.timestamps, b.init_indices, None, pool, b.assignments, b.centroid_times, b.member_offsets, b.members,
+                    b.event_order, b.event_offsets, b.status, b.workspace, k)
+    assert torch.equal(b.assignments, want["assignments"])
+    cent = co.centroid_update(x2, b.member_offsets, b.members, k)
+    assert torch.equal(cent.view(k, P, D), want["centroids"])
+    ticket = torch.zeros(1, dtype=torch.int32, device=dev)
+    cos, low, dist, reps, cnt, rflags, mflags, mlist, nm = co.relevance_select(qd.view(-1), evd, G, b.event_offsets, b.event_order,
+                                                                               b.assignments, ticket)
+    assert mlist[: int(nm)].tolist() == want["minor"] and torch.equal(cos, want["cos"])
+    mask = co.pixel_diff(d.pixel_values, T, P, W)
+    out, kept, nk, oids, oam, nout = co.compact_stream(d.features, T, P, mask, mflags, d.input_ids, synthetic.IMAGE_TOKEN_INDEX,
+                                                       d.attention_mask)
+    n1, n2 = int(nk), int(nout[0])
+    assert torch.equal(mask.view(torch.bool), want["mask"]) and torch.equal(out[:n1], want["features"])
+    assert torch.equal(oids[:n2], want["input_ids"]) and torch.equal(oam[:n2], want["attention_mask"])
+
+
 def test_pixel_diff_kernels_agree(dev):
     """The TMA-staged kernel (default), the L2-reuse kernel and the oracle arithmetic give the same raw mask."""
     import os
@@ -1116,12 +1153,14 @@ def test_relevance_select_matches_unfused(dev, name, from_hidden):
     if from_hidden:
         lens = [int(v) for v in torch.randint(1, 40, (k,), generator=gen)]
         cu = torch.tensor([0] + list(torch.tensor(lens).cumsum(0)), dtype=torch.int32).to(dev)
-        hidden = (torch.randn(sum(lens), Dl, generator=gen) + 0.5 * q.float().cpu()).to(torch.bfloat16).to(dev)
+        sign = torch.repeat_interleave(torch.tensor([1.0 if j % 2 else -0.2 for j in range(k)]), torch.tensor(lens)).unsqueeze(1)
+        hidden = (torch.randn(sum(lens), Dl, generator=gen) + sign * q.float().cpu()).to(torch.bfloat16).to(dev)
         ev = ops.seq_mean_pool(hidden, cu)
         b = ops.relevance_select(q, None, G, off, order, assign, ticket, k=k, hidden=hidden, cu_seqlens=cu)
         assert torch.equal(b["events"], ev)
     else:
-        ev = (torch.randn(k, Dl, generator=gen) + 0.5 * q.float().cpu()).to(torch.bfloat16).to(dev)
+        sign = torch.tensor([1.0 if j % 2 else -0.2 for j in range(k)]).unsqueeze(1)
+        ev = (torch.randn(k, Dl, generator=gen) + sign * q.float().cpu()).to(torch.bfloat16).to(dev)
         b = ops.relevance_select(q, ev, G, off, order, assign, ticket, k=k)
     dist, reps, counts, rflags = ops.representatives_gram(G, off, order, k, 2)
     cos, low, mflags, mlist, nm = ops.relevance_minor(q, ev, assign, rflags, ticket, 0.45)
@@ -1244,3 +1283,39 @@ def test_early_pixel_diff_overlapped_with_solver(dev):
     raw = ops.pixel_diff(d.pixel_values, T, P, W)
     for ctas, ef in ((1, True), (3, False), (0, True)):
         assert torch.equal(ops.pixel_diff(d.pixel_values, T, P, W, max_ctas=ctas, evict_first=ef), raw)
+
+
+def test_pipeline_multi_item_inputs(dev):
+    """Several visual items in one prompt (cogreasoner_chat.py:392-430): video segments (each its own pixel-difference segment, first
+    frame fully kept), an image and a single-frame video (all tokens kept, no minor-frame override in the mask, token 0 still
+    pooled by compress_unimportant_events) -- the fused pipeline against the oracle."""
+    items = [(70, "video"), (1, "image"), (45, "video"), (1, "video"), (63, "video")]
+    T, P, D = sum(t for t, _ in items), 6, 128
+    k = math.ceil(T / 15)
+    st = synthetic.make_stream(T, P, D, 41, C=24, near_threshold_frac=0.1, items=items)
+    ev, q = synthetic.make_embeddings(k, 256, 41, low_frac=0.8)
+    g = torch.Generator().manual_seed(41)
+    init = torch.randperm(T, generator=g)[:k]
+    p1 = orc.phase1(st.features, T, st.timestamps, init_indices=init.tolist())
+    p2 = orc.phase2(st.features, p1, ev, q, st.pixel_values, st.grid_sizes, st.merge_sizes, st.modals, st.input_ids,
+                    synthetic.IMAGE_TOKEN_INDEX, st.attention_mask)
+    W = st.pixel_values.numel() // (T * P)
+    d = st.to(dev)
+    for early in (False, True):
+        sc = StreamCompressor(T, P, D, W, st.input_ids.numel(), device=dev, items=items)
+        sc.phase1(d.features, d.timestamps, init_indices=init.to(dev), pixel_values=d.pixel_values if early else None)
+        sc.phase2(d.features, ev.to(dev), q.to(dev), d.pixel_values, d.input_ids, d.attention_mask)
+        r = sc.results()
+        assert torch.equal(r["assignments"].cpu(), p1.assignments) and r["minor"] == p2.minor
+        assert torch.equal(r["mask"].cpu(), p2.mask)
+        assert torch.equal(r["input_ids"].cpu(), p2.input_ids)
+        assert_bf16_close(r["features"], p2.features)
+    mask = p2.mask.view(T, P)
+    assert bool(mask[70].all()) and bool(mask[116].all())       # image / single-frame video: every token kept
+    assert bool(mask[71].all()) and bool(mask[117].all())       # first frame of the following video segments
+    # the drop-in method handles the same item list (it always did): same mask
+    npat = st.grid_sizes.prod(dim=1).div(st.merge_sizes ** 2).long()
+    got = _Stub()._get_compression_mask(d.pixel_values, npat.to(dev), d.grid_sizes, d.merge_sizes, st.modals, minor_frame_indices=p2.minor)
+    assert torch.equal(got.cpu(), p2.mask)
+    with pytest.raises(ValueError):
+        StreamCompressor(T, P, D, W, st.input_ids.numel(), device=dev, items=[(T - 1, "video")])
