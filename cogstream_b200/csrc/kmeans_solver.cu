@@ -476,6 +476,27 @@ __device__ void compute_S(const SolverArgs& a, const int* s_offs, const int* s_m
     return;
   }
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  if (total <= 2 * stride) {
+    // few entries per thread (short streams, or only a handful of changed clusters): one entry at a time with 16 member loads in
+    // flight -- an event of ~15 frames is ONE L2 round trip instead of four.  Same ascending member order, same bits.
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += stride) {
+      const int i = (int)(idx / ncols);
+      const int j = cols[(int)(idx - (int64_t)i * ncols)];
+      const int beg = s_offs[j], len = s_offs[j + 1] - beg;
+      const double* g = a.G + (int64_t)i * a.ldg;
+      double sum = 0.0;
+      for (int e = 0; e < len; e += 16) {
+        double v[16];
+#pragma unroll
+        for (int w = 0; w < 16; ++w) v[w] = (e + w < len) ? __ldg(g + s_memb[beg + e + w]) : 0.0;
+#pragma unroll
+        for (int w = 0; w < 16; ++w)
+          if (e + w < len) sum += v[w];
+      }
+      S[(int64_t)i * k + j] = sum;
+    }
+    return;
+  }
   for (int64_t idx0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx0 < total; idx0 += kSE * stride) {
     const double* g[kSE];
     int beg[kSE], len[kSE];
@@ -806,6 +827,7 @@ __device__ void solver_outputs(const SolverArgs& a, const int* s_offs, const int
   const int k = a.k;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   csb_kmeans_status* st = a.status;
+  my_margin = warp_min(my_margin);  // (the first lane of every frame group tracked its frames' margins)
   if (lane == 0 && my_margin < __int_as_float(0x7f800000))
     atomicMin(reinterpret_cast<unsigned*>(&st->min_margin), __float_as_uint(fmaxf(my_margin, 0.f)));
   if (blockIdx.x == 0) {
@@ -958,7 +980,16 @@ __global__ void __launch_bounds__(kSolverThreads, WIDE ? 1 : 2) kmeans_solver_ke
     const double* S = a.S[cur];
     const double* q = s_q[cur];
     const double* ctc = s_ctb[cur];
-    for (int i = blockIdx.x * kSolverWarps + warp; i < T; i += nb * kSolverWarps) {
+    // A frame is handled by a group of L lanes (L = 32, or 16 / 8 when k <= 64 / 32 and the frame's k columns fit 4 per lane):
+    // a warp then works on 32 / L frames side by side -- the same per-frame arithmetic, the dependent chain (S row load, fp64
+    // square roots, reductions) of several frames overlapped.  Reductions run over the group's lanes only (min / max / argmin
+    // with the lowest-index tie-break do not depend on the reduction tree).
+    const int L = (!WIDE && k <= 32) ? 8 : ((!WIDE && k <= 64) ? 16 : 32);
+    const int gpw = 32 / L;                      // frames per warp pass
+    const int sub = lane & (L - 1), grp = lane / L;
+    for (int i0 = (blockIdx.x * kSolverWarps + warp) * gpw; i0 < T; i0 += nb * kSolverWarps * gpw) {
+      const bool frame_ok = i0 + grp < T;
+      const int i = frame_ok ? i0 + grp : T - 1;  // idle groups shadow the last frame (full-warp shuffles below), no store
       const double gii = diag[i];
       const TS ti = a.diag_in_smem ? s_ts[i] : load_ts<TS>(a.ts, i);
       float fmin_ = __int_as_float(0x7f800000), fmax_ = -fmin_;
@@ -990,19 +1021,27 @@ __global__ void __launch_bounds__(kSolverThreads, WIDE ? 1 : 2) kmeans_solver_ke
             }
           }
       } else {
+      {
+        double s0[4];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int j = lane + 32 * u;
-        if (j < k) {
-          const double d2 = gii - 2.0 * (__ldcg(S + (int64_t)i * k + j) * s_rn[j]) + q[j];
-          dc[u] = (float)sqrt(d2 > 0.0 ? d2 : 0.0);
-          TS dt = ti - (TS)ctc[j];
-          tc[u] = dt < TS(0) ? -dt : dt;
-          fmin_ = fminf(fmin_, dc[u]); fmax_ = fmaxf(fmax_, dc[u]);
-          tmin_ = tc[u] < tmin_ ? tc[u] : tmin_; tmax_ = tc[u] > tmax_ ? tc[u] : tmax_;
+        for (int u = 0; u < 4; ++u) {
+          const int j = sub + L * u;
+          s0[u] = j < k ? __ldcg(S + (int64_t)i * k + j) : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int j = sub + L * u;
+          if (j < k) {
+            const double d2 = gii - 2.0 * (s0[u] * s_rn[j]) + q[j];
+            dc[u] = (float)sqrt(d2 > 0.0 ? d2 : 0.0);
+            TS dt = ti - (TS)ctc[j];
+            tc[u] = dt < TS(0) ? -dt : dt;
+            fmin_ = fminf(fmin_, dc[u]); fmax_ = fmaxf(fmax_, dc[u]);
+            tmin_ = tc[u] < tmin_ ? tc[u] : tmin_; tmax_ = tc[u] > tmax_ ? tc[u] : tmax_;
+          }
         }
       }
-      // k > 128: further blocks of 128 columns, 4 independent S loads per lane in flight (the row of S is an L2 / HBM read)
+      // k > 128 (then L == 32): further blocks of 128 columns, 4 independent S loads per lane in flight
       for (int j0 = 128; j0 < k; j0 += 128) {
         double sv[4];
 #pragma unroll
@@ -1024,8 +1063,12 @@ __global__ void __launch_bounds__(kSolverThreads, WIDE ? 1 : 2) kmeans_solver_ke
         }
       }
       }
-      fmin_ = warp_min(fmin_); fmax_ = warp_max(fmax_);
-      tmin_ = warp_min(tmin_); tmax_ = warp_max(tmax_);
+      for (int o = L >> 1; o > 0; o >>= 1) {  // min / max over the group's lanes
+        const float f0 = __shfl_xor_sync(0xffffffffu, fmin_, o), f1 = __shfl_xor_sync(0xffffffffu, fmax_, o);
+        const TS t0 = __shfl_xor_sync(0xffffffffu, tmin_, o), t1 = __shfl_xor_sync(0xffffffffu, tmax_, o);
+        fmin_ = f0 < fmin_ ? f0 : fmin_; fmax_ = f1 > fmax_ ? f1 : fmax_;
+        tmin_ = t0 < tmin_ ? t0 : tmin_; tmax_ = t1 > tmax_ ? t1 : tmax_;
+      }
       const float fspread = __fsub_rn(fmax_, fmin_);
       const TS tspread = tmax_ - tmin_;
       float best = __int_as_float(0x7f800000), second = best;
@@ -1067,7 +1110,7 @@ __global__ void __launch_bounds__(kSolverThreads, WIDE ? 1 : 2) kmeans_solver_ke
       } else {
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
-        const int j = lane + 32 * u;
+        const int j = sub + L * u;
         if (j < k) consider(dc[u], tc[u], j);
       }
       for (int j0 = 128; j0 < k; j0 += 128) {
@@ -1090,8 +1133,7 @@ __global__ void __launch_bounds__(kSolverThreads, WIDE ? 1 : 2) kmeans_solver_ke
         }
       }
       }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
+      for (int o = L >> 1; o > 0; o >>= 1) {
         const float ob = __shfl_xor_sync(0xffffffffu, best, o);
         const float os = __shfl_xor_sync(0xffffffffu, second, o);
         const int oj = __shfl_xor_sync(0xffffffffu, bestj, o);
@@ -1099,7 +1141,7 @@ __global__ void __launch_bounds__(kSolverThreads, WIDE ? 1 : 2) kmeans_solver_ke
         second = fminf(hi, fminf(second, os));
         if (ob < best || (ob == best && oj < bestj)) { best = ob; bestj = oj; }
       }
-      if (lane == 0) {
+      if (sub == 0 && frame_ok) {
         a.assignments[i] = bestj;  // :104 lowest index on ties
         a.assign32[i] = bestj;
         if (k > 1) my_margin = fminf(my_margin, second - best);
@@ -1364,7 +1406,10 @@ int csb_kmeans_solve(const double* G, const void* timestamps, const csb_kmeans_p
   // flight the extra co-resident CTAs cost the bandwidth-bound kernels of the other streams 7 % (measured: 2.15 vs 2.00 M frames/s)
   int fpw = p->frames_per_warp > 0 ? (int)p->frames_per_warp : 2;  // (CSB_SOLVER_FPW overrides: tuning runs)
   if (const char* o = getenv("CSB_SOLVER_FPW")) fpw = atoi(o) > 0 ? atoi(o) : fpw;
-  int64_t nb = (T + fpw * kSolverWarps - 1) / (fpw * kSolverWarps);
+  // a warp pass covers 32 / L frames (L lanes per frame: 8 / 16 for k <= 32 / 64 in the narrow kernel, see the assignment pass)
+  const int gpw = wide ? 1 : (k <= 32 ? 4 : (k <= 64 ? 2 : 1));
+  if (!(p->frames_per_warp > 0) && !getenv("CSB_SOLVER_FPW") && gpw > 1) fpw = 1;  // the side-by-side frames already halve the CTA count
+  int64_t nb = (T + (int64_t)fpw * gpw * kSolverWarps - 1) / ((int64_t)fpw * gpw * kSolverWarps);
   if (nb > sms) nb = sms;
   if (nb < 1) nb = 1;
   void* args[] = {&a};

@@ -48,10 +48,8 @@ class StreamConfig:
     reseed_pool: Optional[int] = None
     compute_centroids: bool = True
     gather_events: bool = False  # also materialise the event-major packed token copy (csb_embed_scatter_ordered makes it unnecessary)
-    # independent kernels of one stream run on a side CUDA stream (parallel branches of the captured graphs): the Exp(1) /
-    # pool draws next to the Gram kernel, the representative selection next to centroid_gather, the relevance test next to
-    # the pixel-difference kernel.  Measured at config 2: one stream alone 0.609 -> 0.593 ms, but 6 streams in flight
-    # 0.31 -> 0.34 ms per stream (twice the CUDA streams fighting for the same SMs), so it is off unless latency is the goal.
+    # phase 2 without an early pixel mask: run the pixel-difference kernel on the side stream next to the selection launch
+    # (the Exp(1) / pool draws of phase 1 always run next to the Gram kernel)
     parallel_branches: bool = False
     # phase1(pixel_values=...) starts the raw pixel-difference mask on a side stream right after the Gram kernel, next to the
     # k-means solver.  Measured at config 2 (scripts/overlap_probe2.py): with L2 evict-first pixel loads and the grid capped at
@@ -175,7 +173,6 @@ class StreamCompressor:
             return
         T, k = self.T, self.k
         x2 = features.view(T, self.K)
-        par = self.cfg.parallel_branches and pixel_values is None
         fork = pixel_values is not None
 
         def draws():
@@ -205,18 +202,14 @@ class StreamCompressor:
             return nonlocal_out
 
         G = self.G if gram is None else gram
-        if par:  # the draws do not depend on the Gram matrix: a parallel branch
-            with self._branch():
-                d_ = draws()
-            if gram is None:
-                ops.gram(x2, impl=self.cfg.gram_impl, out=self.G, workspace=self.gram_ws)
-            self._join()
-        else:
-            if gram is None:
-                ops.gram(x2, impl=self.cfg.gram_impl, out=self.G, workspace=self.gram_ws)
-            if fork:
-                self._ev_fork.record(torch.cuda.current_stream(self.device))
+        # the RNG draws (three tiny torch kernels) do not depend on the Gram matrix: they run on the side stream next to it
+        with self._branch():
             d_ = draws()
+        if gram is None:
+            ops.gram(x2, impl=self.cfg.gram_impl, out=self.G, workspace=self.gram_ws)
+        if fork:
+            self._ev_fork.record(torch.cuda.current_stream(self.device))
+        self._join()
         n_given, noise, pool = d_["n_given"], d_["noise"], d_["pool"]
         self._G_used = G
         ops.kmeans_solve(G, timestamps, self.km, n_init_given=n_given, exp_noise=noise if k > 1 else None,

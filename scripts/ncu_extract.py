@@ -1,5 +1,5 @@
-"""Extract the per-kernel counters we quote from an `ncu --set full` report into profiles/r1_ncu_full_summary.json.
-Usage: python scripts/ncu_extract.py <report.ncu-rep> <capture-tag> [--skip-first N]   (needs `ncu` on PATH; CPU only)"""
+"""Extract the per-kernel counters we quote from an `ncu --set full` report into profiles/<round>_ncu_full_summary.json.
+Usage: python scripts/ncu_extract.py <report.ncu-rep> <capture-tag> [round-prefix, default r2]   (needs `ncu` on PATH; CPU only)"""
 import csv, io, json, os, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 rep, tag = sys.argv[1], sys.argv[2]
@@ -21,7 +21,7 @@ for r in data:
         if m in col:
             e[m] = f"{r[col[m]]} {units[col[m]]}".strip()
     res.append(e)
-path = os.path.join(ROOT, "profiles", "r1_ncu_full_summary.json")
+path = os.path.join(ROOT, "profiles", (sys.argv[3] if len(sys.argv) > 3 else "r2") + "_ncu_full_summary.json")
 cur = json.load(open(path)) if os.path.isfile(path) else []
 cur = [c for c in cur if c.get("capture") != tag] + res
 json.dump(cur, open(path, "w"), indent=1)

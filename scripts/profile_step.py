@@ -22,7 +22,7 @@ sc = StreamCompressor(T, P, D, st.pixel_values.numel() // (T * P), st.input_ids.
 torch.manual_seed(1234)
 random.seed(1234)
 for i in range(steps):
-    sc.phase1(d.features, d.timestamps)
+    sc.phase1(d.features, d.timestamps, pixel_values=d.pixel_values)  # the pixel-difference mask runs next to the solver
     sc.phase2(d.features, ev, q, d.pixel_values, d.input_ids, d.attention_mask)
 torch.cuda.synchronize()
 r = sc.results()

@@ -1312,7 +1312,8 @@ def test_pipeline_multi_item_inputs(dev):
         assert_bf16_close(r["features"], p2.features)
     mask = p2.mask.view(T, P)
     assert bool(mask[70].all()) and bool(mask[116].all())       # image / single-frame video: every token kept
-    assert bool(mask[71].all()) and bool(mask[117].all())       # first frame of the following video segments
+    for f in (71, 117):                                         # first frame of the following video segments: fully kept,
+        assert bool(mask[f].all()) or (f in p2.minor and int(mask[f].sum()) == 1)  # unless the minor override beats it (:416-422)
     # the drop-in method handles the same item list (it always did): same mask
     npat = st.grid_sizes.prod(dim=1).div(st.merge_sizes ** 2).long()
     got = _Stub()._get_compression_mask(d.pixel_values, npat.to(dev), d.grid_sizes, d.merge_sizes, st.modals, minor_frame_indices=p2.minor)
