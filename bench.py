@@ -1035,6 +1035,8 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=4, help="timed e2e steps (each moves streams_per_step x 759 MB over PCIe)")
     ap.add_argument("--segment", type=int, default=120, help="config4: new frames per question (120 = 60 s at 2 fps)")
     args = ap.parse_args()
+    if os.environ.get("CSB_NOEARLY"):
+        args.early_pixel = 0
     if args.impl == "reference":
         run_reference_arm(args)
         return

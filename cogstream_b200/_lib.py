@@ -103,6 +103,7 @@ PROTOTYPES = {
     "csb_embed_scatter_workspace_bytes": (_sz, [_i64]),
     "csb_embed_scatter_ordered": (C.c_int, [_p, _i64, _i64, _p, _i64, _p, _p, _i64, _i64, _i64, _i32, _p, _p, _p, _sz, _p]),
     "csb_embed_scatter": (C.c_int, [_p, _i64, _i64, _p, _i64, _p, _i64, _i64, _i32, _p, _p, _p, _sz, _p]),
+    "csb_ln_merge": (C.c_int, [_p, _i64, _i64, _i64, _p, _p, _dbl, _p, _p]),
     "csb_seq_mean_pool_workspace_bytes": (_sz, [_i64, _i64]),
     "csb_seq_mean_pool": (C.c_int, [_p, _p, _i64, _i64, _i32, _p, _p, _sz, _p]),
 }

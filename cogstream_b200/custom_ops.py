@@ -361,3 +361,13 @@ def seq_mean_pool(hidden: T_, cu_seqlens: T_) -> T_:
 @seq_mean_pool.register_fake
 def _(hidden, cu_seqlens):
     return hidden.new_empty((cu_seqlens.shape[0] - 1, hidden.shape[1]))
+
+
+@_op("ln_merge")
+def ln_merge(hidden: T_, merge: int, gamma: T_, beta: T_, eps: float) -> T_:
+    return ops.ln_merge(hidden, merge, gamma, beta, eps)
+
+
+@ln_merge.register_fake
+def _(hidden, merge, gamma, beta, eps):
+    return hidden.new_empty((hidden.shape[0] // (merge * merge), hidden.shape[1]))

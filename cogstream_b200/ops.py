@@ -638,3 +638,24 @@ def seq_mean_pool(hidden: torch.Tensor, cu_seqlens: torch.Tensor, *, out: Option
         check(_lib.load().csb_seq_mean_pool(hidden.data_ptr(), cu_seqlens.data_ptr(), n_seq, Dl, _EL_DTYPE[hidden.dtype],
                                             o.data_ptr(), ws.data_ptr(), ws.numel(), _stream(hidden)), "seq_mean_pool")
     return o
+
+
+# --------------------------------------------------------------------------------------------- upstream: encoder tail
+def ln_merge(hidden: torch.Tensor, merge: int, gamma: torch.Tensor, beta: torch.Tensor, eps: float, *,
+             out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """``post_layernorm`` + the ``merge x merge`` bilinear token merge of the vision tower in one pass
+    (modeling_videollama3_encoder.py:479, :485-502).  ``hidden`` [n, C] bf16, merge-block-contiguous -> [n / merge^2, C] bf16."""
+    _need(hidden, "hidden", torch.bfloat16, 2)
+    _need(gamma, "gamma", torch.bfloat16, 1)
+    _need(beta, "beta", torch.bfloat16, 1)
+    n, Cw = hidden.shape
+    if gamma.shape[0] != Cw or beta.shape[0] != Cw:
+        raise ValueError("ln_merge: LayerNorm weight / bias width mismatch")
+    m2 = int(merge) * int(merge)
+    if n % m2:
+        raise ValueError(f"ln_merge: {n} rows are not whole {merge} x {merge} blocks")
+    o = out if out is not None else torch.empty(n // m2, Cw, dtype=torch.bfloat16, device=hidden.device)
+    with _on_device(hidden):
+        check(_lib.load().csb_ln_merge(hidden.data_ptr(), n, Cw, int(merge), gamma.data_ptr(), beta.data_ptr(), float(eps), o.data_ptr(),
+                                       _stream(hidden)), "ln_merge")
+    return o

@@ -15,6 +15,7 @@ the per-stream stats rows (``gather_stats``), as in SURVEY.md section 8(e).
 from __future__ import annotations
 
 import math
+import os
 import random
 from dataclasses import dataclass
 from typing import Dict, List, Optional, Sequence
@@ -55,10 +56,11 @@ class StreamConfig:
     # k-means solver.  Measured at config 2 (scripts/overlap_probe2.py): with L2 evict-first pixel loads and the grid capped at
     # `early_pixel_ctas` CTAs the 508 MB pass (160 us on 64 SMs) hides completely under the ~190 us latency-bound solver without
     # slowing it (solver + pixel back to back 321 us, overlapped 207 us); an uncapped grid stretches the solver by ~15 us.
-    early_pixel_ctas: int = 64
-    # frames per warp in the solver's assignment pass (csb_kmeans_params.frames_per_warp): 2 = fewer co-resident CTAs, best
-    # throughput with several streams in flight; 1 = ~2 us less per Lloyd iteration for a stream that runs alone
-    solver_frames_per_warp: int = 2
+    early_pixel_ctas: int = int(os.environ.get("CSB_EARLY_PIX_CTAS", "64"))
+    parallel_draws: bool = os.environ.get("CSB_PAR_DRAWS", "1") != "0"  # RNG draws on the side stream, next to the Gram kernel
+    # sequential frame passes per warp in the solver's assignment pass (csb_kmeans_params.frames_per_warp); 0 = the library's
+    # choice (k <= 64: frames side by side on sub-warp groups, one pass; else two passes).  More passes = fewer co-resident CTAs
+    solver_frames_per_warp: int = 0
 
     def clusters_for(self, T: int) -> int:
         if self.cluster_num is not None:
@@ -202,14 +204,21 @@ class StreamCompressor:
             return nonlocal_out
 
         G = self.G if gram is None else gram
-        # the RNG draws (three tiny torch kernels) do not depend on the Gram matrix: they run on the side stream next to it
-        with self._branch():
+        if self.cfg.parallel_draws:
+            # the RNG draws (three tiny torch kernels) do not depend on the Gram matrix: they run on the side stream next to it
+            with self._branch():
+                d_ = draws()
+            if gram is None:
+                ops.gram(x2, impl=self.cfg.gram_impl, out=self.G, workspace=self.gram_ws)
+            if fork:
+                self._ev_fork.record(torch.cuda.current_stream(self.device))
+            self._join()
+        else:
+            if gram is None:
+                ops.gram(x2, impl=self.cfg.gram_impl, out=self.G, workspace=self.gram_ws)
+            if fork:
+                self._ev_fork.record(torch.cuda.current_stream(self.device))
             d_ = draws()
-        if gram is None:
-            ops.gram(x2, impl=self.cfg.gram_impl, out=self.G, workspace=self.gram_ws)
-        if fork:
-            self._ev_fork.record(torch.cuda.current_stream(self.device))
-        self._join()
         n_given, noise, pool = d_["n_given"], d_["noise"], d_["pool"]
         self._G_used = G
         ops.kmeans_solve(G, timestamps, self.km, n_init_given=n_given, exp_noise=noise if k > 1 else None,

@@ -104,9 +104,10 @@ typedef struct csb_kmeans_params {
                              always drawn by the host, :41); the remaining k - n are sampled k-means++ */
   int64_t n_reseed_pool;  /* entries available in reseed_pool (host random.randint(0, T-1) draws) */
   int64_t ldg;            /* leading dimension of G (elements); 0 means T */
-  int64_t frames_per_warp; /* assignment pass: frames a warp takes per Lloyd iteration = how many CTAs the cooperative launch
-                             uses (T / (8 * frames_per_warp)).  0 = default (2).  1 shortens an iteration by ~2 us at T = 600
-                             (single-stream latency); 2 leaves more SMs to the kernels of concurrent streams (throughput). */
+  int64_t frames_per_warp; /* assignment pass: sequential frame passes of a warp per Lloyd iteration.  A pass covers 32 / L frames
+                             side by side (L lanes per frame: 8 / 16 / 32 for k <= 32 / 64 / more), and the cooperative launch
+                             uses T / (8 * (32 / L) * frames_per_warp) CTAs.  0 = default (1 pass when L < 32, else 2): 38 CTAs
+                             at T = 600, k = 40.  Fewer passes shorten an iteration, more leave SMs to concurrent streams. */
 } csb_kmeans_params;
 
 /* Device-side result block, written by csb_kmeans_solve (read it after a stream sync). */
@@ -370,6 +371,17 @@ CSB_API size_t csb_seq_mean_pool_workspace_bytes(int64_t n_seq, int64_t Dl);
  *   hidden [cu_seqlens[n_seq], Dl] `dtype`, cu_seqlens device int32 [n_seq + 1], out [n_seq, Dl] `dtype`. */
 CSB_API int csb_seq_mean_pool(const void* hidden, const int32_t* cu_seqlens, int64_t n_seq, int64_t Dl, int dtype, void* out,
                       void* workspace, size_t workspace_bytes, csb_stream_t stream);
+
+/* ---- upstream of the path: the vision tower's tail ------------------------------------------------------
+ * model/modeling_videollama3_encoder.py:479 (post_layernorm) + :485-502 (view / permute / reshape / permute /
+ * F.interpolate(size = grid / merge, mode='bilinear') / permute / view) in ONE pass: the encoder's last hidden states arrive
+ * merge-block-contiguous (the merge^2 patches of a merged token are consecutive rows), so the chain is "LayerNorm the rows of a
+ * block, blend them" -- for even merge the four central patches with weights 1/4, for odd merge the central patch alone (what
+ * align_corners=False bilinear sampling at scale = merge evaluates).  ATen's op order: LayerNorm in fp32 with biased variance,
+ * rounded to bf16; blend in fp32, rounded to bf16.  Item-independent (valid across items that share `merge`).
+ *   hidden [n_rows, C] bf16, gamma / beta [C] bf16, out [n_rows / merge^2, C] bf16; C % 8 == 0, C <= 2048. */
+CSB_API int csb_ln_merge(const void* hidden_bf16, int64_t n_rows, int64_t C, int64_t merge, const void* gamma_bf16,
+                         const void* beta_bf16, double eps, void* out_bf16, csb_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -43,6 +43,7 @@ __all__ = [
     "compress_unimportant_events",
     "get_compression_mask",
     "compress_visual_tokens",
+    "encoder_tail",
     "phase1",
     "phase2",
     "Phase1Result",
@@ -346,6 +347,24 @@ def compress_visual_tokens(
         ends = starts[1:] + [len(input_ids)]
         position_ids = torch.cat([torch.arange(e - s) for s, e in zip(starts, ends)])
     return mm_features, input_ids, attention_mask, position_ids, labels
+
+
+def encoder_tail(hidden_states: torch.Tensor, grid_sizes: torch.Tensor, merge_sizes: torch.Tensor, ln_weight: torch.Tensor,
+                 ln_bias: torch.Tensor, eps: float) -> torch.Tensor:
+    """model/modeling_videollama3_encoder.py:479-504 -- ``post_layernorm`` followed, per item, by the view / permute / reshape /
+    permute / bilinear ``interpolate`` / permute / view chain that merges every ``merge x merge`` patch block into one token.
+    Runs on whatever device the inputs live on (the parity tests run it with the CUDA ATen kernels the reference itself uses)."""
+    h = torch.nn.functional.layer_norm(hidden_states, (hidden_states.shape[-1],), ln_weight, ln_bias, eps)  # :479
+    chunks = h.split(grid_sizes.prod(dim=1).tolist(), dim=0)  # :481
+    outs = []
+    for hs, grid, m in zip(chunks, grid_sizes.tolist(), merge_sizes.tolist()):  # :484-502
+        t, gh, gw = grid
+        c = hs.shape[-1]
+        hs = hs.view(t, gh // m, gw // m, m, m, c).permute(0, 1, 3, 2, 4, 5)
+        hs = hs.reshape(t, gh, gw, c).permute(0, 3, 1, 2)
+        hs = torch.nn.functional.interpolate(hs, size=(gh // m, gw // m), mode="bilinear")
+        outs.append(hs.permute(0, 2, 3, 1).reshape(-1, c))
+    return torch.cat(outs, dim=0)  # :504
 
 
 # --------------------------------------------------------------------------------------

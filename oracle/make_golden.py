@@ -376,6 +376,25 @@ def summary_case(T=150, P=4, D=64, Dl=96, seed=77, vocab=512):
     )
 
 
+def encoder_tail_case(C=1152, seed=5):
+    """Encoder tail (modeling_videollama3_encoder.py:479-504): the unmodified reference forward on a stand-in with identity
+    embeddings / layers, several items with merge sizes 1, 2, 3 and 4, the SigLIP width.  CPU ATen arithmetic."""
+    g = torch.Generator().manual_seed(seed)
+    grid = torch.tensor([[3, 4, 6], [1, 2, 2], [2, 6, 6], [2, 4, 8], [1, 8, 4]])
+    merge = torch.tensor([2, 1, 3, 2, 4])
+    n = int(grid.prod(dim=1).sum())
+    hidden = (torch.randn(n, C, generator=g) * 3 + torch.randn(n, 1, generator=g)).to(torch.bfloat16)
+    ln = torch.nn.LayerNorm(C, eps=1e-6).to(torch.bfloat16)
+    with torch.no_grad():
+        ln.weight.copy_(1 + 0.2 * torch.randn(C, generator=g))
+        ln.bias.copy_(0.1 * torch.randn(C, generator=g))
+    want = ref_loader.ref_encoder_tail(hidden, grid, merge, ln)
+    got = orc.encoder_tail(hidden, grid, merge, ln.weight.detach(), ln.bias.detach(), ln.eps)
+    assert torch.equal(want, got), "oracle.encoder_tail differs from the reference forward"
+    return dict(hidden=hidden, grid_sizes=grid, merge_sizes=merge, ln_weight=ln.weight.detach().clone(), ln_bias=ln.bias.detach().clone(),
+                eps=ln.eps, out=want)
+
+
 def main():
     assert ref_loader.available(), "reference not mounted"
     os.makedirs(GOLDEN_DIR, exist_ok=True)
@@ -396,6 +415,10 @@ def main():
     torch.save(summ, path)
     print(f"summary_case: k={summ['spec']['k']} ids={summ['event_ids'].numel()} minor={len(summ['minor'])} "
           f"-> {os.path.getsize(path) / 1024:.0f} KB")
+    et = encoder_tail_case()
+    path = os.path.join(GOLDEN_DIR, "encoder_tail.pt")
+    torch.save(et, path)
+    print(f"encoder_tail: {tuple(et['hidden'].shape)} -> {tuple(et['out'].shape)} -> {os.path.getsize(path) / 1024:.0f} KB")
     print("oracle == reference on every case (bit-for-bit)")
 
 

@@ -18,6 +18,8 @@ import contextlib
 import importlib.util
 import os
 import sys
+
+import torch
 import types
 
 REFERENCE_ROOT = os.environ.get("COGSTREAM_REFERENCE_ROOT", "/root/reference")
@@ -48,6 +50,24 @@ def chat_module():
 
         _cache["cc"] = cc
     return _cache["cc"]
+
+
+def encoder_module():
+    """The reference's ``model.modeling_videollama3_encoder`` (imports in the build container: flash_attn is present)."""
+    if REFERENCE_ROOT not in sys.path:
+        sys.path.insert(0, REFERENCE_ROOT)
+    import importlib
+    return importlib.import_module("model.modeling_videollama3_encoder")
+
+
+def ref_encoder_tail(hidden_states, grid_sizes, merge_sizes, post_layernorm):
+    """``Videollama3VisionEncoderModel.forward`` (:477-506) run UNMODIFIED on a stand-in whose embeddings / transformer stack are the
+    identity, i.e. exactly its tail: post_layernorm + the per-item bilinear merge."""
+    import types
+    M = encoder_module().Videollama3VisionEncoderModel
+    stub = types.SimpleNamespace(embeddings=lambda x: x, encoder=lambda h, g, m: h, post_layernorm=post_layernorm)
+    with torch.no_grad():
+        return M.forward(stub, hidden_states, grid_sizes, merge_sizes)
 
 
 def stub_self(image_token_index: int = 151665):

@@ -114,7 +114,7 @@ def test_custom_ops_registered_and_shape_inference():
              "select_representatives", "representatives_gram", "event_order", "gather_rows", "cosine_flags", "minor_frames",
              "relevance_minor", "relevance_select", "relevance_select_hidden", "pool_norm", "pool_frames_inplace", "pixel_diff",
              "mask_finalize", "pixel_mask", "compact_tokens", "filter_ids", "compact_stream", "embed_scatter", "embed_scatter_ordered",
-             "seq_mean_pool")
+             "seq_mean_pool", "ln_merge")
     for name in names:
         assert hasattr(torch.ops.cogstream_b200, name), name
     # every compute entry point of the header is reachable through the dispatcher (plumbing / workspace-size queries aside)

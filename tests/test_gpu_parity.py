@@ -1320,3 +1320,52 @@ def test_pipeline_multi_item_inputs(dev):
     assert torch.equal(got.cpu(), p2.mask)
     with pytest.raises(ValueError):
         StreamCompressor(T, P, D, W, st.input_ids.numel(), device=dev, items=[(T - 1, "video")])
+
+
+# ---- round 2: encoder tail ------------------------------------------------------------------------------------
+def _ulp_close(a, b, max_ulp=1, max_frac=2e-3):
+    """bf16 tensors equal up to `max_ulp` in at most `max_frac` of the elements (fp32 statistics summed in another order)."""
+    af, bf = a.float().cpu(), b.float().cpu()
+    ulp = bf.abs().clamp_min(1e-30).log2().floor().exp2() * 2.0 ** -7
+    diff = (af - bf).abs()
+    assert bool((diff <= max_ulp * ulp * 1.001).all()), float((diff / ulp).max())
+    assert float((diff > 0).float().mean()) <= max_frac, float((diff > 0).float().mean())
+    assert rel_err(a, b) < REL_TOL
+
+
+def test_encoder_tail_matches_reference_golden(dev):
+    """csb_ln_merge (post_layernorm + bilinear merge, one pass) against the unmodified reference forward's output (CPU ATen) and
+    against the same torch ops run on the GPU (the kernels the reference itself executes): <= 1 bf16 ulp in <= 0.2 % of the
+    elements (the fp32 mean / variance are summed in a different order), items with merge sizes 1 / 2 / 3 / 4."""
+    import os
+    from conftest import ROOT
+    from cogstream_b200 import encoder_tail
+    g = torch.load(os.path.join(ROOT, "tests", "golden", "encoder_tail.pt"))
+    ln = torch.nn.LayerNorm(g["hidden"].shape[1], eps=g["eps"]).to(torch.bfloat16).to(dev)
+    with torch.no_grad():
+        ln.weight.copy_(g["ln_weight"]); ln.bias.copy_(g["ln_bias"])
+    got = encoder_tail(ln, g["hidden"].to(dev), g["grid_sizes"].to(dev), g["merge_sizes"].to(dev))
+    assert got.shape == g["out"].shape
+    _ulp_close(got, g["out"])
+    on_gpu = orc.encoder_tail(g["hidden"].to(dev), g["grid_sizes"].to(dev), g["merge_sizes"].to(dev), ln.weight.detach(), ln.bias.detach(), g["eps"])
+    _ulp_close(got, on_gpu)
+
+
+def test_encoder_tail_full_size(dev):
+    """Config-2 sized tail (600 frames x 720 patches x 1152 channels, merge 2): against the torch ops on the GPU, chunked."""
+    from cogstream_b200 import encoder_tail
+    T, G, C = 600, 720, 1152
+    gen = torch.Generator(device=dev).manual_seed(3)
+    hidden = (torch.randn(T * G, C, device=dev, generator=gen) * 2 + 0.5).to(torch.bfloat16)
+    ln = torch.nn.LayerNorm(C, eps=1e-6).to(torch.bfloat16).to(dev)
+    with torch.no_grad():
+        ln.weight.copy_(1 + 0.1 * torch.randn(C, device=dev, generator=gen)); ln.bias.copy_(0.1 * torch.randn(C, device=dev, generator=gen))
+    grid = torch.tensor([[T, 24, 30]], device=dev)
+    merge = torch.tensor([2], device=dev)
+    got = encoder_tail(ln, hidden, grid, merge)
+    assert got.shape == (T * G // 4, C)
+    for f0 in (0, 299, 599):  # three frames of the stream through the reference's op chain
+        want = orc.encoder_tail(hidden[f0 * G: (f0 + 1) * G], torch.tensor([[1, 24, 30]], device=dev), merge, ln.weight.detach(), ln.bias.detach(), 1e-6)
+        _ulp_close(got[f0 * 180: (f0 + 1) * 180], want)
+    with pytest.raises(RuntimeError, match="invalid for input of size"):
+        encoder_tail(ln, hidden[: 25 * 30], torch.tensor([[1, 25, 30]], device=dev), merge)

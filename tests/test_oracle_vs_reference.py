@@ -30,3 +30,18 @@ def test_prompt_matches_reference():
     ts = torch.tensor([0.0, 1.0, 7.25, 100.5], dtype=torch.float64)
     assert create_visual_summary_prompt(12, ts) == cc.create_visual_summary_prompt(12, ts)
     assert create_visual_summary_prompt(4, [3.0, 4.0]) == cc.create_visual_summary_prompt(4, [3.0, 4.0])
+
+
+def test_encoder_tail_live():
+    """oracle.encoder_tail == the unmodified Videollama3VisionEncoderModel.forward tail (modeling_videollama3_encoder.py:479-504)."""
+    g = torch.Generator().manual_seed(9)
+    grid = torch.tensor([[2, 6, 4], [1, 4, 4], [3, 2, 2]])
+    merge = torch.tensor([2, 4, 1])
+    C = 64
+    hidden = torch.randn(int(grid.prod(dim=1).sum()), C, generator=g).to(torch.bfloat16)
+    ln = torch.nn.LayerNorm(C, eps=1e-6).to(torch.bfloat16)
+    with torch.no_grad():
+        ln.weight.copy_(torch.randn(C, generator=g)); ln.bias.copy_(torch.randn(C, generator=g))
+    want = ref_loader.ref_encoder_tail(hidden, grid, merge, ln)
+    got = orc.encoder_tail(hidden, grid, merge, ln.weight.detach(), ln.bias.detach(), ln.eps)
+    assert torch.equal(want, got)
