@@ -228,7 +228,7 @@ def _config_dict(args, world=None):
     if wl in ("config2", "config3"):
         w = CFG2
         d = dict(T=w["T"], P=w["P"], D=w["D"], k=math.ceil(w["T"] / 15), pixel_row=f"[T*{w['P'] * w['merge'] ** 2}, {w['C']}] bf16",
-                 embed_dim=w["Dl"], timestamps="float64", init="k-means++ sampled on device (Exp(1) noise drawn in the timed region)",
+                 embed_dim=w["Dl"], timestamps="float64", init="k-means++ sampled on device by the solver's built-in Philox generator (first centre, Exp(1) noise, re-seeds)",
                  l2=f"every lane has its own inputs (757 MB per stream, {args.depth} lanes = {0.757 * args.depth:.1f} GB distinct per GPU) "
                     "> 126 MB L2; no explicit flush")
         if wl == "config2":
@@ -738,12 +738,10 @@ def _stage_times_config4(sc, cache, d, ev_d, q_d, seg, reps=3):
     from cogstream_b200 import ops
     T, P, k = sc.T, sc.P, sc.k
     x2 = cache.X[:T]
-    noise = sc.noise[: k - 1]
 
     def solve(max_it):
-        sc.km.init_indices[:1].fill_(5)
-        sc.pool.random_(0, T)
-        ops.kmeans_solve(cache.gram, cache.ts[:T], sc.km, n_init_given=1, exp_noise=noise, reseed_pool=sc.pool, max_iteration=max_it)
+        ops.kmeans_solve(cache.gram, cache.ts[:T], sc.km, n_init_given=0, exp_noise=None, reseed_pool=None, max_iteration=max_it,
+                         rng_state=sc.rng_state)
 
     def ext():
         cache.T = T - seg
@@ -862,12 +860,11 @@ def _stage_list(sc, d, ev_d, q_d):
 
     T, P, k = sc.T, sc.P, sc.k
     x2 = d.features.view(T, sc.K)
-    noise = sc.noise[: k - 1]
-    state = {}
 
     def solve():
-        ops.kmeans_solve(sc.G, d.timestamps, sc.km, n_init_given=1, exp_noise=noise, reseed_pool=sc.pool, alpha=sc.cfg.alpha,
-                         max_iteration=sc.cfg.max_iteration, tol=sc.cfg.tol)
+        ops.kmeans_solve(sc.G, d.timestamps, sc.km, n_init_given=0, exp_noise=None, reseed_pool=None, alpha=sc.cfg.alpha,
+                         max_iteration=sc.cfg.max_iteration, tol=sc.cfg.tol, frames_per_warp=sc.cfg.solver_frames_per_warp,
+                         rng_state=sc.rng_state)
 
     def select():
         ops.relevance_select(q_d.view(-1), ev_d, sc.G, sc.km.event_offsets, sc.km.event_order, sc.km.assignments, sc._ticket, k=k,
@@ -880,7 +877,6 @@ def _stage_list(sc, d, ev_d, q_d):
 
     return [
         ("gram", lambda: ops.gram(x2, out=sc.G, workspace=sc.gram_ws)),
-        ("rng_noise", lambda: noise.exponential_(1)),
         ("kmeans_solve", solve),
         ("centroids", lambda: ops.centroid_gather(x2, sc.km.member_offsets, sc.km.members, sc.km.event_offsets, k,
                                                   sc.centroids, sc.packed)),
@@ -895,8 +891,6 @@ def _stage_times(sc, d, ev_d, q_d, reps=5):
     the launching stream (so host launch latency is not in the number), after one in-order pass has set up its inputs."""
     T = sc.T
     stages = _stage_list(sc, d, ev_d, q_d)
-    sc.km.init_indices[:1].fill_(random.randint(0, T - 1))
-    sc.pool.random_(0, T)
     for _, fn in stages:  # in-order pass: every stage sees valid inputs
         fn()
     return {name: _ev_time(fn, reps) for name, fn in stages}

@@ -28,6 +28,7 @@ class KMeansParams(C.Structure):
         ("n_init_given", C.c_int64),
         ("n_reseed_pool", C.c_int64),
         ("ldg", C.c_int64),
+        ("rng_state", C.c_void_p),
         ("frames_per_warp", C.c_int64),
     ]
 

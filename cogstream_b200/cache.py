@@ -28,6 +28,8 @@ class StreamCache:
         self.ts = torch.empty(capacity, dtype=ts_dtype, device=self.device)
         self.G = torch.empty(capacity, capacity, dtype=torch.float64, device=self.device)
         self.ws = torch.empty(ops.gram_workspace_bytes(capacity, self.K), dtype=torch.uint8, device=self.device)
+        self.rng_state = torch.randint(0, 2 ** 62, (2,), dtype=torch.int64, device=self.device)  # the solver's built-in generator
+        self.rng_state[1] = 0
         self.T = 0
 
     def append(self, features: torch.Tensor, timestamps: torch.Tensor, *, gram_impl: int = 0) -> int:
@@ -57,22 +59,28 @@ class StreamCache:
         if T <= k:
             raise ValueError("StreamCache.cluster: need more frames than clusters (the reference returns early, kmeans_with_time.py:30)")
         buf = ops.KMeansBuffers(T, k, self.ts.dtype, self.device)
-        noise = None
+        noise, rng = None, None
         if init_indices is not None:
             buf.init_indices.copy_(torch.as_tensor(list(init_indices), dtype=torch.int64))
             n_given = k
+        elif first_index is None and exp_noise is None:
+            n_given, rng = 0, self.rng_state  # first centre, Exp(1) noise and re-seeds from the solver's built-in generator
         else:
             first = random.randint(0, T - 1) if first_index is None else int(first_index)
             buf.init_indices[:1].fill_(first)
             n_given = 1
             if k > 1:
                 noise = exp_noise if exp_noise is not None else torch.empty(k - 1, T, dtype=torch.float32, device=self.device).exponential_(1)
-        # default pool = the strict upper bound on draws (k - 1 degenerate init rounds + k empty clusters per iteration): it
-        # cannot run out.  With a caller-supplied pool, `validate=True` reads the status back (one sync) and raises on overflow.
-        pool = reseed_pool if reseed_pool is not None else \
-            torch.randint(0, T, (k * (int(max_iteration) + 1),), dtype=torch.int64, device=self.device)
+        # re-seed draws: the built-in generator cannot run out; a caller-supplied pool can (`validate=True` reads the status back,
+        # one sync, and raises on overflow); without either, a pool of the strict upper bound k * (max_iteration + 1) is drawn
+        pool = reseed_pool
+        if pool is None and rng is None:
+            if init_indices is not None:
+                rng = self.rng_state
+            else:
+                pool = torch.randint(0, T, (k * (int(max_iteration) + 1),), dtype=torch.int64, device=self.device)
         ops.kmeans_solve(self.gram, self.ts[:T], buf, n_init_given=n_given, exp_noise=noise, reseed_pool=pool, alpha=float(alpha),
-                         max_iteration=int(max_iteration), tol=float(tol))
+                         max_iteration=int(max_iteration), tol=float(tol), rng_state=rng)
         if validate and ops.decode_status(buf.status)["reseed_overflow"]:
             raise RuntimeError("StreamCache.cluster: reseed_pool exhausted; the clustering is not the reference's")
         return buf, k

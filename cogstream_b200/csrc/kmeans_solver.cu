@@ -47,6 +47,7 @@ struct SolverArgs {
   unsigned long long* tl;  // phase timeline (globaltimer ns), [0] = entries written; profiling aid
   int diag_in_smem;   // 1: keep a shared-memory copy of the diagonal (T small enough)
   int multiwarp_fill; // 1: per-warp cluster counters fit in shared memory
+  const unsigned long long* rng;  // device {seed, offset} of the built-in generator, or nullptr (noise / pool supplied by the caller)
   int fused_init;     // 1: CTA 0 of the solver runs the k-means++ init itself (no separate kmeanspp launch)
   int init_exact;     // validation switch (CSB_INIT_EXACT): every sampling round evaluates the exact IEEE scores
   int32_t* assign32;  // [T] compact copy of the assignments (what every CTA reloads after the barrier)
@@ -86,6 +87,47 @@ __device__ __forceinline__ void grid_sync_backoff(unsigned* counter, unsigned& t
     }
     __syncthreads();
   }
+}
+
+// ---- built-in generator (csb_kmeans_params.rng_state): Philox4x32-10, counter = (index, stream, offset), key = seed ----------
+// The fused pipeline draws its randomness here instead of launching torch's generator kernels in front of the solver: the Exp(1)
+// noise of sampling round r for frame i is -log(U(r, i)), the host random.randint draws of kmeans_with_time.py:41 / :57 / :118
+// are floor(U * T).  Every thread that needs draw (stream, index) computes the same value; the offset advances once per solve.
+__device__ __forceinline__ uint32_t philox_draw(unsigned long long seed, unsigned long long offset, uint32_t stream, uint32_t index) {
+  uint32_t c0 = index, c1 = stream, c2 = (uint32_t)offset, c3 = (uint32_t)(offset >> 32);
+  uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    c0 = hi1 ^ c1 ^ k0; c1 = lo1; c2 = hi0 ^ c3 ^ k1; c3 = lo0;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  return c0;
+}
+constexpr uint32_t kRngFirst = 0xFFFFFFFFu, kRngReseed = 0xFFFFFFFEu;  // streams; sampling round r uses stream r
+
+struct RngKey {
+  unsigned long long seed, offset;
+};
+__device__ __forceinline__ RngKey load_rng(const SolverArgs& a) {
+  RngKey k;
+  k.seed = a.rng ? a.rng[0] : 0ull;
+  k.offset = a.rng ? a.rng[1] : 0ull;
+  return k;
+}
+// Exp(1) noise of sampling round `row` for frame i: the caller's array, or the built-in generator
+__device__ __forceinline__ float noise_at(const SolverArgs& a, const RngKey& rk, int row, int i) {
+  if (a.exp_noise) return __ldg(a.exp_noise + (int64_t)row * a.T + i);
+  const uint32_t x = philox_draw(rk.seed, rk.offset, (uint32_t)row, (uint32_t)i);
+  return -logf(((float)(x >> 8) + 0.5f) * 5.9604644775390625e-8f);  // U in (0, 1): 24 bits + 1/2, never 0 or 1
+}
+// n-th random.randint(0, T-1) draw: the caller's pool (flags an overflow), or the built-in generator
+__device__ __forceinline__ int reseed_at(const SolverArgs& a, const RngKey& rk, int n, bool* overflow) {
+  if (a.rng && !a.reseed_pool) return (int)(((unsigned long long)philox_draw(rk.seed, rk.offset, kRngReseed, (uint32_t)n) * (unsigned)a.T) >> 32);
+  if (n < a.n_reseed_pool) return (int)a.reseed_pool[n];
+  *overflow = true;
+  return 0;
 }
 
 constexpr int kTimelineMax = 440;
@@ -138,8 +180,9 @@ __device__ void kmeanspp_block(const SolverArgs& a, float* s_near, const double*
   for (int i = threadIdx.x; i < T; i += blockDim.x) s_near[i] = __int_as_float(0x7f800000);
   __syncthreads();
   int noise_row = 0, degenerate = 0, used = *used_io;
-  // T <= 4 * NT (one frame batch per thread): the Exp(1) row of the NEXT sampling round is fetched together with the Gram row
-  // of the update pass, one L2 round trip per round instead of two dependent ones
+  const RngKey rk = load_rng(a);
+  // T <= 4 * NT (one frame batch per thread): the Exp(1) row of the NEXT sampling round is fetched (or generated) together with
+  // the Gram row of the update pass, one L2 round trip per round instead of two dependent ones
   const bool prefetch_noise = T <= 4 * NT;
   float nzp[4] = {1.f, 1.f, 1.f, 1.f};
   bool nzp_valid = false;
@@ -148,8 +191,10 @@ __device__ void kmeanspp_block(const SolverArgs& a, float* s_near, const double*
     int c;
     if (m < a.n_init_given) {
       c = (int)a.init_indices[m];
+    } else if (m == 0) {  // :41 the first centre, from the built-in generator (n_init_given == 0)
+      c = (int)(((unsigned long long)philox_draw(rk.seed, rk.offset, kRngFirst, 0u) * (unsigned)T) >> 32);
+      if (threadIdx.x == 0) a.init_indices[0] = c;
     } else {
-      const float* noise = a.exp_noise + (int64_t)noise_row * T;
       // :53-54 sum of nearest^2: per-warp partials were left in ws[wsb] by the update pass of the previous round
       const float* ws = sc->ws[wsb];
       float sum = ws[0];
@@ -157,11 +202,12 @@ __device__ void kmeanspp_block(const SolverArgs& a, float* s_near, const double*
       for (int w = 1; w < NW; ++w) sum += ws[w];
       if (sum == 0.f) {                           // :55-57
         ++degenerate;
-        c = 0;
-        if (used < a.n_reseed_pool) c = (int)a.reseed_pool[used];
-        else if (threadIdx.x == 0) a.status->reseed_overflow = 1;
+        bool ovf = false;
+        c = reseed_at(a, rk, used, &ovf);
+        if (ovf && threadIdx.x == 0) a.status->reseed_overflow = 1;
         ++used;
       } else {
+        const int this_row = noise_row;
         ++noise_row;
         // ---- approximate scores: this thread's best / second best ----
         float best = 0.f, second = 0.f;
@@ -172,7 +218,7 @@ __device__ void kmeanspp_block(const SolverArgs& a, float* s_near, const double*
           for (int u = 0; u < 4; ++u) {
             const int ii = i0 + u * NT;
             nd[u] = ii < T ? s_near[ii] : 0.f;
-            nz[u] = nzp_valid ? nzp[u] : (ii < T ? __ldg(noise + ii) : 1.f);
+            nz[u] = nzp_valid ? nzp[u] : (ii < T ? noise_at(a, rk, this_row, ii) : 1.f);
           }
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
@@ -220,7 +266,7 @@ __device__ void kmeanspp_block(const SolverArgs& a, float* s_near, const double*
               const int ii = i0 + u * NT;
               if (ii < T) {
                 const float ndv = s_near[ii];
-                const float nzv = nzp_valid ? nzp[u] : __ldg(noise + ii);
+                const float nzv = nzp_valid ? nzp[u] : noise_at(a, rk, this_row, ii);
                 const float n2 = __fmul_rn(ndv, ndv);
                 // a zero numerator would send the warp down the IEEE division's slow path: substituted, result selected
                 const float p = __fdiv_rn(n2 == 0.f ? 1.f : n2, sum);  // :59
@@ -251,12 +297,11 @@ __device__ void kmeanspp_block(const SolverArgs& a, float* s_near, const double*
       const double gcc = diag[c];
       const double* gc = G + (int64_t)c * a.ldg;
       float part = 0.f;
-      if (prefetch_noise && m + 1 >= a.n_init_given) {
-        const float* nn = a.exp_noise + (int64_t)noise_row * T;  // row of the next sampling round (rows are consumed in order)
+      if (prefetch_noise && m + 1 >= a.n_init_given) {  // row of the next sampling round (rows are consumed in order)
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
           const int ii = threadIdx.x + u * NT;
-          nzp[u] = ii < T ? __ldg(nn + ii) : 1.f;
+          nzp[u] = ii < T ? noise_at(a, rk, noise_row, ii) : 1.f;
         }
         nzp_valid = true;
       }
@@ -312,6 +357,7 @@ __device__ void rebuild_members_smem(const SolverArgs& a, const MemberSmem& m, i
   const int T = a.T, k = a.k;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int nw = a.multiwarp_fill ? kSolverWarps : 1;
+  const RngKey rk = load_rng(a);
   // (1) the changed flags were set by the caller while it loaded the new assignments (a frame that moved flags both its old
   //     and its new cluster; the first iteration flags everything: the initial CSR lists only the k seed frames); zero the counters
   (void)force_all;
@@ -365,9 +411,9 @@ __device__ void rebuild_members_smem(const SolverArgs& a, const MemberSmem& m, i
       const int c = m.cursor[j];
       m.offs[j] = run;
       if (c == 0) {
-        int r = 0;
-        if (u < a.n_reseed_pool) r = (int)a.reseed_pool[u];
-        else a.status->reseed_overflow = 1;
+        bool ovf = false;
+        const int r = reseed_at(a, rk, u, &ovf);
+        if (ovf) a.status->reseed_overflow = 1;
         ++u;
         m.memb[run] = r;
         m.changed[j] = 1;  // the centre jumps to a freshly drawn frame
@@ -634,13 +680,18 @@ __global__ void __launch_bounds__(kGridInitThreads) kmeanspp_grid_kernel(SolverA
   }
   unsigned bar = 0;
   int noise_row = 0, degenerate = 0, used = 0;
+  const RngKey rk = load_rng(a);
   int c = 0;
+  if (a.n_init_given == 0) {  // :41 the first centre, from the built-in generator
+    c = (int)(((unsigned long long)philox_draw(rk.seed, rk.offset, kRngFirst, 0u) * (unsigned)T) >> 32);
+    if (blockIdx.x == 0 && threadIdx.x == 0) a.init_indices[0] = c;
+  }
   for (int m = 0; m < k; ++m) {
     if (m < a.n_init_given) c = (int)a.init_indices[m];  // else: c was chosen at the end of the previous iteration
     if (m + 1 >= k) break;
     // ---- update the nearest distances with centre c; per-CTA partial of sum nearest^2 (:45-53) ----
     const bool sample_next = m + 1 >= a.n_init_given;
-    const float* noise = a.exp_noise + (int64_t)noise_row * T;  // the row the next round consumes if it samples
+    // (noise row `noise_row` = the one the next round consumes if it samples)
     const double gcc = __ldg(a.G + (int64_t)c * a.ldg + c);
     const double* gc = a.G + (int64_t)c * a.ldg;
     double g[kGridInitU];
@@ -648,7 +699,7 @@ __global__ void __launch_bounds__(kGridInitThreads) kmeanspp_grid_kernel(SolverA
 #pragma unroll
     for (int u = 0; u < kGridInitU; ++u) {
       g[u] = fi[u] >= 0 ? __ldg(gc + fi[u]) : 0.0;
-      nz[u] = (sample_next && fi[u] >= 0) ? __ldg(noise + fi[u]) : 1.f;
+      nz[u] = (sample_next && fi[u] >= 0) ? noise_at(a, rk, noise_row, fi[u]) : 1.f;
     }
     float part = 0.f, n2[kGridInitU], uq[kGridInitU], umax = 0.f;
 #pragma unroll
@@ -751,9 +802,9 @@ __global__ void __launch_bounds__(kGridInitThreads) kmeanspp_grid_kernel(SolverA
     const float sum = s_sum;
     if (sum == 0.f) {  // :55-57 every frame coincides with a centre: host-drawn index, no noise row consumed
       ++degenerate;
-      c = 0;
-      if (used < a.n_reseed_pool) c = (int)a.reseed_pool[used];
-      else if (blockIdx.x == 0 && threadIdx.x == 0) st->reseed_overflow = 1;
+      bool ovf = false;
+      c = reseed_at(a, rk, used, &ovf);
+      if (ovf && blockIdx.x == 0 && threadIdx.x == 0) st->reseed_overflow = 1;
       ++used;
     } else {
       ++noise_row;
@@ -869,6 +920,7 @@ __device__ void solver_outputs(const SolverArgs& a, const int* s_offs, const int
       }
     }
     if (threadIdx.x == 0) {
+      if (a.rng) const_cast<unsigned long long*>(a.rng)[1] += 1;  // every CTA loaded the key long before (grid barriers in between)
       st->iterations = it;
       st->converged = converged ? 1 : 0;
       st->n_reseed_used = used;
@@ -1307,8 +1359,9 @@ int csb_kmeans_solve(const double* G, const void* timestamps, const csb_kmeans_p
               (long long)p->T, (long long)p->k);
   CSB_REQUIRE(p->T < (1ll << 30) && p->k <= 4096, "kmeans_solve: T or k too large (k <= 4096)");
   CSB_REQUIRE(p->ts_dtype == CSB_F32 || p->ts_dtype == CSB_F64, "kmeans_solve: timestamps must be f32 or f64");
-  CSB_REQUIRE(p->n_init_given >= 1 && p->n_init_given <= p->k, "kmeans_solve: n_init_given must be in [1,k]");
-  CSB_REQUIRE(p->n_init_given == p->k || exp_noise, "kmeans_solve: exp_noise required when centres are sampled");
+  CSB_REQUIRE(p->n_init_given >= (p->rng_state ? 0 : 1) && p->n_init_given <= p->k,
+              "kmeans_solve: n_init_given must be in [1,k] ([0,k] with the built-in generator)");
+  CSB_REQUIRE(p->n_init_given == p->k || exp_noise || p->rng_state, "kmeans_solve: exp_noise or rng_state required when centres are sampled");
   CSB_REQUIRE(p->n_reseed_pool == 0 || reseed_pool, "kmeans_solve: reseed_pool is null");
   CSB_REQUIRE(p->max_iteration >= 0, "kmeans_solve: max_iteration < 0");
   CSB_REQUIRE(p->ldg == 0 || p->ldg >= p->T, "kmeans_solve: ldg < T");
@@ -1328,6 +1381,7 @@ int csb_kmeans_solve(const double* G, const void* timestamps, const csb_kmeans_p
   a.event_order = event_order; a.event_offsets = event_offsets;
   a.diag_in_smem = sp.diag_in_smem; a.multiwarp_fill = sp.multiwarp_fill;
   a.init_exact = getenv("CSB_INIT_EXACT") ? 1 : 0;
+  a.rng = reinterpret_cast<const unsigned long long*>(p->rng_state);
   char* w = reinterpret_cast<char*>(workspace);
   a.diag = reinterpret_cast<double*>(w); w += align_up(sizeof(double) * T, 256);
   for (int b = 0; b < 2; ++b) { a.S[b] = reinterpret_cast<double*>(w); w += align_up(sizeof(double) * T * k, 256); }

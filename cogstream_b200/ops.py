@@ -152,8 +152,11 @@ class KMeansBuffers:
 
 def kmeans_solve(G: torch.Tensor, timestamps: torch.Tensor, buf: KMeansBuffers, *, n_init_given: int,
                  exp_noise: Optional[torch.Tensor], reseed_pool: Optional[torch.Tensor], alpha: float = 2.0,
-                 max_iteration: int = 30, tol: float = 1e-4, frames_per_warp: int = 0) -> None:
-    """k-means++ + Lloyd on the Gram matrix.  ``buf.init_indices[:n_init_given]`` must be filled."""
+                 max_iteration: int = 30, tol: float = 1e-4, frames_per_warp: int = 0,
+                 rng_state: Optional[torch.Tensor] = None) -> None:
+    """k-means++ + Lloyd on the Gram matrix.  ``buf.init_indices[:n_init_given]`` must be filled.
+    ``rng_state`` (device int64[2] = {seed, offset}): the solver draws the Exp(1) noise, the re-seed indices and (with
+    ``n_init_given == 0``) the first centre itself; ``exp_noise`` / ``reseed_pool`` may then be None."""
     _, ldg = _gram_view(G)
     _need(timestamps, "timestamps", None, 1)
     if timestamps.dtype not in _TS_DTYPE:
@@ -169,8 +172,12 @@ def kmeans_solve(G: torch.Tensor, timestamps: torch.Tensor, buf: KMeansBuffers, 
     if reseed_pool is not None:
         _need(reseed_pool, "reseed_pool", torch.int64, 1)
         n_pool = reseed_pool.numel()
+    if rng_state is not None:
+        _need(rng_state, "rng_state", torch.int64, 1)
+        if rng_state.numel() != 2:
+            raise ValueError("rng_state must be an int64[2] tensor {seed, offset}")
     p = KMeansParams(T, k, _TS_DTYPE[timestamps.dtype], int(max_iteration), float(alpha), float(tol), int(n_init_given), n_pool, ldg,
-                     int(frames_per_warp))
+                     _ptr(rng_state), int(frames_per_warp))
     with _on_device(G):
         check(_lib.load().csb_kmeans_solve(
             G.data_ptr(), timestamps.data_ptr(), C.byref(p), buf.init_indices.data_ptr(), _ptr(exp_noise), _ptr(reseed_pool),

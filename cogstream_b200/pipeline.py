@@ -57,7 +57,13 @@ class StreamConfig:
     # `early_pixel_ctas` CTAs the 508 MB pass (160 us on 64 SMs) hides completely under the ~190 us latency-bound solver without
     # slowing it (solver + pixel back to back 321 us, overlapped 207 us); an uncapped grid stretches the solver by ~15 us.
     early_pixel_ctas: int = int(os.environ.get("CSB_EARLY_PIX_CTAS", "64"))
-    parallel_draws: bool = os.environ.get("CSB_PAR_DRAWS", "1") != "0"  # RNG draws on the side stream, next to the Gram kernel
+    # randomness of the clustering (first centre, Exp(1) sampling noise, re-seed indices): True = the solver's built-in Philox
+    # generator (csb_kmeans_params.rng_state: nothing is launched in front of the solver, the re-seed supply cannot run out);
+    # False = torch's CUDA generator (3 small kernels per stream).  Injected init_indices / exp_noise / reseed_pool always win.
+    device_rng: bool = os.environ.get("CSB_DEVICE_RNG", "1") != "0"
+    # with device_rng=False: run torch's draws on the side stream next to the Gram kernel (-28 us for a stream that runs alone,
+    # -5 % throughput with six streams in flight: more graph branches to schedule)
+    parallel_draws: bool = os.environ.get("CSB_PAR_DRAWS", "0") != "0"
     # sequential frame passes per warp in the solver's assignment pass (csb_kmeans_params.frames_per_warp); 0 = the library's
     # choice (k <= 64: frames side by side on sub-warp groups, one pass; else two passes).  More passes = fewer co-resident CTAs
     solver_frames_per_warp: int = 0
@@ -98,7 +104,10 @@ class StreamCompressor:
             self.G = torch.empty(T, T, dtype=torch.float64, device=dev)
             self.gram_ws = torch.empty(ops.gram_workspace_bytes(T, self.K), dtype=torch.uint8, device=dev)
             self.km = ops.KMeansBuffers(T, k, ts_dtype, dev)
-            self.noise = torch.empty(max(k - 1, 1), T, dtype=torch.float32, device=dev)
+            self.noise = torch.empty(max(k - 1, 1), T, dtype=torch.float32, device=dev) if not self.cfg.device_rng else None
+            # {seed, offset} of the solver's built-in generator, seeded from torch's CUDA generator (torch.manual_seed reproduces it)
+            self.rng_state = torch.randint(0, 2 ** 62, (2,), dtype=torch.int64, device=dev)
+            self.rng_state[1] = 0
             n_pool = self.cfg.reseed_pool if self.cfg.reseed_pool is not None else k * (self.cfg.max_iteration + 1)
             self.pool = torch.zeros(max(1, n_pool), dtype=torch.int64, device=dev)
             self.centroids = torch.empty(k, self.K, dtype=torch.float32, device=dev) if self.cfg.compute_centroids else None
@@ -178,34 +187,39 @@ class StreamCompressor:
         fork = pixel_values is not None
 
         def draws():
-            nonlocal_out = {}
+            """-> dict(n_given, noise, pool, rng).  Default: the solver's built-in generator (no launch at all); injected values and
+            ``device_rng=False`` go through the caller's / torch's generators as before."""
+            out = dict(noise=None, pool=reseed_pool, rng=None)
+            use_rng = self.cfg.device_rng and exp_noise is None
+            if use_rng:
+                out["rng"] = self.rng_state
+            elif reseed_pool is None:
+                out["pool"] = self.pool
+                self.pool.random_(0, T)
             if init_indices is not None:
                 self.km.init_indices.copy_(init_indices, non_blocking=True)
-                nonlocal_out["n_given"], nonlocal_out["noise"] = k, None
+                out["n_given"] = k
+                return out
+            if use_rng and (first_index is None or first_index == "device"):
+                out["n_given"] = 0  # the first centre comes from the built-in generator too (kmeans_with_time.py:41)
+                return out
+            if first_index == "device":  # drawn by the CUDA generator: no host value baked into a captured graph
+                torch.randint(0, T, (1,), device=self.device, out=self.km.init_indices[:1])
             else:
-                if first_index == "device":  # drawn by the CUDA generator: no host value baked into a captured graph
-                    torch.randint(0, T, (1,), device=self.device, out=self.km.init_indices[:1])
-                else:
-                    first = random.randint(0, T - 1) if first_index is None else first_index  # kmeans_with_time.py:41
-                    self.km.init_indices[:1].fill_(first)
-                nonlocal_out["n_given"] = 1
-                if exp_noise is not None:
-                    nonlocal_out["noise"] = exp_noise
-                else:
-                    nz = self.noise[: k - 1]
-                    if k > 1:
-                        nz.exponential_(1)  # one batched draw (the drop-in function draws per round like ATen does)
-                    nonlocal_out["noise"] = nz
-            pl = reseed_pool
-            if pl is None:
-                pl = self.pool
-                pl.random_(0, T)
-            nonlocal_out["pool"] = pl
-            return nonlocal_out
+                first = random.randint(0, T - 1) if first_index is None else first_index  # kmeans_with_time.py:41
+                self.km.init_indices[:1].fill_(first)
+            out["n_given"] = 1
+            if exp_noise is not None:
+                out["noise"] = exp_noise
+            elif not use_rng and k > 1:
+                nz = self.noise[: k - 1]
+                nz.exponential_(1)  # one batched draw (the drop-in function draws per round like ATen does)
+                out["noise"] = nz
+            return out
 
         G = self.G if gram is None else gram
-        if self.cfg.parallel_draws:
-            # the RNG draws (three tiny torch kernels) do not depend on the Gram matrix: they run on the side stream next to it
+        if self.cfg.parallel_draws and not self.cfg.device_rng:
+            # torch-generator draws (three tiny kernels) do not depend on the Gram matrix: they run on the side stream next to it
             with self._branch():
                 d_ = draws()
             if gram is None:
@@ -219,11 +233,10 @@ class StreamCompressor:
             if fork:
                 self._ev_fork.record(torch.cuda.current_stream(self.device))
             d_ = draws()
-        n_given, noise, pool = d_["n_given"], d_["noise"], d_["pool"]
         self._G_used = G
-        ops.kmeans_solve(G, timestamps, self.km, n_init_given=n_given, exp_noise=noise if k > 1 else None,
-                         reseed_pool=pool, alpha=self.cfg.alpha, max_iteration=self.cfg.max_iteration, tol=self.cfg.tol,
-                         frames_per_warp=self.cfg.solver_frames_per_warp)
+        ops.kmeans_solve(G, timestamps, self.km, n_init_given=d_["n_given"], exp_noise=d_["noise"] if k > 1 else None,
+                         reseed_pool=d_["pool"], alpha=self.cfg.alpha, max_iteration=self.cfg.max_iteration, tol=self.cfg.tol,
+                         frames_per_warp=self.cfg.solver_frames_per_warp, rng_state=d_["rng"])
         if fork:
             # enqueued AFTER the cooperative solver so its CTAs become resident first; the HBM-bound difference kernel then
             # fills the rest of the machine while the (latency-bound) solver iterates

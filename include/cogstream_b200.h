@@ -104,6 +104,12 @@ typedef struct csb_kmeans_params {
                              always drawn by the host, :41); the remaining k - n are sampled k-means++ */
   int64_t n_reseed_pool;  /* entries available in reseed_pool (host random.randint(0, T-1) draws) */
   int64_t ldg;            /* leading dimension of G (elements); 0 means T */
+  void* rng_state;        /* device uint64[2] {seed, offset} or NULL.  With it the solver draws its own randomness (Philox4x32-10):
+                             the Exp(1) noise of every sampling round (exp_noise may then be NULL), the random.randint draws for
+                             degenerate rounds and empty clusters (reseed_pool NULL: they cannot run out), and -- with
+                             n_init_given == 0 -- the first centre.  offset is advanced by one per solve (CUDA-graph replays draw
+                             fresh numbers).  Same distributions as the reference's generators, not the same streams: the
+                             drop-in function keeps torch's / random's own streams through exp_noise + reseed_pool. */
   int64_t frames_per_warp; /* assignment pass: sequential frame passes of a warp per Lloyd iteration.  A pass covers 32 / L frames
                              side by side (L lanes per frame: 8 / 16 / 32 for k <= 32 / 64 / more), and the cooperative launch
                              uses T / (8 * (32 / L) * frames_per_warp) CTAs.  0 = default (1 pass when L < 32, else 2): 38 CTAs
@@ -133,7 +139,7 @@ CSB_API size_t csb_kmeans_workspace_bytes(int64_t T, int64_t k);
  * reseed_pool entry instead, so both host RNG streams are consumed exactly like the reference does.
  *   G             [T,T] fp64 (csb_gram)
  *   timestamps    [T]   ts_dtype
- *   init_indices  [k]   int64; first n_init_given entries are inputs, the rest are outputs
+ *   init_indices  [k]   int64; first n_init_given entries are inputs (0 allowed with params->rng_state), the rest are outputs
  *   exp_noise     [k-1,T] fp32 or NULL when n_init_given == k
  *   reseed_pool   [n_reseed_pool] int64 frame indices for empty clusters, consumed in order
  *   assignments   [T]   int64  out (:104, lowest index wins ties)

@@ -17,7 +17,6 @@ torch.manual_seed(0)
 sc.phase1(d.features, d.timestamps, first_index=5)
 sc.phase2(d.features, ev, q, d.pixel_values, d.input_ids, d.attention_mask)
 torch.cuda.synchronize()
-noise = sc.noise[: k - 1]
 
 def timed(name, fn, reps=3):
     fn(); torch.cuda.synchronize()
@@ -29,8 +28,7 @@ def timed(name, fn, reps=3):
 
 timed("gram", lambda: ops.gram(x2, out=sc.G, workspace=sc.gram_ws))
 def solve(max_it):
-    sc.km.init_indices[:1].fill_(5); sc.pool.random_(0, T)
-    ops.kmeans_solve(sc.G, d.timestamps, sc.km, n_init_given=1, exp_noise=noise, reseed_pool=sc.pool, max_iteration=max_it)
+    ops.kmeans_solve(sc.G, d.timestamps, sc.km, n_init_given=0, exp_noise=None, reseed_pool=None, max_iteration=max_it, rng_state=sc.rng_state)
 timed("kmeans (init + 0 iterations)", lambda: solve(0))
 timed("kmeans (init + 1 iteration)", lambda: solve(1))
 timed("kmeans (full)", lambda: solve(30))

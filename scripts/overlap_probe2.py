@@ -15,13 +15,11 @@ sc = StreamCompressor(T, P, D, st.pixel_values.numel() // (T * P), st.input_ids.
 torch.manual_seed(1); random.seed(1)
 x2 = d.features.view(T, sc.K)
 ops.gram(x2, out=sc.G, workspace=sc.gram_ws)
-noise = sc.noise[: k - 1]; noise.exponential_(1); sc.pool.random_(0, T)
 main = torch.cuda.current_stream()
 side = torch.cuda.Stream()
 
 def solve():
-    sc.km.init_indices[:1].fill_(5)
-    ops.kmeans_solve(sc.G, d.timestamps, sc.km, n_init_given=1, exp_noise=noise, reseed_pool=sc.pool)
+    ops.kmeans_solve(sc.G, d.timestamps, sc.km, n_init_given=0, exp_noise=None, reseed_pool=None, rng_state=sc.rng_state)
 
 def run(overlap, reps=10):
     ts = []

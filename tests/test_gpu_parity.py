@@ -1369,3 +1369,86 @@ def test_encoder_tail_full_size(dev):
         _ulp_close(got[f0 * 180: (f0 + 1) * 180], want)
     with pytest.raises(RuntimeError, match="invalid for input of size"):
         encoder_tail(ln, hidden[: 25 * 30], torch.tensor([[1, 25, 30]], device=dev), merge)
+
+
+# ---- round 2: the solver's built-in generator (csb_kmeans_params.rng_state) ---------------------------------------------------
+def _philox_host(seed, offset, stream, index):
+    """numpy replica of philox_draw (csrc/kmeans_solver.cu): Philox4x32-10, counter (index, stream, offset), key = seed."""
+    import numpy as np
+    index = np.asarray(index, dtype=np.uint64)
+    c0 = index & np.uint64(0xFFFFFFFF)
+    c1 = np.full_like(c0, np.uint64(stream))
+    c2 = np.full_like(c0, np.uint64(offset & 0xFFFFFFFF))
+    c3 = np.full_like(c0, np.uint64(offset >> 32))
+    k0, k1 = np.uint64(seed & 0xFFFFFFFF), np.uint64(seed >> 32)
+    M0, M1, m32 = np.uint64(0xD2511F53), np.uint64(0xCD9E8D57), np.uint64(0xFFFFFFFF)
+    for _ in range(10):
+        p0, p1 = M0 * c0, M1 * c2
+        hi0, lo0, hi1, lo1 = p0 >> np.uint64(32), p0 & m32, p1 >> np.uint64(32), p1 & m32
+        c0, c1, c2, c3 = hi1 ^ c1 ^ k0, lo1, hi0 ^ c3 ^ k1, lo0
+        k0, k1 = (k0 + np.uint64(0x9E3779B9)) & m32, (k1 + np.uint64(0xBB67AE85)) & m32
+    return c0.astype(np.uint32)
+
+
+def test_builtin_generator_matches_host_replay(dev):
+    """kmeans_solve with rng_state: the centres / assignments are those of the CPU oracle fed with the SAME draws (Philox replayed on
+    the host: first centre, Exp(1) noise rows, re-seed indices); the offset advances by one per solve; same state -> same result."""
+    import numpy as np
+    T, P, D, k = 300, 4, 64, 20
+    feats, _ = synthetic.make_features(T, P, D, 17)
+    f3 = feats.view(T, P, D)
+    ts = torch.arange(T, dtype=torch.float64)
+    x2 = f3.view(T, -1).to(dev)
+    G = ops.gram(x2)
+    seed, off = 0x1234567890ABCDEF & (2 ** 62 - 1), 5
+    runs = []
+    for rep in range(2):
+        state = torch.tensor([seed, off], dtype=torch.int64, device=dev)
+        buf = ops.KMeansBuffers(T, k, torch.float64, dev)
+        ops.kmeans_solve(G, ts.to(dev), buf, n_init_given=0, exp_noise=None, reseed_pool=None, rng_state=state)
+        st = ops.decode_status(buf.status)
+        runs.append((buf.init_indices.cpu().tolist(), buf.assignments.cpu(), st["iterations"], st["n_reseed_used"]))
+        assert state.tolist() == [seed, off + 1]
+    assert runs[0][0] == runs[1][0] and torch.equal(runs[0][1], runs[1][1])
+    first = int((int(_philox_host(seed, off, 0xFFFFFFFF, [0])[0]) * T) >> 32)
+    u = (_philox_host(seed, off, np.arange(k - 1)[:, None].repeat(T, 1), np.arange(T)[None, :].repeat(k - 1, 0)) >> np.uint32(8)).astype(np.float32)
+    noise = torch.from_numpy(-np.log((u + np.float32(0.5)) * np.float32(2.0 ** -24)).astype(np.float32))
+    reseeds = [int((int(v) * T) >> 32) for v in _philox_host(seed, off, 0xFFFFFFFE, np.arange(64))]
+    info = orc.KMeansInfo()
+    orig = random.randint
+    try:
+        random.randint = lambda a, b: first
+        _, _, as_o = orc.kmeans_with_time_min_max(f3, ts, k, exp_noise=noise, reseed_indices=reseeds, info=info)
+    finally:
+        random.randint = orig
+    assert runs[0][0] == info.init_indices
+    assert torch.equal(runs[0][1], as_o) and runs[0][2] == info.iterations and runs[0][3] == len(info.reseed_indices)
+
+
+def test_builtin_generator_samples_proportional_to_squared_distance(dev):
+    """k-means++ with the built-in generator on 4 frames at distances 0, 1, 2, 3 from the given first centre: the second centre is
+    frame i with probability d_i^2 / 14 (kmeans_with_time.py:53-60), checked over 4000 offsets."""
+    x = torch.zeros(4, 8)
+    x[:, 0] = torch.tensor([0.0, 1.0, 2.0, 3.0])
+    G = ops.gram(x.to(torch.bfloat16).to(dev))
+    ts = torch.arange(4, dtype=torch.float64, device=dev)
+    counts = [0, 0, 0, 0]
+    state = torch.tensor([987654321, 0], dtype=torch.int64, device=dev)
+    buf = ops.KMeansBuffers(4, 2, torch.float64, dev)
+    picks = torch.empty(4000, dtype=torch.int64, device=dev)
+    for n in range(4000):
+        buf.init_indices[:1].fill_(0)
+        ops.kmeans_solve(G, ts, buf, n_init_given=1, exp_noise=None, reseed_pool=None, max_iteration=0, rng_state=state)
+        picks[n] = buf.init_indices[1]
+    for v in picks.tolist():
+        counts[v] += 1
+    assert counts[0] == 0
+    for i, want in ((1, 1 / 14), (2, 4 / 14), (3, 9 / 14)):
+        assert abs(counts[i] / 4000 - want) < 0.03, counts
+    # the first centre and the re-seeds are uniform over the frames
+    firsts = torch.empty(2000, dtype=torch.int64, device=dev)
+    for n in range(2000):
+        ops.kmeans_solve(G, ts, buf, n_init_given=0, exp_noise=None, reseed_pool=None, max_iteration=0, rng_state=state)
+        firsts[n] = buf.init_indices[0]
+    hist = torch.bincount(firsts.cpu(), minlength=4).tolist()
+    assert min(hist) > 400 and max(hist) < 600, hist
