@@ -14,46 +14,47 @@
 
 namespace csb {
 
-// LayerNorm of one row held in registers (raw = the lane's 16-byte slices): fp32 statistics over the warp, output rounded to bf16
+// fp32 mean and 1/std of one row held in registers (raw = the lane's 16-byte slices; columns beyond C were loaded as zeros)
 template <int NV>
-__device__ __forceinline__ void ln_row(const uint4 (&raw)[NV], int Cv, int lane, const float* __restrict__ s_g, const float* __restrict__ s_b,
-                                       float eps, float inv_c, float (&y)[NV][8]) {
+__device__ __forceinline__ void row_stats(const uint4 (&raw)[NV], int Cv, int lane, float eps, float inv_c, float& mean, float& rstd) {
   float s = 0.f;
 #pragma unroll
   for (int u = 0; u < NV; ++u) {
-    unpack8(raw[u], y[u]);
+    float f[8];
+    unpack8(raw[u], f);
 #pragma unroll
-    for (int e = 0; e < 8; ++e) s += y[u][e];  // columns beyond C were loaded as zeros
+    for (int e = 0; e < 8; ++e) s += f[e];
   }
-  const float mean = warp_sum(s) * inv_c;
+  mean = warp_sum(s) * inv_c;
   float v = 0.f;
 #pragma unroll
   for (int u = 0; u < NV; ++u) {
-    const bool ok = lane + 32 * u < Cv;
-#pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      const float d = y[u][e] - mean;
-      v = ok ? fmaf(d, d, v) : v;
-    }
-  }
-  const float rstd = rsqrtf(warp_sum(v) * inv_c + eps);
-#pragma unroll
-  for (int u = 0; u < NV; ++u) {
-    const int c = (lane + 32 * u) * 8;
     if (lane + 32 * u < Cv) {
-      const float4 g0 = *reinterpret_cast<const float4*>(s_g + c), g1 = *reinterpret_cast<const float4*>(s_g + c + 4);
-      const float4 b0 = *reinterpret_cast<const float4*>(s_b + c), b1 = *reinterpret_cast<const float4*>(s_b + c + 4);
-      const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w}, bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+      float f[8];
+      unpack8(raw[u], f);
 #pragma unroll
-      for (int e = 0; e < 8; ++e) y[u][e] = round_bf16(fmaf(gg[e], rstd * (y[u][e] - mean), bb[e]));  // LayerNorm output is a bf16 tensor
+      for (int e = 0; e < 8; ++e) {
+        const float d = f[e] - mean;
+        v = fmaf(d, d, v);
+      }
     }
   }
+  rstd = rsqrtf(warp_sum(v) * inv_c + eps);
+}
+
+// LayerNorm output (a bf16 tensor in the reference) of 8 channels of one row
+__device__ __forceinline__ void ln8(const uint4& raw, float mean, float rstd, const float (&g)[8], const float (&b)[8], float (&y)[8]) {
+  float f[8];
+  unpack8(raw, f);
+#pragma unroll
+  for (int e = 0; e < 8; ++e) y[e] = round_bf16(fmaf(g[e], rstd * (f[e] - mean), b[e]));
 }
 
 // A warp per output token.  All rows of the block that carry weight (4 for even m, 1 for odd m) are requested before any is
-// processed: 4 rows x NV x 16 B per lane in flight (10 KB per warp at C = 1152), which is what keeps HBM busy at 8 warps per SM.
+// processed (4 rows x NV x 16 B per lane in flight, 10 KB per warp at C = 1152); the statistics are taken from the raw registers
+// and the normalise + blend + store step walks the columns 8 at a time, so the live state stays below 170 registers: 12 warps / SM.
 template <int NV>
-__global__ void __launch_bounds__(256, 1) ln_merge_kernel(const uint4* __restrict__ x, int64_t n_out, int Cv, int m, const uint4* __restrict__ gamma,
+__global__ void __launch_bounds__(192, 2) ln_merge_kernel(const uint4* __restrict__ x, int64_t n_out, int Cv, int m, const uint4* __restrict__ gamma,
                                                           const uint4* __restrict__ beta, float eps, uint4* __restrict__ out) {
   extern __shared__ float s_gb[];  // gamma [C], beta [C] as fp32
   float* s_g = s_gb;
@@ -85,39 +86,41 @@ __global__ void __launch_bounds__(256, 1) ln_merge_kernel(const uint4* __restric
         const int c = lane + 32 * u;
         raw[r][u] = (c < Cv && (r == 0 || blend)) ? ldg_stream(rows[r] + c) : make_uint4(0, 0, 0, 0);
       }
-    float acc[NV][8];
-    ln_row<NV>(raw[0], Cv, lane, s_g, s_b, eps, inv_c, acc);
+    float mean[4], rstd[4];
+    row_stats<NV>(raw[0], Cv, lane, eps, inv_c, mean[0], rstd[0]);
     if (blend) {
-      // h0 * (w0 * v00 + w1 * v01) + h1 * (w0 * v10 + w1 * v11), all weights 1/2 (exact scalings: one rounding per addition)
-      float r1[NV][8];
-      ln_row<NV>(raw[1], Cv, lane, s_g, s_b, eps, inv_c, r1);
 #pragma unroll
-      for (int u = 0; u < NV; ++u)
-#pragma unroll
-        for (int e = 0; e < 8; ++e) acc[u][e] = __fadd_rn(0.5f * acc[u][e], 0.5f * r1[u][e]);
-      float r2[NV][8];
-      ln_row<NV>(raw[2], Cv, lane, s_g, s_b, eps, inv_c, r2);
-      ln_row<NV>(raw[3], Cv, lane, s_g, s_b, eps, inv_c, r1);
-#pragma unroll
-      for (int u = 0; u < NV; ++u)
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          const float lo = __fadd_rn(0.5f * r2[u][e], 0.5f * r1[u][e]);
-          acc[u][e] = __fadd_rn(0.5f * acc[u][e], 0.5f * lo);
-        }
+      for (int r = 1; r < 4; ++r) row_stats<NV>(raw[r], Cv, lane, eps, inv_c, mean[r], rstd[r]);
     }
     uint4* o = out + t * Cv;
 #pragma unroll
     for (int u = 0; u < NV; ++u) {
       const int c = lane + 32 * u;
-      if (c < Cv) {
-        uint4 w;
-        w.x = float_to_bf16_bits(acc[u][0]) | (float_to_bf16_bits(acc[u][1]) << 16);
-        w.y = float_to_bf16_bits(acc[u][2]) | (float_to_bf16_bits(acc[u][3]) << 16);
-        w.z = float_to_bf16_bits(acc[u][4]) | (float_to_bf16_bits(acc[u][5]) << 16);
-        w.w = float_to_bf16_bits(acc[u][6]) | (float_to_bf16_bits(acc[u][7]) << 16);
-        o[c] = w;
+      if (c >= Cv) continue;
+      const float4 g0 = *reinterpret_cast<const float4*>(s_g + c * 8), g1 = *reinterpret_cast<const float4*>(s_g + c * 8 + 4);
+      const float4 b0 = *reinterpret_cast<const float4*>(s_b + c * 8), b1 = *reinterpret_cast<const float4*>(s_b + c * 8 + 4);
+      const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w}, bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+      float acc[8];
+      ln8(raw[0][u], mean[0], rstd[0], gg, bb, acc);
+      if (blend) {
+        // h0 * (w0 * v00 + w1 * v01) + h1 * (w0 * v10 + w1 * v11), all weights 1/2 (exact scalings: one rounding per addition)
+        float y1[8], y2[8], y3[8];
+        ln8(raw[1][u], mean[1], rstd[1], gg, bb, y1);
+        ln8(raw[2][u], mean[2], rstd[2], gg, bb, y2);
+        ln8(raw[3][u], mean[3], rstd[3], gg, bb, y3);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const float hi = __fadd_rn(0.5f * acc[e], 0.5f * y1[e]);
+          const float lo = __fadd_rn(0.5f * y2[e], 0.5f * y3[e]);
+          acc[e] = __fadd_rn(0.5f * hi, 0.5f * lo);
+        }
       }
+      uint4 w;
+      w.x = float_to_bf16_bits(acc[0]) | (float_to_bf16_bits(acc[1]) << 16);
+      w.y = float_to_bf16_bits(acc[2]) | (float_to_bf16_bits(acc[3]) << 16);
+      w.z = float_to_bf16_bits(acc[4]) | (float_to_bf16_bits(acc[5]) << 16);
+      w.w = float_to_bf16_bits(acc[6]) | (float_to_bf16_bits(acc[7]) << 16);
+      o[c] = w;
     }
   }
 }
@@ -140,12 +143,12 @@ int csb_ln_merge(const void* hidden, int64_t n_rows, int64_t C, int64_t merge, c
               "ln_merge: buffers must be 16-byte aligned");
   const int64_t n_out = n_rows / (merge * merge);
   const int Cv = (int)(C / 8);
-  int64_t blocks = (n_out + 7) / 8;
-  if (blocks > (int64_t)kNumSMs) blocks = kNumSMs;  // persistent, one CTA per SM (255 registers): warps stride over the output tokens
+  int64_t blocks = (n_out + 5) / 6;
+  if (blocks > (int64_t)kNumSMs * 2) blocks = (int64_t)kNumSMs * 2;  // persistent, two CTAs per SM: warps stride over the output tokens
   cudaStream_t s = as_stream(stream);
   const size_t smem = sizeof(float) * 2 * (size_t)C;
 #define CSB_LN_LAUNCH(NVV) \
-  ln_merge_kernel<NVV><<<(unsigned)blocks, 256, smem, s>>>((const uint4*)hidden, n_out, Cv, (int)merge, (const uint4*)gamma, (const uint4*)beta, (float)eps, (uint4*)out)
+  ln_merge_kernel<NVV><<<(unsigned)blocks, 192, smem, s>>>((const uint4*)hidden, n_out, Cv, (int)merge, (const uint4*)gamma, (const uint4*)beta, (float)eps, (uint4*)out)
   if (Cv <= 64) CSB_LN_LAUNCH(2);
   else if (Cv <= 160) CSB_LN_LAUNCH(5);
   else CSB_LN_LAUNCH(8);

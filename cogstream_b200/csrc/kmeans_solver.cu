@@ -49,6 +49,9 @@ struct SolverArgs {
   int multiwarp_fill; // 1: per-warp cluster counters fit in shared memory
   const unsigned long long* rng;  // device {seed, offset} of the built-in generator, or nullptr (noise / pool supplied by the caller)
   int fused_init;     // 1: CTA 0 of the solver runs the k-means++ init itself (no separate kmeanspp launch)
+  float* noise_ws;    // [(k-1), T] or nullptr: rows >= kNoiseInlineRows of the built-in generator's noise, filled by CTAs 1.. of the
+                      // fused launch while CTA 0 already runs the first sampling rounds
+  unsigned* noise_ready;  // arrival counter of those CTAs
   int init_exact;     // validation switch (CSB_INIT_EXACT): every sampling round evaluates the exact IEEE scores
   int32_t* assign32;  // [T] compact copy of the assignments (what every CTA reloads after the barrier)
 };
@@ -93,7 +96,7 @@ __device__ __forceinline__ void grid_sync_backoff(unsigned* counter, unsigned& t
 // The fused pipeline draws its randomness here instead of launching torch's generator kernels in front of the solver: the Exp(1)
 // noise of sampling round r for frame i is -log(U(r, i)), the host random.randint draws of kmeans_with_time.py:41 / :57 / :118
 // are floor(U * T).  Every thread that needs draw (stream, index) computes the same value; the offset advances once per solve.
-__device__ __forceinline__ uint32_t philox_draw(unsigned long long seed, unsigned long long offset, uint32_t stream, uint32_t index) {
+__device__ __forceinline__ uint4 philox_draw4(unsigned long long seed, unsigned long long offset, uint32_t stream, uint32_t index) {
   uint32_t c0 = index, c1 = stream, c2 = (uint32_t)offset, c3 = (uint32_t)(offset >> 32);
   uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
 #pragma unroll
@@ -103,9 +106,17 @@ __device__ __forceinline__ uint32_t philox_draw(unsigned long long seed, unsigne
     c0 = hi1 ^ c1 ^ k0; c1 = lo1; c2 = hi0 ^ c3 ^ k1; c3 = lo0;
     k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
   }
-  return c0;
+  return make_uint4(c0, c1, c2, c3);
+}
+__device__ __forceinline__ uint32_t philox_draw(unsigned long long seed, unsigned long long offset, uint32_t stream, uint32_t index) {
+  return philox_draw4(seed, offset, stream, index).x;
+}
+__device__ __forceinline__ float exp1_from_bits(uint32_t x) {
+  return -logf(((float)(x >> 8) + 0.5f) * 5.9604644775390625e-8f);  // U in (0, 1): 24 bits + 1/2, never 0 or 1
 }
 constexpr uint32_t kRngFirst = 0xFFFFFFFFu, kRngReseed = 0xFFFFFFFEu;  // streams; sampling round r uses stream r
+
+constexpr int kNoiseInlineRows = 2;  // sampling rounds whose noise the init CTA generates itself while the others fill noise_ws
 
 struct RngKey {
   unsigned long long seed, offset;
@@ -119,8 +130,11 @@ __device__ __forceinline__ RngKey load_rng(const SolverArgs& a) {
 // Exp(1) noise of sampling round `row` for frame i: the caller's array, or the built-in generator
 __device__ __forceinline__ float noise_at(const SolverArgs& a, const RngKey& rk, int row, int i) {
   if (a.exp_noise) return __ldg(a.exp_noise + (int64_t)row * a.T + i);
-  const uint32_t x = philox_draw(rk.seed, rk.offset, (uint32_t)row, (uint32_t)i);
-  return -logf(((float)(x >> 8) + 0.5f) * 5.9604644775390625e-8f);  // U in (0, 1): 24 bits + 1/2, never 0 or 1
+  if (a.noise_ws && row >= kNoiseInlineRows) return __ldcg(a.noise_ws + (int64_t)row * a.T + i);  // pre-generated by the idle CTAs
+  // frame i of sampling round `row`: component i & 3 of the call (i >> 2, row)
+  const uint4 x = philox_draw4(rk.seed, rk.offset, (uint32_t)row, (uint32_t)(i >> 2));
+  const uint32_t w = (i & 2) ? ((i & 1) ? x.w : x.z) : ((i & 1) ? x.y : x.x);
+  return exp1_from_bits(w);
 }
 // n-th random.randint(0, T-1) draw: the caller's pool (flags an overflow), or the built-in generator
 __device__ __forceinline__ int reseed_at(const SolverArgs& a, const RngKey& rk, int n, bool* overflow) {
@@ -187,6 +201,7 @@ __device__ void kmeanspp_block(const SolverArgs& a, float* s_near, const double*
   float nzp[4] = {1.f, 1.f, 1.f, 1.f};
   bool nzp_valid = false;
   int wsb = 0;  // ws buffer the next sampling round reads
+  bool ws_ready = false;
   for (int m = 0; m < k; ++m) {
     int c;
     if (m < a.n_init_given) {
@@ -297,6 +312,17 @@ __device__ void kmeanspp_block(const SolverArgs& a, float* s_near, const double*
       const double gcc = diag[c];
       const double* gc = G + (int64_t)c * a.ldg;
       float part = 0.f;
+      if (a.noise_ws && !a.exp_noise && !ws_ready && noise_row >= kNoiseInlineRows && m + 1 >= a.n_init_given) {
+        // first use of a pre-generated row: the other CTAs finished them long ago (2 rounds = 3 us); make it formal
+        if (threadIdx.x == 0) {
+          unsigned v;
+          do {
+            asm volatile("ld.acquire.gpu.u32 %0, [%1];" : "=r"(v) : "l"(a.noise_ready) : "memory");
+          } while (v < gridDim.x - 1);
+        }
+        __syncthreads();
+        ws_ready = true;
+      }
       if (prefetch_noise && m + 1 >= a.n_init_given) {  // row of the next sampling round (rows are consumed in order)
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
@@ -987,6 +1013,23 @@ __global__ void __launch_bounds__(kSolverThreads, WIDE ? 1 : 2) kmeans_solver_ke
         *a.used = used;
       }
       mark(a, 2);
+    } else if (a.noise_ws) {
+      // the idle CTAs pre-generate the Exp(1) noise of sampling rounds >= kNoiseInlineRows (4 frames per Philox call)
+      const RngKey rk = load_rng(a);
+      const int q4 = (T + 3) >> 2;  // calls per row
+      const int64_t total = (int64_t)(k - 1 - kNoiseInlineRows) * q4;
+      for (int64_t e = (int64_t)(blockIdx.x - 1) * blockDim.x + threadIdx.x; e < total; e += (int64_t)(nb - 1) * blockDim.x) {
+        const int row = kNoiseInlineRows + (int)(e / q4), c = (int)(e - (int64_t)(e / q4) * q4);
+        const uint4 x = philox_draw4(rk.seed, rk.offset, (uint32_t)row, (uint32_t)c);
+        float* dst = a.noise_ws + (int64_t)row * T + 4 * c;
+        const float v[4] = {exp1_from_bits(x.x), exp1_from_bits(x.y), exp1_from_bits(x.z), exp1_from_bits(x.w)};
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (4 * c + u < T) __stcg(dst + u, v[u]);
+      }
+      __threadfence();
+      __syncthreads();
+      if (threadIdx.x == 0) atomicAdd(a.noise_ready, 1u);
     }
     grid_sync_backoff(a.barrier, bar, nb);
     used = __ldcg(a.used);
@@ -1343,6 +1386,7 @@ size_t csb_kmeans_workspace_bytes(int64_t T, int64_t k) {
   b += align_up(sizeof(double) * T, 256);              // diag
   b += 2 * align_up(sizeof(double) * T * k, 256);      // S
   b += align_up(sizeof(int32_t) * T, 256);             // compact assignments
+  if (T <= 1024) b += align_up(sizeof(float) * T * k, 256);  // pre-generated noise of the built-in generator (fused init)
   b += 4096;                                           // barrier + used + phase timeline
   return b;
 }
@@ -1386,7 +1430,10 @@ int csb_kmeans_solve(const double* G, const void* timestamps, const csb_kmeans_p
   a.diag = reinterpret_cast<double*>(w); w += align_up(sizeof(double) * T, 256);
   for (int b = 0; b < 2; ++b) { a.S[b] = reinterpret_cast<double*>(w); w += align_up(sizeof(double) * T * k, 256); }
   a.assign32 = reinterpret_cast<int32_t*>(w); w += align_up(sizeof(int32_t) * T, 256);
+  float* noise_ws = nullptr;
+  if (T <= 1024) { noise_ws = reinterpret_cast<float*>(w); w += align_up(sizeof(float) * T * k, 256); }
   a.barrier = reinterpret_cast<unsigned*>(w);
+  a.noise_ready = reinterpret_cast<unsigned*>(w + 192);
   a.used = reinterpret_cast<int32_t*>(w + 128);
   a.tl = reinterpret_cast<unsigned long long*>(w + 256);
   cudaStream_t s = as_stream(stream);
@@ -1466,6 +1513,8 @@ int csb_kmeans_solve(const double* G, const void* timestamps, const csb_kmeans_p
   int64_t nb = (T + (int64_t)fpw * gpw * kSolverWarps - 1) / ((int64_t)fpw * gpw * kSolverWarps);
   if (nb > sms) nb = sms;
   if (nb < 1) nb = 1;
+  // built-in generator + fused init + helpers to spare: CTAs 1.. pre-generate the noise rows while CTA 0 samples
+  a.noise_ws = (a.fused_init && a.rng && !exp_noise && nb > 1 && k - 1 > kNoiseInlineRows && p->n_init_given < k) ? noise_ws : nullptr;
   void* args[] = {&a};
   e = cudaLaunchCooperativeKernel((const void*)kern, dim3((unsigned)nb), dim3(kSolverThreads), args, smem, s);
   if (e != cudaSuccess) { set_error("kmeans_solve: launch: %s", cudaGetErrorString(e)); return CSB_ERR_CUDA; }

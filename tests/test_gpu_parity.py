@@ -802,9 +802,10 @@ def test_cuda_graph_replay(dev, T, P, D):
     sc.capture(d.features, d.timestamps, evd, qd, d.pixel_values, d.input_ids, d.attention_mask)
     outs = []
     for _ in range(2):
-        torch.manual_seed(4242)
+        sc.rng_state[1] = 4242  # the solver's built-in generator: same {seed, offset} -> same draws (it advances by one per solve)
         sc.replay1(); sc.replay2()
         r = sc.results()
+        assert int(sc.rng_state[1]) == 4243
         outs.append((r["assignments"].clone(), r["mask"].clone(), r["features"].clone(), list(r["minor"]), r["status"]))
     assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1]) and torch.equal(outs[0][2], outs[1][2])
     assign, mask, feats, minor, status = outs[1]
@@ -1323,12 +1324,14 @@ def test_pipeline_multi_item_inputs(dev):
 
 
 # ---- round 2: encoder tail ------------------------------------------------------------------------------------
-def _ulp_close(a, b, max_ulp=1, max_frac=2e-3):
-    """bf16 tensors equal up to `max_ulp` in at most `max_frac` of the elements (fp32 statistics summed in another order)."""
+def _ulp_close(a, b, max_frac=5e-3, scale=4.0):
+    """bf16 tensors equal except in at most `max_frac` of the elements, and there by at most one bf16 ulp of the OPERANDS' magnitude
+    (the LayerNorm outputs that are blended are O(`scale`); a blend of values of mixed sign can be much smaller than they are, so an
+    ulp of the result is not the yardstick): fp32 statistics summed in another order flip a rounding now and then."""
     af, bf = a.float().cpu(), b.float().cpu()
-    ulp = bf.abs().clamp_min(1e-30).log2().floor().exp2() * 2.0 ** -7
     diff = (af - bf).abs()
-    assert bool((diff <= max_ulp * ulp * 1.001).all()), float((diff / ulp).max())
+    ulp = torch.maximum(bf.abs(), torch.full_like(bf, scale)).log2().floor().exp2() * 2.0 ** -7
+    assert bool((diff <= ulp * 1.001).all()), float((diff / ulp).max())
     assert float((diff > 0).float().mean()) <= max_frac, float((diff > 0).float().mean())
     assert rel_err(a, b) < REL_TOL
 
@@ -1387,7 +1390,7 @@ def _philox_host(seed, offset, stream, index):
         hi0, lo0, hi1, lo1 = p0 >> np.uint64(32), p0 & m32, p1 >> np.uint64(32), p1 & m32
         c0, c1, c2, c3 = hi1 ^ c1 ^ k0, lo1, hi0 ^ c3 ^ k1, lo0
         k0, k1 = (k0 + np.uint64(0x9E3779B9)) & m32, (k1 + np.uint64(0xBB67AE85)) & m32
-    return c0.astype(np.uint32)
+    return np.stack([c0, c1, c2, c3], axis=-1).astype(np.uint32)  # [..., 4]
 
 
 def test_builtin_generator_matches_host_replay(dev):
@@ -1410,10 +1413,12 @@ def test_builtin_generator_matches_host_replay(dev):
         runs.append((buf.init_indices.cpu().tolist(), buf.assignments.cpu(), st["iterations"], st["n_reseed_used"]))
         assert state.tolist() == [seed, off + 1]
     assert runs[0][0] == runs[1][0] and torch.equal(runs[0][1], runs[1][1])
-    first = int((int(_philox_host(seed, off, 0xFFFFFFFF, [0])[0]) * T) >> 32)
-    u = (_philox_host(seed, off, np.arange(k - 1)[:, None].repeat(T, 1), np.arange(T)[None, :].repeat(k - 1, 0)) >> np.uint32(8)).astype(np.float32)
+    first = int((int(_philox_host(seed, off, 0xFFFFFFFF, [0])[0, 0]) * T) >> 32)
+    # noise of sampling round r for frame i = component i & 3 of the call (i >> 2, stream r)
+    calls = _philox_host(seed, off, np.arange(k - 1)[:, None].repeat(T // 4, 1), np.arange(T // 4)[None, :].repeat(k - 1, 0))  # [k-1, T/4, 4]
+    u = (calls.reshape(k - 1, T) >> np.uint32(8)).astype(np.float32)
     noise = torch.from_numpy(-np.log((u + np.float32(0.5)) * np.float32(2.0 ** -24)).astype(np.float32))
-    reseeds = [int((int(v) * T) >> 32) for v in _philox_host(seed, off, 0xFFFFFFFE, np.arange(64))]
+    reseeds = [int((int(v) * T) >> 32) for v in _philox_host(seed, off, 0xFFFFFFFE, np.arange(64))[:, 0]]
     info = orc.KMeansInfo()
     orig = random.randint
     try:
