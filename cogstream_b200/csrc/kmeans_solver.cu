@@ -955,6 +955,185 @@ __device__ void solver_outputs(const SolverArgs& a, const int* s_offs, const int
   }
 }
 
+// ---- distances + assignment (kmeans_with_time.py:73-104) of the frames [f_begin, f_end): warp `gwarp` of `n_gwarps` ------------
+// S = sum-of-Gram columns of the current centres, q = ||c_j||^2, ctc = centre times, s_rn = 1 / n_j (shared memory), diag = Gram
+// diagonal, s_ts = shared-memory copy of the timestamps or nullptr.  Used by the cooperative solver (all frames, every CTA) and
+// by the frame-sharded Lloyd kernels (a rank's own frames).
+template <typename TS, bool WIDE>
+__device__ __forceinline__ void assign_pass(const SolverArgs& a, const double* __restrict__ S, const double* q, const double* ctc,
+                                            const double* s_rn, const double* diag, const TS* s_ts, TS alpha, int f_begin, int f_end,
+                                            int gwarp, int n_gwarps, float& my_margin) {
+  const int k = a.k;
+  const int lane = threadIdx.x & 31;
+  // A frame is handled by a group of L lanes (L = 32, or 16 / 8 when k <= 64 / 32 and the frame's k columns fit 4 per lane):
+  // a warp then works on 32 / L frames side by side -- the same per-frame arithmetic, the dependent chain (S row load, fp64
+  // square roots, reductions) of several frames overlapped.  Reductions run over the group's lanes only (min / max / argmin
+  // with the lowest-index tie-break do not depend on the reduction tree).
+  const int L = (!WIDE && k <= 32) ? 8 : ((!WIDE && k <= 64) ? 16 : 32);
+  const int gpw = 32 / L;                      // frames per warp pass
+  const int sub = lane & (L - 1), grp = lane / L;
+  for (int i0 = f_begin + gwarp * gpw; i0 < f_end; i0 += n_gwarps * gpw) {
+    const bool frame_ok = i0 + grp < f_end;
+    const int i = frame_ok ? i0 + grp : f_end - 1;  // idle groups shadow the last frame (full-warp shuffles below), no store
+    const double gii = diag[i];
+    const TS ti = s_ts ? s_ts[i] : load_ts<TS>(a.ts, i);
+    float fmin_ = __int_as_float(0x7f800000), fmax_ = -fmin_;
+    TS tmin_ = (TS)__int_as_float(0x7f800000), tmax_ = -tmin_;
+    constexpr int kWB = WIDE ? 8 : 1;  // 128-column blocks held in registers
+    double sv[kWB][4];
+    float dc[4];
+    TS tc[4];
+    if (WIDE) {
+#pragma unroll
+      for (int bk = 0; bk < kWB; ++bk)
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int j = bk * 128 + lane + 32 * u;
+          sv[bk][u] = j < k ? __ldcg(S + (int64_t)i * k + j) : 0.0;
+        }
+#pragma unroll
+      for (int bk = 0; bk < kWB; ++bk)
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int j = bk * 128 + lane + 32 * u;
+          if (j < k) {
+            const double d2 = gii - 2.0 * (sv[bk][u] * s_rn[j]) + q[j];
+            const float d = (float)sqrt(d2 > 0.0 ? d2 : 0.0);
+            TS dt = ti - (TS)ctc[j];
+            dt = dt < TS(0) ? -dt : dt;
+            fmin_ = fminf(fmin_, d); fmax_ = fmaxf(fmax_, d);
+            tmin_ = dt < tmin_ ? dt : tmin_; tmax_ = dt > tmax_ ? dt : tmax_;
+          }
+        }
+    } else {
+    {
+      double s0[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int j = sub + L * u;
+        s0[u] = j < k ? __ldcg(S + (int64_t)i * k + j) : 0.0;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int j = sub + L * u;
+        if (j < k) {
+          const double d2 = gii - 2.0 * (s0[u] * s_rn[j]) + q[j];
+          dc[u] = (float)sqrt(d2 > 0.0 ? d2 : 0.0);
+          TS dt = ti - (TS)ctc[j];
+          tc[u] = dt < TS(0) ? -dt : dt;
+          fmin_ = fminf(fmin_, dc[u]); fmax_ = fmaxf(fmax_, dc[u]);
+          tmin_ = tc[u] < tmin_ ? tc[u] : tmin_; tmax_ = tc[u] > tmax_ ? tc[u] : tmax_;
+        }
+      }
+    }
+    // k > 128 (then L == 32): further blocks of 128 columns, 4 independent S loads per lane in flight
+    for (int j0 = 128; j0 < k; j0 += 128) {
+      double sv[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int j = j0 + lane + 32 * u;
+        sv[u] = j < k ? __ldcg(S + (int64_t)i * k + j) : 0.0;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int j = j0 + lane + 32 * u;
+        if (j < k) {
+          const double d2 = gii - 2.0 * (sv[u] * s_rn[j]) + q[j];
+          const float d = (float)sqrt(d2 > 0.0 ? d2 : 0.0);
+          TS dt = ti - (TS)ctc[j];
+          dt = dt < TS(0) ? -dt : dt;
+          fmin_ = fminf(fmin_, d); fmax_ = fmaxf(fmax_, d);
+          tmin_ = dt < tmin_ ? dt : tmin_; tmax_ = dt > tmax_ ? dt : tmax_;
+        }
+      }
+    }
+    }
+    for (int o = L >> 1; o > 0; o >>= 1) {  // min / max over the group's lanes
+      const float f0 = __shfl_xor_sync(0xffffffffu, fmin_, o), f1 = __shfl_xor_sync(0xffffffffu, fmax_, o);
+      const TS t0 = __shfl_xor_sync(0xffffffffu, tmin_, o), t1 = __shfl_xor_sync(0xffffffffu, tmax_, o);
+      fmin_ = f0 < fmin_ ? f0 : fmin_; fmax_ = f1 > fmax_ ? f1 : fmax_;
+      tmin_ = t0 < tmin_ ? t0 : tmin_; tmax_ = t1 > tmax_ ? t1 : tmax_;
+    }
+    const float fspread = __fsub_rn(fmax_, fmin_);
+    const TS tspread = tmax_ - tmin_;
+    float best = __int_as_float(0x7f800000), second = best;
+    int bestj = 0x7fffffff;
+    auto consider = [&](float d, TS dt, int j) {
+      // 0 / spread is exactly +0; a zero numerator (the row minimum: one lane of every warp) would send the warp down the
+      // IEEE division's slow path, so it is substituted and the quotient selected afterwards
+      const float fnum = __fsub_rn(d, fmin_);
+      float nf = (fmax_ > fmin_) ? __fdiv_rn(fnum == 0.f ? 1.f : fnum, fspread) : 0.f;  // :86-91
+      nf = fnum == 0.f ? 0.f : nf;
+      const TS tnum = dt - tmin_;
+      TS nt = (tmax_ > tmin_) ? (tnum == TS(0) ? TS(1) : tnum) / tspread : TS(0);          // :94-99
+      nt = tnum == TS(0) ? TS(0) : nt;
+      float fin;                                                                               // :101
+      if (sizeof(TS) == 8) {
+        const double v = __dadd_rn((double)__fmul_rn(nf, nf), __dmul_rn((double)alpha, __dmul_rn((double)nt, (double)nt)));
+        fin = __double2float_rn(sqrt(v));
+      } else {
+        const float ntf = (float)nt;
+        fin = __fsqrt_rn(__fadd_rn(__fmul_rn(nf, nf), __fmul_rn((float)alpha, __fmul_rn(ntf, ntf))));
+      }
+      if (fin < best) { second = best; best = fin; bestj = j; }
+      else if (fin < second) second = fin;
+    };
+    if (WIDE) {
+#pragma unroll
+      for (int bk = 0; bk < kWB; ++bk)
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int j = bk * 128 + lane + 32 * u;
+          if (j < k) {  // same arithmetic as the first pass: the same d, dt bits
+            const double d2 = gii - 2.0 * (sv[bk][u] * s_rn[j]) + q[j];
+            const float d = (float)sqrt(d2 > 0.0 ? d2 : 0.0);
+            TS dt = ti - (TS)ctc[j];
+            dt = dt < TS(0) ? -dt : dt;
+            consider(d, dt, j);
+          }
+        }
+    } else {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int j = sub + L * u;
+      if (j < k) consider(dc[u], tc[u], j);
+    }
+    for (int j0 = 128; j0 < k; j0 += 128) {
+      double sv[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int j = j0 + lane + 32 * u;
+        sv[u] = j < k ? __ldcg(S + (int64_t)i * k + j) : 0.0;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int j = j0 + lane + 32 * u;
+        if (j < k) {
+          const double d2 = gii - 2.0 * (sv[u] * s_rn[j]) + q[j];
+          const float d = (float)sqrt(d2 > 0.0 ? d2 : 0.0);
+          TS dt = ti - (TS)ctc[j];
+          dt = dt < TS(0) ? -dt : dt;
+          consider(d, dt, j);
+        }
+      }
+    }
+    }
+    for (int o = L >> 1; o > 0; o >>= 1) {
+      const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+      const float os = __shfl_xor_sync(0xffffffffu, second, o);
+      const int oj = __shfl_xor_sync(0xffffffffu, bestj, o);
+      const float hi = fmaxf(best, ob);
+      second = fminf(hi, fminf(second, os));
+      if (ob < best || (ob == best && oj < bestj)) { best = ob; bestj = oj; }
+    }
+    if (sub == 0 && frame_ok) {
+      a.assignments[i] = bestj;  // :104 lowest index on ties
+      a.assign32[i] = bestj;
+      if (k > 1) my_margin = fminf(my_margin, second - best);
+    }
+  }
+}
+
 // WIDE (128 < k <= 1024): the assignment pass keeps a frame's whole row of S in registers (one L2 / HBM round trip per frame
 // instead of one per 128 columns and per pass); its own instantiation so that the small-k kernel keeps its register budget.
 template <typename TS, bool WIDE>
@@ -1075,173 +1254,8 @@ __global__ void __launch_bounds__(kSolverThreads, WIDE ? 1 : 2) kmeans_solver_ke
     const double* S = a.S[cur];
     const double* q = s_q[cur];
     const double* ctc = s_ctb[cur];
-    // A frame is handled by a group of L lanes (L = 32, or 16 / 8 when k <= 64 / 32 and the frame's k columns fit 4 per lane):
-    // a warp then works on 32 / L frames side by side -- the same per-frame arithmetic, the dependent chain (S row load, fp64
-    // square roots, reductions) of several frames overlapped.  Reductions run over the group's lanes only (min / max / argmin
-    // with the lowest-index tie-break do not depend on the reduction tree).
-    const int L = (!WIDE && k <= 32) ? 8 : ((!WIDE && k <= 64) ? 16 : 32);
-    const int gpw = 32 / L;                      // frames per warp pass
-    const int sub = lane & (L - 1), grp = lane / L;
-    for (int i0 = (blockIdx.x * kSolverWarps + warp) * gpw; i0 < T; i0 += nb * kSolverWarps * gpw) {
-      const bool frame_ok = i0 + grp < T;
-      const int i = frame_ok ? i0 + grp : T - 1;  // idle groups shadow the last frame (full-warp shuffles below), no store
-      const double gii = diag[i];
-      const TS ti = a.diag_in_smem ? s_ts[i] : load_ts<TS>(a.ts, i);
-      float fmin_ = __int_as_float(0x7f800000), fmax_ = -fmin_;
-      TS tmin_ = (TS)__int_as_float(0x7f800000), tmax_ = -tmin_;
-      constexpr int kWB = WIDE ? 8 : 1;  // 128-column blocks held in registers
-      double sv[kWB][4];
-      float dc[4];
-      TS tc[4];
-      if (WIDE) {
-#pragma unroll
-        for (int bk = 0; bk < kWB; ++bk)
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const int j = bk * 128 + lane + 32 * u;
-            sv[bk][u] = j < k ? __ldcg(S + (int64_t)i * k + j) : 0.0;
-          }
-#pragma unroll
-        for (int bk = 0; bk < kWB; ++bk)
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const int j = bk * 128 + lane + 32 * u;
-            if (j < k) {
-              const double d2 = gii - 2.0 * (sv[bk][u] * s_rn[j]) + q[j];
-              const float d = (float)sqrt(d2 > 0.0 ? d2 : 0.0);
-              TS dt = ti - (TS)ctc[j];
-              dt = dt < TS(0) ? -dt : dt;
-              fmin_ = fminf(fmin_, d); fmax_ = fmaxf(fmax_, d);
-              tmin_ = dt < tmin_ ? dt : tmin_; tmax_ = dt > tmax_ ? dt : tmax_;
-            }
-          }
-      } else {
-      {
-        double s0[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int j = sub + L * u;
-          s0[u] = j < k ? __ldcg(S + (int64_t)i * k + j) : 0.0;
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int j = sub + L * u;
-          if (j < k) {
-            const double d2 = gii - 2.0 * (s0[u] * s_rn[j]) + q[j];
-            dc[u] = (float)sqrt(d2 > 0.0 ? d2 : 0.0);
-            TS dt = ti - (TS)ctc[j];
-            tc[u] = dt < TS(0) ? -dt : dt;
-            fmin_ = fminf(fmin_, dc[u]); fmax_ = fmaxf(fmax_, dc[u]);
-            tmin_ = tc[u] < tmin_ ? tc[u] : tmin_; tmax_ = tc[u] > tmax_ ? tc[u] : tmax_;
-          }
-        }
-      }
-      // k > 128 (then L == 32): further blocks of 128 columns, 4 independent S loads per lane in flight
-      for (int j0 = 128; j0 < k; j0 += 128) {
-        double sv[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int j = j0 + lane + 32 * u;
-          sv[u] = j < k ? __ldcg(S + (int64_t)i * k + j) : 0.0;
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int j = j0 + lane + 32 * u;
-          if (j < k) {
-            const double d2 = gii - 2.0 * (sv[u] * s_rn[j]) + q[j];
-            const float d = (float)sqrt(d2 > 0.0 ? d2 : 0.0);
-            TS dt = ti - (TS)ctc[j];
-            dt = dt < TS(0) ? -dt : dt;
-            fmin_ = fminf(fmin_, d); fmax_ = fmaxf(fmax_, d);
-            tmin_ = dt < tmin_ ? dt : tmin_; tmax_ = dt > tmax_ ? dt : tmax_;
-          }
-        }
-      }
-      }
-      for (int o = L >> 1; o > 0; o >>= 1) {  // min / max over the group's lanes
-        const float f0 = __shfl_xor_sync(0xffffffffu, fmin_, o), f1 = __shfl_xor_sync(0xffffffffu, fmax_, o);
-        const TS t0 = __shfl_xor_sync(0xffffffffu, tmin_, o), t1 = __shfl_xor_sync(0xffffffffu, tmax_, o);
-        fmin_ = f0 < fmin_ ? f0 : fmin_; fmax_ = f1 > fmax_ ? f1 : fmax_;
-        tmin_ = t0 < tmin_ ? t0 : tmin_; tmax_ = t1 > tmax_ ? t1 : tmax_;
-      }
-      const float fspread = __fsub_rn(fmax_, fmin_);
-      const TS tspread = tmax_ - tmin_;
-      float best = __int_as_float(0x7f800000), second = best;
-      int bestj = 0x7fffffff;
-      auto consider = [&](float d, TS dt, int j) {
-        // 0 / spread is exactly +0; a zero numerator (the row minimum: one lane of every warp) would send the warp down the
-        // IEEE division's slow path, so it is substituted and the quotient selected afterwards
-        const float fnum = __fsub_rn(d, fmin_);
-        float nf = (fmax_ > fmin_) ? __fdiv_rn(fnum == 0.f ? 1.f : fnum, fspread) : 0.f;  // :86-91
-        nf = fnum == 0.f ? 0.f : nf;
-        const TS tnum = dt - tmin_;
-        TS nt = (tmax_ > tmin_) ? (tnum == TS(0) ? TS(1) : tnum) / tspread : TS(0);          // :94-99
-        nt = tnum == TS(0) ? TS(0) : nt;
-        float fin;                                                                               // :101
-        if (sizeof(TS) == 8) {
-          const double v = __dadd_rn((double)__fmul_rn(nf, nf), __dmul_rn((double)alpha, __dmul_rn((double)nt, (double)nt)));
-          fin = __double2float_rn(sqrt(v));
-        } else {
-          const float ntf = (float)nt;
-          fin = __fsqrt_rn(__fadd_rn(__fmul_rn(nf, nf), __fmul_rn((float)alpha, __fmul_rn(ntf, ntf))));
-        }
-        if (fin < best) { second = best; best = fin; bestj = j; }
-        else if (fin < second) second = fin;
-      };
-      if (WIDE) {
-#pragma unroll
-        for (int bk = 0; bk < kWB; ++bk)
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const int j = bk * 128 + lane + 32 * u;
-            if (j < k) {  // same arithmetic as the first pass: the same d, dt bits
-              const double d2 = gii - 2.0 * (sv[bk][u] * s_rn[j]) + q[j];
-              const float d = (float)sqrt(d2 > 0.0 ? d2 : 0.0);
-              TS dt = ti - (TS)ctc[j];
-              dt = dt < TS(0) ? -dt : dt;
-              consider(d, dt, j);
-            }
-          }
-      } else {
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int j = sub + L * u;
-        if (j < k) consider(dc[u], tc[u], j);
-      }
-      for (int j0 = 128; j0 < k; j0 += 128) {
-        double sv[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int j = j0 + lane + 32 * u;
-          sv[u] = j < k ? __ldcg(S + (int64_t)i * k + j) : 0.0;
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int j = j0 + lane + 32 * u;
-          if (j < k) {
-            const double d2 = gii - 2.0 * (sv[u] * s_rn[j]) + q[j];
-            const float d = (float)sqrt(d2 > 0.0 ? d2 : 0.0);
-            TS dt = ti - (TS)ctc[j];
-            dt = dt < TS(0) ? -dt : dt;
-            consider(d, dt, j);
-          }
-        }
-      }
-      }
-      for (int o = L >> 1; o > 0; o >>= 1) {
-        const float ob = __shfl_xor_sync(0xffffffffu, best, o);
-        const float os = __shfl_xor_sync(0xffffffffu, second, o);
-        const int oj = __shfl_xor_sync(0xffffffffu, bestj, o);
-        const float hi = fmaxf(best, ob);
-        second = fminf(hi, fminf(second, os));
-        if (ob < best || (ob == best && oj < bestj)) { best = ob; bestj = oj; }
-      }
-      if (sub == 0 && frame_ok) {
-        a.assignments[i] = bestj;  // :104 lowest index on ties
-        a.assign32[i] = bestj;
-        if (k > 1) my_margin = fminf(my_margin, second - best);
-      }
-    }
+    assign_pass<TS, WIDE>(a, S, q, ctc, s_rn, diag, a.diag_in_smem ? s_ts : nullptr, alpha, 0, T, blockIdx.x * kSolverWarps + warp,
+                          (int)nb * kSolverWarps, my_margin);
     mark(a, 10);
     grid_sync(a.barrier, bar, nb);
     mark(a, 11);
@@ -1418,6 +1432,7 @@ int csb_kmeans_solve(const double* G, const void* timestamps, const csb_kmeans_p
     return CSB_ERR_WORKSPACE;
   }
   SolverArgs a;
+  memset(&a, 0, sizeof(a));
   a.G = G; a.ldg = p->ldg > 0 ? p->ldg : T; a.ts = timestamps; a.T = (int)T; a.k = (int)k; a.max_iter = p->max_iteration; a.alpha = p->alpha; a.tol = p->tol;
   a.n_init_given = (int)p->n_init_given; a.n_reseed_pool = (int)p->n_reseed_pool;
   a.init_indices = init_indices; a.exp_noise = exp_noise; a.reseed_pool = reseed_pool; a.assignments = assignments;
@@ -1434,6 +1449,7 @@ int csb_kmeans_solve(const double* G, const void* timestamps, const csb_kmeans_p
   if (T <= 1024) { noise_ws = reinterpret_cast<float*>(w); w += align_up(sizeof(float) * T * k, 256); }
   a.barrier = reinterpret_cast<unsigned*>(w);
   a.noise_ready = reinterpret_cast<unsigned*>(w + 192);
+  a.noise_ws = nullptr;  // set below, for the fused launch only (the separate init kernels generate their noise inline)
   a.used = reinterpret_cast<int32_t*>(w + 128);
   a.tl = reinterpret_cast<unsigned long long*>(w + 256);
   cudaStream_t s = as_stream(stream);
