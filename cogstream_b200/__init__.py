@@ -18,6 +18,7 @@ from .cache import StreamCache  # noqa: F401
 from .serving import StreamInputs, StreamPool, check_rows, run_sharded  # noqa: F401
 from .summary_forward import make_varlen_summary_forward  # noqa: F401
 from .encoder_tail import FusedEncoderTailMixin, encoder_tail, install_encoder_tail  # noqa: F401
+from .sharded import FrameShardedKMeans, frame_range  # noqa: F401
 from .pipeline import STATS_FIELDS, StreamCompressor, StreamConfig, gather_stats, pad_rows, shard_streams  # noqa: F401
 
 __version__ = "0.1.0"

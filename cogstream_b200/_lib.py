@@ -60,6 +60,14 @@ class RelevanceArgs(C.Structure):
     ]
 
 
+class LloydShard(C.Structure):
+    """csb_lloyd_shard (include/cogstream_b200.h)."""
+    _fields_ = [("phase", C.c_int32), ("reserved", C.c_int32), ("f_begin", C.c_int64), ("f_end", C.c_int64), ("per_rank", C.c_int64),
+                ("exchange", C.c_void_p), ("state", C.c_void_p), ("state_bytes", C.c_size_t)]
+
+
+LLOYD_INIT, LLOYD_ASSIGN, LLOYD_UPDATE, LLOYD_SHIFT, LLOYD_OUTPUT = 1, 2, 3, 4, 5
+
 # layout of the device-side csb_kmeans_status (8 x 4 bytes); read back as an int32[8] tensor
 STATUS_WORDS = 8
 ST_ITER, ST_CONV, ST_RESEED, ST_DEGEN, ST_OVERFLOW, ST_NOISE, ST_MARGIN, ST_SHIFT = range(8)
@@ -78,6 +86,8 @@ PROTOTYPES = {
     "csb_gram_extend": (C.c_int, [_p, _i64, _i64, _i64, _p, _i64, _p, _sz, C.c_int, _p]),
     "csb_kmeans_workspace_bytes": (_sz, [_i64, _i64]),
     "csb_kmeans_solve": (C.c_int, [_p, _p, C.POINTER(KMeansParams), _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
+    "csb_kmeans_lloyd_state_bytes": (_sz, [_i64, _i64]),
+    "csb_kmeans_lloyd_phase": (C.c_int, [_p, _p, C.POINTER(KMeansParams), C.POINTER(LloydShard), _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
     "csb_centroid_update": (C.c_int, [_p, _i64, _i64, _p, _p, _i64, _p, _p]),
     "csb_centroid_gather": (C.c_int, [_p, _i64, _i64, _p, _p, _p, _i64, _p, _p, _p]),
     "csb_dist_to_assigned": (C.c_int, [_p, _i64, _i64, _p, _i64, _p, _p, _p]),

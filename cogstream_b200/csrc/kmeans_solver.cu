@@ -496,15 +496,16 @@ constexpr int kSE = 4;
 constexpr int kSRowGroup = 32;
 constexpr int kSR = 4;  // columns in flight per thread in the row-streaming variant (x 4 member loads each)
 constexpr int64_t kSRowMinEntries = 1 << 20;
-__device__ void compute_S_rows(const SolverArgs& a, const int* s_offs, const int* s_memb, const int* cols, int ncols, double* S) {
-  const int T = a.T, k = a.k;
-  const int n_slabs = (T + (int)blockDim.x - 1) / (int)blockDim.x;
+__device__ void compute_S_rows(const SolverArgs& a, const int* s_offs, const int* s_memb, const int* cols, int ncols, double* S, int f_begin,
+                               int f_end) {
+  const int k = a.k;
+  const int n_slabs = (f_end - f_begin + (int)blockDim.x - 1) / (int)blockDim.x;
   const int n_groups = (ncols + kSRowGroup - 1) / kSRowGroup;
   const int n_items = n_slabs * n_groups;
   for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
     const int slab = item % n_slabs, c0 = (item / n_slabs) * kSRowGroup;
-    const int i = slab * blockDim.x + threadIdx.x;
-    if (i >= T) continue;
+    const int i = f_begin + slab * blockDim.x + threadIdx.x;
+    if (i >= f_end) continue;
     const double* gi = a.G + i;
     const int c1 = min(ncols, c0 + kSRowGroup);
     for (int cc = c0; cc < c1; cc += kSR) {
@@ -540,11 +541,13 @@ __device__ void compute_S_rows(const SolverArgs& a, const int* s_offs, const int
   }
 }
 
-__device__ void compute_S(const SolverArgs& a, const int* s_offs, const int* s_memb, const int* cols, int ncols, double* S) {
-  const int T = a.T, k = a.k;
-  const int64_t total = (int64_t)T * ncols;
+// Frames [f_begin, f_end) only: all of them in the single-GPU solver, a rank's own frames in the frame-sharded loop.
+__device__ void compute_S(const SolverArgs& a, const int* s_offs, const int* s_memb, const int* cols, int ncols, double* S, int f_begin,
+                          int f_end) {
+  const int k = a.k;
+  const int64_t total = (int64_t)(f_end - f_begin) * ncols;
   if (total >= kSRowMinEntries) {
-    compute_S_rows(a, s_offs, s_memb, cols, ncols, S);
+    compute_S_rows(a, s_offs, s_memb, cols, ncols, S, f_begin, f_end);
     return;
   }
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -552,8 +555,8 @@ __device__ void compute_S(const SolverArgs& a, const int* s_offs, const int* s_m
     // few entries per thread (short streams, or only a handful of changed clusters): one entry at a time with 16 member loads in
     // flight -- an event of ~15 frames is ONE L2 round trip instead of four.  Same ascending member order, same bits.
     for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += stride) {
-      const int i = (int)(idx / ncols);
-      const int j = cols[(int)(idx - (int64_t)i * ncols)];
+      const int il = (int)(idx / ncols), i = f_begin + il;
+      const int j = cols[(int)(idx - (int64_t)il * ncols)];
       const int beg = s_offs[j], len = s_offs[j + 1] - beg;
       const double* g = a.G + (int64_t)i * a.ldg;
       double sum = 0.0;
@@ -581,8 +584,8 @@ __device__ void compute_S(const SolverArgs& a, const int* s_offs, const int* s_m
       s[u] = 0.0;
       len[u] = 0; beg[u] = 0; g[u] = a.G; out[u] = -1;
       if (idx < total) {
-        const int i = (int)(idx / ncols);
-        const int j = cols[(int)(idx - (int64_t)i * ncols)];
+        const int il = (int)(idx / ncols), i = f_begin + il;
+        const int j = cols[(int)(idx - (int64_t)il * ncols)];
         beg[u] = s_offs[j];
         len[u] = s_offs[j + 1] - beg[u];
         g[u] = a.G + (int64_t)i * a.ldg;
@@ -1134,6 +1137,94 @@ __device__ __forceinline__ void assign_pass(const SolverArgs& a, const double* _
   }
 }
 
+// ---- centre shift (:123-125): sum_j ||c'_j - c_j|| + ||ct' - ct||, identical in every thread of every CTA -------------------------
+// Only changed clusters move.  Lane e of the warp owning cluster j sums the values of member e, e+32, ... (fixed order => an
+// unchanged list would reproduce the same bits: shift exactly 0).  The value of member m for cluster j is S[m][j] in the single-GPU
+// solver (vn / vc = the new / old S, stride k, by_column) and the all-gathered per-frame entry S[m][assign(m)] in the frame-sharded
+// loop (stride 1; `per` > 0: the [world][2][per] exchange layout, vn / vc = its two planes).  Updates q_nxt, 1/n, n of the changed
+// clusters, copies q of the others.
+template <typename TS>
+__device__ double shift_pass(const SolverArgs& a, const int* s_offs, const int* s_memb, const int* s_changed, const double* q_cur, double* q_nxt,
+                             double* s_rn, double* s_nn, const double* ct_cur, const double* ct_nxt, double* s_red, const double* vn,
+                             const double* vc, int per, const int* cnt_real) {
+  const int k = a.k;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // single GPU (per == 0): vn / vc = the new / old S, entry (member m, cluster j) = S[m][j].
+  // frame-sharded (per > 0): vn = the exchange buffer [world][2 * per + k]; rank r's segment holds S_nxt[i][a_i] and S_cur[i][a_i] of
+  // its frames i (planes of `per`) and, for a re-seeded (empty) cluster j whose seed frame it owns, S_cur[seed][j] at 2 * per + j;
+  // the seed's new entry S_nxt[seed][j] is the Gram diagonal.
+  const int64_t seg = 2 * (int64_t)per + k;
+  auto at_new = [&](int m, int j) -> double {
+    if (per == 0) return __ldcg(vn + (int64_t)m * k + j);
+    if (cnt_real[j] == 0) return __ldcg(a.G + (int64_t)m * a.ldg + m);
+    const int r = m / per;
+    return __ldcg(vn + r * seg + (m - r * per));
+  };
+  auto at_old = [&](int m, int j) -> double {
+    if (per == 0) return __ldcg(vc + (int64_t)m * k + j);
+    const int r = m / per;
+    if (cnt_real[j] == 0) return __ldcg(vn + r * seg + 2 * per + j);
+    return __ldcg(vn + r * seg + per + (m - r * per));
+  };
+  double part = 0.0;
+  constexpr int kSB = 4;  // clusters of a warp whose member loads are issued together (one L2 round trip instead of kSB)
+  for (int j0 = warp; j0 < k; j0 += kSolverWarps * kSB) {
+    int jj[kSB], beg[kSB], end[kSB];
+    double sn[kSB], sc[kSB];
+#pragma unroll
+    for (int u = 0; u < kSB; ++u) {
+      const int j = j0 + u * kSolverWarps;
+      jj[u] = -1; beg[u] = 0; end[u] = 0; sn[u] = 0.0; sc[u] = 0.0;
+      if (j < k) {
+        if (!s_changed[j]) {
+          if (lane == 0) q_nxt[j] = q_cur[j];
+        } else {
+          jj[u] = j; beg[u] = s_offs[j]; end[u] = s_offs[j + 1];
+          const int e = beg[u] + lane;
+          if (e < end[u]) {
+            sn[u] = at_new(s_memb[e], j);
+            sc[u] = at_old(s_memb[e], j);
+          }
+        }
+      }
+    }
+    double my_tn = 0.0, my_tc = 0.0;
+    int my_j = -1, my_n = 1;
+#pragma unroll
+    for (int u = 0; u < kSB; ++u) {
+      if (jj[u] < 0) continue;  // warp-uniform
+      const int j = jj[u];
+      for (int e = beg[u] + lane + 32; e < end[u]; e += 32) {  // clusters of more than 32 members (same per-lane order)
+        const double v1 = at_new(s_memb[e], j), v2 = at_old(s_memb[e], j);
+        sn[u] += v1;
+        sc[u] += v2;
+      }
+      const double tn = warp_sum(sn[u]), tc = warp_sum(sc[u]);
+      if (lane == u) { my_tn = tn; my_tc = tc; my_j = j; my_n = end[u] - beg[u]; }
+    }
+    // lane u finishes cluster u of the batch: the divisions and the square root of the kSB clusters run side by side
+    if (my_j >= 0) {
+      const int j = my_j;
+      const double n = (double)my_n;
+      const double qn = my_tn / (n * n);
+      const double cross = my_tc / (n * s_nn[j]);
+      const double sh2 = (qn + q_cur[j]) - 2.0 * cross;
+      q_nxt[j] = qn;
+      s_rn[j] = 1.0 / n;  // cluster j's entries are owned by this warp until the next block barrier
+      s_nn[j] = n;
+      part += sqrt(sh2 > 0.0 ? sh2 : 0.0);
+    }
+  }
+  const double shift_feat = block_sum<double>(part, s_red);
+  double tpart = 0.0;
+  for (int j = threadIdx.x; j < k; j += blockDim.x) {
+    const TS d = (TS)ct_nxt[j] - (TS)ct_cur[j];
+    tpart += (double)(d * d);
+  }
+  const double shift_time = sqrt(block_sum<double>(tpart, s_red));
+  return shift_feat + shift_time;
+}
+
 // WIDE (128 < k <= 1024): the assignment pass keeps a frame's whole row of S in registers (one L2 / HBM round trip per frame
 // instead of one per 128 columns and per pass); its own instantiation so that the small-k kernel keeps its register budget.
 template <typename TS, bool WIDE>
@@ -1235,7 +1326,7 @@ __global__ void __launch_bounds__(kSolverThreads, WIDE ? 1 : 2) kmeans_solver_ke
   }
   if (threadIdx.x == 0) s_offs[k] = k;
   __syncthreads();
-  compute_S(a, s_offs, s_memb, s_cols, k, a.S[0]);
+  compute_S(a, s_offs, s_memb, s_cols, k, a.S[0], 0, T);
   grid_sync(a.barrier, bar, nb);
   mark(a, 3);
 
@@ -1291,7 +1382,7 @@ __global__ void __launch_bounds__(kSolverThreads, WIDE ? 1 : 2) kmeans_solver_ke
     }
     __syncthreads();
     mark(a, 12);
-    compute_S(a, s_offs, s_memb, s_cols, s_ncols, a.S[nxt]);
+    compute_S(a, s_offs, s_memb, s_cols, s_ncols, a.S[nxt], 0, T);
     mark(a, 13);
     grid_sync(a.barrier, bar, nb);
     mark(a, 14);
@@ -1299,74 +1390,238 @@ __global__ void __launch_bounds__(kSolverThreads, WIDE ? 1 : 2) kmeans_solver_ke
     // ---------- centre shift (:123-125); every CTA evaluates it identically ----------
     // Only changed clusters move.  Lane e of the warp owning cluster j sums member e, e+32, ... of column j of the
     // new and the old S (fixed order => an unchanged list would reproduce the same bits: shift exactly 0).
-    double part = 0.0;
-    constexpr int kSB = 4;  // clusters of a warp whose member loads are issued together (one L2 round trip instead of kSB)
-    for (int j0 = warp; j0 < k; j0 += kSolverWarps * kSB) {
-      int jj[kSB], beg[kSB], end[kSB];
-      double sn[kSB], sc[kSB];
-#pragma unroll
-      for (int u = 0; u < kSB; ++u) {
-        const int j = j0 + u * kSolverWarps;
-        jj[u] = -1; beg[u] = 0; end[u] = 0; sn[u] = 0.0; sc[u] = 0.0;
-        if (j < k) {
-          if (!s_changed[j]) {
-            if (lane == 0) s_q[nxt][j] = s_q[cur][j];
-          } else {
-            jj[u] = j; beg[u] = s_offs[j]; end[u] = s_offs[j + 1];
-            const int e = beg[u] + lane;
-            if (e < end[u]) {
-              const int64_t row = (int64_t)s_memb[e] * k + j;
-              sn[u] = __ldcg(a.S[nxt] + row);
-              sc[u] = __ldcg(a.S[cur] + row);
-            }
-          }
-        }
-      }
-      double my_tn = 0.0, my_tc = 0.0;
-      int my_j = -1, my_n = 1;
-#pragma unroll
-      for (int u = 0; u < kSB; ++u) {
-        if (jj[u] < 0) continue;  // warp-uniform
-        const int j = jj[u];
-        for (int e = beg[u] + lane + 32; e < end[u]; e += 32) {  // clusters of more than 32 members (same per-lane order)
-          const int64_t row = (int64_t)s_memb[e] * k + j;
-          const double vn = __ldcg(a.S[nxt] + row), vc = __ldcg(a.S[cur] + row);
-          sn[u] += vn;
-          sc[u] += vc;
-        }
-        const double tn = warp_sum(sn[u]), tc = warp_sum(sc[u]);
-        if (lane == u) { my_tn = tn; my_tc = tc; my_j = j; my_n = end[u] - beg[u]; }
-      }
-      // lane u finishes cluster u of the batch: the divisions and the square root of the kSB clusters run side by side
-      if (my_j >= 0) {
-        const int j = my_j;
-        const double n = (double)my_n;
-        const double qn = my_tn / (n * n);
-        const double cross = my_tc / (n * s_nn[j]);
-        const double sh2 = (qn + s_q[cur][j]) - 2.0 * cross;
-        s_q[nxt][j] = qn;
-        s_rn[j] = 1.0 / n;  // cluster j's entries are owned by this warp until the barrier below
-        s_nn[j] = n;
-        part += sqrt(sh2 > 0.0 ? sh2 : 0.0);
-      }
-    }
-    const double shift_feat = block_sum<double>(part, s_red);
-    double tpart = 0.0;
-    for (int j = threadIdx.x; j < k; j += blockDim.x) {
-      const TS d = (TS)s_ctb[nxt][j] - (TS)s_ctb[cur][j];
-      tpart += (double)(d * d);
-    }
-    const double shift_time = sqrt(block_sum<double>(tpart, s_red));
+    const double shift = shift_pass<TS>(a, s_offs, s_memb, s_changed, s_q[cur], s_q[nxt], s_rn, s_nn, s_ctb[cur], s_ctb[nxt], s_red,
+                                        a.S[nxt], a.S[cur], 0, nullptr);
     __syncthreads();
     cur = nxt;
     mark(a, 15);
-    const double shift = shift_feat + shift_time;
     last_shift = (float)shift;
     if (shift <= a.tol) { converged = true; break; }  // :130
   }
 
   // ---------------- outputs ----------------
   solver_outputs<TS>(a, s_offs, s_memb, s_ctb[cur], s_cntw, s_cursor, my_margin, it, converged, used, last_shift);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------------------
+// Frame-sharded Lloyd loop (first half): a single long stream over the GPUs of one box.
+// Every rank holds the Gram matrix (the per-stream cache keeps it up to date) and runs the k-means++ init redundantly (a chain of
+// k - 1 dependent sampling rounds: nothing to shard); the Lloyd iteration is split by FRAMES: rank r computes the distance /
+// assignment pass and the S rows of its own frames [f_begin, f_end) only.  One iteration = three launches with a collective after
+// the first two (the host side issues them: NCCL all-gather over NVLink):
+//     ASSIGN  own frames -> assign32[f_begin:f_end)                          | all-gather assign32 [T]
+//     UPDATE  (every rank, identical) membership CSR, centre times, changed columns; S[nxt] rows of the own frames for the
+//             changed clusters; per own frame i the entries S_nxt[i][a_i], S_cur[i][a_i]     | all-gather of those [T] x 2
+//     SHIFT   (every rank, identical) ||c_j||^2, 1/n_j and the centre shift from the gathered entries -> converged?
+// The state that the single-GPU kernel keeps in shared memory across iterations lives in global memory between launches
+// (LloydState, identical on every rank).  The phases call the SAME device functions as the cooperative solver (assign_pass,
+// rebuild_members_smem, compute_S, shift_pass) with the same summation orders: assignments, iteration count, re-seeds and
+// centre times are bit-identical to the single-GPU solve.
+// ---------------------------------------------------------------------------------------------------------------------------------
+enum { kLloydInit = 1, kLloydAssign = 2, kLloydUpdate = 3, kLloydShift = 4, kLloydOutput = 5 };
+enum { kScCur = 0, kScIt = 1, kScUsed = 2, kScConverged = 3, kScLastShift = 4, kScMargin = 5 };
+
+struct LloydState {
+  double* q[2];      // [k]
+  double* ctb[2];    // [k]
+  double* rn;        // [k]
+  double* nn;        // [k]
+  int* ver;          // [k]
+  int* verbuf[2];    // [k]
+  int* changed;      // [k]
+  int* cntw_last;    // [k] assigned frames per cluster (without the seed of a re-seeded one)
+  int* offs;         // [k + 1]
+  int* memb;         // [T + k]
+  int* assign_prev;  // [T]
+  int* scal;         // [8]
+  double* xch;       // [world][2][per] exchange planes: S_nxt[i][a_i] / S_cur[i][a_i] of every frame
+  int phase, f_begin, f_end, per;
+};
+
+template <typename TS, bool WIDE>
+__global__ void __launch_bounds__(kSolverThreads, 1) lloyd_phase_kernel(SolverArgs a, LloydState L) {
+  extern __shared__ double smem_d[];
+  const int T = a.T, k = a.k;
+  double* s_q[2] = {smem_d, smem_d + k};
+  double* s_ctb[2] = {smem_d + 2 * k, smem_d + 3 * k};
+  double* s_rn = smem_d + 4 * k;
+  double* s_nn = smem_d + 5 * k;
+  double* s_red = smem_d + 6 * k;
+  double* s_diag = s_red + 32;
+  TS* s_ts = reinterpret_cast<TS*>(s_diag + T);
+  int* s_assign = reinterpret_cast<int*>(s_diag + (a.diag_in_smem ? 2 * T : 0));
+  int* s_offs = s_assign + T;
+  int* s_cursor = s_offs + (k + 1);
+  int* s_memb = s_cursor + (k + 1);
+  int* s_changed = s_memb + (T + k);
+  int* s_ver = s_changed + k;
+  int* s_verbuf[2] = {s_ver + k, s_ver + 2 * k};
+  int* s_cols = s_ver + 3 * k;
+  int* s_cntw = s_cols + k;
+  __shared__ int s_ncols;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const unsigned nb = gridDim.x;
+  const int nw = a.multiwarp_fill ? kSolverWarps : 1;
+  const int cur = L.scal[kScCur], nxt = cur ^ 1;
+  if (a.diag_in_smem)
+    for (int i = threadIdx.x; i < T; i += blockDim.x) { s_diag[i] = a.diag[i]; s_ts[i] = load_ts<TS>(a.ts, i); }
+  const double* diag = a.diag_in_smem ? s_diag : a.diag;
+
+  if (L.phase == kLloydInit) {
+    // centres = the k seed frames (kmeans_with_time.py:65-66); S[0] rows of the own frames
+    for (int j = threadIdx.x; j < k; j += blockDim.x) {
+      s_offs[j] = j;
+      s_memb[j] = (int)__ldcg(a.init_indices + j);
+      s_cols[j] = j;
+    }
+    if (threadIdx.x == 0) s_offs[k] = k;
+    __syncthreads();
+    compute_S(a, s_offs, s_memb, s_cols, k, a.S[0], L.f_begin, L.f_end);
+    if (blockIdx.x == 0) {
+      for (int j = threadIdx.x; j < k; j += blockDim.x) {
+        const int c = s_memb[j];
+        L.q[0][j] = a.diag[c];
+        L.ctb[0][j] = (double)load_ts<TS>(a.ts, c);
+        L.rn[j] = 1.0; L.nn[j] = 1.0;
+        L.ver[j] = 1; L.verbuf[0][j] = 1; L.verbuf[1][j] = 0;
+        L.cntw_last[j] = 0;
+        L.offs[j] = j; L.memb[j] = c;
+      }
+      if (threadIdx.x == 0) {
+        L.offs[k] = k;
+        L.scal[kScCur] = 0; L.scal[kScIt] = 0; L.scal[kScUsed] = *a.used; L.scal[kScConverged] = 0;
+        L.scal[kScLastShift] = 0; L.scal[kScMargin] = 0x7f800000;
+      }
+    }
+    return;
+  }
+
+  if (L.phase == kLloydAssign) {
+    for (int j = threadIdx.x; j < k; j += blockDim.x) { s_q[cur][j] = L.q[cur][j]; s_ctb[cur][j] = L.ctb[cur][j]; s_rn[j] = L.rn[j]; }
+    __syncthreads();
+    float my_margin = __int_as_float(0x7f800000);
+    assign_pass<TS, WIDE>(a, a.S[cur], s_q[cur], s_ctb[cur], s_rn, diag, a.diag_in_smem ? s_ts : nullptr, (TS)a.alpha, L.f_begin, L.f_end,
+                          blockIdx.x * kSolverWarps + warp, (int)nb * kSolverWarps, my_margin);
+    my_margin = warp_min(my_margin);
+    if (lane == 0 && my_margin < __int_as_float(0x7f800000))
+      atomicMin(reinterpret_cast<unsigned*>(L.scal + kScMargin), __float_as_uint(fmaxf(my_margin, 0.f)));
+    return;
+  }
+
+  if (L.phase == kLloydUpdate) {  // cooperative launch (one grid barrier)
+    const int it = L.scal[kScIt] + 1;
+    int used = L.scal[kScUsed];
+    unsigned bar = 0;
+    for (int j = threadIdx.x; j < k; j += blockDim.x) {
+      s_changed[j] = it == 1 ? 1 : 0;
+      s_ver[j] = L.ver[j]; s_verbuf[nxt][j] = L.verbuf[nxt][j];
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < T; i += blockDim.x) {
+      const int now = __ldcg(a.assign32 + i), before = L.assign_prev[i];
+      if (it > 1 && now != before) { s_changed[before] = 1; s_changed[now] = 1; }
+      s_assign[i] = now;
+    }
+    __syncthreads();
+    MemberSmem ms;
+    ms.assign = s_assign; ms.offs = s_offs; ms.memb = s_memb; ms.cursor = s_cursor; ms.cntw = s_cntw; ms.changed = s_changed;
+    ms.ts_smem = a.diag_in_smem ? s_ts : nullptr;
+    ms.ct_new = s_ctb[nxt];
+    rebuild_members_smem<TS>(a, ms, &used, it == 1);
+    if (warp == 0) {
+      int nc = 0;
+      for (int j0 = 0; j0 < k; j0 += 32) {
+        const int j = j0 + lane;
+        bool stale = false;
+        if (j < k) {
+          if (s_changed[j]) s_ver[j] += 1;
+          stale = s_verbuf[nxt][j] != s_ver[j];
+          if (stale) s_verbuf[nxt][j] = s_ver[j];
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, stale);
+        if (stale) s_cols[nc + __popc(bal & ((1u << lane) - 1u))] = j;
+        nc += __popc(bal);
+      }
+      if (lane == 0) s_ncols = nc;
+    }
+    __syncthreads();
+    compute_S(a, s_offs, s_memb, s_cols, s_ncols, a.S[nxt], L.f_begin, L.f_end);
+    grid_sync(a.barrier, bar, nb);
+    // exchange planes: what the (replicated) shift pass needs of this rank's rows
+    const int64_t seg = 2 * (int64_t)L.per + k;
+    for (int i = L.f_begin + blockIdx.x * blockDim.x + threadIdx.x; i < L.f_end; i += nb * blockDim.x) {
+      const int ai = s_assign[i];
+      const int r = i / L.per, o = i - r * L.per;
+      // an unchanged cluster's column was not recomputed in S[nxt] (its shift term is skipped): send the value it would have
+      const double v_cur = __ldcg(a.S[cur] + (int64_t)i * k + ai);
+      L.xch[r * seg + o] = s_changed[ai] ? __ldcg(a.S[nxt] + (int64_t)i * k + ai) : v_cur;
+      L.xch[r * seg + L.per + o] = v_cur;
+    }
+    // re-seeded (empty) clusters: the owner of the seed frame exports the seed's entry of the OLD column
+    if (blockIdx.x == 0 && L.f_end > L.f_begin) {
+      const int rme = L.f_begin / L.per;
+      for (int j = threadIdx.x; j < k; j += blockDim.x) {
+        double v = 0.0;
+        if (s_cntw[(nw - 1) * k + j] == 0) {
+          const int seed = s_memb[s_offs[j]];
+          if (seed >= L.f_begin && seed < L.f_end) v = __ldcg(a.S[cur] + (int64_t)seed * k + j);
+        }
+        L.xch[rme * seg + 2 * L.per + j] = v;
+      }
+    }
+    if (blockIdx.x == 0) {
+      for (int j = threadIdx.x; j < k; j += blockDim.x) {
+        L.changed[j] = s_changed[j]; L.ver[j] = s_ver[j]; L.verbuf[nxt][j] = s_verbuf[nxt][j];
+        L.ctb[nxt][j] = s_ctb[nxt][j];
+        L.cntw_last[j] = s_cntw[(nw - 1) * k + j];
+        L.offs[j] = s_offs[j];
+      }
+      if (threadIdx.x == 0) { L.offs[k] = s_offs[k]; L.scal[kScUsed] = used; }
+      const int nmem = s_offs[k];
+      for (int m = threadIdx.x; m < nmem; m += blockDim.x) L.memb[m] = s_memb[m];
+      for (int i = threadIdx.x; i < T; i += blockDim.x) L.assign_prev[i] = s_assign[i];
+    }
+    return;
+  }
+
+  if (L.phase == kLloydShift) {  // one CTA
+    for (int j = threadIdx.x; j < k; j += blockDim.x) {
+      s_q[cur][j] = L.q[cur][j]; s_ctb[cur][j] = L.ctb[cur][j]; s_ctb[nxt][j] = L.ctb[nxt][j];
+      s_rn[j] = L.rn[j]; s_nn[j] = L.nn[j]; s_changed[j] = L.changed[j]; s_offs[j] = L.offs[j];
+      s_cols[j] = L.cntw_last[j];
+    }
+    if (threadIdx.x == 0) s_offs[k] = L.offs[k];
+    __syncthreads();
+    const int nmem = s_offs[k];
+    for (int m = threadIdx.x; m < nmem; m += blockDim.x) s_memb[m] = L.memb[m];
+    __syncthreads();
+    const double shift = shift_pass<TS>(a, s_offs, s_memb, s_changed, s_q[cur], s_q[nxt], s_rn, s_nn, s_ctb[cur], s_ctb[nxt], s_red,
+                                        L.xch, nullptr, L.per, s_cols);
+    __syncthreads();
+    for (int j = threadIdx.x; j < k; j += blockDim.x) { L.q[nxt][j] = s_q[nxt][j]; L.rn[j] = s_rn[j]; L.nn[j] = s_nn[j]; }
+    if (threadIdx.x == 0) {
+      L.scal[kScCur] = nxt;
+      L.scal[kScIt] = L.scal[kScIt] + 1;
+      L.scal[kScConverged] = shift <= a.tol ? 1 : 0;  // :130
+      L.scal[kScLastShift] = __float_as_int((float)shift);
+    }
+    return;
+  }
+
+  if (L.phase == kLloydOutput) {  // one CTA
+    for (int j = threadIdx.x; j < k; j += blockDim.x) {
+      s_offs[j] = L.offs[j]; s_ctb[cur][j] = L.ctb[cur][j]; s_cntw[(nw - 1) * k + j] = L.cntw_last[j];
+    }
+    if (threadIdx.x == 0) s_offs[k] = L.offs[k];
+    __syncthreads();
+    const int nmem = s_offs[k];
+    for (int m = threadIdx.x; m < nmem; m += blockDim.x) s_memb[m] = L.memb[m];
+    if (L.scal[kScIt] > 0)
+      for (int i = threadIdx.x; i < T; i += blockDim.x) a.assignments[i] = L.assign_prev[i];  // (:104 of the last iteration)
+    __syncthreads();
+    solver_outputs<TS>(a, s_offs, s_memb, s_ctb[cur], s_cntw, s_cursor, __int_as_float(L.scal[kScMargin]), L.scal[kScIt],
+                       L.scal[kScConverged] != 0, L.scal[kScUsed], __int_as_float(L.scal[kScLastShift]));
+  }
 }
 
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -1421,7 +1676,8 @@ int csb_kmeans_solve(const double* G, const void* timestamps, const csb_kmeans_p
               "kmeans_solve: n_init_given must be in [1,k] ([0,k] with the built-in generator)");
   CSB_REQUIRE(p->n_init_given == p->k || exp_noise || p->rng_state, "kmeans_solve: exp_noise or rng_state required when centres are sampled");
   CSB_REQUIRE(p->n_reseed_pool == 0 || reseed_pool, "kmeans_solve: reseed_pool is null");
-  CSB_REQUIRE(p->max_iteration >= 0, "kmeans_solve: max_iteration < 0");
+  // max_iteration < 0: the k-means++ init only (init_indices, Gram diagonal, pool usage): the frame-sharded Lloyd phases follow
+  const bool init_only = p->max_iteration < 0;
   CSB_REQUIRE(p->ldg == 0 || p->ldg >= p->T, "kmeans_solve: ldg < T");
   const int64_t T = p->T, k = p->k;
   const SolverSmemPlan sp = plan_smem(T, k);
@@ -1475,7 +1731,7 @@ int csb_kmeans_solve(const double* G, const void* timestamps, const csb_kmeans_p
   bool grid_init = T > kGridInitMinT && p->n_init_given < k;
   if (const char* o = getenv("CSB_INIT_GRID")) grid_init = atoi(o) != 0 && T <= (int64_t)sms * kGridInitThreads * kGridInitU;
   // short streams (one init thread per <= 4 frames at the solver's block size): the init runs on CTA 0 of the solver launch
-  a.fused_init = (!grid_init && T <= 1024 && sp.diag_in_smem && !getenv("CSB_INIT_THREADS")) ? 1 : 0;
+  a.fused_init = (!grid_init && T <= 1024 && sp.diag_in_smem && !getenv("CSB_INIT_THREADS") && !init_only) ? 1 : 0;
   if (const char* o = getenv("CSB_FUSED_INIT")) a.fused_init = a.fused_init && atoi(o) != 0;
   if (a.fused_init) {
     // nothing to launch here
@@ -1521,6 +1777,7 @@ int csb_kmeans_solve(const double* G, const void* timestamps, const csb_kmeans_p
   // Lloyd loop: frames_per_warp frames per warp in the assignment phase (default 2; T = 600: 38 CTAs).  The loop is
   // latency-bound: one frame per warp (75 CTAs) saves ~2 us per iteration for a stream that runs alone, but with six streams in
   // flight the extra co-resident CTAs cost the bandwidth-bound kernels of the other streams 7 % (measured: 2.15 vs 2.00 M frames/s)
+  if (init_only) return CSB_OK;
   int fpw = p->frames_per_warp > 0 ? (int)p->frames_per_warp : 2;  // (CSB_SOLVER_FPW overrides: tuning runs)
   if (const char* o = getenv("CSB_SOLVER_FPW")) fpw = atoi(o) > 0 ? atoi(o) : fpw;
   // a warp pass covers 32 / L frames (L lanes per frame: 8 / 16 for k <= 32 / 64 in the narrow kernel, see the assignment pass)
@@ -1534,6 +1791,105 @@ int csb_kmeans_solve(const double* G, const void* timestamps, const csb_kmeans_p
   void* args[] = {&a};
   e = cudaLaunchCooperativeKernel((const void*)kern, dim3((unsigned)nb), dim3(kSolverThreads), args, smem, s);
   if (e != cudaSuccess) { set_error("kmeans_solve: launch: %s", cudaGetErrorString(e)); return CSB_ERR_CUDA; }
+  count_launch(1);
+  return CSB_OK;
+}
+
+size_t csb_kmeans_lloyd_state_bytes(int64_t T, int64_t k) {
+  if (T <= 0 || k <= 0) return 0;
+  return 6 * align_up(sizeof(double) * k, 256) + 6 * align_up(sizeof(int) * k, 256) + align_up(sizeof(int) * (k + 1), 256) +
+         align_up(sizeof(int) * (T + k), 256) + align_up(sizeof(int) * T, 256) + 256;
+}
+
+int csb_kmeans_lloyd_phase(const double* G, const void* timestamps, const csb_kmeans_params* p, const csb_lloyd_shard* sh,
+                           int64_t* init_indices, const int64_t* reseed_pool, int32_t* assign32, int64_t* assignments, void* centroid_times,
+                           int32_t* member_offsets, int32_t* members, int32_t* event_order, int32_t* event_offsets, csb_kmeans_status* status,
+                           void* workspace, size_t workspace_bytes, csb_stream_t stream) {
+  CSB_DEVICE_OR_RETURN();
+  CSB_REQUIRE(p && sh, "kmeans_lloyd_phase: null params");
+  CSB_REQUIRE(G && timestamps && init_indices && assign32 && assignments && centroid_times && member_offsets && members && status &&
+                  workspace && sh->state && sh->exchange,
+              "kmeans_lloyd_phase: null pointer");
+  CSB_REQUIRE(p->k >= 1 && p->T > p->k && p->T < (1ll << 30) && p->k <= 4096, "kmeans_lloyd_phase: need T > k >= 1, k <= 4096");
+  CSB_REQUIRE(p->ts_dtype == CSB_F32 || p->ts_dtype == CSB_F64, "kmeans_lloyd_phase: timestamps must be f32 or f64");
+  CSB_REQUIRE(sh->phase >= kLloydInit && sh->phase <= kLloydOutput, "kmeans_lloyd_phase: unknown phase %d", sh->phase);
+  CSB_REQUIRE(sh->per_rank > 0 && sh->f_begin >= 0 && sh->f_begin <= sh->f_end && sh->f_end <= p->T && sh->f_end - sh->f_begin <= sh->per_rank &&
+                  (sh->f_begin % sh->per_rank == 0 || sh->f_begin == sh->f_end),
+              "kmeans_lloyd_phase: bad frame range");
+  CSB_REQUIRE(p->ldg == 0 || p->ldg >= p->T, "kmeans_lloyd_phase: ldg < T");
+  const int64_t T = p->T, k = p->k;
+  const SolverSmemPlan sp = plan_smem(T, k);
+  CSB_REQUIRE(sp.bytes <= 225 * 1024, "kmeans_lloyd_phase: T=%lld k=%lld do not fit the shared-memory membership", (long long)T, (long long)k);
+  if (workspace_bytes < csb_kmeans_workspace_bytes(T, k)) { set_error("kmeans_lloyd_phase: workspace too small"); return CSB_ERR_WORKSPACE; }
+  if (sh->state_bytes < csb_kmeans_lloyd_state_bytes(T, k)) { set_error("kmeans_lloyd_phase: state too small"); return CSB_ERR_WORKSPACE; }
+  SolverArgs a;
+  memset(&a, 0, sizeof(a));
+  a.G = G; a.ldg = p->ldg > 0 ? p->ldg : T; a.ts = timestamps; a.T = (int)T; a.k = (int)k; a.max_iter = p->max_iteration; a.alpha = p->alpha; a.tol = p->tol;
+  a.n_init_given = (int)p->n_init_given; a.n_reseed_pool = (int)p->n_reseed_pool;
+  a.init_indices = init_indices; a.reseed_pool = reseed_pool; a.assignments = assignments;
+  a.ct_out = centroid_times; a.member_offsets = member_offsets; a.members = members; a.status = status;
+  a.event_order = event_order; a.event_offsets = event_offsets;
+  a.diag_in_smem = sp.diag_in_smem; a.multiwarp_fill = sp.multiwarp_fill;
+  a.rng = reinterpret_cast<const unsigned long long*>(p->rng_state);
+  char* w = reinterpret_cast<char*>(workspace);
+  a.diag = reinterpret_cast<double*>(w); w += align_up(sizeof(double) * T, 256);
+  for (int b = 0; b < 2; ++b) { a.S[b] = reinterpret_cast<double*>(w); w += align_up(sizeof(double) * T * k, 256); }
+  w += align_up(sizeof(int32_t) * T, 256);
+  if (T <= 1024) w += align_up(sizeof(float) * T * k, 256);
+  a.assign32 = assign32;  // the caller's [world * per_rank] buffer (all-gathered between ASSIGN and UPDATE)
+  a.barrier = reinterpret_cast<unsigned*>(w);
+  a.used = reinterpret_cast<int32_t*>(w + 128);
+  a.tl = reinterpret_cast<unsigned long long*>(w + 256);
+  LloydState L;
+  char* sw = reinterpret_cast<char*>(sh->state);
+  auto carve = [&](size_t bytes) { char* r = sw; sw += align_up(bytes, 256); return r; };
+  for (int b = 0; b < 2; ++b) L.q[b] = reinterpret_cast<double*>(carve(sizeof(double) * k));
+  for (int b = 0; b < 2; ++b) L.ctb[b] = reinterpret_cast<double*>(carve(sizeof(double) * k));
+  L.rn = reinterpret_cast<double*>(carve(sizeof(double) * k));
+  L.nn = reinterpret_cast<double*>(carve(sizeof(double) * k));
+  L.ver = reinterpret_cast<int*>(carve(sizeof(int) * k));
+  for (int b = 0; b < 2; ++b) L.verbuf[b] = reinterpret_cast<int*>(carve(sizeof(int) * k));
+  L.changed = reinterpret_cast<int*>(carve(sizeof(int) * k));
+  L.cntw_last = reinterpret_cast<int*>(carve(sizeof(int) * k));
+  (void)carve(sizeof(int) * k);
+  L.offs = reinterpret_cast<int*>(carve(sizeof(int) * (k + 1)));
+  L.memb = reinterpret_cast<int*>(carve(sizeof(int) * (T + k)));
+  L.assign_prev = reinterpret_cast<int*>(carve(sizeof(int) * T));
+  L.scal = reinterpret_cast<int*>(carve(32));
+  L.xch = reinterpret_cast<double*>(sh->exchange);
+  L.phase = sh->phase; L.f_begin = (int)sh->f_begin; L.f_end = (int)sh->f_end; L.per = (int)sh->per_rank;
+  cudaStream_t s = as_stream(stream);
+  const bool wide = k > 128 && k <= 1024;
+  auto kern = (p->ts_dtype == CSB_F64) ? (wide ? lloyd_phase_kernel<double, true> : lloyd_phase_kernel<double, false>)
+                                       : (wide ? lloyd_phase_kernel<float, true> : lloyd_phase_kernel<float, false>);
+  const size_t smem = sp.bytes;
+  cudaError_t e;
+  if (smem > 48 * 1024) {
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { set_error("kmeans_lloyd_phase: smem attr: %s", cudaGetErrorString(e)); return CSB_ERR_CUDA; }
+  }
+  int dev = 0, sms = kNumSMs;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int64_t nf = sh->f_end - sh->f_begin;
+  int64_t nb = 1;
+  if (sh->phase == kLloydAssign) {
+    const int gpw = wide ? 1 : (k <= 32 ? 4 : (k <= 64 ? 2 : 1));
+    nb = (nf + (int64_t)gpw * kSolverWarps - 1) / ((int64_t)gpw * kSolverWarps);
+  } else if (sh->phase == kLloydInit || sh->phase == kLloydUpdate) {
+    nb = (nf * (k < 64 ? k : 64) + kSolverThreads * 4 - 1) / (kSolverThreads * 4);  // S rows: ~4 entries per thread and pass
+  }
+  if (nb > sms) nb = sms;
+  if (nb < 1) nb = 1;
+  void* args[] = {&a, &L};
+  if (sh->phase == kLloydUpdate) {
+    e = cudaMemsetAsync(a.barrier, 0, 4, s);
+    if (e != cudaSuccess) { set_error("kmeans_lloyd_phase: memset: %s", cudaGetErrorString(e)); return CSB_ERR_CUDA; }
+    e = cudaLaunchCooperativeKernel((const void*)kern, dim3((unsigned)nb), dim3(kSolverThreads), args, smem, s);
+  } else {
+    e = cudaLaunchKernel((const void*)kern, dim3((unsigned)nb), dim3(kSolverThreads), args, smem, s);
+  }
+  if (e != cudaSuccess) { set_error("kmeans_lloyd_phase: launch: %s", cudaGetErrorString(e)); return CSB_ERR_CUDA; }
   count_launch(1);
   return CSB_OK;
 }

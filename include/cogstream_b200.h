@@ -97,7 +97,7 @@ typedef struct csb_kmeans_params {
   int64_t T;              /* frames */
   int64_t k;              /* clusters, T > k >= 1 (T <= k is the caller's early return, :30-32) */
   int32_t ts_dtype;       /* CSB_F32 or CSB_F64: dtype of timestamps / centroid_times */
-  int32_t max_iteration;  /* :4  default 30 */
+  int32_t max_iteration;  /* :4  default 30; < 0: the k-means++ init only (the frame-sharded Lloyd phases follow) */
   double alpha;           /* :4  default 2 */
   double tol;             /* :4  default 1e-4 */
   int64_t n_init_given;   /* how many entries of init_indices are prescribed (>=1: the first centre is
@@ -156,6 +156,41 @@ CSB_API int csb_kmeans_solve(const double* G, const void* timestamps, const csb_
                      int64_t* assignments, void* centroid_times, int32_t* member_offsets, int32_t* members,
                      int32_t* event_order, int32_t* event_offsets, csb_kmeans_status* status, void* workspace,
                      size_t workspace_bytes, csb_stream_t stream);
+
+/* ---- frame-sharded Lloyd loop: ONE long stream over the GPUs of a box (first half) --------------------------
+ * Every rank holds G (the per-stream cache keeps it current) and runs the k-means++ init redundantly -- csb_kmeans_solve with
+ * max_iteration < 0 = init only (k - 1 dependent sampling rounds: nothing to shard).  The Lloyd iteration is split by frames:
+ * rank r owns frames [r * per_rank, min(T, (r + 1) * per_rank)).  The caller drives the phases and issues the collectives
+ * between them (NCCL all-gather over NVLink; the buffers are laid out rank-major so the gathers are in place):
+ *     CSB_LLOYD_INIT    S[0] rows of the own frames, state reset                 (after the init)
+ *   repeat until converged / max_iteration:
+ *     CSB_LLOYD_ASSIGN  distances + argmin of the own frames -> assign32[f_begin:f_end)        (kmeans_with_time.py:73-104)
+ *         all-gather assign32  [world * per_rank] int32
+ *     CSB_LLOYD_UPDATE  (identical on every rank) membership, centre times, re-seeds (:107-120); S rows of the own frames for
+ *                       the changed clusters; exchange[rank] = {S_nxt[i][a_i], S_cur[i][a_i] of the own frames, seed entries}
+ *         all-gather exchange  [world * (2 * per_rank + k)] fp64
+ *     CSB_LLOYD_SHIFT   (identical on every rank) ||c_j||^2, centre shift (:123-125), convergence flag -> state
+ *         read csb_kmeans_lloyd_converged (one small D2H per iteration, like the reference's `if shift <= tol`)
+ *     CSB_LLOYD_OUTPUT  the outputs of csb_kmeans_solve (assignments, centroid_times, CSR, event order, status)
+ * Same device functions and summation orders as csb_kmeans_solve: assignments, iterations, re-seeds, centre times bit-identical.
+ * All ranks must pass the same G, timestamps, init_indices, reseed_pool / rng_state contents. */
+enum { CSB_LLOYD_INIT = 1, CSB_LLOYD_ASSIGN = 2, CSB_LLOYD_UPDATE = 3, CSB_LLOYD_SHIFT = 4, CSB_LLOYD_OUTPUT = 5 };
+typedef struct csb_lloyd_shard {
+  int32_t phase;
+  int32_t reserved;
+  int64_t f_begin, f_end;  /* own frames */
+  int64_t per_rank;        /* frames per rank = ceil(T / world) (or any value with world * per_rank >= T) */
+  void* exchange;          /* device fp64 [world * (2 * per_rank + k)] */
+  void* state;             /* device, csb_kmeans_lloyd_state_bytes(T, k); int32 word 3 of its last 256 bytes = converged flag */
+  size_t state_bytes;
+} csb_lloyd_shard;
+CSB_API size_t csb_kmeans_lloyd_state_bytes(int64_t T, int64_t k);
+CSB_API int csb_kmeans_lloyd_phase(const double* G, const void* timestamps, const csb_kmeans_params* params /* host */,
+                           const csb_lloyd_shard* shard /* host */, int64_t* init_indices, const int64_t* reseed_pool,
+                           int32_t* assign32 /* [world * per_rank] */, int64_t* assignments, void* centroid_times,
+                           int32_t* member_offsets, int32_t* members, int32_t* event_order, int32_t* event_offsets,
+                           csb_kmeans_status* status, void* workspace /* csb_kmeans_workspace_bytes */, size_t workspace_bytes,
+                           csb_stream_t stream);
 
 /* Centroid features from the defining members: C[j] = (sum of member rows, ascending, fp32) / n_j.
  * kmeans_with_time.py:110-120, one pass over the member rows; atomic-free and deterministic. */

@@ -24,3 +24,9 @@ run config2_n4 4 bench.py --gpus 4 --no-cpu-baseline --steps 10
 run config3_n$N $N bench.py --gpus $N --workload config3 --steps 5 --no-cpu-baseline
 run config5_n$N $N bench.py --gpus $N --workload config5 --steps 10 --no-cpu-baseline
 run config4_n$N $N bench.py --gpus $N --workload config4 --steps 5 --no-cpu-baseline
+for np in 2 4 $N; do
+  port=$((port+1))
+  timeout 600 $TR --nproc-per-node $np --master-port $port scripts/sharded_config4.py >> gpurun_out/mg_sharded_config4.jsonl 2>> gpurun_out/mg_sharded_config4.err
+done
+timeout 300 python scripts/sharded_config4.py >> gpurun_out/mg_sharded_config4.jsonl 2>> gpurun_out/mg_sharded_config4.err
+cat gpurun_out/mg_sharded_config4.jsonl

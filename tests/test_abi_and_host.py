@@ -119,7 +119,8 @@ def test_custom_ops_registered_and_shape_inference():
         assert hasattr(torch.ops.cogstream_b200, name), name
     # every compute entry point of the header is reachable through the dispatcher (plumbing / workspace-size queries aside)
     covered = {"csb_" + n.replace("_hidden", "").replace("embed_scatter_ordered", "embed_scatter_ordered") for n in names}
-    plumbing = {"csb_abi_version", "csb_last_error", "csb_check_device", "csb_kernel_launches", "csb_pixel_diff_ex"}
+    plumbing = {"csb_abi_version", "csb_last_error", "csb_check_device", "csb_kernel_launches", "csb_pixel_diff_ex",
+                "csb_kmeans_lloyd_phase", "csb_kmeans_lloyd_state_bytes"}  # (driven by cogstream_b200.sharded, a multi-launch protocol)
     missing = [d for d in _declared() if d not in covered and d not in plumbing and not d.endswith("_workspace_bytes")]
     assert missing == [], missing
     m = torch.empty(12, dtype=torch.uint8, device="meta")
@@ -170,3 +171,14 @@ def test_install_rebinds_reference_names():
     sig = inspect.signature(compression.VisualStreamCompressionMixin.prepare_inputs_labels_for_multimodal)
     assert list(sig.parameters) == ["self", "input_ids", "attention_mask", "position_ids", "past_key_values", "labels",
                                     "pixel_values", "grid_sizes", "merge_sizes", "modals", "total_image_num", "if_visual"]
+
+
+def test_frame_range_partition():
+    from cogstream_b200 import frame_range
+    for T, world in ((14400, 8), (600, 7), (130, 8), (5, 8), (1000, 1)):
+        seen = []
+        for r in range(world):
+            per, b, e = frame_range(T, r, world)
+            assert per * world >= T and 0 <= b <= e <= T and e - b <= per and (b % per == 0 or b == e)
+            seen += list(range(b, e))
+        assert seen == list(range(T))

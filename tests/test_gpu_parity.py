@@ -1457,3 +1457,83 @@ def test_builtin_generator_samples_proportional_to_squared_distance(dev):
         firsts[n] = buf.init_indices[0]
     hist = torch.bincount(firsts.cpu(), minlength=4).tolist()
     assert min(hist) > 400 and max(hist) < 600, hist
+
+
+# ---- round 2: frame-sharded Lloyd loop -------------------------------------------------------------------------
+def _emulate_ranks(T, k, ts, G, world, dev, **kw):
+    """Drive `world` FrameShardedKMeans instances in lock step on one GPU; the all-gathers are emulated by copying the ranks' slices."""
+    from cogstream_b200 import FrameShardedKMeans
+    ranks = [FrameShardedKMeans(T, k, ts.dtype, dev, rank=r, world=world) for r in range(world)]
+    kws = []
+    for r in range(world):
+        kr = dict(kw)
+        if kr.get("rng_state") is not None:
+            kr["rng_state"] = kw["rng_state"].clone()  # same {seed, offset} on every rank, each advances its own copy
+        kws.append(kr)
+    gens = [km.phases(G, ts, **kr) for km, kr in zip(ranks, kws)]
+    n_coll = 0
+    while True:
+        step = []
+        for g in gens:
+            try:
+                step.append(next(g))
+            except StopIteration:
+                step.append(None)
+        if all(x is None for x in step):
+            break
+        assert all(x is not None for x in step), "ranks disagree on the number of collectives"
+        count = step[0][1]
+        full = torch.cat([buf[r * count: (r + 1) * count] for r, (buf, _) in enumerate(step)])
+        for buf, _ in step:
+            buf.copy_(full)
+        n_coll += 1
+    return ranks, n_coll
+
+
+@pytest.mark.parametrize("T,P,D,k,world,ts_dtype,dup", [
+    (600, 4, 64, 40, 2, torch.float64, False),
+    (600, 4, 64, 40, 8, torch.float64, True),    # duplicated centres -> empty clusters -> re-seeds (seed frames owned by other ranks)
+    (333, 2, 32, 23, 3, torch.float32, True),    # T not divisible by world, float32 timestamps
+    (520, 1, 32, 200, 4, torch.float64, True),   # k > 128: the WIDE assignment pass
+    (130, 2, 32, 9, 8, torch.float64, False),    # 17 frames per rank, the last rank owns 11
+    (2300, 2, 32, 154, 4, torch.float64, False), # long stream: row-streaming S kernel, grid k-means++
+])
+def test_frame_sharded_lloyd_equals_single_gpu(dev, T, P, D, k, world, ts_dtype, dup):
+    """The frame-sharded Lloyd loop (ranks emulated in lock step on one GPU, collectives = slice copies) gives bit-identical
+    assignments, iteration count, re-seed count, centre times, CSR and event order to csb_kmeans_solve, with injected centres and
+    with the built-in generator (replicated k-means++)."""
+    feats, _ = synthetic.make_features(T, P, D, T + k)
+    x2 = feats.view(T, -1).to(dev)
+    G = ops.gram(x2)
+    ts = (torch.arange(T, dtype=torch.float64) / 2.0).to(ts_dtype).to(dev)
+    g = torch.Generator().manual_seed(T)
+    init = torch.randperm(T, generator=g)[:k]
+    if dup:
+        init[k // 2:] = init[0]  # half of the centres coincide: ties go to the lowest index, the rest start empty
+    pool = torch.randint(0, T, (k * 31,), generator=g).to(dev)
+    for mode in ("injected", "rng"):
+        ref = ops.KMeansBuffers(T, k, ts_dtype, dev)
+        if mode == "injected":
+            ref.init_indices.copy_(init)
+            ops.kmeans_solve(G, ts, ref, n_init_given=k, exp_noise=None, reseed_pool=pool)
+            ranks, n_coll = _emulate_ranks(T, k, ts, G, world, dev, init_indices=init, reseed_pool=pool)
+        else:
+            state = torch.tensor([77 + T, 3], dtype=torch.int64, device=dev)
+            ops.kmeans_solve(G, ts, ref, n_init_given=0, exp_noise=None, reseed_pool=None, rng_state=state.clone())
+            ranks, n_coll = _emulate_ranks(T, k, ts, G, world, dev, rng_state=state)
+        want = ops.decode_status(ref.status)
+        assert n_coll == 2 * want["iterations"]
+        if mode == "injected" and dup:
+            assert want["n_reseed_used"] > 0
+        for km in ranks:
+            got = ops.decode_status(km.buf.status)
+            assert (got["iterations"], got["converged"], got["n_reseed_used"], got["degenerate_rounds"]) == \
+                (want["iterations"], want["converged"], want["n_reseed_used"], want["degenerate_rounds"]), (mode, km.rank)
+            assert torch.equal(km.buf.init_indices, ref.init_indices)
+            assert torch.equal(km.buf.assignments, ref.assignments), (mode, km.rank)
+            assert torch.equal(km.buf.centroid_times, ref.centroid_times)
+            assert torch.equal(km.buf.member_offsets, ref.member_offsets)
+            n = int(ref.member_offsets[-1])
+            assert torch.equal(km.buf.members[:n], ref.members[:n])
+            assert torch.equal(km.buf.event_offsets, ref.event_offsets) and torch.equal(km.buf.event_order, ref.event_order)
+            assert got["min_margin"] == want["min_margin"]
