@@ -1151,9 +1151,10 @@ __device__ double shift_pass(const SolverArgs& a, const int* s_offs, const int* 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   // single GPU (per == 0): vn / vc = the new / old S, entry (member m, cluster j) = S[m][j].
   // frame-sharded (per > 0): vn = the exchange buffer [world][2 * per + k]; rank r's segment holds S_nxt[i][a_i] and S_cur[i][a_i] of
-  // its frames i (planes of `per`) and, for a re-seeded (empty) cluster j whose seed frame it owns, S_cur[seed][j] at 2 * per + j;
-  // the seed's new entry S_nxt[seed][j] is the Gram diagonal.
-  const int64_t seg = 2 * (int64_t)per + k;
+  // its frames i (planes of `per`) and, for a re-seeded (empty) cluster j whose seed frame it owns, S_cur[seed][j] at 2 * per + j
+  // (the last slot, 2 * per + k, carries the rank's running decision margin); the seed's new entry S_nxt[seed][j] is the Gram
+  // diagonal.
+  const int64_t seg = 2 * (int64_t)per + k + 1;
   auto at_new = [&](int m, int j) -> double {
     if (per == 0) return __ldcg(vn + (int64_t)m * k + j);
     if (cnt_real[j] == 0) return __ldcg(a.G + (int64_t)m * a.ldg + m);
@@ -1419,7 +1420,7 @@ __global__ void __launch_bounds__(kSolverThreads, WIDE ? 1 : 2) kmeans_solver_ke
 // centre times are bit-identical to the single-GPU solve.
 // ---------------------------------------------------------------------------------------------------------------------------------
 enum { kLloydInit = 1, kLloydAssign = 2, kLloydUpdate = 3, kLloydShift = 4, kLloydOutput = 5 };
-enum { kScCur = 0, kScIt = 1, kScUsed = 2, kScConverged = 3, kScLastShift = 4, kScMargin = 5 };
+enum { kScCur = 0, kScIt = 1, kScUsed = 2, kScConverged = 3, kScLastShift = 4, kScMargin = 5, kScGlobalMargin = 6 };
 
 struct LloydState {
   double* q[2];      // [k]
@@ -1548,7 +1549,7 @@ __global__ void __launch_bounds__(kSolverThreads, 1) lloyd_phase_kernel(SolverAr
     compute_S(a, s_offs, s_memb, s_cols, s_ncols, a.S[nxt], L.f_begin, L.f_end);
     grid_sync(a.barrier, bar, nb);
     // exchange planes: what the (replicated) shift pass needs of this rank's rows
-    const int64_t seg = 2 * (int64_t)L.per + k;
+    const int64_t seg = 2 * (int64_t)L.per + k + 1;
     for (int i = L.f_begin + blockIdx.x * blockDim.x + threadIdx.x; i < L.f_end; i += nb * blockDim.x) {
       const int ai = s_assign[i];
       const int r = i / L.per, o = i - r * L.per;
@@ -1568,6 +1569,7 @@ __global__ void __launch_bounds__(kSolverThreads, 1) lloyd_phase_kernel(SolverAr
         }
         L.xch[rme * seg + 2 * L.per + j] = v;
       }
+      if (threadIdx.x == 0) L.xch[rme * seg + 2 * L.per + k] = (double)__int_as_float(L.scal[kScMargin]);  // own frames' margin so far
     }
     if (blockIdx.x == 0) {
       for (int j = threadIdx.x; j < k; j += blockDim.x) {
@@ -1600,6 +1602,10 @@ __global__ void __launch_bounds__(kSolverThreads, 1) lloyd_phase_kernel(SolverAr
     __syncthreads();
     for (int j = threadIdx.x; j < k; j += blockDim.x) { L.q[nxt][j] = s_q[nxt][j]; L.rn[j] = s_rn[j]; L.nn[j] = s_nn[j]; }
     if (threadIdx.x == 0) {
+      float mg = __int_as_float(0x7f800000);  // smallest decision margin over all ranks' frames (diagnostic of csb_kmeans_status)
+      const int64_t seg = 2 * (int64_t)L.per + k + 1;
+      for (int r = 0; r * L.per < T; ++r) mg = fminf(mg, (float)__ldcg(L.xch + r * seg + 2 * L.per + k));
+      L.scal[kScGlobalMargin] = __float_as_int(mg);
       L.scal[kScCur] = nxt;
       L.scal[kScIt] = L.scal[kScIt] + 1;
       L.scal[kScConverged] = shift <= a.tol ? 1 : 0;  // :130
@@ -1619,7 +1625,7 @@ __global__ void __launch_bounds__(kSolverThreads, 1) lloyd_phase_kernel(SolverAr
     if (L.scal[kScIt] > 0)
       for (int i = threadIdx.x; i < T; i += blockDim.x) a.assignments[i] = L.assign_prev[i];  // (:104 of the last iteration)
     __syncthreads();
-    solver_outputs<TS>(a, s_offs, s_memb, s_ctb[cur], s_cntw, s_cursor, __int_as_float(L.scal[kScMargin]), L.scal[kScIt],
+    solver_outputs<TS>(a, s_offs, s_memb, s_ctb[cur], s_cntw, s_cursor, __int_as_float(L.scal[kScIt] > 0 ? L.scal[kScGlobalMargin] : 0x7f800000), L.scal[kScIt],
                        L.scal[kScConverged] != 0, L.scal[kScUsed], __int_as_float(L.scal[kScLastShift]));
   }
 }

@@ -8,7 +8,7 @@ costs the new tiles only) and
     the same generator state, so they pick the same centres;
   * splits the Lloyd iteration by FRAMES: rank ``r`` owns frames ``[r * per, (r + 1) * per)`` and computes their distance /
     assignment pass and their rows of the sum-of-Gram-columns matrix S only.  Two NCCL all-gathers per iteration (over NVLink):
-    the int32 assignments ``[T]`` and, per frame, the two S entries the centre-shift needs ``[2 T + world * k]`` fp64;
+    the int32 assignments ``[T]`` and, per frame, the two S entries the centre-shift needs ``[world * (2 per + k + 1)]`` fp64;
     membership, centre times, re-seeds, ||c||^2 and the convergence test are evaluated identically on every rank.
 
 Same device functions and summation orders as the single-GPU solver (``csb_kmeans_solve``): assignments, iteration count,
@@ -49,7 +49,7 @@ class FrameShardedKMeans:
         self.per, self.f_begin, self.f_end = frame_range(T, rank, world)
         self.buf = ops.KMeansBuffers(T, k, ts_dtype, self.device)
         self.assign32 = torch.zeros(world * self.per, dtype=torch.int32, device=self.device)
-        self.seg = 2 * self.per + k
+        self.seg = 2 * self.per + k + 1
         self.exchange = torch.zeros(world * self.seg, dtype=torch.float64, device=self.device)
         self.state = torch.zeros(int(_lib.load().csb_kmeans_lloyd_state_bytes(T, k)), dtype=torch.uint8, device=self.device)
         self._flags = self.state[-256:].view(torch.int32)[:8]

@@ -168,7 +168,7 @@ CSB_API int csb_kmeans_solve(const double* G, const void* timestamps, const csb_
  *         all-gather assign32  [world * per_rank] int32
  *     CSB_LLOYD_UPDATE  (identical on every rank) membership, centre times, re-seeds (:107-120); S rows of the own frames for
  *                       the changed clusters; exchange[rank] = {S_nxt[i][a_i], S_cur[i][a_i] of the own frames, seed entries}
- *         all-gather exchange  [world * (2 * per_rank + k)] fp64
+ *         all-gather exchange  [world * (2 * per_rank + k + 1)] fp64
  *     CSB_LLOYD_SHIFT   (identical on every rank) ||c_j||^2, centre shift (:123-125), convergence flag -> state
  *         read csb_kmeans_lloyd_converged (one small D2H per iteration, like the reference's `if shift <= tol`)
  *     CSB_LLOYD_OUTPUT  the outputs of csb_kmeans_solve (assignments, centroid_times, CSR, event order, status)
@@ -180,7 +180,7 @@ typedef struct csb_lloyd_shard {
   int32_t reserved;
   int64_t f_begin, f_end;  /* own frames */
   int64_t per_rank;        /* frames per rank = ceil(T / world) (or any value with world * per_rank >= T) */
-  void* exchange;          /* device fp64 [world * (2 * per_rank + k)] */
+  void* exchange;          /* device fp64 [world * (2 * per_rank + k + 1)] */
   void* state;             /* device, csb_kmeans_lloyd_state_bytes(T, k); int32 word 3 of its last 256 bytes = converged flag */
   size_t state_bytes;
 } csb_lloyd_shard;

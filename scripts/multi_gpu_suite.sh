@@ -11,7 +11,7 @@ run() { # name nproc args...
   echo "$name rc=$?"; tail -c 300 gpurun_out/mg_$name.json | head -c 300; echo
 }
 # copy-only probe: H2D / D2H per rank at 1, 2, 4, N ranks, default vs NUMA-local pinning
-for np in 1 2 4 $N; do
+for np in 1 4 $N; do
   for mode in default numa; do
     port=$((port+1))
     if [ "$np" = "1" ]; then PROBE_MODE=$mode timeout 120 python scripts/h2d_probe.py >> gpurun_out/mg_h2d_probe.jsonl 2>> gpurun_out/mg_h2d_probe.err
@@ -20,11 +20,10 @@ for np in 1 2 4 $N; do
 done
 cat gpurun_out/mg_h2d_probe.jsonl
 run config2_n$N $N bench.py --gpus $N --no-cpu-baseline
-run config2_n4 4 bench.py --gpus 4 --no-cpu-baseline --steps 10
 run config3_n$N $N bench.py --gpus $N --workload config3 --steps 5 --no-cpu-baseline
 run config5_n$N $N bench.py --gpus $N --workload config5 --steps 10 --no-cpu-baseline
 run config4_n$N $N bench.py --gpus $N --workload config4 --steps 5 --no-cpu-baseline
-for np in 2 4 $N; do
+for np in 2 $N; do
   port=$((port+1))
   timeout 600 $TR --nproc-per-node $np --master-port $port scripts/sharded_config4.py >> gpurun_out/mg_sharded_config4.jsonl 2>> gpurun_out/mg_sharded_config4.err
 done
