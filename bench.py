@@ -964,8 +964,12 @@ def _roofline(stages, sc, ms_stream=None, ms_single=None):
     dom = max((n for n in stages if n in alg_bytes), key=lambda n: stages[n])
     gram_flops = T * (T + 1) * K  # 2 * (T(T+1)/2 unique entries) * K
     gram_tf = gram_flops / (stages["gram"] * 1e-3) / 1e12
+    def _traffic(name):  # dram__bytes_read.sum + dram__bytes_write.sum per launch, from the committed ncu --set full capture
+        t = traffic.get(name)
+        return t.get("total") if isinstance(t, dict) else t
+
     roof = dict(bound="hbm", kernel=_KERNEL_OF_STAGE.get(dom, dom), stage=dom, achieved=per[dom]["gbs"], peak=pk["hbm_gbs"], unit="GB/s",
-                frac=per[dom]["frac"], traffic=traffic.get(dom), algorithmic_bytes=alg_bytes[dom], ms=stages[dom])
+                frac=per[dom]["frac"], traffic=_traffic(dom), algorithmic_bytes=alg_bytes[dom], ms=stages[dom])
     if dom == "kmeans_solve":
         roof["note"] = ("latency-bound: k-1 dependent k-means++ sampling rounds + the Lloyd iterations (grid barriers) on the L2-resident "
                         "2.9 MB Gram matrix; neither the HBM nor the tensor roofline is approached by construction.  Several streams in "
@@ -974,6 +978,8 @@ def _roofline(stages, sc, ms_stream=None, ms_single=None):
         roof.update(bound="tensor", achieved=gram_tf, peak=pk["bf16_tflops"], unit="TFLOP/s", frac=gram_tf / pk["bf16_tflops"],
                     algorithmic_flops=gram_flops, hbm_view=per["gram"])
     roof["peaks"] = pk["source"]
+    for n in per:
+        per[n]["traffic"] = _traffic(n)
     roof["per_kernel_hbm"] = per
     roof["gram_tensor"] = dict(ms=stages["gram"], tflops=round(gram_tf, 1), frac_of_burst=round(gram_tf / pk["bf16_tflops"], 3),
                                algorithmic_flops=gram_flops)
