@@ -22,7 +22,8 @@ sc = StreamCompressor(T, P, D, st.pixel_values.numel() // (T * P), st.input_ids.
 torch.manual_seed(1234)
 random.seed(1234)
 for i in range(steps):
-    sc.phase1(d.features, d.timestamps, pixel_values=d.pixel_values)  # the pixel-difference mask runs next to the solver
+    # the pixel-difference mask runs next to the solver (CSB_NOEARLY=1: serial, for a clean solver timeline)
+    sc.phase1(d.features, d.timestamps, pixel_values=None if os.environ.get("CSB_NOEARLY") else d.pixel_values)
     sc.phase2(d.features, ev, q, d.pixel_values, d.input_ids, d.attention_mask)
 torch.cuda.synchronize()
 r = sc.results()
