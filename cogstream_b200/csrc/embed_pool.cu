@@ -68,6 +68,84 @@ __global__ void __launch_bounds__(kRankThreads) ids_rank_kernel(const int64_t* _
   }
 }
 
+// Multi-CTA form for long id sequences (the k packed event prompts: 1e5+ ids): a CTA ranks kRankChunk ids (relative prefixes per
+// 32-id chunk + its total); the last CTA to finish turns the totals into exclusive bases.  The scatter kernel adds the two.
+constexpr int kRankChunk = 4096;
+
+__global__ void __launch_bounds__(kRankThreads) ids_rank_multi_kernel(const int64_t* __restrict__ ids, int64_t n, int64_t image_token, int64_t vocab,
+                                                                      int32_t* __restrict__ chunk_prefix, int32_t* __restrict__ cta_base,
+                                                                      int32_t* __restrict__ cta_bad, unsigned* ticket, int32_t* __restrict__ status) {
+  __shared__ int s_warp[kRankThreads / 32];
+  __shared__ int s_run, s_bad, s_last;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) { s_run = 0; s_bad = 0; }
+  __syncthreads();
+  const int64_t begin = (int64_t)blockIdx.x * kRankChunk, end = min(n, begin + kRankChunk);
+  int bad = 0;
+  for (int64_t base = begin; base < end; base += kRankThreads) {
+    const int64_t i = base + threadIdx.x;
+    const int64_t id = i < end ? ids[i] : -1;
+    const bool img = i < end && id == image_token;
+    if (i < end && (id < 0 || id >= vocab)) ++bad;
+    const unsigned bal = __ballot_sync(0xffffffffu, img);
+    if (lane == 0) s_warp[warp] = __popc(bal);
+    __syncthreads();
+    int v = s_warp[lane];
+    int inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += t;
+    }
+    const int warp_excl = __shfl_sync(0xffffffffu, inc - v, warp);
+    const int total = __shfl_sync(0xffffffffu, inc, 31);
+    const int run = s_run;
+    if (lane == 0 && base + (int64_t)warp * 32 < end) chunk_prefix[(base >> 5) + warp] = run + warp_excl;  // relative to this CTA
+    __syncthreads();
+    if (threadIdx.x == 0) s_run = run + total;
+    __syncthreads();
+  }
+  bad = warp_sum(bad);
+  if (lane == 0 && bad) atomicAdd(&s_bad, bad);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    cta_base[blockIdx.x] = s_run;  // totals for now
+    cta_bad[blockIdx.x] = s_bad;
+    __threadfence();
+    s_last = (atomicAdd(ticket, 1u) == gridDim.x - 1) ? 1 : 0;
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  // exclusive scan of the CTA totals (gridDim.x <= 1024), one value per thread
+  const int nbk = gridDim.x;
+  int v = (int)threadIdx.x < nbk ? __ldcg(cta_base + threadIdx.x) : 0;
+  int b = (int)threadIdx.x < nbk ? __ldcg(cta_bad + threadIdx.x) : 0;
+  int inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += t;
+  }
+  b = warp_sum(b);
+  __syncthreads();
+  if (lane == 31) s_warp[warp] = inc;
+  if (threadIdx.x == 0) s_bad = 0;  // reused as the grand total of out-of-range ids
+  __syncthreads();
+  if (lane == 0 && b) atomicAdd(&s_bad, b);
+  int wbase = 0;
+  for (int w = 0; w < warp; ++w) wbase += s_warp[w];
+  if ((int)threadIdx.x < nbk) cta_base[threadIdx.x] = wbase + inc - v;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int tot = 0;
+    for (int w = 0; w < kRankThreads / 32; ++w) tot += s_warp[w];
+    status[0] = tot;
+    status[1] = s_bad;
+    *ticket = 0;
+  }
+}
+
 // x * 0.0 + f in the arithmetic of the tensor dtype (ATen evaluates the two ops separately, rounding after each)
 __device__ __forceinline__ uint32_t zero_mul_add_bf16x2(uint32_t e2, uint32_t f2) {
   const float e_lo = __uint_as_float(e2 << 16), e_hi = __uint_as_float(e2 & 0xffff0000u);
@@ -82,17 +160,47 @@ __global__ void __launch_bounds__(256) embed_scatter_kernel(const int64_t* __res
                                                             int64_t vocab, const uint4* __restrict__ table,
                                                             const uint4* __restrict__ feats, int64_t n_feats, int Dv,
                                                             const int32_t* __restrict__ chunk_prefix, uint4* __restrict__ out,
-                                                            const int32_t* __restrict__ frame_order, int tokens_per_frame) {
+                                                            const int32_t* __restrict__ frame_order, int tokens_per_frame,
+                                                            const int32_t* __restrict__ cta_base, int32_t* __restrict__ status) {
   __shared__ const uint4* s_src[kRowsPerCta];
   __shared__ int s_img[kRowsPerCta];
+  __shared__ int s_cnt[8], s_badc[8];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t row0 = (int64_t)blockIdx.x * kRowsPerCta;
+  int64_t prefix;
+  if (chunk_prefix) {
+    prefix = chunk_prefix[blockIdx.x] + (cta_base ? cta_base[row0 / kRankChunk] : 0);
+  } else {
+    // short id sequences (a single prompt): no rank kernel -- every CTA counts the <image> ids in front of its rows itself
+    // (the ids are L2-resident: n <= 16k ids = 128 KB); the last CTA thereby sees every id and writes the status words
+    const bool last = blockIdx.x == gridDim.x - 1;
+    int cnt = 0, bad = 0;
+    for (int64_t i = threadIdx.x; i < row0; i += blockDim.x) {
+      const int64_t id = __ldg(ids + i);
+      cnt += id == image_token;
+      bad += (id < 0 || id >= vocab);
+    }
+    cnt = warp_sum(cnt); bad = warp_sum(bad);
+    if (lane == 0) { s_cnt[warp] = cnt; s_badc[warp] = bad; }
+    __syncthreads();
+    int tot = 0, btot = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) { tot += s_cnt[w]; btot += s_badc[w]; }
+    prefix = tot;
+    if (last && warp == 0) {
+      const int64_t i = row0 + lane;
+      const int64_t id = i < n ? ids[i] : 0;
+      const int own = __popc(__ballot_sync(0xffffffffu, i < n && id == image_token));
+      const int ownbad = __popc(__ballot_sync(0xffffffffu, i < n && (id < 0 || id >= vocab)));
+      if (lane == 0) { status[0] = tot + own; status[1] = btot + ownbad; }
+    }
+  }
   if (warp == 0) {
     const int64_t i = row0 + lane;
     const int64_t id = i < n ? ids[i] : -1;
     const bool img = i < n && id == image_token;
     const unsigned bal = __ballot_sync(0xffffffffu, img);
-    const int64_t rank = (int64_t)chunk_prefix[blockIdx.x] + __popc(bal & ((1u << lane) - 1u));
+    const int64_t rank = prefix + __popc(bal & ((1u << lane) - 1u));
     const uint4* src = nullptr;  // nullptr -> zeros (id out of range, or more <image> ids than feature rows: flagged in status)
     if (img) {
       if (rank < n_feats) {
@@ -240,7 +348,8 @@ extern "C" {
 
 size_t csb_embed_scatter_workspace_bytes(int64_t n_ids) {
   if (n_ids <= 0) return 256;
-  return align_up256(sizeof(int32_t) * (size_t)((n_ids + 31) / 32 + 2));
+  const int64_t nbk = (n_ids + kRankChunk - 1) / kRankChunk;
+  return align_up256(sizeof(int32_t) * (size_t)((n_ids + 31) / 32 + 2)) + align_up256(sizeof(int32_t) * (size_t)(2 * nbk + 2)) + 256;
 }
 
 static int embed_scatter_impl(const int64_t* input_ids, int64_t n_ids, int64_t image_token_index, const void* embed_table, int64_t vocab,
@@ -261,20 +370,44 @@ static int embed_scatter_impl(const int64_t* input_ids, int64_t n_ids, int64_t i
     return CSB_ERR_WORKSPACE;
   }
   cudaStream_t s = as_stream(stream);
-  int32_t* prefix = reinterpret_cast<int32_t*>(workspace);
-  ids_rank_kernel<<<1, kRankThreads, 0, s>>>(input_ids, n_ids, image_token_index, vocab, prefix, status);
-  int st = check_launch("ids_rank");
-  if (st) return st;
   const unsigned grid = (unsigned)((n_ids + kRowsPerCta - 1) / kRowsPerCta);
   const int Dv = (int)(D / per);
+  // ranks of the <image> ids: computed inside the scatter kernel for a single prompt, by a multi-CTA rank kernel for long packed
+  // sequences (CSB_EMBED_RANK=1: the single-CTA rank kernel, kept as the validation path)
+  const int32_t* prefix = nullptr;
+  const int32_t* cta_base = nullptr;
+  const char* force = getenv("CSB_EMBED_RANK");
+  if (force && atoi(force) == 1) {
+    int32_t* pf = reinterpret_cast<int32_t*>(workspace);
+    ids_rank_kernel<<<1, kRankThreads, 0, s>>>(input_ids, n_ids, image_token_index, vocab, pf, status);
+    int st = check_launch("ids_rank");
+    if (st) return st;
+    prefix = pf;
+  } else if (n_ids > 16384 || (force && atoi(force) == 2)) {
+    char* w = reinterpret_cast<char*>(workspace);
+    int32_t* pf = reinterpret_cast<int32_t*>(w);
+    w += align_up256(sizeof(int32_t) * (size_t)((n_ids + 31) / 32 + 2));
+    const int64_t nbk = (n_ids + kRankChunk - 1) / kRankChunk;
+    CSB_REQUIRE(nbk <= kRankThreads, "embed_scatter: more than 4M ids");
+    int32_t* cb = reinterpret_cast<int32_t*>(w);
+    int32_t* cbad = cb + nbk;
+    unsigned* ticket = reinterpret_cast<unsigned*>(w + align_up256(sizeof(int32_t) * (size_t)(2 * nbk + 2)));
+    cudaError_t e = cudaMemsetAsync(ticket, 0, 4, s);
+    if (e != cudaSuccess) { set_error("embed_scatter: memset: %s", cudaGetErrorString(e)); return CSB_ERR_CUDA; }
+    ids_rank_multi_kernel<<<(unsigned)nbk, kRankThreads, 0, s>>>(input_ids, n_ids, image_token_index, vocab, pf, cb, cbad, ticket, status);
+    int st = check_launch("ids_rank_multi");
+    if (st) return st;
+    prefix = pf;
+    cta_base = cb;
+  }
   if (dtype == CSB_BF16)
     embed_scatter_kernel<true><<<grid, 256, 0, s>>>(input_ids, n_ids, image_token_index, vocab, (const uint4*)embed_table,
                                                      (const uint4*)features, n_features, Dv, prefix, (uint4*)out, frame_order,
-                                                     (int)tokens_per_frame);
+                                                     (int)tokens_per_frame, cta_base, status);
   else
     embed_scatter_kernel<false><<<grid, 256, 0, s>>>(input_ids, n_ids, image_token_index, vocab, (const uint4*)embed_table,
                                                       (const uint4*)features, n_features, Dv, prefix, (uint4*)out, frame_order,
-                                                      (int)tokens_per_frame);
+                                                      (int)tokens_per_frame, cta_base, status);
   return check_launch("embed_scatter");
 }
 

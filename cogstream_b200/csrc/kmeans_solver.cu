@@ -49,8 +49,8 @@ struct SolverArgs {
   int multiwarp_fill; // 1: per-warp cluster counters fit in shared memory
   const unsigned long long* rng;  // device {seed, offset} of the built-in generator, or nullptr (noise / pool supplied by the caller)
   int fused_init;     // 1: CTA 0 of the solver runs the k-means++ init itself (no separate kmeanspp launch)
-  float* noise_ws;    // [(k-1), T] or nullptr: rows >= kNoiseInlineRows of the built-in generator's noise, filled by CTAs 1.. of the
-                      // fused launch while CTA 0 already runs the first sampling rounds
+  float* noise_ws;    // [(k-1), T] or nullptr: the built-in generator's noise, filled by CTAs 1.. of the fused launch while CTA 0
+                      // sets up (it waits for them before its first sampling round)
   unsigned* noise_ready;  // arrival counter of those CTAs
   int init_exact;     // validation switch (CSB_INIT_EXACT): every sampling round evaluates the exact IEEE scores
   int32_t* assign32;  // [T] compact copy of the assignments (what every CTA reloads after the barrier)
@@ -116,8 +116,6 @@ __device__ __forceinline__ float exp1_from_bits(uint32_t x) {
 }
 constexpr uint32_t kRngFirst = 0xFFFFFFFFu, kRngReseed = 0xFFFFFFFEu;  // streams; sampling round r uses stream r
 
-constexpr int kNoiseInlineRows = 2;  // sampling rounds whose noise the init CTA generates itself while the others fill noise_ws
-
 struct RngKey {
   unsigned long long seed, offset;
 };
@@ -127,14 +125,26 @@ __device__ __forceinline__ RngKey load_rng(const SolverArgs& a) {
   k.offset = a.rng ? a.rng[1] : 0ull;
   return k;
 }
-// Exp(1) noise of sampling round `row` for frame i: the caller's array, or the built-in generator
-__device__ __forceinline__ float noise_at(const SolverArgs& a, const RngKey& rk, int row, int i) {
-  if (a.exp_noise) return __ldg(a.exp_noise + (int64_t)row * a.T + i);
-  if (a.noise_ws && row >= kNoiseInlineRows) return __ldcg(a.noise_ws + (int64_t)row * a.T + i);  // pre-generated by the idle CTAs
-  // frame i of sampling round `row`: component i & 3 of the call (i >> 2, row)
-  const uint4 x = philox_draw4(rk.seed, rk.offset, (uint32_t)row, (uint32_t)(i >> 2));
+// Exp(1) noise of sampling round `row` for frame i from the built-in generator: component i & 3 of the call (i >> 2, row).
+// Out of line on purpose: inlined into the k-means++ round loop (three call sites) the Philox rounds cost the torch-noise path
+// 16 us per solve (register allocation / code size of the hot loop), although they never run there.
+__device__ __noinline__ float noise_generate(unsigned long long seed, unsigned long long offset, int row, int i) {
+  const uint4 x = philox_draw4(seed, offset, (uint32_t)row, (uint32_t)(i >> 2));
   const uint32_t w = (i & 2) ? ((i & 1) ? x.w : x.z) : ((i & 1) ? x.y : x.x);
   return exp1_from_bits(w);
+}
+// Exp(1) noise of sampling round `row` for frame i: the caller's array, the rows pre-generated by the idle CTAs, or the generator
+// The k-means++ round loop is instantiated once per noise source, so that the array paths carry none of the generator's code
+// (measured: with the generator reachable from the loop a solve takes 16 us longer even when it never runs):
+//   kNoiseArray  the caller's array (read-only for the kernel: ld.global.nc)
+//   kNoiseWs     rows pre-generated into the workspace by the idle CTAs of the fused launch (ld.global.cg: written in this kernel)
+//   kNoiseGen    generated on the spot (separate init kernels)
+enum { kNoiseArray = 0, kNoiseWs = 1, kNoiseGen = 2 };
+template <int SRC>
+__device__ __forceinline__ float noise_at(const SolverArgs& a, const RngKey& rk, int row, int i) {
+  if (SRC == kNoiseArray) return __ldg(a.exp_noise + (int64_t)row * a.T + i);
+  if (SRC == kNoiseWs) return __ldcg(a.noise_ws + (int64_t)row * a.T + i);
+  return noise_generate(rk.seed, rk.offset, row, i);
 }
 // n-th random.randint(0, T-1) draw: the caller's pool (flags an overflow), or the built-in generator
 __device__ __forceinline__ int reseed_at(const SolverArgs& a, const RngKey& rk, int n, bool* overflow) {
@@ -184,9 +194,9 @@ struct PPScratch {
   float ws[2][32];
 };
 
-template <int NT>
-__device__ void kmeanspp_block(const SolverArgs& a, float* s_near, const double* diag, PPScratch* sc, int* used_io,
-                               int* n_noise_used, int* n_degenerate) {
+template <int NT, int RNG>
+__device__ void kmeanspp_block_impl(const SolverArgs& a, float* s_near, const double* diag, PPScratch* sc, int* used_io,
+                                    int* n_noise_used, int* n_degenerate) {
   constexpr int NW = NT / 32;
   const int T = a.T, k = a.k;
   const double* G = a.G;
@@ -233,7 +243,7 @@ __device__ void kmeanspp_block(const SolverArgs& a, float* s_near, const double*
           for (int u = 0; u < 4; ++u) {
             const int ii = i0 + u * NT;
             nd[u] = ii < T ? s_near[ii] : 0.f;
-            nz[u] = nzp_valid ? nzp[u] : (ii < T ? noise_at(a, rk, this_row, ii) : 1.f);
+            nz[u] = nzp_valid ? nzp[u] : (ii < T ? noise_at<RNG>(a, rk, this_row, ii) : 1.f);
           }
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
@@ -281,7 +291,7 @@ __device__ void kmeanspp_block(const SolverArgs& a, float* s_near, const double*
               const int ii = i0 + u * NT;
               if (ii < T) {
                 const float ndv = s_near[ii];
-                const float nzv = nzp_valid ? nzp[u] : noise_at(a, rk, this_row, ii);
+                const float nzv = nzp_valid ? nzp[u] : noise_at<RNG>(a, rk, this_row, ii);
                 const float n2 = __fmul_rn(ndv, ndv);
                 // a zero numerator would send the warp down the IEEE division's slow path: substituted, result selected
                 const float p = __fdiv_rn(n2 == 0.f ? 1.f : n2, sum);  // :59
@@ -312,22 +322,14 @@ __device__ void kmeanspp_block(const SolverArgs& a, float* s_near, const double*
       const double gcc = diag[c];
       const double* gc = G + (int64_t)c * a.ldg;
       float part = 0.f;
-      if (a.noise_ws && !a.exp_noise && !ws_ready && noise_row >= kNoiseInlineRows && m + 1 >= a.n_init_given) {
-        // first use of a pre-generated row: the other CTAs finished them long ago (2 rounds = 3 us); make it formal
-        if (threadIdx.x == 0) {
-          unsigned v;
-          do {
-            asm volatile("ld.acquire.gpu.u32 %0, [%1];" : "=r"(v) : "l"(a.noise_ready) : "memory");
-          } while (v < gridDim.x - 1);
-        }
-        __syncthreads();
-        ws_ready = true;
-      }
-      if (prefetch_noise && m + 1 >= a.n_init_given) {  // row of the next sampling round (rows are consumed in order)
+      // the workspace rows are filled by the other CTAs during the first microseconds of the launch: the first fetch waits for
+      // them, and is issued after this round's update pass instead of next to its Gram row to give them that much longer
+      const bool late_fetch = RNG == kNoiseWs && !ws_ready && m + 1 >= a.n_init_given;
+      if (prefetch_noise && !late_fetch && m + 1 >= a.n_init_given) {  // row of the next sampling round (consumed in order)
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
           const int ii = threadIdx.x + u * NT;
-          nzp[u] = ii < T ? noise_at(a, rk, noise_row, ii) : 1.f;
+          nzp[u] = ii < T ? noise_at<RNG>(a, rk, noise_row, ii) : 1.f;
         }
         nzp_valid = true;
       }
@@ -353,12 +355,37 @@ __device__ void kmeanspp_block(const SolverArgs& a, float* s_near, const double*
       part = warp_sum(part);
       wsb ^= 1;
       if (lane == 0) sc->ws[wsb][warp] = part;
+      if (late_fetch && threadIdx.x == 0) {
+        unsigned v;
+        do {
+          asm volatile("ld.acquire.gpu.u32 %0, [%1];" : "=r"(v) : "l"(a.noise_ready) : "memory");
+        } while (v < gridDim.x - 1);
+      }
       __syncthreads();
+      if (late_fetch) {
+        ws_ready = true;
+        if (prefetch_noise) {
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int ii = threadIdx.x + u * NT;
+            nzp[u] = ii < T ? noise_at<RNG>(a, rk, noise_row, ii) : 1.f;
+          }
+          nzp_valid = true;
+        }
+      }
     }
   }
   *used_io = used;
   *n_noise_used = noise_row;
   *n_degenerate = degenerate;
+}
+
+template <int NT>
+__device__ __forceinline__ void kmeanspp_block(const SolverArgs& a, float* s_near, const double* diag, PPScratch* sc, int* used_io,
+                                               int* n_noise_used, int* n_degenerate) {
+  if (a.exp_noise) kmeanspp_block_impl<NT, kNoiseArray>(a, s_near, diag, sc, used_io, n_noise_used, n_degenerate);
+  else if (a.noise_ws) kmeanspp_block_impl<NT, kNoiseWs>(a, s_near, diag, sc, used_io, n_noise_used, n_degenerate);
+  else kmeanspp_block_impl<NT, kNoiseGen>(a, s_near, diag, sc, used_io, n_noise_used, n_degenerate);
 }
 
 // ---- membership CSR in shared memory from the new assignments (kmeans_with_time.py:110-120) ---------
@@ -728,7 +755,7 @@ __global__ void __launch_bounds__(kGridInitThreads) kmeanspp_grid_kernel(SolverA
 #pragma unroll
     for (int u = 0; u < kGridInitU; ++u) {
       g[u] = fi[u] >= 0 ? __ldg(gc + fi[u]) : 0.0;
-      nz[u] = (sample_next && fi[u] >= 0) ? noise_at(a, rk, noise_row, fi[u]) : 1.f;
+      nz[u] = (sample_next && fi[u] >= 0) ? (a.exp_noise ? noise_at<kNoiseArray>(a, rk, noise_row, fi[u]) : noise_at<kNoiseGen>(a, rk, noise_row, fi[u])) : 1.f;
     }
     float part = 0.f, n2[kGridInitU], uq[kGridInitU], umax = 0.f;
 #pragma unroll
@@ -1262,6 +1289,25 @@ __global__ void __launch_bounds__(kSolverThreads, WIDE ? 1 : 2) kmeans_solver_ke
   __shared__ PPScratch s_pp;
   if (a.fused_init) {
     // ---------------- k-means++ inside this launch: CTA 0 samples the centres while the other CTAs preload and wait ------------
+    if (blockIdx.x > 0 && a.noise_ws) {
+      // the idle CTAs pre-generate the Exp(1) noise of all sampling rounds (4 frames per Philox call) before anything else:
+      // CTA 0 needs the first row a few microseconds into the launch
+      const RngKey rk = load_rng(a);
+      const int q4 = (T + 3) >> 2;  // calls per row
+      const int64_t total = (int64_t)(k - 1) * q4;
+      for (int64_t e = (int64_t)(blockIdx.x - 1) * blockDim.x + threadIdx.x; e < total; e += (int64_t)(nb - 1) * blockDim.x) {
+        const int row = (int)(e / q4), c = (int)(e - (int64_t)(e / q4) * q4);
+        const uint4 x = philox_draw4(rk.seed, rk.offset, (uint32_t)row, (uint32_t)c);
+        float* dst = a.noise_ws + (int64_t)row * T + 4 * c;
+        const float v[4] = {exp1_from_bits(x.x), exp1_from_bits(x.y), exp1_from_bits(x.z), exp1_from_bits(x.w)};
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (4 * c + u < T) __stcg(dst + u, v[u]);
+      }
+      __threadfence();
+      __syncthreads();
+      if (threadIdx.x == 0) atomicAdd(a.noise_ready, 1u);
+    }
     for (int i = threadIdx.x; i < T; i += blockDim.x) {
       const double g = a.G[(int64_t)i * a.ldg + i];
       s_diag[i] = g;
@@ -1284,23 +1330,6 @@ __global__ void __launch_bounds__(kSolverThreads, WIDE ? 1 : 2) kmeans_solver_ke
         *a.used = used;
       }
       mark(a, 2);
-    } else if (a.noise_ws) {
-      // the idle CTAs pre-generate the Exp(1) noise of sampling rounds >= kNoiseInlineRows (4 frames per Philox call)
-      const RngKey rk = load_rng(a);
-      const int q4 = (T + 3) >> 2;  // calls per row
-      const int64_t total = (int64_t)(k - 1 - kNoiseInlineRows) * q4;
-      for (int64_t e = (int64_t)(blockIdx.x - 1) * blockDim.x + threadIdx.x; e < total; e += (int64_t)(nb - 1) * blockDim.x) {
-        const int row = kNoiseInlineRows + (int)(e / q4), c = (int)(e - (int64_t)(e / q4) * q4);
-        const uint4 x = philox_draw4(rk.seed, rk.offset, (uint32_t)row, (uint32_t)c);
-        float* dst = a.noise_ws + (int64_t)row * T + 4 * c;
-        const float v[4] = {exp1_from_bits(x.x), exp1_from_bits(x.y), exp1_from_bits(x.z), exp1_from_bits(x.w)};
-#pragma unroll
-        for (int u = 0; u < 4; ++u)
-          if (4 * c + u < T) __stcg(dst + u, v[u]);
-      }
-      __threadfence();
-      __syncthreads();
-      if (threadIdx.x == 0) atomicAdd(a.noise_ready, 1u);
     }
     grid_sync_backoff(a.barrier, bar, nb);
     used = __ldcg(a.used);
@@ -1793,7 +1822,8 @@ int csb_kmeans_solve(const double* G, const void* timestamps, const csb_kmeans_p
   if (nb > sms) nb = sms;
   if (nb < 1) nb = 1;
   // built-in generator + fused init + helpers to spare: CTAs 1.. pre-generate the noise rows while CTA 0 samples
-  a.noise_ws = (a.fused_init && a.rng && !exp_noise && nb > 1 && k - 1 > kNoiseInlineRows && p->n_init_given < k) ? noise_ws : nullptr;
+  a.noise_ws = (a.fused_init && a.rng && !exp_noise && nb > 1 && k > 1 && p->n_init_given < k &&
+                !getenv("CSB_NO_NOISE_WS")) ? noise_ws : nullptr;
   void* args[] = {&a};
   e = cudaLaunchCooperativeKernel((const void*)kern, dim3((unsigned)nb), dim3(kSolverThreads), args, smem, s);
   if (e != cudaSuccess) { set_error("kmeans_solve: launch: %s", cudaGetErrorString(e)); return CSB_ERR_CUDA; }

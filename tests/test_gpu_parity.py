@@ -1541,8 +1541,10 @@ def test_frame_sharded_lloyd_equals_single_gpu(dev, T, P, D, k, world, ts_dtype,
 
 def test_gram_long_stream_large_K_error(dev):
     """the direct-write path (more tiles than SMs, one K range per tile) carries a fp32 sum over K / 6144 accumulator
-    segments.  At K = 207,360 (P = 180 tokens of 1152 channels, 34 segments) and T = 2304 the error stays a scale-type error below
-    1e-5 of the diagonal -- what DESIGN.md 3.8 states -- and G is exactly symmetric."""
+    segments on top of the tensor core's truncating accumulation.  At K = 207,360 (P = 180 tokens of 1152 channels, 34 segments)
+    and T = 2304 the error is what DESIGN.md 3.8 states: a COMMON negative scale factor (measured -6.6e-6; chains restart per
+    segment, so it stays below the 384-MMA bound of 2.3e-5; the row-wise min-max normalisation of the distances cancels it) plus an
+    entry-wise residual (measured 1.3e-5 at most), both bounded by 3e-5 here; G is exactly symmetric."""
     T, K = 2304, 207360
     g = torch.Generator(device=dev).manual_seed(5)
     x = torch.empty(T, K, dtype=torch.bfloat16, device=dev)
@@ -1554,8 +1556,41 @@ def test_gram_long_stream_large_K_error(dev):
     ref = torch.empty(rows.numel(), T, dtype=torch.float64, device=dev)
     for c0 in range(0, T, 256):
         ref[:, c0: c0 + 256] = xr @ x[c0: c0 + 256].double().T
-    scale = float(G.diagonal().max())
-    err = float((G[rows] - ref).abs().max() / scale)
-    print(f"direct path, K={K}: max error {err:.2e} of the diagonal")
-    assert err < 1e-5
+    rel = (G[rows] - ref) / ref  # every entry is ~K/4 or larger here (inputs have mean 0.5)
+    drift = float(rel.median())
+    resid = float((rel - drift).abs().max())
+    print(f"direct path, K={K}: common drift {drift:.2e}, residual {resid:.2e}")
+    assert -3e-5 < drift <= 0.0
+    assert resid < 3e-5
     assert torch.equal(G, G.T)
+
+
+@pytest.mark.parametrize("n", [1, 33, 4099, 16384, 16385, 50000, 140003])
+def test_embed_scatter_rank_paths_agree(dev, monkeypatch, n):
+    """The three ways the <image>-id ranks are obtained (inside the scatter kernel for n <= 16k ids, the multi-CTA rank kernel for
+    longer packed sequences, the single-CTA kernel kept for validation) give identical rows and status words."""
+    D, vocab = 64, 97
+    gen = torch.Generator().manual_seed(n)
+    img = vocab - 1
+    ids = torch.randint(0, vocab - 1, (n,), generator=gen)
+    ids[torch.rand(n, generator=gen) < 0.7] = img
+    if n > 40:
+        ids[7] = vocab + 5  # an id outside the table: flagged in status[1], its row is zero
+    n_img = int((ids == img).sum())
+    w = torch.randn(vocab, D, generator=gen).to(torch.bfloat16).to(dev)
+    f = torch.randn(n_img, D, generator=gen).to(torch.bfloat16).to(dev)
+    outs = []
+    for mode in (None, "1", "2"):
+        if mode is None:
+            monkeypatch.delenv("CSB_EMBED_RANK", raising=False)
+        else:
+            monkeypatch.setenv("CSB_EMBED_RANK", mode)
+        o, st = ops.embed_scatter(ids.to(dev), img, w, f, check_count=False)
+        outs.append((o.clone(), st.tolist()))
+    monkeypatch.delenv("CSB_EMBED_RANK", raising=False)
+    assert outs[0][1] == [n_img, 1 if n > 40 else 0]
+    for o, st in outs[1:]:
+        assert st == outs[0][1] and torch.equal(o, outs[0][0])
+    want = orc.embed_scatter(torch.where(ids >= vocab, torch.zeros_like(ids), ids), img, w.cpu(), f.cpu())
+    ok = ids < vocab
+    assert torch.equal(outs[0][0].cpu()[ok], want[ok])
