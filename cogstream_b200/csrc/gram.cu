@@ -352,9 +352,9 @@ __global__ void __launch_bounds__(256) gram_simt_kernel(const __nv_bfloat16* __r
 // ---------------------------------------------------------------------------------------------------
 // Sum the K ranges in fp64 (fixed order) and write both triangles of G.
 // ---------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) gram_reduce_kernel(const float* __restrict__ partial, int T, int nb, int b0, int n_tiles,
-                                                          int n_kr, double* __restrict__ G, int64_t ldg,
-                                                          const __grid_constant__ GramFlipMask flips, int transposed_store) {
+__global__ void __launch_bounds__(512, 2) gram_reduce_kernel(const float* __restrict__ partial, int T, int nb, int b0, int n_tiles,
+                                                             int n_kr, double* __restrict__ G, int64_t ldg,
+                                                             const __grid_constant__ GramFlipMask flips, int transposed_store) {
   int tid = blockIdx.x, bj = b0;
   while (tid >= bj + 1) { tid -= bj + 1; ++bj; }
   int bi = tid;
@@ -363,47 +363,72 @@ __global__ void __launch_bounds__(256) gram_reduce_kernel(const float* __restric
   // block (flip bit): rows = block bj unless both or neither apply.
   const int flipped = (blockIdx.x < 192) ? (int)((flips.w[blockIdx.x >> 6] >> (blockIdx.x & 63)) & 1ull) : 0;
   if (flipped != transposed_store) { const int x = bi; bi = bj; bj = x; }
-  // grid (n_tiles, 32) x 256 threads: a lane pair owns 4 consecutive columns of one tile row; the even lane sums the even K
-  // ranges, the odd lane the odd ones (each in ascending order, all loads of a thread in flight at once), and the two halves
-  // are added even + odd: a fixed order, so G is deterministic.
+  // grid (n_tiles, 32) x 512 threads: the CTA owns 4 rows x 128 columns of its tile, a lane pair 2 consecutive columns of one
+  // row; the even lane sums the even K ranges, the odd lane the odd ones (each in ascending order), and the two halves are
+  // added even + odd: a fixed order, so G is deterministic.  Up to 40 K ranges (148 SMs / 4 units = 37 at config 2) every load
+  // of a thread is in flight at once -- one L2 round trip -- at 64 registers, i.e. with the whole grid resident.
   const int half = threadIdx.x & 1;
-  const int e4 = blockIdx.y * 128 + (threadIdx.x >> 1);  // float4 index inside the tile, 4096 per tile
-  const int r = e4 >> 5, c = (e4 & 31) * 4;
+  const int e2 = blockIdx.y * 256 + (threadIdx.x >> 1);  // float2 index inside the tile, 8192 per tile
+  const int r = e2 >> 6, c = (e2 & 63) * 2;
   const int gi = bi * kTile + r, gj = bj * kTile + c;
   const bool valid = gi < T && gj < T;  // no early return: the pair exchange below is a full-warp shuffle
   // launched with programmatic stream serialization: the blocks are resident before the Gram kernel ends; wait for its
   // completion (and the visibility of its partial tiles) here
   asm volatile("griddepcontrol.wait;" ::: "memory");
-  const float4* base = reinterpret_cast<const float4*>(partial + (int64_t)blockIdx.x * (kTile * kTile)) + e4;
-  const int64_t kr_stride4 = (int64_t)n_tiles * kTile * kTile / 4;
-  double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-  int kr = valid ? half : n_kr;
-  for (; kr + 2 * 7 < n_kr; kr += 2 * 8) {
-    float4 v[8];
+  // address = (uniform: tile base + 2u K ranges) + (per thread, 32 bits: element + the lane's parity range): one address register
+  const unsigned stride_b = (unsigned)n_tiles * (kTile * kTile * 4u);  // bytes between K ranges (< 2^31: n_tiles <= 136 x 64 KB)
+  const unsigned toff = (unsigned)e2 * 8u + (unsigned)half * stride_b;
+  const char* tbase = reinterpret_cast<const char*>(partial) + (size_t)blockIdx.x * (kTile * kTile * 4);
+  double s0 = 0.0, s1 = 0.0;
+  constexpr int kBatch = 20;
+  for (int k0 = 0; k0 < n_kr; k0 += 2 * kBatch) {
+    float2 v[kBatch];
+    const char* ub = tbase + (size_t)k0 * stride_b;
 #pragma unroll
-    for (int u = 0; u < 8; ++u) v[u] = __ldcs(base + (int64_t)(kr + 2 * u) * kr_stride4);
+    for (int u = 0; u < kBatch; ++u) {
+      const int kr = k0 + 2 * u + half;
+      v[u] = (valid && kr < n_kr) ? __ldcs(reinterpret_cast<const float2*>(ub + (size_t)(2 * u) * stride_b + toff)) : make_float2(0.f, 0.f);
+    }
+    // ascending order; the padding terms are +0.0 (x + 0.0 == x)
 #pragma unroll
-    for (int u = 0; u < 8; ++u) { s0 += (double)v[u].x; s1 += (double)v[u].y; s2 += (double)v[u].z; s3 += (double)v[u].w; }
-  }
-  for (; kr < n_kr; kr += 2) {
-    const float4 v = __ldcs(base + (int64_t)kr * kr_stride4);
-    s0 += (double)v.x; s1 += (double)v.y; s2 += (double)v.z; s3 += (double)v.w;
+    for (int u = 0; u < kBatch; ++u) { s0 += (double)v[u].x; s1 += (double)v[u].y; }
   }
   {
     const double o0 = __shfl_xor_sync(0xffffffffu, s0, 1), o1 = __shfl_xor_sync(0xffffffffu, s1, 1);
-    const double o2 = __shfl_xor_sync(0xffffffffu, s2, 1), o3 = __shfl_xor_sync(0xffffffffu, s3, 1);
     // even + odd on both lanes (commutative, so both lanes hold the same bits)
     s0 = half ? o0 + s0 : s0 + o0;
     s1 = half ? o1 + s1 : s1 + o1;
-    s2 = half ? o2 + s2 : s2 + o2;
-    s3 = half ? o3 + s3 : s3 + o3;
   }
-  const double sv[4] = {s0, s1, s2, s3};
-#pragma unroll
-  for (int u = 0; u < 4; ++u) {
-    if (valid && gj + u < T) {
-      if (!half) G[(int64_t)gi * ldg + gj + u] = sv[u];
-      else if (bi != bj) G[(int64_t)(gj + u) * ldg + gi] = sv[u];
+  // Stores.  Even lanes write their 2 consecutive doubles of G[gi][gj..] (a warp covers 256 contiguous bytes); the mirrored
+  // triangle is staged through shared memory so that the 4 rows of a column go out as one 32-byte run G[gj][gi0..gi0+3]
+  // (column-strided 8-byte stores from the registers touched one sector per element).
+  __shared__ double s_t[kTile][5];
+  const bool vec_ok = (ldg & 1) == 0 && (reinterpret_cast<uintptr_t>(G) & 15u) == 0;
+  if (valid && !half) {
+    double* g = G + (int64_t)gi * ldg + gj;
+    if (vec_ok && gj + 1 < T) {
+      *reinterpret_cast<double2*>(g) = make_double2(s0, s1);
+    } else {
+      g[0] = s0;
+      if (gj + 1 < T) g[1] = s1;
+    }
+  }
+  if (bi != bj) {  // uniform over the CTA
+    if (half) { s_t[c][r & 3] = s0; s_t[c + 1][r & 3] = s1; }
+    __syncthreads();
+    if (threadIdx.x < kTile) {
+      const int col = threadIdx.x;
+      const int gi0 = bi * kTile + blockIdx.y * 4, gc = bj * kTile + col;
+      if (gc < T && gi0 < T) {
+        double* g = G + (int64_t)gc * ldg + gi0;
+        if (vec_ok && gi0 + 3 < T) {
+          *reinterpret_cast<double2*>(g) = make_double2(s_t[col][0], s_t[col][1]);
+          *reinterpret_cast<double2*>(g + 2) = make_double2(s_t[col][2], s_t[col][3]);
+        } else {
+          for (int u = 0; u < 4; ++u)
+            if (gi0 + u < T) g[u] = s_t[col][u];
+        }
+      }
     }
   }
 }
@@ -1212,7 +1237,7 @@ int csb_gram_extend(const void* x, int64_t T_old, int64_t T, int64_t K, double* 
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = rgrid;
-  cfg.blockDim = dim3(256);
+  cfg.blockDim = dim3(512);
   cfg.stream = s;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;

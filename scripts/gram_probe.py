@@ -6,14 +6,17 @@ T, P, D = int(os.environ.get('T', 600)), int(os.environ.get('P', 180)), 1152
 x = synthetic.make_features(T, P, D, 0)[0].view(T, -1).cuda()
 G = torch.empty(T, T, dtype=torch.float64, device="cuda")
 ws = torch.empty(ops.gram_workspace_bytes(T, P * D), dtype=torch.uint8, device="cuda")
-for name, impl in [("full", 0), ("no-mma (loads only)", 16), ("no-tma (mma only)", 32), ("reduce kernel only", 256), ("full", 0)]:
+# NOTE: these are wall-clock times of back-to-back calls.  A full call is GPU-bound (Gram kernel ~80 us + reduce ~6 us on the stream);
+# the "reduce kernel only" line is HOST-bound (~15 us per call: tensor-map encode + two launches), it says nothing about the
+# reduce kernel, which takes ~6 us of GPU time (measured by replacing it with an empty kernel: full 86.2 -> 80.4 us).
+for name, impl in [("full", 0), ("no-mma (loads only)", 16), ("no-tma (mma only)", 32), ("reduce kernel only (host-bound)", 256), ("full", 0)]:
     for _ in range(3): ops.gram(x, impl=impl, out=G, workspace=ws)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(20): ops.gram(x, impl=impl, out=G, workspace=ws)
     e1.record(); torch.cuda.synchronize()
-    print(f"{name:22s} {e0.elapsed_time(e1)/20*1e3:7.1f} us (incl. ~13 us reduce kernel)")
+    print(f"{name:32s} {e0.elapsed_time(e1)/20*1e3:7.1f} us per call (Gram kernel + ~6 us reduce kernel)")
 
 # per-CTA time marks (impl bit 7): where the kernel time goes
 import numpy as np
