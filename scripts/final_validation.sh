@@ -1,0 +1,14 @@
+#!/bin/bash
+# End-of-round validation on one B200 (run through gpurun from the repo root): full GPU test suite, smoke, the default bench line,
+# the CPU reference arm, the solver timeline, then -- only after the plain program exited 0 -- the ncu launch list of the same program.
+# Usage: bash scripts/final_validation.sh <tag>     (outputs: gpurun_out/<tag>_*)
+tag=${1:-r2f}
+mkdir -p gpurun_out
+timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/${tag}_tests.log 2>&1; echo "tests rc=$?"; tail -3 gpurun_out/${tag}_tests.log
+timeout 300 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" > gpurun_out/${tag}_smoke.log 2>&1; echo "smoke rc=$?"; tail -2 gpurun_out/${tag}_smoke.log
+timeout 600 python bench.py > gpurun_out/${tag}_bench.json 2> gpurun_out/${tag}_bench.err; echo "bench rc=$?"; cut -c1-400 gpurun_out/${tag}_bench.json
+timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/${tag}_bench_ref.json 2> gpurun_out/${tag}_bench_ref.err; echo "ref rc=$?"; cut -c1-300 gpurun_out/${tag}_bench_ref.json
+CSB_NOEARLY=1 CSB_TIMELINE=1 timeout 300 python scripts/profile_step.py 3 > gpurun_out/${tag}_timeline.txt 2>&1; echo "timeline rc=$?"
+timeout 300 python scripts/profile_step.py 3 > gpurun_out/${tag}_plain.log 2>&1 && \
+  timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${tag}_launches.csv \
+    python scripts/profile_step.py 3 > gpurun_out/${tag}_ncu1.log 2>&1; echo "ncu launches rc=$?"

@@ -1286,6 +1286,31 @@ def test_early_pixel_diff_overlapped_with_solver(dev):
         assert torch.equal(ops.pixel_diff(d.pixel_values, T, P, W, max_ctas=ctas, evict_first=ef), raw)
 
 
+def test_pipeline_without_centroid_pass(dev):
+    """StreamConfig(compute_centroids=False): the fp32 centroids (kmeans_with_time.py:134) are not materialised; every other
+    output of the fused path is identical (the representatives come from the Gram matrix, cogreasoner_chat.py:50-64)."""
+    T, P, D = 300, 12, 128
+    k = math.ceil(T / 15)
+    st = synthetic.make_stream(T, P, D, 11, C=32, near_threshold_frac=0.1)
+    ev, q = synthetic.make_embeddings(k, 256, 11)
+    d = st.to(dev)
+    W = st.pixel_values.numel() // (T * P)
+    init = torch.randperm(T, generator=torch.Generator().manual_seed(11))[:k].to(dev)
+    outs = []
+    for cc in (True, False):
+        sc = StreamCompressor(T, P, D, W, st.input_ids.numel(), device=dev, cfg=StreamConfig(compute_centroids=cc))
+        sc.phase1(d.features, d.timestamps, init_indices=init, pixel_values=d.pixel_values)
+        sc.phase2(d.features, ev.to(dev), q.to(dev), d.pixel_values, d.input_ids, d.attention_mask)
+        r = sc.results()
+        assert (r["centroids"] is not None) == cc
+        outs.append(r)
+    a, b = outs
+    for key in ("assignments", "centroid_times", "mask", "features", "input_ids", "attention_mask", "cos", "low_flags"):
+        assert torch.equal(a[key], b[key]), key
+    assert a["minor"] == b["minor"] and a["n_kept"] == b["n_kept"]
+    assert all(torch.equal(x, y) for x, y in zip(a["representatives"], b["representatives"]))
+
+
 def test_pipeline_multi_item_inputs(dev):
     """Several visual items in one prompt (cogreasoner_chat.py:392-430): video segments (each its own pixel-difference segment, first
     frame fully kept), an image and a single-frame video (all tokens kept, no minor-frame override in the mask, token 0 still
