@@ -925,9 +925,10 @@ def _stage_times(sc, d, ev_d, q_d, reps=5):
 
 
 def _neighbour_ops(sc, d, reps=5):
-    """The two ops on either side of the timed path (NOT inside `value`): the fused
-    embed_tokens + <image>-row replacement on the compacted prompt, and the var-len mean pool of the k event-summary hidden
-    states (k prompts of ~T*P/k image tokens, LLM width 3584).  HBM-bound; reported against the measured copy peak."""
+    """The ops on either side of the timed path (NOT inside `value`): the fused
+    embed_tokens + <image>-row replacement on the compacted prompt, the var-len mean pool of the k event-summary hidden
+    states (k prompts of ~T*P/k image tokens, LLM width 3584), and the encoder tail (LayerNorm + bilinear merge) that produces
+    the features.  HBM-bound; reported against the measured copy peak."""
     from cogstream_b200 import ops
     pk = _peaks()
     dev = d.features.device
@@ -953,6 +954,18 @@ def _neighbour_ops(sc, d, reps=5):
     b = 2 * sum(lens) * Dl
     out["seq_mean_pool"] = dict(ms=round(ms, 5), rows=int(sum(lens)), Dl=Dl, algorithmic_bytes=b, gbs=round(b / ms / 1e6, 1),
                                 frac=round(b / ms / 1e6 / pk["hbm_gbs"], 3))
+    del hidden, po
+    # upstream: the encoder tail of one config-2 stream, post_layernorm + 2x2 bilinear merge in one pass
+    m = CFG2["merge"]
+    n_patch = sc.T * sc.P * m * m
+    h = torch.randn(n_patch, D, device=dev).to(torch.bfloat16)
+    g = torch.randn(D, device=dev).to(torch.bfloat16)
+    bta = torch.randn(D, device=dev).to(torch.bfloat16)
+    lo = torch.empty(n_patch // (m * m), D, dtype=torch.bfloat16, device=dev)
+    ms = _ev_time(lambda: ops.ln_merge(h, m, g, bta, 1e-6, out=lo), reps)
+    b = 2 * n_patch * D + 2 * (n_patch // (m * m)) * D
+    out["ln_merge"] = dict(ms=round(ms, 5), rows=int(n_patch), D=D, merge=m, algorithmic_bytes=b, gbs=round(b / ms / 1e6, 1),
+                           frac=round(b / ms / 1e6 / pk["hbm_gbs"], 3))
     return out
 
 

@@ -1286,6 +1286,24 @@ def test_early_pixel_diff_overlapped_with_solver(dev):
         assert torch.equal(ops.pixel_diff(d.pixel_values, T, P, W, max_ctas=ctas, evict_first=ef), raw)
 
 
+@pytest.mark.parametrize("C", [8, 40, 64, 72, 264, 520, 1152, 1280, 1288, 2048])
+def test_ln_merge_kernels_agree(dev, monkeypatch, C):
+    """The bulk-copy kernel (per-warp shared-memory rings, C <= 1280) and the column-wise register kernel produce the same bits
+    for every merge size, including widths that leave a partial 32-lane column slot and token counts below one CTA's worth."""
+    gen = torch.Generator(device=dev).manual_seed(C)
+    w = (1 + 0.2 * torch.randn(C, device=dev, generator=gen)).to(torch.bfloat16)
+    b = (0.3 * torch.randn(C, device=dev, generator=gen)).to(torch.bfloat16)
+    for m, n_tok in ((1, 7), (2, 2500), (3, 41), (4, 300)):
+        h = (torch.randn(n_tok * m * m, C, device=dev, generator=gen) * 2 + 0.4).to(torch.bfloat16)
+        monkeypatch.delenv("CSB_LN_COLUMNWISE", raising=False)
+        a = ops.ln_merge(h, m, w, b, 1e-6).clone()
+        monkeypatch.setenv("CSB_LN_COLUMNWISE", "1")
+        c = ops.ln_merge(h, m, w, b, 1e-6).clone()
+        monkeypatch.delenv("CSB_LN_COLUMNWISE", raising=False)
+        assert a.shape == (n_tok, C)
+        assert torch.equal(a, c), (C, m)
+
+
 def test_pipeline_without_centroid_pass(dev):
     """StreamConfig(compute_centroids=False): the fp32 centroids (kmeans_with_time.py:134) are not materialised; every other
     output of the fused path is identical (the representatives come from the Gram matrix, cogreasoner_chat.py:50-64)."""
