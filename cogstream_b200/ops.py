@@ -164,6 +164,10 @@ def kmeans_solve(G: torch.Tensor, timestamps: torch.Tensor, buf: KMeansBuffers, 
     T, k = buf.T, buf.k
     if G.shape != (T, T) or timestamps.shape[0] != T:
         raise ValueError("kmeans_solve: shape mismatch")
+    if buf.centroid_times.dtype != timestamps.dtype:
+        # the solver writes the centre times in the timestamps' dtype (kmeans_with_time.py:66): a float32 buffer would be overrun
+        raise TypeError(f"kmeans_solve: buffers were allocated for {buf.centroid_times.dtype} timestamps, got {timestamps.dtype} "
+                        "(KMeansBuffers / StreamCompressor ts_dtype)")
     if exp_noise is not None:
         _need(exp_noise, "exp_noise", torch.float32, 2)
         if exp_noise.shape != (k - 1, T):

@@ -3,6 +3,7 @@ oracle on the same seeded inputs.  Integer / index / mask results must be bit-ex
 features within 1e-3 relative (north star), the tolerance being norm-wise plus at most one bf16 ulp per element.
 """
 import math
+import os
 import random
 
 import pytest
@@ -1302,6 +1303,35 @@ def test_ln_merge_kernels_agree(dev, monkeypatch, C):
         monkeypatch.delenv("CSB_LN_COLUMNWISE", raising=False)
         assert a.shape == (n_tok, C)
         assert torch.equal(a, c), (C, m)
+
+
+def test_timestamp_dtype_mismatch_raises(dev):
+    """The solver writes the centre times in the timestamps' dtype (kmeans_with_time.py:66): buffers allocated for another dtype
+    are refused instead of being overrun / misread (found by scripts/fuzz_parity.py)."""
+    T, P, D = 150, 2, 64
+    st = synthetic.make_stream(T, P, D, 3, C=8, ts_dtype=torch.float32)
+    d = st.to(dev)
+    W = st.pixel_values.numel() // (T * P)
+    sc = StreamCompressor(T, P, D, W, st.input_ids.numel(), device=dev)  # ts_dtype defaults to float64
+    with pytest.raises(TypeError, match="timestamps"):
+        sc.phase1(d.features, d.timestamps)
+    sc32 = StreamCompressor(T, P, D, W, st.input_ids.numel(), device=dev, ts_dtype=torch.float32)
+    sc32.phase1(d.features, d.timestamps)
+    torch.cuda.synchronize()
+    assert sc32.km.centroid_times.dtype == torch.float32 and bool(torch.isfinite(sc32.km.centroid_times).all())
+
+
+def test_fuzz_parity_sweep():
+    """scripts/fuzz_parity.py: 40 random small streams (odd T around the 128-row tile edges, k around the 32 / 64 / 128 kernel
+    switches, duplicated frames, float32 time, fractional fps, early / late pixel mask) through the fused pipeline against the
+    oracle."""
+    import subprocess
+    import sys as _sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([_sys.executable, os.path.join(root, "scripts", "fuzz_parity.py"), "40", "7000"], capture_output=True, text=True,
+                       timeout=600)
+    print(r.stdout[-2000:])
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
 
 
 def test_pipeline_without_centroid_pass(dev):
