@@ -28,8 +28,16 @@ for case in range(n_cases):
     dup = rnd.random() < 0.2       # duplicated frames: exact ties, empty clusters, re-seeds
     f32_time = rnd.random() < 0.2  # float32 timestamps
     fps = rnd.choice([1.0, 2.0, 3.0, 0.5])
+    items = None
+    if rnd.random() < 0.3:  # several visual items in one prompt: video segments, images, single-frame videos
+        items, left = [], T
+        while left > 0:
+            kind = rnd.random()
+            n = 1 if kind < 0.3 else min(left, rnd.randint(2, max(2, T // 2)))
+            items.append((n, "image" if kind < 0.15 else "video"))
+            left -= n
     st = synthetic.make_stream(T, P, D, seed, C=24, iid=iid, near_threshold_frac=0.1, fps=fps,
-                               ts_dtype=torch.float32 if f32_time else torch.float64)
+                               ts_dtype=torch.float32 if f32_time else torch.float64, items=items)
     if dup:
         f3 = st.features.view(T, P, D)
         src = torch.randint(0, T, (T // 5,), generator=torch.Generator().manual_seed(seed))
@@ -56,7 +64,7 @@ for case in range(n_cases):
                     synthetic.IMAGE_TOKEN_INDEX, st.attention_mask)
     W = st.pixel_values.numel() // (T * P)
     sc = StreamCompressor(T, P, D, W, st.input_ids.numel(), device=dev, cfg=StreamConfig(cluster_num=k),
-                          ts_dtype=torch.float32 if f32_time else torch.float64)
+                          ts_dtype=torch.float32 if f32_time else torch.float64, items=items)
     d = st.to(dev)
     sc.phase1(d.features, d.timestamps, init_indices=init.to(dev), reseed_pool=pool.to(dev), pixel_values=d.pixel_values if case % 2 else None)
     sc.phase2(d.features, ev.to(dev), q.to(dev), d.pixel_values, d.input_ids, d.attention_mask)
@@ -99,7 +107,7 @@ for case in range(n_cases):
     else:
         bad = [n for n, v in checks.items() if not v]
         fails.append((case, T, P, D, kk, iid, dup, f32_time, bad))
-        print(f"case {case} FAILED: T={T} P={P} D={D} k={kk} iid={iid} dup={dup} f32_time={f32_time}: {bad} "
+        print(f"case {case} FAILED: T={T} P={P} D={D} k={kk} iid={iid} dup={dup} f32_time={f32_time} items={items}: {bad} "
               f"(ct ulps {ct_ulps:.1f}, iters {r['status']['iterations']}/{p1.info.iterations}, margin gpu {r['status']['min_margin']:.2e} cpu {p1.info.min_margin:.2e})")
 print(f"fuzz: {ok} ok ({tie_cases} of them with equivalent representatives among duplicated frames: downstream indices not compared), "
       f"{skipped} skipped (reference decided by its own rounding noise / oracle error), {len(fails)} failed; "

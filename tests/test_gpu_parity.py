@@ -1334,6 +1334,19 @@ def test_fuzz_parity_sweep():
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
 
 
+def test_fuzz_generator_sharded_cache_sweep():
+    """scripts/fuzz_more.py: the built-in generator against the oracle fed with the host-replayed draws (degenerate sampling rounds,
+    long streams, float32 time), the frame-sharded Lloyd loop against the single-GPU solver, StreamCache against the oracle --
+    20 random cases each."""
+    import subprocess
+    import sys as _sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([_sys.executable, os.path.join(root, "scripts", "fuzz_more.py"), "20", "4000"], capture_output=True, text=True,
+                       timeout=900)
+    print(r.stdout[-2000:])
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+
+
 def test_pipeline_without_centroid_pass(dev):
     """StreamConfig(compute_centroids=False): the fp32 centroids (kmeans_with_time.py:134) are not materialised; every other
     output of the fused path is identical (the representatives come from the Gram matrix, cogreasoner_chat.py:50-64)."""
