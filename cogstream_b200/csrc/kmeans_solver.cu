@@ -1366,7 +1366,7 @@ __global__ void __launch_bounds__(kSolverThreads, WIDE ? 1 : 2) kmeans_solver_ke
 
   const TS alpha = (TS)a.alpha;
   int cur = 0, it = 0;
-  bool converged = false;
+  bool converged = false, had_empty = false;
   float last_shift = 0.f;
   float my_margin = __int_as_float(0x7f800000);
   while (it < a.max_iter) {
@@ -1385,14 +1385,25 @@ __global__ void __launch_bounds__(kSolverThreads, WIDE ? 1 : 2) kmeans_solver_ke
     const int nxt = cur ^ 1;
     for (int j = threadIdx.x; j < k; j += blockDim.x) s_changed[j] = it == 1 ? 1 : 0;
     __syncthreads();
+    int moved = 0;
     for (int i = threadIdx.x; i < T; i += blockDim.x) {
       const int now = __ldcg(a.assign32 + i), before = s_assign[i];  // (s_assign holds garbage before the first iteration)
-      if (it > 1 && now != before) { s_changed[before] = 1; s_changed[now] = 1; }
+      if (it > 1 && now != before) { s_changed[before] = 1; s_changed[now] = 1; moved = 1; }
       s_assign[i] = now;
     }
-    __syncthreads();
+    // No frame moved and no cluster was empty (an empty cluster is re-seeded with a fresh draw every iteration, :117-120): the
+    // membership, hence every centre, is what it was -- the centre shift is exactly 0 and the reference stops here (:130).  Every
+    // CTA sees the same assignments and takes the same branch; the lists / centre times of the previous rebuild are the outputs.
+    if (!__syncthreads_or(moved) && it > 1 && !had_empty) {
+      mark(a, 12);
+      last_shift = 0.f;
+      converged = true;
+      break;
+    }
     ms.ct_new = s_ctb[nxt];
+    const int used_before = used;
     rebuild_members_smem<TS>(a, ms, &used, it == 1);
+    had_empty = used != used_before;
     // version stamps: a changed cluster gets a new version; a column of S[nxt] is recomputed iff it is stale
     if (warp == 0) {
       int nc = 0;
