@@ -763,261 +763,6 @@ __global__ void __launch_bounds__(160, 1) gram_tc_kernel(const __grid_constant__
   if (warp == 2) ptx::tmem_dealloc(tmem_base, 512);
 }
 
-// ---------------------------------------------------------------------------------------------------
-// Long streams, 2-SM UMMA (cta_group::2): a CTA PAIR owns the two row blocks of one super-row against four consecutive column
-// blocks.  CTA r holds A = row block 2I + r and, for each of the two N=256 ops, HALF of B (one column block); the pair's
-// tensor cores share the B halves, so per 64-wide K chunk a CTA takes 48 KB of TMA writes and 64 KB of operand reads
-// (896 cycles of shared-memory time, below the 1024-cycle MMA floor) instead of 64 + 96 KB with cta_group::1.
-// Roles per CTA: warp 4 lane 0 = TMA producer (its own three blocks; completion bytes go to the LEADER's full barrier),
-// warp 1 of the leader (rank 0) = MMA issuer for both CTAs, warps 0-3 = accumulator drain of the CTA's own TMEM.
-// One K range per tile (direct mode): the last drain writes fp64 G; mid-K drains go through the fp32 partial tiles.
-// ---------------------------------------------------------------------------------------------------
-struct GramPairUnit {
-  int n_ops;          // 1 or 2
-  int a_blk[2];       // row block of CTA 0 / 1
-  int c_blk[4];       // column block of TMEM tile slot t: op t/2, B half t%2 (loaded by CTA t%2)
-  int tile_id[2][4];  // [rank][slot] upper-triangular tile id, -1 = not part of the output
-};
-
-static void plan_pairs(int nb, int b0, GramPairUnit* out, int* n_out) {
-  int n = 0;
-  const int ns = (nb + 1) / 2;
-  constexpr int kMacro = 12;
-  for (int MI = 0; MI < ns; MI += kMacro)
-    for (int MJ = MI; MJ < ns; MJ += kMacro)
-      for (int I = MI; I < MI + kMacro && I < ns; ++I) {
-        const int jend = (MJ + kMacro < ns) ? MJ + kMacro : ns;
-        for (int J = (MJ > I ? MJ : I); J < jend; J += 2) {
-          GramPairUnit u;
-          memset(&u, 0, sizeof(u));
-          const int ncolsb = (J + 1 < jend) ? 4 : 2;  // the run may end with a single super-column
-          u.n_ops = ncolsb / 2;
-          bool any = false;
-          for (int r = 0; r < 2; ++r) u.a_blk[r] = 2 * I + r;
-          for (int t = 0; t < 4; ++t) u.c_blk[t] = 2 * J + t;
-          for (int r = 0; r < 2; ++r)
-            for (int t = 0; t < 4; ++t) {
-              const int bi = u.a_blk[r], bj = u.c_blk[t];
-              const bool ok = t < ncolsb && bi < nb && bj < nb && bi <= bj && bj >= b0;
-              u.tile_id[r][t] = ok ? tri_id(bi, bj, b0) : -1;
-              any |= ok;
-            }
-          if (!any) continue;
-          if (out) out[n] = u;
-          ++n;
-        }
-      }
-  *n_out = n;
-}
-
-struct __align__(8) Gram2SmemCtl {
-  uint64_t full[kMaxStages];
-  uint64_t empty[kMaxStages];
-  uint64_t accum_done;
-  uint64_t tmem_free;  // leader: both CTAs have drained a mid-K segment
-  uint32_t tmem_base;
-};
-
-namespace ptx {
-__device__ __forceinline__ void tma_load_2d_2sm(void* smem_dst, const CUtensorMap* map, uint64_t* leader_bar, int c0, int c1) {
-  // executed by both CTAs of the pair; clearing the peer bit of the barrier address makes the bytes count on CTA 0's barrier
-  asm volatile(
-      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
-          smem_u32(smem_dst)),
-      "l"(map), "r"(smem_u32(leader_bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1)
-      : "memory");
-}
-__device__ __forceinline__ void umma2_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
-      : "memory");
-}
-__device__ __forceinline__ void umma2_commit_both(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
-               "h"((uint16_t)3)
-               : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {  // arrive on the same barrier of cluster rank 0
-  asm volatile(
-      "{\n\t.reg .b32 ra;\n\t"
-      "mapa.shared::cluster.u32 ra, %0, 0;\n\t"
-      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}" ::"r"(smem_u32(bar))
-      : "memory");
-}
-__device__ __forceinline__ void cluster_sync2() {
-  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-}  // namespace ptx
-
-__global__ void __launch_bounds__(160, 1) gram_tc2_kernel(const __grid_constant__ CUtensorMap xmap,
-                                                          const GramPairUnit* __restrict__ pairs, int n_tiles, int n_chunks,
-                                                          int kStages, float* __restrict__ partial, double* __restrict__ Gout,
-                                                          int64_t ldg, int T) {
-  extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  constexpr int kSlots = 3;  // A rows, B half of op 0, B half of op 1
-  constexpr int stage_bytes = kSlots * kBlockBytes;
-  Gram2SmemCtl* ctl = reinterpret_cast<Gram2SmemCtl*>(smem + (size_t)kStages * stage_bytes);
-  __shared__ GramPairUnit unit;
-  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
-  unsigned rank;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
-  const int nchunk = n_chunks;
-  if (threadIdx.x < (int)(sizeof(GramPairUnit) / sizeof(int)))
-    reinterpret_cast<int*>(&unit)[threadIdx.x] = reinterpret_cast<const int*>(pairs + (blockIdx.x >> 1))[threadIdx.x];
-  if (warp == 1 && lane == 0) {
-    for (int s = 0; s < kStages; ++s) {
-      ptx::mbar_init(&ctl->full[s], 1);   // used on the leader only: its producer's arrive + the bytes of both CTAs
-      ptx::mbar_init(&ctl->empty[s], 1);  // one multicast commit of the leader's MMA thread
-    }
-    ptx::mbar_init(&ctl->accum_done, 1);
-    ptx::mbar_init(&ctl->tmem_free, 2);   // one arrival per CTA
-    ptx::fence_barrier_init();
-  }
-  __syncthreads();
-  ptx::cluster_sync2();  // barriers of both CTAs exist before any remote completion / arrival
-  if (warp == 2) {
-    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(ptx::smem_u32(&ctl->tmem_base)) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
-  }
-  ptx::tc_fence_before();
-  __syncthreads();
-  ptx::cluster_sync2();
-  ptx::tc_fence_after();
-  const uint32_t tmem_base = ctl->tmem_base;
-  const int n_ops = unit.n_ops;
-  const int n_slots = 1 + n_ops;
-  const int nseg = (nchunk + kSegChunks - 1) / kSegChunks;
-
-  if (warp == 4) {
-    if (lane == 0) {
-      // ===== TMA producer: this CTA's A rows and its halves of B; every byte is counted on the leader's full barrier =====
-      asm volatile("prefetch.tensormap [%0];" ::"l"(&xmap) : "memory");
-      int blk[kSlots];
-      blk[0] = unit.a_blk[rank];
-      blk[1] = unit.c_blk[rank];
-      blk[2] = unit.c_blk[2 + rank];
-      for (int c = 0; c < nchunk; ++c) {
-        const int s = c % kStages;
-        const uint32_t ph = (uint32_t)(c / kStages) & 1u;
-        ptx::mbar_wait(&ctl->empty[s], ph ^ 1u);
-        if (rank == 0) ptx::mbar_expect_tx(&ctl->full[s], (uint32_t)(2 * n_slots * kBlockBytes));
-        uint8_t* stage = smem + (size_t)s * stage_bytes;
-        for (int q = 0; q < n_slots; ++q)
-          ptx::tma_load_2d_2sm(stage + (size_t)q * kBlockBytes, &xmap, &ctl->full[s], c * kChunk, blk[q] * kTile);
-        if (c == kStages - 1 || (nchunk < kStages && c == nchunk - 1)) {
-          for (int f = c + 1; f < c + 1 + kPrefetch && f < nchunk; ++f)
-            for (int q = 0; q < n_slots; ++q) ptx::tma_prefetch_l2_2d(&xmap, f * kChunk, blk[q] * kTile);
-        } else if (c >= kStages && c + kPrefetch < nchunk) {
-          for (int q = 0; q < n_slots; ++q) ptx::tma_prefetch_l2_2d(&xmap, (c + kPrefetch) * kChunk, blk[q] * kTile);
-        }
-      }
-    }
-  } else {
-    constexpr uint32_t idesc = make_idesc(256, 256);
-    constexpr uint32_t kDescHi = 64u | (1u << 14) | (2u << 29);
-    const uint32_t smem_lo = ptx::smem_u32(smem) >> 4;
-    for (int seg = 0; seg < nseg; ++seg) {
-      const int cs = seg * kSegChunks, ce = min(nchunk, cs + kSegChunks);
-      if (warp == 1 && rank == 0) {
-        if (seg > 0) {  // both CTAs have read their accumulators of the previous segment
-          ptx::mbar_wait(&ctl->tmem_free, (uint32_t)(seg - 1) & 1u);
-          ptx::tc_fence_after();
-        }
-        for (int c = cs; c < ce; ++c) {
-          const int s = c % kStages;
-          const uint32_t ph = (uint32_t)(c / kStages) & 1u;
-          ptx::mbar_wait(&ctl->full[s], ph);
-          ptx::tc_fence_after();
-          if (ptx::elect_one()) {
-            const uint32_t so = smem_lo + (uint32_t)(s * stage_bytes >> 4);
-            const uint32_t alo = so | (1u << 16);
-#pragma unroll
-            for (int o = 0; o < 2; ++o) {
-              if (o < n_ops) {
-                const uint32_t blo = (so + (uint32_t)((1 + o) * kBlockBytes >> 4)) | (1u << 16);
-#pragma unroll
-                for (int ks = 0; ks < kChunk / 16; ++ks) {
-                  const uint64_t ad = ((uint64_t)kDescHi << 32) | (uint64_t)(alo + 2u * ks);
-                  const uint64_t bd = ((uint64_t)kDescHi << 32) | (uint64_t)(blo + 2u * ks);
-                  ptx::umma2_bf16(tmem_base + (uint32_t)o * 256u, ad, bd, idesc, (c > cs || ks > 0) ? 1u : 0u);
-                }
-              }
-            }
-            ptx::umma2_commit_both(&ctl->empty[s]);
-            if (c == ce - 1) ptx::umma2_commit_both(&ctl->accum_done);
-          }
-          __syncwarp();
-        }
-      }
-      ptx::mbar_wait_relaxed(&ctl->accum_done, (uint32_t)seg & 1u);
-      ptx::tc_fence_after();
-      // ---- drain this CTA's accumulators: lane = row of A block a_blk[rank]; tile slot t = column block c_blk[t] ----
-      const int row = warp * 32 + lane;
-      const int ablk = unit.a_blk[rank];
-      const int rows_ok = min(kTile, T - ablk * kTile);  // <= 0 when the row block does not exist
-      const bool row_ok = row < rows_ok;
-      for (int t = 0; t < 2 * n_ops; ++t) {
-        const int tid = unit.tile_id[rank][t];
-        if (tid < 0) continue;  // uniform over the CTA
-        const int bblk = unit.c_blk[t];
-        const int ncols = min(kTile, T - bblk * kTile);
-        const int ncb = (ncols + 31) >> 5;
-        float* out = partial + (int64_t)tid * (kTile * kTile) + row;
-#pragma unroll 1
-        for (int cb = 0; cb < ncb; ++cb) {
-          uint32_t r[32];
-          ptx::tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(t * 128 + cb * 32), r);
-          ptx::tmem_ld_wait();
-          if (!row_ok) continue;
-          float* o = out + (int64_t)(cb * 32) * kTile;
-          float val[32];
-          if (seg == 0) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) val[j] = __uint_as_float(r[j]);
-          } else {
-            float prev[32];
-#pragma unroll
-            for (int j = 0; j < 32; ++j) prev[j] = (cb * 32 + j < ncols) ? __ldcg(o + j * kTile) : 0.f;
-#pragma unroll
-            for (int j = 0; j < 32; ++j) val[j] = __fadd_rn(prev[j], __uint_as_float(r[j]));
-          }
-          if (seg == nseg - 1) {
-            const int64_t ga = (int64_t)ablk * kTile + row;
-            const int64_t gb0 = (int64_t)bblk * kTile + cb * 32;
-            double* grow = Gout + ga * ldg + gb0;
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (cb * 32 + j < ncols) grow[j] = (double)val[j];
-            if (ablk != bblk) {
-              double* gcol = Gout + gb0 * ldg + ga;
-#pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (cb * 32 + j < ncols) gcol[(int64_t)j * ldg] = (double)val[j];
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (cb * 32 + j < ncols) o[j * kTile] = val[j];
-          }
-        }
-      }
-      if (seg + 1 < nseg) {
-        ptx::tc_fence_before();
-        asm volatile("bar.sync 1, 128;" ::: "memory");  // this CTA's accumulators have been read
-        if (threadIdx.x == 0) ptx::mbar_arrive_leader(&ctl->tmem_free);
-      }
-    }
-  }
-  ptx::tc_fence_before();
-  __syncthreads();
-  ptx::cluster_sync2();  // no exit (and no TMEM release) while the pair is still working
-  if (warp == 2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
-}
-
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                     const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                     CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -1084,73 +829,6 @@ int csb_gram_extend(const void* x, int64_t T_old, int64_t T, int64_t K, double* 
     int kr_simt = (2 * kNumSMs + p.n_tiles - 1) / p.n_tiles;
     if (kr_simt > p.n_chunks) kr_simt = p.n_chunks;
     const int kr_max = kr_simt > p.n_kr ? kr_simt : p.n_kr;
-    // ---- long streams: the 2-SM UMMA kernel (one K range per tile, more pair units than SM pairs) ----
-    // Opt-in (impl bit 10 or CSB_GRAM_2SM=1): measured at config 4 it runs exactly as fast as the 1-SM kernel (4.0 ms) although it
-    // moves 25 % fewer bytes into each SM -- the main loop there is paced by loaded L2 latency x ring depth (loads-only 3.6 ms,
-    // MMA + drains 3.0 ms), not by shared-memory or tensor throughput.  Kept as the validated starting point for that work.
-    if (p.nb > 16 && p.n_kr == 1 && !((impl >> 4) & 32) && (((impl >> 4) & 64) || getenv("CSB_GRAM_2SM"))) {
-      constexpr int kPairCache = 16;
-      struct PairCache { int nb, b0, n; GramPairUnit* pairs; };
-      static thread_local PairCache pcache[kPairCache];
-      static thread_local int pcache_n = 0;
-      PairCache* pc = nullptr;
-      for (int i = 0; i < pcache_n; ++i)
-        if (pcache[i].nb == p.nb && pcache[i].b0 == p.b0) pc = &pcache[i];
-      GramPairUnit* h_tmp = nullptr;
-      int n_pairs = 0;
-      const GramPairUnit* h_pairs = nullptr;
-      if (!pc && pcache_n < kPairCache) {
-        pc = &pcache[pcache_n++];
-        pc->nb = p.nb; pc->b0 = p.b0;
-        plan_pairs(p.nb, p.b0, nullptr, &pc->n);
-        pc->pairs = (GramPairUnit*)malloc(sizeof(GramPairUnit) * (size_t)pc->n);
-        plan_pairs(p.nb, p.b0, pc->pairs, &pc->n);
-      }
-      if (pc) { h_pairs = pc->pairs; n_pairs = pc->n; }
-      else {
-        plan_pairs(p.nb, p.b0, nullptr, &n_pairs);
-        h_tmp = (GramPairUnit*)malloc(sizeof(GramPairUnit) * (size_t)n_pairs);
-        plan_pairs(p.nb, p.b0, h_tmp, &n_pairs);
-        h_pairs = h_tmp;
-      }
-      GramPairUnit* d_pairs = reinterpret_cast<GramPairUnit*>(reinterpret_cast<char*>(workspace) +
-                                                              align_up((size_t)kr_max * p.n_tiles * kTile * kTile * sizeof(float), 256));
-      cudaError_t e2 = cudaMemcpyAsync(d_pairs, h_pairs, sizeof(GramPairUnit) * (size_t)n_pairs, cudaMemcpyHostToDevice, s);
-      if (h_tmp) { cudaStreamSynchronize(s); free(h_tmp); }
-      if (e2 != cudaSuccess) { set_error("gram: pair table copy: %s", cudaGetErrorString(e2)); return CSB_ERR_CUDA; }
-      PFN_encodeTiled enc2 = get_encode_fn();
-      if (!enc2) { set_error("gram: cuTensorMapEncodeTiled unavailable"); return CSB_ERR_CUDA; }
-      CUtensorMap map2;
-      cuuint64_t dims2[2] = {(cuuint64_t)K, (cuuint64_t)T};
-      cuuint64_t strides2[1] = {(cuuint64_t)K * 2};
-      cuuint32_t box2[2] = {(cuuint32_t)kChunk, (cuuint32_t)kTile};
-      cuuint32_t estr2[2] = {1, 1};
-      CUresult r2 = enc2(&map2, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(x), dims2, strides2, box2, estr2,
-                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-      if (r2 != CUDA_SUCCESS) { set_error("gram: cuTensorMapEncodeTiled failed (%d)", (int)r2); return CSB_ERR_CUDA; }
-      const int stages2 = 4;
-      const size_t smem2 = (size_t)stages2 * 3 * kBlockBytes + sizeof(Gram2SmemCtl) + 1024;
-      e2 = cudaFuncSetAttribute(gram_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
-      if (e2 != cudaSuccess) { set_error("gram: smem attr: %s", cudaGetErrorString(e2)); return CSB_ERR_CUDA; }
-      cudaLaunchConfig_t cfg;
-      memset(&cfg, 0, sizeof(cfg));
-      cfg.gridDim = dim3((unsigned)(2 * n_pairs));
-      cfg.blockDim = dim3(160);
-      cfg.dynamicSmemBytes = smem2;
-      cfg.stream = s;
-      cudaLaunchAttribute cattr[1];
-      cattr[0].id = cudaLaunchAttributeClusterDimension;
-      cattr[0].val.clusterDim.x = 2;
-      cattr[0].val.clusterDim.y = 1;
-      cattr[0].val.clusterDim.z = 1;
-      cfg.attrs = cattr;
-      cfg.numAttrs = 1;
-      const GramPairUnit* dp = d_pairs;
-      e2 = cudaLaunchKernelEx(&cfg, gram_tc2_kernel, map2, dp, p.n_tiles, p.n_chunks, stages2, partial, G, ldg, (int)T);
-      if (e2 != cudaSuccess) { set_error("gram: 2-SM launch: %s", cudaGetErrorString(e2)); return CSB_ERR_CUDA; }
-      return check_launch("gram_tc2");
-    }
     GramUnit* d_units = nullptr;
     static thread_local GramUnitTable table;  // plan for small problems, passed by value
     static thread_local GramFlipMask table_flips;

@@ -699,15 +699,53 @@ struct GridInitBufs {
   int force_exact;    // profiling / test aid: always take the two-barrier exact path
 };
 
-__global__ void __launch_bounds__(kGridInitThreads) kmeanspp_grid_kernel(SolverArgs a, GridInitBufs b) {
+// CL = true: the CTAs are ONE thread-block cluster (<= 16 CTAs, T <= 32,768).  The per-round exchange goes through distributed
+// shared memory instead of global memory, and the software grid barrier (atomic + acquire poll through the L2, ~1.4 us, plus an
+// L2 round trip for the partials afterwards) becomes the hardware cluster barrier (barrier.cluster arrive.release /
+// wait.acquire, ~0.2 us) followed by four 16-byte ld.shared::cluster loads per peer.  Same arithmetic, same candidate rule,
+// same fixed summation tree: the chosen centres are those of the grid form with the same CTA count.
+constexpr int kClusterInitMax = 16;
+constexpr bool kClusterInitDefault = false;  // until measured on B200: opt-in with CSB_INIT_CLUSTER=1
+struct __align__(16) ClusterRound {  // what a CTA publishes per sampling round: 64 bytes = four 16-byte loads for a peer
+  float part;
+  int cnt;
+  int pad[2];
+  float n2[kGridInitCand];
+  float nz[kGridInitCand];
+  int idx[kGridInitCand];
+};
+static_assert(kGridInitCand == 4 && sizeof(ClusterRound) == 64, "ClusterRound is read with four 16-byte loads");
+
+__device__ __forceinline__ void cluster_barrier() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint2 ld_cluster_v2(const void* local_smem, unsigned rank) {
+  uint32_t addr = (uint32_t)__cvta_generic_to_shared(local_smem), remote;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(addr), "r"(rank));
+  uint2 v;
+  asm volatile("ld.shared::cluster.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(remote) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint4 ld_cluster_v4(const void* local_smem, unsigned rank) {
+  uint32_t addr = (uint32_t)__cvta_generic_to_shared(local_smem), remote;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(addr), "r"(rank));
+  uint4 v;
+  asm volatile("ld.shared::cluster.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(remote) : "memory");
+  return v;
+}
+
+template <bool CL>
+__global__ void __launch_bounds__(kGridInitThreads, 1) kmeanspp_grid_kernel(SolverArgs a, GridInitBufs b) {
   constexpr int NW = kGridInitThreads / 32;
   __shared__ float s_wv[NW];
   __shared__ int s_wi[NW];
   __shared__ float s_ws[NW];
   __shared__ float s_cn2[kGridInitCand], s_cnz[kGridInitCand];
   __shared__ int s_ci[kGridInitCand];
-  __shared__ int s_cnt, s_c, s_ovf;
-  __shared__ float s_sum, s_umax;
+  __shared__ int s_cnt, s_c[2], s_ovf[2];
+  __shared__ float s_sum[2], s_umax;
+  __shared__ ClusterRound s_x[2];  // CL: this CTA's published round data, double-buffered by round parity
+  __shared__ __align__(8) unsigned s_fb[2];  // CL, exact fallback: this CTA's best {score bits, frame} (written / read between the two barriers of a round)
   const int T = a.T, k = a.k;
   const unsigned nb = gridDim.x;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -774,39 +812,67 @@ __global__ void __launch_bounds__(kGridInitThreads) kmeanspp_grid_kernel(SolverA
     if (!sample_next) continue;  // the next centre is prescribed too: no total needed
     part = warp_sum(part);
     umax = warp_max(umax);
-    if (lane == 0) { s_ws[warp] = part; s_wv[warp] = umax; }
-    if (threadIdx.x == 0) { s_cnt = 0; }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      float t = s_ws[0], um = s_wv[0];
-      for (int w = 1; w < NW; ++w) { t += s_ws[w]; um = fmaxf(um, s_wv[w]); }
-      b.part[(m & 1) * nb + blockIdx.x] = t;
-      s_umax = um;
-    }
-    __syncthreads();
-    {
-      const float um = s_umax;
+    if (CL) {
+      // One block barrier, then the cluster barrier: the per-warp partials are combined by warp 0 (fixed shuffle tree), every
+      // thread takes the block maximum straight from the per-warp values, and the candidates go directly into the round buffer
+      // the peers read.  Buffer m & 1 was last read by the peers in round m - 2, i.e. before the barrier of round m - 1 that
+      // this CTA has passed; the per-warp arrays are rewritten only after the cluster barrier every reader arrives at.
+      ClusterRound* x = &s_x[m & 1];
+      if (lane == 0) { s_ws[warp] = part; s_wv[warp] = umax; }
+      if (threadIdx.x == 0) x->cnt = 0;
+      __syncthreads();
+      float um = s_wv[0];
+#pragma unroll
+      for (int w = 1; w < NW; ++w) um = fmaxf(um, s_wv[w]);
+      if (warp == 0) {
+        const float t = warp_sum(lane < NW ? s_ws[lane] : 0.f);
+        if (lane == 0) x->part = t;
+      }
       const float thr = um - um * 9.5367431640625e-7f;  // u_max * (1 - 2^-20)
       if (um > 0.f) {
 #pragma unroll
         for (int u = 0; u < kGridInitU; ++u) {
           if (fi[u] >= 0 && uq[u] >= thr) {
-            const int slot = atomicAdd(&s_cnt, 1);
-            if (slot < kGridInitCand) { s_cn2[slot] = n2[u]; s_cnz[slot] = nz[u]; s_ci[slot] = fi[u]; }
+            const int slot = atomicAdd(&x->cnt, 1);
+            if (slot < kGridInitCand) { x->n2[slot] = n2[u]; x->nz[slot] = nz[u]; x->idx[slot] = fi[u]; }
           }
         }
       }
-    }
-    __syncthreads();
-    {
+      cluster_barrier();  // every thread of every CTA: releases the writes above, acquires the peers'
+    } else {
+      if (lane == 0) { s_ws[warp] = part; s_wv[warp] = umax; }
+      if (threadIdx.x == 0) { s_cnt = 0; }
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        float t = s_ws[0], um = s_wv[0];
+        for (int w = 1; w < NW; ++w) { t += s_ws[w]; um = fmaxf(um, s_wv[w]); }
+        b.part[(m & 1) * nb + blockIdx.x] = t;
+        s_umax = um;
+      }
+      __syncthreads();
+      {
+        const float um = s_umax;
+        const float thr = um - um * 9.5367431640625e-7f;  // u_max * (1 - 2^-20)
+        if (um > 0.f) {
+#pragma unroll
+          for (int u = 0; u < kGridInitU; ++u) {
+            if (fi[u] >= 0 && uq[u] >= thr) {
+              const int slot = atomicAdd(&s_cnt, 1);
+              if (slot < kGridInitCand) { s_cn2[slot] = n2[u]; s_cnz[slot] = nz[u]; s_ci[slot] = fi[u]; }
+            }
+          }
+        }
+      }
+      __syncthreads();
       const int cnt = s_cnt;
       if (threadIdx.x == 0) b.cnt[(m & 1) * nb + blockIdx.x] = b.force_exact ? kGridInitCand + 1 : cnt;
       if (threadIdx.x < min(cnt, kGridInitCand)) {
         const int64_t o = ((int64_t)(m & 1) * nb + blockIdx.x) * kGridInitCand + threadIdx.x;
         b.cand_n2[o] = s_cn2[threadIdx.x]; b.cand_nz[o] = s_cnz[threadIdx.x]; b.cand_i[o] = s_ci[threadIdx.x];
       }
+      grid_sync(b.barrier, bar, nb);
     }
-    grid_sync(b.barrier, bar, nb);
+    const int rb = CL ? (m & 1) : 0;
     // ---- total (fixed shuffle tree: the same bits in every CTA), overflow flag, candidates ----
     // lane q takes CTA q (q += 32): its partial, count and all candidate slots are loaded together -- one L2 round trip
     if (warp == 0) {
@@ -821,7 +887,17 @@ __global__ void __launch_bounds__(kGridInitThreads) kmeanspp_grid_kernel(SolverA
       for (int r = 0; r < kMaxQ; ++r) {
         const unsigned q = lane + 32 * r;
         ccnt[r] = 0;
-        if (q < nb) {
+        if (CL) {
+          if (r == 0 && q < nb) {  // a cluster has <= 16 CTAs: lane q reads peer q's 64 bytes (all four loads in flight together)
+            const char* xb = reinterpret_cast<const char*>(&s_x[m & 1]);
+            const uint4 h = ld_cluster_v4(xb, q), v2 = ld_cluster_v4(xb + 16, q), vz = ld_cluster_v4(xb + 32, q), vi = ld_cluster_v4(xb + 48, q);
+            v += __uint_as_float(h.x);
+            ccnt[r] = (int)h.y;
+            cn2[r][0] = __uint_as_float(v2.x); cn2[r][1] = __uint_as_float(v2.y); cn2[r][2] = __uint_as_float(v2.z); cn2[r][3] = __uint_as_float(v2.w);
+            cnz[r][0] = __uint_as_float(vz.x); cnz[r][1] = __uint_as_float(vz.y); cnz[r][2] = __uint_as_float(vz.z); cnz[r][3] = __uint_as_float(vz.w);
+            cix[r][0] = (int)vi.x; cix[r][1] = (int)vi.y; cix[r][2] = (int)vi.z; cix[r][3] = (int)vi.w;
+          }
+        } else if (q < nb) {
           v += __ldcg(b.part + (m & 1) * nb + q);
           ccnt[r] = __ldcg(b.cnt + (m & 1) * nb + q);
           const int64_t o = ((int64_t)(m & 1) * nb + q) * kGridInitCand;
@@ -832,6 +908,7 @@ __global__ void __launch_bounds__(kGridInitThreads) kmeanspp_grid_kernel(SolverA
         }
         ovf |= ccnt[r] > kGridInitCand;
       }
+      if (CL) ovf |= b.force_exact;
       v = warp_sum(v);
       ovf = __any_sync(0xffffffffu, ovf);
       if (v != 0.f && !ovf) {
@@ -852,10 +929,10 @@ __global__ void __launch_bounds__(kGridInitThreads) kmeanspp_grid_kernel(SolverA
           if (ov > gb || (ov == gb && oi < gi)) { gb = ov; gi = oi; }
         }
       }
-      if (lane == 0) { s_sum = v; s_ovf = ovf; s_c = gi; }
+      if (lane == 0) { s_sum[rb] = v; s_ovf[rb] = ovf; s_c[rb] = gi; }
     }
     __syncthreads();
-    const float sum = s_sum;
+    const float sum = s_sum[rb];
     if (sum == 0.f) {  // :55-57 every frame coincides with a centre: host-drawn index, no noise row consumed
       ++degenerate;
       bool ovf = false;
@@ -864,8 +941,8 @@ __global__ void __launch_bounds__(kGridInitThreads) kmeanspp_grid_kernel(SolverA
       ++used;
     } else {
       ++noise_row;
-      if (!s_ovf) {
-        c = s_c;
+      if (!s_ovf[rb]) {
+        c = s_c[rb];
       } else {
         // ---- exact fallback: scores of all frames with the known total, per-CTA argmax, second barrier ----
         float best = -1.f;
@@ -892,16 +969,23 @@ __global__ void __launch_bounds__(kGridInitThreads) kmeanspp_grid_kernel(SolverA
             const int oi = s_wi[w];
             if (ov > best || (ov == best && oi < besti)) { best = ov; besti = oi; }
           }
-          b.best_v[blockIdx.x] = best;
-          b.best_i[blockIdx.x] = besti;
+          if (CL) { s_fb[0] = __float_as_uint(best); s_fb[1] = (unsigned)besti; }
+          else { b.best_v[blockIdx.x] = best; b.best_i[blockIdx.x] = besti; }
         }
-        grid_sync(b.barrier, bar, nb);
+        if (CL) cluster_barrier();
+        else grid_sync(b.barrier, bar, nb);
         if (warp == 0) {
           float gb = -1.f;
           int gi = 0x7fffffff;
           for (unsigned q = lane; q < nb; q += 32) {
-            const float ov = __ldcg(b.best_v + q);
-            const int oi = __ldcg(b.best_i + q);
+            float ov;
+            int oi;
+            if (CL) {
+              const uint2 h = ld_cluster_v2(s_fb, q);
+              ov = __uint_as_float(h.x); oi = (int)h.y;
+            } else {
+              ov = __ldcg(b.best_v + q); oi = __ldcg(b.best_i + q);
+            }
             if (ov > gb || (ov == gb && oi < gi)) { gb = ov; gi = oi; }
           }
 #pragma unroll
@@ -910,14 +994,16 @@ __global__ void __launch_bounds__(kGridInitThreads) kmeanspp_grid_kernel(SolverA
             const int oi = __shfl_xor_sync(0xffffffffu, gi, o);
             if (ov > gb || (ov == gb && oi < gi)) { gb = ov; gi = oi; }
           }
-          if (lane == 0) s_c = gi;
+          if (lane == 0) s_c[rb] = gi;
         }
         __syncthreads();
-        c = s_c;
+        c = s_c[rb];
       }
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) a.init_indices[m + 1] = c;
-    __syncthreads();  // s_c / s_sum are rewritten in the next round
+    // s_c / s_sum are rewritten in the next round: a block barrier here, or (CL) results double-buffered by round parity --
+    // buffer rb is rewritten in round m + 2, behind the block barrier of round m + 1 that every reader of round m has passed
+    if (!CL) __syncthreads();
   }
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     st->degenerate_rounds = degenerate;
@@ -925,6 +1011,7 @@ __global__ void __launch_bounds__(kGridInitThreads) kmeanspp_grid_kernel(SolverA
     *a.used = used;
   }
   mark(a, 2);
+  if (CL) cluster_barrier();  // no CTA leaves (and frees its shared memory) while a peer may still be reading it
 }
 
 // ---- outputs shared by the grid and the cluster solver: CSR, centre times, chronological event order, status (CTA 0) ----
@@ -1797,9 +1884,44 @@ int csb_kmeans_solve(const double* G, const void* timestamps, const csb_kmeans_p
     gb.best_v = reinterpret_cast<float*>(carve(sizeof(float) * nbi));
     gb.best_i = reinterpret_cast<int*>(carve(sizeof(int) * nbi));
     gb.force_exact = getenv("CSB_INIT_EXACT") ? 1 : 0;
-    void* iargs[] = {&a, &gb};
-    e = cudaLaunchCooperativeKernel((const void*)kmeanspp_grid_kernel, dim3((unsigned)nbi), dim3(kGridInitThreads), iargs, 0, s);
-    if (e != cudaSuccess) { set_error("kmeans_solve: init launch: %s", cudaGetErrorString(e)); return CSB_ERR_CUDA; }
+    // One thread-block cluster when the stream fits 16 CTAs (T <= 32,768): hardware cluster barrier + DSMEM exchange per round
+    // instead of the software grid barrier + L2 round trip.  The cluster size is a power of two (surplus CTAs own an empty
+    // slice); sizes above 8 are non-portable and taken only if the device can place such a cluster.  CSB_INIT_CLUSTER=0: off.
+    bool clustered = false;
+    const char* cl_env = getenv("CSB_INIT_CLUSTER");
+    const bool cl_want = cl_env ? atoi(cl_env) != 0 : kClusterInitDefault;
+    if (cl_want && T <= (int64_t)kClusterInitMax * kGridInitThreads * kGridInitU) {
+      int csz = 2;
+      while (csz < nbi && csz < kClusterInitMax) csz *= 2;
+      if ((int64_t)csz * kGridInitThreads * kGridInitU < T) csz = kClusterInitMax;
+      cudaLaunchConfig_t cfg;
+      memset(&cfg, 0, sizeof(cfg));
+      cfg.gridDim = dim3((unsigned)csz);
+      cfg.blockDim = dim3(kGridInitThreads);
+      cfg.stream = s;
+      cudaLaunchAttribute cattr[1];
+      cattr[0].id = cudaLaunchAttributeClusterDimension;
+      cattr[0].val.clusterDim.x = (unsigned)csz;
+      cattr[0].val.clusterDim.y = 1;
+      cattr[0].val.clusterDim.z = 1;
+      cfg.attrs = cattr;
+      cfg.numAttrs = 1;
+      bool ok = true;
+      if (csz > 8) ok = cudaFuncSetAttribute(kmeanspp_grid_kernel<true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess;
+      int n_clusters = 0;
+      if (ok) ok = cudaOccupancyMaxActiveClusters(&n_clusters, kmeanspp_grid_kernel<true>, &cfg) == cudaSuccess && n_clusters >= 1;
+      if (!ok) cudaGetLastError();  // not placeable here: clear the error, take the cooperative grid below
+      if (ok) {
+        e = cudaLaunchKernelEx(&cfg, kmeanspp_grid_kernel<true>, a, gb);
+        if (e != cudaSuccess) { set_error("kmeans_solve: cluster init launch: %s", cudaGetErrorString(e)); return CSB_ERR_CUDA; }
+        clustered = true;
+      }
+    }
+    if (!clustered) {
+      void* iargs[] = {&a, &gb};
+      e = cudaLaunchCooperativeKernel((const void*)kmeanspp_grid_kernel<false>, dim3((unsigned)nbi), dim3(kGridInitThreads), iargs, 0, s);
+      if (e != cudaSuccess) { set_error("kmeans_solve: init launch: %s", cudaGetErrorString(e)); return CSB_ERR_CUDA; }
+    }
     count_launch(1);
   } else {
     // few warps = cheap block barriers: the rounds are a dependent chain, each about (frames / threads) elements of work

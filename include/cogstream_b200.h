@@ -81,7 +81,7 @@ CSB_API int csb_pool_norm(const void* x_bf16, int64_t T, int64_t P, int64_t D, v
  *     cogreasoner_chat.py:61) is ||x_i||^2 + ||c||^2 - 2<x_i,c> with c a frame or a mean of
  *     frames, i.e. a function of G.
  *     impl: 0 = tcgen05/TMA kernel (default), 1 = CUDA-core reference kernel (validation only); higher bits are
- *     validation / profiling switches (512: force the partial-tile + reduce path, 1024: 2-SM UMMA kernel for long streams).
+ *     validation / profiling switches (512: force the partial-tile + reduce path).
  * ------------------------------------------------------------------------------------------- */
 CSB_API size_t csb_gram_workspace_bytes(int64_t T, int64_t K);
 CSB_API int csb_gram(const void* x_bf16, int64_t T, int64_t K, double* G, void* workspace, size_t workspace_bytes,

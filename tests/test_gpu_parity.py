@@ -84,8 +84,6 @@ def test_gram_long_stream_direct_write(dev, T, K):
     G2 = ops.gram(x, impl=512)
     assert torch.equal(G, G2)
     assert torch.equal(G, G.T)
-    G3 = ops.gram(x, impl=1024)  # opt-in 2-SM UMMA kernel (cta_group::2 pairs): the same bits
-    assert torch.equal(G, G3)
     idx = torch.randperm(T, generator=g)[:96].to(dev)
     sub = x[idx].double()
     ref = sub @ sub.T
@@ -1041,8 +1039,9 @@ def test_drop_in_call_site_matches_reference(dev, fused_embed):
                                                  (2200, 2, 32, 2, torch.float32),  # float32 timestamps (WIDE<float>)
                                                  (2300, 8, 1152, 3, torch.float64)])  # K = 9216: two accumulator segments
 def test_kmeanspp_long_stream_grid_init(dev, monkeypatch, T, P, D, seed, ts_dtype):
-    """Long streams (T > 2048) run k-means++ on a cooperative grid; the centres, assignments and iteration count equal the
-    single-CTA kernel's and the CPU oracle's for the same injected Exp(1) noise."""
+    """Long streams (T > 2048) run k-means++ on one thread-block cluster (hardware barrier + DSMEM exchange per round; the
+    cooperative grid with the software barrier when CSB_INIT_CLUSTER=0 or T > 32,768); the centres, assignments and iteration
+    count equal the single-CTA kernel's and the CPU oracle's for the same injected Exp(1) noise."""
     import os
     k = math.ceil(T / 15)
     feats, _ = synthetic.make_features(T, P, D, seed)
@@ -1053,16 +1052,21 @@ def test_kmeanspp_long_stream_grid_init(dev, monkeypatch, T, P, D, seed, ts_dtyp
     pool = [int(v) for v in torch.randint(0, T, (64,), generator=g)]
     f3 = feats.view(T, P, D)
     res = {}
-    for mode in ("1", "0", "exact"):  # grid (one barrier per round), single CTA, grid with the exact two-barrier fallback
+    # cluster (one barrier per round), single CTA, software-barrier grid, then both multi-CTA forms with the exact two-barrier fallback
+    for mode in ("1", "0", "grid", "exact", "grid-exact"):
         monkeypatch.setenv("CSB_INIT_GRID", "0" if mode == "0" else "1")
-        if mode == "exact":
+        monkeypatch.setenv("CSB_INIT_CLUSTER", "0" if mode.startswith("grid") else "1")
+        if mode.endswith("exact"):
             monkeypatch.setenv("CSB_INIT_EXACT", "1")
+        else:
+            monkeypatch.delenv("CSB_INIT_EXACT", raising=False)
         _, _, assign, info = kmeans_with_time_min_max(f3.to(dev), ts.to(dev), k, first_index=first, exp_noise=noise,
                                                       reseed_indices=pool, return_info=True)
         res[mode] = (info.init_indices.tolist(), assign.cpu(), info.iterations, info.n_reseed_used, info.n_noise_used)
     monkeypatch.delenv("CSB_INIT_GRID")
+    monkeypatch.delenv("CSB_INIT_CLUSTER")
     monkeypatch.delenv("CSB_INIT_EXACT")
-    for other in ("0", "exact"):
+    for other in ("0", "grid", "exact", "grid-exact"):
         assert res["1"][0] == res[other][0] and torch.equal(res["1"][1], res[other][1]) and res["1"][2:] == res[other][2:]
     info_o = orc.KMeansInfo()
     orig = random.randint
