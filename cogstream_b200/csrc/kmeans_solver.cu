@@ -697,6 +697,8 @@ struct GridInitBufs {
   float* best_v;      // [nb] exact fallback: per-CTA best score / frame
   int* best_i;
   int force_exact;    // profiling / test aid: always take the two-barrier exact path
+  int profile;        // profiling aid (CSB_INIT_PROFILE=1): thread 0 of CTA 0 sums the clock cycles of the five phases of a
+                      // round and stores the per-round averages in part[0..5] (+ the round count) when the kernel ends
 };
 
 // CL = true: the CTAs are ONE thread-block cluster (<= 16 CTAs, T <= 32,768).  The per-round exchange goes through distributed
@@ -705,7 +707,7 @@ struct GridInitBufs {
 // wait.acquire, ~0.2 us) followed by four 16-byte ld.shared::cluster loads per peer.  Same arithmetic, same candidate rule,
 // same fixed summation tree: the chosen centres are those of the grid form with the same CTA count.
 constexpr int kClusterInitMax = 16;
-constexpr bool kClusterInitDefault = false;  // until measured on B200: opt-in with CSB_INIT_CLUSTER=1
+constexpr bool kClusterInitDefault = true;   // CSB_INIT_CLUSTER=0: the cooperative grid with the software barrier (validation)
 struct __align__(16) ClusterRound {  // what a CTA publishes per sampling round: 64 bytes = four 16-byte loads for a peer
   float part;
   int cnt;
@@ -734,9 +736,9 @@ __device__ __forceinline__ uint4 ld_cluster_v4(const void* local_smem, unsigned 
   return v;
 }
 
-template <bool CL>
-__global__ void __launch_bounds__(kGridInitThreads, 1) kmeanspp_grid_kernel(SolverArgs a, GridInitBufs b) {
-  constexpr int NW = kGridInitThreads / 32;
+template <bool CL, int NT, int U>
+__global__ void __launch_bounds__(NT, 1) kmeanspp_grid_kernel(SolverArgs a, GridInitBufs b) {
+  constexpr int NW = NT / 32;
   __shared__ float s_wv[NW];
   __shared__ int s_wi[NW];
   __shared__ float s_ws[NW];
@@ -755,15 +757,15 @@ __global__ void __launch_bounds__(kGridInitThreads, 1) kmeanspp_grid_kernel(Solv
     st->reseed_overflow = 0; st->n_noise_used = 0; st->min_margin = __int_as_float(0x7f800000); st->last_shift = 0.f;
   }
   mark(a, 1);
-  // frames of this thread: base + u * kGridInitThreads, u < kGridInitU, inside the CTA's contiguous slice
+  // frames of this thread: base + u * NT, u < U, inside the CTA's contiguous slice
   const int per_cta = (T + (int)nb - 1) / (int)nb;
   const int cta0 = blockIdx.x * per_cta, cta1 = min(T, cta0 + per_cta);
-  int fi[kGridInitU];
-  float near[kGridInitU];
-  double dg[kGridInitU];
+  int fi[U];
+  float near[U];
+  double dg[U];
 #pragma unroll
-  for (int u = 0; u < kGridInitU; ++u) {
-    const int i = cta0 + threadIdx.x + u * kGridInitThreads;
+  for (int u = 0; u < U; ++u) {
+    const int i = cta0 + threadIdx.x + u * NT;
     fi[u] = i < cta1 ? i : -1;
     near[u] = __int_as_float(0x7f800000);
     dg[u] = 0.0;
@@ -775,6 +777,12 @@ __global__ void __launch_bounds__(kGridInitThreads, 1) kmeanspp_grid_kernel(Solv
   unsigned bar = 0;
   int noise_row = 0, degenerate = 0, used = 0;
   const RngKey rk = load_rng(a);
+  const bool prof = b.profile && blockIdx.x == 0 && threadIdx.x == 0;
+  long long tacc[5] = {0, 0, 0, 0, 0}, tprev = 0;
+  int trounds = 0;
+  auto lap = [&](int i) {
+    if (prof) { const long long t = clock64(); tacc[i] += t - tprev; tprev = t; }
+  };
   int c = 0;
   if (a.n_init_given == 0) {  // :41 the first centre, from the built-in generator
     c = (int)(((unsigned long long)philox_draw(rk.seed, rk.offset, kRngFirst, 0u) * (unsigned)T) >> 32);
@@ -785,19 +793,20 @@ __global__ void __launch_bounds__(kGridInitThreads, 1) kmeanspp_grid_kernel(Solv
     if (m + 1 >= k) break;
     // ---- update the nearest distances with centre c; per-CTA partial of sum nearest^2 (:45-53) ----
     const bool sample_next = m + 1 >= a.n_init_given;
+    if (prof) { tprev = clock64(); ++trounds; }
     // (noise row `noise_row` = the one the next round consumes if it samples)
     const double gcc = __ldg(a.G + (int64_t)c * a.ldg + c);
     const double* gc = a.G + (int64_t)c * a.ldg;
-    double g[kGridInitU];
-    float nz[kGridInitU];
+    double g[U];
+    float nz[U];
 #pragma unroll
-    for (int u = 0; u < kGridInitU; ++u) {
+    for (int u = 0; u < U; ++u) {
       g[u] = fi[u] >= 0 ? __ldg(gc + fi[u]) : 0.0;
       nz[u] = (sample_next && fi[u] >= 0) ? (a.exp_noise ? noise_at<kNoiseArray>(a, rk, noise_row, fi[u]) : noise_at<kNoiseGen>(a, rk, noise_row, fi[u])) : 1.f;
     }
-    float part = 0.f, n2[kGridInitU], uq[kGridInitU], umax = 0.f;
+    float part = 0.f, n2[U], uq[U], umax = 0.f;
 #pragma unroll
-    for (int u = 0; u < kGridInitU; ++u) {
+    for (int u = 0; u < U; ++u) {
       n2[u] = 0.f; uq[u] = 0.f;
       if (fi[u] >= 0) {
         const double d2 = dg[u] + gcc - 2.0 * g[u];
@@ -810,8 +819,11 @@ __global__ void __launch_bounds__(kGridInitThreads, 1) kmeanspp_grid_kernel(Solv
       }
     }
     if (!sample_next) continue;  // the next centre is prescribed too: no total needed
+    lap(0);  // Gram row + noise loaded, distances updated
     part = warp_sum(part);
-    umax = warp_max(umax);
+    // the scores are non-negative floats: their order is the order of their bit patterns, so the maxima are single REDUX ops
+    if (CL) umax = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(umax)));
+    else umax = warp_max(umax);
     if (CL) {
       // One block barrier, then the cluster barrier: the per-warp partials are combined by warp 0 (fixed shuffle tree), every
       // thread takes the block maximum straight from the per-warp values, and the candidates go directly into the round buffer
@@ -821,9 +833,7 @@ __global__ void __launch_bounds__(kGridInitThreads, 1) kmeanspp_grid_kernel(Solv
       if (lane == 0) { s_ws[warp] = part; s_wv[warp] = umax; }
       if (threadIdx.x == 0) x->cnt = 0;
       __syncthreads();
-      float um = s_wv[0];
-#pragma unroll
-      for (int w = 1; w < NW; ++w) um = fmaxf(um, s_wv[w]);
+      const float um = __uint_as_float(__reduce_max_sync(0xffffffffu, lane < NW ? __float_as_uint(s_wv[lane]) : 0u));
       if (warp == 0) {
         const float t = warp_sum(lane < NW ? s_ws[lane] : 0.f);
         if (lane == 0) x->part = t;
@@ -831,13 +841,14 @@ __global__ void __launch_bounds__(kGridInitThreads, 1) kmeanspp_grid_kernel(Solv
       const float thr = um - um * 9.5367431640625e-7f;  // u_max * (1 - 2^-20)
       if (um > 0.f) {
 #pragma unroll
-        for (int u = 0; u < kGridInitU; ++u) {
+        for (int u = 0; u < U; ++u) {
           if (fi[u] >= 0 && uq[u] >= thr) {
             const int slot = atomicAdd(&x->cnt, 1);
             if (slot < kGridInitCand) { x->n2[slot] = n2[u]; x->nz[slot] = nz[u]; x->idx[slot] = fi[u]; }
           }
         }
       }
+      lap(1);  // block reduction, candidates published
       cluster_barrier();  // every thread of every CTA: releases the writes above, acquires the peers'
     } else {
       if (lane == 0) { s_ws[warp] = part; s_wv[warp] = umax; }
@@ -855,7 +866,7 @@ __global__ void __launch_bounds__(kGridInitThreads, 1) kmeanspp_grid_kernel(Solv
         const float thr = um - um * 9.5367431640625e-7f;  // u_max * (1 - 2^-20)
         if (um > 0.f) {
 #pragma unroll
-          for (int u = 0; u < kGridInitU; ++u) {
+          for (int u = 0; u < U; ++u) {
             if (fi[u] >= 0 && uq[u] >= thr) {
               const int slot = atomicAdd(&s_cnt, 1);
               if (slot < kGridInitCand) { s_cn2[slot] = n2[u]; s_cnz[slot] = nz[u]; s_ci[slot] = fi[u]; }
@@ -870,8 +881,10 @@ __global__ void __launch_bounds__(kGridInitThreads, 1) kmeanspp_grid_kernel(Solv
         const int64_t o = ((int64_t)(m & 1) * nb + blockIdx.x) * kGridInitCand + threadIdx.x;
         b.cand_n2[o] = s_cn2[threadIdx.x]; b.cand_nz[o] = s_cnz[threadIdx.x]; b.cand_i[o] = s_ci[threadIdx.x];
       }
+      lap(1);
       grid_sync(b.barrier, bar, nb);
     }
+    lap(2);  // barrier
     const int rb = CL ? (m & 1) : 0;
     // ---- total (fixed shuffle tree: the same bits in every CTA), overflow flag, candidates ----
     // lane q takes CTA q (q += 32): its partial, count and all candidate slots are loaded together -- one L2 round trip
@@ -922,16 +935,24 @@ __global__ void __launch_bounds__(kGridInitThreads, 1) kmeanspp_grid_kernel(Solv
               const int oi = cix[r][sl];
               if (sc > gb || (sc == gb && oi < gi)) { gb = sc; gi = oi; }
             }
+        if (CL) {
+          // (largest score, then lowest frame) with two REDUX ops: scores are >= +0, a lane without a candidate has key 0
+          const unsigned key = gb < 0.f ? 0u : __float_as_uint(gb) + 1u;
+          const unsigned kmax = __reduce_max_sync(0xffffffffu, key);
+          gi = __reduce_min_sync(0xffffffffu, (key == kmax && kmax != 0u) ? gi : 0x7fffffff);
+        } else {
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-          const float ov = __shfl_xor_sync(0xffffffffu, gb, o);
-          const int oi = __shfl_xor_sync(0xffffffffu, gi, o);
-          if (ov > gb || (ov == gb && oi < gi)) { gb = ov; gi = oi; }
+          for (int o = 16; o > 0; o >>= 1) {
+            const float ov = __shfl_xor_sync(0xffffffffu, gb, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, gi, o);
+            if (ov > gb || (ov == gb && oi < gi)) { gb = ov; gi = oi; }
+          }
         }
       }
       if (lane == 0) { s_sum[rb] = v; s_ovf[rb] = ovf; s_c[rb] = gi; }
     }
     __syncthreads();
+    lap(3);  // peers read, exact scores, winner broadcast
     const float sum = s_sum[rb];
     if (sum == 0.f) {  // :55-57 every frame coincides with a centre: host-drawn index, no noise row consumed
       ++degenerate;
@@ -948,7 +969,7 @@ __global__ void __launch_bounds__(kGridInitThreads, 1) kmeanspp_grid_kernel(Solv
         float best = -1.f;
         int besti = 0x7fffffff;
 #pragma unroll
-        for (int u = 0; u < kGridInitU; ++u) {
+        for (int u = 0; u < U; ++u) {
           if (fi[u] >= 0) {
             const float sc = __fdiv_rn(__fdiv_rn(n2[u], sum), nz[u]);
             if (sc > best) { best = sc; besti = fi[u]; }  // fi ascending in u: first max kept
@@ -1004,6 +1025,11 @@ __global__ void __launch_bounds__(kGridInitThreads, 1) kmeanspp_grid_kernel(Solv
     // s_c / s_sum are rewritten in the next round: a block barrier here, or (CL) results double-buffered by round parity --
     // buffer rb is rewritten in round m + 2, behind the block barrier of round m + 1 that every reader of round m has passed
     if (!CL) __syncthreads();
+    lap(4);
+  }
+  if (prof && trounds > 0) {
+    for (int i = 0; i < 5; ++i) b.part[i] = (float)((double)tacc[i] / trounds);
+    b.part[5] = (float)trounds;
   }
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     st->degenerate_rounds = degenerate;
@@ -1884,6 +1910,7 @@ int csb_kmeans_solve(const double* G, const void* timestamps, const csb_kmeans_p
     gb.best_v = reinterpret_cast<float*>(carve(sizeof(float) * nbi));
     gb.best_i = reinterpret_cast<int*>(carve(sizeof(int) * nbi));
     gb.force_exact = getenv("CSB_INIT_EXACT") ? 1 : 0;
+    gb.profile = getenv("CSB_INIT_PROFILE") ? 1 : 0;
     // One thread-block cluster when the stream fits 16 CTAs (T <= 32,768): hardware cluster barrier + DSMEM exchange per round
     // instead of the software grid barrier + L2 round trip.  The cluster size is a power of two (surplus CTAs own an empty
     // slice); sizes above 8 are non-portable and taken only if the device can place such a cluster.  CSB_INIT_CLUSTER=0: off.
@@ -1894,10 +1921,22 @@ int csb_kmeans_solve(const double* G, const void* timestamps, const csb_kmeans_p
       int csz = 2;
       while (csz < nbi && csz < kClusterInitMax) csz *= 2;
       if ((int64_t)csz * kGridInitThreads * kGridInitU < T) csz = kClusterInitMax;
+      if (const char* o = getenv("CSB_INIT_CLUSTER_SIZE")) {  // tuning aid: 2 / 4 / 8 / 16, if the stream fits
+        const int v = atoi(o);
+        if ((v == 2 || v == 4 || v == 8 || v == 16) && (int64_t)v * kGridInitThreads * kGridInitU >= T) csz = v;
+      }
+      // frames per CTA decide the block: one frame per thread keeps the per-round dependent chain (fp64 distance, square root,
+      // two divisions) at one frame's latency -- 1024 threads x 1 frame when the slice fits, else 512 threads x <= 4 frames
+      // (CSB_INIT_CLUSTER_BLOCK=512 forces the latter: tuning aid)
+      const int64_t per_cta = (T + csz - 1) / csz;
+      const char* blk_env = getenv("CSB_INIT_CLUSTER_BLOCK");
+      const int variant = (per_cta <= 512) ? 0 : ((per_cta <= 1024 && !(blk_env && atoi(blk_env) == 512)) ? 1 : 2);
+      void (*ckern)(SolverArgs, GridInitBufs) = variant == 0 ? kmeanspp_grid_kernel<true, 512, 1>
+                                               : (variant == 1 ? kmeanspp_grid_kernel<true, 1024, 1> : kmeanspp_grid_kernel<true, kGridInitThreads, kGridInitU>);
       cudaLaunchConfig_t cfg;
       memset(&cfg, 0, sizeof(cfg));
       cfg.gridDim = dim3((unsigned)csz);
-      cfg.blockDim = dim3(kGridInitThreads);
+      cfg.blockDim = dim3(variant == 1 ? 1024 : 512);
       cfg.stream = s;
       cudaLaunchAttribute cattr[1];
       cattr[0].id = cudaLaunchAttributeClusterDimension;
@@ -1907,19 +1946,19 @@ int csb_kmeans_solve(const double* G, const void* timestamps, const csb_kmeans_p
       cfg.attrs = cattr;
       cfg.numAttrs = 1;
       bool ok = true;
-      if (csz > 8) ok = cudaFuncSetAttribute(kmeanspp_grid_kernel<true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess;
+      if (csz > 8) ok = cudaFuncSetAttribute(ckern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess;
       int n_clusters = 0;
-      if (ok) ok = cudaOccupancyMaxActiveClusters(&n_clusters, kmeanspp_grid_kernel<true>, &cfg) == cudaSuccess && n_clusters >= 1;
+      if (ok) ok = cudaOccupancyMaxActiveClusters(&n_clusters, ckern, &cfg) == cudaSuccess && n_clusters >= 1;
       if (!ok) cudaGetLastError();  // not placeable here: clear the error, take the cooperative grid below
       if (ok) {
-        e = cudaLaunchKernelEx(&cfg, kmeanspp_grid_kernel<true>, a, gb);
+        e = cudaLaunchKernelEx(&cfg, ckern, a, gb);
         if (e != cudaSuccess) { set_error("kmeans_solve: cluster init launch: %s", cudaGetErrorString(e)); return CSB_ERR_CUDA; }
         clustered = true;
       }
     }
     if (!clustered) {
       void* iargs[] = {&a, &gb};
-      e = cudaLaunchCooperativeKernel((const void*)kmeanspp_grid_kernel<false>, dim3((unsigned)nbi), dim3(kGridInitThreads), iargs, 0, s);
+      e = cudaLaunchCooperativeKernel((const void*)kmeanspp_grid_kernel<false, kGridInitThreads, kGridInitU>, dim3((unsigned)nbi), dim3(kGridInitThreads), iargs, 0, s);
       if (e != cudaSuccess) { set_error("kmeans_solve: init launch: %s", cudaGetErrorString(e)); return CSB_ERR_CUDA; }
     }
     count_launch(1);

@@ -55,6 +55,28 @@ for T in sizes:
         row[f"{mode}_iterations"] = st["iterations"]
         row[f"{mode}_init_noise_ms"] = round(timed(lambda: solve_noise(0), 3), 4)
         picks[mode, "noise"] = buf.init_indices.cpu().clone()
+    # per-phase clock cycles of a sampling round (thread 0 of CTA 0): loads + update | block reduction + publish | barrier |
+    # peers + scores + broadcast | rest
+    os.environ["CSB_INIT_PROFILE"] = "1"
+    off = (8 * T + 255) // 256 * 256
+    for mode, csz, blk in (("cluster", None, None), ("cluster", None, 512), ("cluster", 8, None), ("cluster", 8, 512), ("grid", None, None)):
+        os.environ["CSB_INIT_CLUSTER"] = "1" if mode == "cluster" else "0"
+        if csz:
+            os.environ["CSB_INIT_CLUSTER_SIZE"] = str(csz)
+        if blk:
+            os.environ["CSB_INIT_CLUSTER_BLOCK"] = str(blk)
+        buf.init_indices[0] = first
+        ops.kmeans_solve(G, ts, buf, n_init_given=1, exp_noise=noise, reseed_pool=pool, max_iteration=-1)
+        torch.cuda.synchronize()
+        tag = f"{mode}{csz or ''}{'_b512' if blk else ''}"
+        row[f"{tag}_phase_cycles"] = [round(float(v), 1) for v in buf.workspace[off: off + 24].view(torch.float32).cpu()]
+        picks[tag] = buf.init_indices.cpu().clone()
+        ms = timed(lambda: ops.kmeans_solve(G, ts, buf, n_init_given=1, exp_noise=noise, reseed_pool=pool, max_iteration=-1), 2)
+        row[f"{tag}_prof_ms"] = round(ms, 4)
+        os.environ.pop("CSB_INIT_CLUSTER_SIZE", None)
+        os.environ.pop("CSB_INIT_CLUSTER_BLOCK", None)
+    row["same_centres_variants"] = all(bool(torch.equal(picks["grid"], picks[t])) for t in ("cluster", "cluster_b512", "cluster8", "cluster8_b512"))
+    os.environ.pop("CSB_INIT_PROFILE")
     os.environ.pop("CSB_INIT_CLUSTER")
     row["same_centres_rng"] = bool(torch.equal(picks["cluster", "rng"], picks["grid", "rng"]))
     row["same_assignments_rng"] = bool(torch.equal(picks["cluster", "rng_assign"], picks["grid", "rng_assign"]))
