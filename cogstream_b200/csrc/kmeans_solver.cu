@@ -54,6 +54,9 @@ struct SolverArgs {
   unsigned* noise_ready;  // arrival counter of those CTAs
   int init_exact;     // validation switch (CSB_INIT_EXACT): every sampling round evaluates the exact IEEE scores
   int32_t* assign32;  // [T] compact copy of the assignments (what every CTA reloads after the barrier)
+  int assign_words;   // 4-byte words reserved for the shared-memory assignment array (16-bit entries; T words when the fused init
+                      // aliases it as float[T])
+  int assign_exact;   // validation switch (CSB_ASSIGN_EXACT): the wide assignment pass evaluates every cluster exactly (no filter)
 };
 
 __device__ __forceinline__ void grid_sync(unsigned* counter, unsigned& target, unsigned nblocks) {
@@ -395,7 +398,7 @@ __device__ __forceinline__ void kmeanspp_block(const SolverArgs& a, float* s_nea
 // warp does the whole range when those counters would not fit.  Empty clusters take the next frame of the
 // reseed pool in ascending cluster order (:118).
 struct MemberSmem {
-  int* assign;   // [T] new assignments
+  const unsigned short* assign;  // [T] new assignments (k <= 4096: 16 bits each)
   int* offs;     // [k+1]
   int* memb;     // [T+k]
   int* cursor;   // [k+1] scratch
@@ -1126,6 +1129,7 @@ __device__ __forceinline__ void assign_pass(const SolverArgs& a, const double* _
     double sv[kWB][4];
     float dc[4];
     TS tc[4];
+    double d2lo = __longlong_as_double(0x7ff0000000000000ll), d2hi = -d2lo;  // WIDE: extremes of the squared feature distance
     if (WIDE) {
 #pragma unroll
       for (int bk = 0; bk < kWB; ++bk)
@@ -1134,6 +1138,8 @@ __device__ __forceinline__ void assign_pass(const SolverArgs& a, const double* _
           const int j = bk * 128 + lane + 32 * u;
           sv[bk][u] = j < k ? __ldcg(S + (int64_t)i * k + j) : 0.0;
         }
+      // The row extremes of d = (float)sqrt(max(d2, 0)) are the images of the extremes of d2 (clamp, square root and rounding are
+      // monotone), so this pass needs no square root: two per frame follow the reduction.
 #pragma unroll
       for (int bk = 0; bk < kWB; ++bk)
 #pragma unroll
@@ -1141,10 +1147,9 @@ __device__ __forceinline__ void assign_pass(const SolverArgs& a, const double* _
           const int j = bk * 128 + lane + 32 * u;
           if (j < k) {
             const double d2 = gii - 2.0 * (sv[bk][u] * s_rn[j]) + q[j];
-            const float d = (float)sqrt(d2 > 0.0 ? d2 : 0.0);
             TS dt = ti - (TS)ctc[j];
             dt = dt < TS(0) ? -dt : dt;
-            fmin_ = fminf(fmin_, d); fmax_ = fmaxf(fmax_, d);
+            d2lo = d2 < d2lo ? d2 : d2lo; d2hi = d2 > d2hi ? d2 : d2hi;
             tmin_ = dt < tmin_ ? dt : tmin_; tmax_ = dt > tmax_ ? dt : tmax_;
           }
         }
@@ -1191,11 +1196,22 @@ __device__ __forceinline__ void assign_pass(const SolverArgs& a, const double* _
       }
     }
     }
+    if (WIDE) {
+      for (int o = 16; o > 0; o >>= 1) {
+        const double f0 = __shfl_xor_sync(0xffffffffu, d2lo, o), f1 = __shfl_xor_sync(0xffffffffu, d2hi, o);
+        const TS t0 = __shfl_xor_sync(0xffffffffu, tmin_, o), t1 = __shfl_xor_sync(0xffffffffu, tmax_, o);
+        d2lo = f0 < d2lo ? f0 : d2lo; d2hi = f1 > d2hi ? f1 : d2hi;
+        tmin_ = t0 < tmin_ ? t0 : tmin_; tmax_ = t1 > tmax_ ? t1 : tmax_;
+      }
+      fmin_ = (float)sqrt(d2lo > 0.0 ? d2lo : 0.0);
+      fmax_ = (float)sqrt(d2hi > 0.0 ? d2hi : 0.0);
+    } else {
     for (int o = L >> 1; o > 0; o >>= 1) {  // min / max over the group's lanes
       const float f0 = __shfl_xor_sync(0xffffffffu, fmin_, o), f1 = __shfl_xor_sync(0xffffffffu, fmax_, o);
       const TS t0 = __shfl_xor_sync(0xffffffffu, tmin_, o), t1 = __shfl_xor_sync(0xffffffffu, tmax_, o);
       fmin_ = f0 < fmin_ ? f0 : fmin_; fmax_ = f1 > fmax_ ? f1 : fmax_;
       tmin_ = t0 < tmin_ ? t0 : tmin_; tmax_ = t1 > tmax_ ? t1 : tmax_;
+    }
     }
     const float fspread = __fsub_rn(fmax_, fmin_);
     const TS tspread = tmax_ - tmin_;
@@ -1222,12 +1238,54 @@ __device__ __forceinline__ void assign_pass(const SolverArgs& a, const double* _
       else if (fin < second) second = fin;
     };
     if (WIDE) {
+      // Filter.  The exact final distance F_j = sqrt(nf_j^2 + alpha nt_j^2) (:101) costs three fp64 square roots and two IEEE
+      // divisions per cluster; with k ~ 1000 clusters per frame that arithmetic IS the pass.  An fp32 estimate F~_j (approximate
+      // square root, reciprocal multiplies) is within E of F_j:
+      //   |nf~ - nf| <= 4e-7 fmax / (fmax - fmin) + 3e-7   (the estimate of d is within 3 ulp of the double-rounded exact d)
+      //   sqrt(alpha) |nt~ - nt| <= 3e-7 sqrt(alpha),  fp32 evaluation of F~ and the final roundings of F: < 5e-7
+      // so with E = 5e-7 fmax / (fmax - fmin) + 1e-6 (2 + sqrt(alpha)) the reference's pick (smallest F, lowest index on ties)
+      // is among the clusters with F~_j <= min F~ + 2 E.  Only those (and the second smallest estimate, for the margin
+      // diagnostic) are evaluated exactly -- typically 2 of k.  A NaN / overflowing estimate counts as a candidate.
+      const float inv_f = fmax_ > fmin_ ? __frcp_rn(fspread) : 0.f;
+      const float inv_t = tmax_ > tmin_ ? __frcp_rn((float)tspread) : 0.f;
+      const float alf = (float)alpha;
+      float f2[kWB][4];
+      float m1 = __int_as_float(0x7f800000), m2 = m1;
+      if (a.assign_exact != 1 && a.assign_exact != 3) {
+#pragma unroll
+        for (int bk = 0; bk < kWB; ++bk)
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int j = bk * 128 + lane + 32 * u;
+            f2[bk][u] = __int_as_float(0x7f800000);
+            if (j < k) {
+              const double d2 = gii - 2.0 * (sv[bk][u] * s_rn[j]) + q[j];
+              float da;
+              asm("sqrt.approx.f32 %0, %1;" : "=f"(da) : "f"((float)(d2 > 0.0 ? d2 : 0.0)));
+              TS dt = ti - (TS)ctc[j];
+              dt = dt < TS(0) ? -dt : dt;
+              const float nf = (da - fmin_) * inv_f, nt = (float)(dt - tmin_) * inv_t;
+              const float v = fmaf(alf * nt, nt, nf * nf);
+              f2[bk][u] = v;
+              if (v < m1) { m2 = m1; m1 = v; }
+              else if (v < m2) m2 = v;
+            }
+          }
+        for (int o = 16; o > 0; o >>= 1) {
+          const float o1 = __shfl_xor_sync(0xffffffffu, m1, o), o2 = __shfl_xor_sync(0xffffffffu, m2, o);
+          m2 = fminf(fmaxf(m1, o1), fminf(m2, o2));
+          m1 = fminf(m1, o1);
+        }
+      }
+      const float E = 5e-7f * (fmax_ > fmin_ ? fmax_ * inv_f : 0.f) + 1e-6f * (2.f + sqrtf(alf));
+      const float thrF = sqrtf(m1) + 2.f * E;
+      const float thr2 = a.assign_exact == 1 ? __int_as_float(0x7f800000) : (a.assign_exact >= 2 ? -1.f : fmaxf(thrF * thrF * 1.000001f, m2));
 #pragma unroll
       for (int bk = 0; bk < kWB; ++bk)
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
           const int j = bk * 128 + lane + 32 * u;
-          if (j < k) {  // same arithmetic as the first pass: the same d, dt bits
+          if (j < k && (a.assign_exact == 1 || !(f2[bk][u] > thr2))) {  // same arithmetic as the first pass: the same d2, dt bits
             const double d2 = gii - 2.0 * (sv[bk][u] * s_rn[j]) + q[j];
             const float d = (float)sqrt(d2 > 0.0 ? d2 : 0.0);
             TS dt = ti - (TS)ctc[j];
@@ -1269,6 +1327,7 @@ __device__ __forceinline__ void assign_pass(const SolverArgs& a, const double* _
       second = fminf(hi, fminf(second, os));
       if (ob < best || (ob == best && oj < bestj)) { best = ob; bestj = oj; }
     }
+    if (WIDE && a.assign_exact >= 2) bestj = 0;  // (timing aids: no cluster was evaluated)
     if (sub == 0 && frame_ok) {
       a.assignments[i] = bestj;  // :104 lowest index on ties
       a.assign32[i] = bestj;
@@ -1379,10 +1438,10 @@ __global__ void __launch_bounds__(kSolverThreads, WIDE ? 1 : 2) kmeans_solver_ke
   double* s_nn = smem_d + 5 * k;
   double* s_red = smem_d + 6 * k;
   double* s_diag = s_red + 32;
-  // ints: assign[T], offs[k+1], cursor[k+1], memb[T+k], changed[k], ver[k], verbuf[2][k], cols[k], cntw[nw*k]
+  // ints: assign[T] (16-bit entries, assign_words words), offs[k+1], cursor[k+1], memb[T+k], changed[k], ver[k], verbuf[2][k], cols[k], cntw[nw*k]
   TS* s_ts = reinterpret_cast<TS*>(s_diag + T);  // [T] (8-byte slots) next to the diagonal, same condition
-  int* s_assign = reinterpret_cast<int*>(s_diag + (a.diag_in_smem ? 2 * T : 0));
-  int* s_offs = s_assign + T;
+  unsigned short* s_assign = reinterpret_cast<unsigned short*>(s_diag + (a.diag_in_smem ? 2 * T : 0));
+  int* s_offs = reinterpret_cast<int*>(s_assign) + a.assign_words;
   int* s_cursor = s_offs + (k + 1);
   int* s_memb = s_cursor + (k + 1);
   int* s_changed = s_memb + (T + k);
@@ -1502,7 +1561,7 @@ __global__ void __launch_bounds__(kSolverThreads, WIDE ? 1 : 2) kmeans_solver_ke
     for (int i = threadIdx.x; i < T; i += blockDim.x) {
       const int now = __ldcg(a.assign32 + i), before = s_assign[i];  // (s_assign holds garbage before the first iteration)
       if (it > 1 && now != before) { s_changed[before] = 1; s_changed[now] = 1; moved = 1; }
-      s_assign[i] = now;
+      s_assign[i] = (unsigned short)now;
     }
     // No frame moved and no cluster was empty (an empty cluster is re-seeded with a fresh draw every iteration, :117-120): the
     // membership, hence every centre, is what it was -- the centre shift is exactly 0 and the reference stops here (:130).  Every
@@ -1603,8 +1662,8 @@ __global__ void __launch_bounds__(kSolverThreads, 1) lloyd_phase_kernel(SolverAr
   double* s_red = smem_d + 6 * k;
   double* s_diag = s_red + 32;
   TS* s_ts = reinterpret_cast<TS*>(s_diag + T);
-  int* s_assign = reinterpret_cast<int*>(s_diag + (a.diag_in_smem ? 2 * T : 0));
-  int* s_offs = s_assign + T;
+  unsigned short* s_assign = reinterpret_cast<unsigned short*>(s_diag + (a.diag_in_smem ? 2 * T : 0));
+  int* s_offs = reinterpret_cast<int*>(s_assign) + a.assign_words;
   int* s_cursor = s_offs + (k + 1);
   int* s_memb = s_cursor + (k + 1);
   int* s_changed = s_memb + (T + k);
@@ -1674,7 +1733,7 @@ __global__ void __launch_bounds__(kSolverThreads, 1) lloyd_phase_kernel(SolverAr
     for (int i = threadIdx.x; i < T; i += blockDim.x) {
       const int now = __ldcg(a.assign32 + i), before = L.assign_prev[i];
       if (it > 1 && now != before) { s_changed[before] = 1; s_changed[now] = 1; }
-      s_assign[i] = now;
+      s_assign[i] = (unsigned short)now;
     }
     __syncthreads();
     MemberSmem ms;
@@ -1786,15 +1845,20 @@ __global__ void __launch_bounds__(kSolverThreads, 1) lloyd_phase_kernel(SolverAr
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 struct SolverSmemPlan {
-  int diag_in_smem, multiwarp_fill;
+  int diag_in_smem, multiwarp_fill, assign_words;
   size_t bytes;
 };
 
 static SolverSmemPlan plan_smem(int64_t T, int64_t k) {
   SolverSmemPlan p;
-  const size_t base = sizeof(double) * (6 * k + 32) + sizeof(int) * (2 * T + 8 * k + 4) + 16;
+  // assignments are 16-bit in shared memory (k <= 4096); short streams keep T words, the fused init aliases them as float[T].
+  // At BASELINE config 4 (T = 14,400, k = 960) that is what lets the per-warp counters of the membership rebuild fit under the
+  // 196 KB carve-out (190 KB in all): the rebuild runs 8 warps wide (143 -> 55 us per iteration) and the L1 keeps 60 KB for the
+  // Gram-row streaming of the S pass (with the 228 KB carve-out that pass ran 1.5x slower).
+  p.assign_words = (int)(T <= 1024 ? T : (T + 1) / 2);
+  const size_t base = sizeof(double) * (6 * k + 32) + sizeof(int) * ((size_t)p.assign_words + T + 8 * k + 4) + 16;
   const size_t budget = 200 * 1024;
-  p.multiwarp_fill = (base + sizeof(int) * kSolverWarps * k <= budget) ? 1 : 0;
+  p.multiwarp_fill = (base + sizeof(int) * kSolverWarps * k <= budget && !getenv("CSB_NO_MULTIWARP")) ? 1 : 0;  // (env: tuning aid)
   size_t b = base + sizeof(int) * (p.multiwarp_fill ? kSolverWarps : 1) * k;
   p.diag_in_smem = (b + 2 * sizeof(double) * T <= budget) ? 1 : 0;  // Gram diagonal + timestamps
   if (p.diag_in_smem) b += 2 * sizeof(double) * T;
@@ -1853,8 +1917,9 @@ int csb_kmeans_solve(const double* G, const void* timestamps, const csb_kmeans_p
   a.init_indices = init_indices; a.exp_noise = exp_noise; a.reseed_pool = reseed_pool; a.assignments = assignments;
   a.ct_out = centroid_times; a.member_offsets = member_offsets; a.members = members; a.status = status;
   a.event_order = event_order; a.event_offsets = event_offsets;
-  a.diag_in_smem = sp.diag_in_smem; a.multiwarp_fill = sp.multiwarp_fill;
+  a.diag_in_smem = sp.diag_in_smem; a.multiwarp_fill = sp.multiwarp_fill; a.assign_words = sp.assign_words;
   a.init_exact = getenv("CSB_INIT_EXACT") ? 1 : 0;
+  a.assign_exact = getenv("CSB_ASSIGN_EXACT") ? atoi(getenv("CSB_ASSIGN_EXACT")) : 0;  // (2 / 3: timing aids, wrong results)
   a.rng = reinterpret_cast<const unsigned long long*>(p->rng_state);
   char* w = reinterpret_cast<char*>(workspace);
   a.diag = reinterpret_cast<double*>(w); w += align_up(sizeof(double) * T, 256);
@@ -2037,7 +2102,7 @@ int csb_kmeans_lloyd_phase(const double* G, const void* timestamps, const csb_km
   a.init_indices = init_indices; a.reseed_pool = reseed_pool; a.assignments = assignments;
   a.ct_out = centroid_times; a.member_offsets = member_offsets; a.members = members; a.status = status;
   a.event_order = event_order; a.event_offsets = event_offsets;
-  a.diag_in_smem = sp.diag_in_smem; a.multiwarp_fill = sp.multiwarp_fill;
+  a.diag_in_smem = sp.diag_in_smem; a.multiwarp_fill = sp.multiwarp_fill; a.assign_words = sp.assign_words;
   a.rng = reinterpret_cast<const unsigned long long*>(p->rng_state);
   char* w = reinterpret_cast<char*>(workspace);
   a.diag = reinterpret_cast<double*>(w); w += align_up(sizeof(double) * T, 256);

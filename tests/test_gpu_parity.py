@@ -1079,6 +1079,52 @@ def test_kmeanspp_long_stream_grid_init(dev, monkeypatch, T, P, D, seed, ts_dtyp
     assert torch.equal(res["1"][1], as_o) and res["1"][2] == info_o.iterations
 
 
+@pytest.mark.parametrize("case", ["scenes", "duplicates", "iid_small_spread", "f32_time", "near_duplicates"])
+def test_wide_assignment_filter_equals_exact(dev, monkeypatch, case):
+    """k > 128: the assignment pass evaluates the exact final distance (three fp64 square roots, two IEEE divisions) only for
+    the clusters whose fp32 estimate is within the proven error bound of the smallest estimate.  Same assignments, iteration
+    and re-seed counts, centre times as the pass that evaluates every cluster exactly (CSB_ASSIGN_EXACT=1), on inputs built to
+    stress the bound: exact ties (duplicated frames and centres), nearly equidistant clusters (small min-max spread), float32 time."""
+    T, P, D = (1700, 2, 64) if case != "iid_small_spread" else (1500, 8, 256)
+    k = 160 if case != "iid_small_spread" else 200
+    g = torch.Generator().manual_seed(len(case))
+    if case == "iid_small_spread":
+        feats = torch.randn(T, P * D, generator=g).to(torch.bfloat16)  # every frame about equally far from every centre
+    else:
+        feats, _ = synthetic.make_features(T, P, D, len(case))
+        feats = feats.view(T, P * D).clone()
+    if case == "duplicates":
+        for i in range(1, T, 3):
+            feats[i] = feats[i - 1]  # exact duplicates: ties between clusters seeded with copies of one frame
+    if case == "near_duplicates":
+        base = feats[::50].repeat_interleave(50, 0)[:T].float()
+        feats = (base + 1e-3 * torch.randn(T, P * D, generator=g)).to(torch.bfloat16)
+    ts = torch.arange(T, dtype=torch.float64) / 2.0
+    if case == "f32_time":
+        ts = ts.float()
+    if case == "duplicates":
+        init = list(range(0, 2 * k, 2))  # neighbours i, i+1 are often copies: duplicated centres
+    else:
+        init = torch.randperm(T, generator=g)[:k].tolist()
+    pool = torch.randint(0, T, (4096,), generator=g).tolist()
+    f3 = feats.view(T, P, D).to(dev)
+    res = {}
+    for mode in ("filter", "exact"):
+        if mode == "exact":
+            monkeypatch.setenv("CSB_ASSIGN_EXACT", "1")
+        _, ct, assign, info = kmeans_with_time_min_max(f3, ts.to(dev), k, init_indices=init, reseed_indices=pool, return_info=True)
+        res[mode] = (assign.cpu(), ct.cpu(), info.iterations, info.converged, info.n_reseed_used, info.min_margin)
+    monkeypatch.delenv("CSB_ASSIGN_EXACT")
+    a, b = res["filter"], res["exact"]
+    print(f"{case}: iterations {a[2]}, re-seeds {a[4]}, margin filter {a[5]:.3e} exact {b[5]:.3e}")
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]) and a[2:5] == b[2:5]
+    # the margin diagnostic is exact whenever it is small (both candidates inside the bound), else within the bound
+    assert a[5] == b[5] or (b[5] > 1e-6 and abs(a[5] - b[5]) < 1e-4)
+    _, _, as_o = orc.kmeans_with_time_min_max(feats.view(T, P, D), ts, k, init_indices=init, reseed_indices=pool)
+    if case not in ("iid_small_spread", "near_duplicates"):  # (there the reference's own fp32 sgemm noise decides some frames)
+        assert torch.equal(a[0], as_o)
+
+
 def test_scan_fallback_paths_agree(dev, monkeypatch):
     """The compaction / id-filter scans are single cooperative launches; grids beyond co-residency use the multi-launch
     "last block done" scans (forced here with CSB_NO_COOP_SCAN): identical outputs."""
