@@ -524,60 +524,90 @@ constexpr int kSE = 4;
 // contiguous bytes of Gram row m (the entry-per-thread gather below touches one 8-byte value per 32-byte sector once G no
 // longer fits in L2: 1.66 GB at T = 14,400).  Same values added in the same ascending member order -> the same bits.
 constexpr int kSRowGroup = 32;
-constexpr int kSR = 4;  // columns in flight per thread in the row-streaming variant (x 4 member loads each)
 constexpr int64_t kSRowMinEntries = 1 << 20;
+// NC columns x NM members in flight per thread (32 loads): 4 x 8 for ordinary member lists (T / k ~ 15 frames: two rounds per
+// 4 columns), 16 x 2 when every list of the group is short (the initial pass: one seed frame per cluster).
+template <int NC, int NM>
+__device__ __forceinline__ void s_rows_columns(const SolverArgs& a, const int* s_offs, const int* s_memb, const int* cols, int c0, int c1,
+                                               const double* gi, double* srow) {
+  for (int cc = c0; cc < c1; cc += NC) {
+    int beg[NC], len[NC], col[NC];
+    double s[NC];
+    int maxlen = 0;
+#pragma unroll
+    for (int u = 0; u < NC; ++u) {
+      s[u] = 0.0; len[u] = 0; beg[u] = 0; col[u] = -1;
+      if (cc + u < c1) {
+        col[u] = cols[cc + u];
+        beg[u] = s_offs[col[u]];
+        len[u] = s_offs[col[u] + 1] - beg[u];
+        maxlen = max(maxlen, len[u]);
+      }
+    }
+    for (int e = 0; e < maxlen; e += NM) {
+      double v[NC][NM];
+#pragma unroll
+      for (int u = 0; u < NC; ++u)
+#pragma unroll
+        for (int w = 0; w < NM; ++w) v[u][w] = (e + w < len[u]) ? __ldg(gi + (int64_t)s_memb[beg[u] + e + w] * a.ldg) : 0.0;
+#pragma unroll
+      for (int u = 0; u < NC; ++u)
+#pragma unroll
+        for (int w = 0; w < NM; ++w)
+          if (e + w < len[u]) s[u] += v[u][w];  // ascending member order, whatever the batch size
+    }
+#pragma unroll
+    for (int u = 0; u < NC; ++u)
+      if (col[u] >= 0) srow[col[u]] = s[u];
+  }
+}
+
+// Work items (a slab of 256 frames x a group of 32 listed columns) differ in cost with the cluster sizes, so the CTAs draw them
+// from a ticket counter instead of a static round-robin (the slowest CTA used to finish 40-200 us after the first).  The
+// counter is never reset: a pass consumes n_items + gridDim.x tickets (every CTA draws exactly one ticket past the end), so
+// every CTA knows the base of the next pass.  The next ticket is drawn before the current item is processed.
+template <bool DEEP>  // DEEP: the 255-register wide solver; else 16 loads in flight (the 128-register kernels must not spill)
 __device__ void compute_S_rows(const SolverArgs& a, const int* s_offs, const int* s_memb, const int* cols, int ncols, double* S, int f_begin,
-                               int f_end) {
+                               int f_end, unsigned& ticket_base) {
   const int k = a.k;
   const int n_slabs = (f_end - f_begin + (int)blockDim.x - 1) / (int)blockDim.x;
   const int n_groups = (ncols + kSRowGroup - 1) / kSRowGroup;
   const int n_items = n_slabs * n_groups;
-  for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+  unsigned* ticket = a.barrier + 1;
+  __shared__ int s_item;
+  unsigned next = 0;
+  if (threadIdx.x == 0) next = atomicAdd(ticket, 1u) - ticket_base;
+  for (;;) {
+    __syncthreads();  // the previous item's readers of s_item are done
+    if (threadIdx.x == 0) s_item = (int)next;
+    __syncthreads();
+    const int item = s_item;
+    if (item >= n_items) break;
+    if (threadIdx.x == 0) next = atomicAdd(ticket, 1u) - ticket_base;  // in flight while this item is processed
     const int slab = item % n_slabs, c0 = (item / n_slabs) * kSRowGroup;
     const int i = f_begin + slab * blockDim.x + threadIdx.x;
     if (i >= f_end) continue;
-    const double* gi = a.G + i;
     const int c1 = min(ncols, c0 + kSRowGroup);
-    for (int cc = c0; cc < c1; cc += kSR) {
-      int beg[kSR], len[kSR], col[kSR];
-      double s[kSR];
-      int maxlen = 0;
-#pragma unroll
-      for (int u = 0; u < kSR; ++u) {
-        s[u] = 0.0; len[u] = 0; beg[u] = 0; col[u] = -1;
-        if (cc + u < c1) {
-          col[u] = cols[cc + u];
-          beg[u] = s_offs[col[u]];
-          len[u] = s_offs[col[u] + 1] - beg[u];
-          maxlen = max(maxlen, len[u]);
-        }
-      }
-      for (int e = 0; e < maxlen; e += 4) {
-        double v[kSR][4];
-#pragma unroll
-        for (int u = 0; u < kSR; ++u)
-#pragma unroll
-          for (int w = 0; w < 4; ++w) v[u][w] = (e + w < len[u]) ? __ldg(gi + (int64_t)s_memb[beg[u] + e + w] * a.ldg) : 0.0;
-#pragma unroll
-        for (int u = 0; u < kSR; ++u)
-#pragma unroll
-          for (int w = 0; w < 4; ++w)
-            if (e + w < len[u]) s[u] += v[u][w];
-      }
-#pragma unroll
-      for (int u = 0; u < kSR; ++u)
-        if (col[u] >= 0) S[(int64_t)i * k + col[u]] = s[u];
+    if (DEEP) {
+      int gmax = 0;
+      for (int cc = c0; cc < c1; ++cc) gmax = max(gmax, s_offs[cols[cc] + 1] - s_offs[cols[cc]]);
+      if (gmax <= 2) s_rows_columns<16, 2>(a, s_offs, s_memb, cols, c0, c1, a.G + i, S + (int64_t)i * k);
+      else s_rows_columns<4, 8>(a, s_offs, s_memb, cols, c0, c1, a.G + i, S + (int64_t)i * k);
+    } else {
+      s_rows_columns<4, 4>(a, s_offs, s_memb, cols, c0, c1, a.G + i, S + (int64_t)i * k);
     }
   }
+  ticket_base += (unsigned)n_items + gridDim.x;
 }
 
 // Frames [f_begin, f_end) only: all of them in the single-GPU solver, a rank's own frames in the frame-sharded loop.
+template <bool DEEP>
 __device__ void compute_S(const SolverArgs& a, const int* s_offs, const int* s_memb, const int* cols, int ncols, double* S, int f_begin,
-                          int f_end) {
+                          int f_end, unsigned& ticket_base) {
   const int k = a.k;
   const int64_t total = (int64_t)(f_end - f_begin) * ncols;
   if (total >= kSRowMinEntries) {
-    compute_S_rows(a, s_offs, s_memb, cols, ncols, S, f_begin, f_end);
+    compute_S_rows<DEEP>(a, s_offs, s_memb, cols, ncols, S, f_begin, f_end, ticket_base);
     return;
   }
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -1451,7 +1481,7 @@ __global__ void __launch_bounds__(kSolverThreads, WIDE ? 1 : 2) kmeans_solver_ke
   int* s_cntw = s_cols + k;
   __shared__ int s_ncols;
 
-  unsigned bar = 0;
+  unsigned bar = 0, s_ticket = 0;
   const unsigned nb = gridDim.x;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   csb_kmeans_status* st = a.status;
@@ -1528,7 +1558,7 @@ __global__ void __launch_bounds__(kSolverThreads, WIDE ? 1 : 2) kmeans_solver_ke
   }
   if (threadIdx.x == 0) s_offs[k] = k;
   __syncthreads();
-  compute_S(a, s_offs, s_memb, s_cols, k, a.S[0], 0, T);
+  compute_S<WIDE>(a, s_offs, s_memb, s_cols, k, a.S[0], 0, T, s_ticket);
   grid_sync(a.barrier, bar, nb);
   mark(a, 3);
 
@@ -1595,7 +1625,7 @@ __global__ void __launch_bounds__(kSolverThreads, WIDE ? 1 : 2) kmeans_solver_ke
     }
     __syncthreads();
     mark(a, 12);
-    compute_S(a, s_offs, s_memb, s_cols, s_ncols, a.S[nxt], 0, T);
+    compute_S<WIDE>(a, s_offs, s_memb, s_cols, s_ncols, a.S[nxt], 0, T, s_ticket);
     mark(a, 13);
     grid_sync(a.barrier, bar, nb);
     mark(a, 14);
@@ -1674,6 +1704,7 @@ __global__ void __launch_bounds__(kSolverThreads, 1) lloyd_phase_kernel(SolverAr
   __shared__ int s_ncols;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const unsigned nb = gridDim.x;
+  unsigned s_ticket = 0;  // (the launcher zeroes the ticket counter in front of every launch that runs an S pass)
   const int nw = a.multiwarp_fill ? kSolverWarps : 1;
   const int cur = L.scal[kScCur], nxt = cur ^ 1;
   if (a.diag_in_smem)
@@ -1689,7 +1720,7 @@ __global__ void __launch_bounds__(kSolverThreads, 1) lloyd_phase_kernel(SolverAr
     }
     if (threadIdx.x == 0) s_offs[k] = k;
     __syncthreads();
-    compute_S(a, s_offs, s_memb, s_cols, k, a.S[0], L.f_begin, L.f_end);
+    compute_S<WIDE>(a, s_offs, s_memb, s_cols, k, a.S[0], L.f_begin, L.f_end, s_ticket);
     if (blockIdx.x == 0) {
       for (int j = threadIdx.x; j < k; j += blockDim.x) {
         const int c = s_memb[j];
@@ -1758,7 +1789,7 @@ __global__ void __launch_bounds__(kSolverThreads, 1) lloyd_phase_kernel(SolverAr
       if (lane == 0) s_ncols = nc;
     }
     __syncthreads();
-    compute_S(a, s_offs, s_memb, s_cols, s_ncols, a.S[nxt], L.f_begin, L.f_end);
+    compute_S<WIDE>(a, s_offs, s_memb, s_cols, s_ncols, a.S[nxt], L.f_begin, L.f_end, s_ticket);
     grid_sync(a.barrier, bar, nb);
     // exchange planes: what the (replicated) shift pass needs of this rank's rows
     const int64_t seg = 2 * (int64_t)L.per + k + 1;
@@ -2155,9 +2186,11 @@ int csb_kmeans_lloyd_phase(const double* G, const void* timestamps, const csb_km
   if (nb > sms) nb = sms;
   if (nb < 1) nb = 1;
   void* args[] = {&a, &L};
-  if (sh->phase == kLloydUpdate) {
-    e = cudaMemsetAsync(a.barrier, 0, 4, s);
+  if (sh->phase == kLloydInit || sh->phase == kLloydUpdate) {  // grid barrier word + the ticket counter of the S pass
+    e = cudaMemsetAsync(a.barrier, 0, 8, s);
     if (e != cudaSuccess) { set_error("kmeans_lloyd_phase: memset: %s", cudaGetErrorString(e)); return CSB_ERR_CUDA; }
+  }
+  if (sh->phase == kLloydUpdate) {
     e = cudaLaunchCooperativeKernel((const void*)kern, dim3((unsigned)nb), dim3(kSolverThreads), args, smem, s);
   } else {
     e = cudaLaunchKernel((const void*)kern, dim3((unsigned)nb), dim3(kSolverThreads), args, smem, s);
