@@ -56,6 +56,7 @@ struct SolverArgs {
   int32_t* assign32;  // [T] compact copy of the assignments (what every CTA reloads after the barrier)
   int assign_words;   // 4-byte words reserved for the shared-memory assignment array (16-bit entries; T words when the fused init
                       // aliases it as float[T])
+  int s_no_pairs;     // validation switch (CSB_S_NO_PAIRS): the row-streaming S pass with one frame per thread
   int assign_exact;   // validation switch (CSB_ASSIGN_EXACT): the wide assignment pass evaluates every cluster exactly (no filter)
 };
 
@@ -562,6 +563,51 @@ __device__ __forceinline__ void s_rows_columns(const SolverArgs& a, const int* s
   }
 }
 
+// Two adjacent frames per thread (one 16-byte load per member row) and 32-bit row offsets: the scalar form above spends ~15
+// integer instructions per 8-byte load (64-bit row offset, leading dimension re-read from the constant bank) and was
+// instruction-issue-bound (ncu: 59 % of the solver's instructions at BASELINE config 4), not memory-bound.  Needs an even
+// leading dimension, a 16-byte aligned G, even slice bounds and (T - 1) * ldg < 2^32; same values added in the same order.
+template <int NC, int NM>
+__device__ __forceinline__ void s_rows_columns2(const int* s_offs, const int* s_memb, const int* cols, int c0, int c1, const double* gi,
+                                                unsigned ldg, double* srow, int k) {
+  for (int cc = c0; cc < c1; cc += NC) {
+    int beg[NC], len[NC], col[NC];
+    double2 s[NC];
+    int maxlen = 0;
+#pragma unroll
+    for (int u = 0; u < NC; ++u) {
+      s[u] = make_double2(0.0, 0.0); len[u] = 0; beg[u] = 0; col[u] = -1;
+      if (cc + u < c1) {
+        col[u] = cols[cc + u];
+        beg[u] = s_offs[col[u]];
+        len[u] = s_offs[col[u] + 1] - beg[u];
+        maxlen = max(maxlen, len[u]);
+      }
+    }
+    for (int e = 0; e < maxlen; e += NM) {
+      double2 v[NC][NM];
+#pragma unroll
+      for (int u = 0; u < NC; ++u)
+#pragma unroll
+        for (int w = 0; w < NM; ++w) {
+          v[u][w] = make_double2(0.0, 0.0);
+          if (e + w < len[u]) {
+            const unsigned off = (unsigned)s_memb[beg[u] + e + w] * ldg;
+            v[u][w] = __ldg(reinterpret_cast<const double2*>(gi + off));
+          }
+        }
+#pragma unroll
+      for (int u = 0; u < NC; ++u)
+#pragma unroll
+        for (int w = 0; w < NM; ++w)
+          if (e + w < len[u]) { s[u].x += v[u][w].x; s[u].y += v[u][w].y; }
+    }
+#pragma unroll
+    for (int u = 0; u < NC; ++u)
+      if (col[u] >= 0) { srow[col[u]] = s[u].x; srow[k + col[u]] = s[u].y; }
+  }
+}
+
 // Work items (a slab of 256 frames x a group of 32 listed columns) differ in cost with the cluster sizes, so the CTAs draw them
 // from a ticket counter instead of a static round-robin (the slowest CTA used to finish 40-200 us after the first).  The
 // counter is never reset: a pass consumes n_items + gridDim.x tickets (every CTA draws exactly one ticket past the end), so
@@ -570,8 +616,13 @@ template <bool DEEP>  // DEEP: the 255-register wide solver; else 16 loads in fl
 __device__ void compute_S_rows(const SolverArgs& a, const int* s_offs, const int* s_memb, const int* cols, int ncols, double* S, int f_begin,
                                int f_end, unsigned& ticket_base) {
   const int k = a.k;
-  const int n_slabs = (f_end - f_begin + (int)blockDim.x - 1) / (int)blockDim.x;
-  const int n_groups = (ncols + kSRowGroup - 1) / kSRowGroup;
+  const bool pairs = DEEP && !a.s_no_pairs && (a.ldg & 1) == 0 && (reinterpret_cast<uintptr_t>(a.G) & 15u) == 0 && ((f_begin | f_end) & 1) == 0 &&
+                     (int64_t)(a.T - 1) * a.ldg < (1ll << 32);
+  const int fpt = pairs ? 2 : 1;                      // frames per thread
+  const int group = pairs ? kSRowGroup / 2 : kSRowGroup;  // listed columns per work item (items of about the same size either way)
+  const int slab_frames = (int)blockDim.x * fpt;
+  const int n_slabs = (f_end - f_begin + slab_frames - 1) / slab_frames;
+  const int n_groups = (ncols + group - 1) / group;
   const int n_items = n_slabs * n_groups;
   unsigned* ticket = a.barrier + 1;
   __shared__ int s_item;
@@ -584,15 +635,20 @@ __device__ void compute_S_rows(const SolverArgs& a, const int* s_offs, const int
     const int item = s_item;
     if (item >= n_items) break;
     if (threadIdx.x == 0) next = atomicAdd(ticket, 1u) - ticket_base;  // in flight while this item is processed
-    const int slab = item % n_slabs, c0 = (item / n_slabs) * kSRowGroup;
-    const int i = f_begin + slab * blockDim.x + threadIdx.x;
+    const int slab = item % n_slabs, c0 = (item / n_slabs) * group;
+    const int i = f_begin + slab * slab_frames + (int)threadIdx.x * fpt;
     if (i >= f_end) continue;
-    const int c1 = min(ncols, c0 + kSRowGroup);
+    const int c1 = min(ncols, c0 + group);
     if (DEEP) {
       int gmax = 0;
       for (int cc = c0; cc < c1; ++cc) gmax = max(gmax, s_offs[cols[cc] + 1] - s_offs[cols[cc]]);
-      if (gmax <= 2) s_rows_columns<16, 2>(a, s_offs, s_memb, cols, c0, c1, a.G + i, S + (int64_t)i * k);
-      else s_rows_columns<4, 8>(a, s_offs, s_memb, cols, c0, c1, a.G + i, S + (int64_t)i * k);
+      if (pairs) {
+        if (gmax <= 2) s_rows_columns2<16, 1>(s_offs, s_memb, cols, c0, c1, a.G + i, (unsigned)a.ldg, S + (int64_t)i * k, k);
+        else s_rows_columns2<4, 4>(s_offs, s_memb, cols, c0, c1, a.G + i, (unsigned)a.ldg, S + (int64_t)i * k, k);
+      } else {
+        if (gmax <= 2) s_rows_columns<16, 2>(a, s_offs, s_memb, cols, c0, c1, a.G + i, S + (int64_t)i * k);
+        else s_rows_columns<4, 8>(a, s_offs, s_memb, cols, c0, c1, a.G + i, S + (int64_t)i * k);
+      }
     } else {
       s_rows_columns<4, 4>(a, s_offs, s_memb, cols, c0, c1, a.G + i, S + (int64_t)i * k);
     }
@@ -1310,19 +1366,29 @@ __device__ __forceinline__ void assign_pass(const SolverArgs& a, const double* _
       const float E = 5e-7f * (fmax_ > fmin_ ? fmax_ * inv_f : 0.f) + 1e-6f * (2.f + sqrtf(alf));
       const float thrF = sqrtf(m1) + 2.f * E;
       const float thr2 = a.assign_exact == 1 ? __int_as_float(0x7f800000) : (a.assign_exact >= 2 ? -1.f : fmaxf(thrF * thrF * 1.000001f, m2));
+      // candidate slots of this lane as a bit mask; the exact evaluation is ONE copy of the code in a loop over the set bits
+      // (unrolled per slot it was 32 copies of ~200 instructions: the pass stalled on instruction fetch).  The S entry of a
+      // candidate is re-read (an L2 hit: the row was loaded a moment ago); slots ascend, so ties keep the lowest cluster.
+      unsigned cand = 0;
 #pragma unroll
       for (int bk = 0; bk < kWB; ++bk)
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
           const int j = bk * 128 + lane + 32 * u;
-          if (j < k && (a.assign_exact == 1 || !(f2[bk][u] > thr2))) {  // same arithmetic as the first pass: the same d2, dt bits
-            const double d2 = gii - 2.0 * (sv[bk][u] * s_rn[j]) + q[j];
-            const float d = (float)sqrt(d2 > 0.0 ? d2 : 0.0);
-            TS dt = ti - (TS)ctc[j];
-            dt = dt < TS(0) ? -dt : dt;
-            consider(d, dt, j);
-          }
+          if (j < k && (a.assign_exact == 1 || !(f2[bk][u] > thr2))) cand |= 1u << (bk * 4 + u);
         }
+#pragma unroll 1
+      while (cand) {
+        const int slot = __ffs(cand) - 1;
+        cand &= cand - 1;
+        const int j = (slot >> 2) * 128 + lane + 32 * (slot & 3);
+        const double svj = __ldcg(S + (int64_t)i * k + j);
+        const double d2 = gii - 2.0 * (svj * s_rn[j]) + q[j];  // same arithmetic as the first pass: the same d2, dt bits
+        const float d = (float)sqrt(d2 > 0.0 ? d2 : 0.0);
+        TS dt = ti - (TS)ctc[j];
+        dt = dt < TS(0) ? -dt : dt;
+        consider(d, dt, j);
+      }
     } else {
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
@@ -1951,6 +2017,7 @@ int csb_kmeans_solve(const double* G, const void* timestamps, const csb_kmeans_p
   a.diag_in_smem = sp.diag_in_smem; a.multiwarp_fill = sp.multiwarp_fill; a.assign_words = sp.assign_words;
   a.init_exact = getenv("CSB_INIT_EXACT") ? 1 : 0;
   a.assign_exact = getenv("CSB_ASSIGN_EXACT") ? atoi(getenv("CSB_ASSIGN_EXACT")) : 0;  // (2 / 3: timing aids, wrong results)
+  a.s_no_pairs = getenv("CSB_S_NO_PAIRS") ? 1 : 0;
   a.rng = reinterpret_cast<const unsigned long long*>(p->rng_state);
   char* w = reinterpret_cast<char*>(workspace);
   a.diag = reinterpret_cast<double*>(w); w += align_up(sizeof(double) * T, 256);

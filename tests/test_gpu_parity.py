@@ -1125,6 +1125,34 @@ def test_wide_assignment_filter_equals_exact(dev, monkeypatch, case):
         assert torch.equal(a[0], as_o)
 
 
+@pytest.mark.parametrize("T", [4100, 4101])
+def test_long_stream_S_pass_variants_agree(dev, monkeypatch, T):
+    """T x changed clusters >= 2^20: the S columns are accumulated by streaming Gram rows, two adjacent frames per thread
+    (16-byte loads, 32-bit row offsets) when T is even, one frame per thread otherwise (or with CSB_S_NO_PAIRS=1); work items are
+    drawn from a ticket counter.  Every variant gives the oracle's assignments and the same centre times / margin bits."""
+    P, D = 1, 64
+    k = math.ceil(T / 15)
+    feats, _ = synthetic.make_features(T, P, D, 7)
+    ts = torch.arange(T, dtype=torch.float64) / 2.0
+    g = torch.Generator().manual_seed(T)
+    init = torch.randperm(T, generator=g)[:k].tolist()
+    pool = torch.randint(0, T, (4096,), generator=g).tolist()
+    f3 = feats.view(T, P, D)
+    res = []
+    for no_pairs in (False, True):
+        if no_pairs:
+            monkeypatch.setenv("CSB_S_NO_PAIRS", "1")
+        _, ct, assign, info = kmeans_with_time_min_max(f3.to(dev), ts.to(dev), k, init_indices=init, reseed_indices=pool, return_info=True)
+        res.append((assign.cpu(), ct.cpu(), info.iterations, info.converged, info.n_reseed_used, info.min_margin))
+    monkeypatch.delenv("CSB_S_NO_PAIRS")
+    a, b = res
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]) and a[2:] == b[2:]
+    info_o = orc.KMeansInfo()
+    _, ct_o, as_o = orc.kmeans_with_time_min_max(f3, ts, k, init_indices=init, reseed_indices=pool, info=info_o)
+    assert torch.equal(a[0], as_o) and a[2] == info_o.iterations and a[4] == len(info_o.reseed_indices)
+    assert torch.equal(a[1], ct_o)
+
+
 def test_scan_fallback_paths_agree(dev, monkeypatch):
     """The compaction / id-filter scans are single cooperative launches; grids beyond co-residency use the multi-launch
     "last block done" scans (forced here with CSB_NO_COOP_SCAN): identical outputs."""
