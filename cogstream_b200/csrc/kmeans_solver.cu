@@ -525,6 +525,7 @@ constexpr int kSE = 4;
 // contiguous bytes of Gram row m (the entry-per-thread gather below touches one 8-byte value per 32-byte sector once G no
 // longer fits in L2: 1.66 GB at T = 14,400).  Same values added in the same ascending member order -> the same bits.
 constexpr int kSRowGroup = 32;
+constexpr int kSPairBatch = 8;  // member rows in flight per column and thread in the two-frames-per-thread form (x 4 columns x 16 bytes)
 constexpr int64_t kSRowMinEntries = 1 << 20;
 // NC columns x NM members in flight per thread (32 loads): 4 x 8 for ordinary member lists (T / k ~ 15 frames: two rounds per
 // 4 columns), 16 x 2 when every list of the group is short (the initial pass: one seed frame per cluster).
@@ -608,43 +609,42 @@ __device__ __forceinline__ void s_rows_columns2(const int* s_offs, const int* s_
   }
 }
 
-// Work items (a slab of 256 frames x a group of 32 listed columns) differ in cost with the cluster sizes, so the CTAs draw them
-// from a ticket counter instead of a static round-robin (the slowest CTA used to finish 40-200 us after the first).  The
-// counter is never reset: a pass consumes n_items + gridDim.x tickets (every CTA draws exactly one ticket past the end), so
-// every CTA knows the base of the next pass.  The next ticket is drawn before the current item is processed.
+// Work items (a slab of 32 or 64 frames x a group of listed columns) differ in cost with the cluster sizes, so every WARP draws
+// its items from a ticket counter instead of a static round-robin (the slowest CTA used to finish 40-200 us after the first, and
+// a CTA-wide item made seven warps wait for the eighth).  The counter is never reset: a pass consumes n_items + (warps in the
+// grid) tickets (every warp draws exactly one ticket past the end), so everybody knows the base of the next pass.  The next
+// ticket is drawn before the current item is processed.
 template <bool DEEP>  // DEEP: the 255-register wide solver; else 16 loads in flight (the 128-register kernels must not spill)
 __device__ void compute_S_rows(const SolverArgs& a, const int* s_offs, const int* s_memb, const int* cols, int ncols, double* S, int f_begin,
                                int f_end, unsigned& ticket_base) {
   const int k = a.k;
+  const int lane = threadIdx.x & 31;
   const bool pairs = DEEP && !a.s_no_pairs && (a.ldg & 1) == 0 && (reinterpret_cast<uintptr_t>(a.G) & 15u) == 0 && ((f_begin | f_end) & 1) == 0 &&
                      (int64_t)(a.T - 1) * a.ldg < (1ll << 32);
-  const int fpt = pairs ? 2 : 1;                      // frames per thread
-  const int group = pairs ? kSRowGroup / 2 : kSRowGroup;  // listed columns per work item (items of about the same size either way)
-  const int slab_frames = (int)blockDim.x * fpt;
+  const int fpt = pairs ? 2 : 1;                           // frames per thread
+  const int group = pairs ? kSRowGroup / 2 : kSRowGroup;   // listed columns per work item (items of about the same size either way)
+  const int slab_frames = 32 * fpt;
   const int n_slabs = (f_end - f_begin + slab_frames - 1) / slab_frames;
   const int n_groups = (ncols + group - 1) / group;
   const int n_items = n_slabs * n_groups;
   unsigned* ticket = a.barrier + 1;
-  __shared__ int s_item;
   unsigned next = 0;
-  if (threadIdx.x == 0) next = atomicAdd(ticket, 1u) - ticket_base;
+  if (lane == 0) next = atomicAdd(ticket, 1u) - ticket_base;
   for (;;) {
-    __syncthreads();  // the previous item's readers of s_item are done
-    if (threadIdx.x == 0) s_item = (int)next;
-    __syncthreads();
-    const int item = s_item;
+    const int item = (int)__shfl_sync(0xffffffffu, next, 0);
     if (item >= n_items) break;
-    if (threadIdx.x == 0) next = atomicAdd(ticket, 1u) - ticket_base;  // in flight while this item is processed
+    if (lane == 0) next = atomicAdd(ticket, 1u) - ticket_base;  // in flight while this item is processed
+    // consecutive tickets = consecutive slabs of one column group: the warps working side by side share the group's member rows
     const int slab = item % n_slabs, c0 = (item / n_slabs) * group;
-    const int i = f_begin + slab * slab_frames + (int)threadIdx.x * fpt;
-    if (i >= f_end) continue;
+    const int i = f_begin + slab * slab_frames + lane * fpt;
+    if (i < f_end) {  // (lanes past the slice end idle; they rejoin at the shuffle above)
     const int c1 = min(ncols, c0 + group);
     if (DEEP) {
       int gmax = 0;
       for (int cc = c0; cc < c1; ++cc) gmax = max(gmax, s_offs[cols[cc] + 1] - s_offs[cols[cc]]);
       if (pairs) {
         if (gmax <= 2) s_rows_columns2<16, 1>(s_offs, s_memb, cols, c0, c1, a.G + i, (unsigned)a.ldg, S + (int64_t)i * k, k);
-        else s_rows_columns2<4, 4>(s_offs, s_memb, cols, c0, c1, a.G + i, (unsigned)a.ldg, S + (int64_t)i * k, k);
+        else s_rows_columns2<4, kSPairBatch>(s_offs, s_memb, cols, c0, c1, a.G + i, (unsigned)a.ldg, S + (int64_t)i * k, k);
       } else {
         if (gmax <= 2) s_rows_columns<16, 2>(a, s_offs, s_memb, cols, c0, c1, a.G + i, S + (int64_t)i * k);
         else s_rows_columns<4, 8>(a, s_offs, s_memb, cols, c0, c1, a.G + i, S + (int64_t)i * k);
@@ -652,8 +652,10 @@ __device__ void compute_S_rows(const SolverArgs& a, const int* s_offs, const int
     } else {
       s_rows_columns<4, 4>(a, s_offs, s_memb, cols, c0, c1, a.G + i, S + (int64_t)i * k);
     }
+    }
   }
-  ticket_base += (unsigned)n_items + gridDim.x;
+  __syncwarp();
+  ticket_base += (unsigned)n_items + gridDim.x * (blockDim.x >> 5);
 }
 
 // Frames [f_begin, f_end) only: all of them in the single-GPU solver, a rank's own frames in the frame-sharded loop.
