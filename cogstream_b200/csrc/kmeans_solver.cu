@@ -788,6 +788,8 @@ struct GridInitBufs {
   float* best_v;      // [nb] exact fallback: per-CTA best score / frame
   int* best_i;
   int force_exact;    // profiling / test aid: always take the two-barrier exact path
+  int n_cluster;      // CL: CTAs of the sampling cluster (= the first cluster of the grid); the other clusters are helpers
+  int n_helpers;      // CL: helper CTAs that pre-generate the built-in generator's noise rows into a.noise_ws (0: none)
   int profile;        // profiling aid (CSB_INIT_PROFILE=1): thread 0 of CTA 0 sums the clock cycles of the five phases of a
                       // round and stores the per-round averages in part[0..5] (+ the round count) when the kernel ends
 };
@@ -840,9 +842,31 @@ __global__ void __launch_bounds__(NT, 1) kmeanspp_grid_kernel(SolverArgs a, Grid
   __shared__ ClusterRound s_x[2];  // CL: this CTA's published round data, double-buffered by round parity
   __shared__ __align__(8) unsigned s_fb[2];  // CL, exact fallback: this CTA's best {score bits, frame} (written / read between the two barriers of a round)
   const int T = a.T, k = a.k;
-  const unsigned nb = gridDim.x;
+  const unsigned nb = CL ? (unsigned)b.n_cluster : gridDim.x;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   csb_kmeans_status* st = a.status;
+  if (CL && blockIdx.x >= nb) {
+    // ---- helper clusters (built-in generator): all Exp(1) noise rows, 4 frames per Philox call, into the workspace; the 132
+    // SMs the sampling cluster leaves idle finish this in a few microseconds, and the sampling rounds then read a noise row like
+    // a caller-supplied one instead of running ~300 generator instructions per frame and round on 16 SMs.  Same values as
+    // noise_generate().  Arrival is counted on the grid-init barrier word; the sampling cluster waits for all helpers first.
+    const RngKey hk = load_rng(a);
+    const int q4 = (T + 3) >> 2;  // calls per row
+    const int64_t total = (int64_t)(k - 1) * q4;
+    for (int64_t e = (int64_t)(blockIdx.x - nb) * NT + threadIdx.x; e < total; e += (int64_t)b.n_helpers * NT) {
+      const int row = (int)(e / q4), cc = (int)(e - (int64_t)row * q4);
+      const uint4 x = philox_draw4(hk.seed, hk.offset, (uint32_t)row, (uint32_t)cc);
+      float* dst = a.noise_ws + (int64_t)row * T + 4 * cc;
+      const float v[4] = {exp1_from_bits(x.x), exp1_from_bits(x.y), exp1_from_bits(x.z), exp1_from_bits(x.w)};
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (4 * cc + u < T) __stcg(dst + u, v[u]);
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) atomicAdd(b.barrier, 1u);
+    return;
+  }
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     st->iterations = 0; st->converged = 0; st->n_reseed_used = 0; st->degenerate_rounds = 0;
     st->reseed_overflow = 0; st->n_noise_used = 0; st->min_margin = __int_as_float(0x7f800000); st->last_shift = 0.f;
@@ -879,6 +903,18 @@ __global__ void __launch_bounds__(NT, 1) kmeanspp_grid_kernel(SolverArgs a, Grid
     c = (int)(((unsigned long long)philox_draw(rk.seed, rk.offset, kRngFirst, 0u) * (unsigned)T) >> 32);
     if (blockIdx.x == 0 && threadIdx.x == 0) a.init_indices[0] = c;
   }
+  const bool noise_pre = CL && b.n_helpers > 0;  // the helper clusters' rows (else: the caller's array, or generated on the spot)
+  if (noise_pre) {
+    if (threadIdx.x == 0) {
+      unsigned v;
+      for (;;) {
+        asm volatile("ld.acquire.gpu.u32 %0, [%1];" : "=r"(v) : "l"(b.barrier) : "memory");
+        if (v >= (unsigned)b.n_helpers) break;
+        __nanosleep(200);
+      }
+    }
+    __syncthreads();
+  }
   for (int m = 0; m < k; ++m) {
     if (m < a.n_init_given) c = (int)a.init_indices[m];  // else: c was chosen at the end of the previous iteration
     if (m + 1 >= k) break;
@@ -893,7 +929,8 @@ __global__ void __launch_bounds__(NT, 1) kmeanspp_grid_kernel(SolverArgs a, Grid
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       g[u] = fi[u] >= 0 ? __ldg(gc + fi[u]) : 0.0;
-      nz[u] = (sample_next && fi[u] >= 0) ? (a.exp_noise ? noise_at<kNoiseArray>(a, rk, noise_row, fi[u]) : noise_at<kNoiseGen>(a, rk, noise_row, fi[u])) : 1.f;
+      nz[u] = (sample_next && fi[u] >= 0) ? (a.exp_noise ? noise_at<kNoiseArray>(a, rk, noise_row, fi[u])
+                                                          : (noise_pre ? noise_at<kNoiseWs>(a, rk, noise_row, fi[u]) : noise_at<kNoiseGen>(a, rk, noise_row, fi[u]))) : 1.f;
     }
     float part = 0.f, n2[U], uq[U], umax = 0.f;
 #pragma unroll
@@ -2076,6 +2113,7 @@ int csb_kmeans_solve(const double* G, const void* timestamps, const csb_kmeans_p
     gb.best_i = reinterpret_cast<int*>(carve(sizeof(int) * nbi));
     gb.force_exact = getenv("CSB_INIT_EXACT") ? 1 : 0;
     gb.profile = getenv("CSB_INIT_PROFILE") ? 1 : 0;
+    gb.n_cluster = 0; gb.n_helpers = 0;
     // One thread-block cluster when the stream fits 16 CTAs (T <= 32,768): hardware cluster barrier + DSMEM exchange per round
     // instead of the software grid barrier + L2 round trip.  The cluster size is a power of two (surplus CTAs own an empty
     // slice); sizes above 8 are non-portable and taken only if the device can place such a cluster.  CSB_INIT_CLUSTER=0: off.
@@ -2098,9 +2136,20 @@ int csb_kmeans_solve(const double* G, const void* timestamps, const csb_kmeans_p
       const int variant = (per_cta <= 512) ? 0 : ((per_cta <= 1024 && !(blk_env && atoi(blk_env) == 512)) ? 1 : 2);
       void (*ckern)(SolverArgs, GridInitBufs) = variant == 0 ? kmeanspp_grid_kernel<true, 512, 1>
                                                : (variant == 1 ? kmeanspp_grid_kernel<true, 1024, 1> : kmeanspp_grid_kernel<true, kGridInitThreads, kGridInitU>);
+      // built-in generator: further clusters of the same launch pre-generate the noise rows (into S[1], unused before the first
+      // Lloyd iteration) on the SMs the sampling cluster leaves idle (CSB_INIT_HELPERS=0: generate inside the rounds)
+      int n_hclusters = 0;
+      if (a.rng && !exp_noise && k > 1 && p->n_init_given < k && !(getenv("CSB_INIT_HELPERS") && atoi(getenv("CSB_INIT_HELPERS")) == 0)) {
+        n_hclusters = (sms - csz) / csz;
+        if (n_hclusters > 8) n_hclusters = 8;
+        if (n_hclusters < 0) n_hclusters = 0;
+      }
+      gb.n_cluster = csz;
+      gb.n_helpers = n_hclusters * csz;
+      if (gb.n_helpers > 0) a.noise_ws = reinterpret_cast<float*>(a.S[1]);
       cudaLaunchConfig_t cfg;
       memset(&cfg, 0, sizeof(cfg));
-      cfg.gridDim = dim3((unsigned)csz);
+      cfg.gridDim = dim3((unsigned)(csz * (1 + n_hclusters)));
       cfg.blockDim = dim3(variant == 1 ? 1024 : 512);
       cfg.stream = s;
       cudaLaunchAttribute cattr[1];
@@ -2120,6 +2169,7 @@ int csb_kmeans_solve(const double* G, const void* timestamps, const csb_kmeans_p
         if (e != cudaSuccess) { set_error("kmeans_solve: cluster init launch: %s", cudaGetErrorString(e)); return CSB_ERR_CUDA; }
         clustered = true;
       }
+      a.noise_ws = nullptr;  // (the solver launch below sets its own, for the fused init only)
     }
     if (!clustered) {
       void* iargs[] = {&a, &gb};

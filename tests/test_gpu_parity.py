@@ -1557,11 +1557,15 @@ def _philox_host(seed, offset, stream, index):
     return np.stack([c0, c1, c2, c3], axis=-1).astype(np.uint32)  # [..., 4]
 
 
-def test_builtin_generator_matches_host_replay(dev):
+@pytest.mark.parametrize("T,k,envs", [(300, 20, [{}]),
+                                      # long stream: k-means++ on a thread-block cluster; helper clusters pre-generate the noise rows,
+                                      # or the rounds generate them (CSB_INIT_HELPERS=0), or the cooperative grid does (CSB_INIT_CLUSTER=0)
+                                      (4160, 40, [{}, {"CSB_INIT_HELPERS": "0"}, {"CSB_INIT_CLUSTER": "0"}])])
+def test_builtin_generator_matches_host_replay(dev, monkeypatch, T, k, envs):
     """kmeans_solve with rng_state: the centres / assignments are those of the CPU oracle fed with the SAME draws (Philox replayed on
     the host: first centre, Exp(1) noise rows, re-seed indices); the offset advances by one per solve; same state -> same result."""
     import numpy as np
-    T, P, D, k = 300, 4, 64, 20
+    P, D = 4, 64
     feats, _ = synthetic.make_features(T, P, D, 17)
     f3 = feats.view(T, P, D)
     ts = torch.arange(T, dtype=torch.float64)
@@ -1569,14 +1573,19 @@ def test_builtin_generator_matches_host_replay(dev):
     G = ops.gram(x2)
     seed, off = 0x1234567890ABCDEF & (2 ** 62 - 1), 5
     runs = []
-    for rep in range(2):
+    for env in envs + envs[:1]:
+        for name, val in env.items():
+            monkeypatch.setenv(name, val)
         state = torch.tensor([seed, off], dtype=torch.int64, device=dev)
         buf = ops.KMeansBuffers(T, k, torch.float64, dev)
         ops.kmeans_solve(G, ts.to(dev), buf, n_init_given=0, exp_noise=None, reseed_pool=None, rng_state=state)
         st = ops.decode_status(buf.status)
         runs.append((buf.init_indices.cpu().tolist(), buf.assignments.cpu(), st["iterations"], st["n_reseed_used"]))
         assert state.tolist() == [seed, off + 1]
-    assert runs[0][0] == runs[1][0] and torch.equal(runs[0][1], runs[1][1])
+        for name in env:
+            monkeypatch.delenv(name)
+    for other in runs[1:]:
+        assert runs[0][0] == other[0] and torch.equal(runs[0][1], other[1]) and runs[0][2:] == other[2:]
     first = int((int(_philox_host(seed, off, 0xFFFFFFFF, [0])[0, 0]) * T) >> 32)
     # noise of sampling round r for frame i = component i & 3 of the call (i >> 2, stream r)
     calls = _philox_host(seed, off, np.arange(k - 1)[:, None].repeat(T // 4, 1), np.arange(T // 4)[None, :].repeat(k - 1, 0))  # [k-1, T/4, 4]
