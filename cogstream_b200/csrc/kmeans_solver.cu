@@ -509,7 +509,14 @@ __device__ void rebuild_members_smem(const SolverArgs& a, const MemberSmem& m, i
     const int beg = m.offs[j], end = m.offs[j + 1];
     TS tsum = TS(0);
     const void* tsrc = m.ts_smem ? m.ts_smem : a.ts;  // k threads x ~T/k dependent reads: shared memory when it fits
-    for (int e = beg; e < end; ++e) tsum += load_ts<TS>(tsrc, m.memb[e]);
+    for (int e = beg; e < end; e += 8) {  // 8 member timestamps in flight (global memory when the shared copy does not fit), added in member order
+      TS v[8];
+#pragma unroll
+      for (int w = 0; w < 8; ++w) v[w] = e + w < end ? load_ts<TS>(tsrc, m.memb[e + w]) : TS(0);
+#pragma unroll
+      for (int w = 0; w < 8; ++w)
+        if (e + w < end) tsum += v[w];
+    }
     m.ct_new[j] = (double)(TS)(tsum / (TS)(end - beg));
   }
   __syncthreads();
@@ -876,13 +883,15 @@ __global__ void __launch_bounds__(NT, 1) kmeanspp_grid_kernel(SolverArgs a, Grid
   const int per_cta = (T + (int)nb - 1) / (int)nb;
   const int cta0 = blockIdx.x * per_cta, cta1 = min(T, cta0 + per_cta);
   int fi[U];
-  float near[U];
+  float near[U];    // nearest distance squared (fp32, as the reference computes it)
+  double near2[U];  // smallest clamped fp64 squared distance so far
   double dg[U];
 #pragma unroll
   for (int u = 0; u < U; ++u) {
     const int i = cta0 + threadIdx.x + u * NT;
     fi[u] = i < cta1 ? i : -1;
     near[u] = __int_as_float(0x7f800000);
+    near2[u] = __longlong_as_double(0x7ff0000000000000ll);
     dg[u] = 0.0;
     if (fi[u] >= 0) {
       dg[u] = a.G[(int64_t)i * a.ldg + i];
@@ -892,7 +901,7 @@ __global__ void __launch_bounds__(NT, 1) kmeanspp_grid_kernel(SolverArgs a, Grid
   unsigned bar = 0;
   int noise_row = 0, degenerate = 0, used = 0;
   const RngKey rk = load_rng(a);
-  const bool prof = b.profile && blockIdx.x == 0 && threadIdx.x == 0;
+  const bool prof = CL && b.profile && blockIdx.x == 0 && threadIdx.x == 0;  // (the grid form has no registers to spare)
   long long tacc[5] = {0, 0, 0, 0, 0}, tprev = 0;
   int trounds = 0;
   auto lap = [&](int i) {
@@ -937,10 +946,17 @@ __global__ void __launch_bounds__(NT, 1) kmeanspp_grid_kernel(SolverArgs a, Grid
     for (int u = 0; u < U; ++u) {
       n2[u] = 0.f; uq[u] = 0.f;
       if (fi[u] >= 0) {
+        // nearest distance = min over the centres of (float)sqrt(max(d2, 0)) = the image of the smallest clamped d2 (clamp, square
+        // root and rounding are monotone): the fp64 square root (13 cycles per warp on the SM) runs only when a frame gets a
+        // nearer centre -- for whole warps of one scene at a time, and ever more rarely as the rounds go on
         const double d2 = dg[u] + gcc - 2.0 * g[u];
-        const float d = (float)sqrt(d2 > 0.0 ? d2 : 0.0);
-        near[u] = fminf(near[u], d);
-        n2[u] = __fmul_rn(near[u], near[u]);  // :53
+        const double d2c = d2 > 0.0 ? d2 : 0.0;
+        if (d2c < near2[u]) {
+          near2[u] = d2c;
+          const float d = (float)sqrt(d2c);
+          near[u] = __fmul_rn(d, d);  // nearest^2, :53
+        }
+        n2[u] = near[u];
         part += n2[u];
         uq[u] = n2[u] == 0.f ? 0.f : __fdiv_rn(n2[u] == 0.f ? 1.f : n2[u], nz[u]);  // (zero numerators: see kmeanspp_block)
         umax = fmaxf(umax, uq[u]);
@@ -1693,10 +1709,19 @@ __global__ void __launch_bounds__(kSolverThreads, WIDE ? 1 : 2) kmeans_solver_ke
     for (int j = threadIdx.x; j < k; j += blockDim.x) s_changed[j] = it == 1 ? 1 : 0;
     __syncthreads();
     int moved = 0;
-    for (int i = threadIdx.x; i < T; i += blockDim.x) {
-      const int now = __ldcg(a.assign32 + i), before = s_assign[i];  // (s_assign holds garbage before the first iteration)
-      if (it > 1 && now != before) { s_changed[before] = 1; s_changed[now] = 1; moved = 1; }
-      s_assign[i] = (unsigned short)now;
+    for (int i0 = threadIdx.x; i0 < T; i0 += 8 * blockDim.x) {  // 8 loads in flight per thread (one L2 round trip per 2048 frames)
+      int now[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) now[u] = i0 + u * blockDim.x < T ? __ldcg(a.assign32 + i0 + u * blockDim.x) : 0;
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int i = i0 + u * blockDim.x;
+        if (i < T) {
+          const int before = s_assign[i];  // (s_assign holds garbage before the first iteration)
+          if (it > 1 && now[u] != before) { s_changed[before] = 1; s_changed[now[u]] = 1; moved = 1; }
+          s_assign[i] = (unsigned short)now[u];
+        }
+      }
     }
     // No frame moved and no cluster was empty (an empty cluster is re-seeded with a fresh draw every iteration, :117-120): the
     // membership, hence every centre, is what it was -- the centre shift is exactly 0 and the reference stops here (:130).  Every
