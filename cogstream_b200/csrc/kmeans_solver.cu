@@ -796,6 +796,7 @@ struct GridInitBufs {
   int* best_i;
   int force_exact;    // profiling / test aid: always take the two-barrier exact path
   int n_cluster;      // CL: CTAs of the sampling cluster (= the first cluster of the grid); the other clusters are helpers
+  int push;           // CL: round records pushed into the peers' buffers (st.async + mbarrier) instead of barrier + remote loads
   int n_helpers;      // CL: helper CTAs that pre-generate the built-in generator's noise rows into a.noise_ws (0: none)
   int profile;        // profiling aid (CSB_INIT_PROFILE=1): thread 0 of CTA 0 sums the clock cycles of the five phases of a
                       // round and stores the per-round averages in part[0..5] (+ the round count) when the kernel ends
@@ -836,6 +837,37 @@ __device__ __forceinline__ uint4 ld_cluster_v4(const void* local_smem, unsigned 
   return v;
 }
 
+// Push exchange (the default): instead of publishing its round record locally and meeting the peers at the cluster barrier, a CTA
+// writes the record straight into every peer's receive buffer with st.async (16-byte stores from registers that count their
+// bytes on the peer's mbarrier); a peer waits on its own mbarrier (hardware sleep, wake-up on the last byte) and reads local
+// shared memory.  One one-way trip through the cluster network per round instead of barrier arrive + wait + remote loads.
+// Buffers and mbarriers alternate with the round parity: a CTA can be at most one round ahead of a peer.
+__device__ __forceinline__ void st_async_v4(const void* local_dst, const void* local_mbar, unsigned rank, uint4 v) {
+  uint32_t d = (uint32_t)__cvta_generic_to_shared(local_dst), mb = (uint32_t)__cvta_generic_to_shared(local_mbar), rd, rb;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rd) : "r"(d), "r"(rank));
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rb) : "r"(mb), "r"(rank));
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(rd), "r"(v.x), "r"(v.y),
+               "r"(v.z), "r"(v.w), "r"(rb)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_init_local(unsigned long long* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx_local(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_local(unsigned long long* bar, unsigned parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t}" ::"r"((uint32_t)__cvta_generic_to_shared(bar)),
+      "r"(parity)
+      : "memory");
+}
+
 template <bool CL, int NT, int U>
 __global__ void __launch_bounds__(NT, 1) kmeanspp_grid_kernel(SolverArgs a, GridInitBufs b) {
   constexpr int NW = NT / 32;
@@ -847,6 +879,8 @@ __global__ void __launch_bounds__(NT, 1) kmeanspp_grid_kernel(SolverArgs a, Grid
   __shared__ int s_cnt, s_c[2], s_ovf[2];
   __shared__ float s_sum[2], s_umax;
   __shared__ ClusterRound s_x[2];  // CL: this CTA's published round data, double-buffered by round parity
+  __shared__ ClusterRound s_in[2][CL ? kClusterInitMax : 1];  // CL, push exchange: the peers' round records (by round parity)
+  __shared__ __align__(8) unsigned long long s_mbar[2];         // CL, push exchange: bytes of the peers' records, by round parity
   __shared__ __align__(8) unsigned s_fb[2];  // CL, exact fallback: this CTA's best {score bits, frame} (written / read between the two barriers of a round)
   const int T = a.T, k = a.k;
   const unsigned nb = CL ? (unsigned)b.n_cluster : gridDim.x;
@@ -878,6 +912,17 @@ __global__ void __launch_bounds__(NT, 1) kmeanspp_grid_kernel(SolverArgs a, Grid
     st->iterations = 0; st->converged = 0; st->n_reseed_used = 0; st->degenerate_rounds = 0;
     st->reseed_overflow = 0; st->n_noise_used = 0; st->min_margin = __int_as_float(0x7f800000); st->last_shift = 0.f;
   }
+  const bool push = CL && b.push;
+  if (push) {
+    if (threadIdx.x == 0) {
+      mbar_init_local(&s_mbar[0], 1);
+      mbar_init_local(&s_mbar[1], 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    cluster_barrier();  // every CTA's mbarriers exist before any peer's bytes can arrive
+  }
+  unsigned n_push0 = 0u, n_push1 = 0u;  // completed uses of each mbarrier (its phase parity)
   mark(a, 1);
   // frames of this thread: base + u * NT, u < U, inside the CTA's contiguous slice
   const int per_cta = (T + (int)nb - 1) / (int)nb;
@@ -902,10 +947,11 @@ __global__ void __launch_bounds__(NT, 1) kmeanspp_grid_kernel(SolverArgs a, Grid
   int noise_row = 0, degenerate = 0, used = 0;
   const RngKey rk = load_rng(a);
   const bool prof = CL && b.profile && blockIdx.x == 0 && threadIdx.x == 0;  // (the grid form has no registers to spare)
-  long long tacc[5] = {0, 0, 0, 0, 0}, tprev = 0;
-  int trounds = 0;
+  __shared__ long long s_tacc[7];  // [0..4] phase sums, [5] previous mark, [6] rounds (shared memory: the 64-register variant has none to spare)
+  if (prof)
+    for (int i = 0; i < 7; ++i) s_tacc[i] = 0;
   auto lap = [&](int i) {
-    if (prof) { const long long t = clock64(); tacc[i] += t - tprev; tprev = t; }
+    if (prof) { const long long t = clock64(); s_tacc[i] += t - s_tacc[5]; s_tacc[5] = t; }
   };
   int c = 0;
   if (a.n_init_given == 0) {  // :41 the first centre, from the built-in generator
@@ -929,7 +975,8 @@ __global__ void __launch_bounds__(NT, 1) kmeanspp_grid_kernel(SolverArgs a, Grid
     if (m + 1 >= k) break;
     // ---- update the nearest distances with centre c; per-CTA partial of sum nearest^2 (:45-53) ----
     const bool sample_next = m + 1 >= a.n_init_given;
-    if (prof) { tprev = clock64(); ++trounds; }
+    if (prof) { s_tacc[5] = clock64(); ++s_tacc[6]; }
+    if (push && sample_next && threadIdx.x == 0) mbar_expect_tx_local(&s_mbar[m & 1], nb * (unsigned)sizeof(ClusterRound));
     // (noise row `noise_row` = the one the next round consumes if it samples)
     const double gcc = __ldg(a.G + (int64_t)c * a.ldg + c);
     const double* gc = a.G + (int64_t)c * a.ldg;
@@ -993,7 +1040,20 @@ __global__ void __launch_bounds__(NT, 1) kmeanspp_grid_kernel(SolverArgs a, Grid
         }
       }
       lap(1);  // block reduction, candidates published
-      cluster_barrier();  // every thread of every CTA: releases the writes above, acquires the peers'
+      if (push) {
+        __syncthreads();  // the record is complete
+        if (warp == 0 && lane < (int)nb) {
+          const uint4* rec = reinterpret_cast<const uint4*>(x);
+          const uint4 r0 = rec[0], r1 = rec[1], r2 = rec[2], r3 = rec[3];
+          char* dst = reinterpret_cast<char*>(&s_in[m & 1][blockIdx.x]);  // this CTA's slot in the peer's buffer (rank = blockIdx.x)
+          st_async_v4(dst, &s_mbar[m & 1], (unsigned)lane, r0);
+          st_async_v4(dst + 16, &s_mbar[m & 1], (unsigned)lane, r1);
+          st_async_v4(dst + 32, &s_mbar[m & 1], (unsigned)lane, r2);
+          st_async_v4(dst + 48, &s_mbar[m & 1], (unsigned)lane, r3);
+        }
+      } else {
+        cluster_barrier();  // every thread of every CTA: releases the writes above, acquires the peers'
+      }
     } else {
       if (lane == 0) { s_ws[warp] = part; s_wv[warp] = umax; }
       if (threadIdx.x == 0) { s_cnt = 0; }
@@ -1045,9 +1105,16 @@ __global__ void __launch_bounds__(NT, 1) kmeanspp_grid_kernel(SolverArgs a, Grid
         const unsigned q = lane + 32 * r;
         ccnt[r] = 0;
         if (CL) {
-          if (r == 0 && q < nb) {  // a cluster has <= 16 CTAs: lane q reads peer q's 64 bytes (all four loads in flight together)
-            const char* xb = reinterpret_cast<const char*>(&s_x[m & 1]);
-            const uint4 h = ld_cluster_v4(xb, q), v2 = ld_cluster_v4(xb + 16, q), vz = ld_cluster_v4(xb + 32, q), vi = ld_cluster_v4(xb + 48, q);
+          if (r == 0 && push) mbar_wait_local(&s_mbar[m & 1], ((m & 1) ? n_push1 : n_push0) & 1u);  // (warp 0, all lanes: the peers' records have landed)
+          if (r == 0 && q < nb) {  // a cluster has <= 16 CTAs: lane q takes peer q's 64 bytes
+            uint4 h, v2, vz, vi;
+            if (push) {
+              const uint4* rec = reinterpret_cast<const uint4*>(&s_in[m & 1][q]);
+              h = rec[0]; v2 = rec[1]; vz = rec[2]; vi = rec[3];
+            } else {  // remote loads after the cluster barrier (all four in flight together)
+              const char* xb = reinterpret_cast<const char*>(&s_x[m & 1]);
+              h = ld_cluster_v4(xb, q); v2 = ld_cluster_v4(xb + 16, q); vz = ld_cluster_v4(xb + 32, q); vi = ld_cluster_v4(xb + 48, q);
+            }
             v += __uint_as_float(h.x);
             ccnt[r] = (int)h.y;
             cn2[r][0] = __uint_as_float(v2.x); cn2[r][1] = __uint_as_float(v2.y); cn2[r][2] = __uint_as_float(v2.z); cn2[r][3] = __uint_as_float(v2.w);
@@ -1095,6 +1162,7 @@ __global__ void __launch_bounds__(NT, 1) kmeanspp_grid_kernel(SolverArgs a, Grid
       }
       if (lane == 0) { s_sum[rb] = v; s_ovf[rb] = ovf; s_c[rb] = gi; }
     }
+    if (m & 1) ++n_push1; else ++n_push0;
     __syncthreads();
     lap(3);  // peers read, exact scores, winner broadcast
     const float sum = s_sum[rb];
@@ -1171,9 +1239,9 @@ __global__ void __launch_bounds__(NT, 1) kmeanspp_grid_kernel(SolverArgs a, Grid
     if (!CL) __syncthreads();
     lap(4);
   }
-  if (prof && trounds > 0) {
-    for (int i = 0; i < 5; ++i) b.part[i] = (float)((double)tacc[i] / trounds);
-    b.part[5] = (float)trounds;
+  if (prof && s_tacc[6] > 0) {
+    for (int i = 0; i < 5; ++i) b.part[i] = (float)((double)s_tacc[i] / (double)s_tacc[6]);
+    b.part[5] = (float)s_tacc[6];
   }
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     st->degenerate_rounds = degenerate;
@@ -2139,6 +2207,7 @@ int csb_kmeans_solve(const double* G, const void* timestamps, const csb_kmeans_p
     gb.force_exact = getenv("CSB_INIT_EXACT") ? 1 : 0;
     gb.profile = getenv("CSB_INIT_PROFILE") ? 1 : 0;
     gb.n_cluster = 0; gb.n_helpers = 0;
+    gb.push = (getenv("CSB_INIT_PUSH") && atoi(getenv("CSB_INIT_PUSH")) == 0) ? 0 : 1;  // (0: cluster barrier + DSMEM loads, validation)
     // One thread-block cluster when the stream fits 16 CTAs (T <= 32,768): hardware cluster barrier + DSMEM exchange per round
     // instead of the software grid barrier + L2 round trip.  The cluster size is a power of two (surplus CTAs own an empty
     // slice); sizes above 8 are non-portable and taken only if the device can place such a cluster.  CSB_INIT_CLUSTER=0: off.

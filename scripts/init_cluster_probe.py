@@ -59,8 +59,10 @@ for T in sizes:
     # peers + scores + broadcast | rest
     os.environ["CSB_INIT_PROFILE"] = "1"
     off = (8 * T + 255) // 256 * 256
-    for mode, csz, blk in (("cluster", None, None), ("cluster", None, 512), ("cluster", 8, None), ("cluster", 8, 512), ("grid", None, None)):
-        os.environ["CSB_INIT_CLUSTER"] = "1" if mode == "cluster" else "0"
+    for mode, csz, blk in (("cluster", None, None), ("cluster_nopush", None, None), ("cluster", None, 512), ("cluster", 8, None),
+                           ("cluster", 8, 512), ("grid", None, None)):
+        os.environ["CSB_INIT_CLUSTER"] = "1" if mode.startswith("cluster") else "0"
+        os.environ["CSB_INIT_PUSH"] = "0" if mode.endswith("nopush") else "1"
         if csz:
             os.environ["CSB_INIT_CLUSTER_SIZE"] = str(csz)
         if blk:
@@ -75,8 +77,9 @@ for T in sizes:
         row[f"{tag}_prof_ms"] = round(ms, 4)
         os.environ.pop("CSB_INIT_CLUSTER_SIZE", None)
         os.environ.pop("CSB_INIT_CLUSTER_BLOCK", None)
-    row["same_centres_variants"] = all(bool(torch.equal(picks["grid"], picks[t])) for t in ("cluster", "cluster_b512", "cluster8", "cluster8_b512"))
+    row["same_centres_variants"] = all(bool(torch.equal(picks["grid"], picks[t])) for t in ("cluster", "cluster_nopush", "cluster_b512", "cluster8", "cluster8_b512"))
     os.environ.pop("CSB_INIT_PROFILE")
+    os.environ.pop("CSB_INIT_PUSH")
     os.environ.pop("CSB_INIT_CLUSTER")
     row["same_centres_rng"] = bool(torch.equal(picks["cluster", "rng"], picks["grid", "rng"]))
     row["same_assignments_rng"] = bool(torch.equal(picks["cluster", "rng_assign"], picks["grid", "rng_assign"]))

@@ -1053,9 +1053,11 @@ def test_kmeanspp_long_stream_grid_init(dev, monkeypatch, T, P, D, seed, ts_dtyp
     f3 = feats.view(T, P, D)
     res = {}
     # cluster (one barrier per round), single CTA, software-barrier grid, then both multi-CTA forms with the exact two-barrier fallback
-    for mode in ("1", "0", "grid", "exact", "grid-exact"):
+    # ("barrier*": the cluster kernel with the barrier + remote-load exchange instead of the st.async push)
+    for mode in ("1", "0", "grid", "barrier", "exact", "grid-exact", "barrier-exact"):
         monkeypatch.setenv("CSB_INIT_GRID", "0" if mode == "0" else "1")
         monkeypatch.setenv("CSB_INIT_CLUSTER", "0" if mode.startswith("grid") else "1")
+        monkeypatch.setenv("CSB_INIT_PUSH", "0" if mode.startswith("barrier") else "1")
         if mode.endswith("exact"):
             monkeypatch.setenv("CSB_INIT_EXACT", "1")
         else:
@@ -1065,8 +1067,9 @@ def test_kmeanspp_long_stream_grid_init(dev, monkeypatch, T, P, D, seed, ts_dtyp
         res[mode] = (info.init_indices.tolist(), assign.cpu(), info.iterations, info.n_reseed_used, info.n_noise_used)
     monkeypatch.delenv("CSB_INIT_GRID")
     monkeypatch.delenv("CSB_INIT_CLUSTER")
+    monkeypatch.delenv("CSB_INIT_PUSH")
     monkeypatch.delenv("CSB_INIT_EXACT")
-    for other in ("0", "grid", "exact", "grid-exact"):
+    for other in ("0", "grid", "barrier", "exact", "grid-exact", "barrier-exact"):
         assert res["1"][0] == res[other][0] and torch.equal(res["1"][1], res[other][1]) and res["1"][2:] == res[other][2:]
     info_o = orc.KMeansInfo()
     orig = random.randint
