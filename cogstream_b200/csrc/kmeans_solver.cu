@@ -782,7 +782,7 @@ __global__ void __launch_bounds__(kInitThreads) kmeanspp_kernel(SolverArgs a) {
 // factor of all scores.  Cooperative launch (co-residency for the software barrier).
 constexpr int kGridInitThreads = 512;
 constexpr int kGridInitU = 4;
-constexpr int kGridInitMinT = 2048;
+constexpr int kGridInitMinT = 1024;  // above the fused init of short streams: the cluster kernel beats the single-CTA kernel at every size (profiles/r2_init_midsize_probe.jsonl)
 constexpr int kGridInitCand = 4;
 
 struct GridInitBufs {
@@ -2170,7 +2170,8 @@ int csb_kmeans_solve(const double* G, const void* timestamps, const csb_kmeans_p
   const bool wide = k > 128 && k <= 1024;
   auto kern = (p->ts_dtype == CSB_F64) ? (wide ? kmeans_solver_kernel<double, true> : kmeans_solver_kernel<double, false>)
                                        : (wide ? kmeans_solver_kernel<float, true> : kmeans_solver_kernel<float, false>);
-  if (smem > 48 * 1024) {
+  // (the 48 KB default covers static + dynamic shared memory: opt in from 40 KB of dynamic, the kernels have < 1 KB of static)
+  if (smem > 40 * 1024) {
     e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { set_error("kmeans_solve: smem attr: %s", cudaGetErrorString(e)); return CSB_ERR_CUDA; }
   }
@@ -2282,7 +2283,7 @@ int csb_kmeans_solve(const double* G, const void* timestamps, const csb_kmeans_p
     else if (nt <= 512) { nt = 512; ikern = f64 ? kmeanspp_kernel<double, 512> : kmeanspp_kernel<float, 512>; }
     else { nt = 1024; ikern = f64 ? kmeanspp_kernel<double, 1024> : kmeanspp_kernel<float, 1024>; }
     const size_t ismem = sizeof(float) * T + (sp.diag_in_smem ? sizeof(double) * T : 0) + 16;
-    if (ismem > 48 * 1024) {
+    if (ismem > 40 * 1024) {  // (static + dynamic must fit the 48 KB default otherwise)
       e = cudaFuncSetAttribute(ikern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ismem);
       if (e != cudaSuccess) { set_error("kmeans_solve: init smem attr: %s", cudaGetErrorString(e)); return CSB_ERR_CUDA; }
     }
@@ -2381,7 +2382,8 @@ int csb_kmeans_lloyd_phase(const double* G, const void* timestamps, const csb_km
                                        : (wide ? lloyd_phase_kernel<float, true> : lloyd_phase_kernel<float, false>);
   const size_t smem = sp.bytes;
   cudaError_t e;
-  if (smem > 48 * 1024) {
+  // (the 48 KB default covers static + dynamic shared memory: opt in from 40 KB of dynamic, the kernels have < 1 KB of static)
+  if (smem > 40 * 1024) {
     e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { set_error("kmeans_lloyd_phase: smem attr: %s", cudaGetErrorString(e)); return CSB_ERR_CUDA; }
   }

@@ -1674,7 +1674,7 @@ int csb_relevance_select(const csb_relevance_args* p, csb_stream_t stream) {
   }
   const unsigned grid = (unsigned)(p->k + (p->k + 7) / 8);
   auto launch = [&](auto kern) -> int {
-    if (smem > 48 * 1024) {
+    if (smem > 40 * 1024) {  // (static + dynamic must fit the 48 KB default otherwise)
       cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (e != cudaSuccess) { set_error("relevance_select: smem attr: %s", cudaGetErrorString(e)); return CSB_ERR_CUDA; }
     }

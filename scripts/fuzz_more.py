@@ -49,6 +49,8 @@ for case in range(n_cases):
     seed, off = rnd.getrandbits(62), rnd.getrandbits(20)
     state = torch.tensor([seed, off], dtype=torch.int64, device=dev)
     buf = ops.KMeansBuffers(T, k, ts_dtype, dev)
+    if os.environ.get("FUZZ_VERBOSE"):
+        print(f"gen case {case}: T={T} k={k} P={P} D={D} dup={dup} heavy_dup={heavy_dup} ts={ts_dtype}", flush=True)
     ops.kmeans_solve(G, ts.to(dev), buf, n_init_given=0, exp_noise=None, reseed_pool=None, rng_state=state)
     stt = ops.decode_status(buf.status)
     first = int((int(tg._philox_host(seed, off, 0xFFFFFFFF, [0])[0, 0]) * T) >> 32)

@@ -1156,6 +1156,22 @@ def test_long_stream_S_pass_variants_agree(dev, monkeypatch, T):
     assert torch.equal(a[1], ct_o)
 
 
+def test_kmeans_shared_memory_opt_in_window(dev):
+    """T = 2100, k = 20: the solver's dynamic shared memory (48,728 bytes) plus its static shared memory crosses the 48 KB default
+    although the dynamic part alone does not -- the launcher has to opt in (found by scripts/fuzz_more.py: 'occupancy query failed')."""
+    T, P, D, k = 2100, 4, 64, 20
+    feats, _ = synthetic.make_features(T, P, D, 101)
+    f3 = feats.view(T, P, D)
+    ts = (torch.arange(T, dtype=torch.float64) / 2.0).float()
+    g = torch.Generator().manual_seed(1)
+    init = torch.randperm(T, generator=g)[:k].tolist()
+    pool = torch.randint(0, T, (256,), generator=g).tolist()
+    _, ct, assign, info = kmeans_with_time_min_max(f3.to(dev), ts.to(dev), k, init_indices=init, reseed_indices=pool, return_info=True)
+    info_o = orc.KMeansInfo()
+    _, ct_o, as_o = orc.kmeans_with_time_min_max(f3, ts, k, init_indices=init, reseed_indices=pool, info=info_o)
+    assert torch.equal(assign.cpu(), as_o) and info.iterations == info_o.iterations
+
+
 def test_scan_fallback_paths_agree(dev, monkeypatch):
     """The compaction / id-filter scans are single cooperative launches; grids beyond co-residency use the multi-launch
     "last block done" scans (forced here with CSB_NO_COOP_SCAN): identical outputs."""
