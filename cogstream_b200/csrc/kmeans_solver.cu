@@ -802,11 +802,13 @@ struct GridInitBufs {
                       // round and stores the per-round averages in part[0..5] (+ the round count) when the kernel ends
 };
 
-// CL = true: the CTAs are ONE thread-block cluster (<= 16 CTAs, T <= 32,768).  The per-round exchange goes through distributed
-// shared memory instead of global memory, and the software grid barrier (atomic + acquire poll through the L2, ~1.4 us, plus an
-// L2 round trip for the partials afterwards) becomes the hardware cluster barrier (barrier.cluster arrive.release /
-// wait.acquire, ~0.2 us) followed by four 16-byte ld.shared::cluster loads per peer.  Same arithmetic, same candidate rule,
-// same fixed summation tree: the chosen centres are those of the grid form with the same CTA count.
+// CL = true (the default for T <= 32,768): the sampling CTAs are ONE thread-block cluster (<= 16 CTAs).  The per-round exchange goes
+// through distributed shared memory instead of global memory: by default every CTA pushes its round record into the peers'
+// buffers (st.async + mbarrier, see below); with CSB_INIT_PUSH=0 -- and always in the rare exact-score fallback -- the software
+// grid barrier (atomic + acquire poll through the L2, ~1.4 us, plus an L2 round trip for the partials afterwards) becomes the
+// hardware cluster barrier (barrier.cluster arrive.release / wait.acquire) followed by four 16-byte ld.shared::cluster loads per
+// peer.  Same arithmetic, same candidate rule, same fixed summation tree: the chosen centres are those of the grid form.
+// Further clusters of the same launch (blockIdx.x >= n_cluster) are helpers: they pre-generate the built-in generator's noise.
 constexpr int kClusterInitMax = 16;
 constexpr bool kClusterInitDefault = true;   // CSB_INIT_CLUSTER=0: the cooperative grid with the software barrier (validation)
 struct __align__(16) ClusterRound {  // what a CTA publishes per sampling round: 64 bytes = four 16-byte loads for a peer

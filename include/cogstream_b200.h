@@ -137,6 +137,10 @@ CSB_API size_t csb_kmeans_workspace_bytes(int64_t T, int64_t k);
  * q ~ Exp(1) (the host draws exp_noise from the torch generator the reference would have used).
  * Noise rows are consumed one per sampling round; a round with probs_sum == 0 (:55-57) takes the next
  * reseed_pool entry instead, so both host RNG streams are consumed exactly like the reference does.
+ * Streams of more than 1024 frames take two launches: the k-means++ rounds run on one thread-block cluster (<= 16 CTAs; the round
+ * records travel through distributed shared memory; with params->rng_state further clusters of the same launch pre-generate
+ * the noise rows), then the cooperative Lloyd kernel.  min_margin is exact whenever it is below ~1e-6 (k > 128: clusters
+ * whose fp32 distance estimate is provably not the smallest are not evaluated exactly); everything else is bit-identical.
  *   G             [T,T] fp64 (csb_gram)
  *   timestamps    [T]   ts_dtype
  *   init_indices  [k]   int64; first n_init_given entries are inputs (0 allowed with params->rng_state), the rest are outputs
