@@ -4,7 +4,7 @@ import collections, os, re, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 lib = os.path.join(ROOT, "cogstream_b200", "lib", "libcogstream_b200.so")
 sass = subprocess.run(["/usr/local/cuda/bin/cuobjdump", "-sass", lib], capture_output=True, text=True).stdout
-KEYS = ["UTCHMMA", "UTCHMMA.2CTA", "UTMALDG", "UTMAPF", "UBLKCP", "LDTM", "UTCBAR", "SYNCS", "REDUX", "HMMA", "HADD2.BF16", "LDG.E.128", "STG.E.128",
+KEYS = ["UTCHMMA", "UTCHMMA.2CTA", "UTMALDG", "UTMAPF", "UBLKCP", "LDTM", "UTCBAR", "SYNCS", "STAS", "UCGABAR_ARV", "REDUX", "HMMA", "HADD2.BF16", "LDG.E.128", "STG.E.128",
         "DADD", "DFMA", "MUFU.RSQ64H", "ATOM", "RED", "BAR.SYNC", "ELECT", "ACQBULK", "CCTL", "NANOSLEEP"]
 cur = None
 counts = collections.OrderedDict()
