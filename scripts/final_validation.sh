@@ -12,3 +12,6 @@ CSB_NOEARLY=1 CSB_TIMELINE=1 timeout 300 python scripts/profile_step.py 3 > gpur
 timeout 300 python scripts/profile_step.py 3 > gpurun_out/${tag}_plain.log 2>&1 && \
   timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${tag}_launches.csv \
     python scripts/profile_step.py 3 > gpurun_out/${tag}_ncu1.log 2>&1; echo "ncu launches rc=$?"
+# randomised sweeps with seeds the test suite does not use (the shared-memory opt-in window of round 2 was found this way)
+timeout 200 python scripts/fuzz_more.py 40 5000 > gpurun_out/${tag}_fuzz_more.log 2>&1; echo "fuzz_more rc=$?"; tail -1 gpurun_out/${tag}_fuzz_more.log
+timeout 200 python scripts/fuzz_parity.py 150 7000 > gpurun_out/${tag}_fuzz_parity.log 2>&1; echo "fuzz_parity rc=$?"; tail -1 gpurun_out/${tag}_fuzz_parity.log | cut -c1-300
